@@ -1,0 +1,517 @@
+"""acu — Python host-side mirror of the arrow-rs compute API over the arrow_cuda C ABI.
+
+This is plumbing for tests and bench.py: arrays live in numpy on the host (``HostArray``,
+mirroring PrimitiveArray / BooleanArray: values buffer + LSB-first validity bitmap + bit
+offset + cached null_count) or in HBM (``DeviceArray``). ``Context`` exposes the reference's
+function names (filter, take, add, lt, cast, sum ...) and raises ``ArrowError`` with the
+reference's message text. The compute always happens in libarrow_cuda.so; nothing here
+falls back to the CPU.
+
+Reference API being mirrored: arrow/src/compute/mod.rs:20-40, arrow/src/compute/kernels.rs:20-34.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi as abi
+from ._abi import (ADD, ADD_WRAPPING, DISTINCT, DIV, EQ, F32, F64, GT, GT_EQ, I8, I16, I32, I64, LT, LT_EQ, MAX,
+                   MIN, MUL, MUL_WRAPPING, NEQ, NOT_DISTINCT, REM, SUB, SUB_WRAPPING, SUM, U8, U16, U32, U64,
+                   bitmap_bytes)
+
+BOOL = "bool"
+NP_DTYPES = [np.int8, np.int16, np.int32, np.int64, np.uint8, np.uint16, np.uint32, np.uint64, np.float32, np.float64]
+
+
+class ArrowError(Exception):
+    """Mirrors arrow_schema::ArrowError; str(e) == the reference's Display text."""
+
+    def __init__(self, status, message, index=-1, detail=None):
+        super().__init__(message)
+        self.status = status
+        self.message = message
+        self.index = index
+        self.detail = detail
+
+
+def pack_bits(bools, offset=0):
+    """LSB-first bitmap of `bools` starting at bit `offset`; padded to whole u64 words (+8 B)."""
+    bools = np.asarray(bools, dtype=bool)
+    n = len(bools) + offset
+    buf = np.zeros(bitmap_bytes(n) + 8, dtype=np.uint8)
+    if len(bools):
+        padded = np.zeros(n, dtype=bool)
+        padded[offset:] = bools
+        packed = np.packbits(padded, bitorder="little")
+        buf[: len(packed)] = packed
+    return buf
+
+
+def unpack_bits(buf, offset, n):
+    if n == 0:
+        return np.zeros(0, dtype=bool)
+    bits = np.unpackbits(np.asarray(buf, dtype=np.uint8), bitorder="little")
+    return bits[offset: offset + n].astype(bool)
+
+
+class HostArray:
+    """Primitive or boolean Arrow array in host memory (numpy)."""
+
+    def __init__(self, dtype, values, length, validity=None, validity_offset=0, values_offset=0, null_count=-1,
+                 is_scalar=False):
+        self.dtype = dtype
+        self.values = values            # np array of natives, or uint8 bitmap when dtype == BOOL
+        self.values_offset = values_offset
+        self.validity = validity        # uint8 bitmap or None
+        self.validity_offset = validity_offset
+        self.length = length
+        self.null_count = null_count
+        self.is_scalar = is_scalar
+
+    # -- constructors ------------------------------------------------------------------
+    @staticmethod
+    def from_list(dtype, items, force_validity=False, bit_offset=0, scalar=False):
+        """Build from a python list; None = null (like `Int32Array::from(vec![Some(1), None])`)."""
+        n = len(items)
+        mask = np.array([x is not None for x in items], dtype=bool)
+        if dtype == BOOL:
+            vals = pack_bits([bool(x) if x is not None else False for x in items], bit_offset)
+            voff = bit_offset
+        else:
+            npdt = NP_DTYPES[dtype]
+            vals = np.zeros(n, dtype=npdt)
+            for i, x in enumerate(items):
+                if x is not None:
+                    vals[i] = x
+            voff = 0
+        validity = None
+        nc = 0
+        if force_validity or not mask.all():
+            validity = pack_bits(mask, bit_offset)
+            nc = int(n - mask.sum())
+        return HostArray(dtype, vals, n, validity, bit_offset if validity is not None else 0, voff, nc, scalar)
+
+    @staticmethod
+    def from_numpy(dtype, values, mask=None, bit_offset=0):
+        values = np.ascontiguousarray(values, dtype=NP_DTYPES[dtype])
+        validity, nc = None, 0
+        if mask is not None:
+            mask = np.asarray(mask, dtype=bool)
+            validity = pack_bits(mask, bit_offset)
+            nc = int(len(mask) - mask.sum())
+        return HostArray(dtype, values, len(values), validity, bit_offset if validity is not None else 0, 0, nc)
+
+    @staticmethod
+    def bool_from_numpy(bools, mask=None, bit_offset=0, mask_offset=0):
+        bools = np.asarray(bools, dtype=bool)
+        validity, nc = None, 0
+        if mask is not None:
+            mask = np.asarray(mask, dtype=bool)
+            validity = pack_bits(mask, mask_offset)
+            nc = int(len(mask) - mask.sum())
+        return HostArray(BOOL, pack_bits(bools, bit_offset), len(bools), validity, mask_offset, bit_offset, nc)
+
+    def scalar(self):
+        """Wrap a 1-element array as a Datum scalar (arrow-array/src/scalar.rs:128-152)."""
+        assert self.length == 1
+        return HostArray(self.dtype, self.values, 1, self.validity, self.validity_offset, self.values_offset,
+                         self.null_count, True)
+
+    # -- views ------------------------------------------------------------------------
+    def valid_mask(self):
+        if self.validity is None:
+            return np.ones(self.length, dtype=bool)
+        return unpack_bits(self.validity, self.validity_offset, self.length)
+
+    def value_array(self):
+        if self.dtype == BOOL:
+            return unpack_bits(self.values, self.values_offset, self.length)
+        return np.asarray(self.values[: self.length])
+
+    def to_list(self):
+        vals, mask = self.value_array(), self.valid_mask()
+        return [(v.item() if m else None) for v, m in zip(vals, mask)]
+
+    def slice(self, offset, length):
+        """Array::slice — zero-copy: pointer/bit-offset arithmetic only."""
+        if self.dtype == BOOL:
+            vals, voff = self.values, self.values_offset + offset
+        else:
+            vals, voff = self.values[offset:], 0
+        nc = -1 if self.validity is not None else 0
+        return HostArray(self.dtype, vals, length, self.validity, self.validity_offset + offset if self.validity is not None else 0,
+                         voff, nc, False)
+
+    def width(self):
+        return 1 if self.dtype == BOOL else abi.DTYPE_SIZE[self.dtype]
+
+
+def _np_ptr(a):
+    return a.ctypes.data if a is not None else None
+
+
+def host_descriptor(h):
+    """acu_array pointing at numpy memory (used by the oracle wrapper in tests/)."""
+    d = abi.Array()
+    d.values = _np_ptr(h.values)
+    d.values_offset = h.values_offset
+    d.validity = _np_ptr(h.validity)
+    d.validity_offset = h.validity_offset
+    d.len = h.length
+    d.null_count = h.null_count if h.validity is not None else 0
+    d.is_scalar = 1 if h.is_scalar else 0
+    return d
+
+
+class DeviceArray:
+    """A HostArray's buffers uploaded to HBM (DeviceBuffer pair) with the same offsets."""
+
+    def __init__(self, ctx, dtype, length, d_values, values_offset, d_validity, validity_offset, null_count, is_scalar,
+                 owned):
+        self.ctx, self.dtype, self.length = ctx, dtype, length
+        self.d_values, self.values_offset = d_values, values_offset
+        self.d_validity, self.validity_offset = d_validity, validity_offset
+        self.null_count, self.is_scalar = null_count, is_scalar
+        self._owned = owned
+
+    def descriptor(self):
+        d = abi.Array()
+        d.values = self.d_values
+        d.values_offset = self.values_offset
+        d.validity = self.d_validity
+        d.validity_offset = self.validity_offset
+        d.len = self.length
+        d.null_count = self.null_count if self.d_validity else 0
+        d.is_scalar = 1 if self.is_scalar else 0
+        return d
+
+    def free(self):
+        for p in self._owned:
+            self.ctx.free(p)
+        self._owned = []
+
+
+class Context:
+    """acu_ctx wrapper: one device, one stream."""
+
+    def __init__(self, device=0):
+        self.lib = abi.load_library()
+        h = C.c_void_p()
+        st = self.lib.acu_ctx_create(device, C.byref(h))
+        if st != abi.OK:
+            raise RuntimeError(f"acu_ctx_create(device={device}) failed with status {st}: no usable CUDA device "
+                               "(arrow-cuda has no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if self.h:
+            self.lib.acu_ctx_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- errors / memory -----------------------------------------------------------------
+    def check(self, st):
+        if st != abi.OK:
+            d = self.lib.acu_last_error(self.h).contents
+            raise ArrowError(st, d.message.decode(), d.index, d)
+
+    def malloc(self, nbytes):
+        p = C.c_void_p()
+        self.check(self.lib.acu_malloc(self.h, max(int(nbytes), 1), C.byref(p)))
+        return p.value
+
+    def free(self, p):
+        if p:
+            self.check(self.lib.acu_free(self.h, p))
+
+    def h2d(self, dptr, arr):
+        arr = np.ascontiguousarray(arr)
+        self.check(self.lib.acu_memcpy_h2d(self.h, dptr, arr.ctypes.data, arr.nbytes))
+
+    def d2h(self, dptr, nbytes, dtype=np.uint8):
+        out = np.empty(max(int(nbytes), 0) // np.dtype(dtype).itemsize, dtype=dtype)
+        if out.nbytes:
+            self.check(self.lib.acu_memcpy_d2h(self.h, out.ctypes.data, dptr, out.nbytes))
+        return out
+
+    def sync(self):
+        self.check(self.lib.acu_ctx_sync(self.h))
+
+    def launch_count(self):
+        return self.lib.acu_launch_count(self.h)
+
+    def upload(self, h):
+        owned = []
+        if h.dtype == BOOL:
+            buf = np.asarray(h.values, dtype=np.uint8)
+            dv = self.malloc(buf.nbytes + 8)
+            self.h2d(dv, buf)
+        else:
+            vals = np.ascontiguousarray(h.values[: max(h.length, 1 if h.is_scalar else 0)])
+            dv = self.malloc(vals.nbytes + 16)
+            if vals.nbytes:
+                self.h2d(dv, vals)
+        owned.append(dv)
+        dn = None
+        if h.validity is not None:
+            dn = self.malloc(h.validity.nbytes + 8)
+            self.h2d(dn, h.validity)
+            owned.append(dn)
+        return DeviceArray(self, h.dtype, h.length, dv, h.values_offset, dn, h.validity_offset,
+                           h.null_count if h.validity is not None else 0, h.is_scalar, owned)
+
+    def alloc_out(self, nbytes_values, n_rows):
+        out = abi.ArrayOut()
+        out.values = self.malloc(nbytes_values + 16)
+        out.validity = self.malloc(bitmap_bytes(n_rows) + 8)
+        return out
+
+    def download_out(self, out, dtype):
+        n = out.len
+        if dtype == BOOL:
+            vals = self.d2h(out.values, bitmap_bytes(n))
+        else:
+            vals = self.d2h(out.values, n * abi.DTYPE_SIZE[dtype], NP_DTYPES[dtype])
+        validity = self.d2h(out.validity, bitmap_bytes(n)) if out.has_validity else None
+        res = HostArray(dtype, vals, n, validity, 0, 0, out.null_count if out.has_validity else 0)
+        self.free(out.values)
+        self.free(out.validity)
+        return res
+
+    def _free_out(self, out):
+        self.free(out.values)
+        self.free(out.validity)
+
+    # -- filter (arrow-select/src/filter.rs) ----------------------------------------------
+    def filter(self, values, predicate):
+        """arrow::compute::filter(values, predicate) for primitive and boolean arrays."""
+        dv, dp = self.upload(values), self.upload(predicate)
+        plan = C.c_void_p()
+        out = None
+        try:
+            pd = dp.descriptor()
+            self.check(self.lib.acu_filter_plan_create(self.h, C.byref(pd), C.byref(plan)))
+            count = self.lib.acu_filter_plan_count(plan)
+            out = self.alloc_out(count * values.width(), count)
+            vd = dv.descriptor()
+            if values.dtype == BOOL:
+                self.check(self.lib.acu_filter_boolean(self.h, plan, C.byref(vd), C.byref(out)))
+            else:
+                self.check(self.lib.acu_filter_primitive(self.h, plan, values.width(), C.byref(vd), C.byref(out)))
+            res, out = self.download_out(out, values.dtype), None
+            return res
+        finally:
+            if out is not None:
+                self._free_out(out)
+            if plan:
+                self.lib.acu_filter_plan_destroy(self.h, plan)
+            dv.free()
+            dp.free()
+
+    def filter_plan(self, predicate):
+        """FilterBuilder::new(predicate).optimize().build() -> (count, strategy)."""
+        dp = self.upload(predicate)
+        plan = C.c_void_p()
+        try:
+            pd = dp.descriptor()
+            self.check(self.lib.acu_filter_plan_create(self.h, C.byref(pd), C.byref(plan)))
+            return self.lib.acu_filter_plan_count(plan), self.lib.acu_filter_plan_strategy(plan)
+        finally:
+            if plan:
+                self.lib.acu_filter_plan_destroy(self.h, plan)
+            dp.free()
+
+    # -- take (arrow-select/src/take.rs) ----------------------------------------------------
+    def take(self, values, indices, check_bounds=False):
+        dv, di = self.upload(values), self.upload(indices)
+        out = self.alloc_out(indices.length * values.width(), indices.length)
+        try:
+            vd, idd = dv.descriptor(), di.descriptor()
+            if values.dtype == BOOL:
+                self.check(self.lib.acu_take_boolean(self.h, C.byref(vd), C.byref(idd), indices.dtype, int(check_bounds), C.byref(out)))
+            else:
+                self.check(self.lib.acu_take_primitive(self.h, values.width(), C.byref(vd), C.byref(idd), indices.dtype,
+                                                       int(check_bounds), C.byref(out)))
+            res, out = self.download_out(out, values.dtype), None
+            return res
+        finally:
+            if out is not None:
+                self._free_out(out)
+            dv.free()
+            di.free()
+
+    # -- variable width (Utf8) ---------------------------------------------------------------
+    def take_bytes(self, offsets, data, nulls_of, indices, check_bounds=False):
+        """take on a Utf8/Binary array given as (offsets np.int32/int64, data np.uint8, nulls_of HostArray
+        carrying validity/len). Returns (offsets, data, nulls HostArray)."""
+        ob = offsets.dtype.itemsize
+        d_off = self.malloc(offsets.nbytes + 16)
+        self.h2d(d_off, offsets)
+        d_data = self.malloc(data.nbytes + 16)
+        if data.nbytes:
+            self.h2d(d_data, data)
+        dn, di = self.upload(nulls_of), self.upload(indices)
+        m = indices.length
+        d_out_off = self.malloc((m + 1) * ob + 16)
+        out = self.alloc_out(0, m)
+        d_out_data = None
+        try:
+            total = C.c_int64(0)
+            nd, idd = dn.descriptor(), di.descriptor()
+            self.check(self.lib.acu_take_bytes(self.h, ob, d_off, d_data, C.byref(nd), C.byref(idd), indices.dtype,
+                                               int(check_bounds), d_out_off, None, 0, C.byref(total), C.byref(out)))
+            d_out_data = self.malloc(total.value + 16)
+            self.check(self.lib.acu_take_bytes(self.h, ob, d_off, d_data, C.byref(nd), C.byref(idd), indices.dtype,
+                                               int(check_bounds), d_out_off, d_out_data, total.value, C.byref(total), C.byref(out)))
+            o = self.d2h(d_out_off, (m + 1) * ob, offsets.dtype)
+            b = self.d2h(d_out_data, total.value)
+            validity = self.d2h(out.validity, bitmap_bytes(m)) if out.has_validity else None
+            return o, b, HostArray(U8, np.zeros(0, np.uint8), m, validity, 0, 0, out.null_count if out.has_validity else 0)
+        finally:
+            self._free_out(out)
+            for p in (d_off, d_data, d_out_off, d_out_data):
+                self.free(p)
+            dn.free()
+            di.free()
+
+    def filter_bytes(self, offsets, data, nulls_of, predicate):
+        ob = offsets.dtype.itemsize
+        d_off = self.malloc(offsets.nbytes + 16)
+        self.h2d(d_off, offsets)
+        d_data = self.malloc(data.nbytes + 16)
+        if data.nbytes:
+            self.h2d(d_data, data)
+        dn, dp = self.upload(nulls_of), self.upload(predicate)
+        plan = C.c_void_p()
+        d_out_off = d_out_data = None
+        out = None
+        try:
+            pd = dp.descriptor()
+            self.check(self.lib.acu_filter_plan_create(self.h, C.byref(pd), C.byref(plan)))
+            count = self.lib.acu_filter_plan_count(plan)
+            d_out_off = self.malloc((count + 1) * ob + 16)
+            out = self.alloc_out(0, count)
+            total = C.c_int64(0)
+            nd = dn.descriptor()
+            self.check(self.lib.acu_filter_bytes(self.h, plan, ob, d_off, d_data, C.byref(nd), d_out_off, None, 0,
+                                                 C.byref(total), C.byref(out)))
+            d_out_data = self.malloc(total.value + 16)
+            self.check(self.lib.acu_filter_bytes(self.h, plan, ob, d_off, d_data, C.byref(nd), d_out_off, d_out_data,
+                                                 total.value, C.byref(total), C.byref(out)))
+            o = self.d2h(d_out_off, (count + 1) * ob, offsets.dtype)
+            b = self.d2h(d_out_data, total.value)
+            validity = self.d2h(out.validity, bitmap_bytes(count)) if out.has_validity else None
+            return o, b, HostArray(U8, np.zeros(0, np.uint8), count, validity, 0, 0, out.null_count if out.has_validity else 0)
+        finally:
+            if out is not None:
+                self._free_out(out)
+            if plan:
+                self.lib.acu_filter_plan_destroy(self.h, plan)
+            for p in (d_off, d_data, d_out_off, d_out_data):
+                self.free(p)
+            dn.free()
+            dp.free()
+
+    # -- numeric (arrow-arith/src/numeric.rs) -----------------------------------------------
+    def arith(self, op, a, b):
+        assert a.dtype == b.dtype
+        n = b.length if a.is_scalar and not b.is_scalar else a.length
+        da, db = self.upload(a), self.upload(b)
+        out = self.alloc_out(n * a.width(), n)
+        try:
+            ad, bd = da.descriptor(), db.descriptor()
+            self.check(self.lib.acu_arith(self.h, a.dtype, op, C.byref(ad), C.byref(bd), C.byref(out)))
+            res, out = self.download_out(out, a.dtype), None
+            return res
+        finally:
+            if out is not None:
+                self._free_out(out)
+            da.free()
+            db.free()
+
+    def add(self, a, b): return self.arith(ADD, a, b)
+    def add_wrapping(self, a, b): return self.arith(ADD_WRAPPING, a, b)
+    def sub(self, a, b): return self.arith(SUB, a, b)
+    def sub_wrapping(self, a, b): return self.arith(SUB_WRAPPING, a, b)
+    def mul(self, a, b): return self.arith(MUL, a, b)
+    def mul_wrapping(self, a, b): return self.arith(MUL_WRAPPING, a, b)
+    def div(self, a, b): return self.arith(DIV, a, b)
+    def rem(self, a, b): return self.arith(REM, a, b)
+
+    def neg(self, a, checked=True):
+        da = self.upload(a)
+        out = self.alloc_out(a.length * a.width(), a.length)
+        try:
+            ad = da.descriptor()
+            self.check(self.lib.acu_neg(self.h, a.dtype, int(checked), C.byref(ad), C.byref(out)))
+            res, out = self.download_out(out, a.dtype), None
+            return res
+        finally:
+            if out is not None:
+                self._free_out(out)
+            da.free()
+
+    def neg_wrapping(self, a): return self.neg(a, checked=False)
+
+    # -- cmp (arrow-ord/src/cmp.rs) -----------------------------------------------------------
+    def cmp(self, op, a, b):
+        assert a.dtype == b.dtype
+        n = b.length if a.is_scalar else a.length
+        da, db = self.upload(a), self.upload(b)
+        out = self.alloc_out(bitmap_bytes(n), n)
+        try:
+            ad, bd = da.descriptor(), db.descriptor()
+            self.check(self.lib.acu_cmp(self.h, a.dtype, op, C.byref(ad), C.byref(bd), C.byref(out)))
+            res, out = self.download_out(out, BOOL), None
+            return res
+        finally:
+            if out is not None:
+                self._free_out(out)
+            da.free()
+            db.free()
+
+    def eq(self, a, b): return self.cmp(EQ, a, b)
+    def neq(self, a, b): return self.cmp(NEQ, a, b)
+    def lt(self, a, b): return self.cmp(LT, a, b)
+    def lt_eq(self, a, b): return self.cmp(LT_EQ, a, b)
+    def gt(self, a, b): return self.cmp(GT, a, b)
+    def gt_eq(self, a, b): return self.cmp(GT_EQ, a, b)
+    def distinct(self, a, b): return self.cmp(DISTINCT, a, b)
+    def not_distinct(self, a, b): return self.cmp(NOT_DISTINCT, a, b)
+
+    # -- cast (arrow-cast/src/cast/mod.rs) -----------------------------------------------------
+    def cast(self, a, to_dtype, safe=True):
+        da = self.upload(a)
+        out = self.alloc_out(a.length * abi.DTYPE_SIZE[to_dtype], a.length)
+        try:
+            ad = da.descriptor()
+            self.check(self.lib.acu_cast_numeric(self.h, a.dtype, to_dtype, int(safe), C.byref(ad), C.byref(out)))
+            res, out = self.download_out(out, to_dtype), None
+            return res
+        finally:
+            if out is not None:
+                self._free_out(out)
+            da.free()
+
+    # -- aggregate (arrow-arith/src/aggregate.rs) ----------------------------------------------
+    def aggregate(self, op, a):
+        da = self.upload(a)
+        try:
+            bits, cnt = C.c_uint64(0), C.c_int64(0)
+            ad = da.descriptor()
+            self.check(self.lib.acu_aggregate(self.h, a.dtype, op, C.byref(ad), C.byref(bits), C.byref(cnt)))
+            if cnt.value == 0:
+                return None
+            return np.array([bits.value], dtype=np.uint64).view(NP_DTYPES[a.dtype])[0].item() if abi.DTYPE_SIZE[a.dtype] == 8 \
+                else np.array([bits.value], dtype=np.uint64).view(np.uint8)[: abi.DTYPE_SIZE[a.dtype]].view(NP_DTYPES[a.dtype])[0].item()
+        finally:
+            da.free()
+
+    def sum(self, a): return self.aggregate(SUM, a)
+    def min(self, a): return self.aggregate(MIN, a)
+    def max(self, a): return self.aggregate(MAX, a)

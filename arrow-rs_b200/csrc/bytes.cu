@@ -1,0 +1,291 @@
+// bytes.cu — variable-width (Utf8 / Binary, i32 or i64 offsets) filter and take.
+//
+//   take_bytes   (arrow-select/src/take.rs:499-627)  — also Dictionary<K,Utf8> -> Utf8 cast,
+//                which the reference implements as take(dict_values, keys)
+//                (arrow-cast/src/cast/dictionary.rs:310-317)
+//   filter_bytes (arrow-select/src/filter.rs:893-928)
+//
+// Design: lengths -> device-wide inclusive scan -> byte copy.
+//   1. nulls first (take_nulls / filter_nulls), exactly like the reference;
+//   2. len[j] = offsets[idx+1]-offsets[idx] for valid output slots, 0 for null slots
+//      (take.rs:556-583; filter copies null slots too, filter.rs:891-892);
+//   3. three-level decoupled scan over int64 lengths (4096 elements per CTA) gives the new
+//      offsets; i32 overflow reports the first running total above i32::MAX (take.rs:520-523);
+//   4. copy: one warp per 32 rows, each lane streams its row's bytes.
+#include <stdio.h>
+
+#include "bitmap.cuh"
+#include "internal.cuh"
+
+#define SCAN_ELEMS 4096
+#define PLAN_TILE_WORDS 64
+#define PLAN_SCAN_CHUNK 4096
+
+namespace {
+
+__device__ __forceinline__ int64_t ld_off(const void *offs, int ob, int64_t i) {
+  return ob == 4 ? (int64_t)__ldg(static_cast<const int32_t *>(offs) + i) : __ldg(static_cast<const int64_t *>(offs) + i);
+}
+
+template <int IT> struct IdxRaw;
+template <> struct IdxRaw<0> { using t = uint8_t; };
+template <> struct IdxRaw<1> { using t = int8_t; };
+template <> struct IdxRaw<2> { using t = uint16_t; };
+template <> struct IdxRaw<3> { using t = int16_t; };
+template <> struct IdxRaw<4> { using t = uint32_t; };
+template <> struct IdxRaw<5> { using t = uint64_t; };
+__device__ __forceinline__ uint64_t ld_index(const void *idx, int kind, int64_t j) {
+  switch (kind) {
+    case 0: return __ldg(static_cast<const uint8_t *>(idx) + j);
+    case 1: return (uint64_t)(uint32_t)(int32_t)__ldg(static_cast<const int8_t *>(idx) + j);
+    case 2: return __ldg(static_cast<const uint16_t *>(idx) + j);
+    case 3: return (uint64_t)(uint32_t)(int32_t)__ldg(static_cast<const int16_t *>(idx) + j);
+    case 4: return __ldg(static_cast<const uint32_t *>(idx) + j);
+    default: return __ldg(static_cast<const uint64_t *>(idx) + j);
+  }
+}
+
+// len[j] of the j-th output slot
+__global__ void __launch_bounds__(256) k_lengths(const void *offs, int ob, const void *idx, int kind, int64_t m,
+                                                 const uint8_t *out_valid /* bit offset 0 or NULL */,
+                                                 int64_t *__restrict__ len) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
+    int64_t l = 0;
+    if (!out_valid || ld_bit(out_valid, j)) {
+      const int64_t i = (int64_t)ld_index(idx, kind, j);
+      l = ld_off(offs, ob, i + 1) - ld_off(offs, ob, i);
+    }
+    len[j] = l;
+  }
+}
+
+// ---- device-wide inclusive scan of int64 (in place) ------------------------------------
+__global__ void __launch_bounds__(1024) k_scan_block(int64_t *__restrict__ data, int64_t n, int64_t *__restrict__ block_tot) {
+  __shared__ int64_t warp_tot[32];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_ELEMS + (int64_t)threadIdx.x * 4;
+  int64_t c[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) c[k] = (base + k < n) ? data[base + k] : 0;
+  c[1] += c[0]; c[2] += c[1]; c[3] += c[2];
+  int64_t incl = c[3];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int64_t y = __shfl_up_sync(ACU_FULL_MASK, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) warp_tot[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int64_t w = warp_tot[lane], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int64_t y = __shfl_up_sync(ACU_FULL_MASK, wi, o);
+      if (lane >= o) wi += y;
+    }
+    warp_tot[lane] = wi - w;
+    if (lane == 31 && block_tot) block_tot[blockIdx.x] = wi;
+  }
+  __syncthreads();
+  const int64_t excl = warp_tot[wid] + incl - c[3];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (base + k < n) data[base + k] = excl + c[k];
+}
+
+__global__ void __launch_bounds__(1024) k_scan_add(int64_t *__restrict__ data, int64_t n, const int64_t *__restrict__ block_incl) {
+  if (blockIdx.x == 0) return;
+  const int64_t add = block_incl[blockIdx.x - 1];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_ELEMS + (int64_t)threadIdx.x * 4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (base + k < n) data[base + k] += add;
+}
+
+acu_status scan_inclusive(acu_ctx *ctx, int64_t *data, int64_t n, int64_t *tmp /* >= blocks + blocks/4096 + 2 */) {
+  if (n <= 0) return ACU_OK;
+  const int64_t blocks = (n + SCAN_ELEMS - 1) / SCAN_ELEMS;
+  ACU_LAUNCH(ctx, k_scan_block, (unsigned)blocks, 1024, 0, data, n, blocks > 1 ? tmp : nullptr);
+  if (blocks > 1) {
+    ACU_TRY(scan_inclusive(ctx, tmp, blocks, tmp + blocks));
+    ACU_LAUNCH(ctx, k_scan_add, (unsigned)blocks, 1024, 0, data, n, tmp);
+  }
+  return ACU_OK;
+}
+
+// offsets[0] = 0, offsets[j+1] = incl[j]; records the first j whose running total exceeds `limit`
+__global__ void __launch_bounds__(256) k_write_offsets(const int64_t *__restrict__ incl, int64_t m, void *out_offs, int ob,
+                                                       int64_t limit, unsigned long long *res) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  unsigned long long err = ~0ull;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
+    const int64_t v = incl[j];
+    if (v > limit && (unsigned long long)j < err) err = (unsigned long long)j;
+    if (ob == 4) static_cast<int32_t *>(out_offs)[j + 1] = (int32_t)v;
+    else static_cast<int64_t *>(out_offs)[j + 1] = v;
+    if (j == 0) { if (ob == 4) static_cast<int32_t *>(out_offs)[0] = 0; else static_cast<int64_t *>(out_offs)[0] = 0; }
+  }
+  if (err != ~0ull) atomicMin(res + RES_ERR_INDEX, err);
+}
+
+// One lane per output row; a warp's 32 rows are adjacent in the destination.
+__global__ void __launch_bounds__(256) k_copy_bytes(const void *offs, int ob, const uint8_t *__restrict__ data, const void *idx,
+                                                    int kind, int64_t m, const int64_t *__restrict__ incl,
+                                                    uint8_t *__restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
+    const int64_t end = incl[j];
+    const int64_t beg = j ? incl[j - 1] : 0;
+    const int64_t l = end - beg;
+    if (l <= 0) continue;
+    const int64_t i = (int64_t)ld_index(idx, kind, j);
+    const uint8_t *s = data + ld_off(offs, ob, i);
+    uint8_t *d = out + beg;
+    for (int64_t k = 0; k < l; ++k) d[k] = __ldg(s + k);
+  }
+}
+
+// Indices(Vec<usize>) of FilterBuilder::optimize (filter.rs:285-298): selected row ids, u64.
+__global__ void __launch_bounds__(256) k_plan_indices(const uint64_t *__restrict__ mask, const uint32_t *__restrict__ tile_local,
+                                                      const uint32_t *__restrict__ tile_count,
+                                                      const uint64_t *__restrict__ chunk_offset, int64_t n_tiles,
+                                                      uint64_t *__restrict__ out_idx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t t = warp; t < n_tiles; t += nwarps) {
+    if (tile_count[t] == 0) continue;
+    const uint64_t out0 = chunk_offset[t / PLAN_SCAN_CHUNK] + tile_local[t];
+    const uint64_t m0 = mask[t * PLAN_TILE_WORDS + 2 * lane], m1 = mask[t * PLAN_TILE_WORDS + 2 * lane + 1];
+    const uint32_t c0 = __popcll(m0), c1 = __popcll(m1);
+    uint32_t incl = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(ACU_FULL_MASK, incl, o);
+      if (lane >= o) incl += y;
+    }
+    uint64_t k = out0 + incl - (c0 + c1);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint64_t m = h ? m1 : m0;
+      const uint64_t row = (uint64_t)(t * PLAN_TILE_WORDS + 2 * lane + h) << 6;
+      while (m) {
+        const int b = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        out_idx[k++] = row + b;
+      }
+    }
+  }
+}
+
+int index_kind(acu_dtype t) {
+  switch (t) {
+    case ACU_U8: return 0; case ACU_I8: return 1; case ACU_U16: return 2; case ACU_I16: return 3;
+    case ACU_U32: case ACU_I32: return 4; case ACU_U64: case ACU_I64: return 5;
+    default: return -1;
+  }
+}
+
+// lengths -> scan -> offsets (+ optional byte copy). `idx`/`kind` address the source rows.
+acu_status gather_bytes(acu_ctx *ctx, int32_t ob, const void *offsets, const uint8_t *data, const void *idx, int kind,
+                        int64_t m, const uint8_t *out_valid, void *out_offsets, uint8_t *out_data,
+                        int64_t out_cap, int64_t *out_len) {
+  const int64_t blocks = (m + SCAN_ELEMS - 1) / SCAN_ELEMS;
+  void *scratch;
+  ACU_TRY(acu_scratch(ctx, (size_t)(m + blocks + blocks / SCAN_ELEMS + 4096) * 8, &scratch));
+  int64_t *len = static_cast<int64_t *>(scratch);
+  const int grid = acu_grid(ctx, (m + 255) / 256, 8);
+  ACU_LAUNCH(ctx, k_lengths, grid, 256, 0, offsets, (int)ob, idx, kind, m, out_valid, len);
+  ACU_TRY(scan_inclusive(ctx, len, m, len + m));
+  ACU_TRY(acu_res_reset(ctx));
+  const int64_t limit = ob == 4 ? (int64_t)INT32_MAX : INT64_MAX;
+  ACU_LAUNCH(ctx, k_write_offsets, grid, 256, 0, len, m, out_offsets, (int)ob, limit, ctx->d_res);
+  ACU_CUDA(ctx, cudaMemcpyAsync(ctx->d_res + RES_AUX0, len + (m - 1), 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  ACU_TRY(acu_res_fetch(ctx));
+  if (ctx->h_res[RES_ERR_INDEX] != ~0ull) {
+    const int64_t j = (int64_t)ctx->h_res[RES_ERR_INDEX];
+    int64_t cap = 0;
+    ACU_CUDA(ctx, cudaMemcpyAsync(&cap, len + j, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return acu_fail(ctx, ACU_ERR_OFFSET_OVERFLOW, j, 0, 0, (uint64_t)cap, "%lld", (long long)cap);
+  }
+  *out_len = (int64_t)ctx->h_res[RES_AUX0];
+  if (out_data && *out_len > 0) {
+    if (*out_len > out_cap)
+      return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, (uint64_t)*out_len,
+                      "output data capacity %lld < required %lld", (long long)out_cap, (long long)*out_len);
+    ACU_LAUNCH(ctx, k_copy_bytes, grid, 256, 0, offsets, (int)ob, data, idx, kind, m, len, out_data);
+    ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return ACU_OK;
+}
+
+acu_status zero_first_offset(acu_ctx *ctx, void *out_offsets, int ob) {
+  ACU_CUDA(ctx, cudaMemsetAsync(out_offsets, 0, (size_t)ob, ctx->stream));
+  ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ACU_OK;
+}
+
+}  // namespace
+
+extern "C" acu_status acu_take_bytes(acu_ctx *ctx, int32_t offset_bytes, const void *offsets, const uint8_t *data,
+                                     const acu_array *nulls_of, const acu_array *indices, acu_dtype index_dtype,
+                                     int32_t check_bounds, void *out_offsets, uint8_t *out_data,
+                                     int64_t out_data_capacity, int64_t *out_data_len, acu_array_out *out_nulls) {
+  *out_data_len = 0;
+  if (offset_bytes != 4 && offset_bytes != 8)
+    return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "offset width must be 4 or 8");
+  // take_nulls + bounds handling (elem_bytes = 0: no value gather)
+  ACU_TRY(acu_take_common(ctx, 0, nulls_of, false, indices, index_dtype, check_bounds, out_nulls));
+  const int64_t m = indices->len;
+  if (m == 0) return zero_first_offset(ctx, out_offsets, offset_bytes);
+  const uint8_t *ov = (out_nulls->has_validity && out_nulls->null_count > 0) ? out_nulls->validity : nullptr;
+  return gather_bytes(ctx, offset_bytes, offsets, data, indices->values, index_kind(index_dtype), m, ov, out_offsets,
+                      out_data, out_data_capacity, out_data_len);
+}
+
+extern "C" acu_status acu_filter_bytes(acu_ctx *ctx, const acu_filter_plan *plan, int32_t offset_bytes,
+                                       const void *offsets, const uint8_t *data, const acu_array *nulls_of,
+                                       void *out_offsets, uint8_t *out_data, int64_t out_data_capacity,
+                                       int64_t *out_data_len, acu_array_out *out_nulls) {
+  *out_data_len = 0;
+  if (offset_bytes != 4 && offset_bytes != 8)
+    return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "offset width must be 4 or 8");
+  const int64_t plen = acu_filter_plan_len(plan), count = acu_filter_plan_count(plan);
+  if (plen > nulls_of->len)
+    return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, (uint64_t)nulls_of->len,
+                    "Filter predicate of length %lld is larger than target array of length %lld", (long long)plen,
+                    (long long)nulls_of->len);
+  out_nulls->len = count;
+  out_nulls->has_validity = 0;
+  out_nulls->null_count = 0;
+  if (count == 0) return zero_first_offset(ctx, out_offsets, offset_bytes);
+  // selected row ids (the reference's `Indices` strategy), then the same gather as take
+  void *idx_mem = nullptr;
+  ACU_TRY(acu_malloc(ctx, (size_t)count * 8, &idx_mem));
+  acu_status st = ACU_OK;
+  do {
+    const int64_t n_tiles = acu_plan_n_tiles(plan);
+    k_plan_indices<<<acu_grid(ctx, (n_tiles + 7) / 8, 8), 256, 0, ctx->stream>>>(
+        acu_plan_mask(plan), acu_plan_tile_local(plan), acu_plan_tile_count(plan), acu_plan_chunk_offset(plan), n_tiles,
+        static_cast<uint64_t *>(idx_mem));
+    ctx->launches++;
+    if (acu_filter_plan_strategy(plan) == ACU_FILTER_ALL) {  // values.slice(0, count)
+      out_nulls->has_validity = nulls_of->validity != nullptr;
+      if (nulls_of->validity) {
+        if ((st = acu_res_reset(ctx)) != ACU_OK) break;
+        if ((st = acu_bitmap_and_launch(ctx, nulls_of->validity, nulls_of->validity_offset, nullptr, 0, count,
+                                        reinterpret_cast<uint64_t *>(out_nulls->validity), true)) != ACU_OK) break;
+        if ((st = acu_res_fetch(ctx)) != ACU_OK) break;
+        out_nulls->null_count = count - (int64_t)ctx->h_res[RES_COUNT];
+      }
+    } else {
+      if ((st = acu_filter_nulls_internal(ctx, plan, nulls_of, out_nulls)) != ACU_OK) break;
+    }
+    st = gather_bytes(ctx, offset_bytes, offsets, data, idx_mem, 5, count, nullptr, out_offsets, out_data,
+                      out_data_capacity, out_data_len);
+  } while (0);
+  acu_status st2 = acu_free(ctx, idx_mem);
+  return st != ACU_OK ? st : st2;
+}

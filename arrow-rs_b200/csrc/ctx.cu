@@ -1,0 +1,264 @@
+// ctx.cu — acu_ctx (device + stream + scratch), DeviceBuffer allocation, copies, timing,
+// error detail, synthetic input generators. Boundary: include/arrow_cuda.h.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <new>
+
+#include "common.cuh"
+
+acu_status acu_fail(acu_ctx *ctx, acu_status st, int64_t index, uint64_t lhs, uint64_t rhs,
+                    uint64_t len, const char *fmt, ...) {
+  acu_error_detail &e = ctx->err;
+  e.status = st;
+  e.cuda_error = 0;
+  e.index = index;
+  e.lhs_bits = lhs;
+  e.rhs_bits = rhs;
+  e.len = len;
+  // message = Display of the ArrowError variant (arrow-schema/src/error.rs:96-137)
+  const char *prefix = "";
+  switch (st) {
+    case ACU_ERR_INVALID_ARGUMENT: prefix = "Invalid argument error: "; break;
+    case ACU_ERR_COMPUTE: prefix = "Compute error: "; break;
+    case ACU_ERR_ARITHMETIC_OVERFLOW: prefix = "Arithmetic overflow: "; break;
+    case ACU_ERR_OFFSET_OVERFLOW: prefix = "Offset overflow error: "; break;
+    case ACU_ERR_CAST: prefix = "Cast error: "; break;
+    case ACU_ERR_NOT_YET_IMPLEMENTED: prefix = "Not yet implemented: "; break;
+    default: break;
+  }
+  size_t n = strlen(prefix);
+  memcpy(e.message, prefix, n);
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(e.message + n, sizeof(e.message) - n, fmt, ap);
+  va_end(ap);
+  return st;
+}
+
+acu_status acu_cuda_fail(acu_ctx *ctx, cudaError_t e, const char *what) {
+  acu_status st = (e == cudaErrorMemoryAllocation) ? ACU_ERR_OUT_OF_MEMORY : ACU_ERR_CUDA;
+  acu_fail(ctx, st, -1, 0, 0, 0, "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  ctx->err.cuda_error = (int32_t)e;
+  cudaGetLastError();  // clear sticky-less errors
+  return st;
+}
+
+acu_status acu_scratch(acu_ctx *ctx, size_t bytes, void **out) {
+  if (bytes > ctx->scratch_bytes) {
+    size_t want = (bytes + (1u << 20)) & ~(size_t)((1u << 20) - 1);
+    if (ctx->d_scratch) {
+      ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      ACU_CUDA(ctx, cudaFree(ctx->d_scratch));
+      ctx->d_scratch = nullptr;
+      ctx->scratch_bytes = 0;
+    }
+    ACU_CUDA(ctx, cudaMalloc(&ctx->d_scratch, want));
+    ctx->scratch_bytes = want;
+  }
+  *out = ctx->d_scratch;
+  return ACU_OK;
+}
+
+__global__ void k_res_reset(unsigned long long *res) {
+  int i = threadIdx.x;
+  if (i < RES_SLOTS) res[i] = (i == RES_ERR_INDEX) ? ~0ull : 0ull;
+}
+
+acu_status acu_res_reset(acu_ctx *ctx) {
+  ACU_LAUNCH(ctx, k_res_reset, 1, 32, 0, ctx->d_res);
+  return ACU_OK;
+}
+
+acu_status acu_res_fetch(acu_ctx *ctx) {
+  ACU_CUDA(ctx, cudaMemcpyAsync(ctx->h_res, ctx->d_res, RES_SLOTS * sizeof(unsigned long long),
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ACU_OK;
+}
+
+extern "C" {
+
+int32_t acu_abi_version(void) { return ACU_ABI_VERSION; }
+
+acu_status acu_ctx_create(int32_t device, acu_ctx **out) {
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || device < 0 || device >= count) return ACU_ERR_CUDA;  // no CPU fallback
+  if (cudaSetDevice(device) != cudaSuccess) return ACU_ERR_CUDA;
+  acu_ctx *ctx = new (std::nothrow) acu_ctx();
+  if (!ctx) return ACU_ERR_OUT_OF_MEMORY;
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return ACU_ERR_CUDA; }
+  ctx->sm_count = prop.multiProcessorCount;
+  bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreate(&ctx->ev_start) == cudaSuccess &&
+            cudaEventCreate(&ctx->ev_stop) == cudaSuccess &&
+            cudaMalloc(&ctx->d_res, RES_SLOTS * sizeof(unsigned long long)) == cudaSuccess &&
+            cudaHostAlloc(&ctx->h_res, RES_SLOTS * sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
+  if (!ok) { acu_ctx_destroy(ctx); return ACU_ERR_CUDA; }
+  // keep freed blocks in the stream-ordered pool (no OS round trip between calls)
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  ctx->err.status = ACU_OK;
+  ctx->err.index = -1;
+  *out = ctx;
+  return ACU_OK;
+}
+
+acu_status acu_comm_destroy(acu_ctx *ctx);
+
+void acu_ctx_destroy(acu_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->nccl_comm) acu_comm_destroy(ctx);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (auto &kv : ctx->allocs) cudaFree(kv.first);
+  if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  if (ctx->d_res) cudaFree(ctx->d_res);
+  if (ctx->h_res) cudaFreeHost(ctx->h_res);
+  if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+  if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+acu_status acu_ctx_sync(acu_ctx *ctx) {
+  ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ACU_OK;
+}
+
+const acu_error_detail *acu_last_error(const acu_ctx *ctx) { return &ctx->err; }
+int64_t acu_launch_count(const acu_ctx *ctx) { return ctx->launches; }
+int32_t acu_device_sm_count(const acu_ctx *ctx) { return ctx->sm_count; }
+int64_t acu_bytes_allocated(const acu_ctx *ctx) { return ctx->bytes_allocated; }
+
+acu_status acu_malloc(acu_ctx *ctx, size_t bytes, void **out) {
+  *out = nullptr;
+  size_t rounded = (bytes + 255) & ~(size_t)255;
+  if (rounded == 0) rounded = 256;
+  void *p = nullptr;
+  ACU_CUDA(ctx, cudaSetDevice(ctx->device));
+  ACU_CUDA(ctx, cudaMallocAsync(&p, rounded, ctx->stream));
+  ctx->allocs[p] = rounded;
+  ctx->bytes_allocated += (int64_t)rounded;
+  *out = p;
+  return ACU_OK;
+}
+
+acu_status acu_free(acu_ctx *ctx, void *dptr) {
+  if (!dptr) return ACU_OK;
+  auto it = ctx->allocs.find(dptr);
+  if (it == ctx->allocs.end())
+    return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "acu_free: pointer not owned by this ctx");
+  ctx->bytes_allocated -= (int64_t)it->second;
+  ctx->allocs.erase(it);
+  ACU_CUDA(ctx, cudaFreeAsync(dptr, ctx->stream));
+  return ACU_OK;
+}
+
+acu_status acu_memset(acu_ctx *ctx, void *dptr, int32_t byte, size_t bytes) {
+  if (bytes) ACU_CUDA(ctx, cudaMemsetAsync(dptr, byte, bytes, ctx->stream));
+  return ACU_OK;
+}
+
+acu_status acu_memcpy_h2d(acu_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  if (bytes) ACU_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ACU_OK;
+}
+acu_status acu_memcpy_d2h(acu_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  if (bytes) ACU_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ACU_OK;
+}
+acu_status acu_memcpy_d2d(acu_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  if (bytes) ACU_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return ACU_OK;
+}
+acu_status acu_memcpy_h2d_async(acu_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  if (bytes) ACU_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return ACU_OK;
+}
+acu_status acu_memcpy_d2h_async(acu_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  if (bytes) ACU_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return ACU_OK;
+}
+acu_status acu_host_alloc(acu_ctx *ctx, size_t bytes, void **out) {
+  ACU_CUDA(ctx, cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return ACU_OK;
+}
+acu_status acu_host_free(acu_ctx *ctx, void *host) {
+  if (host) ACU_CUDA(ctx, cudaFreeHost(host));
+  return ACU_OK;
+}
+
+acu_status acu_timer_start(acu_ctx *ctx) {
+  ACU_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+  return ACU_OK;
+}
+acu_status acu_timer_stop(acu_ctx *ctx, float *out_ms) {
+  ACU_CUDA(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
+  ACU_CUDA(ctx, cudaEventSynchronize(ctx->ev_stop));
+  ACU_CUDA(ctx, cudaEventElapsedTime(out_ms, ctx->ev_start, ctx->ev_stop));
+  return ACU_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// Synthetic inputs; host twin: oracle/oracle.cpp orc_generate_*
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_generate_values(int kind, uint64_t seed, int64_t first_row,
+                                                         uint64_t param, void *out, int64_t n) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    uint64_t r = splitmix64(seed ^ (uint64_t)(first_row + i));
+    switch (kind) {
+      case 0: static_cast<uint64_t *>(out)[i] = r; break;
+      case 1: static_cast<int64_t *>(out)[i] = (int64_t)(r >> 2) - ((int64_t)1 << 61); break;
+      case 2: static_cast<double *>(out)[i] = __dadd_rn(__dmul_rn((double)(r >> 11), 2.0e6 / 9007199254740992.0), -1.0e6); break;
+      case 3: static_cast<uint32_t *>(out)[i] = (uint32_t)__umul64hi(r, param); break;
+      default: static_cast<int32_t *>(out)[i] = (int32_t)__umul64hi(r, param); break;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_generate_bits(uint64_t seed, int64_t first_row, uint64_t thr,
+                                                       int all, uint64_t *out, int64_t n) {
+  // one thread per output byte-lane: warp ballot packs 32 rows at a time
+  int64_t words = (n + 63) / 64;
+  int lane = threadIdx.x & 31;
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = warp; w < words; w += nwarps) {
+    int64_t i0 = w * 64 + lane, i1 = i0 + 32;
+    bool b0 = i0 < n && (all || splitmix64(seed ^ (uint64_t)(first_row + i0)) < thr);
+    bool b1 = i1 < n && (all || splitmix64(seed ^ (uint64_t)(first_row + i1)) < thr);
+    uint32_t lo = __ballot_sync(ACU_FULL_MASK, b0), hi = __ballot_sync(ACU_FULL_MASK, b1);
+    if (lane == 0) out[w] = (uint64_t)lo | ((uint64_t)hi << 32);
+  }
+}
+
+extern "C" acu_status acu_generate_values(acu_ctx *ctx, int32_t kind, uint64_t seed, int64_t first_row,
+                                          uint64_t param, void *out, int64_t n) {
+  if (kind < 0 || kind > 4) return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "unknown generator kind %d", kind);
+  if (n <= 0) return ACU_OK;
+  ACU_LAUNCH(ctx, k_generate_values, acu_grid(ctx, (n + 255) / 256, 16), 256, 0, kind, seed, first_row, param, out, n);
+  return ACU_OK;
+}
+
+extern "C" acu_status acu_generate_bits(acu_ctx *ctx, uint64_t seed, int64_t first_row, double p,
+                                        uint8_t *out_bits, int64_t n) {
+  if (n <= 0) return ACU_OK;
+  uint64_t thr = p >= 1.0 ? ~0ull : (uint64_t)(p * 18446744073709551616.0);
+  int64_t words = (n + 63) / 64;
+  ACU_LAUNCH(ctx, k_generate_bits, acu_grid(ctx, (words + 7) / 8, 16), 256, 0, seed, first_row, thr,
+             p >= 1.0 ? 1 : 0, reinterpret_cast<uint64_t *>(out_bits), n);
+  return ACU_OK;
+}

@@ -1,0 +1,199 @@
+// reduce.cu — arrow-arith/src/aggregate.rs sum / min / max on the device.
+//
+// Reference: aggregate() :317-366, accumulators :52-176, sum :943, min :1012, max :1027.
+// sum wraps for integers (add_wrapping) and is IEEE for floats; min/max use the totalOrder
+// (arrow-array/src/arithmetic.rs:400-437). Float `sum` is order-dependent in the reference
+// itself (lane count depends on compile-time target features, aggregate.rs:303-313), so
+// parity for it is tolerance-based; everything else is bit-exact.
+//
+// Design: one streaming pass (HBM-bound, 8N + N/8 bytes). Lane l of a warp owns rows l and
+// l+32 of each 64-row strip (one validity word per strip), 4 strips in flight. Per-thread
+// accumulators -> warp shuffle tree -> per-CTA partial in scratch; the last CTA to finish
+// (atomic ticket) folds the partials in a fixed order, so results are deterministic for a
+// given grid. Float min/max run on integer totalOrder keys.
+#include <limits>
+#include <type_traits>
+
+#include "bitmap.cuh"
+
+namespace {
+
+template <class T> struct KeyOf { using type = T; };
+template <> struct KeyOf<double> { using type = int64_t; };
+template <> struct KeyOf<float> { using type = int32_t; };
+
+template <class T> __device__ __forceinline__ typename KeyOf<T>::type to_key(T v) {
+  if constexpr (std::is_floating_point<T>::value) return total_key(v);
+  else return v;
+}
+template <class T> __device__ __forceinline__ T from_key(typename KeyOf<T>::type k) {
+  if constexpr (sizeof(T) == 8 && std::is_floating_point<T>::value) return __longlong_as_double(k ^ (int64_t)((uint64_t)(k >> 63) >> 1));
+  else if constexpr (std::is_floating_point<T>::value) return __int_as_float(k ^ (int32_t)((uint32_t)(k >> 31) >> 1));
+  else return k;
+}
+
+// accumulator domain: sum -> T itself; min/max -> totalOrder key
+template <class T, int OP> struct AccOf { using type = typename std::conditional<OP == ACU_SUM, T, typename KeyOf<T>::type>::type; };
+
+template <class A, int OP> __device__ __forceinline__ A acc_identity() {
+  if constexpr (OP == ACU_SUM) return A(0);
+  else if constexpr (OP == ACU_MIN) return std::numeric_limits<A>::max();   // MAX_TOTAL_ORDER
+  else return std::numeric_limits<A>::lowest();                            // MIN_TOTAL_ORDER
+}
+template <class A, int OP> __device__ __forceinline__ A acc_merge(A a, A b) {
+  if constexpr (OP == ACU_SUM) {
+    if constexpr (std::is_same<A, double>::value) return __dadd_rn(a, b);
+    else if constexpr (std::is_same<A, float>::value) return __fadd_rn(a, b);
+    else return (A)((typename std::make_unsigned<A>::type)a + (typename std::make_unsigned<A>::type)b);  // add_wrapping
+  } else if constexpr (OP == ACU_MIN) {
+    return b < a ? b : a;
+  } else {
+    return b > a ? b : a;
+  }
+}
+template <class T, int OP> __device__ __forceinline__ typename AccOf<T, OP>::type acc_lift(T v) {
+  if constexpr (OP == ACU_SUM) return v;
+  else return to_key<T>(v);
+}
+
+template <class A> __device__ __forceinline__ A shfl_down_any(A v, int o) {
+  if constexpr (sizeof(A) == 8) {
+    long long x;
+    memcpy(&x, &v, 8);
+    x = __shfl_down_sync(ACU_FULL_MASK, x, o);
+    memcpy(&v, &x, 8);
+    return v;
+  } else {
+    int x = 0;
+    memcpy(&x, &v, sizeof(A));
+    x = __shfl_down_sync(ACU_FULL_MASK, x, o);
+    memcpy(&v, &x, sizeof(A));
+    return v;
+  }
+}
+
+template <class T, int OP>
+__global__ void __launch_bounds__(256) k_reduce(const T *__restrict__ v, int64_t n, const uint8_t *__restrict__ valid,
+                                                int64_t voff, typename AccOf<T, OP>::type *__restrict__ partial,
+                                                unsigned int *__restrict__ ticket, unsigned long long *__restrict__ res) {
+  using A = typename AccOf<T, OP>::type;
+  constexpr int U = 4;
+  __shared__ A s_part[8];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t strips = (n + 63) >> 6;
+  A acc = acc_identity<A, OP>();
+  unsigned valid_cnt = 0;
+  for (int64_t s0 = warp * U; s0 < strips; s0 += nwarps * U) {
+    T x[U][2];
+    uint64_t vw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = (s0 + u) * 64;
+      const int64_t k = n - row;
+      vw[u] = k >= 64 ? ~0ull : (k <= 0 ? 0ull : ((~0ull) >> (64 - k)));
+      if (valid) vw[u] &= ld_bits64(valid, voff + row, voff + n);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int64_t i = row + h * 32 + lane;
+        x[u][h] = i < n ? __ldg(v + i) : T();
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        if ((vw[u] >> (h * 32 + lane)) & 1ull) acc = acc_merge<A, OP>(acc, acc_lift<T, OP>(x[u][h]));
+      if (lane == 0) valid_cnt += __popcll(vw[u]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc = acc_merge<A, OP>(acc, shfl_down_any(acc, o));
+  if (lane == 0) {
+    s_part[wid] = acc;
+    if (valid_cnt) atomicAdd(res + RES_COUNT, (unsigned long long)valid_cnt);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    A b = s_part[0];
+    for (int w = 1; w < 8; ++w) b = acc_merge<A, OP>(b, s_part[w]);
+    partial[blockIdx.x] = b;
+    __threadfence();
+    s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && wid == 0) {  // fixed-order fold of the per-CTA partials
+    __threadfence();
+    A f = acc_identity<A, OP>();
+    for (unsigned i = lane; i < gridDim.x; i += 32) f = acc_merge<A, OP>(f, *(volatile A *)(partial + i));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) f = acc_merge<A, OP>(f, shfl_down_any(f, o));
+    if (lane == 0) {
+      T r;
+      if constexpr (OP == ACU_SUM) r = f;
+      else r = from_key<T>(f);
+      unsigned long long bits = 0;
+      memcpy(&bits, &r, sizeof(T));
+      res[RES_AUX0] = bits;
+      *ticket = 0;
+    }
+  }
+}
+
+template <class T, int OP>
+acu_status reduce_launch(acu_ctx *ctx, const acu_array *a, const uint8_t *valid) {
+  using A = typename AccOf<T, OP>::type;
+  const int64_t strips = (a->len + 63) >> 6;
+  const int grid = acu_wave_grid(ctx, k_reduce<T, OP>, 256, 0, (strips + 31) / 32);
+  void *scratch;
+  ACU_TRY(acu_scratch(ctx, 256 + (size_t)grid * sizeof(A), &scratch));
+  unsigned int *ticket = static_cast<unsigned int *>(scratch);
+  A *partial = reinterpret_cast<A *>(static_cast<uint8_t *>(scratch) + 256);
+  ACU_CUDA(ctx, cudaMemsetAsync(ticket, 0, 4, ctx->stream));
+  ACU_LAUNCH(ctx, (k_reduce<T, OP>), grid, 256, 0, static_cast<const T *>(a->values), a->len, valid, a->validity_offset,
+             partial, ticket, ctx->d_res);
+  return ACU_OK;
+}
+
+template <class T>
+acu_status aggregate_typed(acu_ctx *ctx, acu_agg_op op, const acu_array *a, uint64_t *out_bits, int64_t *out_valid) {
+  *out_bits = 0;
+  *out_valid = 0;
+  if (a->len == 0) return ACU_OK;  // None
+  acu_status st;
+  const int64_t nc = acu_resolve_null_count(ctx, a, &st);
+  ACU_TRY(st);
+  *out_valid = a->len - nc;
+  if (nc == a->len) return ACU_OK;  // aggregate.rs:320-323
+  const uint8_t *valid = (a->validity && nc > 0) ? a->validity : nullptr;
+  ACU_TRY(acu_res_reset(ctx));
+  switch (op) {
+    case ACU_SUM: ACU_TRY((reduce_launch<T, ACU_SUM>(ctx, a, valid))); break;
+    case ACU_MIN: ACU_TRY((reduce_launch<T, ACU_MIN>(ctx, a, valid))); break;
+    default: ACU_TRY((reduce_launch<T, ACU_MAX>(ctx, a, valid))); break;
+  }
+  ACU_TRY(acu_res_fetch(ctx));
+  *out_bits = ctx->h_res[RES_AUX0];
+  return ACU_OK;
+}
+
+}  // namespace
+
+extern "C" acu_status acu_aggregate(acu_ctx *ctx, acu_dtype dtype, acu_agg_op op, const acu_array *a,
+                                    uint64_t *out_bits, int64_t *out_valid_count) {
+  switch (dtype) {
+    case ACU_I8: return aggregate_typed<int8_t>(ctx, op, a, out_bits, out_valid_count);
+    case ACU_I16: return aggregate_typed<int16_t>(ctx, op, a, out_bits, out_valid_count);
+    case ACU_I32: return aggregate_typed<int32_t>(ctx, op, a, out_bits, out_valid_count);
+    case ACU_I64: return aggregate_typed<int64_t>(ctx, op, a, out_bits, out_valid_count);
+    case ACU_U8: return aggregate_typed<uint8_t>(ctx, op, a, out_bits, out_valid_count);
+    case ACU_U16: return aggregate_typed<uint16_t>(ctx, op, a, out_bits, out_valid_count);
+    case ACU_U32: return aggregate_typed<uint32_t>(ctx, op, a, out_bits, out_valid_count);
+    case ACU_U64: return aggregate_typed<uint64_t>(ctx, op, a, out_bits, out_valid_count);
+    case ACU_F32: return aggregate_typed<float>(ctx, op, a, out_bits, out_valid_count);
+    case ACU_F64: return aggregate_typed<double>(ctx, op, a, out_bits, out_valid_count);
+  }
+  return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "aggregate: dtype %d", (int)dtype);
+}

@@ -1,0 +1,378 @@
+// take.cu — arrow-select/src/take.rs on the device.
+//
+//   take_primitive = take_native + take_nulls   (take.rs:405-457)
+//   take_bits / take_boolean                     (take.rs:460-496)
+//   check_bounds                                 (take.rs:167-209)
+//   ToIndices                                    (take.rs:1030-1084)
+//
+// Design (gather, HBM/sector-bound): persistent CTAs walk index tiles of 2048 indices.
+// The NEXT tile's indices are prefetched into shared memory with a 1-D bulk async copy
+// (cp.async.bulk + mbarrier, the TMA engine: UBLKCP in SASS) while the current tile is
+// gathered, so the index stream never sits on the dependent-load critical path. Each thread
+// then issues 8 independent gathers (values + validity bit) before storing; output values
+// are written with fully coalesced stores, output validity is packed with a warp ballot
+// (lane == output bit), and the null count / out-of-bounds detection ride in the same pass.
+#include <stdio.h>
+
+#include <type_traits>
+
+#include "bitmap.cuh"
+#include "internal.cuh"
+
+#define TAKE_TILE 2048
+#define TAKE_PER_THREAD (TAKE_TILE / 256)
+
+namespace {
+
+// ---- mbarrier + bulk-copy PTX wrappers --------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int W> struct VecOf;
+template <> struct VecOf<1> { using type = uint8_t; };
+template <> struct VecOf<2> { using type = uint16_t; };
+template <> struct VecOf<4> { using type = uint32_t; };
+template <> struct VecOf<8> { using type = uint64_t; };
+template <> struct VecOf<16> { using type = uint4; };
+struct alignas(16) U32B { uint4 lo, hi; };
+template <> struct VecOf<32> { using type = U32B; };
+
+template <class V> __device__ __forceinline__ V zero_of() { V v; memset(&v, 0, sizeof(V)); return v; }
+template <class V> __device__ __forceinline__ V gather_ld(const V *p) {
+  if constexpr (sizeof(V) == 32) {
+    V v;
+    v.lo = __ldg(reinterpret_cast<const uint4 *>(p));
+    v.hi = __ldg(reinterpret_cast<const uint4 *>(p) + 1);
+    return v;
+  } else {
+    return __ldg(p);
+  }
+}
+
+struct TakeArgs {
+  const void *values;       // NULL for take_nulls-only / take_boolean passes
+  int64_t n_values;
+  const uint8_t *vvalid;    // values validity to gather (NULL: none)
+  int64_t vvoff;
+  const uint8_t *vbits;     // boolean VALUES to gather (take_boolean), else NULL
+  int64_t vboff;
+  const void *idx;
+  int64_t m;
+  const uint8_t *ivalid;    // index validity (only when it has nulls, or to clone)
+  int64_t ivoff;
+  int idx_has_nulls;        // indices.null_count() > 0
+  void *out;
+  uint32_t *out_valid;      // u32 words, bit offset 0 (NULL: none)
+  uint32_t *out_bits;       // take_boolean values
+  unsigned long long *res;
+  int use_bulk;             // idx base 16-B aligned: stage index tiles with cp.async.bulk
+};
+
+// ToIndices (take.rs:1030-1084). IT: 0=u8 1=i8 2=u16 3=i16 4=u32/i32 5=u64/i64
+template <int IT> struct IdxOf;
+template <> struct IdxOf<0> { using raw = uint8_t; };
+template <> struct IdxOf<1> { using raw = int8_t; };
+template <> struct IdxOf<2> { using raw = uint16_t; };
+template <> struct IdxOf<3> { using raw = int16_t; };
+template <> struct IdxOf<4> { using raw = uint32_t; };
+template <> struct IdxOf<5> { using raw = uint64_t; };
+template <int IT> __device__ __forceinline__ uint64_t widen(typename IdxOf<IT>::raw v) {
+  if constexpr (IT == 1 || IT == 3) return (uint64_t)(uint32_t)(int32_t)v;  // `as u32` sign-extends
+  else return (uint64_t)v;
+}
+
+template <int W, int IT>
+__global__ void __launch_bounds__(256) k_take(const TakeArgs a) {
+  using V = typename VecOf<W>::type;
+  using I = typename IdxOf<IT>::raw;
+  __shared__ __align__(16) I s_idx[2][TAKE_TILE];
+  __shared__ __align__(8) uint64_t s_bar[2];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const I *idx = static_cast<const I *>(a.idx);
+  const int64_t n_tiles = (a.m + TAKE_TILE - 1) / TAKE_TILE;
+  const bool gather_values = (W > 0) && a.values != nullptr;
+  unsigned valid_cnt = 0;
+  unsigned long long err = ~0ull;
+
+  if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  // stage tile `t` into buffer `b`
+  auto stage = [&](int64_t t, int b) {
+    const int64_t j0 = t * TAKE_TILE;
+    const int cnt = (int)((a.m - j0) < TAKE_TILE ? (a.m - j0) : TAKE_TILE);
+    const bool bulk = a.use_bulk && cnt == TAKE_TILE;  // full tiles only: size % 16 == 0
+    if (bulk) {
+      if (tid == 0) {
+        mbar_expect_tx(&s_bar[b], (unsigned)(TAKE_TILE * sizeof(I)));
+        bulk_g2s(&s_idx[b][0], idx + j0, (unsigned)(TAKE_TILE * sizeof(I)), &s_bar[b]);
+      }
+    } else {
+      for (int k = tid; k < cnt; k += 256) s_idx[b][k] = __ldg(idx + j0 + k);
+    }
+    return bulk;
+  };
+
+  unsigned phase[2] = {0, 0};
+  int64_t t = blockIdx.x;
+  bool cur_bulk = false;
+  if (t < n_tiles) cur_bulk = stage(t, 0);
+  int buf = 0;
+  for (; t < n_tiles; t += gridDim.x) {
+    const int64_t tn = t + gridDim.x;
+    bool next_bulk = false;
+    if (tn < n_tiles) next_bulk = stage(tn, buf ^ 1);  // prefetch while we gather
+    if (cur_bulk) { mbar_wait(&s_bar[buf], phase[buf]); phase[buf] ^= 1; }
+    else __syncthreads();
+
+    const int64_t j0 = t * TAKE_TILE;
+    uint64_t ix[TAKE_PER_THREAD];
+    bool live[TAKE_PER_THREAD], inb[TAKE_PER_THREAD];
+    V v[TAKE_PER_THREAD];
+    uint32_t bit[TAKE_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < TAKE_PER_THREAD; ++k) {
+      const int j = k * 256 + tid;
+      live[k] = j0 + j < a.m;
+      ix[k] = live[k] ? widen<IT>(s_idx[buf][j]) : 0ull;
+      inb[k] = live[k] && ix[k] < (uint64_t)a.n_values;
+    }
+    // ---- 8 independent gathers in flight per thread ----
+#pragma unroll
+    for (int k = 0; k < TAKE_PER_THREAD; ++k) {
+      if (gather_values) v[k] = inb[k] ? gather_ld<V>(static_cast<const V *>(a.values) + ix[k]) : zero_of<V>();
+      uint32_t b = 1u;
+      if (a.vvalid) b = inb[k] ? ld_bit(a.vvalid, a.vvoff + (int64_t)ix[k]) : 0u;
+      if (a.vbits) b |= (inb[k] ? ld_bit(a.vbits, a.vboff + (int64_t)ix[k]) : 0u) << 1;
+      bit[k] = b;
+    }
+#pragma unroll
+    for (int k = 0; k < TAKE_PER_THREAD; ++k) {
+      const int j = k * 256 + tid;
+      const int64_t gj = j0 + j;  // warp-uniform base: gj - lane is a multiple of 32
+      uint32_t iv = ~0u;
+      if (a.ivalid) iv = ld_bits32(a.ivalid, a.ivoff + (gj - lane), a.ivoff + a.m);
+      const bool idx_valid = live[k] && ((iv >> lane) & 1u);
+      // out-of-bounds at a VALID index slot panics in the reference (take.rs:447,454);
+      // at a NULL slot it yields T::default() (already zero)
+      const bool counts_as_valid_idx = a.idx_has_nulls ? idx_valid : live[k];
+      if (live[k] && !inb[k] && counts_as_valid_idx) { unsigned long long e = (unsigned long long)gj; err = e < err ? e : err; }
+      if (gather_values && live[k]) static_cast<V *>(a.out)[gj] = v[k];
+      if (a.out_valid) {
+        bool ob = live[k];
+        if (a.vvalid) ob = ob && (bit[k] & 1u) && counts_as_valid_idx;  // take_bits of values.nulls
+        else ob = idx_valid;                                             // indices.nulls().cloned()
+        const uint32_t word = __ballot_sync(ACU_FULL_MASK, ob);
+        if (lane == 0 && gj < a.m) { a.out_valid[gj >> 5] = word; valid_cnt += __popc(word); }
+      }
+      if (a.out_bits) {  // take_bits on boolean values: unset at null indices
+        const bool ob = live[k] && counts_as_valid_idx && ((bit[k] >> 1) & 1u);
+        const uint32_t word = __ballot_sync(ACU_FULL_MASK, ob);
+        if (lane == 0 && gj < a.m) a.out_bits[gj >> 5] = word;
+      }
+    }
+    __syncthreads();  // everyone is done with s_idx[buf] before it is refilled
+    buf ^= 1;
+    cur_bulk = next_bulk;
+  }
+  if (a.out_valid) {
+    if (lane == 0 && valid_cnt) atomicAdd(a.res + RES_COUNT, (unsigned long long)valid_cnt);
+  }
+  if (err != ~0ull) atomicMin(a.res + RES_ERR_INDEX, err);
+}
+
+// check_bounds (take.rs:167-209) on the ORIGINAL index type: lowest offending row.
+template <int IT, bool SIGNED>
+__global__ void __launch_bounds__(256) k_check_bounds(const void *idx_v, int64_t m, int64_t len,
+                                                      const uint8_t *ivalid, int64_t ivoff,
+                                                      unsigned long long *res) {
+  using I = typename IdxOf<IT>::raw;
+  const I *idx = static_cast<const I *>(idx_v);
+  unsigned long long err = ~0ull;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
+    if (ivalid && !ld_bit(ivalid, ivoff + j)) continue;
+    bool bad;
+    if constexpr (SIGNED) {
+      using S = typename std::make_signed<I>::type;
+      const int64_t v = (int64_t)(S)idx[j];
+      // nullable path only tests `index >= len` (take.rs:183); otherwise also `< 0` (:193-199)
+      bad = ivalid ? (v >= len) : (v < 0 || v >= len);
+    } else {
+      bad = (uint64_t)idx[j] >= (uint64_t)len;
+    }
+    if (bad && (unsigned long long)j < err) err = (unsigned long long)j;
+  }
+  if (err != ~0ull) atomicMin(res + RES_ERR_INDEX, err);
+}
+
+int index_kind(acu_dtype t) {
+  switch (t) {
+    case ACU_U8: return 0; case ACU_I8: return 1; case ACU_U16: return 2; case ACU_I16: return 3;
+    case ACU_U32: case ACU_I32: return 4; case ACU_U64: case ACU_I64: return 5;
+    default: return -1;
+  }
+}
+uint64_t index_max(acu_dtype t) {
+  switch (t) {
+    case ACU_I8: return INT8_MAX; case ACU_I16: return INT16_MAX; case ACU_I32: return INT32_MAX;
+    case ACU_I64: return INT64_MAX; case ACU_U8: return UINT8_MAX; case ACU_U16: return UINT16_MAX;
+    case ACU_U32: return UINT32_MAX; default: return UINT64_MAX;
+  }
+}
+
+template <int W>
+acu_status launch_take_w(acu_ctx *ctx, int kind, const TakeArgs &ta) {
+  const int64_t tiles = (ta.m + TAKE_TILE - 1) / TAKE_TILE;
+#define ACU_TAKE_CASE(IT)                                                                                   \
+  case IT: ACU_LAUNCH(ctx, (k_take<W, IT>), acu_wave_grid(ctx, k_take<W, IT>, 256, 0, tiles), 256, 0, ta); \
+    break;
+  switch (kind) {
+    ACU_TAKE_CASE(0) ACU_TAKE_CASE(1) ACU_TAKE_CASE(2) ACU_TAKE_CASE(3) ACU_TAKE_CASE(4) ACU_TAKE_CASE(5)
+    default: break;
+  }
+#undef ACU_TAKE_CASE
+  return ACU_OK;
+}
+
+acu_status launch_take(acu_ctx *ctx, int elem_bytes, int kind, const TakeArgs &ta) {
+  switch (elem_bytes) {
+    case 1: return launch_take_w<1>(ctx, kind, ta);
+    case 2: return launch_take_w<2>(ctx, kind, ta);
+    case 4: return launch_take_w<4>(ctx, kind, ta);
+    case 8: return launch_take_w<8>(ctx, kind, ta);
+    case 16: return launch_take_w<16>(ctx, kind, ta);
+    case 32: return launch_take_w<32>(ctx, kind, ta);
+    default: return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "take: unsupported element width %d", elem_bytes);
+  }
+}
+
+acu_status fetch_index(acu_ctx *ctx, const acu_array *indices, acu_dtype t, int64_t j, uint64_t *raw, char *text, size_t n) {
+  uint64_t v = 0;
+  const int sz = acu_dtype_size(t);
+  ACU_CUDA(ctx, cudaMemcpyAsync(&v, static_cast<const uint8_t *>(indices->values) + (size_t)j * sz, sz, cudaMemcpyDeviceToHost, ctx->stream));
+  ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *raw = v;
+  if (acu_dtype_is_signed(t)) {
+    int64_t s = sz == 1 ? (int8_t)v : sz == 2 ? (int16_t)v : sz == 4 ? (int32_t)v : (int64_t)v;
+    snprintf(text, n, "%lld", (long long)s);
+  } else {
+    snprintf(text, n, "%llu", (unsigned long long)v);
+  }
+  return ACU_OK;
+}
+
+}  // namespace
+
+// Shared front end of take_primitive / take_boolean / take_bytes' null handling.
+// `elem_bytes` == 0: no value gather (bits / nulls only).
+acu_status acu_take_common(acu_ctx *ctx, int32_t elem_bytes, const acu_array *values, bool boolean_values,
+                           const acu_array *indices, acu_dtype index_dtype, int32_t check_bounds,
+                           acu_array_out *out) {
+  const int kind = index_kind(index_dtype);
+  if (kind < 0)  // take.rs:103
+    return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "Take only supported for integers, got %s", acu_dtype_name(index_dtype));
+  acu_status st;
+  const int64_t m = indices->len;
+  const int64_t inc = acu_resolve_null_count(ctx, indices, &st);
+  ACU_TRY(st);
+  const bool idx_nulls = indices->validity && inc > 0;
+  if (check_bounds && m > 0 && (uint64_t)values->len <= index_max(index_dtype)) {  // T::Native::from_usize(len)
+    ACU_TRY(acu_res_reset(ctx));
+    const int grid = acu_grid(ctx, (m + 255) / 256, 8);
+    const uint8_t *iv = idx_nulls ? indices->validity : nullptr;
+    const bool sgn = acu_dtype_is_signed(index_dtype);
+#define ACU_CB_CASE(IT)                                                                                                   \
+  case IT:                                                                                                                \
+    if (sgn) ACU_LAUNCH(ctx, (k_check_bounds<IT, true>), grid, 256, 0, indices->values, m, values->len, iv, indices->validity_offset, ctx->d_res); \
+    else ACU_LAUNCH(ctx, (k_check_bounds<IT, false>), grid, 256, 0, indices->values, m, values->len, iv, indices->validity_offset, ctx->d_res);    \
+    break;
+    switch (kind) { ACU_CB_CASE(0) ACU_CB_CASE(1) ACU_CB_CASE(2) ACU_CB_CASE(3) ACU_CB_CASE(4) ACU_CB_CASE(5) default: break; }
+#undef ACU_CB_CASE
+    ACU_TRY(acu_res_fetch(ctx));
+    if (ctx->h_res[RES_ERR_INDEX] != ~0ull) {
+      const int64_t j = (int64_t)ctx->h_res[RES_ERR_INDEX];
+      uint64_t raw;
+      char text[32];
+      ACU_TRY(fetch_index(ctx, indices, index_dtype, j, &raw, text, sizeof text));
+      return acu_fail(ctx, ACU_ERR_COMPUTE, j, raw, 0, (uint64_t)values->len,
+                      "Array index out of bounds, cannot get item at index %s from %lld entries", text, (long long)values->len);
+    }
+  }
+  out->len = m;
+  out->has_validity = 0;
+  out->null_count = 0;
+  if (m == 0) return ACU_OK;  // take_impl: new_empty_array (take.rs:216-218)
+  const int64_t vnc = acu_resolve_null_count(ctx, values, &st);
+  ACU_TRY(st);
+  const bool val_nulls = values->validity && vnc > 0;  // take_nulls (take.rs:419-430)
+
+  TakeArgs ta{};
+  ta.values = (elem_bytes > 0 && !boolean_values) ? values->values : nullptr;
+  ta.n_values = values->len;
+  if (val_nulls) { ta.vvalid = values->validity; ta.vvoff = values->validity_offset; }
+  if (boolean_values) { ta.vbits = static_cast<const uint8_t *>(values->values); ta.vboff = values->values_offset; ta.out_bits = static_cast<uint32_t *>(out->values); }
+  ta.idx = indices->values;
+  ta.m = m;
+  if (idx_nulls || (!val_nulls && indices->validity)) { ta.ivalid = indices->validity; ta.ivoff = indices->validity_offset; }
+  ta.idx_has_nulls = idx_nulls;
+  ta.out = out->values;
+  if (val_nulls || indices->validity) ta.out_valid = reinterpret_cast<uint32_t *>(out->validity);
+  ta.res = ctx->d_res;
+  ta.use_bulk = ((uintptr_t)indices->values % 16) == 0;
+  ACU_TRY(acu_res_reset(ctx));
+  ACU_TRY(launch_take(ctx, ta.values ? elem_bytes : 1, kind, ta));
+  ACU_TRY(acu_res_fetch(ctx));
+  if (ctx->h_res[RES_ERR_INDEX] != ~0ull) {
+    const int64_t j = (int64_t)ctx->h_res[RES_ERR_INDEX];
+    uint64_t raw;
+    char text[32];
+    ACU_TRY(fetch_index(ctx, indices, index_dtype, j, &raw, text, sizeof text));
+    return acu_fail(ctx, ACU_ERR_PANIC_OUT_OF_BOUNDS, j, raw, 0, (uint64_t)values->len, "Out-of-bounds index %s", text);
+  }
+  if (ta.out_valid) {
+    const int64_t null_count = m - (int64_t)ctx->h_res[RES_COUNT];
+    if (val_nulls) {  // NullBuffer::from_unsliced_buffer: None when no nulls (null.rs:266-270)
+      if (null_count > 0) { out->has_validity = 1; out->null_count = null_count; }
+    } else {
+      out->has_validity = 1;
+      out->null_count = null_count;
+    }
+  }
+  return ACU_OK;
+}
+
+extern "C" acu_status acu_take_primitive(acu_ctx *ctx, int32_t elem_bytes, const acu_array *values,
+                                         const acu_array *indices, acu_dtype index_dtype,
+                                         int32_t check_bounds, acu_array_out *out) {
+  return acu_take_common(ctx, elem_bytes, values, false, indices, index_dtype, check_bounds, out);
+}
+
+extern "C" acu_status acu_take_boolean(acu_ctx *ctx, const acu_array *values, const acu_array *indices,
+                                       acu_dtype index_dtype, int32_t check_bounds, acu_array_out *out) {
+  return acu_take_common(ctx, 0, values, true, indices, index_dtype, check_bounds, out);
+}

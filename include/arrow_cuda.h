@@ -1,0 +1,319 @@
+/*
+ * arrow_cuda.h — C ABI of the B200-native arrow::compute hot path.
+ *
+ * This is the drop-in boundary: one extern "C" entry point per
+ * reference kernel, taking raw DEVICE pointers + explicit lengths / bit offsets, so
+ * that a thin Rust `arrow-cuda` crate (rust/arrow-cuda, source only — no rustc in
+ * this image) or the C++ host mirror (arrow-rs_b200/host/arrow_cuda.hpp) can wrap
+ * them with the reference's own signatures over ArrayRef / RecordBatch.
+ *
+ * Layout contract (mirrors arrow-buffer; reference file:line in brackets):
+ *   - values buffer: contiguous little-endian natives, pointer already advanced to
+ *     logical element 0                      [arrow-buffer/src/buffer/scalar.rs:29-46]
+ *   - validity / boolean bitmap: bytes, bit i of the logical array at byte
+ *     (off+i)>>3, bit (off+i)&7, LSB first, 1 = valid / true
+ *                                            [arrow-buffer/src/util/bit_util.rs:52-66,
+ *                                             arrow-buffer/src/buffer/boolean.rs:97-104]
+ *   - null_count is cached beside the bitmap  [arrow-buffer/src/buffer/null.rs:34-37]
+ *
+ * Every OUTPUT bitmap is written with bit offset 0 and must have a capacity of
+ * acu_bitmap_bytes(len) = 8*ceil(len/64) bytes (kernels store whole 64-bit words);
+ * bits at positions >= len are unspecified, exactly as in the reference
+ * (arrow-ord/src/cmp.rs:598-608).
+ *
+ * Calls are synchronous with respect to the host: every entry point that returns a
+ * host-visible scalar (count, null_count, error index) synchronises the ctx stream
+ * before returning. One acu_ctx = one device + one stream + scratch; a ctx must not
+ * be used from two host threads at once, distinct ctxs are independent (the
+ * reference kernels are pure, re-entrant functions: arrow-array/src/array/mod.rs:99).
+ *
+ * There is NO CPU fallback behind this ABI: if no CUDA device is present
+ * acu_ctx_create fails with ACU_ERR_CUDA.
+ */
+#ifndef ARROW_CUDA_H
+#define ARROW_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACU_ABI_VERSION 1
+
+/* ------------------------------------------------------------------------- */
+/* Status codes — one per ArrowError variant the hot path can produce        */
+/* (arrow-schema/src/error.rs:26-67), plus the reference's panics, plus      */
+/* device-side failures.                                                     */
+/* ------------------------------------------------------------------------- */
+typedef int32_t acu_status;
+enum {
+  ACU_OK = 0,
+  ACU_ERR_INVALID_ARGUMENT = 1,    /* ArrowError::InvalidArgumentError          */
+  ACU_ERR_COMPUTE = 2,             /* ArrowError::ComputeError                  */
+  ACU_ERR_ARITHMETIC_OVERFLOW = 3, /* ArrowError::ArithmeticOverflow            */
+  ACU_ERR_DIVIDE_BY_ZERO = 4,      /* ArrowError::DivideByZero                  */
+  ACU_ERR_OFFSET_OVERFLOW = 5,     /* ArrowError::OffsetOverflowError(usize)    */
+  ACU_ERR_CAST = 6,                /* ArrowError::CastError                     */
+  ACU_ERR_NOT_YET_IMPLEMENTED = 7, /* ArrowError::NotYetImplemented             */
+  ACU_ERR_PANIC_OUT_OF_BOUNDS = 8, /* the reference panics (take.rs:447,454)    */
+  ACU_ERR_CUDA = 100,              /* CUDA runtime error (detail.cuda_error)    */
+  ACU_ERR_NCCL = 101,              /* NCCL error                                */
+  ACU_ERR_OUT_OF_MEMORY = 102
+};
+
+/* Filled on every non-OK return; lets the host shim rebuild the reference's exact
+ * message, e.g. "Overflow happened on: {lhs} + {rhs}" (arrow-array/src/arithmetic.rs:163-170)
+ * or "Array index out of bounds, cannot get item at index {index} from {len} entries"
+ * (arrow-select/src/take.rs:186-188). `message` already holds that text. */
+typedef struct acu_error_detail {
+  acu_status status;
+  int32_t cuda_error;   /* cudaError_t / ncclResult_t when status >= 100 */
+  int64_t index;        /* lowest offending logical row, -1 if n/a        */
+  uint64_t lhs_bits;    /* operand bit patterns at `index`                */
+  uint64_t rhs_bits;
+  uint64_t len;         /* array length / capacity relevant to the error  */
+  char message[256];
+} acu_error_detail;
+
+typedef struct acu_ctx acu_ctx;
+
+/* Native types (arrow-array/src/types.rs:67-80, ArrowPrimitiveType::Native). */
+typedef enum acu_dtype {
+  ACU_I8 = 0, ACU_I16 = 1, ACU_I32 = 2, ACU_I64 = 3,
+  ACU_U8 = 4, ACU_U16 = 5, ACU_U32 = 6, ACU_U64 = 7,
+  ACU_F32 = 8, ACU_F64 = 9
+} acu_dtype;
+
+/* arrow-arith/src/numeric.rs:181-190 `enum Op` — same order. */
+typedef enum acu_arith_op {
+  ACU_ADD_WRAPPING = 0, ACU_ADD = 1,
+  ACU_SUB_WRAPPING = 2, ACU_SUB = 3,
+  ACU_MUL_WRAPPING = 4, ACU_MUL = 5,
+  ACU_DIV = 6, ACU_REM = 7
+} acu_arith_op;
+
+/* arrow-ord/src/cmp.rs:40-60 `enum Op`. */
+typedef enum acu_cmp_op {
+  ACU_EQ = 0, ACU_NEQ = 1, ACU_LT = 2, ACU_LT_EQ = 3, ACU_GT = 4, ACU_GT_EQ = 5,
+  ACU_DISTINCT = 6, ACU_NOT_DISTINCT = 7
+} acu_cmp_op;
+
+/* arrow-arith/src/aggregate.rs:943,1012,1027. */
+typedef enum acu_agg_op { ACU_SUM = 0, ACU_MIN = 1, ACU_MAX = 2 } acu_agg_op;
+
+/* A borrowed, immutable view of a primitive / boolean array in HBM
+ * (PrimitiveArray{values,nulls} arrow-array/src/array/primitive_array.rs:596-601;
+ *  BooleanArray{values,nulls} arrow-array/src/array/boolean_array.rs:68-71). */
+typedef struct acu_array {
+  const void *values;       /* device ptr to logical element 0 (for boolean arrays: bitmap bytes) */
+  int64_t values_offset;    /* boolean arrays only: bit offset of logical row 0 in `values`      */
+  const uint8_t *validity;  /* device ptr to validity bytes, NULL = no NullBuffer                */
+  int64_t validity_offset;  /* bit offset of logical row 0 in `validity`                         */
+  int64_t len;              /* logical length                                                    */
+  int64_t null_count;       /* cached null count; -1 = unknown (counted on device)               */
+  int32_t is_scalar;        /* Datum::get().1 (arrow-array/src/scalar.rs:78-152): len must be 1  */
+  int32_t reserved;
+} acu_array;
+
+/* Caller-owned output. `values` capacity: len*width bytes (boolean results:
+ * acu_bitmap_bytes(len)); `validity` capacity: acu_bitmap_bytes(len).
+ * On return: len, null_count, has_validity (0 => the reference returns nulls = None
+ * and the validity buffer content is unspecified). */
+typedef struct acu_array_out {
+  void *values;
+  uint8_t *validity;
+  int64_t len;
+  int64_t null_count;
+  int32_t has_validity;
+  int32_t reserved;
+} acu_array_out;
+
+static inline size_t acu_bitmap_bytes(int64_t len) { return (size_t)((len + 63) / 64) * 8; }
+
+/* ------------------------------------------------------------------------- */
+/* Context, memory, timing                                                   */
+/* ------------------------------------------------------------------------- */
+int32_t acu_abi_version(void);
+acu_status acu_ctx_create(int32_t device, acu_ctx **out);
+void acu_ctx_destroy(acu_ctx *ctx);
+acu_status acu_ctx_sync(acu_ctx *ctx);
+/* Detail of the last failing call on this ctx (never NULL once ctx exists). */
+const acu_error_detail *acu_last_error(const acu_ctx *ctx);
+/* Number of kernels this ctx has launched since creation (bench.py: gpu_launches). */
+int64_t acu_launch_count(const acu_ctx *ctx);
+int32_t acu_device_sm_count(const acu_ctx *ctx);
+
+/* DeviceBuffer allocation: 256-B aligned, stream-ordered (cudaMallocAsync pool);
+ * mirrors arrow-buffer's 128-B aligned host allocation (src/alloc/alignment.rs:38). */
+acu_status acu_malloc(acu_ctx *ctx, size_t bytes, void **out_dptr);
+acu_status acu_free(acu_ctx *ctx, void *dptr);
+acu_status acu_memset(acu_ctx *ctx, void *dptr, int32_t byte, size_t bytes);
+acu_status acu_memcpy_h2d(acu_ctx *ctx, void *dst_dptr, const void *src_host, size_t bytes);
+acu_status acu_memcpy_d2h(acu_ctx *ctx, void *dst_host, const void *src_dptr, size_t bytes);
+acu_status acu_memcpy_d2d(acu_ctx *ctx, void *dst_dptr, const void *src_dptr, size_t bytes);
+/* Asynchronous variants (ordered on the ctx stream; host memory must be pinned). */
+acu_status acu_memcpy_h2d_async(acu_ctx *ctx, void *dst_dptr, const void *src_host, size_t bytes);
+acu_status acu_memcpy_d2h_async(acu_ctx *ctx, void *dst_host, const void *src_dptr, size_t bytes);
+acu_status acu_host_alloc(acu_ctx *ctx, size_t bytes, void **out_host);   /* pinned */
+acu_status acu_host_free(acu_ctx *ctx, void *host);
+/* Bytes currently allocated through acu_malloc on this ctx (observability; the
+ * reference's MemoryPool tracking, arrow-buffer/src/pool.rs:73-85). */
+int64_t acu_bytes_allocated(const acu_ctx *ctx);
+
+/* CUDA-event timer on the ctx stream (events see exactly the stream kernels run on). */
+acu_status acu_timer_start(acu_ctx *ctx);
+acu_status acu_timer_stop(acu_ctx *ctx, float *out_ms);  /* records + synchronises */
+
+/* Deterministic synthetic inputs generated on the device:
+ * element i = f(splitmix64(seed ^ (first_row + i))). The same generator exists on the
+ * host in oracle/ so that any row range can be spot-checked.
+ *   kind 0: raw 64-bit values (Int64 full range)
+ *   kind 1: Int64 uniform in [-2^61, 2^61)
+ *   kind 2: Float64 uniform in [-1e6, 1e6)
+ *   kind 3: UInt32 uniform in [0, param)         (take indices, distribution B)
+ *   kind 4: Int32 uniform in [0, param)
+ * acu_generate_bits: bit i = splitmix64(seed ^ (first_row+i)) < p * 2^64. */
+acu_status acu_generate_values(acu_ctx *ctx, int32_t kind, uint64_t seed, int64_t first_row,
+                               uint64_t param, void *out, int64_t n);
+acu_status acu_generate_bits(acu_ctx *ctx, uint64_t seed, int64_t first_row, double p,
+                             uint8_t *out_bits, int64_t n);
+
+/* ------------------------------------------------------------------------- */
+/* Bitmaps                                                                   */
+/* ------------------------------------------------------------------------- */
+/* popcount of bits [offset, offset+len)  — BooleanBuffer::count_set_bits
+ * (arrow-buffer/src/buffer/boolean.rs) / BooleanArray::true_count when `validity`
+ * is non-NULL (arrow-array/src/array/boolean_array.rs:175-187). */
+acu_status acu_bitmap_count(acu_ctx *ctx, const uint8_t *bits, int64_t offset,
+                            const uint8_t *validity, int64_t validity_offset, int64_t len,
+                            int64_t *out_count);
+
+/* ------------------------------------------------------------------------- */
+/* filter — arrow-select/src/filter.rs                                       */
+/* ------------------------------------------------------------------------- */
+/* FilterBuilder::new + optimize + build (filter.rs:254-324): folds predicate nulls
+ * into the mask (prep_null_mask_filter :167-171), counts selected rows, and keeps a
+ * device-resident plan (normalised mask words + per-tile output offsets) that can be
+ * applied to any number of columns (FilterPredicate, filter.rs:442-533). */
+typedef struct acu_filter_plan acu_filter_plan;
+typedef enum acu_filter_strategy {  /* IterationStrategy, filter.rs:328-365 */
+  ACU_FILTER_NONE = 0, ACU_FILTER_ALL = 1, ACU_FILTER_INDEX = 2, ACU_FILTER_SLICES = 3
+} acu_filter_strategy;
+
+acu_status acu_filter_plan_create(acu_ctx *ctx, const acu_array *predicate /* boolean array */,
+                                  acu_filter_plan **out_plan);
+void acu_filter_plan_destroy(acu_ctx *ctx, acu_filter_plan *plan);
+int64_t acu_filter_plan_count(const acu_filter_plan *plan);      /* FilterPredicate::count */
+int64_t acu_filter_plan_len(const acu_filter_plan *plan);        /* predicate length       */
+int32_t acu_filter_plan_strategy(const acu_filter_plan *plan);   /* acu_filter_strategy    */
+
+/* filter_primitive / filter_native + filter_nulls (filter.rs:732-788, :512-533).
+ * elem_bytes in {1,2,4,8,16,32}. Error if plan len > values.len (filter.rs:536-542).
+ * out->values capacity: count*elem_bytes. out->has_validity = 0 when the source has no
+ * nulls or the filtered result has none (filter.rs:518-526). */
+acu_status acu_filter_primitive(acu_ctx *ctx, const acu_filter_plan *plan, int32_t elem_bytes,
+                                const acu_array *values, acu_array_out *out);
+/* filter_boolean / filter_bits (filter.rs:680-729): `values` is a boolean array. */
+acu_status acu_filter_boolean(acu_ctx *ctx, const acu_filter_plan *plan, const acu_array *values,
+                              acu_array_out *out);
+/* filter_bytes for Utf8/Binary (offset_bytes = 4) and Large* (8) (filter.rs:893-928).
+ * Two-phase: out_offsets (count+1 entries) is always written and *out_data_len returned;
+ * value bytes are copied only if out_data != NULL (capacity out_data_capacity). */
+acu_status acu_filter_bytes(acu_ctx *ctx, const acu_filter_plan *plan, int32_t offset_bytes,
+                            const void *offsets, const uint8_t *data, const acu_array *nulls_of,
+                            void *out_offsets, uint8_t *out_data, int64_t out_data_capacity,
+                            int64_t *out_data_len, acu_array_out *out_nulls);
+
+/* ------------------------------------------------------------------------- */
+/* take — arrow-select/src/take.rs                                           */
+/* ------------------------------------------------------------------------- */
+/* take_primitive = take_native + take_nulls (take.rs:405-457). `indices.values`
+ * has native type index_dtype (any integer type; ToIndices take.rs:1030-1084:
+ * i8/i16 sign-extend to u32, i32/i64 reinterpret). check_bounds != 0 =>
+ * TakeOptions{check_bounds:true} (take.rs:167-209): ACU_ERR_COMPUTE with the lowest
+ * offending index. Otherwise an out-of-bounds VALID index returns
+ * ACU_ERR_PANIC_OUT_OF_BOUNDS (the reference panics) and an out-of-bounds index in a
+ * NULL slot yields T::default() = 0 (take.rs:442-448). */
+acu_status acu_take_primitive(acu_ctx *ctx, int32_t elem_bytes, const acu_array *values,
+                              const acu_array *indices, acu_dtype index_dtype,
+                              int32_t check_bounds, acu_array_out *out);
+/* take_boolean / take_bits (take.rs:460-496). */
+acu_status acu_take_boolean(acu_ctx *ctx, const acu_array *values, const acu_array *indices,
+                            acu_dtype index_dtype, int32_t check_bounds, acu_array_out *out);
+/* take_bytes (take.rs:499-627); also Dictionary<K,Utf8> -> Utf8 cast =
+ * unpack_dictionary (arrow-cast/src/cast/dictionary.rs:310-317) with values = the
+ * dictionary and indices = the keys. i32 offset overflow => ACU_ERR_OFFSET_OVERFLOW
+ * (take.rs:520-523). Two-phase like acu_filter_bytes. `nulls_of` carries the
+ * validity/len/null_count of the byte array (its `values` member is ignored). */
+acu_status acu_take_bytes(acu_ctx *ctx, int32_t offset_bytes, const void *offsets,
+                          const uint8_t *data, const acu_array *nulls_of,
+                          const acu_array *indices, acu_dtype index_dtype, int32_t check_bounds,
+                          void *out_offsets, uint8_t *out_data, int64_t out_data_capacity,
+                          int64_t *out_data_len, acu_array_out *out_nulls);
+
+/* ------------------------------------------------------------------------- */
+/* numeric — arrow-arith/src/numeric.rs, arity.rs                            */
+/* ------------------------------------------------------------------------- */
+/* add/add_wrapping/sub/sub_wrapping/mul/mul_wrapping/div/rem (numeric.rs:36-81).
+ * a and b have native type `dtype`; either may be a scalar (is_scalar, len 1).
+ * Floats: every op is the IEEE single operation (no FMA contraction), never errors.
+ * Integers: wrapping ops via `binary` (op evaluated at every slot), checked ops via
+ * `try_binary` (zero under nulls, first failing valid index reported)
+ * (arity.rs:104-135, :254-299). Length mismatch => ACU_ERR_COMPUTE. */
+acu_status acu_arith(acu_ctx *ctx, acu_dtype dtype, acu_arith_op op, const acu_array *a,
+                     const acu_array *b, acu_array_out *out);
+/* neg (checked != 0) / neg_wrapping (numeric.rs:103-186). */
+acu_status acu_neg(acu_ctx *ctx, acu_dtype dtype, int32_t checked, const acu_array *a,
+                   acu_array_out *out);
+
+/* ------------------------------------------------------------------------- */
+/* cmp — arrow-ord/src/cmp.rs                                                */
+/* ------------------------------------------------------------------------- */
+/* eq/neq/lt/lt_eq/gt/gt_eq/distinct/not_distinct (cmp.rs:79-202). Result is a boolean
+ * array: out->values = bit-packed results. Floats compare by IEEE-754 totalOrder
+ * (arrow-array/src/arithmetic.rs:400-410). */
+acu_status acu_cmp(acu_ctx *ctx, acu_dtype dtype, acu_cmp_op op, const acu_array *a,
+                   const acu_array *b, acu_array_out *out);
+
+/* ------------------------------------------------------------------------- */
+/* cast — arrow-cast/src/cast/mod.rs                                         */
+/* ------------------------------------------------------------------------- */
+/* cast_numeric_arrays (mod.rs:2550-2614). safe != 0 => numeric_cast (unrepresentable
+ * value -> null, output always has a validity buffer: primitive_array.rs:1065-1103);
+ * safe == 0 => try_numeric_cast (ACU_ERR_CAST "Can't cast value {v} to type {T}"). */
+acu_status acu_cast_numeric(acu_ctx *ctx, acu_dtype from, acu_dtype to, int32_t safe,
+                            const acu_array *a, acu_array_out *out);
+
+/* ------------------------------------------------------------------------- */
+/* aggregate — arrow-arith/src/aggregate.rs                                  */
+/* ------------------------------------------------------------------------- */
+/* sum/min/max (aggregate.rs:943,1012,1027): *out_bits = the native result's bit
+ * pattern (zero-extended), *out_valid_count = number of non-null rows; the reference
+ * returns None iff out_valid_count == 0 (aggregate.rs:320-323). */
+acu_status acu_aggregate(acu_ctx *ctx, acu_dtype dtype, acu_agg_op op, const acu_array *a,
+                         uint64_t *out_bits, int64_t *out_valid_count);
+
+/* ------------------------------------------------------------------------- */
+/* multi-GPU: row-range shards, NCCL only for the final scalar reduce        */
+/* ------------------------------------------------------------------------- */
+#define ACU_NCCL_UNIQUE_ID_BYTES 128
+acu_status acu_comm_get_unique_id(uint8_t out_id[ACU_NCCL_UNIQUE_ID_BYTES]);
+acu_status acu_comm_init(acu_ctx *ctx, const uint8_t id[ACU_NCCL_UNIQUE_ID_BYTES], int32_t rank,
+                         int32_t world_size);
+acu_status acu_comm_destroy(acu_ctx *ctx);
+/* All-reduce `n` per-shard partial aggregates of one (dtype, op) in one NCCL call.
+ * partial_bits[i] / valid_counts[i] are what acu_aggregate returned on this rank;
+ * on return they hold the global result. Float min/max are reduced on their
+ * totalOrder integer keys (NCCL's float min/max are IEEE, not totalOrder). */
+acu_status acu_comm_allreduce_aggregates(acu_ctx *ctx, acu_dtype dtype, acu_agg_op op,
+                                         uint64_t *partial_bits, int64_t *valid_counts,
+                                         int32_t n);
+/* Sum int64 scalars across ranks (row counts, null counts). */
+acu_status acu_comm_allreduce_i64_sum(acu_ctx *ctx, int64_t *values, int32_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARROW_CUDA_H */

@@ -1,0 +1,216 @@
+"""ctypes wrapper of oracle/liboracle.so with the same method names as acu.Context.
+
+TEST INFRASTRUCTURE: the oracle is the CPU restatement of the reference (see oracle/oracle.cpp);
+it is the checker, never the thing measured or shipped.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import acu
+from acu import _abi as abi
+from acu import BOOL, HostArray, ArrowError, bitmap_bytes
+
+ORACLE_DIR = os.path.join(abi.REPO, "oracle")
+ORACLE_LIB = os.path.join(ORACLE_DIR, "liboracle.so")
+
+P = C.POINTER
+vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
+
+
+def build_oracle():
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True)
+
+
+class Oracle:
+    def __init__(self):
+        if not os.path.exists(ORACLE_LIB):
+            build_oracle()
+        lib = C.CDLL(ORACLE_LIB)
+        lib.orc_last_error.restype = P(abi.ErrorDetail)
+        lib.orc_last_error.argtypes = []
+        sigs = {
+            "orc_bitmap_count": [vp, i64, vp, i64, i64, P(i64)],
+            "orc_filter_primitive": [P(abi.Array), i32, P(abi.Array), P(abi.ArrayOut), P(i64), P(i32)],
+            "orc_filter_boolean": [P(abi.Array), P(abi.Array), P(abi.ArrayOut), P(i64)],
+            "orc_filter_bytes": [P(abi.Array), i32, vp, vp, P(abi.Array), vp, vp, i64, P(i64), P(abi.ArrayOut), P(i64)],
+            "orc_take_primitive": [i32, P(abi.Array), P(abi.Array), i32, i32, P(abi.ArrayOut)],
+            "orc_take_boolean": [P(abi.Array), P(abi.Array), i32, i32, P(abi.ArrayOut)],
+            "orc_take_bytes": [i32, vp, vp, P(abi.Array), P(abi.Array), i32, i32, vp, vp, i64, P(i64), P(abi.ArrayOut)],
+            "orc_arith": [i32, i32, P(abi.Array), P(abi.Array), P(abi.ArrayOut)],
+            "orc_neg": [i32, i32, P(abi.Array), P(abi.ArrayOut)],
+            "orc_cmp": [i32, i32, P(abi.Array), P(abi.Array), P(abi.ArrayOut)],
+            "orc_cast_numeric": [i32, i32, i32, P(abi.Array), P(abi.ArrayOut)],
+            "orc_aggregate": [i32, i32, P(abi.Array), i32, P(u64), P(i64)],
+            "orc_generate_values": [i32, u64, i64, u64, vp, i64],
+            "orc_generate_bits": [u64, i64, C.c_double, vp, i64],
+        }
+        for name, args in sigs.items():
+            fn = getattr(lib, name)
+            fn.restype = i32
+            fn.argtypes = args
+        self.lib = lib
+
+    # ------------------------------------------------------------------------------------
+    def check(self, st):
+        if st != abi.OK:
+            d = self.lib.orc_last_error().contents
+            raise ArrowError(st, d.message.decode(), d.index, d)
+
+    @staticmethod
+    def _out(nbytes_values, n_rows):
+        out = abi.ArrayOut()
+        vals = np.zeros(nbytes_values + 16, dtype=np.uint8)
+        valid = np.zeros(bitmap_bytes(n_rows) + 8, dtype=np.uint8)
+        out.values = vals.ctypes.data
+        out.validity = valid.ctypes.data
+        return out, vals, valid
+
+    @staticmethod
+    def _result(out, vals, valid, dtype):
+        n = out.len
+        if dtype == BOOL:
+            v = vals[: bitmap_bytes(n)].copy()
+        else:
+            v = vals[: n * abi.DTYPE_SIZE[dtype]].copy().view(acu.NP_DTYPES[dtype])
+        validity = valid[: bitmap_bytes(n)].copy() if out.has_validity else None
+        return HostArray(dtype, v, n, validity, 0, 0, out.null_count if out.has_validity else 0)
+
+    # -- filter ----------------------------------------------------------------------------
+    def filter(self, values, predicate):
+        cap = max(values.length, predicate.length)
+        out, vals, valid = self._out(cap * values.width(), cap)
+        pd, vd = acu.host_descriptor(predicate), acu.host_descriptor(values)
+        cnt = i64(0)
+        if values.dtype == BOOL:
+            self.check(self.lib.orc_filter_boolean(C.byref(pd), C.byref(vd), C.byref(out), C.byref(cnt)))
+        else:
+            strat = i32(0)
+            self.check(self.lib.orc_filter_primitive(C.byref(pd), values.width(), C.byref(vd), C.byref(out), C.byref(cnt), C.byref(strat)))
+        return self._result(out, vals, valid, values.dtype)
+
+    def filter_plan(self, predicate):
+        out, vals, valid = self._out(predicate.length, predicate.length)
+        dummy = HostArray(acu.U8, np.zeros(predicate.length + 1, np.uint8), predicate.length)
+        pd, vd = acu.host_descriptor(predicate), acu.host_descriptor(dummy)
+        cnt, strat = i64(0), i32(0)
+        self.check(self.lib.orc_filter_primitive(C.byref(pd), 1, C.byref(vd), C.byref(out), C.byref(cnt), C.byref(strat)))
+        return cnt.value, strat.value
+
+    def filter_bytes(self, offsets, data, nulls_of, predicate):
+        ob = offsets.dtype.itemsize
+        n = predicate.length
+        out, vals, valid = self._out(0, n)
+        out_off = np.zeros(n + 2, dtype=offsets.dtype)
+        out_data = np.zeros(len(data) + 16, dtype=np.uint8)
+        pd, nd = acu.host_descriptor(predicate), acu.host_descriptor(nulls_of)
+        total, cnt = i64(0), i64(0)
+        self.check(self.lib.orc_filter_bytes(C.byref(pd), ob, offsets.ctypes.data, data.ctypes.data, C.byref(nd),
+                                             out_off.ctypes.data, out_data.ctypes.data, len(data), C.byref(total),
+                                             C.byref(out), C.byref(cnt)))
+        m = out.len
+        validity = valid[: bitmap_bytes(m)].copy() if out.has_validity else None
+        return out_off[: m + 1].copy(), out_data[: total.value].copy(), HostArray(acu.U8, np.zeros(0, np.uint8), m, validity, 0, 0,
+                                                                                  out.null_count if out.has_validity else 0)
+
+    # -- take ------------------------------------------------------------------------------
+    def take(self, values, indices, check_bounds=False):
+        out, vals, valid = self._out(indices.length * values.width(), indices.length)
+        vd, idd = acu.host_descriptor(values), acu.host_descriptor(indices)
+        if values.dtype == BOOL:
+            self.check(self.lib.orc_take_boolean(C.byref(vd), C.byref(idd), indices.dtype, int(check_bounds), C.byref(out)))
+        else:
+            self.check(self.lib.orc_take_primitive(values.width(), C.byref(vd), C.byref(idd), indices.dtype, int(check_bounds), C.byref(out)))
+        return self._result(out, vals, valid, values.dtype)
+
+    def take_bytes(self, offsets, data, nulls_of, indices, check_bounds=False):
+        ob = offsets.dtype.itemsize
+        m = indices.length
+        out, vals, valid = self._out(0, m)
+        out_off = np.zeros(m + 2, dtype=offsets.dtype)
+        nd, idd = acu.host_descriptor(nulls_of), acu.host_descriptor(indices)
+        total = i64(0)
+        self.check(self.lib.orc_take_bytes(ob, offsets.ctypes.data, data.ctypes.data, C.byref(nd), C.byref(idd), indices.dtype,
+                                           int(check_bounds), out_off.ctypes.data, None, 0, C.byref(total), C.byref(out)))
+        out_data = np.zeros(total.value + 16, dtype=np.uint8)
+        self.check(self.lib.orc_take_bytes(ob, offsets.ctypes.data, data.ctypes.data, C.byref(nd), C.byref(idd), indices.dtype,
+                                           int(check_bounds), out_off.ctypes.data, out_data.ctypes.data, total.value, C.byref(total), C.byref(out)))
+        validity = valid[: bitmap_bytes(m)].copy() if out.has_validity else None
+        return out_off[: m + 1].copy(), out_data[: total.value].copy(), HostArray(acu.U8, np.zeros(0, np.uint8), m, validity, 0, 0,
+                                                                                  out.null_count if out.has_validity else 0)
+
+    # -- numeric -----------------------------------------------------------------------------
+    def arith(self, op, a, b):
+        n = b.length if a.is_scalar and not b.is_scalar else a.length
+        n = max(n, a.length if not a.is_scalar else 0, b.length if not b.is_scalar else 0, 1)
+        out, vals, valid = self._out(n * a.width(), n)
+        ad, bd = acu.host_descriptor(a), acu.host_descriptor(b)
+        self.check(self.lib.orc_arith(a.dtype, op, C.byref(ad), C.byref(bd), C.byref(out)))
+        return self._result(out, vals, valid, a.dtype)
+
+    def add(self, a, b): return self.arith(abi.ADD, a, b)
+    def add_wrapping(self, a, b): return self.arith(abi.ADD_WRAPPING, a, b)
+    def sub(self, a, b): return self.arith(abi.SUB, a, b)
+    def sub_wrapping(self, a, b): return self.arith(abi.SUB_WRAPPING, a, b)
+    def mul(self, a, b): return self.arith(abi.MUL, a, b)
+    def mul_wrapping(self, a, b): return self.arith(abi.MUL_WRAPPING, a, b)
+    def div(self, a, b): return self.arith(abi.DIV, a, b)
+    def rem(self, a, b): return self.arith(abi.REM, a, b)
+
+    def neg(self, a, checked=True):
+        out, vals, valid = self._out(a.length * a.width(), a.length)
+        ad = acu.host_descriptor(a)
+        self.check(self.lib.orc_neg(a.dtype, int(checked), C.byref(ad), C.byref(out)))
+        return self._result(out, vals, valid, a.dtype)
+
+    def neg_wrapping(self, a): return self.neg(a, checked=False)
+
+    # -- cmp ---------------------------------------------------------------------------------
+    def cmp(self, op, a, b):
+        n = max(a.length, b.length, 1)
+        out, vals, valid = self._out(bitmap_bytes(n), n)
+        ad, bd = acu.host_descriptor(a), acu.host_descriptor(b)
+        self.check(self.lib.orc_cmp(a.dtype, op, C.byref(ad), C.byref(bd), C.byref(out)))
+        return self._result(out, vals, valid, BOOL)
+
+    def eq(self, a, b): return self.cmp(abi.EQ, a, b)
+    def neq(self, a, b): return self.cmp(abi.NEQ, a, b)
+    def lt(self, a, b): return self.cmp(abi.LT, a, b)
+    def lt_eq(self, a, b): return self.cmp(abi.LT_EQ, a, b)
+    def gt(self, a, b): return self.cmp(abi.GT, a, b)
+    def gt_eq(self, a, b): return self.cmp(abi.GT_EQ, a, b)
+    def distinct(self, a, b): return self.cmp(abi.DISTINCT, a, b)
+    def not_distinct(self, a, b): return self.cmp(abi.NOT_DISTINCT, a, b)
+
+    # -- cast / aggregate ----------------------------------------------------------------------
+    def cast(self, a, to_dtype, safe=True):
+        out, vals, valid = self._out(a.length * abi.DTYPE_SIZE[to_dtype], a.length)
+        ad = acu.host_descriptor(a)
+        self.check(self.lib.orc_cast_numeric(a.dtype, to_dtype, int(safe), C.byref(ad), C.byref(out)))
+        return self._result(out, vals, valid, to_dtype)
+
+    def aggregate(self, op, a, vector_bytes=16):
+        bits, cnt = u64(0), i64(0)
+        ad = acu.host_descriptor(a)
+        self.check(self.lib.orc_aggregate(a.dtype, op, C.byref(ad), vector_bytes, C.byref(bits), C.byref(cnt)))
+        if cnt.value == 0:
+            return None
+        raw = np.array([bits.value], dtype=np.uint64).view(np.uint8)[: abi.DTYPE_SIZE[a.dtype]]
+        return raw.view(acu.NP_DTYPES[a.dtype])[0].item()
+
+    def sum(self, a, vector_bytes=16): return self.aggregate(abi.SUM, a, vector_bytes)
+    def min(self, a): return self.aggregate(abi.MIN, a)
+    def max(self, a): return self.aggregate(abi.MAX, a)
+
+    # -- generators ------------------------------------------------------------------------------
+    def generate_values(self, kind, seed, first_row, param, n, np_dtype):
+        out = np.zeros(n, dtype=np_dtype)
+        self.check(self.lib.orc_generate_values(kind, seed, first_row, param, out.ctypes.data, n))
+        return out
+
+    def generate_bits(self, seed, first_row, p, n):
+        out = np.zeros(bitmap_bytes(n) + 8, dtype=np.uint8)
+        self.check(self.lib.orc_generate_bits(seed, first_row, p, out.ctypes.data, n))
+        return out
