@@ -38,6 +38,9 @@ SUM, MIN, MAX = range(3)
 FILTER_NONE, FILTER_ALL, FILTER_INDEX, FILTER_SLICES = range(4)
 
 NCCL_UNIQUE_ID_BYTES = 128
+# acu_kernel_class
+K_ARITH, K_CMP, K_CAST, K_FILTER, K_FILTER_PLAN, K_TAKE, K_REDUCE, K_BYTES = range(8)
+KERNEL_CLASS_NAMES = ["arith", "cmp", "cast", "filter", "filter_plan", "take", "reduce", "bytes"]
 
 
 class ErrorDetail(C.Structure):
@@ -105,11 +108,16 @@ PROTOTYPES = {
     "acu_bytes_allocated": (i64, [vp]),
     "acu_timer_start": (i32, [vp]),
     "acu_timer_stop": (i32, [vp, P(f32)]),
+    "acu_timer_start_slot": (i32, [vp, i32]),
+    "acu_timer_stop_slot": (i32, [vp, i32, P(f32)]),
+    "acu_kernel_stats": (i32, [vp, i32, P(f64), P(i64)]),
+    "acu_kernel_stats_reset": (i32, [vp]),
     "acu_generate_values": (i32, [vp, i32, u64, i64, u64, vp, i64]),
     "acu_generate_bits": (i32, [vp, u64, i64, f64, vp, i64]),
     "acu_bitmap_count": (i32, [vp, vp, i64, vp, i64, i64, P(i64)]),
     "acu_filter_plan_create": (i32, [vp, P(Array), P(vp)]),
     "acu_filter_plan_destroy": (None, [vp, vp]),
+    "acu_filter_plan_indices": (i32, [vp, vp, i32, vp]),
     "acu_filter_plan_count": (i64, [vp]),
     "acu_filter_plan_len": (i64, [vp]),
     "acu_filter_plan_strategy": (i32, [vp]),

@@ -147,34 +147,29 @@ __global__ void __launch_bounds__(256) k_copy_bytes(const void *offs, int ob, co
 }
 
 // Indices(Vec<usize>) of FilterBuilder::optimize (filter.rs:285-298): selected row ids, u64.
-__global__ void __launch_bounds__(256) k_plan_indices(const uint64_t *__restrict__ mask, const uint32_t *__restrict__ tile_local,
-                                                      const uint32_t *__restrict__ tile_count,
-                                                      const uint64_t *__restrict__ chunk_offset, int64_t n_tiles,
-                                                      uint64_t *__restrict__ out_idx) {
+template <class OutT>
+__global__ void __launch_bounds__(256) k_plan_indices(const uint64_t *__restrict__ mask, const uint64_t *__restrict__ tile_off,
+                                                      int64_t n_words_padded, OutT *__restrict__ out_idx) {
+  // one lane per mask word; a warp covers 32 consecutive words (= two 1024-row tiles)
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t t = warp; t < n_tiles; t += nwarps) {
-    if (tile_count[t] == 0) continue;
-    const uint64_t out0 = chunk_offset[t / PLAN_SCAN_CHUNK] + tile_local[t];
-    const uint64_t m0 = mask[t * PLAN_TILE_WORDS + 2 * lane], m1 = mask[t * PLAN_TILE_WORDS + 2 * lane + 1];
-    const uint32_t c0 = __popcll(m0), c1 = __popcll(m1);
-    uint32_t incl = c0 + c1;
+  for (int64_t w0 = warp * 32; w0 < n_words_padded; w0 += nwarps * 32) {
+    uint64_t m = __ldg(mask + w0 + lane);
+    const uint32_t c = __popcll(m);
+    uint32_t incl = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       uint32_t y = __shfl_up_sync(ACU_FULL_MASK, incl, o);
       if (lane >= o) incl += y;
     }
-    uint64_t k = out0 + incl - (c0 + c1);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      uint64_t m = h ? m1 : m0;
-      const uint64_t row = (uint64_t)(t * PLAN_TILE_WORDS + 2 * lane + h) << 6;
-      while (m) {
-        const int b = __ffsll((long long)m) - 1;
-        m &= m - 1;
-        out_idx[k++] = row + b;
-      }
+    if (__shfl_sync(ACU_FULL_MASK, incl, 31) == 0) continue;
+    uint64_t k = __ldg(tile_off + (w0 >> 4)) + incl - c;
+    const uint64_t row = (uint64_t)(w0 + lane) << 6;
+    while (m) {
+      const int b = __ffsll((long long)m) - 1;
+      m &= m - 1;
+      out_idx[k++] = (OutT)(row + b);
     }
   }
 }
@@ -215,7 +210,7 @@ acu_status gather_bytes(acu_ctx *ctx, int32_t ob, const void *offsets, const uin
     if (*out_len > out_cap)
       return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, (uint64_t)*out_len,
                       "output data capacity %lld < required %lld", (long long)out_cap, (long long)*out_len);
-    ACU_LAUNCH(ctx, k_copy_bytes, grid, 256, 0, offsets, (int)ob, data, idx, kind, m, len, out_data);
+    ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_copy_bytes, grid, 256, 0, offsets, (int)ob, data, idx, kind, m, len, out_data);
     ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   return ACU_OK;
@@ -228,6 +223,26 @@ acu_status zero_first_offset(acu_ctx *ctx, void *out_offsets, int ob) {
 }
 
 }  // namespace
+
+extern "C" acu_status acu_filter_plan_indices(acu_ctx *ctx, const acu_filter_plan *plan, acu_dtype index_dtype,
+                                              void *out_indices) {
+  if (index_dtype != ACU_U32 && index_dtype != ACU_U64)
+    return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "plan indices must be UInt32 or UInt64");
+  if (index_dtype == ACU_U32 && acu_filter_plan_len(plan) > (int64_t)UINT32_MAX)
+    return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "predicate too long for UInt32 indices");
+  if (acu_filter_plan_count(plan) == 0) return ACU_OK;
+  const int64_t nwp = acu_plan_n_words_padded(plan);
+  const int grid = acu_grid(ctx, (nwp / 32 + 7) / 8, 8);
+  if (index_dtype == ACU_U32)
+    ACU_LAUNCH_TIMED(ctx, ACU_K_FILTER_PLAN, k_plan_indices<uint32_t>, grid, 256, 0, acu_plan_mask(plan), acu_plan_tile_off(plan),
+                     nwp, static_cast<uint32_t *>(out_indices));
+  else
+    ACU_LAUNCH_TIMED(ctx, ACU_K_FILTER_PLAN, k_plan_indices<uint64_t>, grid, 256, 0, acu_plan_mask(plan), acu_plan_tile_off(plan),
+                     nwp, static_cast<uint64_t *>(out_indices));
+  ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  acu_kstats_drain(ctx);
+  return ACU_OK;
+}
 
 extern "C" acu_status acu_take_bytes(acu_ctx *ctx, int32_t offset_bytes, const void *offsets, const uint8_t *data,
                                      const acu_array *nulls_of, const acu_array *indices, acu_dtype index_dtype,
@@ -266,10 +281,9 @@ extern "C" acu_status acu_filter_bytes(acu_ctx *ctx, const acu_filter_plan *plan
   ACU_TRY(acu_malloc(ctx, (size_t)count * 8, &idx_mem));
   acu_status st = ACU_OK;
   do {
-    const int64_t n_tiles = acu_plan_n_tiles(plan);
-    k_plan_indices<<<acu_grid(ctx, (n_tiles + 7) / 8, 8), 256, 0, ctx->stream>>>(
-        acu_plan_mask(plan), acu_plan_tile_local(plan), acu_plan_tile_count(plan), acu_plan_chunk_offset(plan), n_tiles,
-        static_cast<uint64_t *>(idx_mem));
+    const int64_t nwp = acu_plan_n_words_padded(plan);
+    k_plan_indices<uint64_t><<<acu_grid(ctx, (nwp / 32 + 7) / 8, 8), 256, 0, ctx->stream>>>(
+        acu_plan_mask(plan), acu_plan_tile_off(plan), nwp, static_cast<uint64_t *>(idx_mem));
     ctx->launches++;
     if (acu_filter_plan_strategy(plan) == ACU_FILTER_ALL) {  // values.slice(0, count)
       out_nulls->has_validity = nulls_of->validity != nullptr;

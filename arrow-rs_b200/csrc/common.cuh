@@ -44,7 +44,21 @@ struct acu_ctx {
   // NCCL (loaded with dlopen, see comm.cu)
   void *nccl_comm = nullptr;
   int rank = 0, world = 1;
+  // timers (acu_timer_*_slot) and per-kernel-class device time (acu_kernel_stats)
+  cudaEvent_t tev[ACU_TIMER_SLOTS][2] = {};
+  static constexpr int KEV_PAIRS = 64;
+  cudaEvent_t kev[KEV_PAIRS][2] = {};
+  int kev_class[KEV_PAIRS] = {};
+  int kev_pending = 0;
+  double kstat_ms[ACU_K_CLASSES] = {};
+  int64_t kstat_n[ACU_K_CLASSES] = {};
 };
+
+// Drain the timed-launch events (call after the stream has been synchronised).
+void acu_kstats_drain(acu_ctx *ctx);
+// Begin / end a timed kernel launch of class `cls` (records a CUDA event pair on the stream).
+int acu_kstats_begin(acu_ctx *ctx, int cls);
+void acu_kstats_end(acu_ctx *ctx, int slot);
 
 acu_status acu_fail(acu_ctx *ctx, acu_status st, int64_t index, uint64_t lhs, uint64_t rhs,
                     uint64_t len, const char *fmt, ...) __attribute__((format(printf, 7, 8)));
@@ -72,6 +86,17 @@ int64_t acu_resolve_null_count(acu_ctx *ctx, const acu_array *a, acu_status *st)
     kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);               \
     (ctx)->launches++;                                                             \
     cudaError_t _e = cudaGetLastError();                                           \
+    if (_e != cudaSuccess) return acu_cuda_fail((ctx), _e, "launch " #kernel);     \
+  } while (0)
+
+// Same as ACU_LAUNCH, bracketed by an event pair accumulated into class `cls`.
+#define ACU_LAUNCH_TIMED(ctx, cls, kernel, grid, block, smem, ...)                 \
+  do {                                                                             \
+    int _slot = acu_kstats_begin((ctx), (cls));                                    \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);               \
+    (ctx)->launches++;                                                             \
+    cudaError_t _e = cudaGetLastError();                                           \
+    acu_kstats_end((ctx), _slot);                                                  \
     if (_e != cudaSuccess) return acu_cuda_fail((ctx), _e, "launch " #kernel);     \
   } while (0)
 

@@ -1,0 +1,530 @@
+// compact.cu — arrow-select/src/filter.rs on the device (stream compaction).
+//
+//   FilterBuilder::new/optimize/build  (filter.rs:254-324)  -> acu_filter_plan_create
+//   FilterPredicate::filter            (filter.rs:449-452)  -> acu_filter_primitive / _boolean
+//   filter_native / filter_bits / filter_nulls (filter.rs:512-533, :680-788)
+//
+// Design (HBM-bound):
+//   plan:     one pass over the predicate bits (N/8 bytes): mask = values & validity
+//             normalised to bit offset 0, popcount per 1024-row tile, two-level exclusive scan
+//             -> tile_off[t] = first output row of tile t (u64). The plan is reused by every
+//             column of a RecordBatch (FilterPredicate::filter_record_batch, filter.rs:459-478).
+//   values:   k_filter_values<W>: warp-centric, no CTA barrier. A warp owns a 1024-row tile;
+//             lanes 0..15 hold the tile's 16 mask words (+ exclusive popcount prefix), the
+//             NEXT tile's words/offsets are prefetched while this tile's values are in flight.
+//             Each lane owns 16-byte chunks; its 128-bit load is PREDICATED on "this chunk
+//             holds a selected row", so at low selectivity most 32-B DRAM sectors are never
+//             fetched (real traffic < algorithmic bytes). rank = word prefix + popc(mask below)
+//             -> stored straight to its final position (neighbouring ranks land in the same
+//             sectors and merge in L2).
+//   validity: k_compress_bits: software PEXT — one lane per 64-bit mask word extracts the
+//             selected source bits, a warp scan places them, a warp-private shared-memory
+//             window assembles output words (atomicOr only on the two boundary words), and
+//             the popcount gives filter_nulls' null count. Also used for boolean VALUES
+//             (filter_bits / filter_boolean).
+#include "bitmap.cuh"
+#include "internal.cuh"
+
+#define TILE_ROWS 1024
+#define TILE_WORDS (TILE_ROWS / 64)
+#define SCAN_CHUNK 4096  // tiles per scan block
+
+struct acu_filter_plan {
+  int64_t len = 0;
+  int64_t count = 0;
+  int32_t strategy = ACU_FILTER_NONE;
+  int64_t n_tiles = 0;
+  uint64_t *mask = nullptr;       // n_tiles * TILE_WORDS words padded to a multiple of 32, zero padded
+  uint64_t *tile_off = nullptr;   // n_tiles + 1 exclusive output offsets (padded)
+  uint32_t *tile_count = nullptr; // scratch of the scan
+  uint64_t *chunk_total = nullptr;
+  void *storage = nullptr;
+};
+
+namespace {
+
+// ---- plan kernels ----------------------------------------------------------------------
+// One lane per mask word; a warp covers two tiles (2 x 16 words).
+__global__ void __launch_bounds__(256) k_plan_mask(const uint8_t *__restrict__ pv, int64_t poff,
+                                                   const uint8_t *__restrict__ nv, int64_t noff,
+                                                   int64_t len, int64_t n_words_padded, uint64_t *__restrict__ mask,
+                                                   uint32_t *__restrict__ tile_count, int64_t n_tiles) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w0 = warp * 32; w0 < n_words_padded; w0 += nwarps * 32) {
+    const int64_t w = w0 + lane;
+    const int64_t row = w << 6;
+    uint64_t m = ld_bits64(pv, poff + row, poff + len);
+    if (nv) m &= ld_bits64(nv, noff + row, noff + len);  // prep_null_mask_filter
+    mask[w] = m;
+    unsigned c = __popcll(m);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) c += __shfl_xor_sync(ACU_FULL_MASK, c, o);  // sum inside each 16-lane half
+    const int64_t t = w >> 4;
+    if ((lane & 15) == 0 && t < n_tiles) tile_count[t] = c;
+  }
+}
+
+// Block-wide exclusive scan of up to SCAN_CHUNK tile counts (1024 threads x 4) -> tile_off (chunk-local)
+__global__ void __launch_bounds__(1024) k_plan_scan_chunks(const uint32_t *__restrict__ tile_count, int64_t n_tiles,
+                                                           uint64_t *__restrict__ tile_off,
+                                                           uint64_t *__restrict__ chunk_total) {
+  __shared__ uint32_t warp_tot[32];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_CHUNK + (int64_t)threadIdx.x * 4;
+  uint32_t c[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) c[k] = (base + k < n_tiles) ? tile_count[base + k] : 0u;
+  uint32_t mine = c[0] + c[1] + c[2] + c[3];
+  uint32_t incl = mine;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(ACU_FULL_MASK, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) warp_tot[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t w = warp_tot[lane], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(ACU_FULL_MASK, wi, o);
+      if (lane >= o) wi += y;
+    }
+    warp_tot[lane] = wi - w;  // exclusive
+    if (lane == 31) chunk_total[blockIdx.x] = wi;
+  }
+  __syncthreads();
+  uint32_t excl = warp_tot[wid] + incl - mine;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (base + k < n_tiles) tile_off[base + k] = excl;
+    excl += c[k];
+  }
+}
+
+// Single block: exclusive scan of the chunk totals (u64), grand total -> res[RES_COUNT].
+__global__ void __launch_bounds__(1024) k_plan_scan_top(uint64_t *__restrict__ chunk_total, int64_t n_chunks,
+                                                        unsigned long long *__restrict__ res) {
+  __shared__ uint64_t warp_tot[32];
+  __shared__ uint64_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int64_t base = 0; base < n_chunks; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    uint64_t v = i < n_chunks ? chunk_total[i] : 0ull, incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint64_t y = __shfl_up_sync(ACU_FULL_MASK, incl, o);
+      if (lane >= o) incl += y;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      uint64_t w = warp_tot[lane], wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint64_t y = __shfl_up_sync(ACU_FULL_MASK, wi, o);
+        if (lane >= o) wi += y;
+      }
+      warp_tot[lane] = wi - w;
+    }
+    __syncthreads();
+    const uint64_t carry = carry_s;
+    if (i < n_chunks) chunk_total[i] = carry + warp_tot[wid] + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + warp_tot[31] + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) res[RES_COUNT] = carry_s;
+}
+
+// tile_off[t] += chunk offset; tile_off[n_tiles .. padded) = total
+__global__ void __launch_bounds__(256) k_plan_finalize(uint64_t *__restrict__ tile_off, int64_t n_tiles, int64_t n_padded,
+                                                       const uint64_t *__restrict__ chunk_off,
+                                                       const unsigned long long *__restrict__ res) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_padded; t += stride)
+    tile_off[t] = t < n_tiles ? tile_off[t] + chunk_off[t / SCAN_CHUNK] : res[RES_COUNT];
+}
+
+// ---- value compaction ------------------------------------------------------------------
+struct FilterArgs {
+  const uint8_t *values;
+  uint8_t *out;
+  const uint64_t *mask;
+  const uint64_t *tile_off;
+  int64_t n_tiles;
+  int aligned16;
+};
+
+template <int W>
+__global__ void __launch_bounds__(256, 4) k_filter_values(const FilterArgs a) {
+  constexpr int CPT = TILE_ROWS * W / 16;   // 16-byte chunks per tile
+  constexpr int ITERS = CPT / 32;           // chunk rounds per warp
+  constexpr int BATCH = ITERS < 8 ? ITERS : 8;
+  constexpr int RPC = W <= 16 ? 16 / W : 1; // rows per chunk (W = 32: two chunks per row)
+  constexpr int CPR = W <= 16 ? 1 : W / 16; // chunks per row
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+
+  int64_t t = warp;
+  uint64_t m_next = 0, off_next = 0, end_next = 0;
+  if (t < a.n_tiles) {
+    if (lane < TILE_WORDS) m_next = __ldg(a.mask + t * TILE_WORDS + lane);
+    off_next = __ldg(a.tile_off + t);
+    end_next = __ldg(a.tile_off + t + 1);
+  }
+  for (; t < a.n_tiles; t += nwarps) {
+    const uint64_t m = m_next, out0 = off_next, cnt = end_next - off_next;
+    const int64_t tn = t + nwarps;
+    if (tn < a.n_tiles) {  // prefetch the next tile's mask words + offsets
+      m_next = (lane < TILE_WORDS) ? __ldg(a.mask + tn * TILE_WORDS + lane) : 0ull;
+      off_next = __ldg(a.tile_off + tn);
+      end_next = __ldg(a.tile_off + tn + 1);
+    }
+    if (cnt == 0) continue;  // warp-uniform
+    // exclusive popcount prefix over the 16 mask words (lanes >= 16 hold 0)
+    const uint32_t c = __popcll(m);
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < TILE_WORDS; o <<= 1) {
+      uint32_t y = __shfl_up_sync(ACU_FULL_MASK, incl, o);
+      if (lane >= o) incl += y;
+    }
+    const uint32_t pref = incl - c;
+    const uint8_t *src = a.values + (size_t)t * TILE_ROWS * W;
+    uint8_t *dst = a.out + (size_t)out0 * W;
+#pragma unroll 1
+    for (int b0 = 0; b0 < ITERS; b0 += BATCH) {
+      uint4 v[BATCH];
+      uint32_t bits[BATCH];
+      uint32_t rank[BATCH];
+#pragma unroll
+      for (int j = 0; j < BATCH; ++j) {
+        const int cidx = (b0 + j) * 32 + lane;  // chunk inside the tile
+        const int r = cidx * RPC / CPR;          // first row of the chunk
+        const uint64_t word = __shfl_sync(ACU_FULL_MASK, m, r >> 6);
+        const uint32_t wp = __shfl_sync(ACU_FULL_MASK, pref, r >> 6);
+        bits[j] = (uint32_t)(word >> (r & 63)) & ((1u << RPC) - 1u);
+        rank[j] = wp + __popcll(word & ((1ull << (r & 63)) - 1ull));
+        if (bits[j]) {
+          if (a.aligned16) {
+            v[j] = ld_stream16(src + (size_t)cidx * 16);
+          } else {  // sliced array whose base is not 16-B aligned: 8-byte or element-wise loads
+            if constexpr (W >= 8) {
+              const uint64_t *p = reinterpret_cast<const uint64_t *>(src + (size_t)cidx * 16);
+              const uint64_t lo = (W > 8 || (bits[j] & 1u)) ? __ldg(p) : 0ull;
+              const uint64_t hi = (W > 8 || (bits[j] & 2u)) ? __ldg(p + 1) : 0ull;
+              v[j] = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+            } else if constexpr (W == 4) {
+              const uint32_t *p = reinterpret_cast<const uint32_t *>(src + (size_t)cidx * 16);
+              v[j].x = (bits[j] & 1u) ? __ldg(p) : 0u;
+              v[j].y = (bits[j] & 2u) ? __ldg(p + 1) : 0u;
+              v[j].z = (bits[j] & 4u) ? __ldg(p + 2) : 0u;
+              v[j].w = (bits[j] & 8u) ? __ldg(p + 3) : 0u;
+            } else {
+              uint8_t *vb = reinterpret_cast<uint8_t *>(&v[j]);
+              const uint8_t *p = src + (size_t)cidx * 16;
+#pragma unroll
+              for (int e = 0; e < 16; ++e) vb[e] = ((bits[j] >> (e / W)) & 1u) ? __ldg(p + e) : (uint8_t)0;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < BATCH; ++j) {
+        if (!bits[j]) continue;
+        if constexpr (W == 8) {
+          uint64_t *o = reinterpret_cast<uint64_t *>(dst) + rank[j];
+          if (bits[j] & 1u) *o++ = (uint64_t)v[j].x | ((uint64_t)v[j].y << 32);
+          if (bits[j] & 2u) *o = (uint64_t)v[j].z | ((uint64_t)v[j].w << 32);
+        } else if constexpr (W == 4) {
+          uint32_t *o = reinterpret_cast<uint32_t *>(dst) + rank[j];
+          if (bits[j] & 1u) *o++ = v[j].x;
+          if (bits[j] & 2u) *o++ = v[j].y;
+          if (bits[j] & 4u) *o++ = v[j].z;
+          if (bits[j] & 8u) *o = v[j].w;
+        } else if constexpr (W == 2) {
+          uint16_t *o = reinterpret_cast<uint16_t *>(dst) + rank[j];
+          const uint16_t *ve = reinterpret_cast<const uint16_t *>(&v[j]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if ((bits[j] >> e) & 1u) *o++ = ve[e];
+        } else if constexpr (W == 1) {
+          uint8_t *o = dst + rank[j];
+          const uint8_t *ve = reinterpret_cast<const uint8_t *>(&v[j]);
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if ((bits[j] >> e) & 1u) *o++ = ve[e];
+        } else {  // W = 16 / 32: whole 16-byte chunks, 8-byte stores (rank*W is 8-B aligned at least)
+          const int half = ((b0 + j) * 32 + lane) % CPR;
+          uint64_t *o = reinterpret_cast<uint64_t *>(dst + (size_t)rank[j] * W + half * 16);
+          o[0] = (uint64_t)v[j].x | ((uint64_t)v[j].y << 32);
+          o[1] = (uint64_t)v[j].z | ((uint64_t)v[j].w << 32);
+        }
+      }
+    }
+  }
+}
+
+// ---- bit compaction (validity / boolean values): software PEXT --------------------------
+// One lane per mask word; a warp covers 32 consecutive words (two tiles).
+__global__ void __launch_bounds__(256) k_compress_bits(const uint8_t *__restrict__ src, int64_t soff, int64_t len,
+                                                       const uint64_t *__restrict__ mask,
+                                                       const uint64_t *__restrict__ tile_off, int64_t n_words_padded,
+                                                       uint32_t *__restrict__ out, unsigned long long *__restrict__ res) {
+  __shared__ uint32_t s_win[8][68];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  unsigned valid_cnt = 0;
+  for (int64_t w0 = warp * 32; w0 < n_words_padded; w0 += nwarps * 32) {
+    const int64_t w = w0 + lane;
+    uint64_t m = __ldg(mask + w);
+    const uint32_t cnt = __popcll(m);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(ACU_FULL_MASK, incl, o);
+      if (lane >= o) incl += y;
+    }
+    const uint32_t total = __shfl_sync(ACU_FULL_MASK, incl, 31);
+    if (total == 0) continue;  // warp-uniform
+    const uint64_t base = __ldg(tile_off + (w0 >> 4));  // first output bit of this 32-word group
+    uint64_t bits = 0;
+    if (m) {
+      const uint64_t v = ld_bits64(src, soff + (w << 6), soff + len);
+      int k = 0;
+      while (m) {  // PEXT: gather the bits of v selected by m
+        const int b = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        bits |= ((v >> b) & 1ull) << k++;
+      }
+    }
+    valid_cnt += __popcll(bits);
+    // assemble in a warp-private window aligned to the first output word
+    const uint32_t lead = (uint32_t)(base & 31);
+    const uint32_t nwords = (lead + total + 31) >> 5;  // <= 65
+    for (uint32_t i = lane; i < nwords; i += 32) s_win[wid][i] = 0;
+    __syncwarp();
+    if (cnt) {
+      const uint32_t p = lead + incl - cnt;  // bit position inside the window
+      const uint32_t sh = p & 31;
+      atomicOr(&s_win[wid][p >> 5], (uint32_t)(bits << sh));
+      if (sh + cnt > 32) {
+        const uint64_t rest = bits >> (32 - sh);  // sh == 0 -> bits >> 32
+        atomicOr(&s_win[wid][(p >> 5) + 1], (uint32_t)rest);
+        if (sh + cnt > 64) atomicOr(&s_win[wid][(p >> 5) + 2], (uint32_t)(rest >> 32));
+      }
+    }
+    __syncwarp();
+    uint32_t *o = out + (base >> 5);
+    for (uint32_t i = lane; i < nwords; i += 32) {
+      const uint32_t word = s_win[wid][i];
+      if (i == 0 || i == nwords - 1) { if (word) atomicOr(o + i, word); }  // shared with neighbouring groups
+      else o[i] = word;
+    }
+    __syncwarp();
+  }
+  if (res) {
+    valid_cnt = warp_sum(valid_cnt);
+    if (lane == 0 && valid_cnt) atomicAdd(res + RES_COUNT, (unsigned long long)valid_cnt);
+  }
+}
+
+acu_status check_len(acu_ctx *ctx, const acu_filter_plan *plan, int64_t values_len) {
+  if (plan->len > values_len)  // filter.rs:536-542
+    return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, (uint64_t)values_len,
+                    "Filter predicate of length %lld is larger than target array of length %lld",
+                    (long long)plan->len, (long long)values_len);
+  return ACU_OK;
+}
+
+// `values.slice(0, count)` nulls for IterationStrategy::All (filter.rs:546)
+acu_status slice_nulls(acu_ctx *ctx, const acu_array *a, int64_t count, acu_array_out *out) {
+  out->has_validity = 0;
+  out->null_count = 0;
+  if (!a->validity || count == 0) { out->has_validity = a->validity != nullptr; return ACU_OK; }
+  ACU_TRY(acu_res_reset(ctx));
+  ACU_TRY(acu_bitmap_and_launch(ctx, a->validity, a->validity_offset, nullptr, 0, count,
+                                reinterpret_cast<uint64_t *>(out->validity), true));
+  ACU_TRY(acu_res_fetch(ctx));
+  out->has_validity = 1;
+  out->null_count = count - (int64_t)ctx->h_res[RES_COUNT];
+  return ACU_OK;
+}
+
+template <int W>
+acu_status launch_filter(acu_ctx *ctx, const FilterArgs &fa) {
+  ACU_LAUNCH_TIMED(ctx, ACU_K_FILTER, (k_filter_values<W>), acu_wave_grid(ctx, k_filter_values<W>, 256, 0, (fa.n_tiles + 7) / 8),
+                   256, 0, fa);
+  return ACU_OK;
+}
+
+// out (zeroed by this call) = bits of `src` selected by the plan; optional popcount into res.
+acu_status launch_compress(acu_ctx *ctx, const acu_filter_plan *plan, const uint8_t *src, int64_t soff, uint8_t *out,
+                           bool count) {
+  const int64_t n_words_padded = ((plan->n_tiles * TILE_WORDS + 31) / 32) * 32;
+  ACU_CUDA(ctx, cudaMemsetAsync(out, 0, acu_bitmap_bytes(plan->count), ctx->stream));
+  ACU_LAUNCH_TIMED(ctx, ACU_K_FILTER, k_compress_bits, acu_wave_grid(ctx, k_compress_bits, 256, 0, (n_words_padded / 32 + 7) / 8),
+                   256, 0, src, soff, plan->len, plan->mask, plan->tile_off, n_words_padded, reinterpret_cast<uint32_t *>(out),
+                   count ? ctx->d_res : nullptr);
+  return ACU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+acu_status acu_filter_plan_create(acu_ctx *ctx, const acu_array *pred, acu_filter_plan **out_plan) {
+  *out_plan = nullptr;
+  acu_filter_plan *plan = new acu_filter_plan();
+  const int64_t len = pred->len;
+  plan->len = len;
+  if (len == 0) { *out_plan = plan; return ACU_OK; }
+  acu_status st;
+  const int64_t nc = acu_resolve_null_count(ctx, pred, &st);
+  if (st != ACU_OK) { delete plan; return st; }
+  const int64_t n_tiles = (len + TILE_ROWS - 1) / TILE_ROWS;
+  const int64_t n_chunks = (n_tiles + SCAN_CHUNK - 1) / SCAN_CHUNK;
+  const int64_t n_words_padded = ((n_tiles * TILE_WORDS + 31) / 32) * 32;
+  const int64_t n_off_padded = n_words_padded / TILE_WORDS + 2;
+  plan->n_tiles = n_tiles;
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t mask_b = up((size_t)n_words_padded * 8), off_b = up((size_t)n_off_padded * 8),
+               cnt_b = up((size_t)n_tiles * 4), ch_b = up((size_t)n_chunks * 8);
+  void *mem = nullptr;
+  st = acu_malloc(ctx, mask_b + off_b + cnt_b + ch_b, &mem);
+  if (st != ACU_OK) { delete plan; return st; }
+  uint8_t *p = static_cast<uint8_t *>(mem);
+  plan->storage = mem;
+  plan->mask = reinterpret_cast<uint64_t *>(p);
+  plan->tile_off = reinterpret_cast<uint64_t *>(p + mask_b);
+  plan->tile_count = reinterpret_cast<uint32_t *>(p + mask_b + off_b);
+  plan->chunk_total = reinterpret_cast<uint64_t *>(p + mask_b + off_b + cnt_b);
+  auto bail = [&](acu_status s) { acu_free(ctx, mem); delete plan; return s; };
+  const uint8_t *nv = (pred->validity && nc > 0) ? pred->validity : nullptr;  // filter.rs:261-264
+  {
+    acu_status s = acu_res_reset(ctx);
+    if (s != ACU_OK) return bail(s);
+  }
+  const int slot = acu_kstats_begin(ctx, ACU_K_FILTER_PLAN);
+  k_plan_mask<<<acu_grid(ctx, (n_words_padded / 32 + 7) / 8, 8), 256, 0, ctx->stream>>>(
+      static_cast<const uint8_t *>(pred->values), pred->values_offset, nv, pred->validity_offset, len, n_words_padded,
+      plan->mask, plan->tile_count, n_tiles);
+  k_plan_scan_chunks<<<(unsigned)n_chunks, 1024, 0, ctx->stream>>>(plan->tile_count, n_tiles, plan->tile_off, plan->chunk_total);
+  k_plan_scan_top<<<1, 1024, 0, ctx->stream>>>(plan->chunk_total, n_chunks, ctx->d_res);
+  k_plan_finalize<<<acu_grid(ctx, (n_off_padded + 255) / 256, 8), 256, 0, ctx->stream>>>(plan->tile_off, n_tiles, n_off_padded,
+                                                                                     plan->chunk_total, ctx->d_res);
+  acu_kstats_end(ctx, slot);
+  ctx->launches += 4;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return bail(acu_cuda_fail(ctx, e, "filter plan kernels"));
+  {
+    acu_status s = acu_res_fetch(ctx);
+    if (s != ACU_OK) return bail(s);
+  }
+  plan->count = (int64_t)ctx->h_res[RES_COUNT];
+  // IterationStrategy::default_strategy (filter.rs:346-364)
+  if (plan->count == 0) plan->strategy = ACU_FILTER_NONE;
+  else if (plan->count == len) plan->strategy = ACU_FILTER_ALL;
+  else if ((double)plan->count / (double)len > 0.8) plan->strategy = ACU_FILTER_SLICES;
+  else plan->strategy = ACU_FILTER_INDEX;
+  *out_plan = plan;
+  return ACU_OK;
+}
+
+void acu_filter_plan_destroy(acu_ctx *ctx, acu_filter_plan *plan) {
+  if (!plan) return;
+  if (plan->storage) acu_free(ctx, plan->storage);
+  delete plan;
+}
+int64_t acu_filter_plan_count(const acu_filter_plan *plan) { return plan->count; }
+int64_t acu_filter_plan_len(const acu_filter_plan *plan) { return plan->len; }
+int32_t acu_filter_plan_strategy(const acu_filter_plan *plan) { return plan->strategy; }
+
+acu_status acu_filter_primitive(acu_ctx *ctx, const acu_filter_plan *plan, int32_t elem_bytes,
+                                const acu_array *values, acu_array_out *out) {
+  ACU_TRY(check_len(ctx, plan, values->len));
+  out->len = plan->count;
+  out->has_validity = 0;
+  out->null_count = 0;
+  if (plan->strategy == ACU_FILTER_NONE) return ACU_OK;
+  if (plan->strategy == ACU_FILTER_ALL) {
+    ACU_CUDA(ctx, cudaMemcpyAsync(out->values, values->values, (size_t)plan->count * elem_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    ACU_TRY(slice_nulls(ctx, values, plan->count, out));
+    ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ACU_OK;
+  }
+  FilterArgs fa{};
+  fa.values = static_cast<const uint8_t *>(values->values);
+  fa.out = static_cast<uint8_t *>(out->values);
+  fa.mask = plan->mask;
+  fa.tile_off = plan->tile_off;
+  fa.n_tiles = plan->n_tiles;
+  fa.aligned16 = ((uintptr_t)values->values % 16) == 0;
+  switch (elem_bytes) {
+    case 1: ACU_TRY(launch_filter<1>(ctx, fa)); break;
+    case 2: ACU_TRY(launch_filter<2>(ctx, fa)); break;
+    case 4: ACU_TRY(launch_filter<4>(ctx, fa)); break;
+    case 8: ACU_TRY(launch_filter<8>(ctx, fa)); break;
+    case 16: ACU_TRY(launch_filter<16>(ctx, fa)); break;
+    case 32: ACU_TRY(launch_filter<32>(ctx, fa)); break;
+    default:
+      return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "filter: unsupported element width %d", elem_bytes);
+  }
+  return acu_filter_nulls_internal(ctx, plan, values, out);
+}
+
+acu_status acu_filter_boolean(acu_ctx *ctx, const acu_filter_plan *plan, const acu_array *values,
+                              acu_array_out *out) {
+  ACU_TRY(check_len(ctx, plan, values->len));
+  out->len = plan->count;
+  out->has_validity = 0;
+  out->null_count = 0;
+  if (plan->strategy == ACU_FILTER_NONE) return ACU_OK;
+  if (plan->strategy == ACU_FILTER_ALL) {
+    ACU_TRY(acu_bitmap_and_launch(ctx, static_cast<const uint8_t *>(values->values), values->values_offset, nullptr, 0,
+                                  plan->count, static_cast<uint64_t *>(out->values), false));
+    ACU_TRY(slice_nulls(ctx, values, plan->count, out));
+    ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ACU_OK;
+  }
+  ACU_TRY(launch_compress(ctx, plan, static_cast<const uint8_t *>(values->values), values->values_offset,
+                          static_cast<uint8_t *>(out->values), false));
+  return acu_filter_nulls_internal(ctx, plan, values, out);
+}
+
+}  // extern "C"
+
+// FilterPredicate::filter_nulls (filter.rs:512-533): bit-compact the validity, count, drop
+// the buffer when the result has no nulls. Synchronises the stream.
+acu_status acu_filter_nulls_internal(acu_ctx *ctx, const acu_filter_plan *plan, const acu_array *a,
+                                     acu_array_out *out) {
+  out->has_validity = 0;
+  out->null_count = 0;
+  acu_status st;
+  const int64_t nc = acu_resolve_null_count(ctx, a, &st);
+  ACU_TRY(st);
+  if (a->validity && nc > 0 && plan->count > 0) {
+    ACU_TRY(acu_res_reset(ctx));
+    ACU_TRY(launch_compress(ctx, plan, a->validity, a->validity_offset, out->validity, true));
+    ACU_TRY(acu_res_fetch(ctx));
+    const int64_t null_count = plan->count - (int64_t)ctx->h_res[RES_COUNT];
+    if (null_count > 0) { out->has_validity = 1; out->null_count = null_count; }  // filter.rs:523-525
+  } else {
+    ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    acu_kstats_drain(ctx);
+  }
+  return ACU_OK;
+}
+
+// Internal accessors for bytes.cu (filter_bytes materialises the selected row indices).
+const uint64_t *acu_plan_mask(const acu_filter_plan *p) { return p->mask; }
+const uint64_t *acu_plan_tile_off(const acu_filter_plan *p) { return p->tile_off; }
+int64_t acu_plan_n_tiles(const acu_filter_plan *p) { return p->n_tiles; }
+int64_t acu_plan_n_words_padded(const acu_filter_plan *p) { return ((p->n_tiles * TILE_WORDS + 31) / 32) * 32; }

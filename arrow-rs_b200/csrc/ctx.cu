@@ -74,7 +74,32 @@ acu_status acu_res_fetch(acu_ctx *ctx) {
   ACU_CUDA(ctx, cudaMemcpyAsync(ctx->h_res, ctx->d_res, RES_SLOTS * sizeof(unsigned long long),
                                 cudaMemcpyDeviceToHost, ctx->stream));
   ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  acu_kstats_drain(ctx);
   return ACU_OK;
+}
+
+// ---- per-kernel-class device time ---------------------------------------------------------
+int acu_kstats_begin(acu_ctx *ctx, int cls) {
+  if (ctx->kev_pending == acu_ctx::KEV_PAIRS) {  // ring full: wait for the oldest work, drain
+    cudaEventSynchronize(ctx->kev[acu_ctx::KEV_PAIRS - 1][1]);
+    acu_kstats_drain(ctx);
+  }
+  const int slot = ctx->kev_pending++;
+  ctx->kev_class[slot] = cls;
+  cudaEventRecord(ctx->kev[slot][0], ctx->stream);
+  return slot;
+}
+void acu_kstats_end(acu_ctx *ctx, int slot) { cudaEventRecord(ctx->kev[slot][1], ctx->stream); }
+void acu_kstats_drain(acu_ctx *ctx) {
+  for (int i = 0; i < ctx->kev_pending; ++i) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(ctx->kev[i][1]) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, ctx->kev[i][0], ctx->kev[i][1]) == cudaSuccess) {
+      ctx->kstat_ms[ctx->kev_class[i]] += ms;
+      ctx->kstat_n[ctx->kev_class[i]] += 1;
+    }
+  }
+  ctx->kev_pending = 0;
 }
 
 extern "C" {
@@ -98,6 +123,10 @@ acu_status acu_ctx_create(int32_t device, acu_ctx **out) {
             cudaEventCreate(&ctx->ev_stop) == cudaSuccess &&
             cudaMalloc(&ctx->d_res, RES_SLOTS * sizeof(unsigned long long)) == cudaSuccess &&
             cudaHostAlloc(&ctx->h_res, RES_SLOTS * sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
+  for (int i = 0; ok && i < ACU_TIMER_SLOTS; ++i)
+    ok = cudaEventCreate(&ctx->tev[i][0]) == cudaSuccess && cudaEventCreate(&ctx->tev[i][1]) == cudaSuccess;
+  for (int i = 0; ok && i < acu_ctx::KEV_PAIRS; ++i)
+    ok = cudaEventCreate(&ctx->kev[i][0]) == cudaSuccess && cudaEventCreate(&ctx->kev[i][1]) == cudaSuccess;
   if (!ok) { acu_ctx_destroy(ctx); return ACU_ERR_CUDA; }
   // keep freed blocks in the stream-ordered pool (no OS round trip between calls)
   cudaMemPool_t pool;
@@ -124,12 +153,19 @@ void acu_ctx_destroy(acu_ctx *ctx) {
   if (ctx->h_res) cudaFreeHost(ctx->h_res);
   if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
   if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
+  for (int i = 0; i < ACU_TIMER_SLOTS; ++i)
+    for (int j = 0; j < 2; ++j)
+      if (ctx->tev[i][j]) cudaEventDestroy(ctx->tev[i][j]);
+  for (int i = 0; i < acu_ctx::KEV_PAIRS; ++i)
+    for (int j = 0; j < 2; ++j)
+      if (ctx->kev[i][j]) cudaEventDestroy(ctx->kev[i][j]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
 
 acu_status acu_ctx_sync(acu_ctx *ctx) {
   ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  acu_kstats_drain(ctx);
   return ACU_OK;
 }
 
@@ -198,14 +234,30 @@ acu_status acu_host_free(acu_ctx *ctx, void *host) {
   return ACU_OK;
 }
 
-acu_status acu_timer_start(acu_ctx *ctx) {
-  ACU_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+acu_status acu_timer_start_slot(acu_ctx *ctx, int32_t slot) {
+  if (slot < 0 || slot >= ACU_TIMER_SLOTS) return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "timer slot %d", slot);
+  ACU_CUDA(ctx, cudaEventRecord(ctx->tev[slot][0], ctx->stream));
   return ACU_OK;
 }
-acu_status acu_timer_stop(acu_ctx *ctx, float *out_ms) {
-  ACU_CUDA(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
-  ACU_CUDA(ctx, cudaEventSynchronize(ctx->ev_stop));
-  ACU_CUDA(ctx, cudaEventElapsedTime(out_ms, ctx->ev_start, ctx->ev_stop));
+acu_status acu_timer_stop_slot(acu_ctx *ctx, int32_t slot, float *out_ms) {
+  if (slot < 0 || slot >= ACU_TIMER_SLOTS) return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "timer slot %d", slot);
+  ACU_CUDA(ctx, cudaEventRecord(ctx->tev[slot][1], ctx->stream));
+  ACU_CUDA(ctx, cudaEventSynchronize(ctx->tev[slot][1]));
+  ACU_CUDA(ctx, cudaEventElapsedTime(out_ms, ctx->tev[slot][0], ctx->tev[slot][1]));
+  acu_kstats_drain(ctx);
+  return ACU_OK;
+}
+acu_status acu_timer_start(acu_ctx *ctx) { return acu_timer_start_slot(ctx, 0); }
+acu_status acu_timer_stop(acu_ctx *ctx, float *out_ms) { return acu_timer_stop_slot(ctx, 0, out_ms); }
+
+acu_status acu_kernel_stats(acu_ctx *ctx, int32_t cls, double *out_total_ms, int64_t *out_launches) {
+  if (cls < 0 || cls >= ACU_K_CLASSES) return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "kernel class %d", cls);
+  *out_total_ms = ctx->kstat_ms[cls];
+  *out_launches = ctx->kstat_n[cls];
+  return ACU_OK;
+}
+acu_status acu_kernel_stats_reset(acu_ctx *ctx) {
+  for (int i = 0; i < ACU_K_CLASSES; ++i) { ctx->kstat_ms[i] = 0; ctx->kstat_n[i] = 0; }
   return ACU_OK;
 }
 

@@ -154,97 +154,102 @@ struct ArithParams {
   int zero_nulls;          // try_binary / try_unary: zero under nulls, op only at valid slots
 };
 
+// Steady state: a warp owns "groups" of U strips (all rows in bounds, no checks); the ragged
+// remainder (< U*R rows) is finished element-wise by warp 0 so that its bounds-checked code
+// does not inflate the register allocation of the streaming loop.
 template <class T, int CLS, int EPL>
-__global__ void __launch_bounds__(256) k_arith(const ArithParams<T> p) {
+__global__ void __launch_bounds__(256, (CLS == CLS_WRAP ? 4 : 3)) k_arith(const ArithParams<T> p) {
   constexpr int R = (32 * EPL > 64) ? 32 * EPL : 64;  // rows per strip
   constexpr int LPS = R / (32 * EPL);                 // loads per lane per strip
   constexpr int WORDS = R / 64;                       // validity words per strip
   constexpr int U = (LPS >= 2) ? 2 : 4;               // strips in flight per warp
+  constexpr int GROUP = U * R;                        // rows per group
+  constexpr int GWORDS = U * WORDS;                   // validity words per group (<= 32)
+  constexpr bool fallible = (CLS != CLS_WRAP) && !is_fp<T>::value;
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t n = p.n;
-  const int64_t strips = (n + R - 1) / R;
+  const int64_t groups = n / GROUP;
   const bool has_valid = p.out_valid != nullptr;
-  const bool fallible = (CLS != CLS_WRAP) && !is_fp<T>::value;
   T sa = T(), sb = T();
   if (p.a_scalar) sa = __ldg(p.a);
   if (p.b_scalar) sb = __ldg(p.b);
   unsigned valid_cnt = 0;
   unsigned long long err = ~0ull;
 
-  for (int64_t s0 = warp * U; s0 < strips; s0 += nwarps * U) {
-    Pack<T, EPL> va[U][LPS], vb[U][LPS];
-    uint64_t vw[U];
-    // ---- issue every load of the U strips first (memory-level parallelism) ----
+  for (int64_t g = warp; g < groups; g += nwarps) {
+    const int64_t base = g * GROUP;
+    const T *__restrict__ pa = p.a + base + lane * EPL;
+    const T *__restrict__ pb = p.b + base + lane * EPL;
+    Pack<T, EPL> va[U * LPS], vb[U * LPS];
+    // ---- every load of the group is issued before any use (memory-level parallelism) ----
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t base = (s0 + u) * R;
-      vw[u] = ~0ull;
-      if (has_valid && lane < WORDS) {
-        const int64_t row = base + (int64_t)lane * 64;
-        uint64_t w = ones_to(row, n);
-        if (p.av) w &= ld_bits64(p.av, p.aoff + row, p.aoff + n);
-        if (p.bv) w &= ld_bits64(p.bv, p.boff + row, p.boff + n);
-        vw[u] = w;
-      }
-#pragma unroll
-      for (int q = 0; q < LPS; ++q) {
-        const int64_t i0 = base + (int64_t)q * 32 * EPL + (int64_t)lane * EPL;
-        if (i0 + EPL <= n) {
-          if (!p.a_scalar) va[u][q] = pack_load<T, EPL>(p.a + i0);
-          if (!p.b_scalar) vb[u][q] = pack_load<T, EPL>(p.b + i0);
-        } else {
-#pragma unroll
-          for (int e = 0; e < EPL; ++e) {
-            va[u][q].v[e] = (!p.a_scalar && i0 + e < n) ? __ldg(p.a + i0 + e) : T();
-            vb[u][q].v[e] = (!p.b_scalar && i0 + e < n) ? __ldg(p.b + i0 + e) : T();
-          }
-        }
-      }
+    for (int k = 0; k < U * LPS; ++k) {
+      if (!p.a_scalar) va[k] = pack_load<T, EPL>(pa + k * 32 * EPL);
+      if (!p.b_scalar) vb[k] = pack_load<T, EPL>(pb + k * 32 * EPL);
+    }
+    uint64_t vw = ~0ull;  // lane l < GWORDS owns validity word l of the group
+    if (has_valid && lane < GWORDS) {
+      const int64_t row = base + lane * 64;
+      if (p.av) vw &= ld_bits64(p.av, p.aoff + row, p.aoff + n);
+      if (p.bv) vw &= ld_bits64(p.bv, p.boff + row, p.boff + n);
+      p.out_valid[row >> 6] = vw;
+      valid_cnt += __popcll(vw);
     }
     // ---- compute + store ----
+    T *__restrict__ po = p.out + base + lane * EPL;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t base = (s0 + u) * R;
-      if (base >= n) break;
-      if (has_valid && lane < WORDS) {
-        const int64_t row = base + (int64_t)lane * 64;
-        if (row < n) {
-          p.out_valid[(row >> 6)] = vw[u];
-          valid_cnt += __popcll(vw[u]);
+    for (int k = 0; k < U * LPS; ++k) {
+      uint32_t bits = ~0u;
+      if (fallible && p.zero_nulls) {
+        const int pos = k * 32 * EPL + lane * EPL;  // row inside the group
+        const uint64_t w = __shfl_sync(ACU_FULL_MASK, vw, pos >> 6);
+        bits = (uint32_t)(w >> (pos & 63));
+      }
+      Pack<T, EPL> o;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const T l = p.a_scalar ? sa : va[k].v[e];
+        const T r = p.b_scalar ? sb : vb[k].v[e];
+        T x;
+        const bool bad = apply_op<T, CLS>(p.op, l, r, x);
+        if (fallible) {
+          if (!((bits >> e) & 1u)) x = T();
+          else if (bad) {
+            const unsigned long long i = (unsigned long long)(base + k * 32 * EPL + lane * EPL + e);
+            err = i < err ? i : err;
+          }
         }
+        o.v[e] = x;
+      }
+      pack_store<T, EPL>(po + k * 32 * EPL, o);
+    }
+  }
+
+  // ---- ragged remainder: 64-row strips, lane owns rows l and l+32 ----
+  if (warp == 0) {
+    for (int64_t row = groups * GROUP; row < n; row += 64) {
+      uint64_t vw = ones_to(row, n);
+      if (has_valid) {
+        if (p.av) vw &= ld_bits64(p.av, p.aoff + row, p.aoff + n);
+        if (p.bv) vw &= ld_bits64(p.bv, p.boff + row, p.boff + n);
+        if (lane == 0) { p.out_valid[row >> 6] = vw; valid_cnt += __popcll(vw); }
       }
 #pragma unroll
-      for (int q = 0; q < LPS; ++q) {
-        const int pos0 = q * 32 * EPL + lane * EPL;  // position inside the strip
-        const int64_t i0 = base + pos0;
-        uint32_t bits = ~0u;
-        if (p.zero_nulls) {
-          uint64_t w = __shfl_sync(ACU_FULL_MASK, vw[u], pos0 >> 6);
-          bits = (uint32_t)(w >> (pos0 & 63));
+      for (int h = 0; h < 2; ++h) {
+        const int64_t i = row + h * 32 + lane;
+        if (i >= n) continue;
+        const T l = p.a_scalar ? sa : __ldg(p.a + i);
+        const T r = p.b_scalar ? sb : __ldg(p.b + i);
+        T x;
+        const bool bad = apply_op<T, CLS>(p.op, l, r, x);
+        if (fallible) {
+          const bool live = !p.zero_nulls || ((vw >> (h * 32 + lane)) & 1ull);
+          if (!live) x = T();
+          else if (bad) err = (unsigned long long)i < err ? (unsigned long long)i : err;
         }
-        Pack<T, EPL> o;
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) {
-          T l = p.a_scalar ? sa : va[u][q].v[e];
-          T r = p.b_scalar ? sb : vb[u][q].v[e];
-          T x;
-          bool bad = apply_op<T, CLS>(p.op, l, r, x);
-          if (fallible) {
-            const bool live = ((bits >> e) & 1u) && (i0 + e < n);
-            if (!live) x = T();
-            else if (bad) { unsigned long long i = (unsigned long long)(i0 + e); err = i < err ? i : err; }
-          }
-          o.v[e] = x;
-        }
-        if (i0 + EPL <= n) {
-          pack_store<T, EPL>(p.out + i0, o);
-        } else {
-#pragma unroll
-          for (int e = 0; e < EPL; ++e)
-            if (i0 + e < n) p.out[i0 + e] = o.v[e];
-        }
+        p.out[i] = x;
       }
     }
   }
@@ -262,13 +267,13 @@ acu_status launch_arith(acu_ctx *ctx, const ArithParams<T> &p) {
                  (p.b_scalar || (uintptr_t)p.b % 16 == 0);
   if (aligned) {
     constexpr int R = (32 * EPLV > 64) ? 32 * EPLV : 64;
-    int64_t strips = (p.n + R - 1) / R;
-    int64_t blocks = (strips + 8 * 4 - 1) / (8 * 4);
-    ACU_LAUNCH(ctx, (k_arith<T, CLS, EPLV>), acu_wave_grid(ctx, k_arith<T, CLS, EPLV>, 256, 0, blocks), 256, 0, p);
+    int64_t groups = p.n / (4 * R) + 1;
+    int64_t blocks = (groups + 7) / 8;
+    ACU_LAUNCH_TIMED(ctx, ACU_K_ARITH, (k_arith<T, CLS, EPLV>), acu_wave_grid(ctx, k_arith<T, CLS, EPLV>, 256, 0, blocks), 256, 0, p);
   } else {
-    int64_t strips = (p.n + 63) / 64;
-    int64_t blocks = (strips + 8 * 2 - 1) / (8 * 2);
-    ACU_LAUNCH(ctx, (k_arith<T, CLS, 1>), acu_wave_grid(ctx, k_arith<T, CLS, 1>, 256, 0, blocks), 256, 0, p);
+    int64_t groups = p.n / 128 + 1;
+    int64_t blocks = (groups + 7) / 8;
+    ACU_LAUNCH_TIMED(ctx, ACU_K_ARITH, (k_arith<T, CLS, 1>), acu_wave_grid(ctx, k_arith<T, CLS, 1>, 256, 0, blocks), 256, 0, p);
   }
   return ACU_OK;
 }
@@ -561,8 +566,8 @@ acu_status cmp_typed(acu_ctx *ctx, acu_cmp_op op, const acu_array *l, const acu_
   const int64_t strips = (len + 63) >> 6;
   const int64_t blocks = (strips + 31) / 32;
   const bool lt = !(op == ACU_EQ || op == ACU_NEQ || fold);
-  if (lt) ACU_LAUNCH(ctx, (k_cmp<T, true>), acu_wave_grid(ctx, k_cmp<T, true>, 256, 0, blocks), 256, 0, p);
-  else ACU_LAUNCH(ctx, (k_cmp<T, false>), acu_wave_grid(ctx, k_cmp<T, false>, 256, 0, blocks), 256, 0, p);
+  if (lt) ACU_LAUNCH_TIMED(ctx, ACU_K_CMP, (k_cmp<T, true>), acu_wave_grid(ctx, k_cmp<T, true>, 256, 0, blocks), 256, 0, p);
+  else ACU_LAUNCH_TIMED(ctx, ACU_K_CMP, (k_cmp<T, false>), acu_wave_grid(ctx, k_cmp<T, false>, 256, 0, blocks), 256, 0, p);
   ACU_TRY(acu_res_fetch(ctx));
   if (p.out_valid) {
     out->has_validity = 1;
@@ -674,7 +679,7 @@ acu_status cast_typed(acu_ctx *ctx, acu_dtype to, int32_t safe, const acu_array 
   uint64_t *ov = out->has_validity ? reinterpret_cast<uint64_t *>(out->validity) : nullptr;
   ACU_TRY(acu_res_reset(ctx));
   const int64_t strips = (len + 63) >> 6;
-  ACU_LAUNCH(ctx, (k_cast<I, O>), acu_wave_grid(ctx, k_cast<I, O>, 256, 0, (strips + 31) / 32), 256, 0, static_cast<const I *>(a->values),
+  ACU_LAUNCH_TIMED(ctx, ACU_K_CAST, (k_cast<I, O>), acu_wave_grid(ctx, k_cast<I, O>, 256, 0, (strips + 31) / 32), 256, 0, static_cast<const I *>(a->values),
              static_cast<O *>(out->values), len, a->validity, a->validity_offset, ov, safe, ctx->d_res);
   ACU_TRY(acu_res_fetch(ctx));
   if (!safe && ctx->h_res[RES_ERR_INDEX] != ~0ull) {

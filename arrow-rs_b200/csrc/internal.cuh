@@ -3,11 +3,10 @@
 #include "common.cuh"
 
 struct acu_filter_plan;
-const uint64_t *acu_plan_mask(const acu_filter_plan *p);
-const uint32_t *acu_plan_tile_local(const acu_filter_plan *p);
-const uint32_t *acu_plan_tile_count(const acu_filter_plan *p);
-const uint64_t *acu_plan_chunk_offset(const acu_filter_plan *p);
+const uint64_t *acu_plan_mask(const acu_filter_plan *p);      // normalised mask words (padded to x32)
+const uint64_t *acu_plan_tile_off(const acu_filter_plan *p);  // exclusive output offset per 1024-row tile
 int64_t acu_plan_n_tiles(const acu_filter_plan *p);
+int64_t acu_plan_n_words_padded(const acu_filter_plan *p);
 
 // FilterPredicate::filter_nulls (filter.rs:512-533) for any array kind.
 acu_status acu_filter_nulls_internal(acu_ctx *ctx, const acu_filter_plan *plan, const acu_array *a,

@@ -152,7 +152,7 @@ acu_status reduce_launch(acu_ctx *ctx, const acu_array *a, const uint8_t *valid)
   unsigned int *ticket = static_cast<unsigned int *>(scratch);
   A *partial = reinterpret_cast<A *>(static_cast<uint8_t *>(scratch) + 256);
   ACU_CUDA(ctx, cudaMemsetAsync(ticket, 0, 4, ctx->stream));
-  ACU_LAUNCH(ctx, (k_reduce<T, OP>), grid, 256, 0, static_cast<const T *>(a->values), a->len, valid, a->validity_offset,
+  ACU_LAUNCH_TIMED(ctx, ACU_K_REDUCE, (k_reduce<T, OP>), grid, 256, 0, static_cast<const T *>(a->values), a->len, valid, a->validity_offset,
              partial, ticket, ctx->d_res);
   return ACU_OK;
 }

@@ -249,7 +249,7 @@ template <int W>
 acu_status launch_take_w(acu_ctx *ctx, int kind, const TakeArgs &ta) {
   const int64_t tiles = (ta.m + TAKE_TILE - 1) / TAKE_TILE;
 #define ACU_TAKE_CASE(IT)                                                                                   \
-  case IT: ACU_LAUNCH(ctx, (k_take<W, IT>), acu_wave_grid(ctx, k_take<W, IT>, 256, 0, tiles), 256, 0, ta); \
+  case IT: ACU_LAUNCH_TIMED(ctx, ACU_K_TAKE, (k_take<W, IT>), acu_wave_grid(ctx, k_take<W, IT>, 256, 0, tiles), 256, 0, ta); \
     break;
   switch (kind) {
     ACU_TAKE_CASE(0) ACU_TAKE_CASE(1) ACU_TAKE_CASE(2) ACU_TAKE_CASE(3) ACU_TAKE_CASE(4) ACU_TAKE_CASE(5)
@@ -352,7 +352,16 @@ acu_status acu_take_common(acu_ctx *ctx, int32_t elem_bytes, const acu_array *va
     uint64_t raw;
     char text[32];
     ACU_TRY(fetch_index(ctx, indices, index_dtype, j, &raw, text, sizeof text));
-    return acu_fail(ctx, ACU_ERR_PANIC_OUT_OF_BOUNDS, j, raw, 0, (uint64_t)values->len, "Out-of-bounds index %s", text);
+    // the reference panics on the index AFTER ToIndices (u32 / u64): take.rs:447
+    uint64_t widened = raw;
+    switch (index_dtype) {
+      case ACU_I8: widened = (uint32_t)(int32_t)(int8_t)raw; break;
+      case ACU_I16: widened = (uint32_t)(int32_t)(int16_t)raw; break;
+      case ACU_I32: widened = (uint32_t)raw; break;
+      default: break;
+    }
+    return acu_fail(ctx, ACU_ERR_PANIC_OUT_OF_BOUNDS, j, widened, 0, (uint64_t)values->len, "Out-of-bounds index %llu",
+                    (unsigned long long)widened);
   }
   if (ta.out_valid) {
     const int64_t null_count = m - (int64_t)ctx->h_res[RES_COUNT];

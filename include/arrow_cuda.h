@@ -162,9 +162,23 @@ acu_status acu_host_free(acu_ctx *ctx, void *host);
  * reference's MemoryPool tracking, arrow-buffer/src/pool.rs:73-85). */
 int64_t acu_bytes_allocated(const acu_ctx *ctx);
 
-/* CUDA-event timer on the ctx stream (events see exactly the stream kernels run on). */
-acu_status acu_timer_start(acu_ctx *ctx);
-acu_status acu_timer_stop(acu_ctx *ctx, float *out_ms);  /* records + synchronises */
+/* CUDA-event timers on the ctx stream (events see exactly the stream kernels run on).
+ * ACU_TIMER_SLOTS independent slots so that a step timer can bracket per-op timers. */
+#define ACU_TIMER_SLOTS 8
+acu_status acu_timer_start(acu_ctx *ctx);                /* slot 0 */
+acu_status acu_timer_stop(acu_ctx *ctx, float *out_ms);  /* slot 0; records + synchronises */
+acu_status acu_timer_start_slot(acu_ctx *ctx, int32_t slot);
+acu_status acu_timer_stop_slot(acu_ctx *ctx, int32_t slot, float *out_ms);
+
+/* Per-kernel device time, always on: every launch of a hot kernel is bracketed by a pair of
+ * CUDA events on the ctx stream and its elapsed time is accumulated per kernel class when
+ * the call synchronises. bench.py derives roofline.achieved from these (kernel-only) times. */
+typedef enum acu_kernel_class {
+  ACU_K_ARITH = 0, ACU_K_CMP = 1, ACU_K_CAST = 2, ACU_K_FILTER = 3, ACU_K_FILTER_PLAN = 4,
+  ACU_K_TAKE = 5, ACU_K_REDUCE = 6, ACU_K_BYTES = 7, ACU_K_CLASSES = 8
+} acu_kernel_class;
+acu_status acu_kernel_stats(acu_ctx *ctx, int32_t kernel_class, double *out_total_ms, int64_t *out_launches);
+acu_status acu_kernel_stats_reset(acu_ctx *ctx);
 
 /* Deterministic synthetic inputs generated on the device:
  * element i = f(splitmix64(seed ^ (first_row + i))). The same generator exists on the
@@ -205,6 +219,10 @@ typedef enum acu_filter_strategy {  /* IterationStrategy, filter.rs:328-365 */
 acu_status acu_filter_plan_create(acu_ctx *ctx, const acu_array *predicate /* boolean array */,
                                   acu_filter_plan **out_plan);
 void acu_filter_plan_destroy(acu_ctx *ctx, acu_filter_plan *plan);
+/* FilterBuilder::optimize (filter.rs:285-298): materialise IterationStrategy::Indices — the
+ * selected row ids in ascending order, as index_dtype ACU_U32 or ACU_U64 (count entries). */
+acu_status acu_filter_plan_indices(acu_ctx *ctx, const acu_filter_plan *plan, acu_dtype index_dtype,
+                                   void *out_indices);
 int64_t acu_filter_plan_count(const acu_filter_plan *plan);      /* FilterPredicate::count */
 int64_t acu_filter_plan_len(const acu_filter_plan *plan);        /* predicate length       */
 int32_t acu_filter_plan_strategy(const acu_filter_plan *plan);   /* acu_filter_strategy    */

@@ -1,0 +1,49 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol
+include/arrow_cuda.h declares; without a GPU the product path fails loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from acu import _abi as abi
+
+HEADER = os.path.join(abi.REPO, "include", "arrow_cuda.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(acu_[a-z0-9_]+)\s*\(", text)) - {"acu_bitmap_bytes"})
+
+
+def test_library_is_built():
+    assert os.path.exists(abi.LIB_PATH), "run __graft_entry__.build() first"
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    lib = abi.load_library()
+    syms = declared_symbols()
+    assert len(syms) >= 40
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/arrow_cuda.h but not exported"
+        assert s in abi.PROTOTYPES, f"{s} has no ctypes prototype in acu/_abi.py"
+    assert set(abi.PROTOTYPES) == set(syms)
+
+
+def test_struct_layouts_match_header():
+    # sizes the C side asserts implicitly (plain pointers and 64-bit integers, no torch types)
+    assert C.sizeof(abi.Array) == 56
+    assert C.sizeof(abi.ArrayOut) == 40
+    assert C.sizeof(abi.ErrorDetail) == 8 + 8 + 8 + 8 + 8 + 256
+
+
+def test_no_cpu_fallback_without_gpu():
+    """On a box without CUDA devices ctx creation must fail (never silently compute on the CPU)."""
+    lib = abi.load_library()
+    h = C.c_void_p()
+    st = lib.acu_ctx_create(0, C.byref(h))
+    if st == abi.OK:  # a GPU is present: nothing to assert here
+        lib.acu_ctx_destroy(h)
+        pytest.skip("CUDA device present")
+    assert st == abi.ERR_CUDA and not h.value

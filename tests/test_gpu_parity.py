@@ -1,0 +1,380 @@
+"""Differential parity: the CUDA path (through the C ABI) vs the CPU oracle on seeded random,
+sliced, ragged inputs — the reference's own fuzz pattern (fuzz_filter,
+arrow-select/src/filter.rs:1888-1977: random lengths, offsets, null densities vs a naive oracle).
+
+Bar: bit-exact for integer / byte / index / bitmap work, including the bytes written under
+null slots and whether the result carries a NullBuffer at all; floating-point arithmetic is
+compared bit-for-bit except that any NaN matches any NaN (tolerance stated by north_star:
+1 ulp; we hold 0 ulp on non-NaN results). Float `sum` is tolerance-based (order-dependent in
+the reference itself, arrow-arith/src/aggregate.rs:303-313).
+"""
+import numpy as np
+import pytest
+
+import acu
+from acu import _abi as abi
+from acu import BOOL, HostArray
+
+pytestmark = pytest.mark.gpu
+
+INT_DTYPES = [abi.I8, abi.I16, abi.I32, abi.I64, abi.U8, abi.U16, abi.U32, abi.U64]
+FLOAT_DTYPES = [abi.F32, abi.F64]
+SIZES = [0, 1, 31, 32, 33, 63, 64, 65, 127, 128, 129, 1000, 4095, 4096, 4097, 8191, 12345, 70001]
+
+
+def rand_values(rng, dtype, n, small=False):
+    npdt = acu.NP_DTYPES[dtype]
+    if dtype in FLOAT_DTYPES:
+        v = (rng.random(n) * 2e6 - 1e6).astype(npdt)
+        if n:
+            specials = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, -np.nan, 5e-324, 1.0, -1.0], dtype=npdt)
+            k = max(1, n // 16)
+            v[rng.integers(0, n, k)] = specials[rng.integers(0, len(specials), k)]
+        return v
+    info = np.iinfo(npdt)
+    if small:
+        lo, hi = max(info.min, -50), min(info.max, 50)
+        return rng.integers(lo, hi, n, dtype=np.int64).astype(npdt)
+    v = rng.integers(info.min, info.max, n, dtype=npdt, endpoint=True)
+    if n:
+        k = max(1, n // 16)
+        edge = np.array([info.min, info.max, 0, 1, info.max - 1], dtype=npdt)
+        v[rng.integers(0, n, k)] = edge[rng.integers(0, len(edge), k)]
+    return v
+
+
+def rand_array(rng, dtype, n, null_p, offset=0, small=False):
+    """Random primitive array; `offset` > 0 builds a longer buffer and slices it (bit + element offsets)."""
+    total = n + offset
+    vals = rand_values(rng, dtype, total, small)
+    mask = None if null_p is None else rng.random(total) >= null_p
+    h = HostArray.from_numpy(dtype, vals, mask, bit_offset=int(rng.integers(0, 9)) if mask is not None else 0)
+    return h.slice(offset, n) if offset else h
+
+
+def rand_bool(rng, n, true_p, null_p, offset=0):
+    total = n + offset
+    bools = rng.random(total) < true_p
+    mask = None if null_p is None else rng.random(total) >= null_p
+    h = HostArray.bool_from_numpy(bools, mask, bit_offset=int(rng.integers(0, 9)), mask_offset=int(rng.integers(0, 9)))
+    return h.slice(offset, n) if offset else h
+
+
+def same_bits(a, b):
+    return np.array_equal(np.ascontiguousarray(a).view(np.uint8), np.ascontiguousarray(b).view(np.uint8))
+
+
+def assert_same(got, exp, what, float_nan_ok=False, exact_bytes=True):
+    assert got.length == exp.length, f"{what}: length {got.length} != {exp.length}"
+    assert (got.validity is None) == (exp.validity is None), f"{what}: NullBuffer presence differs"
+    n = exp.length
+    if exp.validity is not None:
+        assert got.null_count == exp.null_count, f"{what}: null_count {got.null_count} != {exp.null_count}"
+        assert np.array_equal(got.valid_mask(), exp.valid_mask()), f"{what}: validity bits differ"
+    gv, ev = got.value_array(), exp.value_array()
+    if not exact_bytes:  # logical equality only (arrow-data/src/equal/mod.rs:161-166)
+        m = exp.valid_mask()
+        gv, ev = gv[m], ev[m]
+    if float_nan_ok and exp.dtype in FLOAT_DTYPES:
+        gn, en = np.isnan(gv), np.isnan(ev)
+        assert np.array_equal(gn, en), f"{what}: NaN positions differ"
+        assert same_bits(gv[~gn], ev[~en]), f"{what}: non-NaN float bits differ"
+    else:
+        if not same_bits(gv[:n], ev[:n]):
+            bad = np.nonzero(gv[:n] != ev[:n])[0]
+            raise AssertionError(f"{what}: values differ at {bad[:8]}: {gv[bad[:8]]} vs {ev[bad[:8]]}")
+
+
+def expect_same_error(gpu, oracle, fn):
+    try:
+        exp = fn(oracle)
+    except acu.ArrowError as e:
+        with pytest.raises(acu.ArrowError) as gi:
+            fn(gpu)
+        assert gi.value.status == e.status
+        assert str(gi.value) == str(e), f"{gi.value} != {e}"
+        assert gi.value.index == e.index
+        return None, None
+    return fn(gpu), exp
+
+
+# ---- filter ------------------------------------------------------------------------------
+@pytest.mark.parametrize("width_dtype", [abi.I8, abi.I16, abi.I32, abi.I64, abi.F64])
+@pytest.mark.parametrize("true_p", [0.0, 0.01, 0.1, 0.5, 0.9, 1.0])
+def test_filter_primitive_fuzz(gpu, oracle, width_dtype, true_p):
+    rng = np.random.default_rng(1000 + width_dtype * 17 + int(true_p * 100))
+    for n in SIZES:
+        for null_p, pred_null_p, off in [(None, None, 0), (0.05, None, 3), (0.5, 0.1, 1), (0.0, 0.3, 0)]:
+            values = rand_array(rng, width_dtype, n + int(rng.integers(0, 3)), null_p, off)
+            pred = rand_bool(rng, n, true_p, pred_null_p, off)
+            got, exp = gpu.filter(values, pred), oracle.filter(values, pred)
+            assert_same(got, exp, f"filter n={n} p={true_p} nulls={null_p}/{pred_null_p} off={off}")
+            assert gpu.filter_plan(pred) == oracle.filter_plan(pred)
+
+
+def test_filter_boolean_fuzz(gpu, oracle):
+    rng = np.random.default_rng(7)
+    for n in SIZES:
+        for true_p in [0.1, 0.5, 0.95]:
+            values = rand_bool(rng, n, 0.5, 0.2, 2)
+            pred = rand_bool(rng, n, true_p, 0.1, 5)
+            assert_same(gpu.filter(values, pred), oracle.filter(values, pred), f"filter_boolean n={n} p={true_p}")
+
+
+def test_filter_predicate_shorter_and_longer(gpu, oracle):
+    rng = np.random.default_rng(8)
+    values = rand_array(rng, abi.I64, 5000, 0.1)
+    pred = rand_bool(rng, 4000, 0.3, None)
+    assert_same(gpu.filter(values, pred), oracle.filter(values, pred), "shorter predicate")
+    pred = rand_bool(rng, 5001, 0.3, None)
+    got, exp = expect_same_error(gpu, oracle, lambda be: be.filter(values, pred))
+    assert got is None
+
+
+@pytest.mark.parametrize("width", [16, 32])
+def test_filter_wide_elements(gpu, oracle, width):
+    """Decimal128/256-sized elements: modelled as `width`-byte records over uint64 lanes."""
+    rng = np.random.default_rng(9 + width)
+    lanes = width // 8
+    for n in [0, 1, 100, 4097, 9000]:
+        raw = rng.integers(0, 2**63, n * lanes, dtype=np.uint64)
+        mask = rng.random(n) >= 0.2
+        pred = rand_bool(rng, n, 0.3, None)
+        # run through the C ABI directly with elem_bytes = width
+        import ctypes as C
+        from oracle import Oracle  # noqa: F401
+        vals = HostArray(abi.U64, raw, n, acu.pack_bits(mask), 0, 0, int(n - mask.sum()))
+        dv, dp = gpu.upload(HostArray(abi.U64, raw, n * lanes)), gpu.upload(pred)
+        dn = gpu.malloc(len(vals.validity) + 8)
+        gpu.h2d(dn, vals.validity)
+        plan = C.c_void_p()
+        pd = dp.descriptor()
+        gpu.check(gpu.lib.acu_filter_plan_create(gpu.h, C.byref(pd), C.byref(plan)))
+        count = gpu.lib.acu_filter_plan_count(plan)
+        out = gpu.alloc_out(count * width, count)
+        vd = abi.Array()
+        vd.values, vd.validity, vd.validity_offset, vd.len, vd.null_count = dv.d_values, dn, 0, n, vals.null_count
+        gpu.check(gpu.lib.acu_filter_primitive(gpu.h, plan, width, C.byref(vd), C.byref(out)))
+        got_vals = gpu.d2h(out.values, count * width, np.uint64).reshape(count, lanes)
+        sel = pred.value_array() & pred.valid_mask()
+        assert np.array_equal(got_vals, raw.reshape(n, lanes)[sel])
+        exp_valid = mask[sel]
+        if out.has_validity:
+            got_valid = acu.unpack_bits(gpu.d2h(out.validity, abi.bitmap_bytes(count)), 0, count)
+            assert np.array_equal(got_valid, exp_valid) and out.null_count == int((~exp_valid).sum())
+        else:
+            assert exp_valid.all()
+        gpu.lib.acu_filter_plan_destroy(gpu.h, plan)
+        gpu._free_out(out)
+        gpu.free(dn)
+        dv.free()
+        dp.free()
+
+
+# ---- take --------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [abi.I8, abi.I16, abi.I32, abi.I64, abi.F64])
+@pytest.mark.parametrize("idx_dtype", [abi.U8, abi.I8, abi.U16, abi.I16, abi.U32, abi.I32, abi.U64, abi.I64])
+def test_take_primitive_fuzz(gpu, oracle, dtype, idx_dtype):
+    rng = np.random.default_rng(2000 + dtype * 31 + idx_dtype)
+    idx_max = min(int(np.iinfo(acu.NP_DTYPES[idx_dtype]).max), 100000)
+    for nv in [1, 7, 100, 5000]:
+        nv = min(nv, idx_max)
+        for m in [0, 1, 33, 2047, 2048, 2049, 10000]:
+            for vnull, inull, off in [(None, None, 0), (0.1, None, 0), (None, 0.2, 3), (0.3, 0.3, 2)]:
+                values = rand_array(rng, dtype, nv, vnull, off)
+                raw = rng.integers(0, nv, m + off).astype(acu.NP_DTYPES[idx_dtype])
+                imask = None if inull is None else rng.random(m + off) >= inull
+                if imask is not None and m:  # out-of-bounds values hidden under null index slots
+                    hidden = np.nonzero(~imask)[0]
+                    raw[hidden[: len(hidden) // 2]] = idx_max
+                idx = HostArray.from_numpy(idx_dtype, raw, imask, bit_offset=int(rng.integers(0, 9)) if imask is not None else 0)
+                if off:
+                    idx = idx.slice(off, m)
+                if imask is not None and nv > idx_max - 1:
+                    continue
+                got, exp = expect_same_error(gpu, oracle, lambda be: be.take(values, idx))
+                if exp is not None:
+                    assert_same(got, exp, f"take nv={nv} m={m} nulls={vnull}/{inull} off={off}")
+
+
+def test_take_boolean_fuzz(gpu, oracle):
+    rng = np.random.default_rng(11)
+    for nv, m in [(10, 100), (1000, 5000), (70000, 33)]:
+        values = rand_bool(rng, nv, 0.5, 0.2, 3)
+        idx = HostArray.from_numpy(abi.U32, rng.integers(0, nv, m).astype(np.uint32), rng.random(m) >= 0.1)
+        assert_same(gpu.take(values, idx), oracle.take(values, idx), f"take_boolean nv={nv} m={m}")
+
+
+def test_take_out_of_bounds_contract(gpu, oracle):
+    values = HostArray.from_list(abi.I64, [0, 1, 2, 3])
+    for dt, bad in [(abi.U32, 1000), (abi.I32, -1), (abi.I64, -5), (abi.I8, -1), (abi.U64, 2**40)]:
+        idx = HostArray.from_list(dt, [1, bad, 2])
+        for cb in (False, True):
+            got, exp = expect_same_error(gpu, oracle, lambda be: be.take(values, idx, cb))
+            assert got is None and exp is None
+
+
+# ---- variable width ------------------------------------------------------------------------
+def rand_strings(rng, n, null_p):
+    lens = rng.integers(0, 13, n)
+    offsets = np.zeros(n + 1, dtype=np.int32)
+    offsets[1:] = np.cumsum(lens)
+    data = rng.integers(97, 123, int(offsets[-1]) + 16).astype(np.uint8)
+    mask = rng.random(n) >= null_p if null_p is not None else None
+    nulls = HostArray(abi.U8, np.zeros(0, np.uint8), n, None if mask is None else acu.pack_bits(mask), 0, 0,
+                      0 if mask is None else int(n - mask.sum()))
+    return offsets, data, nulls
+
+
+def assert_same_bytes(got, exp, what):
+    go, gd, gn = got
+    eo, ed, en = exp
+    assert np.array_equal(go, eo), f"{what}: offsets differ"
+    assert np.array_equal(gd, ed), f"{what}: bytes differ"
+    assert (gn.validity is None) == (en.validity is None), f"{what}: NullBuffer presence"
+    if en.validity is not None:
+        assert np.array_equal(gn.valid_mask(), en.valid_mask()) and gn.null_count == en.null_count
+
+
+def test_take_bytes_fuzz(gpu, oracle):
+    """Also the Dictionary<Int32,Utf8> -> Utf8 cast (arrow-cast/src/cast/dictionary.rs:310-317)."""
+    rng = np.random.default_rng(12)
+    for nv, m in [(1, 10), (50, 0), (4096, 20000), (300, 5000)]:
+        for vnull, inull in [(None, None), (0.2, None), (None, 0.1), (0.2, 0.1)]:
+            o, d, n = rand_strings(rng, nv, vnull)
+            idx = HostArray.from_numpy(abi.I32, rng.integers(0, nv, m).astype(np.int32),
+                                       None if inull is None else rng.random(m) >= inull)
+            assert_same_bytes(gpu.take_bytes(o, d, n, idx), oracle.take_bytes(o, d, n, idx), f"take_bytes nv={nv} m={m}")
+
+
+def test_filter_bytes_fuzz(gpu, oracle):
+    rng = np.random.default_rng(13)
+    for n in [0, 1, 100, 4096, 4097, 30000]:
+        for true_p in [0.0, 0.1, 0.9, 1.0]:
+            o, d, nulls = rand_strings(rng, n, 0.15)
+            pred = rand_bool(rng, n, true_p, 0.05)
+            assert_same_bytes(gpu.filter_bytes(o, d, nulls, pred), oracle.filter_bytes(o, d, nulls, pred),
+                              f"filter_bytes n={n} p={true_p}")
+
+
+# ---- numeric -------------------------------------------------------------------------------
+ARITH_OPS = ["add", "add_wrapping", "sub", "sub_wrapping", "mul", "mul_wrapping", "div", "rem"]
+
+
+@pytest.mark.parametrize("dtype", INT_DTYPES + FLOAT_DTYPES)
+@pytest.mark.parametrize("op", ARITH_OPS)
+def test_arith_fuzz(gpu, oracle, dtype, op):
+    rng = np.random.default_rng(3000 + dtype * 13 + ARITH_OPS.index(op))
+    for n in [0, 1, 63, 64, 65, 255, 256, 257, 1000, 5000, 33333]:
+        for an, bn, off, small in [(None, None, 0, True), (0.1, None, 1, True), (0.1, 0.2, 3, False), (0.0, 0.0, 0, True),
+                                   (None, None, 1, False)]:
+            a = rand_array(rng, dtype, n, an, off, small)
+            b = rand_array(rng, dtype, n, bn, off and 2, small)
+            got, exp = expect_same_error(gpu, oracle, lambda be: getattr(be, op)(a, b))
+            if exp is not None:
+                assert_same(got, exp, f"{op} dtype={dtype} n={n} nulls={an}/{bn} off={off}", float_nan_ok=True)
+
+
+@pytest.mark.parametrize("dtype", [abi.I32, abi.I64, abi.U64, abi.F32, abi.F64])
+@pytest.mark.parametrize("op", ARITH_OPS)
+def test_arith_scalar_fuzz(gpu, oracle, dtype, op):
+    rng = np.random.default_rng(4000 + dtype * 13 + ARITH_OPS.index(op))
+    for n in [0, 1, 100, 4097]:
+        for null_p in [None, 0.2]:
+            arr = rand_array(rng, dtype, n, null_p, 1, small=True)
+            for sv in [rand_array(rng, dtype, 1, None, 0, small=True).scalar(), HostArray.from_list(dtype, [None]).scalar()]:
+                for fn in (lambda be: getattr(be, op)(arr, sv), lambda be: getattr(be, op)(sv, arr)):
+                    got, exp = expect_same_error(gpu, oracle, fn)
+                    if exp is not None:
+                        assert_same(got, exp, f"{op} scalar dtype={dtype} n={n}", float_nan_ok=True)
+
+
+@pytest.mark.parametrize("dtype", [abi.I8, abi.I32, abi.I64, abi.F32, abi.F64])
+def test_neg_fuzz(gpu, oracle, dtype):
+    rng = np.random.default_rng(5000 + dtype)
+    for n in [0, 1, 100, 5000]:
+        for null_p in [None, 0.3]:
+            a = rand_array(rng, dtype, n, null_p, 2)
+            for checked in (True, False):
+                got, exp = expect_same_error(gpu, oracle, lambda be: be.neg(a, checked))
+                if exp is not None:
+                    assert_same(got, exp, f"neg dtype={dtype} n={n} checked={checked}", float_nan_ok=True)
+
+
+# ---- cmp -----------------------------------------------------------------------------------
+CMP_OPS = ["eq", "neq", "lt", "lt_eq", "gt", "gt_eq", "distinct", "not_distinct"]
+
+
+@pytest.mark.parametrize("dtype", [abi.I8, abi.I32, abi.I64, abi.U32, abi.U64, abi.F32, abi.F64])
+@pytest.mark.parametrize("op", CMP_OPS)
+def test_cmp_fuzz(gpu, oracle, dtype, op):
+    rng = np.random.default_rng(6000 + dtype * 13 + CMP_OPS.index(op))
+    for n in [0, 1, 63, 64, 65, 1000, 4097, 20000]:
+        for an, bn, off in [(None, None, 0), (0.1, None, 1), (0.1, 0.2, 3), (0.0, 0.0, 0)]:
+            a = rand_array(rng, dtype, n, an, off, small=True)
+            b = rand_array(rng, dtype, n, bn, off, small=True)
+            got, exp = gpu.cmp(abi.EQ + CMP_OPS.index(op), a, b), oracle.cmp(abi.EQ + CMP_OPS.index(op), a, b)
+            assert_same(got, exp, f"{op} dtype={dtype} n={n} nulls={an}/{bn}")
+        if n:
+            arr = rand_array(rng, dtype, n, 0.2, 1, small=True)
+            for sv in [rand_array(rng, dtype, 1, None, 0, small=True).scalar(), HostArray.from_list(dtype, [None]).scalar()]:
+                for x, y in ((arr, sv), (sv, arr), (sv, sv)):
+                    code = abi.EQ + CMP_OPS.index(op)
+                    assert_same(gpu.cmp(code, x, y), oracle.cmp(code, x, y), f"{op} scalar dtype={dtype} n={n}", exact_bytes=False)
+
+
+# ---- cast ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("frm", INT_DTYPES + FLOAT_DTYPES)
+@pytest.mark.parametrize("to", INT_DTYPES + FLOAT_DTYPES)
+def test_cast_fuzz(gpu, oracle, frm, to):
+    rng = np.random.default_rng(7000 + frm * 10 + to)
+    for n in [0, 1, 65, 1000, 4097]:
+        for null_p in [None, 0.1]:
+            a = rand_array(rng, frm, n, null_p, 1)
+            assert_same(gpu.cast(a, to), oracle.cast(a, to), f"cast {frm}->{to} n={n}", float_nan_ok=True)
+            got, exp = expect_same_error(gpu, oracle, lambda be: be.cast(a, to, safe=False))
+            if exp is not None:
+                assert_same(got, exp, f"cast unsafe {frm}->{to} n={n}", float_nan_ok=True)
+
+
+# ---- aggregate -----------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [abi.I8, abi.I32, abi.I64, abi.U64, abi.F32, abi.F64])
+def test_aggregate_fuzz(gpu, oracle, dtype):
+    rng = np.random.default_rng(8000 + dtype)
+    for n in [0, 1, 63, 64, 65, 1000, 70001]:
+        for null_p in [None, 0.1, 1.0]:
+            a = rand_array(rng, dtype, n, null_p, 1)
+            for op in ("min", "max"):
+                g, e = getattr(gpu, op)(a), getattr(oracle, op)(a)
+                if isinstance(e, float) and np.isnan(e):
+                    assert np.isnan(g) and np.signbit(g) == np.signbit(e)
+                else:
+                    assert g == e, f"{op} dtype={dtype} n={n}: {g} != {e}"
+            if dtype in FLOAT_DTYPES:  # order-dependent: finite inputs, relative tolerance
+                vals = (rng.random(n) * 2e3 - 1e3).astype(acu.NP_DTYPES[dtype])
+                b = HostArray.from_numpy(dtype, vals, None if null_p is None else rng.random(n) >= null_p)
+                g, e = gpu.sum(b), oracle.sum(b)
+                assert (g is None) == (e is None)
+                if e is not None:
+                    scale = float(np.abs(vals).sum()) + 1.0
+                    tol = (1e-12 if dtype == abi.F64 else 1e-4) * scale
+                    assert abs(g - e) <= tol, f"sum dtype={dtype} n={n}: {g} vs {e}"
+            else:
+                assert gpu.sum(a) == oracle.sum(a), f"sum dtype={dtype} n={n}"
+
+
+def test_generators_match_host_twin(gpu, oracle):
+    import ctypes as C
+    n = 100003
+    for kind, npdt, param in [(0, np.uint64, 0), (1, np.int64, 0), (2, np.float64, 0), (3, np.uint32, 12345), (4, np.int32, 777)]:
+        d = gpu.malloc(n * 8)
+        gpu.check(gpu.lib.acu_generate_values(gpu.h, kind, 42, 1000, param, d, n))
+        got = gpu.d2h(d, n * np.dtype(npdt).itemsize, npdt)
+        gpu.free(d)
+        assert same_bits(got, oracle.generate_values(kind, 42, 1000, param, n, npdt))
+    d = gpu.malloc(abi.bitmap_bytes(n))
+    gpu.check(gpu.lib.acu_generate_bits(gpu.h, 46, 5, 0.1, d, n))
+    got = acu.unpack_bits(gpu.d2h(d, abi.bitmap_bytes(n)), 0, n)
+    gpu.free(d)
+    assert np.array_equal(got, acu.unpack_bits(oracle.generate_bits(46, 5, 0.1, n), 0, n))
+    cnt = C.c_int64(0)
