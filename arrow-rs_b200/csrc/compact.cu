@@ -271,6 +271,119 @@ __global__ void __launch_bounds__(256, 4) k_filter_values(const FilterArgs a) {
   }
 }
 
+// Same compaction, but the predicated 16-byte loads land in a warp-private shared-memory
+// buffer through cp.async (LDGSTS) instead of registers: a warp keeps ALL of a tile's needed
+// sectors in flight at once (registers only allowed 8 chunks per lane), which is what a
+// latency-bound sparse read needs. Used when the values base is 16-B aligned.
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int W> struct AsyncCfg {
+  static constexpr int PASS_BYTES = (TILE_ROWS * W < 8192) ? TILE_ROWS * W : 8192;  // per-warp buffer
+  static constexpr int PASS_ROWS = PASS_BYTES / W;
+  static constexpr int PASSES = TILE_ROWS / PASS_ROWS;
+  static constexpr int CPP = PASS_BYTES / 16;  // 16-byte chunks per pass
+  static constexpr int ITERS = CPP / 32;
+};
+
+template <int W>
+__global__ void __launch_bounds__(256) k_filter_values_async(const FilterArgs a) {
+  using C = AsyncCfg<W>;
+  constexpr int RPC = W <= 16 ? 16 / W : 1;
+  constexpr int CPR = W <= 16 ? 1 : W / 16;
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint4 *buf = reinterpret_cast<uint4 *>(s_raw + (size_t)wid * C::PASS_BYTES);
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+
+  int64_t t = warp;
+  uint64_t m_next = 0, off_next = 0, end_next = 0;
+  if (t < a.n_tiles) {
+    if (lane < TILE_WORDS) m_next = __ldg(a.mask + t * TILE_WORDS + lane);
+    off_next = __ldg(a.tile_off + t);
+    end_next = __ldg(a.tile_off + t + 1);
+  }
+  for (; t < a.n_tiles; t += nwarps) {
+    const uint64_t m = m_next, out0 = off_next, cnt = end_next - off_next;
+    const int64_t tn = t + nwarps;
+    if (tn < a.n_tiles) {
+      m_next = (lane < TILE_WORDS) ? __ldg(a.mask + tn * TILE_WORDS + lane) : 0ull;
+      off_next = __ldg(a.tile_off + tn);
+      end_next = __ldg(a.tile_off + tn + 1);
+    }
+    if (cnt == 0) continue;
+    const uint32_t c = __popcll(m);
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < TILE_WORDS; o <<= 1) {
+      uint32_t y = __shfl_up_sync(ACU_FULL_MASK, incl, o);
+      if (lane >= o) incl += y;
+    }
+    const uint32_t pref = incl - c;
+    const uint8_t *src = a.values + (size_t)t * TILE_ROWS * W;
+    uint8_t *dst = a.out + (size_t)out0 * W;
+#pragma unroll 1
+    for (int pass = 0; pass < C::PASSES; ++pass) {
+      const int row_base = pass * C::PASS_ROWS;
+      // ---- issue: every needed chunk of the pass goes in flight ----
+#pragma unroll
+      for (int j = 0; j < C::ITERS; ++j) {
+        const int cidx = j * 32 + lane;
+        const int r = row_base + cidx * RPC / CPR;
+        const uint64_t word = __shfl_sync(ACU_FULL_MASK, m, r >> 6);
+        const uint32_t bits = (uint32_t)(word >> (r & 63)) & ((1u << RPC) - 1u);
+        if (bits) cp_async16(buf + cidx, src + ((size_t)pass * C::CPP + cidx) * 16);
+      }
+      cp_async_wait_all();
+      __syncwarp();
+      // ---- consume: rank and store the selected elements ----
+#pragma unroll
+      for (int j = 0; j < C::ITERS; ++j) {
+        const int cidx = j * 32 + lane;
+        const int r = row_base + cidx * RPC / CPR;
+        const uint64_t word = __shfl_sync(ACU_FULL_MASK, m, r >> 6);
+        const uint32_t wp = __shfl_sync(ACU_FULL_MASK, pref, r >> 6);
+        const uint32_t bits = (uint32_t)(word >> (r & 63)) & ((1u << RPC) - 1u);
+        if (!bits) continue;
+        const uint32_t rank = wp + __popcll(word & ((1ull << (r & 63)) - 1ull));
+        const uint4 v = buf[cidx];
+        if constexpr (W == 8) {
+          uint64_t *o = reinterpret_cast<uint64_t *>(dst) + rank;
+          if (bits & 1u) *o++ = (uint64_t)v.x | ((uint64_t)v.y << 32);
+          if (bits & 2u) *o = (uint64_t)v.z | ((uint64_t)v.w << 32);
+        } else if constexpr (W == 4) {
+          uint32_t *o = reinterpret_cast<uint32_t *>(dst) + rank;
+          if (bits & 1u) *o++ = v.x;
+          if (bits & 2u) *o++ = v.y;
+          if (bits & 4u) *o++ = v.z;
+          if (bits & 8u) *o = v.w;
+        } else if constexpr (W == 2) {
+          uint16_t *o = reinterpret_cast<uint16_t *>(dst) + rank;
+          const uint16_t *ve = reinterpret_cast<const uint16_t *>(&v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if ((bits >> e) & 1u) *o++ = ve[e];
+        } else if constexpr (W == 1) {
+          uint8_t *o = dst + rank;
+          const uint8_t *ve = reinterpret_cast<const uint8_t *>(&v);
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if ((bits >> e) & 1u) *o++ = ve[e];
+        } else {
+          const int half = cidx % CPR;
+          uint64_t *o = reinterpret_cast<uint64_t *>(dst + (size_t)rank * W + half * 16);
+          o[0] = (uint64_t)v.x | ((uint64_t)v.y << 32);
+          o[1] = (uint64_t)v.z | ((uint64_t)v.w << 32);
+        }
+      }
+      __syncwarp();  // the buffer is reused by the next pass / tile
+    }
+  }
+}
+
 // ---- bit compaction (validity / boolean values): software PEXT --------------------------
 // One lane per mask word; a warp covers 32 consecutive words (two tiles).
 __global__ void __launch_bounds__(256) k_compress_bits(const uint8_t *__restrict__ src, int64_t soff, int64_t len,
@@ -297,13 +410,25 @@ __global__ void __launch_bounds__(256) k_compress_bits(const uint8_t *__restrict
     const uint64_t base = __ldg(tile_off + (w0 >> 4));  // first output bit of this 32-word group
     uint64_t bits = 0;
     if (m) {
+      // PEXT in 32-bit halves (64-bit shifts / ffs are multi-instruction on the SM)
       const uint64_t v = ld_bits64(src, soff + (w << 6), soff + len);
+      uint32_t m0 = (uint32_t)m, m1 = (uint32_t)(m >> 32);
+      const uint32_t v0 = (uint32_t)v, v1 = (uint32_t)(v >> 32);
+      uint32_t lo = 0, hi = 0;  // compressed halves: lo has popc(m0) bits, hi has popc(m1) bits
       int k = 0;
-      while (m) {  // PEXT: gather the bits of v selected by m
-        const int b = __ffsll((long long)m) - 1;
-        m &= m - 1;
-        bits |= ((v >> b) & 1ull) << k++;
+      while (m0) {
+        const int b = __ffs((int)m0) - 1;
+        m0 &= m0 - 1;
+        lo |= ((v0 >> b) & 1u) << k++;
       }
+      const int k0 = k;
+      k = 0;
+      while (m1) {
+        const int b = __ffs((int)m1) - 1;
+        m1 &= m1 - 1;
+        hi |= ((v1 >> b) & 1u) << k++;
+      }
+      bits = (uint64_t)lo | ((uint64_t)hi << k0);  // k0 <= 32
     }
     valid_cnt += __popcll(bits);
     // assemble in a warp-private window aligned to the first output word
@@ -360,8 +485,16 @@ acu_status slice_nulls(acu_ctx *ctx, const acu_array *a, int64_t count, acu_arra
 
 template <int W>
 acu_status launch_filter(acu_ctx *ctx, const FilterArgs &fa) {
-  ACU_LAUNCH_TIMED(ctx, ACU_K_FILTER, (k_filter_values<W>), acu_wave_grid(ctx, k_filter_values<W>, 256, 0, (fa.n_tiles + 7) / 8),
-                   256, 0, fa);
+  if (fa.aligned16) {
+    constexpr size_t smem = 8 * (size_t)AsyncCfg<W>::PASS_BYTES;  // 8 warps x per-warp landing buffer
+    if (ctx->occupancy.find(reinterpret_cast<const void *>(k_filter_values_async<W>)) == ctx->occupancy.end())  // first use on this device
+      ACU_CUDA(ctx, cudaFuncSetAttribute(k_filter_values_async<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ACU_LAUNCH_TIMED(ctx, ACU_K_FILTER, (k_filter_values_async<W>),
+                     acu_wave_grid(ctx, k_filter_values_async<W>, 256, smem, (fa.n_tiles + 7) / 8), 256, smem, fa);
+  } else {
+    ACU_LAUNCH_TIMED(ctx, ACU_K_FILTER, (k_filter_values<W>), acu_wave_grid(ctx, k_filter_values<W>, 256, 0, (fa.n_tiles + 7) / 8),
+                     256, 0, fa);
+  }
   return ACU_OK;
 }
 

@@ -154,23 +154,24 @@ struct ArithParams {
   int zero_nulls;          // try_binary / try_unary: zero under nulls, op only at valid slots
 };
 
-// Steady state: a warp owns "groups" of U strips (all rows in bounds, no checks); the ragged
-// remainder (< U*R rows) is finished element-wise by warp 0 so that its bounds-checked code
-// does not inflate the register allocation of the streaming loop.
+// Steady state: a warp owns "super-groups" of 2048 rows = 32 validity words (lane l <-> word
+// l: ONE coalesced 256-B bitmap access per operand per super-group), processed as groups of
+// U strips whose loads are all issued before any use. The ragged remainder (< 2048 rows) is
+// finished element-wise by warp 0 so that bounds-checked code stays out of the streaming loop.
 template <class T, int CLS, int EPL>
 __global__ void __launch_bounds__(256, (CLS == CLS_WRAP ? 4 : 3)) k_arith(const ArithParams<T> p) {
   constexpr int R = (32 * EPL > 64) ? 32 * EPL : 64;  // rows per strip
   constexpr int LPS = R / (32 * EPL);                 // loads per lane per strip
-  constexpr int WORDS = R / 64;                       // validity words per strip
   constexpr int U = (LPS >= 2) ? 2 : 4;               // strips in flight per warp
   constexpr int GROUP = U * R;                        // rows per group
-  constexpr int GWORDS = U * WORDS;                   // validity words per group (<= 32)
+  constexpr int SG = 2048;                            // rows per super-group
+  constexpr int GPS = SG / GROUP;                     // groups per super-group
   constexpr bool fallible = (CLS != CLS_WRAP) && !is_fp<T>::value;
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t n = p.n;
-  const int64_t groups = n / GROUP;
+  const int64_t sgroups = n / SG;
   const bool has_valid = p.out_valid != nullptr;
   T sa = T(), sb = T();
   if (p.a_scalar) sa = __ldg(p.a);
@@ -178,58 +179,62 @@ __global__ void __launch_bounds__(256, (CLS == CLS_WRAP ? 4 : 3)) k_arith(const 
   unsigned valid_cnt = 0;
   unsigned long long err = ~0ull;
 
-  for (int64_t g = warp; g < groups; g += nwarps) {
-    const int64_t base = g * GROUP;
-    const T *__restrict__ pa = p.a + base + lane * EPL;
-    const T *__restrict__ pb = p.b + base + lane * EPL;
-    Pack<T, EPL> va[U * LPS], vb[U * LPS];
-    // ---- every load of the group is issued before any use (memory-level parallelism) ----
-#pragma unroll
-    for (int k = 0; k < U * LPS; ++k) {
-      if (!p.a_scalar) va[k] = pack_load<T, EPL>(pa + k * 32 * EPL);
-      if (!p.b_scalar) vb[k] = pack_load<T, EPL>(pb + k * 32 * EPL);
-    }
-    uint64_t vw = ~0ull;  // lane l < GWORDS owns validity word l of the group
-    if (has_valid && lane < GWORDS) {
-      const int64_t row = base + lane * 64;
+  for (int64_t sg = warp; sg < sgroups; sg += nwarps) {
+    const int64_t sbase = sg * SG;
+    uint64_t vw = ~0ull;  // lane l owns validity word l of the super-group
+    if (has_valid) {
+      const int64_t row = sbase + lane * 64;
       if (p.av) vw &= ld_bits64(p.av, p.aoff + row, p.aoff + n);
       if (p.bv) vw &= ld_bits64(p.bv, p.boff + row, p.boff + n);
       p.out_valid[row >> 6] = vw;
       valid_cnt += __popcll(vw);
     }
-    // ---- compute + store ----
-    T *__restrict__ po = p.out + base + lane * EPL;
+#pragma unroll 1
+    for (int gi = 0; gi < GPS; ++gi) {
+      const int64_t base = sbase + gi * GROUP;
+      const T *__restrict__ pa = p.a + base + lane * EPL;
+      const T *__restrict__ pb = p.b + base + lane * EPL;
+      Pack<T, EPL> va[U * LPS], vb[U * LPS];
+      // ---- every load of the group is issued before any use (memory-level parallelism) ----
 #pragma unroll
-    for (int k = 0; k < U * LPS; ++k) {
-      uint32_t bits = ~0u;
-      if (fallible && p.zero_nulls) {
-        const int pos = k * 32 * EPL + lane * EPL;  // row inside the group
-        const uint64_t w = __shfl_sync(ACU_FULL_MASK, vw, pos >> 6);
-        bits = (uint32_t)(w >> (pos & 63));
+      for (int k = 0; k < U * LPS; ++k) {
+        if (!p.a_scalar) va[k] = pack_load<T, EPL>(pa + k * 32 * EPL);
+        if (!p.b_scalar) vb[k] = pack_load<T, EPL>(pb + k * 32 * EPL);
       }
-      Pack<T, EPL> o;
+      // ---- compute + store ----
+      T *__restrict__ po = p.out + base + lane * EPL;
 #pragma unroll
-      for (int e = 0; e < EPL; ++e) {
-        const T l = p.a_scalar ? sa : va[k].v[e];
-        const T r = p.b_scalar ? sb : vb[k].v[e];
-        T x;
-        const bool bad = apply_op<T, CLS>(p.op, l, r, x);
-        if (fallible) {
-          if (!((bits >> e) & 1u)) x = T();
-          else if (bad) {
-            const unsigned long long i = (unsigned long long)(base + k * 32 * EPL + lane * EPL + e);
-            err = i < err ? i : err;
-          }
+      for (int k = 0; k < U * LPS; ++k) {
+        uint32_t bits = ~0u;
+        if (fallible && p.zero_nulls) {
+          const int pos = gi * GROUP + k * 32 * EPL + lane * EPL;  // row inside the super-group
+          const uint64_t w = __shfl_sync(ACU_FULL_MASK, vw, pos >> 6);
+          bits = (uint32_t)(w >> (pos & 63));
         }
-        o.v[e] = x;
+        Pack<T, EPL> o;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          const T l = p.a_scalar ? sa : va[k].v[e];
+          const T r = p.b_scalar ? sb : vb[k].v[e];
+          T x;
+          const bool bad = apply_op<T, CLS>(p.op, l, r, x);
+          if (fallible) {
+            if (!((bits >> e) & 1u)) x = T();
+            else if (bad) {
+              const unsigned long long i = (unsigned long long)(base + k * 32 * EPL + lane * EPL + e);
+              err = i < err ? i : err;
+            }
+          }
+          o.v[e] = x;
+        }
+        pack_store<T, EPL>(po + k * 32 * EPL, o);
       }
-      pack_store<T, EPL>(po + k * 32 * EPL, o);
     }
   }
 
   // ---- ragged remainder: 64-row strips, lane owns rows l and l+32 ----
   if (warp == 0) {
-    for (int64_t row = groups * GROUP; row < n; row += 64) {
+    for (int64_t row = sgroups * SG; row < n; row += 64) {
       uint64_t vw = ones_to(row, n);
       if (has_valid) {
         if (p.av) vw &= ld_bits64(p.av, p.aoff + row, p.aoff + n);
@@ -266,13 +271,10 @@ acu_status launch_arith(acu_ctx *ctx, const ArithParams<T> &p) {
   bool aligned = ((uintptr_t)p.out % 16 == 0) && (p.a_scalar || (uintptr_t)p.a % 16 == 0) &&
                  (p.b_scalar || (uintptr_t)p.b % 16 == 0);
   if (aligned) {
-    constexpr int R = (32 * EPLV > 64) ? 32 * EPLV : 64;
-    int64_t groups = p.n / (4 * R) + 1;
-    int64_t blocks = (groups + 7) / 8;
+    int64_t blocks = (p.n / 2048 + 1 + 7) / 8;  // 8 warps per CTA, one 2048-row super-group per warp step
     ACU_LAUNCH_TIMED(ctx, ACU_K_ARITH, (k_arith<T, CLS, EPLV>), acu_wave_grid(ctx, k_arith<T, CLS, EPLV>, 256, 0, blocks), 256, 0, p);
   } else {
-    int64_t groups = p.n / 128 + 1;
-    int64_t blocks = (groups + 7) / 8;
+    int64_t blocks = (p.n / 2048 + 1 + 7) / 8;
     ACU_LAUNCH_TIMED(ctx, ACU_K_ARITH, (k_arith<T, CLS, 1>), acu_wave_grid(ctx, k_arith<T, CLS, 1>, 256, 0, blocks), 256, 0, p);
   }
   return ACU_OK;

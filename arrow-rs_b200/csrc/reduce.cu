@@ -77,38 +77,45 @@ __global__ void __launch_bounds__(256) k_reduce(const T *__restrict__ v, int64_t
                                                 int64_t voff, typename AccOf<T, OP>::type *__restrict__ partial,
                                                 unsigned int *__restrict__ ticket, unsigned long long *__restrict__ res) {
   using A = typename AccOf<T, OP>::type;
-  constexpr int U = 4;
+  constexpr int U = 8;  // strips (64 rows) in flight per warp: 8 x 2 loads per lane
   __shared__ A s_part[8];
   __shared__ bool s_last;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t strips = (n + 63) >> 6;
+  const int64_t sgroups = (n + 2047) >> 11;  // super-group = 32 strips = 2048 rows = 32 validity words
   A acc = acc_identity<A, OP>();
   unsigned valid_cnt = 0;
-  for (int64_t s0 = warp * U; s0 < strips; s0 += nwarps * U) {
-    T x[U][2];
-    uint64_t vw[U];
+  for (int64_t sg = warp; sg < sgroups; sg += nwarps) {
+    const int64_t sbase = sg << 11;
+    // lane l owns validity word l of the super-group (one coalesced 256-B bitmap access)
+    const int64_t wrow = sbase + lane * 64;
+    const int64_t k = n - wrow;
+    uint64_t vw = k >= 64 ? ~0ull : (k <= 0 ? 0ull : ((~0ull) >> (64 - k)));
+    if (valid) vw &= ld_bits64(valid, voff + wrow, voff + n);
+    valid_cnt += __popcll(vw);
+#pragma unroll 1
+    for (int s0 = 0; s0 < 32; s0 += U) {
+      if (sbase + s0 * 64 >= n) break;
+      T x[U][2];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t row = (s0 + u) * 64;
-      const int64_t k = n - row;
-      vw[u] = k >= 64 ? ~0ull : (k <= 0 ? 0ull : ((~0ull) >> (64 - k)));
-      if (valid) vw[u] &= ld_bits64(valid, voff + row, voff + n);
+      for (int u = 0; u < U; ++u) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int64_t i = row + h * 32 + lane;
-        x[u][h] = i < n ? __ldg(v + i) : T();
+        for (int h = 0; h < 2; ++h) {
+          const int64_t i = sbase + (s0 + u) * 64 + h * 32 + lane;
+          x[u][h] = i < n ? __ldg(v + i) : T();
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint64_t w = __shfl_sync(ACU_FULL_MASK, vw, s0 + u);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          if ((w >> (h * 32 + lane)) & 1ull) acc = acc_merge<A, OP>(acc, acc_lift<T, OP>(x[u][h]));
       }
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h)
-        if ((vw[u] >> (h * 32 + lane)) & 1ull) acc = acc_merge<A, OP>(acc, acc_lift<T, OP>(x[u][h]));
-      if (lane == 0) valid_cnt += __popcll(vw[u]);
-    }
   }
+  valid_cnt = warp_sum(valid_cnt);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc = acc_merge<A, OP>(acc, shfl_down_any(acc, o));
   if (lane == 0) {
@@ -146,7 +153,7 @@ template <class T, int OP>
 acu_status reduce_launch(acu_ctx *ctx, const acu_array *a, const uint8_t *valid) {
   using A = typename AccOf<T, OP>::type;
   const int64_t strips = (a->len + 63) >> 6;
-  const int grid = acu_wave_grid(ctx, k_reduce<T, OP>, 256, 0, (strips + 31) / 32);
+  const int grid = acu_wave_grid(ctx, k_reduce<T, OP>, 256, 0, (strips / 32 + 1 + 7) / 8);
   void *scratch;
   ACU_TRY(acu_scratch(ctx, 256 + (size_t)grid * sizeof(A), &scratch));
   unsigned int *ticket = static_cast<unsigned int *>(scratch);
