@@ -293,8 +293,12 @@ __global__ void __launch_bounds__(256) k_filter_values_async(const FilterArgs a)
   using C = AsyncCfg<W>;
   constexpr int RPC = W <= 16 ? 16 / W : 1;
   constexpr int CPR = W <= 16 ? 1 : W / 16;
+  constexpr int RPJ = 32 * RPC / CPR;  // rows covered by one warp-wide chunk round
   extern __shared__ __align__(16) uint8_t s_raw[];
+  __shared__ uint64_t s_m[8][TILE_WORDS];   // the tile's mask words ...
+  __shared__ uint32_t s_p[8][TILE_WORDS];   // ... and their exclusive popcount prefix (LDS broadcast beats 3 SHFL per round)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int lr = lane * RPC / CPR;           // lane's row offset inside a chunk round
   uint4 *buf = reinterpret_cast<uint4 *>(s_raw + (size_t)wid * C::PASS_BYTES);
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -322,34 +326,32 @@ __global__ void __launch_bounds__(256) k_filter_values_async(const FilterArgs a)
       uint32_t y = __shfl_up_sync(ACU_FULL_MASK, incl, o);
       if (lane >= o) incl += y;
     }
-    const uint32_t pref = incl - c;
+    if (lane < TILE_WORDS) { s_m[wid][lane] = m; s_p[wid][lane] = incl - c; }
+    __syncwarp();
     const uint8_t *src = a.values + (size_t)t * TILE_ROWS * W;
     uint8_t *dst = a.out + (size_t)out0 * W;
 #pragma unroll 1
     for (int pass = 0; pass < C::PASSES; ++pass) {
       const int row_base = pass * C::PASS_ROWS;
+      const uint8_t *psrc = src + ((size_t)pass * C::CPP + lane) * 16;
       // ---- issue: every needed chunk of the pass goes in flight ----
 #pragma unroll
       for (int j = 0; j < C::ITERS; ++j) {
-        const int cidx = j * 32 + lane;
-        const int r = row_base + cidx * RPC / CPR;
-        const uint64_t word = __shfl_sync(ACU_FULL_MASK, m, r >> 6);
-        const uint32_t bits = (uint32_t)(word >> (r & 63)) & ((1u << RPC) - 1u);
-        if (bits) cp_async16(buf + cidx, src + ((size_t)pass * C::CPP + cidx) * 16);
+        const int r = row_base + j * RPJ + lr;
+        const uint32_t bits = (uint32_t)(s_m[wid][r >> 6] >> (r & 63)) & ((1u << RPC) - 1u);
+        if (bits) cp_async16(buf + j * 32 + lane, psrc + (size_t)j * 512);
       }
       cp_async_wait_all();
       __syncwarp();
       // ---- consume: rank and store the selected elements ----
 #pragma unroll
       for (int j = 0; j < C::ITERS; ++j) {
-        const int cidx = j * 32 + lane;
-        const int r = row_base + cidx * RPC / CPR;
-        const uint64_t word = __shfl_sync(ACU_FULL_MASK, m, r >> 6);
-        const uint32_t wp = __shfl_sync(ACU_FULL_MASK, pref, r >> 6);
+        const int r = row_base + j * RPJ + lr;
+        const uint64_t word = s_m[wid][r >> 6];
         const uint32_t bits = (uint32_t)(word >> (r & 63)) & ((1u << RPC) - 1u);
         if (!bits) continue;
-        const uint32_t rank = wp + __popcll(word & ((1ull << (r & 63)) - 1ull));
-        const uint4 v = buf[cidx];
+        const uint32_t rank = s_p[wid][r >> 6] + __popcll(word & ((1ull << (r & 63)) - 1ull));
+        const uint4 v = buf[j * 32 + lane];
         if constexpr (W == 8) {
           uint64_t *o = reinterpret_cast<uint64_t *>(dst) + rank;
           if (bits & 1u) *o++ = (uint64_t)v.x | ((uint64_t)v.y << 32);
@@ -373,13 +375,13 @@ __global__ void __launch_bounds__(256) k_filter_values_async(const FilterArgs a)
           for (int e = 0; e < 16; ++e)
             if ((bits >> e) & 1u) *o++ = ve[e];
         } else {
-          const int half = cidx % CPR;
+          const int half = lane % CPR;  // (j*32 + lane) % CPR, CPR divides 32
           uint64_t *o = reinterpret_cast<uint64_t *>(dst + (size_t)rank * W + half * 16);
           o[0] = (uint64_t)v.x | ((uint64_t)v.y << 32);
           o[1] = (uint64_t)v.z | ((uint64_t)v.w << 32);
         }
       }
-      __syncwarp();  // the buffer is reused by the next pass / tile
+      __syncwarp();  // the buffers are reused by the next pass / tile
     }
   }
 }

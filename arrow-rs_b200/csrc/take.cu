@@ -19,8 +19,8 @@
 #include "bitmap.cuh"
 #include "internal.cuh"
 
-#define TAKE_TILE 2048
-#define TAKE_PER_THREAD (TAKE_TILE / 256)
+#define TAKE_WTILE 256  // indices per warp tile
+#define TAKE_PER_LANE (TAKE_WTILE / 32)
 
 namespace {
 
@@ -99,81 +99,89 @@ template <> struct IdxOf<2> { using raw = uint16_t; };
 template <> struct IdxOf<3> { using raw = int16_t; };
 template <> struct IdxOf<4> { using raw = uint32_t; };
 template <> struct IdxOf<5> { using raw = uint64_t; };
-template <int IT> __device__ __forceinline__ uint64_t widen(typename IdxOf<IT>::raw v) {
-  if constexpr (IT == 1 || IT == 3) return (uint64_t)(uint32_t)(int32_t)v;  // `as u32` sign-extends
-  else return (uint64_t)v;
+// index after ToIndices: u32 for every source type but (u)int64 -> keeps the gather state in 32-bit registers
+template <int IT> struct WideOf { using type = typename std::conditional<IT == 5, uint64_t, uint32_t>::type; };
+template <int IT> __device__ __forceinline__ typename WideOf<IT>::type widen(typename IdxOf<IT>::raw v) {
+  if constexpr (IT == 1 || IT == 3) return (uint32_t)(int32_t)v;  // `as u32` sign-extends
+  else return (typename WideOf<IT>::type)v;
 }
 
-template <int W, int IT>
-__global__ void __launch_bounds__(256) k_take(const TakeArgs a) {
+// BOOL: take_boolean (bit gather of boolean VALUES, no value gather); else take_primitive.
+template <int W, int IT, bool BOOL>
+__global__ void __launch_bounds__(256, 3) k_take(const TakeArgs a) {
   using V = typename VecOf<W>::type;
   using I = typename IdxOf<IT>::raw;
-  __shared__ __align__(16) I s_idx[2][TAKE_TILE];
-  __shared__ __align__(8) uint64_t s_bar[2];
-  const int tid = threadIdx.x, lane = tid & 31;
+  // warp-private double-buffered index tiles: no CTA-wide barrier anywhere in the loop
+  __shared__ __align__(16) I s_idx[8][2][TAKE_WTILE];
+  __shared__ __align__(8) uint64_t s_bar[8][2];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const I *idx = static_cast<const I *>(a.idx);
-  const int64_t n_tiles = (a.m + TAKE_TILE - 1) / TAKE_TILE;
-  const bool gather_values = (W > 0) && a.values != nullptr;
+  const int64_t n_tiles = (a.m + TAKE_WTILE - 1) / TAKE_WTILE;
+  const bool gather_values = !BOOL && a.values != nullptr;
   unsigned valid_cnt = 0;
   unsigned long long err = ~0ull;
 
-  if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
+  if (lane == 0) { mbar_init(&s_bar[wid][0], 1); mbar_init(&s_bar[wid][1], 1); }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncthreads();
+  __syncwarp();
 
-  // stage tile `t` into buffer `b`
+  // stage tile `t` into this warp's buffer `b`
   auto stage = [&](int64_t t, int b) {
-    const int64_t j0 = t * TAKE_TILE;
-    const int cnt = (int)((a.m - j0) < TAKE_TILE ? (a.m - j0) : TAKE_TILE);
-    const bool bulk = a.use_bulk && cnt == TAKE_TILE;  // full tiles only: size % 16 == 0
+    const int64_t j0 = t * TAKE_WTILE;
+    const int cnt = (int)((a.m - j0) < TAKE_WTILE ? (a.m - j0) : TAKE_WTILE);
+    const bool bulk = a.use_bulk && cnt == TAKE_WTILE;  // full tiles only: size % 16 == 0
     if (bulk) {
-      if (tid == 0) {
-        mbar_expect_tx(&s_bar[b], (unsigned)(TAKE_TILE * sizeof(I)));
-        bulk_g2s(&s_idx[b][0], idx + j0, (unsigned)(TAKE_TILE * sizeof(I)), &s_bar[b]);
+      if (lane == 0) {
+        mbar_expect_tx(&s_bar[wid][b], (unsigned)(TAKE_WTILE * sizeof(I)));
+        bulk_g2s(&s_idx[wid][b][0], idx + j0, (unsigned)(TAKE_WTILE * sizeof(I)), &s_bar[wid][b]);
       }
     } else {
-      for (int k = tid; k < cnt; k += 256) s_idx[b][k] = __ldg(idx + j0 + k);
+      for (int k = lane; k < cnt; k += 32) s_idx[wid][b][k] = __ldg(idx + j0 + k);
     }
     return bulk;
   };
 
-  unsigned phase[2] = {0, 0};
-  int64_t t = blockIdx.x;
+  unsigned phase0 = 0, phase1 = 0;  // mbarrier parity per buffer (scalars: no local-memory array)
+  int64_t t = warp;
   bool cur_bulk = false;
   if (t < n_tiles) cur_bulk = stage(t, 0);
   int buf = 0;
-  for (; t < n_tiles; t += gridDim.x) {
-    const int64_t tn = t + gridDim.x;
+  for (; t < n_tiles; t += nwarps) {
+    const int64_t tn = t + nwarps;
     bool next_bulk = false;
     if (tn < n_tiles) next_bulk = stage(tn, buf ^ 1);  // prefetch while we gather
-    if (cur_bulk) { mbar_wait(&s_bar[buf], phase[buf]); phase[buf] ^= 1; }
-    else __syncthreads();
-
-    const int64_t j0 = t * TAKE_TILE;
-    uint64_t ix[TAKE_PER_THREAD];
-    bool live[TAKE_PER_THREAD], inb[TAKE_PER_THREAD];
-    V v[TAKE_PER_THREAD];
-    uint32_t bit[TAKE_PER_THREAD];
-#pragma unroll
-    for (int k = 0; k < TAKE_PER_THREAD; ++k) {
-      const int j = k * 256 + tid;
-      live[k] = j0 + j < a.m;
-      ix[k] = live[k] ? widen<IT>(s_idx[buf][j]) : 0ull;
-      inb[k] = live[k] && ix[k] < (uint64_t)a.n_values;
+    if (cur_bulk) {
+      mbar_wait(&s_bar[wid][buf], buf ? phase1 : phase0);
+      if (buf) phase1 ^= 1; else phase0 ^= 1;
     }
-    // ---- 8 independent gathers in flight per thread ----
+    else __syncwarp();
+
+    const int64_t j0 = t * TAKE_WTILE;
+    typename WideOf<IT>::type ix[TAKE_PER_LANE];
+    bool live[TAKE_PER_LANE], inb[TAKE_PER_LANE];
+    V v[TAKE_PER_LANE];
+    uint32_t bit[TAKE_PER_LANE];
 #pragma unroll
-    for (int k = 0; k < TAKE_PER_THREAD; ++k) {
+    for (int k = 0; k < TAKE_PER_LANE; ++k) {
+      const int j = k * 32 + lane;
+      live[k] = j0 + j < a.m;
+      ix[k] = live[k] ? widen<IT>(s_idx[wid][buf][j]) : 0;
+      inb[k] = live[k] && (uint64_t)ix[k] < (uint64_t)a.n_values;
+    }
+    // ---- 8 independent gathers in flight per lane ----
+#pragma unroll
+    for (int k = 0; k < TAKE_PER_LANE; ++k) {
       if (gather_values) v[k] = inb[k] ? gather_ld<V>(static_cast<const V *>(a.values) + ix[k]) : zero_of<V>();
       uint32_t b = 1u;
       if (a.vvalid) b = inb[k] ? ld_bit(a.vvalid, a.vvoff + (int64_t)ix[k]) : 0u;
-      if (a.vbits) b |= (inb[k] ? ld_bit(a.vbits, a.vboff + (int64_t)ix[k]) : 0u) << 1;
+      if (BOOL) b |= (inb[k] ? ld_bit(a.vbits, a.vboff + (int64_t)ix[k]) : 0u) << 1;
       bit[k] = b;
     }
 #pragma unroll
-    for (int k = 0; k < TAKE_PER_THREAD; ++k) {
-      const int j = k * 256 + tid;
-      const int64_t gj = j0 + j;  // warp-uniform base: gj - lane is a multiple of 32
+    for (int k = 0; k < TAKE_PER_LANE; ++k) {
+      const int64_t gj = j0 + k * 32 + lane;  // gj - lane is a multiple of 32: lane == output bit
       uint32_t iv = ~0u;
       if (a.ivalid) iv = ld_bits32(a.ivalid, a.ivoff + (gj - lane), a.ivoff + a.m);
       const bool idx_valid = live[k] && ((iv >> lane) & 1u);
@@ -189,13 +197,13 @@ __global__ void __launch_bounds__(256) k_take(const TakeArgs a) {
         const uint32_t word = __ballot_sync(ACU_FULL_MASK, ob);
         if (lane == 0 && gj < a.m) { a.out_valid[gj >> 5] = word; valid_cnt += __popc(word); }
       }
-      if (a.out_bits) {  // take_bits on boolean values: unset at null indices
+      if (BOOL) {  // take_bits on boolean values: unset at null indices
         const bool ob = live[k] && counts_as_valid_idx && ((bit[k] >> 1) & 1u);
         const uint32_t word = __ballot_sync(ACU_FULL_MASK, ob);
         if (lane == 0 && gj < a.m) a.out_bits[gj >> 5] = word;
       }
     }
-    __syncthreads();  // everyone is done with s_idx[buf] before it is refilled
+    __syncwarp();  // the whole warp is done with s_idx[wid][buf] before it is refilled
     buf ^= 1;
     cur_bulk = next_bulk;
   }
@@ -247,9 +255,13 @@ uint64_t index_max(acu_dtype t) {
 
 template <int W>
 acu_status launch_take_w(acu_ctx *ctx, int kind, const TakeArgs &ta) {
-  const int64_t tiles = (ta.m + TAKE_TILE - 1) / TAKE_TILE;
+  const int64_t tiles = ((ta.m + TAKE_WTILE - 1) / TAKE_WTILE + 7) / 8;  // CTAs: 8 warp tiles each
 #define ACU_TAKE_CASE(IT)                                                                                   \
-  case IT: ACU_LAUNCH_TIMED(ctx, ACU_K_TAKE, (k_take<W, IT>), acu_wave_grid(ctx, k_take<W, IT>, 256, 0, tiles), 256, 0, ta); \
+  case IT:                                                                                                                   \
+    if (W == 1 && ta.vbits)                                                                                                  \
+      ACU_LAUNCH_TIMED(ctx, ACU_K_TAKE, (k_take<1, IT, true>), acu_wave_grid(ctx, k_take<1, IT, true>, 256, 0, tiles), 256, 0, ta); \
+    else                                                                                                                     \
+      ACU_LAUNCH_TIMED(ctx, ACU_K_TAKE, (k_take<W, IT, false>), acu_wave_grid(ctx, k_take<W, IT, false>, 256, 0, tiles), 256, 0, ta); \
     break;
   switch (kind) {
     ACU_TAKE_CASE(0) ACU_TAKE_CASE(1) ACU_TAKE_CASE(2) ACU_TAKE_CASE(3) ACU_TAKE_CASE(4) ACU_TAKE_CASE(5)

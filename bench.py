@@ -167,28 +167,43 @@ class Workload:
 
     def step(self, timer=None):
         """filter -> take -> add -> sum. Returns (sum_bits, valid_count)."""
-        abi, ctx = self.abi, self.ctx
-        lib, h = ctx.lib, ctx.h
         pred = self.arr(self.d_pred, None, self.n, 0)
         col = self.arr(self.d_i64, self.d_i64_valid, self.n, self.nc_i64)
-        plan = C.c_void_p()
-        ctx.check(lib.acu_filter_plan_create(h, C.byref(pred), C.byref(plan)))
-        try:
-            ctx.check(lib.acu_filter_primitive(h, plan, 8, C.byref(col), C.byref(self.out_filter)))
-        finally:
-            lib.acu_filter_plan_destroy(h, plan)
         idx = self.arr(self.d_idx, None, self.m, 0)
-        ctx.check(lib.acu_take_primitive(h, 8, C.byref(col), C.byref(idx), abi.U32, 0, C.byref(self.out_take)))
         a = self.arr(self.d_a, self.d_a_valid, self.n, self.nc_a)
         b = self.arr(self.d_b, self.d_b_valid, self.n, self.nc_b)
-        ctx.check(lib.acu_arith(h, abi.F64, abi.ADD, C.byref(a), C.byref(b), C.byref(self.out_add)))
-        taken = self.arr(self.out_take.values, self.out_take.validity if self.out_take.has_validity else None, self.m,
-                         self.out_take.null_count if self.out_take.has_validity else 0)
-        bits, cnt = C.c_uint64(0), C.c_int64(0)
-        ctx.check(lib.acu_aggregate(h, abi.I64, abi.SUM, C.byref(taken), C.byref(bits), C.byref(cnt)))
+        return hot_path_step(self.ctx, self.abi, pred, col, idx, a, b, self.out_filter, self.out_take, self.out_add, allreduce=True)
+
+
+def make_arr(abi, values, validity, n, null_count):
+    a = abi.Array()
+    a.values, a.values_offset = values, 0
+    a.validity, a.validity_offset = validity, 0
+    a.len, a.null_count, a.is_scalar = n, null_count, 0
+    return a
+
+
+def hot_path_step(ctx, abi, pred, col, idx, a, b, out_filter, out_take, out_add, allreduce):
+    """One pass of the hot path through the C ABI (device pointers):
+    filter(col, pred) -> take(col, idx) -> add(a, b) -> sum(taken) [-> NCCL all-reduce]."""
+    lib, h = ctx.lib, ctx.h
+    plan = C.c_void_p()
+    ctx.check(lib.acu_filter_plan_create(h, C.byref(pred), C.byref(plan)))
+    try:
+        ctx.check(lib.acu_filter_primitive(h, plan, 8, C.byref(col), C.byref(out_filter)))
+    finally:
+        lib.acu_filter_plan_destroy(h, plan)
+    ctx.check(lib.acu_take_primitive(h, 8, C.byref(col), C.byref(idx), abi.U32, 0, C.byref(out_take)))
+    ctx.check(lib.acu_arith(h, abi.F64, abi.ADD, C.byref(a), C.byref(b), C.byref(out_add)))
+    taken = make_arr(abi, out_take.values, out_take.validity if out_take.has_validity else None, out_take.len,
+                     out_take.null_count if out_take.has_validity else 0)
+    bits, cnt = C.c_uint64(0), C.c_int64(0)
+    ctx.check(lib.acu_aggregate(h, abi.I64, abi.SUM, C.byref(taken), C.byref(bits), C.byref(cnt)))
+    if allreduce:
         pb, pc = (C.c_uint64 * 1)(bits.value), (C.c_int64 * 1)(cnt.value)
         ctx.check(lib.acu_comm_allreduce_aggregates(h, abi.I64, abi.SUM, pb, pc, 1))
         return pb[0], pc[0]
+    return bits.value, cnt.value
 
 
 class HostStaged:
@@ -234,6 +249,142 @@ class HostStaged:
         for _, pv, _, pb, _ in self.outs.values():
             ctx.lib.acu_host_free(ctx.h, pv)
             ctx.lib.acu_host_free(ctx.h, pb)
+
+
+class HostPipelined:
+    """e2e arm (default): the table starts in pinned HOST memory and is streamed through the C ABI as
+    RecordBatches of `batch_rows` rows (BASELINE.json configs[4] streams 2^26-row batches) by `n_workers`
+    contexts = streams = host threads on the same GPU, so one batch's H2D, another's kernels and a third's
+    D2H overlap (PCIe is full duplex). Every batch does: H2D of its 8 input buffers -> the hot-path step ->
+    D2H of filter / take / add outputs."""
+
+    def __init__(self, wl, device, batch_rows=1 << 26, n_workers=3):
+        import acu
+        self.wl, self.acu, self.abi, self.device = wl, acu, wl.abi, device
+        ctx, abi, n = wl.ctx, wl.abi, wl.n
+        lib, h = ctx.lib, ctx.h
+        self.n_workers = n_workers
+        bb = wl.bb
+        self.host = {}
+        for name, dptr, nbytes in [("i64", wl.d_i64, n * 8), ("i64_valid", wl.d_i64_valid, bb), ("pred", wl.d_pred, bb),
+                                   ("a", wl.d_a, n * 8), ("b", wl.d_b, n * 8), ("a_valid", wl.d_a_valid, bb), ("b_valid", wl.d_b_valid, bb)]:
+            p = C.c_void_p()
+            ctx.check(lib.acu_host_alloc(h, nbytes, C.byref(p)))
+            ctx.check(lib.acu_memcpy_d2h(h, p, dptr, nbytes))
+            self.host[name] = p.value
+        # batches: 64-row aligned ranges; per-batch counts (selected rows, null counts) are metadata
+        # a RecordBatch carries (NullBuffer caches null_count)
+        self.batches = []
+        m_off = 0
+
+        def count(dptr, lo, rows):
+            c = C.c_int64(0)
+            ctx.check(lib.acu_bitmap_count(h, dptr + lo // 8, 0, None, 0, rows, C.byref(c)))
+            return c.value
+
+        p_idx = C.c_void_p()
+        ctx.check(lib.acu_host_alloc(h, max(wl.m, 1) * 4, C.byref(p_idx)))
+        self.host["idx"] = p_idx.value
+        for lo in range(0, n, batch_rows):
+            rows = min(batch_rows, n - lo)
+            m_b = count(wl.d_pred, lo, rows)
+            ncs = tuple(rows - count(d, lo, rows) for d in (wl.d_i64_valid, wl.d_a_valid, wl.d_b_valid))
+            # batch-local take indices (an input of the step, like on the CPU arm)
+            pred = make_arr(abi, wl.d_pred + lo // 8, None, rows, 0)
+            plan = C.c_void_p()
+            ctx.check(lib.acu_filter_plan_create(h, C.byref(pred), C.byref(plan)))
+            ctx.check(lib.acu_filter_plan_indices(h, plan, abi.U32, wl.d_idx))
+            lib.acu_filter_plan_destroy(h, plan)
+            ctx.check(lib.acu_memcpy_d2h(h, p_idx.value + m_off * 4, wl.d_idx, m_b * 4))
+            self.batches.append({"lo": lo, "rows": rows, "m": m_b, "m_off": m_off, "ncs": ncs})
+            m_off += m_b
+        self.m_max = max(b["m"] for b in self.batches)
+        self.rows_max = max(b["rows"] for b in self.batches)
+        # pinned outputs: add at row offsets; filter/take values at selected-row offsets; per-batch validity bitmaps
+        self.out = {}
+        mb_max = abi.bitmap_bytes(self.m_max)
+        for name, nbytes in [("add", n * 8), ("add_valid", bb + 8 * len(self.batches)), ("filter", m_off * 8), ("take", m_off * 8),
+                             ("filter_valid", mb_max * len(self.batches)), ("take_valid", mb_max * len(self.batches))]:
+            p = C.c_void_p()
+            ctx.check(lib.acu_host_alloc(h, max(nbytes, 8), C.byref(p)))
+            self.out[name] = p.value
+        self.mb_max = mb_max
+        self.h2d_bytes = n * 24 + 4 * bb + m_off * 4
+        self.d2h_bytes = n * 8 + bb + 2 * (m_off * 8 + abi.bitmap_bytes(m_off))
+        self.workers = [self._make_worker() for _ in range(n_workers)]
+
+    def _make_worker(self):
+        acu, abi = self.acu, self.abi
+        ctx = acu.Context(self.device)
+        rb, mb = abi.bitmap_bytes(self.rows_max), abi.bitmap_bytes(self.m_max)
+        w = {"ctx": ctx}
+        for name, nbytes in [("i64", self.rows_max * 8), ("i64_valid", rb), ("pred", rb), ("a", self.rows_max * 8), ("b", self.rows_max * 8),
+                             ("a_valid", rb), ("b_valid", rb), ("idx", self.m_max * 4)]:
+            w[name] = ctx.malloc(nbytes)
+        for name, vb, bbytes in [("out_filter", self.m_max * 8, mb), ("out_take", self.m_max * 8, mb), ("out_add", self.rows_max * 8, rb)]:
+            o = abi.ArrayOut()
+            o.values, o.validity = ctx.malloc(vb), ctx.malloc(bbytes)
+            w[name] = o
+        return w
+
+    def _run_worker(self, k, result):
+        abi, w = self.abi, self.workers[k]
+        ctx = w["ctx"]
+        lib, h = ctx.lib, ctx.h
+        total, valid = 0, 0
+        try:
+            for bi in range(k, len(self.batches), self.n_workers):
+                bt = self.batches[bi]
+                lo, rows, m, m_off = bt["lo"], bt["rows"], bt["m"], bt["m_off"]
+                rb = abi.bitmap_bytes(rows)
+                for name, off, nbytes in [("i64", lo * 8, rows * 8), ("i64_valid", lo // 8, rb), ("pred", lo // 8, rb), ("a", lo * 8, rows * 8),
+                                          ("b", lo * 8, rows * 8), ("a_valid", lo // 8, rb), ("b_valid", lo // 8, rb), ("idx", m_off * 4, m * 4)]:
+                    ctx.check(lib.acu_memcpy_h2d_async(h, w[name], self.host[name] + off, min(nbytes, self._host_left(name, off))))
+                pred = make_arr(abi, w["pred"], None, rows, 0)
+                col = make_arr(abi, w["i64"], w["i64_valid"], rows, bt["ncs"][0])
+                idx = make_arr(abi, w["idx"], None, m, 0)
+                a = make_arr(abi, w["a"], w["a_valid"], rows, bt["ncs"][1])
+                b = make_arr(abi, w["b"], w["b_valid"], rows, bt["ncs"][2])
+                bits, cnt = hot_path_step(ctx, abi, pred, col, idx, a, b, w["out_filter"], w["out_take"], w["out_add"], allreduce=False)
+                total = (total + bits) & 0xFFFFFFFFFFFFFFFF  # wrapping i64 sum of the per-batch sums
+                valid += cnt
+                mb = abi.bitmap_bytes(m)
+                for src, dst, nbytes in [(w["out_add"].values, self.out["add"] + lo * 8, rows * 8),
+                                         (w["out_add"].validity, self.out["add_valid"] + lo // 8, rb),
+                                         (w["out_filter"].values, self.out["filter"] + m_off * 8, m * 8),
+                                         (w["out_filter"].validity, self.out["filter_valid"] + bi * self.mb_max, mb),
+                                         (w["out_take"].values, self.out["take"] + m_off * 8, m * 8),
+                                         (w["out_take"].validity, self.out["take_valid"] + bi * self.mb_max, mb)]:
+                    ctx.check(lib.acu_memcpy_d2h_async(h, dst, src, nbytes))
+            ctx.sync()
+            result[k] = (total, valid)
+        except Exception as e:  # surface worker failures in the main thread
+            result[k] = e
+
+    def _host_left(self, name, off):
+        n, bb = self.wl.n, self.wl.bb
+        size = {"i64": n * 8, "a": n * 8, "b": n * 8, "i64_valid": bb, "pred": bb, "a_valid": bb, "b_valid": bb, "idx": max(self.wl.m, 1) * 4}[name]
+        return size - off
+
+    def step(self):
+        result = [None] * self.n_workers
+        ts = [threading.Thread(target=self._run_worker, args=(k, result)) for k in range(self.n_workers)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        for r in result:
+            if isinstance(r, Exception):
+                raise r
+        total = sum(r[0] for r in result) & 0xFFFFFFFFFFFFFFFF
+        return total, sum(r[1] for r in result)
+
+    def free(self):
+        ctx = self.wl.ctx
+        for w in self.workers:
+            w["ctx"].close()
+        for p in list(self.host.values()) + list(self.out.values()):
+            ctx.lib.acu_host_free(ctx.h, p)
 
 
 def algorithmic_bytes(n, m):
@@ -319,22 +470,26 @@ def run_gpu(args):
             avail = 64 << 30
         need = n * 34 + (64 << 20)
         if need * world < avail * 0.6:
-            hs = HostStaged(wl)
-            hs.step()
+            hs = HostStaged(wl) if args.e2e_mode == "serial" else HostPipelined(wl, local_rank, args.e2e_batch_rows, args.e2e_workers)
+            e2e_check = hs.step()
             barrier()
-            t0 = C.c_float(0)
-            ctx.check(lib.acu_timer_start_slot(h, 2))
+            # the pipelined arm spans several streams: time it on the host clock around a full device sync
+            # (every worker synchronises its stream before step() returns)
+            t_begin = time.perf_counter()
             for _ in range(args.e2e_steps):
-                hs.step()
-            ctx.check(lib.acu_timer_stop_slot(h, 2, C.byref(t0)))
-            e2e_ms = t0.value / args.e2e_steps
+                e2e_check = hs.step()
+            ctx.sync()
+            e2e_ms = (time.perf_counter() - t_begin) * 1e3 / args.e2e_steps
             if dist is not None:
                 import torch
                 t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 e2e_ms = float(t.item())
             e2e = {"value": n * world / (e2e_ms * 1e-3) / 1e6, "unit": "Mrows/s", "h2d_bytes_per_step": hs.h2d_bytes,
-                   "d2h_bytes_per_step": hs.d2h_bytes, "ms_per_step": e2e_ms, "steps": args.e2e_steps, "rows_per_gpu": n}
+                   "d2h_bytes_per_step": hs.d2h_bytes, "ms_per_step": e2e_ms, "steps": args.e2e_steps, "rows_per_gpu": n,
+                   "mode": args.e2e_mode, "batch_rows": args.e2e_batch_rows, "streams": args.e2e_workers,
+                   "timer": "host perf_counter around steps that end with a stream sync (spans several streams)",
+                   "check": {"sum_bits": int(e2e_check[0]), "valid_rows": int(e2e_check[1])}}
             hs.free()
         else:
             e2e = {"value": None, "unit": "Mrows/s", "skipped": f"host RAM: need {need * world >> 30} GiB pinned, {avail >> 30} GiB available"}
@@ -406,30 +561,33 @@ def cpu_baseline(args, from_ctx=None, steps=1):
                 "pred": orc.generate_bits(SEED_PRED, 0, SELECTIVITY, n), "a": orc.generate_values(2, SEED_VALUES, 0, 0, n, np.float64),
                 "b": orc.generate_values(2, SEED_B, 0, 0, n, np.float64), "a_valid": orc.generate_bits(SEED_VALID_A + 100, 0, 1 - NULL_DENSITY, n),
                 "b_valid": orc.generate_bits(SEED_VALID_B, 0, 1 - NULL_DENSITY, n)}
-    # contiguous row ranges aligned to 64 rows (bitmaps split on u64 words)
-    per = ((n + threads - 1) // threads + 63) // 64 * 64
-    ranges = [(lo, min(lo + per, n)) for lo in range(0, n, per)]
-    # index arrays are an INPUT of take (not timed): positions of the set predicate bits per range
-    idxs, ncs = [], []
-    for lo, hi in ranges:
-        sel = np.nonzero(acu.unpack_bits(data["pred"][lo // 8:], 0, hi - lo))[0].astype(np.uint32)
-        idxs.append(HostArray.from_numpy(abi.U32, sel))
-        # cached null counts, as a NullBuffer carries them (arrow-buffer/src/buffer/null.rs:34-37)
-        ncs.append(tuple(int(hi - lo - acu.unpack_bits(data[k][lo // 8:], 0, hi - lo).sum()) for k in ("i64_valid", "a_valid", "b_valid")))
+    def plan_ranges(parts):
+        """Contiguous row ranges aligned to 64 rows (bitmaps split on u64 words) + per-range take indices (an INPUT
+        of take, not timed) + cached null counts (a NullBuffer carries them, arrow-buffer/src/buffer/null.rs:34-37)."""
+        per = ((n + parts - 1) // parts + 63) // 64 * 64
+        ranges = [(lo, min(lo + per, n)) for lo in range(0, n, per)]
+        idxs, ncs = [], []
+        for lo, hi in ranges:
+            sel = np.nonzero(acu.unpack_bits(data["pred"][lo // 8:], 0, hi - lo))[0].astype(np.uint32)
+            idxs.append(HostArray.from_numpy(abi.U32, sel))
+            ncs.append(tuple(int(hi - lo - acu.unpack_bits(data[k][lo // 8:], 0, hi - lo).sum()) for k in ("i64_valid", "a_valid", "b_valid")))
+        return ranges, idxs, ncs
 
-    def work(k):
-        lo, hi = ranges[k]
-        m = hi - lo
-        col = HostArray(abi.I64, data["i64"][lo:hi], m, data["i64_valid"][lo // 8:], 0, 0, ncs[k][0])
-        pred = HostArray(BOOL, data["pred"][lo // 8:], m, None, 0, 0, 0)
-        a = HostArray(abi.F64, data["a"][lo:hi], m, data["a_valid"][lo // 8:], 0, 0, ncs[k][1])
-        b = HostArray(abi.F64, data["b"][lo:hi], m, data["b_valid"][lo // 8:], 0, 0, ncs[k][2])
-        orc.filter(col, pred)
-        t = orc.take(col, idxs[k])
-        orc.add(a, b)
-        orc.sum(t)
+    def run(parts_plan, nthreads):
+        ranges, idxs, ncs = parts_plan
 
-    def run(nthreads):
+        def work(k):
+            lo, hi = ranges[k]
+            m = hi - lo
+            col = HostArray(abi.I64, data["i64"][lo:hi], m, data["i64_valid"][lo // 8:], 0, 0, ncs[k][0])
+            pred = HostArray(BOOL, data["pred"][lo // 8:], m, None, 0, 0, 0)
+            a = HostArray(abi.F64, data["a"][lo:hi], m, data["a_valid"][lo // 8:], 0, 0, ncs[k][1])
+            b = HostArray(abi.F64, data["b"][lo:hi], m, data["b_valid"][lo // 8:], 0, 0, ncs[k][2])
+            orc.filter(col, pred)
+            t = orc.take(col, idxs[k])
+            orc.add(a, b)
+            orc.sum(t)
+
         t0 = time.perf_counter()
         if nthreads == 1:
             for k in range(len(ranges)):
@@ -442,9 +600,11 @@ def cpu_baseline(args, from_ctx=None, steps=1):
                 t.join()
         return time.perf_counter() - t0
 
-    run(threads)  # warm-up (page faults, output allocation)
-    best_mt = min(run(threads) for _ in range(max(1, steps)))
-    best_1t = run(1) if threads > 1 else best_mt
+    plan_mt = plan_ranges(threads)
+    plan_1t = plan_ranges(1) if threads > 1 else plan_mt  # ONE call over the whole array, as arrow-rs would run it
+    run(plan_mt, threads)  # warm-up (page faults, output allocation)
+    best_mt = min(run(plan_mt, threads) for _ in range(max(1, steps)))
+    best_1t = run(plan_1t, 1) if threads > 1 else best_mt
     return {"value": n / best_mt / 1e6, "unit": "Mrows/s", "cores": threads, "kind": "port",
             "sample": f"first {n} rows of the same synthetic table (1/{max(1, args.rows // n)} of the workload), same step "
                       f"(filter+take+add+sum), row-partitioned over {threads} threads; oracle/ C++ restatement of arrow-rs (no Rust toolchain here)",
@@ -491,6 +651,9 @@ def main():
     ap.add_argument("--rows", type=int, default=1_000_000_000, help="rows per GPU")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-mode", default="pipelined", choices=["pipelined", "serial"])
+    ap.add_argument("--e2e-batch-rows", type=int, default=1 << 26)
+    ap.add_argument("--e2e-workers", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=100_000_000)
     ap.add_argument("--cpu-threads", type=int, default=0)
