@@ -1,0 +1,701 @@
+// arrow_cuda.hpp — C++17 host-side mirror of the arrow-rs compute API over the C ABI.
+//
+// The reference's host language is Rust; there is no Rust toolchain in this image, so this
+// header plays the role of the `arrow-cuda` crate: the same type and function names, argument
+// order and error text as the reference, every call forwarded to libarrow_cuda.so
+// (include/arrow_cuda.h). Arrays own DeviceBuffers (HBM) with arrow-buffer's layout: values
+// buffer + LSB-first validity bitmap + bit offset + cached null_count.
+//
+//   arrow-rs                                              here
+//   ----------------------------------------------------  -------------------------------------------
+//   arrow_schema::ArrowError          (error.rs:26-67)    arrow_cuda::ArrowError
+//   Result<T, ArrowError>                                 arrow_cuda::Result<T>  (.unwrap(), .unwrap_err())
+//   arrow_buffer::Buffer / NullBuffer (immutable.rs:83)   arrow_cuda::Buffer / NullBuffer
+//   ArrayRef = Arc<dyn Array>         (array/mod.rs:446)  ArrayRef = std::shared_ptr<Array>
+//   PrimitiveArray<T>, BooleanArray, StringArray          same names
+//   Scalar<T> / Datum                 (scalar.rs:78-152)  Scalar / Datum
+//   RecordBatch                       (record_batch.rs)   RecordBatch
+//   arrow::compute::{filter, take, cast, ...}             arrow_cuda::compute::{...}
+//   arrow::compute::kernels::{numeric, cmp}::*            arrow_cuda::compute::kernels::{numeric, cmp}::*
+//
+// No CPU fallback: Context::get() throws if no CUDA device / library is available.
+#pragma once
+
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <utility>
+#include <variant>
+#include <vector>
+
+#include "../../include/arrow_cuda.h"
+
+namespace arrow_cuda {
+
+// ---------------------------------------------------------------------------------------
+// ArrowError / Result
+// ---------------------------------------------------------------------------------------
+struct ArrowError {
+  acu_status status = ACU_OK;
+  std::string message;  // == the reference's Display output
+  int64_t index = -1;
+  const std::string &to_string() const { return message; }
+};
+
+template <class T>
+class Result {
+ public:
+  Result(T v) : v_(std::move(v)) {}            // NOLINT(google-explicit-constructor)
+  Result(ArrowError e) : v_(std::move(e)) {}   // NOLINT(google-explicit-constructor)
+  bool is_ok() const { return v_.index() == 0; }
+  bool is_err() const { return !is_ok(); }
+  T unwrap() {
+    if (!is_ok()) throw std::runtime_error("called `Result::unwrap()` on an `Err` value: " + std::get<1>(v_).message);
+    return std::move(std::get<0>(v_));
+  }
+  ArrowError unwrap_err() const {
+    if (is_ok()) throw std::runtime_error("called `Result::unwrap_err()` on an `Ok` value");
+    return std::get<1>(v_);
+  }
+ private:
+  std::variant<T, ArrowError> v_;
+};
+
+// ---------------------------------------------------------------------------------------
+// Context: one acu_ctx per device (the reference kernels are pure functions; the ctx is
+// the implicit "where does this run")
+// ---------------------------------------------------------------------------------------
+class Context {
+ public:
+  static Context &get(int device = 0) {
+    static std::map<int, std::unique_ptr<Context>> ctxs;
+    auto it = ctxs.find(device);
+    if (it == ctxs.end()) it = ctxs.emplace(device, std::unique_ptr<Context>(new Context(device))).first;
+    return *it->second;
+  }
+  acu_ctx *raw() const { return ctx_; }
+  ArrowError last_error(acu_status st) const {
+    const acu_error_detail *d = acu_last_error(ctx_);
+    return ArrowError{st, d->message, d->index};
+  }
+  ~Context() { acu_ctx_destroy(ctx_); }
+ private:
+  explicit Context(int device) {
+    if (acu_ctx_create(device, &ctx_) != ACU_OK)
+      throw std::runtime_error("arrow-cuda: no usable CUDA device (there is no CPU fallback)");
+  }
+  acu_ctx *ctx_ = nullptr;
+};
+
+// ---------------------------------------------------------------------------------------
+// DeviceBuffer (arrow_buffer::Buffer): Arc-owned allocation + byte length
+// ---------------------------------------------------------------------------------------
+class Buffer {
+ public:
+  Buffer() = default;
+  static Buffer allocate(size_t bytes, int device = 0) {
+    Buffer b;
+    void *p = nullptr;
+    acu_ctx *ctx = Context::get(device).raw();
+    if (acu_malloc(ctx, bytes + 16, &p) != ACU_OK) throw std::bad_alloc();
+    b.mem_ = std::shared_ptr<void>(p, [ctx](void *q) { acu_free(ctx, q); });
+    b.len_ = bytes;
+    return b;
+  }
+  static Buffer from_host(const void *src, size_t bytes, int device = 0) {
+    Buffer b = allocate(bytes, device);
+    if (bytes) acu_memcpy_h2d(Context::get(device).raw(), b.mem_.get(), src, bytes);
+    return b;
+  }
+  void to_host(void *dst, size_t bytes, int device = 0) const {
+    if (bytes) acu_memcpy_d2h(Context::get(device).raw(), dst, mem_.get(), bytes);
+  }
+  void *data() const { return mem_.get(); }
+  size_t len() const { return len_; }
+ private:
+  std::shared_ptr<void> mem_;
+  size_t len_ = 0;
+};
+
+// NullBuffer { buffer: BooleanBuffer, null_count } (arrow-buffer/src/buffer/null.rs:34-37)
+struct NullBuffer {
+  Buffer buffer;
+  int64_t offset = 0;  // bit offset
+  int64_t len = 0;
+  int64_t null_count = 0;
+};
+
+inline std::vector<uint8_t> pack_bits(const std::vector<bool> &bits) {
+  std::vector<uint8_t> out(acu_bitmap_bytes((int64_t)bits.size()) + 8, 0);
+  for (size_t i = 0; i < bits.size(); ++i)
+    if (bits[i]) out[i >> 3] |= (uint8_t)(1u << (i & 7));
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------
+// DataType / native type traits (arrow-array/src/types.rs:67-80)
+// ---------------------------------------------------------------------------------------
+enum class DataType { Int8, Int16, Int32, Int64, UInt8, UInt16, UInt32, UInt64, Float32, Float64, Boolean, Utf8 };
+
+template <class T> struct NativeOf;
+#define ACU_NATIVE(T, DT, CODE) \
+  template <> struct NativeOf<T> { static constexpr DataType data_type = DataType::DT; static constexpr acu_dtype code = CODE; };
+ACU_NATIVE(int8_t, Int8, ACU_I8) ACU_NATIVE(int16_t, Int16, ACU_I16) ACU_NATIVE(int32_t, Int32, ACU_I32)
+ACU_NATIVE(int64_t, Int64, ACU_I64) ACU_NATIVE(uint8_t, UInt8, ACU_U8) ACU_NATIVE(uint16_t, UInt16, ACU_U16)
+ACU_NATIVE(uint32_t, UInt32, ACU_U32) ACU_NATIVE(uint64_t, UInt64, ACU_U64) ACU_NATIVE(float, Float32, ACU_F32)
+ACU_NATIVE(double, Float64, ACU_F64)
+#undef ACU_NATIVE
+
+inline int dtype_code(DataType t) { return (int)t; }  // numeric DataTypes share acu_dtype's numbering
+inline int dtype_width(DataType t) {
+  switch (t) {
+    case DataType::Int8: case DataType::UInt8: return 1;
+    case DataType::Int16: case DataType::UInt16: return 2;
+    case DataType::Int32: case DataType::UInt32: case DataType::Float32: return 4;
+    case DataType::Int64: case DataType::UInt64: case DataType::Float64: return 8;
+    default: return 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Arrays
+// ---------------------------------------------------------------------------------------
+class Array {
+ public:
+  virtual ~Array() = default;
+  virtual DataType data_type() const = 0;
+  int64_t len() const { return len_; }
+  bool is_empty() const { return len_ == 0; }
+  const std::optional<NullBuffer> &nulls() const { return nulls_; }
+  int64_t null_count() const { return nulls_ ? nulls_->null_count : 0; }
+  // acu_array view (borrowed)
+  acu_array view(bool scalar = false) const {
+    acu_array a{};
+    a.values = values_ptr();
+    a.values_offset = values_bit_offset();
+    a.validity = nulls_ ? static_cast<const uint8_t *>(nulls_->buffer.data()) : nullptr;
+    a.validity_offset = nulls_ ? nulls_->offset : 0;
+    a.len = len_;
+    a.null_count = nulls_ ? nulls_->null_count : 0;
+    a.is_scalar = scalar ? 1 : 0;
+    return a;
+  }
+  std::vector<bool> valid_mask() const {
+    std::vector<bool> v((size_t)len_, true);
+    if (nulls_) {
+      std::vector<uint8_t> bits(acu_bitmap_bytes(nulls_->offset + len_) + 8);
+      nulls_->buffer.to_host(bits.data(), std::min(bits.size(), nulls_->buffer.len()));
+      for (int64_t i = 0; i < len_; ++i) v[(size_t)i] = (bits[(size_t)((nulls_->offset + i) >> 3)] >> ((nulls_->offset + i) & 7)) & 1;
+    }
+    return v;
+  }
+  bool is_null(int64_t i) const { return !valid_mask()[(size_t)i]; }
+  bool is_valid(int64_t i) const { return !is_null(i); }
+ protected:
+  virtual const void *values_ptr() const = 0;
+  virtual int64_t values_bit_offset() const { return 0; }
+  int64_t len_ = 0;
+  std::optional<NullBuffer> nulls_;
+};
+using ArrayRef = std::shared_ptr<Array>;
+
+inline std::optional<NullBuffer> nulls_from_mask(const std::vector<bool> &valid, bool force = false) {
+  int64_t nc = 0;
+  for (bool b : valid) nc += !b;
+  if (nc == 0 && !force) return std::nullopt;
+  auto bits = pack_bits(valid);
+  return NullBuffer{Buffer::from_host(bits.data(), bits.size()), 0, (int64_t)valid.size(), nc};
+}
+
+template <class T>
+class PrimitiveArray : public Array {
+ public:
+  using Native = T;
+  PrimitiveArray() = default;
+  // PrimitiveArray::new(values, nulls)
+  PrimitiveArray(Buffer values, int64_t len, std::optional<NullBuffer> nulls, int64_t elem_offset = 0)
+      : values_(std::move(values)), elem_offset_(elem_offset) { len_ = len; nulls_ = std::move(nulls); }
+  // From<Vec<T>> / From<Vec<Option<T>>>
+  static PrimitiveArray from(const std::vector<T> &v) {
+    return PrimitiveArray(Buffer::from_host(v.data(), v.size() * sizeof(T)), (int64_t)v.size(), std::nullopt);
+  }
+  static PrimitiveArray from(const std::vector<std::optional<T>> &v) {
+    std::vector<T> vals(v.size(), T());
+    std::vector<bool> valid(v.size(), true);
+    for (size_t i = 0; i < v.size(); ++i) { if (v[i]) vals[i] = *v[i]; else valid[i] = false; }
+    return PrimitiveArray(Buffer::from_host(vals.data(), vals.size() * sizeof(T)), (int64_t)v.size(), nulls_from_mask(valid));
+  }
+  static PrimitiveArray new_null(int64_t len) {
+    std::vector<std::optional<T>> v((size_t)len, std::nullopt);
+    auto a = from(v);
+    if (!a.nulls_) a.nulls_ = nulls_from_mask(std::vector<bool>((size_t)len, false), true);
+    return a;
+  }
+  DataType data_type() const override { return NativeOf<T>::data_type; }
+  // Array::slice — zero copy (pointer + bit-offset arithmetic)
+  PrimitiveArray slice(int64_t offset, int64_t length) const {
+    PrimitiveArray out(values_, length, nulls_, elem_offset_ + offset);
+    if (out.nulls_) {
+      out.nulls_->offset += offset;
+      out.nulls_->len = length;
+      out.nulls_->null_count = -1;  // recounted on device on first use
+    }
+    return out;
+  }
+  std::vector<T> values() const {
+    std::vector<T> v((size_t)len_);
+    if (len_) acu_memcpy_d2h(Context::get().raw(), v.data(), values_ptr(), (size_t)len_ * sizeof(T));
+    return v;
+  }
+  T value(int64_t i) const { return values()[(size_t)i]; }
+  std::vector<std::optional<T>> to_vec() const {
+    auto vals = values();
+    auto valid = valid_mask();
+    std::vector<std::optional<T>> out((size_t)len_);
+    for (size_t i = 0; i < out.size(); ++i) if (valid[i]) out[i] = vals[i];
+    return out;
+  }
+ protected:
+  const void *values_ptr() const override { return static_cast<const T *>(values_.data()) + elem_offset_; }
+ private:
+  Buffer values_;
+  int64_t elem_offset_ = 0;
+};
+using Int8Array = PrimitiveArray<int8_t>;
+using Int16Array = PrimitiveArray<int16_t>;
+using Int32Array = PrimitiveArray<int32_t>;
+using Int64Array = PrimitiveArray<int64_t>;
+using UInt8Array = PrimitiveArray<uint8_t>;
+using UInt16Array = PrimitiveArray<uint16_t>;
+using UInt32Array = PrimitiveArray<uint32_t>;
+using UInt64Array = PrimitiveArray<uint64_t>;
+using Float32Array = PrimitiveArray<float>;
+using Float64Array = PrimitiveArray<double>;
+
+class BooleanArray : public Array {
+ public:
+  BooleanArray() = default;
+  BooleanArray(Buffer bits, int64_t bit_offset, int64_t len, std::optional<NullBuffer> nulls)
+      : bits_(std::move(bits)), bit_offset_(bit_offset) { len_ = len; nulls_ = std::move(nulls); }
+  static BooleanArray from(const std::vector<bool> &v) {
+    auto bits = pack_bits(v);
+    return BooleanArray(Buffer::from_host(bits.data(), bits.size()), 0, (int64_t)v.size(), std::nullopt);
+  }
+  static BooleanArray from(const std::vector<std::optional<bool>> &v) {
+    std::vector<bool> vals(v.size(), false), valid(v.size(), true);
+    for (size_t i = 0; i < v.size(); ++i) { if (v[i]) vals[i] = *v[i]; else valid[i] = false; }
+    auto bits = pack_bits(vals);
+    return BooleanArray(Buffer::from_host(bits.data(), bits.size()), 0, (int64_t)v.size(), nulls_from_mask(valid));
+  }
+  DataType data_type() const override { return DataType::Boolean; }
+  BooleanArray slice(int64_t offset, int64_t length) const {
+    BooleanArray out(bits_, bit_offset_ + offset, length, nulls_);
+    if (out.nulls_) { out.nulls_->offset += offset; out.nulls_->len = length; out.nulls_->null_count = -1; }
+    return out;
+  }
+  std::vector<bool> values() const {
+    std::vector<uint8_t> bits(acu_bitmap_bytes(bit_offset_ + len_) + 8);
+    bits_.to_host(bits.data(), std::min(bits.size(), bits_.len()));
+    std::vector<bool> v((size_t)len_);
+    for (int64_t i = 0; i < len_; ++i) v[(size_t)i] = (bits[(size_t)((bit_offset_ + i) >> 3)] >> ((bit_offset_ + i) & 7)) & 1;
+    return v;
+  }
+  bool value(int64_t i) const { return values()[(size_t)i]; }
+  std::vector<std::optional<bool>> to_vec() const {
+    auto vals = values();
+    auto valid = valid_mask();
+    std::vector<std::optional<bool>> out((size_t)len_);
+    for (size_t i = 0; i < out.size(); ++i) if (valid[i]) out[i] = (bool)vals[i];
+    return out;
+  }
+  int64_t true_count() const {  // boolean_array.rs:175-187
+    acu_array a = view();
+    int64_t c = 0;
+    acu_bitmap_count(Context::get().raw(), static_cast<const uint8_t *>(a.values), a.values_offset, a.validity, a.validity_offset, len_, &c);
+    return c;
+  }
+ protected:
+  const void *values_ptr() const override { return bits_.data(); }
+  int64_t values_bit_offset() const override { return bit_offset_; }
+ private:
+  Buffer bits_;
+  int64_t bit_offset_ = 0;
+};
+
+// GenericByteArray<Utf8> (arrow-array/src/array/byte_array.rs:87-92): i32 offsets + value bytes
+class StringArray : public Array {
+ public:
+  StringArray() = default;
+  StringArray(Buffer offsets, Buffer data, int64_t len, std::optional<NullBuffer> nulls)
+      : offsets_(std::move(offsets)), data_(std::move(data)) { len_ = len; nulls_ = std::move(nulls); }
+  static StringArray from(const std::vector<std::optional<std::string>> &v) {
+    std::vector<int32_t> offs(v.size() + 1, 0);
+    std::string bytes;
+    std::vector<bool> valid(v.size(), true);
+    for (size_t i = 0; i < v.size(); ++i) {
+      if (v[i]) bytes += *v[i]; else valid[i] = false;
+      offs[i + 1] = (int32_t)bytes.size();
+    }
+    return StringArray(Buffer::from_host(offs.data(), offs.size() * 4), Buffer::from_host(bytes.data(), bytes.size()),
+                       (int64_t)v.size(), nulls_from_mask(valid));
+  }
+  static StringArray from(const std::vector<std::string> &v) {
+    std::vector<std::optional<std::string>> o(v.begin(), v.end());
+    return from(o);
+  }
+  DataType data_type() const override { return DataType::Utf8; }
+  const Buffer &offsets() const { return offsets_; }
+  const Buffer &value_data() const { return data_; }
+  std::vector<std::optional<std::string>> to_vec() const {
+    std::vector<int32_t> offs((size_t)len_ + 1);
+    offsets_.to_host(offs.data(), offs.size() * 4);
+    std::string bytes((size_t)offs.back(), '\0');
+    data_.to_host(bytes.data(), bytes.size());
+    auto valid = valid_mask();
+    std::vector<std::optional<std::string>> out((size_t)len_);
+    for (size_t i = 0; i < out.size(); ++i)
+      if (valid[i]) out[i] = bytes.substr((size_t)offs[i], (size_t)(offs[i + 1] - offs[i]));
+    return out;
+  }
+ protected:
+  const void *values_ptr() const override { return nullptr; }
+ private:
+  Buffer offsets_, data_;
+};
+
+// Datum (arrow-array/src/scalar.rs:78-152): an array, or a Scalar wrapping a 1-element array
+template <class A>
+struct Scalar {
+  A array;
+  explicit Scalar(A a) : array(std::move(a)) {}
+};
+template <class T> Scalar<PrimitiveArray<T>> new_scalar(T v) { return Scalar<PrimitiveArray<T>>(PrimitiveArray<T>::from(std::vector<T>{v})); }
+template <class T> Scalar<PrimitiveArray<T>> new_null_scalar() { return Scalar<PrimitiveArray<T>>(PrimitiveArray<T>::new_null(1)); }
+
+template <class A> const A &datum_array(const A &a) { return a; }
+template <class A> const A &datum_array(const Scalar<A> &s) { return s.array; }
+template <class A> bool datum_is_scalar(const A &) { return false; }
+template <class A> bool datum_is_scalar(const Scalar<A> &) { return true; }
+
+// ---------------------------------------------------------------------------------------
+// RecordBatch (arrow-array/src/record_batch.rs:224-232)
+// ---------------------------------------------------------------------------------------
+struct Field { std::string name; DataType data_type; bool nullable = true; };
+using Schema = std::vector<Field>;
+
+class RecordBatch {
+ public:
+  static Result<RecordBatch> try_new(Schema schema, std::vector<ArrayRef> columns) {
+    if (schema.size() != columns.size())
+      return ArrowError{ACU_ERR_INVALID_ARGUMENT, "Invalid argument error: number of columns(" + std::to_string(columns.size()) +
+                                                       ") must match number of fields(" + std::to_string(schema.size()) + ") in schema"};
+    int64_t rows = columns.empty() ? 0 : columns[0]->len();
+    for (auto &c : columns)
+      if (c->len() != rows) return ArrowError{ACU_ERR_INVALID_ARGUMENT, "Invalid argument error: all columns in a record batch must have the same length"};
+    return RecordBatch(std::move(schema), std::move(columns), rows);
+  }
+  RecordBatch(Schema schema, std::vector<ArrayRef> columns, int64_t rows)
+      : schema_(std::move(schema)), columns_(std::move(columns)), rows_(rows) {}
+  const Schema &schema() const { return schema_; }
+  const std::vector<ArrayRef> &columns() const { return columns_; }
+  const ArrayRef &column(size_t i) const { return columns_[i]; }
+  int64_t num_rows() const { return rows_; }
+  size_t num_columns() const { return columns_.size(); }
+ private:
+  Schema schema_;
+  std::vector<ArrayRef> columns_;
+  int64_t rows_ = 0;
+};
+
+// ---------------------------------------------------------------------------------------
+// compute
+// ---------------------------------------------------------------------------------------
+namespace compute {
+namespace detail {
+
+inline acu_array_out make_out(Buffer &values, Buffer &validity, size_t value_bytes, int64_t rows) {
+  values = Buffer::allocate(value_bytes);
+  validity = Buffer::allocate(acu_bitmap_bytes(rows));
+  acu_array_out o{};
+  o.values = values.data();
+  o.validity = static_cast<uint8_t *>(validity.data());
+  return o;
+}
+inline std::optional<NullBuffer> out_nulls(const acu_array_out &o, Buffer validity) {
+  if (!o.has_validity) return std::nullopt;
+  return NullBuffer{std::move(validity), 0, o.len, o.null_count};
+}
+
+template <class T>
+ArrayRef wrap_primitive(DataType dt, Buffer values, int64_t len, std::optional<NullBuffer> nulls) {
+  (void)dt;
+  return std::make_shared<PrimitiveArray<T>>(std::move(values), len, std::move(nulls));
+}
+inline ArrayRef make_primitive(DataType dt, Buffer values, int64_t len, std::optional<NullBuffer> nulls) {
+  switch (dt) {
+    case DataType::Int8: return wrap_primitive<int8_t>(dt, std::move(values), len, std::move(nulls));
+    case DataType::Int16: return wrap_primitive<int16_t>(dt, std::move(values), len, std::move(nulls));
+    case DataType::Int32: return wrap_primitive<int32_t>(dt, std::move(values), len, std::move(nulls));
+    case DataType::Int64: return wrap_primitive<int64_t>(dt, std::move(values), len, std::move(nulls));
+    case DataType::UInt8: return wrap_primitive<uint8_t>(dt, std::move(values), len, std::move(nulls));
+    case DataType::UInt16: return wrap_primitive<uint16_t>(dt, std::move(values), len, std::move(nulls));
+    case DataType::UInt32: return wrap_primitive<uint32_t>(dt, std::move(values), len, std::move(nulls));
+    case DataType::UInt64: return wrap_primitive<uint64_t>(dt, std::move(values), len, std::move(nulls));
+    case DataType::Float32: return wrap_primitive<float>(dt, std::move(values), len, std::move(nulls));
+    default: return wrap_primitive<double>(dt, std::move(values), len, std::move(nulls));
+  }
+}
+inline const char *dtype_display(DataType t) {
+  static const char *n[] = {"Int8", "Int16", "Int32", "Int64", "UInt8", "UInt16", "UInt32", "UInt64", "Float32", "Float64", "Boolean", "Utf8"};
+  return n[(int)t];
+}
+}  // namespace detail
+
+// ---- filter (arrow-select/src/filter.rs) ------------------------------------------------
+// FilterPredicate (filter.rs:442-533): owns the device-resident plan, reusable across columns.
+class FilterPredicate {
+ public:
+  FilterPredicate() = default;
+  explicit FilterPredicate(acu_filter_plan *p) : plan_(p, [](acu_filter_plan *q) { acu_filter_plan_destroy(Context::get().raw(), q); }) {}
+  int64_t count() const { return acu_filter_plan_count(plan_.get()); }
+  Result<ArrayRef> filter(const Array &values) const {
+    Context &c = Context::get();
+    const int64_t n = count();
+    Buffer vb, nb;
+    acu_array v = values.view();
+    acu_status st;
+    if (values.data_type() == DataType::Boolean) {
+      acu_array_out o = detail::make_out(vb, nb, acu_bitmap_bytes(n), n);
+      if ((st = acu_filter_boolean(c.raw(), plan_.get(), &v, &o)) != ACU_OK) return c.last_error(st);
+      return ArrayRef(std::make_shared<BooleanArray>(vb, 0, o.len, detail::out_nulls(o, nb)));
+    }
+    if (values.data_type() == DataType::Utf8) {
+      const auto &s = static_cast<const StringArray &>(values);
+      Buffer offs = Buffer::allocate((size_t)(n + 1) * 4), dummy;
+      acu_array_out o{};
+      nb = Buffer::allocate(acu_bitmap_bytes(n));
+      o.validity = static_cast<uint8_t *>(nb.data());
+      int64_t total = 0;
+      if ((st = acu_filter_bytes(c.raw(), plan_.get(), 4, s.offsets().data(), static_cast<const uint8_t *>(s.value_data().data()), &v,
+                                 offs.data(), nullptr, 0, &total, &o)) != ACU_OK) return c.last_error(st);
+      Buffer data = Buffer::allocate((size_t)total);
+      if ((st = acu_filter_bytes(c.raw(), plan_.get(), 4, s.offsets().data(), static_cast<const uint8_t *>(s.value_data().data()), &v,
+                                 offs.data(), static_cast<uint8_t *>(data.data()), total, &total, &o)) != ACU_OK) return c.last_error(st);
+      return ArrayRef(std::make_shared<StringArray>(offs, data, o.len, detail::out_nulls(o, nb)));
+    }
+    const int w = dtype_width(values.data_type());
+    acu_array_out o = detail::make_out(vb, nb, (size_t)n * w, n);
+    if ((st = acu_filter_primitive(c.raw(), plan_.get(), w, &v, &o)) != ACU_OK) return c.last_error(st);
+    return detail::make_primitive(values.data_type(), vb, o.len, detail::out_nulls(o, nb));
+  }
+  // FilterPredicate::filter_record_batch (filter.rs:459-478): one plan, every column
+  Result<RecordBatch> filter_record_batch(const RecordBatch &batch) const {
+    std::vector<ArrayRef> cols;
+    for (const auto &col : batch.columns()) {
+      auto r = filter(*col);
+      if (r.is_err()) return r.unwrap_err();
+      cols.push_back(r.unwrap());
+    }
+    return RecordBatch(batch.schema(), std::move(cols), count());
+  }
+ private:
+  std::shared_ptr<acu_filter_plan> plan_;
+};
+
+class FilterBuilder {  // filter.rs:254-324
+ public:
+  explicit FilterBuilder(const BooleanArray &filter) {
+    acu_array p = filter.view();
+    acu_filter_plan *plan = nullptr;
+    acu_status st = acu_filter_plan_create(Context::get().raw(), &p, &plan);
+    if (st != ACU_OK) throw std::runtime_error(Context::get().last_error(st).message);
+    pred_ = FilterPredicate(plan);
+  }
+  FilterBuilder &optimize() { return *this; }  // the device plan is always materialised
+  FilterPredicate build() { return pred_; }
+ private:
+  FilterPredicate pred_;
+};
+
+inline Result<ArrayRef> filter(const Array &values, const BooleanArray &predicate) {
+  return FilterBuilder(predicate).build().filter(values);
+}
+inline Result<RecordBatch> filter_record_batch(const RecordBatch &batch, const BooleanArray &predicate) {
+  return FilterBuilder(predicate).optimize().build().filter_record_batch(batch);
+}
+
+// ---- take (arrow-select/src/take.rs) ----------------------------------------------------
+struct TakeOptions { bool check_bounds = false; };  // take.rs:388-394
+
+inline Result<ArrayRef> take(const Array &values, const Array &indices, std::optional<TakeOptions> options = std::nullopt) {
+  Context &c = Context::get();
+  const DataType it = indices.data_type();
+  if ((int)it > (int)DataType::UInt64)  // take.rs:103
+    return ArrowError{ACU_ERR_INVALID_ARGUMENT, std::string("Invalid argument error: Take only supported for integers, got ") + detail::dtype_display(it)};
+  const int cb = options && options->check_bounds ? 1 : 0;
+  const int64_t m = indices.len();
+  acu_array v = values.view(), ix = indices.view();
+  Buffer vb, nb;
+  acu_status st;
+  if (values.data_type() == DataType::Boolean) {
+    acu_array_out o = detail::make_out(vb, nb, acu_bitmap_bytes(m), m);
+    if ((st = acu_take_boolean(c.raw(), &v, &ix, (acu_dtype)dtype_code(it), cb, &o)) != ACU_OK) return c.last_error(st);
+    return ArrayRef(std::make_shared<BooleanArray>(vb, 0, o.len, detail::out_nulls(o, nb)));
+  }
+  if (values.data_type() == DataType::Utf8) {
+    const auto &s = static_cast<const StringArray &>(values);
+    Buffer offs = Buffer::allocate((size_t)(m + 1) * 4);
+    nb = Buffer::allocate(acu_bitmap_bytes(m));
+    acu_array_out o{};
+    o.validity = static_cast<uint8_t *>(nb.data());
+    int64_t total = 0;
+    if ((st = acu_take_bytes(c.raw(), 4, s.offsets().data(), static_cast<const uint8_t *>(s.value_data().data()), &v, &ix,
+                             (acu_dtype)dtype_code(it), cb, offs.data(), nullptr, 0, &total, &o)) != ACU_OK) return c.last_error(st);
+    Buffer data = Buffer::allocate((size_t)total);
+    if ((st = acu_take_bytes(c.raw(), 4, s.offsets().data(), static_cast<const uint8_t *>(s.value_data().data()), &v, &ix,
+                             (acu_dtype)dtype_code(it), cb, offs.data(), static_cast<uint8_t *>(data.data()), total, &total, &o)) != ACU_OK)
+      return c.last_error(st);
+    return ArrayRef(std::make_shared<StringArray>(offs, data, o.len, detail::out_nulls(o, nb)));
+  }
+  const int w = dtype_width(values.data_type());
+  acu_array_out o = detail::make_out(vb, nb, (size_t)m * w, m);
+  if ((st = acu_take_primitive(c.raw(), w, &v, &ix, (acu_dtype)dtype_code(it), cb, &o)) != ACU_OK) return c.last_error(st);
+  return detail::make_primitive(values.data_type(), vb, o.len, detail::out_nulls(o, nb));
+}
+
+inline Result<RecordBatch> take_record_batch(const RecordBatch &batch, const Array &indices) {  // take.rs:1123-1133
+  std::vector<ArrayRef> cols;
+  for (const auto &col : batch.columns()) {
+    auto r = take(*col, indices, std::nullopt);
+    if (r.is_err()) return r.unwrap_err();
+    cols.push_back(r.unwrap());
+  }
+  return RecordBatch::try_new(batch.schema(), std::move(cols));
+}
+
+// ---- kernels::numeric (arrow-arith/src/numeric.rs) ---------------------------------------
+namespace kernels {
+namespace numeric {
+namespace detail2 {
+template <class L, class R>
+Result<ArrayRef> arithmetic_op(acu_arith_op op, const char *sym, const L &lhs, const R &rhs) {
+  const auto &l = datum_array(lhs);
+  const auto &r = datum_array(rhs);
+  const bool ls = datum_is_scalar(lhs), rs = datum_is_scalar(rhs);
+  if (l.data_type() != r.data_type() || dtype_width(l.data_type()) == 0)  // numeric.rs:270-272
+    return ArrowError{ACU_ERR_INVALID_ARGUMENT, std::string("Invalid argument error: Invalid arithmetic operation: ") +
+                                                     compute::detail::dtype_display(l.data_type()) + " " + sym + " " +
+                                                     compute::detail::dtype_display(r.data_type())};
+  Context &c = Context::get();
+  const int64_t n = ls && !rs ? r.len() : l.len();
+  Buffer vb, nb;
+  acu_array a = l.view(ls), b = r.view(rs);
+  acu_array_out o = compute::detail::make_out(vb, nb, (size_t)std::max<int64_t>(n, 1) * dtype_width(l.data_type()), n);
+  acu_status st = acu_arith(c.raw(), (acu_dtype)dtype_code(l.data_type()), op, &a, &b, &o);
+  if (st != ACU_OK) return c.last_error(st);
+  return compute::detail::make_primitive(l.data_type(), vb, o.len, compute::detail::out_nulls(o, nb));
+}
+}  // namespace detail2
+#define ACU_NUMERIC(NAME, OP, SYM) \
+  template <class L, class R> Result<ArrayRef> NAME(const L &lhs, const R &rhs) { return detail2::arithmetic_op(OP, SYM, lhs, rhs); }
+ACU_NUMERIC(add, ACU_ADD, "+") ACU_NUMERIC(add_wrapping, ACU_ADD_WRAPPING, "+") ACU_NUMERIC(sub, ACU_SUB, "-")
+ACU_NUMERIC(sub_wrapping, ACU_SUB_WRAPPING, "-") ACU_NUMERIC(mul, ACU_MUL, "*") ACU_NUMERIC(mul_wrapping, ACU_MUL_WRAPPING, "*")
+ACU_NUMERIC(div, ACU_DIV, "/") ACU_NUMERIC(rem, ACU_REM, "%")
+#undef ACU_NUMERIC
+
+inline Result<ArrayRef> neg_impl(const Array &a, int checked) {
+  Context &c = Context::get();
+  Buffer vb, nb;
+  acu_array v = a.view();
+  acu_array_out o = compute::detail::make_out(vb, nb, (size_t)std::max<int64_t>(a.len(), 1) * dtype_width(a.data_type()), a.len());
+  acu_status st = acu_neg(c.raw(), (acu_dtype)dtype_code(a.data_type()), checked, &v, &o);
+  if (st != ACU_OK) return c.last_error(st);
+  return compute::detail::make_primitive(a.data_type(), vb, o.len, compute::detail::out_nulls(o, nb));
+}
+inline Result<ArrayRef> neg(const Array &a) { return neg_impl(a, 1); }
+inline Result<ArrayRef> neg_wrapping(const Array &a) { return neg_impl(a, 0); }
+}  // namespace numeric
+
+// ---- kernels::cmp (arrow-ord/src/cmp.rs) ---------------------------------------------------
+namespace cmp {
+namespace detail3 {
+template <class L, class R>
+Result<BooleanArray> compare_op(acu_cmp_op op, const char *sym, const L &lhs, const R &rhs) {
+  const auto &l = datum_array(lhs);
+  const auto &r = datum_array(rhs);
+  const bool ls = datum_is_scalar(lhs), rs = datum_is_scalar(rhs);
+  if (l.data_type() != r.data_type())  // cmp.rs:260-264
+    return ArrowError{ACU_ERR_INVALID_ARGUMENT, std::string("Invalid argument error: Invalid comparison operation: ") +
+                                                     compute::detail::dtype_display(l.data_type()) + " " + sym + " " +
+                                                     compute::detail::dtype_display(r.data_type())};
+  Context &c = Context::get();
+  const int64_t n = ls ? r.len() : l.len();
+  Buffer vb, nb;
+  acu_array a = l.view(ls), b = r.view(rs);
+  acu_array_out o = compute::detail::make_out(vb, nb, acu_bitmap_bytes(std::max<int64_t>(n, 1)), std::max<int64_t>(n, 1));
+  acu_status st = acu_cmp(c.raw(), (acu_dtype)dtype_code(l.data_type()), op, &a, &b, &o);
+  if (st != ACU_OK) return c.last_error(st);
+  return BooleanArray(vb, 0, o.len, compute::detail::out_nulls(o, nb));
+}
+}  // namespace detail3
+#define ACU_CMP(NAME, OP, SYM) \
+  template <class L, class R> Result<BooleanArray> NAME(const L &lhs, const R &rhs) { return detail3::compare_op(OP, SYM, lhs, rhs); }
+ACU_CMP(eq, ACU_EQ, "==") ACU_CMP(neq, ACU_NEQ, "!=") ACU_CMP(lt, ACU_LT, "<") ACU_CMP(lt_eq, ACU_LT_EQ, "<=")
+ACU_CMP(gt, ACU_GT, ">") ACU_CMP(gt_eq, ACU_GT_EQ, ">=") ACU_CMP(distinct, ACU_DISTINCT, "IS DISTINCT FROM")
+ACU_CMP(not_distinct, ACU_NOT_DISTINCT, "IS NOT DISTINCT FROM")
+#undef ACU_CMP
+}  // namespace cmp
+}  // namespace kernels
+
+// ---- cast (arrow-cast/src/cast/mod.rs) -------------------------------------------------------
+struct CastOptions { bool safe = true; };  // mod.rs:96-111
+
+inline Result<ArrayRef> cast_with_options(const Array &array, DataType to_type, const CastOptions &opt) {
+  if (dtype_width(array.data_type()) == 0 || dtype_width(to_type) == 0)
+    return ArrowError{ACU_ERR_CAST, std::string("Cast error: Casting from ") + detail::dtype_display(array.data_type()) + " to " +
+                                        detail::dtype_display(to_type) + " not supported"};
+  Context &c = Context::get();
+  Buffer vb, nb;
+  acu_array v = array.view();
+  acu_array_out o = detail::make_out(vb, nb, (size_t)std::max<int64_t>(array.len(), 1) * dtype_width(to_type), array.len());
+  acu_status st = acu_cast_numeric(c.raw(), (acu_dtype)dtype_code(array.data_type()), (acu_dtype)dtype_code(to_type), opt.safe ? 1 : 0, &v, &o);
+  if (st != ACU_OK) return c.last_error(st);
+  return detail::make_primitive(to_type, vb, o.len, detail::out_nulls(o, nb));
+}
+inline Result<ArrayRef> cast(const Array &array, DataType to_type) { return cast_with_options(array, to_type, CastOptions{}); }
+
+// Dictionary<Int32, Utf8> -> Utf8 (arrow-cast/src/cast/dictionary.rs:310-317): take(dict values, keys)
+inline Result<ArrayRef> cast_dictionary_to_utf8(const Int32Array &keys, const StringArray &dictionary) { return take(dictionary, keys, std::nullopt); }
+
+// ---- aggregate (arrow-arith/src/aggregate.rs) ------------------------------------------------
+namespace detail {
+template <class T>
+std::optional<T> aggregate(acu_agg_op op, const PrimitiveArray<T> &a) {
+  uint64_t bits = 0;
+  int64_t valid = 0;
+  acu_array v = a.view();
+  acu_status st = acu_aggregate(Context::get().raw(), NativeOf<T>::code, op, &v, &bits, &valid);
+  if (st != ACU_OK) throw std::runtime_error(Context::get().last_error(st).message);
+  if (valid == 0) return std::nullopt;
+  T out;
+  std::memcpy(&out, &bits, sizeof(T));
+  return out;
+}
+}  // namespace detail
+template <class T> std::optional<T> sum(const PrimitiveArray<T> &a) { return detail::aggregate(ACU_SUM, a); }
+template <class T> std::optional<T> min(const PrimitiveArray<T> &a) { return detail::aggregate(ACU_MIN, a); }
+template <class T> std::optional<T> max(const PrimitiveArray<T> &a) { return detail::aggregate(ACU_MAX, a); }
+
+}  // namespace compute
+
+// downcast helpers (as_primitive::<T>() etc.)
+template <class T> const PrimitiveArray<T> &as_primitive(const ArrayRef &a) { return dynamic_cast<const PrimitiveArray<T> &>(*a); }
+inline const BooleanArray &as_boolean(const ArrayRef &a) { return dynamic_cast<const BooleanArray &>(*a); }
+inline const StringArray &as_string(const ArrayRef &a) { return dynamic_cast<const StringArray &>(*a); }
+
+}  // namespace arrow_cuda

@@ -1,0 +1,362 @@
+// test_host.cpp — the reference's unit tests, re-expressed against the C++ host mirror
+// (arrow_cuda.hpp). Each test cites the arrow-rs test it transcribes; assertions are on the
+// same values and the same error strings. Runs on a CUDA device (no CPU fallback).
+//
+// Build: see arrow-rs_b200/host/Makefile.  Run: ./test_host   (exit code 0 = all passed)
+#include <cmath>
+#include <cstdio>
+#include <functional>
+#include <limits>
+
+#include "arrow_cuda.hpp"
+
+using namespace arrow_cuda;
+using namespace arrow_cuda::compute;
+namespace numeric = arrow_cuda::compute::kernels::numeric;
+namespace cmpk = arrow_cuda::compute::kernels::cmp;
+
+static int g_failed = 0, g_checks = 0;
+#define CHECK(cond)                                                                    \
+  do {                                                                                 \
+    ++g_checks;                                                                        \
+    if (!(cond)) { ++g_failed; std::printf("  FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); } \
+  } while (0)
+#define CHECK_EQ(a, b) CHECK((a) == (b))
+
+template <class T> using O = std::optional<T>;
+static const std::nullopt_t N = std::nullopt;
+
+// arrow-select/src/filter.rs:1177 test_filter_array_slice
+static void test_filter_array_slice() {
+  auto a = Int32Array::from(std::vector<int32_t>{5, 6, 7, 8, 9}).slice(1, 4);
+  auto b = BooleanArray::from(std::vector<bool>{true, false, false, true});
+  auto c = filter(a, b).unwrap();
+  const auto &d = as_primitive<int32_t>(c);
+  CHECK_EQ(2, d.len());
+  CHECK_EQ(6, d.value(0));
+  CHECK_EQ(9, d.value(1));
+}
+
+// filter.rs:1191 test_filter_array_low_density
+static void test_filter_array_low_density() {
+  std::vector<int32_t> data;
+  std::vector<bool> pred;
+  for (int i = 1; i <= 65; ++i) { data.push_back(i); pred.push_back(i % 65 == 0); }
+  data.push_back(66); data.push_back(67);
+  pred.push_back(false); pred.push_back(true);
+  auto c = filter(Int32Array::from(data), BooleanArray::from(pred)).unwrap();
+  const auto &d = as_primitive<int32_t>(c);
+  CHECK_EQ(2, d.len());
+  CHECK_EQ(65, d.value(0));
+  CHECK_EQ(67, d.value(1));
+}
+
+// filter.rs:1208 test_filter_array_high_density
+static void test_filter_array_high_density() {
+  std::vector<O<int32_t>> data;
+  std::vector<bool> pred;
+  for (int i = 1; i <= 65; ++i) { data.push_back(i); pred.push_back(i % 65 != 0); }
+  data[1] = N;
+  for (O<int32_t> v : {O<int32_t>(66), O<int32_t>(N), O<int32_t>(67), O<int32_t>(N)}) data.push_back(v);
+  for (bool b : {false, true, true, true}) pred.push_back(b);
+  auto c = filter(Int32Array::from(data), BooleanArray::from(pred)).unwrap();
+  const auto &d = as_primitive<int32_t>(c);
+  CHECK_EQ(67, d.len());
+  CHECK_EQ(3, d.null_count());
+  CHECK_EQ(1, d.value(0));
+  CHECK(d.is_null(1));
+  CHECK_EQ(64, d.value(63));
+  CHECK(d.is_null(64));
+  CHECK_EQ(67, d.value(65));
+}
+
+// filter.rs:1233 / :1254 test_filter_string_array_simple / _with_null
+static void test_filter_string_array() {
+  auto a = StringArray::from(std::vector<std::string>{"hello", " ", "world", "!"});
+  auto c = filter(a, BooleanArray::from(std::vector<bool>{true, false, true, false})).unwrap();
+  auto d = as_string(c).to_vec();
+  CHECK_EQ(2u, d.size());
+  CHECK(d[0] == O<std::string>("hello"));
+  CHECK(d[1] == O<std::string>("world"));
+  auto a2 = StringArray::from(std::vector<O<std::string>>{std::string("hello"), N, std::string("world"), N});
+  auto c2 = filter(a2, BooleanArray::from(std::vector<bool>{true, false, false, true})).unwrap();
+  auto d2 = as_string(c2).to_vec();
+  CHECK(d2[0] == O<std::string>("hello"));
+  CHECK(!d2[1].has_value());
+}
+
+// filter.rs:1718 test_null_mask, :1738 test_fast_path
+static void test_null_mask_and_fast_path() {
+  auto a = Int64Array::from(std::vector<O<int64_t>>{1, 2, N});
+  auto mask1 = BooleanArray::from(std::vector<O<bool>>{true, true, N});
+  auto out = filter(a, mask1).unwrap();
+  CHECK(as_primitive<int64_t>(out).to_vec() == (std::vector<O<int64_t>>{1, 2}));
+  auto all = filter(a, BooleanArray::from(std::vector<bool>{true, true, true})).unwrap();
+  CHECK(as_primitive<int64_t>(all).to_vec() == (std::vector<O<int64_t>>{1, 2, N}));
+  auto none = filter(a, BooleanArray::from(std::vector<bool>{false, false, false})).unwrap();
+  CHECK_EQ(0, none->len());
+  CHECK(none->data_type() == DataType::Int64);
+}
+
+// filter.rs:536-542 error text
+static void test_filter_predicate_too_long() {
+  auto r = filter(Int32Array::from(std::vector<int32_t>{1, 2}), BooleanArray::from(std::vector<bool>{true, false, true}));
+  CHECK(r.is_err());
+  CHECK_EQ(r.unwrap_err().to_string(), std::string("Invalid argument error: Filter predicate of length 3 is larger than target array of length 2"));
+}
+
+// filter.rs:225-244, :459-478 filter_record_batch: one predicate, every column
+static void test_filter_record_batch() {
+  Schema schema{{"a", DataType::Int32}, {"b", DataType::Utf8}, {"c", DataType::Float64}};
+  std::vector<ArrayRef> cols{
+      std::make_shared<Int32Array>(Int32Array::from(std::vector<O<int32_t>>{1, N, 3, 4})),
+      std::make_shared<StringArray>(StringArray::from(std::vector<std::string>{"w", "x", "y", "z"})),
+      std::make_shared<Float64Array>(Float64Array::from(std::vector<double>{0.5, 1.5, 2.5, 3.5}))};
+  auto batch = RecordBatch::try_new(schema, cols).unwrap();
+  auto out = filter_record_batch(batch, BooleanArray::from(std::vector<bool>{true, true, false, true})).unwrap();
+  CHECK_EQ(3, out.num_rows());
+  CHECK(as_primitive<int32_t>(out.column(0)).to_vec() == (std::vector<O<int32_t>>{1, N, 4}));
+  CHECK(as_string(out.column(1)).to_vec() == (std::vector<O<std::string>>{std::string("w"), std::string("x"), std::string("z")}));
+  CHECK(as_primitive<double>(out.column(2)).to_vec() == (std::vector<O<double>>{0.5, 1.5, 3.5}));
+}
+
+// arrow-select/src/take.rs:1371-1440 test_take_primitive
+template <class T>
+static void take_primitive_case() {
+  auto index = UInt32Array::from(std::vector<O<uint32_t>>{3, N, 1, 3, 2});
+  auto values = PrimitiveArray<T>::from(std::vector<O<T>>{T(0), N, T(2), T(3), N});
+  auto out = take(values, index, std::nullopt).unwrap();
+  CHECK(as_primitive<T>(out).to_vec() == (std::vector<O<T>>{T(3), N, N, T(3), T(2)}));
+}
+static void test_take_primitive() {
+  take_primitive_case<int8_t>();
+  take_primitive_case<int16_t>();
+  take_primitive_case<int32_t>();
+  take_primitive_case<int64_t>();
+  take_primitive_case<uint8_t>();
+  take_primitive_case<uint16_t>();
+  take_primitive_case<uint32_t>();
+  take_primitive_case<uint64_t>();
+  take_primitive_case<float>();
+  take_primitive_case<double>();
+}
+
+// take.rs:1331 test_take_primitive_nullable_indices_non_null_values_with_offset
+static void test_take_with_offset() {
+  auto index = UInt32Array::from(std::vector<O<uint32_t>>{0, 1, 2, 3, N, N}).slice(2, 4);
+  auto values = Int64Array::from(std::vector<int64_t>{0, 10, 20, 30, 40, 50});
+  auto out = take(values, index, std::nullopt).unwrap();
+  CHECK(as_primitive<int64_t>(out).to_vec() == (std::vector<O<int64_t>>{20, 30, N, N}));
+}
+
+// take.rs:1627 test_take_bool
+static void test_take_bool() {
+  auto index = UInt32Array::from(std::vector<O<uint32_t>>{3, N, 1, 3, 2});
+  auto values = BooleanArray::from(std::vector<O<bool>>{false, N, true, false, N});
+  auto out = take(values, index, std::nullopt).unwrap();
+  CHECK(as_boolean(out).to_vec() == (std::vector<O<bool>>{false, N, N, false, true}));
+}
+
+// take.rs:2408 test_take_out_of_bounds, :2455-2465 message, :2423 panic
+static void test_take_out_of_bounds() {
+  auto index = UInt32Array::from(std::vector<O<uint32_t>>{3, N, 1, 3, 6});
+  auto values = Int64Array::from(std::vector<O<int64_t>>{0, N, 2, 3, N});
+  auto r = take(values, index, TakeOptions{true});
+  CHECK(r.is_err());
+  CHECK_EQ(r.unwrap_err().to_string(), std::string("Compute error: Array index out of bounds, cannot get item at index 6 from 5 entries"));
+  auto p = take(Int64Array::from(std::vector<int64_t>{0, 1, 2, 3}), UInt32Array::from(std::vector<uint32_t>{1000}), std::nullopt);
+  CHECK(p.is_err());
+  CHECK_EQ(p.unwrap_err().status, (acu_status)ACU_ERR_PANIC_OUT_OF_BOUNDS);  // the reference panics here
+}
+
+// take.rs:76-88 doc example; take.rs:2719 test_take_bytes_null_indices; dictionary.rs:310-317
+static void test_take_strings_and_dictionary() {
+  auto values = StringArray::from(std::vector<std::string>{"zero", "one", "two"});
+  auto taken = take(values, UInt32Array::from(std::vector<uint32_t>{2, 1}), std::nullopt).unwrap();
+  CHECK(as_string(taken).to_vec() == (std::vector<O<std::string>>{std::string("two"), std::string("one")}));
+  auto dict = StringArray::from(std::vector<O<std::string>>{std::string("one"), N, std::string("three")});
+  auto keys = Int32Array::from(std::vector<O<int32_t>>{0, 1, 2, N, 0, 2});
+  auto flat = cast_dictionary_to_utf8(keys, dict).unwrap();
+  CHECK(as_string(flat).to_vec() ==
+        (std::vector<O<std::string>>{std::string("one"), N, std::string("three"), N, std::string("one"), std::string("three")}));
+}
+
+// arrow-arith/src/numeric.rs:1296-1361 test_integer
+static void test_integer() {
+  auto a = Int32Array::from(std::vector<int32_t>{4, 3, 5, -6, 100});
+  auto b = Int32Array::from(std::vector<int32_t>{6, 2, 5, -7, 3});
+  CHECK(as_primitive<int32_t>(numeric::add(a, b).unwrap()).values() == (std::vector<int32_t>{10, 5, 10, -13, 103}));
+  CHECK(as_primitive<int32_t>(numeric::sub(a, b).unwrap()).values() == (std::vector<int32_t>{-2, 1, 0, 1, 97}));
+  CHECK(as_primitive<int32_t>(numeric::div(a, b).unwrap()).values() == (std::vector<int32_t>{0, 1, 1, 0, 33}));
+  CHECK(as_primitive<int32_t>(numeric::mul(a, b).unwrap()).values() == (std::vector<int32_t>{24, 6, 25, 42, 300}));
+  CHECK(as_primitive<int32_t>(numeric::rem(a, b).unwrap()).values() == (std::vector<int32_t>{4, 1, 0, -6, 1}));
+
+  auto a8 = Int8Array::from(std::vector<O<int8_t>>{int8_t(2), N, int8_t(45)});
+  auto b8 = Int8Array::from(std::vector<O<int8_t>>{int8_t(5), int8_t(3), N});
+  CHECK(as_primitive<int8_t>(numeric::add(a8, b8).unwrap()).to_vec() == (std::vector<O<int8_t>>{int8_t(7), N, N}));
+
+  auto ua = UInt8Array::from(std::vector<uint8_t>{56, 5, 3});
+  auto ub = UInt8Array::from(std::vector<uint8_t>{200, 2, 5});
+  CHECK_EQ(numeric::add(ua, ub).unwrap_err().to_string(), std::string("Arithmetic overflow: Overflow happened on: 56 + 200"));
+  CHECK(as_primitive<uint8_t>(numeric::add_wrapping(ua, ub).unwrap()).values() == (std::vector<uint8_t>{0, 7, 8}));
+  auto uc = UInt8Array::from(std::vector<uint8_t>{34, 5, 3});
+  CHECK_EQ(numeric::sub(uc, ub).unwrap_err().to_string(), std::string("Arithmetic overflow: Overflow happened on: 34 - 200"));
+  CHECK(as_primitive<uint8_t>(numeric::sub_wrapping(uc, ub).unwrap()).values() == (std::vector<uint8_t>{90, 3, 254}));
+  CHECK_EQ(numeric::mul(uc, ub).unwrap_err().to_string(), std::string("Arithmetic overflow: Overflow happened on: 34 * 200"));
+  CHECK(as_primitive<uint8_t>(numeric::mul_wrapping(uc, ub).unwrap()).values() == (std::vector<uint8_t>{144, 10, 15}));
+
+  auto mn = Int16Array::from(std::vector<int16_t>{std::numeric_limits<int16_t>::min()});
+  auto m1 = Int16Array::from(std::vector<int16_t>{-1});
+  CHECK_EQ(numeric::div(mn, m1).unwrap_err().to_string(), std::string("Arithmetic overflow: Overflow happened on: -32768 / -1"));
+  CHECK(as_primitive<int16_t>(numeric::rem(mn, m1).unwrap()).values() == (std::vector<int16_t>{0}));
+  auto x = Int16Array::from(std::vector<int16_t>{21});
+  auto z = Int16Array::from(std::vector<int16_t>{0});
+  CHECK_EQ(numeric::div(x, z).unwrap_err().to_string(), std::string("Divide by zero error"));
+  CHECK_EQ(numeric::rem(x, z).unwrap_err().to_string(), std::string("Divide by zero error"));
+}
+
+// numeric.rs:1364-1397 test_float
+static void test_float() {
+  const float MAX = std::numeric_limits<float>::max(), INF = std::numeric_limits<float>::infinity();
+  auto a = Float32Array::from(std::vector<float>{1.f, MAX, 6.f, -4.f, -1.f, 0.f});
+  auto b = Float32Array::from(std::vector<float>{1.f, MAX, MAX, -3.f, 45.f, 0.f});
+  CHECK(as_primitive<float>(numeric::add(a, b).unwrap()).values() == (std::vector<float>{2.f, INF, MAX, -7.f, 44.f, 0.f}));
+  CHECK(as_primitive<float>(numeric::sub(a, b).unwrap()).values() == (std::vector<float>{0.f, 0.f, -MAX, -1.f, -46.f, 0.f}));
+  CHECK(as_primitive<float>(numeric::mul(a, b).unwrap()).values() == (std::vector<float>{1.f, INF, INF, 12.f, -45.f, 0.f}));
+  auto d = as_primitive<float>(numeric::div(a, b).unwrap()).values();
+  CHECK_EQ(d[0], 1.f);
+  CHECK_EQ(d[1], 1.f);
+  CHECK(d[2] < std::numeric_limits<float>::epsilon());
+  CHECK_EQ(d[3], -4.f / -3.f);
+  CHECK(std::isnan(d[5]));
+  auto r = as_primitive<float>(numeric::rem(a, b).unwrap()).values();
+  CHECK((std::vector<float>(r.begin(), r.begin() + 5)) == (std::vector<float>{0.f, 0.f, 6.f, -1.f, -1.f}));
+  CHECK(std::isnan(r[5]));
+}
+
+// numeric.rs:1152-1185 test_neg; scalar arms numeric.rs:278-317
+static void test_neg_and_scalars() {
+  CHECK(as_primitive<int64_t>(numeric::neg(Int64Array::from(std::vector<int64_t>{1, -5, 2, 693, 3929})).unwrap()).values() ==
+        (std::vector<int64_t>{-1, 5, -2, -693, -3929}));
+  CHECK_EQ(numeric::neg(Int32Array::from(std::vector<int32_t>{std::numeric_limits<int32_t>::min()})).unwrap_err().to_string(),
+           std::string("Arithmetic overflow: Overflow happened on: - -2147483648"));
+  CHECK_EQ(as_primitive<int64_t>(numeric::neg_wrapping(Int64Array::from(std::vector<int64_t>{std::numeric_limits<int64_t>::min()})).unwrap()).value(0),
+           std::numeric_limits<int64_t>::min());
+  CHECK_EQ(numeric::neg(UInt32Array::from(std::vector<uint32_t>{1})).unwrap_err().to_string(),
+           std::string("Invalid argument error: Invalid arithmetic operation: !UInt32"));
+  auto arr = Int64Array::from(std::vector<O<int64_t>>{1, N, 3});
+  CHECK(as_primitive<int64_t>(numeric::add(arr, new_scalar<int64_t>(10)).unwrap()).to_vec() == (std::vector<O<int64_t>>{11, N, 13}));
+  CHECK(as_primitive<int64_t>(numeric::sub(new_scalar<int64_t>(10), arr).unwrap()).to_vec() == (std::vector<O<int64_t>>{9, N, 7}));
+  CHECK(as_primitive<int64_t>(numeric::add(arr, new_null_scalar<int64_t>()).unwrap()).to_vec() == (std::vector<O<int64_t>>{N, N, N}));
+  CHECK_EQ(numeric::add(Int32Array::from(std::vector<int32_t>{1}), Int64Array::from(std::vector<int64_t>{1})).unwrap_err().to_string(),
+           std::string("Invalid argument error: Invalid arithmetic operation: Int32 + Int64"));
+}
+
+// arrow-ord/src/comparison.rs:2475-2571 (NaN totalOrder), :3558-3575 test_floating_zeros
+static void test_cmp_total_order() {
+  const double NaN = std::numeric_limits<double>::quiet_NaN();
+  auto a1 = Float64Array::from(std::vector<double>{NaN, 7.0, 8.0, 8.0, 10.0});
+  auto a2 = Float64Array::from(std::vector<double>{NaN, NaN, 8.0, 8.0, 10.0});
+  CHECK(cmpk::eq(a1, a2).unwrap().values() == (std::vector<bool>{true, false, true, true, true}));
+  CHECK(cmpk::neq(a1, a2).unwrap().values() == (std::vector<bool>{false, true, false, false, false}));
+  auto b1 = Float64Array::from(std::vector<double>{NaN, 7.0, 8.0, 8.0, 11.0, NaN});
+  auto b2 = Float64Array::from(std::vector<double>{NaN, NaN, 8.0, 9.0, 10.0, 1.0});
+  CHECK(cmpk::lt(b1, b2).unwrap().values() == (std::vector<bool>{false, true, false, true, false, false}));
+  CHECK(cmpk::lt_eq(b1, b2).unwrap().values() == (std::vector<bool>{true, true, true, true, false, false}));
+  CHECK(cmpk::gt(b1, b2).unwrap().values() == (std::vector<bool>{false, false, false, false, true, true}));
+  CHECK(cmpk::gt_eq(b1, b2).unwrap().values() == (std::vector<bool>{true, false, true, false, true, true}));
+  CHECK(cmpk::eq(a1, new_scalar<double>(NaN)).unwrap().values() == (std::vector<bool>{true, false, false, false, false}));
+  auto za = Float32Array::from(std::vector<float>{0.0f, -0.0f});
+  auto zb = Float32Array::from(std::vector<float>{-0.0f, 0.0f});
+  CHECK(cmpk::eq(za, zb).unwrap().values() == (std::vector<bool>{false, false}));
+  CHECK(cmpk::eq(za, new_scalar<float>(0.0f)).unwrap().values() == (std::vector<bool>{true, false}));
+  CHECK(cmpk::eq(za, new_scalar<float>(-0.0f)).unwrap().values() == (std::vector<bool>{false, true}));
+}
+
+// arrow-ord/src/cmp.rs:1044-1116 is_distinct_from_nulls, test_distinct_scalar
+static void test_distinct() {
+  auto l = Int32Array::from(std::vector<O<int32_t>>{0, 0, N, 3, 0, 0});
+  auto r = Int32Array::from(std::vector<O<int32_t>>{0, N, N, N, 0, N});
+  CHECK(cmpk::distinct(l, r).unwrap().to_vec() == (std::vector<O<bool>>{false, true, false, true, false, true}));
+  CHECK(cmpk::not_distinct(l, r).unwrap().to_vec() == (std::vector<O<bool>>{true, false, true, false, true, false}));
+  auto a = Int32Array::from(std::vector<O<int32_t>>{N, N, 2, 3});
+  auto b = new_null_scalar<int32_t>();
+  CHECK(cmpk::distinct(a, b).unwrap().to_vec() == (std::vector<O<bool>>{false, false, true, true}));
+  CHECK(cmpk::not_distinct(b, a).unwrap().to_vec() == (std::vector<O<bool>>{true, true, false, false}));
+  CHECK(cmpk::eq(a, b).unwrap().null_count() == 4);
+  CHECK_EQ(cmpk::eq(Int32Array::from(std::vector<int32_t>{1, 2, 3}), Int32Array::from(std::vector<int32_t>{1, 2})).unwrap_err().to_string(),
+           std::string("Invalid argument error: Cannot compare arrays of different lengths, got 3 vs 2"));
+}
+
+// arrow-cast/src/cast/mod.rs:8449-8569 test_cast_from_int64
+static void test_cast_from_int64() {
+  const int64_t I64MIN = std::numeric_limits<int64_t>::min(), I64MAX = std::numeric_limits<int64_t>::max();
+  auto a = Int64Array::from(std::vector<int64_t>{I64MIN, INT32_MIN, INT16_MIN, INT8_MIN, 0, INT8_MAX, INT16_MAX, INT32_MAX, I64MAX});
+  auto f = as_primitive<double>(cast(a, DataType::Float64).unwrap()).values();
+  CHECK(f == (std::vector<double>{-9223372036854775808.0, -2147483648.0, -32768.0, -128.0, 0.0, 127.0, 32767.0, 2147483647.0, 9223372036854775808.0}));
+  auto i32 = as_primitive<int32_t>(cast(a, DataType::Int32).unwrap()).to_vec();
+  CHECK(i32 == (std::vector<O<int32_t>>{N, INT32_MIN, INT16_MIN, INT8_MIN, 0, INT8_MAX, INT16_MAX, INT32_MAX, N}));
+  auto i16 = as_primitive<int16_t>(cast(a, DataType::Int16).unwrap()).to_vec();
+  CHECK(i16 == (std::vector<O<int16_t>>{N, N, int16_t(INT16_MIN), int16_t(INT8_MIN), int16_t(0), int16_t(INT8_MAX), int16_t(INT16_MAX), N, N}));
+  auto e = cast_with_options(Int64Array::from(std::vector<int64_t>{1, I64MAX}), DataType::Int32, CastOptions{false});
+  CHECK_EQ(e.unwrap_err().to_string(), std::string("Cast error: Can't cast value 9223372036854775807 to type Int32"));
+}
+
+// arrow-arith/src/aggregate.rs:1039-1137, :1299-1416, :1985
+static void test_aggregates() {
+  CHECK(sum(Int32Array::from(std::vector<int32_t>{1, 2, 3, 4, 5})) == O<int32_t>(15));
+  CHECK(sum(Float64Array::from(std::vector<double>{1.1, 2.2, 3.3, 4.4, 5.5})) == O<double>(16.5));
+  CHECK(!sum(Int32Array::from(std::vector<O<int32_t>>{N, N, N})).has_value());
+  CHECK(sum(Int32Array::from(std::vector<int32_t>{INT32_MAX, 1})) == O<int32_t>(INT32_MIN));  // test_sum_overflow: wraps
+  auto a = Int32Array::from(std::vector<O<int32_t>>{5, N, N, 8, 9});
+  CHECK(min(a) == O<int32_t>(5));
+  CHECK(max(a) == O<int32_t>(9));
+  const double NaN = std::numeric_limits<double>::quiet_NaN(), INF = std::numeric_limits<double>::infinity();
+  auto f = Float64Array::from(std::vector<double>{-INF, NaN, INF, -NaN});
+  auto mx = *max(f), mn = *min(f);
+  CHECK(std::isnan(mx) && !std::signbit(mx));  // test_primitive_min_max_float_negative_nan
+  CHECK(std::isnan(mn) && std::signbit(mn));
+}
+
+int main() {
+  try {
+    Context::get(0);
+  } catch (const std::exception &e) {
+    std::printf("arrow-cuda host tests need a CUDA device: %s\n", e.what());
+    return 77;
+  }
+  struct T { const char *name; std::function<void()> fn; };
+  std::vector<T> tests = {
+      {"filter_array_slice", test_filter_array_slice},
+      {"filter_array_low_density", test_filter_array_low_density},
+      {"filter_array_high_density", test_filter_array_high_density},
+      {"filter_string_array", test_filter_string_array},
+      {"null_mask_and_fast_path", test_null_mask_and_fast_path},
+      {"filter_predicate_too_long", test_filter_predicate_too_long},
+      {"filter_record_batch", test_filter_record_batch},
+      {"take_primitive", test_take_primitive},
+      {"take_with_offset", test_take_with_offset},
+      {"take_bool", test_take_bool},
+      {"take_out_of_bounds", test_take_out_of_bounds},
+      {"take_strings_and_dictionary", test_take_strings_and_dictionary},
+      {"integer", test_integer},
+      {"float", test_float},
+      {"neg_and_scalars", test_neg_and_scalars},
+      {"cmp_total_order", test_cmp_total_order},
+      {"distinct", test_distinct},
+      {"cast_from_int64", test_cast_from_int64},
+      {"aggregates", test_aggregates},
+  };
+  for (auto &t : tests) {
+    int before = g_failed;
+    try {
+      t.fn();
+    } catch (const std::exception &e) {
+      ++g_failed;
+      std::printf("  EXCEPTION in %s: %s\n", t.name, e.what());
+    }
+    std::printf("test %s ... %s\n", t.name, g_failed == before ? "ok" : "FAILED");
+  }
+  std::printf("%zu tests, %d checks, %d failed\n", tests.size(), g_checks, g_failed);
+  return g_failed ? 1 : 0;
+}

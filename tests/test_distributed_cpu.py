@@ -1,0 +1,152 @@
+"""world_size-2 gloo test (CPU) of the host-side multi-GPU logic: row-range sharding + the final
+reduction of scalar aggregates. Each rank runs the step on its shard with the CPU oracle, the
+partials are exchanged with torch.distributed (gloo) exactly as bench.py does over NCCL, and the
+result must equal the single-process result over the whole table (bit-exact for integers and
+float min/max; float sum within the documented tolerance)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _make_table(n):
+    rng = np.random.default_rng(123)
+    vals = rng.integers(-2**62, 2**62, n, dtype=np.int64)
+    fvals = rng.random(n) * 2e6 - 1e6
+    fvals[rng.integers(0, n, 16)] = np.nan
+    fvals[rng.integers(0, n, 16)] = -np.inf
+    valid = rng.random(n) >= 0.05
+    pred = rng.random(n) < 0.1
+    return vals, fvals, valid, pred
+
+
+def _shard_step(orc, acu, abi, vals, fvals, valid, pred, lo, hi):
+    from acu import HostArray
+    col = HostArray.from_numpy(abi.I64, vals[lo:hi], valid[lo:hi])
+    fcol = HostArray.from_numpy(abi.F64, fvals[lo:hi], valid[lo:hi])
+    p = HostArray.bool_from_numpy(pred[lo:hi])
+    f = orc.filter(col, p)
+    ff = orc.filter(fcol, p)
+    idx = HostArray.from_numpy(abi.U32, np.arange(0, f.length, 2, dtype=np.uint32))  # monotone half-sample of the filtered rows
+    t, tf = orc.take(f, idx), orc.take(ff, idx)
+    nvalid = int(t.valid_mask().sum())
+    return {"rows": f.length, "sum": (orc.sum(t), nvalid), "min": (orc.min(tf), nvalid), "max": (orc.max(tf), nvalid), "fsum": (orc.sum(tf), nvalid)}
+
+
+def _worker(rank, world, port, n, out_q):
+    sys.path.insert(0, os.path.join(REPO, "arrow-rs_b200"))
+    sys.path.insert(0, HERE)
+    import acu
+    from acu import _abi as abi
+    from acu import shard
+    from oracle import Oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    orc = Oracle()
+    vals, fvals, valid, pred = _make_table(n)
+    lo, hi = shard.shard_ranges(n, world)[rank]
+    part = _shard_step(orc, acu, abi, vals, fvals, valid, pred, lo, hi)
+    # --- the exchange: row counts + integer sum as int64 all-reduce(sum), min/max on totalOrder keys ---
+    t = torch.tensor([part["rows"], part["sum"][1], part["sum"][0] or 0], dtype=torch.int64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)  # int64 sum wraps like add_wrapping
+    kmin = torch.tensor([shard.total_order_key(part["min"][0], abi.F64) if part["min"][0] is not None else 2**63 - 1], dtype=torch.int64)
+    kmax = torch.tensor([shard.total_order_key(part["max"][0], abi.F64) if part["max"][0] is not None else -2**63], dtype=torch.int64)
+    dist.all_reduce(kmin, op=dist.ReduceOp.MIN)
+    dist.all_reduce(kmax, op=dist.ReduceOp.MAX)
+    fs = torch.tensor([part["fsum"][0] if part["fsum"][0] is not None and not np.isnan(part["fsum"][0]) else 0.0], dtype=torch.float64)
+    dist.all_reduce(fs, op=dist.ReduceOp.SUM)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, part)
+    if rank == 0:
+        out_q.put({"rows": int(t[0]), "valid": int(t[1]), "sum": int(t[2]), "min": shard.from_total_order_key(int(kmin[0]), abi.F64),
+                   "max": shard.from_total_order_key(int(kmax[0]), abi.F64), "fsum": float(fs[0]), "parts": gathered})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [100_003, 4096])
+def test_two_rank_sharded_step_matches_single_process(n):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+
+    sys.path.insert(0, os.path.join(REPO, "arrow-rs_b200"))
+    import acu
+    from acu import _abi as abi
+    from acu import shard
+    from oracle import Oracle
+    orc = Oracle()
+    vals, fvals, valid, pred = _make_table(n)
+    ranges = shard.shard_ranges(n, world)
+    assert ranges[0][0] == 0 and ranges[-1][1] == n and all(r[0] % 64 == 0 for r in ranges)
+    # the same shard-local pipeline, single process: fold with combine_aggregates
+    parts = [_shard_step(orc, acu, abi, vals, fvals, valid, pred, lo, hi) for lo, hi in ranges]
+    assert got["rows"] == sum(p["rows"] for p in parts)
+    exp_sum, exp_valid = shard.combine_aggregates(abi.SUM, abi.I64, [p["sum"] for p in parts])
+    assert got["valid"] == exp_valid
+    assert np.int64(np.uint64(got["sum"] & 0xFFFFFFFFFFFFFFFF)) == np.int64(exp_sum)
+    exp_min, _ = shard.combine_aggregates(abi.MIN, abi.F64, [p["min"] for p in parts])
+    exp_max, _ = shard.combine_aggregates(abi.MAX, abi.F64, [p["max"] for p in parts])
+    for g, e in ((got["min"], exp_min), (got["max"], exp_max)):
+        assert (np.isnan(g) and np.isnan(e) and np.signbit(g) == np.signbit(e)) or g == e
+    # and the min/max over shards equals the oracle's min/max over the concatenated taken column (totalOrder is associative)
+    from acu import HostArray
+    allvals, allmask = [], []
+    for (lo, hi) in ranges:
+        fcol = HostArray.from_numpy(abi.F64, fvals[lo:hi], valid[lo:hi])
+        ff = orc.filter(fcol, HostArray.bool_from_numpy(pred[lo:hi]))
+        tf = orc.take(ff, HostArray.from_numpy(abi.U32, np.arange(0, ff.length, 2, dtype=np.uint32)))
+        allvals.append(tf.value_array())
+        allmask.append(tf.valid_mask())
+    whole = HostArray.from_numpy(abi.F64, np.concatenate(allvals), np.concatenate(allmask))
+    wmin, wmax = orc.min(whole), orc.max(whole)
+    for g, e in ((got["min"], wmin), (got["max"], wmax)):
+        assert (np.isnan(g) and np.isnan(e) and np.signbit(g) == np.signbit(e)) or g == e
+    assert [p["rows"] for p in got["parts"]] == [p["rows"] for p in parts]
+
+
+def test_shard_ranges_properties():
+    sys.path.insert(0, os.path.join(REPO, "arrow-rs_b200"))
+    from acu import shard
+    for n in [0, 1, 63, 64, 65, 1000, 10**9]:
+        for w in [1, 2, 3, 8]:
+            r = shard.shard_ranges(n, w)
+            assert len(r) == w and r[0][0] == 0 and r[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            assert all(lo % 64 == 0 for lo, _ in r if lo < n)
+
+
+def test_total_order_key_round_trip_and_order():
+    sys.path.insert(0, os.path.join(REPO, "arrow-rs_b200"))
+    from acu import _abi as abi
+    from acu import shard
+    neg_nan = float(np.array([0xFFF8000000000000], dtype=np.uint64).view(np.float64)[0])
+    xs = [neg_nan, -np.inf, -1.5, -0.0, 0.0, 5e-324, 2.0, np.inf, float("nan")]  # ascending totalOrder
+    keys = [shard.total_order_key(x, abi.F64) for x in xs]
+    assert keys == sorted(keys) and len(set(keys)) == len(keys)
+    for x, k in zip(xs, keys):
+        y = shard.from_total_order_key(k, abi.F64)
+        assert np.array([x]).view(np.uint64)[0] == np.array([y]).view(np.uint64)[0]
