@@ -49,6 +49,7 @@ int64_t acu_resolve_null_count(acu_ctx *ctx, const acu_array *a, acu_status *st)
 extern "C" acu_status acu_bitmap_count(acu_ctx *ctx, const uint8_t *bits, int64_t offset,
                                        const uint8_t *validity, int64_t validity_offset, int64_t len,
                                        int64_t *out_count) {
+  ACU_ENTER(ctx);
   *out_count = 0;
   if (len <= 0) return ACU_OK;
   ACU_TRY(acu_res_reset(ctx));

@@ -226,6 +226,7 @@ acu_status zero_first_offset(acu_ctx *ctx, void *out_offsets, int ob) {
 
 extern "C" acu_status acu_filter_plan_indices(acu_ctx *ctx, const acu_filter_plan *plan, acu_dtype index_dtype,
                                               void *out_indices) {
+  ACU_ENTER(ctx);
   if (index_dtype != ACU_U32 && index_dtype != ACU_U64)
     return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "plan indices must be UInt32 or UInt64");
   if (index_dtype == ACU_U32 && acu_filter_plan_len(plan) > (int64_t)UINT32_MAX)
@@ -248,6 +249,7 @@ extern "C" acu_status acu_take_bytes(acu_ctx *ctx, int32_t offset_bytes, const v
                                      const acu_array *nulls_of, const acu_array *indices, acu_dtype index_dtype,
                                      int32_t check_bounds, void *out_offsets, uint8_t *out_data,
                                      int64_t out_data_capacity, int64_t *out_data_len, acu_array_out *out_nulls) {
+  ACU_ENTER(ctx);
   *out_data_len = 0;
   if (offset_bytes != 4 && offset_bytes != 8)
     return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "offset width must be 4 or 8");
@@ -264,6 +266,7 @@ extern "C" acu_status acu_filter_bytes(acu_ctx *ctx, const acu_filter_plan *plan
                                        const void *offsets, const uint8_t *data, const acu_array *nulls_of,
                                        void *out_offsets, uint8_t *out_data, int64_t out_data_capacity,
                                        int64_t *out_data_len, acu_array_out *out_nulls) {
+  ACU_ENTER(ctx);
   *out_data_len = 0;
   if (offset_bytes != 4 && offset_bytes != 8)
     return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "offset width must be 4 or 8");

@@ -126,6 +126,7 @@ acu_status acu_comm_destroy(acu_ctx *ctx) {
 }
 
 acu_status acu_comm_allreduce_i64_sum(acu_ctx *ctx, int64_t *values, int32_t n) {
+  ACU_ENTER(ctx);
   if (ctx->world <= 1 || !ctx->nccl_comm || n <= 0) return ACU_OK;
   NcclApi *api = nccl_api();
   void *buf;
@@ -139,6 +140,7 @@ acu_status acu_comm_allreduce_i64_sum(acu_ctx *ctx, int64_t *values, int32_t n) 
 
 acu_status acu_comm_allreduce_aggregates(acu_ctx *ctx, acu_dtype dtype, acu_agg_op op, uint64_t *partial_bits,
                                          int64_t *valid_counts, int32_t n) {
+  ACU_ENTER(ctx);
   if (ctx->world <= 1 || !ctx->nccl_comm || n <= 0) return ACU_OK;
   NcclApi *api = nccl_api();
   uint8_t *buf;

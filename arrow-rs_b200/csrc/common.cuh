@@ -74,6 +74,14 @@ int64_t acu_resolve_null_count(acu_ctx *ctx, const acu_array *a, acu_status *st)
     if (_e != cudaSuccess) return acu_cuda_fail((ctx), _e, #expr);  \
   } while (0)
 
+// Every C-ABI entry point first makes the ctx's device current on the calling host thread
+// (a ctx may be driven from any thread; new threads default to device 0).
+#define ACU_ENTER(ctx)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = cudaSetDevice((ctx)->device);                                          \
+    if (_e != cudaSuccess) return acu_cuda_fail((ctx), _e, "cudaSetDevice");                \
+  } while (0)
+
 #define ACU_TRY(expr)                  \
   do {                                 \
     acu_status _s = (expr);            \

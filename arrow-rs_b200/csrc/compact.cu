@@ -517,6 +517,7 @@ extern "C" {
 
 acu_status acu_filter_plan_create(acu_ctx *ctx, const acu_array *pred, acu_filter_plan **out_plan) {
   *out_plan = nullptr;
+  ACU_ENTER(ctx);
   acu_filter_plan *plan = new acu_filter_plan();
   const int64_t len = pred->len;
   plan->len = len;
@@ -584,6 +585,7 @@ int32_t acu_filter_plan_strategy(const acu_filter_plan *plan) { return plan->str
 
 acu_status acu_filter_primitive(acu_ctx *ctx, const acu_filter_plan *plan, int32_t elem_bytes,
                                 const acu_array *values, acu_array_out *out) {
+  ACU_ENTER(ctx);
   ACU_TRY(check_len(ctx, plan, values->len));
   out->len = plan->count;
   out->has_validity = 0;
@@ -617,6 +619,7 @@ acu_status acu_filter_primitive(acu_ctx *ctx, const acu_filter_plan *plan, int32
 
 acu_status acu_filter_boolean(acu_ctx *ctx, const acu_filter_plan *plan, const acu_array *values,
                               acu_array_out *out) {
+  ACU_ENTER(ctx);
   ACU_TRY(check_len(ctx, plan, values->len));
   out->len = plan->count;
   out->has_validity = 0;

@@ -175,6 +175,7 @@ void acu_ctx_destroy(acu_ctx *ctx) {
 }
 
 acu_status acu_ctx_sync(acu_ctx *ctx) {
+  ACU_ENTER(ctx);
   ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   acu_kstats_drain(ctx);
   return ACU_OK;
@@ -199,6 +200,7 @@ acu_status acu_malloc(acu_ctx *ctx, size_t bytes, void **out) {
 }
 
 acu_status acu_free(acu_ctx *ctx, void *dptr) {
+  ACU_ENTER(ctx);
   if (!dptr) return ACU_OK;
   auto it = ctx->allocs.find(dptr);
   if (it == ctx->allocs.end())
@@ -210,47 +212,57 @@ acu_status acu_free(acu_ctx *ctx, void *dptr) {
 }
 
 acu_status acu_memset(acu_ctx *ctx, void *dptr, int32_t byte, size_t bytes) {
+  ACU_ENTER(ctx);
   if (bytes) ACU_CUDA(ctx, cudaMemsetAsync(dptr, byte, bytes, ctx->stream));
   return ACU_OK;
 }
 
 acu_status acu_memcpy_h2d(acu_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  ACU_ENTER(ctx);
   if (bytes) ACU_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return ACU_OK;
 }
 acu_status acu_memcpy_d2h(acu_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  ACU_ENTER(ctx);
   if (bytes) ACU_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return ACU_OK;
 }
 acu_status acu_memcpy_d2d(acu_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  ACU_ENTER(ctx);
   if (bytes) ACU_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   return ACU_OK;
 }
 acu_status acu_memcpy_h2d_async(acu_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  ACU_ENTER(ctx);
   if (bytes) ACU_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   return ACU_OK;
 }
 acu_status acu_memcpy_d2h_async(acu_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  ACU_ENTER(ctx);
   if (bytes) ACU_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   return ACU_OK;
 }
 acu_status acu_host_alloc(acu_ctx *ctx, size_t bytes, void **out) {
+  ACU_ENTER(ctx);
   ACU_CUDA(ctx, cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
   return ACU_OK;
 }
 acu_status acu_host_free(acu_ctx *ctx, void *host) {
+  ACU_ENTER(ctx);
   if (host) ACU_CUDA(ctx, cudaFreeHost(host));
   return ACU_OK;
 }
 
 acu_status acu_timer_start_slot(acu_ctx *ctx, int32_t slot) {
+  ACU_ENTER(ctx);
   if (slot < 0 || slot >= ACU_TIMER_SLOTS) return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "timer slot %d", slot);
   ACU_CUDA(ctx, cudaEventRecord(ctx->tev[slot][0], ctx->stream));
   return ACU_OK;
 }
 acu_status acu_timer_stop_slot(acu_ctx *ctx, int32_t slot, float *out_ms) {
+  ACU_ENTER(ctx);
   if (slot < 0 || slot >= ACU_TIMER_SLOTS) return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "timer slot %d", slot);
   ACU_CUDA(ctx, cudaEventRecord(ctx->tev[slot][1], ctx->stream));
   ACU_CUDA(ctx, cudaEventSynchronize(ctx->tev[slot][1]));
@@ -310,6 +322,7 @@ __global__ void __launch_bounds__(256) k_generate_bits(uint64_t seed, int64_t fi
 
 extern "C" acu_status acu_generate_values(acu_ctx *ctx, int32_t kind, uint64_t seed, int64_t first_row,
                                           uint64_t param, void *out, int64_t n) {
+  ACU_ENTER(ctx);
   if (kind < 0 || kind > 4) return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "unknown generator kind %d", kind);
   if (n <= 0) return ACU_OK;
   ACU_LAUNCH(ctx, k_generate_values, acu_grid(ctx, (n + 255) / 256, 16), 256, 0, kind, seed, first_row, param, out, n);
@@ -318,6 +331,7 @@ extern "C" acu_status acu_generate_values(acu_ctx *ctx, int32_t kind, uint64_t s
 
 extern "C" acu_status acu_generate_bits(acu_ctx *ctx, uint64_t seed, int64_t first_row, double p,
                                         uint8_t *out_bits, int64_t n) {
+  ACU_ENTER(ctx);
   if (n <= 0) return ACU_OK;
   uint64_t thr = p >= 1.0 ? ~0ull : (uint64_t)(p * 18446744073709551616.0);
   int64_t words = (n + 63) / 64;

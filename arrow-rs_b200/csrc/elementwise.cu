@@ -732,11 +732,13 @@ acu_status cast_from(acu_ctx *ctx, acu_dtype to, int32_t safe, const acu_array *
 
 extern "C" acu_status acu_arith(acu_ctx *ctx, acu_dtype dtype, acu_arith_op op, const acu_array *a,
                                 const acu_array *b, acu_array_out *out) {
+  ACU_ENTER(ctx);
   ACU_DISPATCH(dtype, arith_typed, ctx, op, a, b, out)
   return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "Invalid arithmetic operation: dtype %d", (int)dtype);
 }
 
 extern "C" acu_status acu_neg(acu_ctx *ctx, acu_dtype dtype, int32_t checked, const acu_array *a, acu_array_out *out) {
+  ACU_ENTER(ctx);
   if (checked && (dtype == ACU_U8 || dtype == ACU_U16 || dtype == ACU_U32 || dtype == ACU_U64))  // numeric.rs:174-176
     return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "Invalid arithmetic operation: !%s", acu_dtype_name(dtype));
   ACU_DISPATCH(dtype, neg_typed, ctx, checked, a, out)
@@ -745,12 +747,14 @@ extern "C" acu_status acu_neg(acu_ctx *ctx, acu_dtype dtype, int32_t checked, co
 
 extern "C" acu_status acu_cmp(acu_ctx *ctx, acu_dtype dtype, acu_cmp_op op, const acu_array *a,
                               const acu_array *b, acu_array_out *out) {
+  ACU_ENTER(ctx);
   ACU_DISPATCH(dtype, cmp_typed, ctx, op, a, b, out)
   return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "Invalid comparison operation: dtype %d", (int)dtype);
 }
 
 extern "C" acu_status acu_cast_numeric(acu_ctx *ctx, acu_dtype from, acu_dtype to, int32_t safe,
                                        const acu_array *a, acu_array_out *out) {
+  ACU_ENTER(ctx);
   ACU_DISPATCH(from, cast_from, ctx, to, safe, a, out)
   return acu_fail(ctx, ACU_ERR_NOT_YET_IMPLEMENTED, -1, 0, 0, 0, "cast from dtype %d", (int)from);
 }

@@ -190,6 +190,7 @@ acu_status aggregate_typed(acu_ctx *ctx, acu_agg_op op, const acu_array *a, uint
 
 extern "C" acu_status acu_aggregate(acu_ctx *ctx, acu_dtype dtype, acu_agg_op op, const acu_array *a,
                                     uint64_t *out_bits, int64_t *out_valid_count) {
+  ACU_ENTER(ctx);
   switch (dtype) {
     case ACU_I8: return aggregate_typed<int8_t>(ctx, op, a, out_bits, out_valid_count);
     case ACU_I16: return aggregate_typed<int16_t>(ctx, op, a, out_bits, out_valid_count);

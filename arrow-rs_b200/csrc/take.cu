@@ -305,6 +305,7 @@ acu_status fetch_index(acu_ctx *ctx, const acu_array *indices, acu_dtype t, int6
 acu_status acu_take_common(acu_ctx *ctx, int32_t elem_bytes, const acu_array *values, bool boolean_values,
                            const acu_array *indices, acu_dtype index_dtype, int32_t check_bounds,
                            acu_array_out *out) {
+  ACU_ENTER(ctx);
   const int kind = index_kind(index_dtype);
   if (kind < 0)  // take.rs:103
     return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "Take only supported for integers, got %s", acu_dtype_name(index_dtype));
