@@ -148,7 +148,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or LIB_PATH
+    path = path or os.environ.get("ACU_LIB_PATH") or LIB_PATH  # ACU_LIB_PATH: tuning builds of the same ABI
     if not os.path.exists(path):
         raise RuntimeError(
             f"{path} is missing: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'). "

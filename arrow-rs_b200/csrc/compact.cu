@@ -281,7 +281,7 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <int W> struct AsyncCfg {
-  static constexpr int PASS_BYTES = (TILE_ROWS * W < 8192) ? TILE_ROWS * W : 8192;  // per-warp buffer
+  static constexpr int PASS_BYTES = (TILE_ROWS * W < 4096) ? TILE_ROWS * W : 4096;  // per-warp landing buffer (4 KB: 6 CTAs/SM)
   static constexpr int PASS_ROWS = PASS_BYTES / W;
   static constexpr int PASSES = TILE_ROWS / PASS_ROWS;
   static constexpr int CPP = PASS_BYTES / 16;  // 16-byte chunks per pass
@@ -412,25 +412,20 @@ __global__ void __launch_bounds__(256) k_compress_bits(const uint8_t *__restrict
     const uint64_t base = __ldg(tile_off + (w0 >> 4));  // first output bit of this 32-word group
     uint64_t bits = 0;
     if (m) {
-      // PEXT in 32-bit halves (64-bit shifts / ffs are multi-instruction on the SM)
+      // PEXT(v, m). The loop runs over the RARER kind of selected bit: validity bitmaps are
+      // mostly ones, so start from all-ones and clear the (few) selected-and-unset rows; data
+      // that is mostly zeros starts from zero and sets. rank(b) = popc(m below bit b).
       const uint64_t v = ld_bits64(src, soff + (w << 6), soff + len);
-      uint32_t m0 = (uint32_t)m, m1 = (uint32_t)(m >> 32);
-      const uint32_t v0 = (uint32_t)v, v1 = (uint32_t)(v >> 32);
-      uint32_t lo = 0, hi = 0;  // compressed halves: lo has popc(m0) bits, hi has popc(m1) bits
-      int k = 0;
-      while (m0) {
-        const int b = __ffs((int)m0) - 1;
-        m0 &= m0 - 1;
-        lo |= ((v0 >> b) & 1u) << k++;
+      const uint64_t ones = m & v, zeros = m & ~v;
+      const bool clear_mode = __popcll(zeros) <= __popcll(ones);
+      uint64_t it = clear_mode ? zeros : ones, acc = 0;
+      while (it) {
+        const int b = __ffsll((long long)it) - 1;
+        it &= it - 1;
+        acc |= 1ull << __popcll(m & ((1ull << b) - 1ull));
       }
-      const int k0 = k;
-      k = 0;
-      while (m1) {
-        const int b = __ffs((int)m1) - 1;
-        m1 &= m1 - 1;
-        hi |= ((v1 >> b) & 1u) << k++;
-      }
-      bits = (uint64_t)lo | ((uint64_t)hi << k0);  // k0 <= 32
+      const uint64_t full = cnt == 64 ? ~0ull : ((1ull << cnt) - 1ull);
+      bits = clear_mode ? (full & ~acc) : acc;
     }
     valid_cnt += __popcll(bits);
     // assemble in a warp-private window aligned to the first output word

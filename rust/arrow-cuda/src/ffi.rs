@@ -1,0 +1,98 @@
+//! 1:1 declarations of `include/arrow_cuda.h`. Uncompiled in this repository (no rustc here):
+//! kept to plain `#[repr(C)]` structs and `extern "C"` prototypes so it is correct by inspection.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_void};
+
+pub type acu_status = i32;
+pub const ACU_OK: acu_status = 0;
+pub const ACU_ERR_INVALID_ARGUMENT: acu_status = 1;
+pub const ACU_ERR_COMPUTE: acu_status = 2;
+pub const ACU_ERR_ARITHMETIC_OVERFLOW: acu_status = 3;
+pub const ACU_ERR_DIVIDE_BY_ZERO: acu_status = 4;
+pub const ACU_ERR_OFFSET_OVERFLOW: acu_status = 5;
+pub const ACU_ERR_CAST: acu_status = 6;
+pub const ACU_ERR_NOT_YET_IMPLEMENTED: acu_status = 7;
+pub const ACU_ERR_PANIC_OUT_OF_BOUNDS: acu_status = 8;
+
+#[repr(C)]
+pub struct acu_ctx { _private: [u8; 0] }
+#[repr(C)]
+pub struct acu_filter_plan { _private: [u8; 0] }
+
+#[repr(C)]
+pub struct acu_error_detail {
+    pub status: acu_status,
+    pub cuda_error: i32,
+    pub index: i64,
+    pub lhs_bits: u64,
+    pub rhs_bits: u64,
+    pub len: u64,
+    pub message: [c_char; 256],
+}
+
+#[repr(C)]
+pub struct acu_array {
+    pub values: *const c_void,
+    pub values_offset: i64,
+    pub validity: *const u8,
+    pub validity_offset: i64,
+    pub len: i64,
+    pub null_count: i64,
+    pub is_scalar: i32,
+    pub reserved: i32,
+}
+
+#[repr(C)]
+pub struct acu_array_out {
+    pub values: *mut c_void,
+    pub validity: *mut u8,
+    pub len: i64,
+    pub null_count: i64,
+    pub has_validity: i32,
+    pub reserved: i32,
+}
+
+extern "C" {
+    pub fn acu_abi_version() -> i32;
+    pub fn acu_ctx_create(device: i32, out: *mut *mut acu_ctx) -> acu_status;
+    pub fn acu_ctx_destroy(ctx: *mut acu_ctx);
+    pub fn acu_ctx_sync(ctx: *mut acu_ctx) -> acu_status;
+    pub fn acu_last_error(ctx: *const acu_ctx) -> *const acu_error_detail;
+    pub fn acu_malloc(ctx: *mut acu_ctx, bytes: usize, out: *mut *mut c_void) -> acu_status;
+    pub fn acu_free(ctx: *mut acu_ctx, dptr: *mut c_void) -> acu_status;
+    pub fn acu_memcpy_h2d(ctx: *mut acu_ctx, dst: *mut c_void, src: *const c_void, bytes: usize) -> acu_status;
+    pub fn acu_memcpy_d2h(ctx: *mut acu_ctx, dst: *mut c_void, src: *const c_void, bytes: usize) -> acu_status;
+    pub fn acu_host_alloc(ctx: *mut acu_ctx, bytes: usize, out: *mut *mut c_void) -> acu_status;
+    pub fn acu_host_free(ctx: *mut acu_ctx, host: *mut c_void) -> acu_status;
+    pub fn acu_bitmap_count(ctx: *mut acu_ctx, bits: *const u8, offset: i64, validity: *const u8, validity_offset: i64,
+                            len: i64, out_count: *mut i64) -> acu_status;
+    pub fn acu_filter_plan_create(ctx: *mut acu_ctx, predicate: *const acu_array, out: *mut *mut acu_filter_plan) -> acu_status;
+    pub fn acu_filter_plan_destroy(ctx: *mut acu_ctx, plan: *mut acu_filter_plan);
+    pub fn acu_filter_plan_count(plan: *const acu_filter_plan) -> i64;
+    pub fn acu_filter_plan_len(plan: *const acu_filter_plan) -> i64;
+    pub fn acu_filter_plan_strategy(plan: *const acu_filter_plan) -> i32;
+    pub fn acu_filter_plan_indices(ctx: *mut acu_ctx, plan: *const acu_filter_plan, index_dtype: i32, out: *mut c_void) -> acu_status;
+    pub fn acu_filter_primitive(ctx: *mut acu_ctx, plan: *const acu_filter_plan, elem_bytes: i32, values: *const acu_array,
+                                out: *mut acu_array_out) -> acu_status;
+    pub fn acu_filter_boolean(ctx: *mut acu_ctx, plan: *const acu_filter_plan, values: *const acu_array, out: *mut acu_array_out) -> acu_status;
+    pub fn acu_filter_bytes(ctx: *mut acu_ctx, plan: *const acu_filter_plan, offset_bytes: i32, offsets: *const c_void, data: *const u8,
+                            nulls_of: *const acu_array, out_offsets: *mut c_void, out_data: *mut u8, out_data_capacity: i64,
+                            out_data_len: *mut i64, out_nulls: *mut acu_array_out) -> acu_status;
+    pub fn acu_take_primitive(ctx: *mut acu_ctx, elem_bytes: i32, values: *const acu_array, indices: *const acu_array,
+                              index_dtype: i32, check_bounds: i32, out: *mut acu_array_out) -> acu_status;
+    pub fn acu_take_boolean(ctx: *mut acu_ctx, values: *const acu_array, indices: *const acu_array, index_dtype: i32,
+                            check_bounds: i32, out: *mut acu_array_out) -> acu_status;
+    pub fn acu_take_bytes(ctx: *mut acu_ctx, offset_bytes: i32, offsets: *const c_void, data: *const u8, nulls_of: *const acu_array,
+                          indices: *const acu_array, index_dtype: i32, check_bounds: i32, out_offsets: *mut c_void,
+                          out_data: *mut u8, out_data_capacity: i64, out_data_len: *mut i64, out_nulls: *mut acu_array_out) -> acu_status;
+    pub fn acu_arith(ctx: *mut acu_ctx, dtype: i32, op: i32, a: *const acu_array, b: *const acu_array, out: *mut acu_array_out) -> acu_status;
+    pub fn acu_neg(ctx: *mut acu_ctx, dtype: i32, checked: i32, a: *const acu_array, out: *mut acu_array_out) -> acu_status;
+    pub fn acu_cmp(ctx: *mut acu_ctx, dtype: i32, op: i32, a: *const acu_array, b: *const acu_array, out: *mut acu_array_out) -> acu_status;
+    pub fn acu_cast_numeric(ctx: *mut acu_ctx, from: i32, to: i32, safe: i32, a: *const acu_array, out: *mut acu_array_out) -> acu_status;
+    pub fn acu_aggregate(ctx: *mut acu_ctx, dtype: i32, op: i32, a: *const acu_array, out_bits: *mut u64, out_valid: *mut i64) -> acu_status;
+    pub fn acu_comm_get_unique_id(out_id: *mut u8) -> acu_status;
+    pub fn acu_comm_init(ctx: *mut acu_ctx, id: *const u8, rank: i32, world: i32) -> acu_status;
+    pub fn acu_comm_destroy(ctx: *mut acu_ctx) -> acu_status;
+    pub fn acu_comm_allreduce_aggregates(ctx: *mut acu_ctx, dtype: i32, op: i32, partial_bits: *mut u64, valid_counts: *mut i64, n: i32) -> acu_status;
+    pub fn acu_comm_allreduce_i64_sum(ctx: *mut acu_ctx, values: *mut i64, n: i32) -> acu_status;
+}
