@@ -182,36 +182,155 @@ int index_kind(acu_dtype t) {
   }
 }
 
-// lengths -> scan -> offsets (+ optional byte copy). `idx`/`kind` address the source rows.
+// ---- fused lengths / scan / offsets / copy -------------------------------------------------
+// CTA = 1024 threads x 4 consecutive rows = 4096 rows (SCAN_ELEMS).
+__device__ __forceinline__ int64_t row_len(const void *offs, int ob, const void *idx, int kind, const uint8_t *out_valid,
+                                           int64_t j, int64_t m, int64_t *src_begin) {
+  if (j >= m || (out_valid && !ld_bit(out_valid, j))) { *src_begin = 0; return 0; }
+  const int64_t i = (int64_t)ld_index(idx, kind, j);
+  const int64_t s = ld_off(offs, ob, i);
+  *src_begin = s;
+  return ld_off(offs, ob, i + 1) - s;
+}
+
+// pass 1: total value bytes of each CTA's 4096 rows
+__global__ void __launch_bounds__(1024) k_bytes_block_totals(const void *offs, int ob, const void *idx, int kind, int64_t m,
+                                                             const uint8_t *out_valid, int64_t *__restrict__ block_tot) {
+  __shared__ int64_t warp_tot[32];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_ELEMS + (int64_t)threadIdx.x * 4;
+  int64_t sum = 0, sb;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sum += row_len(offs, ob, idx, kind, out_valid, base + k, m, &sb);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(ACU_FULL_MASK, sum, o);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) warp_tot[wid] = sum;
+  __syncthreads();
+  if (wid == 0) {
+    int64_t t = warp_tot[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(ACU_FULL_MASK, t, o);
+    if (lane == 0) block_tot[blockIdx.x] = t;
+  }
+}
+
+// pass 2 (after the inclusive scan of the CTA totals): offsets + byte copy.
+// Source bytes are fetched 8 at a time with two aligned loads + funnel shift (ld_bits64 on a
+// byte position), so the copy loop carries no dependent byte loads; a thread's 4 rows are
+// adjacent in the destination.
+__global__ void __launch_bounds__(1024) k_bytes_offsets_copy(const void *offs, int ob, const uint8_t *__restrict__ data,
+                                                             const void *idx, int kind, int64_t m, const uint8_t *out_valid,
+                                                             const int64_t *__restrict__ block_incl, int64_t first_block,
+                                                             void *out_offs, uint8_t *__restrict__ out_data, int64_t limit,
+                                                             int64_t probe_row, unsigned long long *res, int stage_cap) {
+  __shared__ int64_t warp_tot[32];
+  const int64_t blk = first_block + blockIdx.x;
+  const int64_t base = blk * SCAN_ELEMS + (int64_t)threadIdx.x * 4;
+  int64_t len[4], src[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) len[k] = row_len(offs, ob, idx, kind, out_valid, base + k, m, &src[k]);
+  const int64_t mine = len[0] + len[1] + len[2] + len[3];
+  int64_t incl = mine;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int64_t y = __shfl_up_sync(ACU_FULL_MASK, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) warp_tot[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int64_t w = warp_tot[lane], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int64_t y = __shfl_up_sync(ACU_FULL_MASK, wi, o);
+      if (lane >= o) wi += y;
+    }
+    warp_tot[lane] = wi - w;
+  }
+  __syncthreads();
+  extern __shared__ __align__(16) uint8_t s_out[];
+  const int64_t cta_begin = blk ? block_incl[blk - 1] : 0, cta_end = block_incl[blk];
+  const int64_t stage_origin = cta_begin - (int64_t)((uintptr_t)(out_data + cta_begin) & 15);  // global byte that maps to s_out[0]
+  const bool staged = out_data != nullptr && probe_row < 0 && (cta_end - stage_origin) <= (int64_t)stage_cap;
+  int64_t pos = cta_begin + warp_tot[wid] + incl - mine;  // first output byte of this thread
+  unsigned long long err = ~0ull;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t j = base + k;
+    if (j >= m) break;
+    const int64_t end = pos + len[k];
+    if (end > limit && (unsigned long long)j < err) err = (unsigned long long)j;
+    if (j == probe_row) res[RES_AUX1] = (unsigned long long)end;
+    if (probe_row < 0) {
+      if (ob == 4) static_cast<int32_t *>(out_offs)[j + 1] = (int32_t)end;
+      else static_cast<int64_t *>(out_offs)[j + 1] = end;
+      if (j == 0) { if (ob == 4) static_cast<int32_t *>(out_offs)[0] = 0; else static_cast<int64_t *>(out_offs)[0] = 0; }
+      if (out_data) {
+        // staged: the CTA's output bytes are contiguous [cta_begin, cta_end); build them in shared memory laid out
+        // relative to the 16-B aligned global address so that the copy-out is whole 128-bit stores.
+        uint8_t *d = staged ? (s_out + (pos - stage_origin)) : (out_data + pos);
+        for (int64_t c = 0; c < len[k]; c += 8) {
+          const uint64_t w = ld_bits64(data, (src[k] + c) << 3, (src[k] + len[k]) << 3);
+          const int nb = (int)((len[k] - c) < 8 ? (len[k] - c) : 8);
+#pragma unroll
+          for (int bidx = 0; bidx < 8; ++bidx)
+            if (bidx < nb) d[c + bidx] = (uint8_t)(w >> (8 * bidx));
+        }
+      }
+    }
+    pos = end;
+  }
+  if (err != ~0ull) atomicMin(res + RES_ERR_INDEX, err);
+  if (staged) {  // CTA-uniform
+    __syncthreads();
+    const int64_t nbytes = cta_end - stage_origin;          // staged span, starts 16-B aligned in global memory
+    const int64_t lead = cta_begin - stage_origin;          // bytes of the first chunk owned by the previous CTA
+    uint8_t *g = out_data + stage_origin;
+    const int64_t chunks = (nbytes + 15) >> 4;
+    for (int64_t c = threadIdx.x; c < chunks; c += blockDim.x) {
+      const int64_t b0 = c << 4;
+      if (b0 >= lead && b0 + 16 <= nbytes) {
+        *reinterpret_cast<uint4 *>(g + b0) = *reinterpret_cast<const uint4 *>(s_out + b0);
+      } else {  // partial first / last chunk: only this CTA's bytes
+        for (int64_t x = b0 < lead ? lead : b0; x < b0 + 16 && x < nbytes; ++x) g[x] = s_out[x];
+      }
+    }
+  }
+}
+
+// lengths -> CTA totals -> scan -> offsets (+ byte copy when out_data != NULL and it fits).
 acu_status gather_bytes(acu_ctx *ctx, int32_t ob, const void *offsets, const uint8_t *data, const void *idx, int kind,
                         int64_t m, const uint8_t *out_valid, void *out_offsets, uint8_t *out_data,
                         int64_t out_cap, int64_t *out_len) {
   const int64_t blocks = (m + SCAN_ELEMS - 1) / SCAN_ELEMS;
   void *scratch;
-  ACU_TRY(acu_scratch(ctx, (size_t)(m + blocks + blocks / SCAN_ELEMS + 4096) * 8, &scratch));
-  int64_t *len = static_cast<int64_t *>(scratch);
-  const int grid = acu_grid(ctx, (m + 255) / 256, 8);
-  ACU_LAUNCH(ctx, k_lengths, grid, 256, 0, offsets, (int)ob, idx, kind, m, out_valid, len);
-  ACU_TRY(scan_inclusive(ctx, len, m, len + m));
+  ACU_TRY(acu_scratch(ctx, (size_t)(2 * blocks + blocks / SCAN_ELEMS + 4096) * 8, &scratch));
+  int64_t *block_tot = static_cast<int64_t *>(scratch);
+  ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_block_totals, (unsigned)blocks, 1024, 0, offsets, (int)ob, idx, kind, m, out_valid, block_tot);
+  ACU_TRY(scan_inclusive(ctx, block_tot, blocks, block_tot + blocks));
   ACU_TRY(acu_res_reset(ctx));
-  const int64_t limit = ob == 4 ? (int64_t)INT32_MAX : INT64_MAX;
-  ACU_LAUNCH(ctx, k_write_offsets, grid, 256, 0, len, m, out_offsets, (int)ob, limit, ctx->d_res);
-  ACU_CUDA(ctx, cudaMemcpyAsync(ctx->d_res + RES_AUX0, len + (m - 1), 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  ACU_CUDA(ctx, cudaMemcpyAsync(ctx->d_res + RES_AUX0, block_tot + (blocks - 1), 8, cudaMemcpyDeviceToDevice, ctx->stream));
   ACU_TRY(acu_res_fetch(ctx));
-  if (ctx->h_res[RES_ERR_INDEX] != ~0ull) {
-    const int64_t j = (int64_t)ctx->h_res[RES_ERR_INDEX];
-    int64_t cap = 0;
-    ACU_CUDA(ctx, cudaMemcpyAsync(&cap, len + j, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return acu_fail(ctx, ACU_ERR_OFFSET_OVERFLOW, j, 0, 0, (uint64_t)cap, "%lld", (long long)cap);
-  }
   *out_len = (int64_t)ctx->h_res[RES_AUX0];
-  if (out_data && *out_len > 0) {
-    if (*out_len > out_cap)
-      return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, (uint64_t)*out_len,
-                      "output data capacity %lld < required %lld", (long long)out_cap, (long long)*out_len);
-    ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_copy_bytes, grid, 256, 0, offsets, (int)ob, data, idx, kind, m, len, out_data);
-    ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const int64_t limit = ob == 4 ? (int64_t)INT32_MAX : INT64_MAX;
+  uint8_t *copy_to = (out_data && *out_len <= out_cap) ? out_data : nullptr;
+  if (out_data && !copy_to && *out_len <= limit)
+    return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, (uint64_t)*out_len,
+                    "output data capacity %lld < required %lld", (long long)out_cap, (long long)*out_len);
+  ACU_TRY(acu_res_reset(ctx));
+  const int stage_cap = 64 * 1024;
+  ACU_CUDA(ctx, cudaFuncSetAttribute(k_bytes_offsets_copy, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_cap));
+  ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_offsets_copy, (unsigned)blocks, 1024, stage_cap, offsets, (int)ob, data, idx, kind, m, out_valid,
+                   block_tot, (int64_t)0, out_offsets, *out_len <= limit ? copy_to : nullptr, limit, (int64_t)-1, ctx->d_res, stage_cap);
+  ACU_TRY(acu_res_fetch(ctx));
+  if (ctx->h_res[RES_ERR_INDEX] != ~0ull) {  // T::Offset::from_usize(capacity) failed (take.rs:520-523)
+    const int64_t j = (int64_t)ctx->h_res[RES_ERR_INDEX];
+    ACU_LAUNCH(ctx, k_bytes_offsets_copy, 1, 1024, 0, offsets, (int)ob, data, idx, kind, m, out_valid, block_tot, j / SCAN_ELEMS,
+               out_offsets, static_cast<uint8_t *>(nullptr), INT64_MAX, j, ctx->d_res, 0);
+    ACU_TRY(acu_res_fetch(ctx));
+    const long long cap = (long long)ctx->h_res[RES_AUX1];
+    return acu_fail(ctx, ACU_ERR_OFFSET_OVERFLOW, j, 0, 0, (uint64_t)cap, "%lld", cap);
   }
   return ACU_OK;
 }

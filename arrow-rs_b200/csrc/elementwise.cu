@@ -522,6 +522,81 @@ __global__ void __launch_bounds__(256) k_cmp(const CmpParams<T> p) {
   if (p.out_valid && lane == 0 && valid_cnt) atomicAdd(p.res + RES_COUNT, (unsigned long long)valid_cnt);
 }
 
+// Streaming variant for 16-B aligned operands: a warp owns 2048-row super-groups = 32 result
+// words. Every lane reads 128-bit vectors (EPL elements), 4 vector pairs in flight; a lane's
+// EPL result bits sit at bit position lane*EPL of the load's bit string, so each 32-bit half
+// of a result word is ONE warp OR-reduction (redux.sync) of the shifted groups. Lane l ends up
+// owning result word l and validity word l: one coalesced 256-B store each per super-group.
+// The ragged tail (< 2048 rows) is finished by k_cmp on offset pointers.
+template <class T, bool LT>
+__global__ void __launch_bounds__(256, 4) k_cmp_v2(const CmpParams<T> p, const int64_t sgroups) {
+  constexpr int EPL = 16 / sizeof(T);
+  constexpr int RPL = 32 * EPL;          // rows per warp-wide vector load
+  constexpr int HPL = RPL / 32;          // 32-bit result halves per load (= EPL)
+  constexpr int LOADS = 2048 / RPL;      // vector loads per super-group (32 / 16 / 8 / 4)
+  constexpr int U = LOADS < 4 ? LOADS : 4;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n = p.n;
+  T sa = T(), sb = T();
+  if (p.a_scalar) sa = __ldg(p.a);
+  if (p.b_scalar) sb = __ldg(p.b);
+  unsigned valid_cnt = 0;
+  const int grp_shift = (lane * EPL) & 31;   // where this lane's EPL bits land inside their 32-bit half
+  const int grp_half = (lane * EPL) >> 5;    // which half of the load's bit string they belong to
+  for (int64_t sg = warp; sg < sgroups; sg += nwarps) {
+    const int64_t sbase = sg << 11;
+    uint64_t lw = ~0ull, rw = ~0ull;  // lane-owned validity words
+    if (p.a_null_scalar) lw = 0;
+    if (p.b_null_scalar) rw = 0;
+    const int64_t wrow = sbase + lane * 64;
+    if (p.av) lw &= ld_bits64(p.av, p.aoff + wrow, p.aoff + n);
+    if (p.bv) rw &= ld_bits64(p.bv, p.boff + wrow, p.boff + n);
+    uint32_t my_lo = 0, my_hi = 0;    // lane-owned result word
+#pragma unroll 1
+    for (int l0 = 0; l0 < LOADS; l0 += U) {
+      Pack<T, EPL> va[U], vb[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i0 = sbase + (int64_t)(l0 + u) * RPL + lane * EPL;
+        if (!p.a_scalar) va[u] = pack_load<T, EPL>(p.a + i0);
+        if (!p.b_scalar) vb[u] = pack_load<T, EPL>(p.b + i0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        uint32_t x = 0;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          const T l = p.a_scalar ? sa : va[u].v[e];
+          const T r = p.b_scalar ? sb : vb[u].v[e];
+          x |= (uint32_t)(LT ? pred_lt(l, r) : pred_eq(l, r)) << e;
+        }
+        x <<= grp_shift;
+#pragma unroll
+        for (int hh = 0; hh < HPL; ++hh) {
+          const uint32_t half = __reduce_or_sync(ACU_FULL_MASK, grp_half == hh ? x : 0u);
+          const int widx = ((l0 + u) * HPL + hh) >> 1;  // result word inside the super-group
+          if (lane == widx) { if (hh & 1) my_hi = half; else my_lo = half; }
+        }
+      }
+    }
+    uint64_t v = (uint64_t)my_lo | ((uint64_t)my_hi << 32);
+    if (p.neg) v = ~v;
+    if (p.fold == FOLD_DISTINCT) v = (lw ^ rw) | (lw & rw & v);
+    else if (p.fold == FOLD_NOT_DISTINCT) v = ~(lw | rw) | (lw & rw & v);
+    p.out_bits[(sbase >> 6) + lane] = v;
+    if (p.out_valid) {
+      p.out_valid[(sbase >> 6) + lane] = lw & rw;
+      valid_cnt += __popcll(lw & rw);
+    }
+  }
+  if (p.out_valid) {
+    valid_cnt = warp_sum(valid_cnt);
+    if (lane == 0 && valid_cnt) atomicAdd(p.res + RES_COUNT, (unsigned long long)valid_cnt);
+  }
+}
+
 template <class T>
 acu_status cmp_typed(acu_ctx *ctx, acu_cmp_op op, const acu_array *l, const acu_array *r, acu_array_out *out) {
   const bool ls = l->is_scalar != 0, rs = r->is_scalar != 0;
@@ -565,11 +640,30 @@ acu_status cmp_typed(acu_ctx *ctx, acu_cmp_op op, const acu_array *l, const acu_
   if (yn) { if (ys && !(xs && ys)) p.b_null_scalar = 1; else { p.bv = y->validity; p.boff = y->validity_offset; } }
   if (!fold && (xn || yn)) p.out_valid = reinterpret_cast<uint64_t *>(out->validity);
   ACU_TRY(acu_res_reset(ctx));
-  const int64_t strips = (len + 63) >> 6;
-  const int64_t blocks = (strips + 31) / 32;
   const bool lt = !(op == ACU_EQ || op == ACU_NEQ || fold);
-  if (lt) ACU_LAUNCH_TIMED(ctx, ACU_K_CMP, (k_cmp<T, true>), acu_wave_grid(ctx, k_cmp<T, true>, 256, 0, blocks), 256, 0, p);
-  else ACU_LAUNCH_TIMED(ctx, ACU_K_CMP, (k_cmp<T, false>), acu_wave_grid(ctx, k_cmp<T, false>, 256, 0, blocks), 256, 0, p);
+  // streaming head over whole 2048-row super-groups when the value pointers are 16-B aligned
+  const bool aligned = (p.a_scalar || (uintptr_t)p.a % 16 == 0) && (p.b_scalar || (uintptr_t)p.b % 16 == 0);
+  const int64_t sgroups = aligned ? len / 2048 : 0;
+  if (sgroups > 0) {
+    const int64_t blocks = (sgroups + 7) / 8;
+    if (lt) ACU_LAUNCH_TIMED(ctx, ACU_K_CMP, (k_cmp_v2<T, true>), acu_wave_grid(ctx, k_cmp_v2<T, true>, 256, 0, blocks), 256, 0, p, sgroups);
+    else ACU_LAUNCH_TIMED(ctx, ACU_K_CMP, (k_cmp_v2<T, false>), acu_wave_grid(ctx, k_cmp_v2<T, false>, 256, 0, blocks), 256, 0, p, sgroups);
+  }
+  const int64_t head = sgroups * 2048;
+  if (head < len) {  // ragged tail (or everything, for unaligned slices)
+    CmpParams<T> q = p;
+    q.n = len - head;
+    if (!q.a_scalar) q.a += head;
+    if (!q.b_scalar) q.b += head;
+    q.aoff += head;
+    q.boff += head;
+    q.out_bits += head >> 6;
+    if (q.out_valid) q.out_valid += head >> 6;
+    const int64_t strips = (q.n + 63) >> 6;
+    const int64_t blocks = (strips + 31) / 32;
+    if (lt) ACU_LAUNCH_TIMED(ctx, ACU_K_CMP, (k_cmp<T, true>), acu_wave_grid(ctx, k_cmp<T, true>, 256, 0, blocks), 256, 0, q);
+    else ACU_LAUNCH_TIMED(ctx, ACU_K_CMP, (k_cmp<T, false>), acu_wave_grid(ctx, k_cmp<T, false>, 256, 0, blocks), 256, 0, q);
+  }
   ACU_TRY(acu_res_fetch(ctx));
   if (p.out_valid) {
     out->has_validity = 1;
@@ -670,6 +764,59 @@ __global__ void __launch_bounds__(256) k_cast(const I *__restrict__ in, O *__res
   if (err != ~0ull) atomicMin(res + RES_ERR_INDEX, err);
 }
 
+// Streaming variant for casts that cannot fail (anything -> float, widening integer casts):
+// 2048-row super-groups, 128-bit input vectors, lane-owned validity words, zero under nulls.
+template <class I, class O> struct cast_infallible {
+  static constexpr bool value = is_fp<O>::value ||
+      (!is_fp<I>::value && ((std::is_signed<I>::value == std::is_signed<O>::value && sizeof(O) >= sizeof(I)) ||
+                            (!std::is_signed<I>::value && std::is_signed<O>::value && sizeof(O) > sizeof(I))));
+};
+template <class O, int EPL> struct alignas((sizeof(O) * EPL >= 16) ? 16 : sizeof(O) * EPL) OutPack { O v[EPL]; };
+
+template <class I, class O>
+__global__ void __launch_bounds__(256, 4) k_cast_v2(const I *__restrict__ in, O *__restrict__ out, const int64_t n,
+                                                    const int64_t sgroups, const uint8_t *__restrict__ iv, const int64_t ioff,
+                                                    uint64_t *__restrict__ out_valid, unsigned long long *__restrict__ res) {
+  constexpr int EPL = 16 / sizeof(I);
+  constexpr int RPL = 32 * EPL;
+  constexpr int LOADS = 2048 / RPL;
+  constexpr int U = LOADS < 4 ? LOADS : 4;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  unsigned valid_cnt = 0;
+  for (int64_t sg = warp; sg < sgroups; sg += nwarps) {
+    const int64_t sbase = sg << 11;
+    uint64_t vw = ~0ull;
+    if (iv) vw = ld_bits64(iv, ioff + sbase + lane * 64, ioff + n);
+    if (out_valid) { out_valid[(sbase >> 6) + lane] = vw; valid_cnt += __popcll(vw); }
+#pragma unroll 1
+    for (int l0 = 0; l0 < LOADS; l0 += U) {
+      Pack<I, EPL> v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = pack_load<I, EPL>(in + sbase + (int64_t)(l0 + u) * RPL + lane * EPL);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int pos = (l0 + u) * RPL + lane * EPL;
+        const uint64_t w = __shfl_sync(ACU_FULL_MASK, vw, pos >> 6);
+        const uint32_t bits = (uint32_t)(w >> (pos & 63));
+        OutPack<O, EPL> o;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          O x = O();
+          if ((bits >> e) & 1u) num_cast<I, O>(v[u].v[e], x);  // unary_opt / try_unary: valid slots only, zero elsewhere
+          o.v[e] = x;
+        }
+        *reinterpret_cast<OutPack<O, EPL> *>(out + sbase + pos) = o;
+      }
+    }
+  }
+  if (out_valid) {
+    valid_cnt = warp_sum(valid_cnt);
+    if (lane == 0 && valid_cnt) atomicAdd(res + RES_COUNT, (unsigned long long)valid_cnt);
+  }
+}
+
 template <class I, class O>
 acu_status cast_typed(acu_ctx *ctx, acu_dtype to, int32_t safe, const acu_array *a, acu_array_out *out) {
   const int64_t len = a->len;
@@ -680,9 +827,22 @@ acu_status cast_typed(acu_ctx *ctx, acu_dtype to, int32_t safe, const acu_array 
   if (len == 0) return ACU_OK;
   uint64_t *ov = out->has_validity ? reinterpret_cast<uint64_t *>(out->validity) : nullptr;
   ACU_TRY(acu_res_reset(ctx));
-  const int64_t strips = (len + 63) >> 6;
-  ACU_LAUNCH_TIMED(ctx, ACU_K_CAST, (k_cast<I, O>), acu_wave_grid(ctx, k_cast<I, O>, 256, 0, (strips + 31) / 32), 256, 0, static_cast<const I *>(a->values),
-             static_cast<O *>(out->values), len, a->validity, a->validity_offset, ov, safe, ctx->d_res);
+  int64_t head = 0;
+  if constexpr (cast_infallible<I, O>::value) {
+    if ((uintptr_t)a->values % 16 == 0 && (uintptr_t)out->values % 16 == 0 && len >= 2048) {
+      const int64_t sgroups = len / 2048;
+      head = sgroups * 2048;
+      ACU_LAUNCH_TIMED(ctx, ACU_K_CAST, (k_cast_v2<I, O>), acu_wave_grid(ctx, k_cast_v2<I, O>, 256, 0, (sgroups + 7) / 8), 256, 0,
+                       static_cast<const I *>(a->values), static_cast<O *>(out->values), len, sgroups, a->validity,
+                       a->validity_offset, ov, ctx->d_res);
+    }
+  }
+  if (head < len) {
+    const int64_t strips = (len - head + 63) >> 6;
+    ACU_LAUNCH_TIMED(ctx, ACU_K_CAST, (k_cast<I, O>), acu_wave_grid(ctx, k_cast<I, O>, 256, 0, (strips + 31) / 32), 256, 0,
+                     static_cast<const I *>(a->values) + head, static_cast<O *>(out->values) + head, len - head, a->validity,
+                     a->validity_offset + head, ov ? ov + (head >> 6) : nullptr, safe, ctx->d_res);
+  }
   ACU_TRY(acu_res_fetch(ctx));
   if (!safe && ctx->h_res[RES_ERR_INDEX] != ~0ull) {
     const int64_t idx = (int64_t)ctx->h_res[RES_ERR_INDEX];

@@ -9,9 +9,6 @@ import sys
 
 import numpy as np
 import pytest
-import torch
-import torch.distributed as dist
-import torch.multiprocessing as mp
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
@@ -48,6 +45,8 @@ def _shard_step(orc, acu, abi, vals, fvals, valid, pred, lo, hi):
 
 
 def _worker(rank, world, port, n, out_q):
+    import torch
+    import torch.distributed as dist
     sys.path.insert(0, os.path.join(REPO, "arrow-rs_b200"))
     sys.path.insert(0, HERE)
     import acu
@@ -81,6 +80,7 @@ def _worker(rank, world, port, n, out_q):
 
 @pytest.mark.parametrize("n", [100_003, 4096])
 def test_two_rank_sharded_step_matches_single_process(n):
+    import torch.multiprocessing as mp  # imported lazily: collecting the GPU tests must not pay for `import torch`
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
