@@ -183,135 +183,200 @@ int index_kind(acu_dtype t) {
 }
 
 // ---- fused lengths / scan / offsets / copy -------------------------------------------------
-// CTA = 1024 threads x 4 consecutive rows = 4096 rows (SCAN_ELEMS).
-__device__ __forceinline__ int64_t row_len(const void *offs, int ob, const void *idx, int kind, const uint8_t *out_valid,
-                                           int64_t j, int64_t m, int64_t *src_begin) {
-  if (j >= m || (out_valid && !ld_bit(out_valid, j))) { *src_begin = 0; return 0; }
-  const int64_t i = (int64_t)ld_index(idx, kind, j);
-  const int64_t s = ld_off(offs, ob, i);
+// CTA = 1024 threads x 4 rounds of 1024 consecutive rows (SCAN_ELEMS = 4096 rows): lane l <-> row
+// l of a warp's 32-row group, so index loads, offset stores and the warp's 32 validity bits (one
+// aligned u32) are all coalesced. FAST = i32 offsets + 32-bit indices: all per-row arithmetic in
+// 32 bits.
+struct BytesArgs {
+  const void *offs;        // source offsets (i32 or i64)
+  const uint8_t *data;     // source value bytes
+  const void *idx;         // source row of each output row
+  int kind;                // index kind (see ld_index)
+  int ob;                  // offset width
+  int64_t m;               // output rows
+  int64_t n_src;           // source rows (out-of-bounds detection)
+  const uint32_t *out_valid;  // output validity (bit offset 0) or NULL: null slots get zero length
+  int detect_oob;          // report an out-of-bounds index at a valid slot through res[RES_ERR_INDEX]
+};
+
+template <bool FAST>
+__device__ __forceinline__ uint64_t row_span(const BytesArgs &a, int64_t j, bool valid, int64_t *src_begin, bool *oob) {
+  *src_begin = 0;
+  *oob = false;
+  if (j >= a.m || !valid) return 0;
+  uint64_t i;
+  if (FAST) i = __ldg(static_cast<const uint32_t *>(a.idx) + j);
+  else i = ld_index(a.idx, a.kind, j);
+  if (i >= (uint64_t)a.n_src) { *oob = true; return 0; }
+  if (FAST) {
+    const int32_t s = __ldg(static_cast<const int32_t *>(a.offs) + i), e = __ldg(static_cast<const int32_t *>(a.offs) + i + 1);
+    *src_begin = s;
+    return (uint32_t)(e - s);
+  }
+  const int64_t s = ld_off(a.offs, a.ob, (int64_t)i);
   *src_begin = s;
-  return ld_off(offs, ob, i + 1) - s;
+  return (uint64_t)(ld_off(a.offs, a.ob, (int64_t)i + 1) - s);
 }
 
-// pass 1: total value bytes of each CTA's 4096 rows
-__global__ void __launch_bounds__(1024) k_bytes_block_totals(const void *offs, int ob, const void *idx, int kind, int64_t m,
-                                                             const uint8_t *out_valid, int64_t *__restrict__ block_tot) {
-  __shared__ int64_t warp_tot[32];
-  const int64_t base = (int64_t)blockIdx.x * SCAN_ELEMS + (int64_t)threadIdx.x * 4;
-  int64_t sum = 0, sb;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) sum += row_len(offs, ob, idx, kind, out_valid, base + k, m, &sb);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(ACU_FULL_MASK, sum, o);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) warp_tot[wid] = sum;
-  __syncthreads();
-  if (wid == 0) {
-    int64_t t = warp_tot[lane];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(ACU_FULL_MASK, t, o);
-    if (lane == 0) block_tot[blockIdx.x] = t;
-  }
+__device__ __forceinline__ bool slot_valid(const BytesArgs &a, int64_t j, int lane) {
+  if (!a.out_valid) return true;
+  if (j - lane >= a.m) return false;
+  return (__ldg(a.out_valid + ((j - lane) >> 5)) >> lane) & 1u;  // j - lane is a multiple of 32
 }
 
-// pass 2 (after the inclusive scan of the CTA totals): offsets + byte copy.
-// Source bytes are fetched 8 at a time with two aligned loads + funnel shift (ld_bits64 on a
-// byte position), so the copy loop carries no dependent byte loads; a thread's 4 rows are
-// adjacent in the destination.
-__global__ void __launch_bounds__(1024) k_bytes_offsets_copy(const void *offs, int ob, const uint8_t *__restrict__ data,
-                                                             const void *idx, int kind, int64_t m, const uint8_t *out_valid,
-                                                             const int64_t *__restrict__ block_incl, int64_t first_block,
-                                                             void *out_offs, uint8_t *__restrict__ out_data, int64_t limit,
-                                                             int64_t probe_row, unsigned long long *res, int stage_cap) {
-  __shared__ int64_t warp_tot[32];
-  const int64_t blk = first_block + blockIdx.x;
-  const int64_t base = blk * SCAN_ELEMS + (int64_t)threadIdx.x * 4;
-  int64_t len[4], src[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) len[k] = row_len(offs, ob, idx, kind, out_valid, base + k, m, &src[k]);
-  const int64_t mine = len[0] + len[1] + len[2] + len[3];
-  int64_t incl = mine;
+// pass 1: total value bytes of each CTA's 4096 rows (+ out-of-bounds detection)
+template <bool FAST>
+__global__ void __launch_bounds__(1024) k_bytes_block_totals(const BytesArgs a, int64_t *__restrict__ block_tot,
+                                                             unsigned long long *__restrict__ res) {
+  __shared__ uint64_t warp_tot[32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int64_t y = __shfl_up_sync(ACU_FULL_MASK, incl, o);
-    if (lane >= o) incl += y;
-  }
-  if (lane == 31) warp_tot[wid] = incl;
-  __syncthreads();
-  if (wid == 0) {
-    int64_t w = warp_tot[lane], wi = w;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int64_t y = __shfl_up_sync(ACU_FULL_MASK, wi, o);
-      if (lane >= o) wi += y;
-    }
-    warp_tot[lane] = wi - w;
-  }
-  __syncthreads();
-  extern __shared__ __align__(16) uint8_t s_out[];
-  const int64_t cta_begin = blk ? block_incl[blk - 1] : 0, cta_end = block_incl[blk];
-  const int64_t stage_origin = cta_begin - (int64_t)((uintptr_t)(out_data + cta_begin) & 15);  // global byte that maps to s_out[0]
-  const bool staged = out_data != nullptr && probe_row < 0 && (cta_end - stage_origin) <= (int64_t)stage_cap;
-  int64_t pos = cta_begin + warp_tot[wid] + incl - mine;  // first output byte of this thread
+  const int64_t base = (int64_t)blockIdx.x * SCAN_ELEMS + threadIdx.x;
+  uint64_t sum = 0;
   unsigned long long err = ~0ull;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int64_t j = base + k;
-    if (j >= m) break;
-    const int64_t end = pos + len[k];
-    if (end > limit && (unsigned long long)j < err) err = (unsigned long long)j;
-    if (j == probe_row) res[RES_AUX1] = (unsigned long long)end;
-    if (probe_row < 0) {
-      if (ob == 4) static_cast<int32_t *>(out_offs)[j + 1] = (int32_t)end;
-      else static_cast<int64_t *>(out_offs)[j + 1] = end;
-      if (j == 0) { if (ob == 4) static_cast<int32_t *>(out_offs)[0] = 0; else static_cast<int64_t *>(out_offs)[0] = 0; }
-      if (out_data) {
-        // staged: the CTA's output bytes are contiguous [cta_begin, cta_end); build them in shared memory laid out
-        // relative to the 16-B aligned global address so that the copy-out is whole 128-bit stores.
-        uint8_t *d = staged ? (s_out + (pos - stage_origin)) : (out_data + pos);
-        for (int64_t c = 0; c < len[k]; c += 8) {
-          const uint64_t w = ld_bits64(data, (src[k] + c) << 3, (src[k] + len[k]) << 3);
-          const int nb = (int)((len[k] - c) < 8 ? (len[k] - c) : 8);
+    const int64_t j = base + k * 1024;
+    int64_t sb;
+    bool oob;
+    sum += row_span<FAST>(a, j, slot_valid(a, j, lane), &sb, &oob);
+    if (oob && a.detect_oob && (unsigned long long)j < err) err = (unsigned long long)j;
+  }
 #pragma unroll
-          for (int bidx = 0; bidx < 8; ++bidx)
-            if (bidx < nb) d[c + bidx] = (uint8_t)(w >> (8 * bidx));
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(ACU_FULL_MASK, sum, o);
+  if (lane == 0) warp_tot[wid] = sum;
+  __syncthreads();
+  if (wid == 0) {
+    uint64_t t = warp_tot[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(ACU_FULL_MASK, t, o);
+    if (lane == 0) block_tot[blockIdx.x] = (int64_t)t;
+  }
+  if (err != ~0ull) atomicMin(res + RES_ERR_INDEX, err);
+}
+
+// pass 2 (after the inclusive scan of the CTA totals): offsets + byte copy. Source bytes are
+// fetched 8 at a time with two aligned loads + funnel shift (ld_bits64 on a byte position): no
+// dependent byte loads. The CTA's output bytes [cta_begin, cta_end) are built in shared memory
+// laid out relative to the 16-B aligned global address and written back as whole 128-bit stores
+// (STAGED); CTAs whose output does not fit the staging buffer store bytes directly.
+template <bool FAST, bool STAGED>
+__device__ __forceinline__ void copy_row(uint8_t *__restrict__ dst, const uint8_t *__restrict__ data, int64_t src, uint64_t len) {
+  for (uint64_t c = 0; c < len; c += 8) {
+    const uint64_t w = ld_bits64(data, (src + (int64_t)c) << 3, (src + (int64_t)len) << 3);
+    const int nb = (int)((len - c) < 8 ? (len - c) : 8);
+#pragma unroll
+    for (int bidx = 0; bidx < 8; ++bidx)
+      if (bidx < nb) dst[c + bidx] = (uint8_t)(w >> (8 * bidx));
+  }
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(1024) k_bytes_offsets_copy(const BytesArgs a, const int64_t *__restrict__ block_incl,
+                                                             int64_t first_block, void *out_offs, uint8_t *__restrict__ out_data,
+                                                             int64_t limit, int64_t probe_row, unsigned long long *res,
+                                                             int stage_cap) {
+  extern __shared__ __align__(16) uint8_t s_out[];
+  __shared__ uint64_t warp_tot[33];
+  const int64_t blk = first_block + blockIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t cta_begin = blk ? block_incl[blk - 1] : 0, cta_end = block_incl[blk];
+  const int64_t stage_origin = cta_begin - (int64_t)((uintptr_t)(out_data + cta_begin) & 15);  // global byte that maps to s_out[0]
+  const bool staged = out_data != nullptr && probe_row < 0 && (cta_end - stage_origin) <= (int64_t)stage_cap;
+  uint64_t running = 0;  // bytes of the previous rounds, relative to cta_begin
+  unsigned long long err = ~0ull;
+  for (int k = 0; k < 4; ++k) {
+    const int64_t j = blk * SCAN_ELEMS + k * 1024 + threadIdx.x;
+    int64_t src;
+    bool oob;
+    const uint64_t len = row_span<FAST>(a, j, slot_valid(a, j, lane), &src, &oob);
+    uint64_t incl = len;
+    if (FAST) {  // a CTA's 4096 rows of an i32-offset array never exceed 2^31 bytes... per row; sums fit 44 bits: scan in 64 but shuffle cheaply
+      uint32_t lo = (uint32_t)len;  // FAST lengths fit 32 bits; a round's total (1024 rows) may not -> widen after the warp scan
+      uint64_t acc = lo;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t y = __shfl_up_sync(ACU_FULL_MASK, acc, o);
+        if (lane >= o) acc += y;
+      }
+      incl = acc;
+    } else {
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t y = __shfl_up_sync(ACU_FULL_MASK, incl, o);
+        if (lane >= o) incl += y;
+      }
+    }
+    __syncthreads();  // warp_tot of the previous round has been consumed
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      uint64_t w = warp_tot[lane], wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t y = __shfl_up_sync(ACU_FULL_MASK, wi, o);
+        if (lane >= o) wi += y;
+      }
+      warp_tot[lane] = wi - w;
+      if (lane == 31) warp_tot[32] = wi;  // round total
+    }
+    __syncthreads();
+    const uint64_t rel = running + warp_tot[wid] + incl - len;  // first output byte of this row, relative to cta_begin
+    running += warp_tot[32];
+    if (j < a.m) {
+      const int64_t end = cta_begin + (int64_t)(rel + len);
+      if (end > limit && (unsigned long long)j < err) err = (unsigned long long)j;
+      if (j == probe_row) res[RES_AUX1] = (unsigned long long)end;
+      if (probe_row < 0) {
+        if (a.ob == 4) static_cast<int32_t *>(out_offs)[j + 1] = (int32_t)end;
+        else static_cast<int64_t *>(out_offs)[j + 1] = end;
+        if (j == 0) { if (a.ob == 4) static_cast<int32_t *>(out_offs)[0] = 0; else static_cast<int64_t *>(out_offs)[0] = 0; }
+        if (out_data && len) {
+          if (staged) copy_row<FAST, true>(s_out + (uint32_t)(cta_begin - stage_origin + (int64_t)rel), a.data, src, len);
+          else copy_row<FAST, false>(out_data + cta_begin + (int64_t)rel, a.data, src, len);
         }
       }
     }
-    pos = end;
   }
   if (err != ~0ull) atomicMin(res + RES_ERR_INDEX, err);
   if (staged) {  // CTA-uniform
     __syncthreads();
-    const int64_t nbytes = cta_end - stage_origin;          // staged span, starts 16-B aligned in global memory
-    const int64_t lead = cta_begin - stage_origin;          // bytes of the first chunk owned by the previous CTA
+    const uint32_t nbytes = (uint32_t)(cta_end - stage_origin);  // staged span, starts 16-B aligned in global memory
+    const uint32_t lead = (uint32_t)(cta_begin - stage_origin);  // bytes of the first chunk owned by the previous CTA
     uint8_t *g = out_data + stage_origin;
-    const int64_t chunks = (nbytes + 15) >> 4;
-    for (int64_t c = threadIdx.x; c < chunks; c += blockDim.x) {
-      const int64_t b0 = c << 4;
+    const uint32_t chunks = (nbytes + 15) >> 4;
+    for (uint32_t c = threadIdx.x; c < chunks; c += 1024) {
+      const uint32_t b0 = c << 4;
       if (b0 >= lead && b0 + 16 <= nbytes) {
         *reinterpret_cast<uint4 *>(g + b0) = *reinterpret_cast<const uint4 *>(s_out + b0);
       } else {  // partial first / last chunk: only this CTA's bytes
-        for (int64_t x = b0 < lead ? lead : b0; x < b0 + 16 && x < nbytes; ++x) g[x] = s_out[x];
+        for (uint32_t x = b0 < lead ? lead : b0; x < b0 + 16 && x < nbytes; ++x) g[x] = s_out[x];
       }
     }
   }
 }
 
 // lengths -> CTA totals -> scan -> offsets (+ byte copy when out_data != NULL and it fits).
+// Returns ACU_ERR_PANIC_OUT_OF_BOUNDS-style detection through *oob_row (>= 0) when detect_oob.
 acu_status gather_bytes(acu_ctx *ctx, int32_t ob, const void *offsets, const uint8_t *data, const void *idx, int kind,
-                        int64_t m, const uint8_t *out_valid, void *out_offsets, uint8_t *out_data,
-                        int64_t out_cap, int64_t *out_len) {
+                        int64_t m, int64_t n_src, const uint8_t *out_valid, bool detect_oob, void *out_offsets,
+                        uint8_t *out_data, int64_t out_cap, int64_t *out_len, int64_t *oob_row) {
+  if (oob_row) *oob_row = -1;
   const int64_t blocks = (m + SCAN_ELEMS - 1) / SCAN_ELEMS;
   void *scratch;
   ACU_TRY(acu_scratch(ctx, (size_t)(2 * blocks + blocks / SCAN_ELEMS + 4096) * 8, &scratch));
   int64_t *block_tot = static_cast<int64_t *>(scratch);
-  ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_block_totals, (unsigned)blocks, 1024, 0, offsets, (int)ob, idx, kind, m, out_valid, block_tot);
-  ACU_TRY(scan_inclusive(ctx, block_tot, blocks, block_tot + blocks));
+  BytesArgs a{offsets, data, idx, kind, (int)ob, m, n_src, reinterpret_cast<const uint32_t *>(out_valid), detect_oob ? 1 : 0};
+  const bool fast = ob == 4 && kind == 4 && ((uintptr_t)idx % 4 == 0);
   ACU_TRY(acu_res_reset(ctx));
+  if (fast) ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_block_totals<true>, (unsigned)blocks, 1024, 0, a, block_tot, ctx->d_res);
+  else ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_block_totals<false>, (unsigned)blocks, 1024, 0, a, block_tot, ctx->d_res);
+  ACU_TRY(scan_inclusive(ctx, block_tot, blocks, block_tot + blocks));
   ACU_CUDA(ctx, cudaMemcpyAsync(ctx->d_res + RES_AUX0, block_tot + (blocks - 1), 8, cudaMemcpyDeviceToDevice, ctx->stream));
   ACU_TRY(acu_res_fetch(ctx));
+  if (detect_oob && ctx->h_res[RES_ERR_INDEX] != ~0ull) {
+    if (oob_row) *oob_row = (int64_t)ctx->h_res[RES_ERR_INDEX];
+    return ACU_OK;
+  }
   *out_len = (int64_t)ctx->h_res[RES_AUX0];
   const int64_t limit = ob == 4 ? (int64_t)INT32_MAX : INT64_MAX;
   uint8_t *copy_to = (out_data && *out_len <= out_cap) ? out_data : nullptr;
@@ -320,14 +385,22 @@ acu_status gather_bytes(acu_ctx *ctx, int32_t ob, const void *offsets, const uin
                     "output data capacity %lld < required %lld", (long long)out_cap, (long long)*out_len);
   ACU_TRY(acu_res_reset(ctx));
   const int stage_cap = 64 * 1024;
-  ACU_CUDA(ctx, cudaFuncSetAttribute(k_bytes_offsets_copy, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_cap));
-  ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_offsets_copy, (unsigned)blocks, 1024, stage_cap, offsets, (int)ob, data, idx, kind, m, out_valid,
-                   block_tot, (int64_t)0, out_offsets, *out_len <= limit ? copy_to : nullptr, limit, (int64_t)-1, ctx->d_res, stage_cap);
+  a.detect_oob = 0;
+  uint8_t *dst = *out_len <= limit ? copy_to : nullptr;
+  if (fast) {
+    ACU_CUDA(ctx, cudaFuncSetAttribute(k_bytes_offsets_copy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_cap));
+    ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_offsets_copy<true>, (unsigned)blocks, 1024, stage_cap, a, block_tot, (int64_t)0, out_offsets,
+                     dst, limit, (int64_t)-1, ctx->d_res, stage_cap);
+  } else {
+    ACU_CUDA(ctx, cudaFuncSetAttribute(k_bytes_offsets_copy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_cap));
+    ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_offsets_copy<false>, (unsigned)blocks, 1024, stage_cap, a, block_tot, (int64_t)0, out_offsets,
+                     dst, limit, (int64_t)-1, ctx->d_res, stage_cap);
+  }
   ACU_TRY(acu_res_fetch(ctx));
   if (ctx->h_res[RES_ERR_INDEX] != ~0ull) {  // T::Offset::from_usize(capacity) failed (take.rs:520-523)
     const int64_t j = (int64_t)ctx->h_res[RES_ERR_INDEX];
-    ACU_LAUNCH(ctx, k_bytes_offsets_copy, 1, 1024, 0, offsets, (int)ob, data, idx, kind, m, out_valid, block_tot, j / SCAN_ELEMS,
-               out_offsets, static_cast<uint8_t *>(nullptr), INT64_MAX, j, ctx->d_res, 0);
+    ACU_LAUNCH(ctx, k_bytes_offsets_copy<false>, 1, 1024, 0, a, block_tot, j / SCAN_ELEMS, out_offsets, static_cast<uint8_t *>(nullptr),
+               INT64_MAX, j, ctx->d_res, 0);
     ACU_TRY(acu_res_fetch(ctx));
     const long long cap = (long long)ctx->h_res[RES_AUX1];
     return acu_fail(ctx, ACU_ERR_OFFSET_OVERFLOW, j, 0, 0, (uint64_t)cap, "%lld", cap);
@@ -372,13 +445,50 @@ extern "C" acu_status acu_take_bytes(acu_ctx *ctx, int32_t offset_bytes, const v
   *out_data_len = 0;
   if (offset_bytes != 4 && offset_bytes != 8)
     return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "offset width must be 4 or 8");
+  const int64_t m = indices->len;
+  acu_status st;
+  const int64_t vnc = acu_resolve_null_count(ctx, nulls_of, &st);
+  ACU_TRY(st);
+  const int kind = index_kind(index_dtype);
+  if (!check_bounds && kind >= 0 && !(nulls_of->validity && vnc > 0)) {
+    // values without nulls: take_nulls = indices.nulls().cloned() (take.rs:429) is a bitmap copy, and the
+    // out-of-bounds check rides in the first bytes pass — no separate gather pass.
+    out_nulls->len = m;
+    out_nulls->has_validity = 0;
+    out_nulls->null_count = 0;
+    if (m == 0) return zero_first_offset(ctx, out_offsets, offset_bytes);
+    if (indices->validity) {
+      ACU_TRY(acu_res_reset(ctx));
+      ACU_TRY(acu_bitmap_and_launch(ctx, indices->validity, indices->validity_offset, nullptr, 0, m,
+                                    reinterpret_cast<uint64_t *>(out_nulls->validity), true));
+      ACU_TRY(acu_res_fetch(ctx));
+      out_nulls->has_validity = 1;
+      out_nulls->null_count = m - (int64_t)ctx->h_res[RES_COUNT];
+    }
+    const uint8_t *ov = (out_nulls->has_validity && out_nulls->null_count > 0) ? out_nulls->validity : nullptr;
+    int64_t oob_row = -1;
+    ACU_TRY(gather_bytes(ctx, offset_bytes, offsets, data, indices->values, kind, m, nulls_of->len, ov, true, out_offsets, out_data,
+                         out_data_capacity, out_data_len, &oob_row));
+    if (oob_row >= 0) {  // the reference panics on a bounds-checked slice index (take.rs:517)
+      uint64_t raw = 0;
+      const int sz = acu_dtype_size(index_dtype);
+      ACU_CUDA(ctx, cudaMemcpyAsync(&raw, static_cast<const uint8_t *>(indices->values) + (size_t)oob_row * sz, sz, cudaMemcpyDeviceToHost, ctx->stream));
+      ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      uint64_t widened = raw;
+      if (index_dtype == ACU_I8) widened = (uint32_t)(int32_t)(int8_t)raw;
+      else if (index_dtype == ACU_I16) widened = (uint32_t)(int32_t)(int16_t)raw;
+      else if (index_dtype == ACU_I32) widened = (uint32_t)raw;
+      return acu_fail(ctx, ACU_ERR_PANIC_OUT_OF_BOUNDS, oob_row, widened, 0, (uint64_t)nulls_of->len, "Out-of-bounds index %llu",
+                      (unsigned long long)widened);
+    }
+    return ACU_OK;
+  }
   // take_nulls + bounds handling (elem_bytes = 0: no value gather)
   ACU_TRY(acu_take_common(ctx, 0, nulls_of, false, indices, index_dtype, check_bounds, out_nulls));
-  const int64_t m = indices->len;
   if (m == 0) return zero_first_offset(ctx, out_offsets, offset_bytes);
   const uint8_t *ov = (out_nulls->has_validity && out_nulls->null_count > 0) ? out_nulls->validity : nullptr;
-  return gather_bytes(ctx, offset_bytes, offsets, data, indices->values, index_kind(index_dtype), m, ov, out_offsets,
-                      out_data, out_data_capacity, out_data_len);
+  return gather_bytes(ctx, offset_bytes, offsets, data, indices->values, index_kind(index_dtype), m, nulls_of->len, ov, false, out_offsets,
+                      out_data, out_data_capacity, out_data_len, nullptr);
 }
 
 extern "C" acu_status acu_filter_bytes(acu_ctx *ctx, const acu_filter_plan *plan, int32_t offset_bytes,
@@ -419,8 +529,8 @@ extern "C" acu_status acu_filter_bytes(acu_ctx *ctx, const acu_filter_plan *plan
     } else {
       if ((st = acu_filter_nulls_internal(ctx, plan, nulls_of, out_nulls)) != ACU_OK) break;
     }
-    st = gather_bytes(ctx, offset_bytes, offsets, data, idx_mem, 5, count, nullptr, out_offsets, out_data,
-                      out_data_capacity, out_data_len);
+    st = gather_bytes(ctx, offset_bytes, offsets, data, idx_mem, 5, count, nulls_of->len, nullptr, false, out_offsets, out_data,
+                      out_data_capacity, out_data_len, nullptr);
   } while (0);
   acu_status st2 = acu_free(ctx, idx_mem);
   return st != ACU_OK ? st : st2;

@@ -30,6 +30,7 @@ class Bench:
     def __init__(self, ctx, reps):
         self.ctx, self.lib, self.h, self.reps, self.rows = ctx, ctx.lib, ctx.h, reps, []
         self.peak = peak()
+        self.only = None
 
     def arr(self, values, validity, n, nc, voff=0, scalar=0):
         a = abi.Array()
@@ -54,6 +55,8 @@ class Bench:
         return d, c.value
 
     def timed(self, name, classes, alg_bytes, rows, fn, note=""):
+        if self.only and self.only not in name:
+            return
         for _ in range(2):
             fn()
         self.ctx.check(self.lib.acu_kernel_stats_reset(self.h))
@@ -81,10 +84,12 @@ def main():
     ap.add_argument("--rows", type=int, default=1_000_000_000)
     ap.add_argument("--small-rows", type=int, default=100_000_000)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--only", default=None, help="substring of the op names to run")
     args = ap.parse_args()
     n, ns = args.rows, args.small_rows
     with acu.Context(0) as ctx:
         b = Bench(ctx, args.reps)
+        b.only = args.only
         lib, h = ctx.lib, ctx.h
         bb = abi.bitmap_bytes(n)
         # ---------------- config 3: binary add/mul + cmp Float64 1e9, 5 % nulls ----------------
