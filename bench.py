@@ -34,6 +34,25 @@ SEED_VALUES, SEED_B, SEED_VALID_A, SEED_VALID_B, SEED_PRED = 42, 43, 44, 45, 46 
 SELECTIVITY, NULL_DENSITY = 0.10, 0.05
 
 
+def profiled_traffic(rows):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
+    (profiles/rNN_traffic.json, taken at 1e9 rows per GPU); null for other sizes."""
+    if rows != 1_000_000_000:
+        return None
+    best = None
+    pdir = os.path.join(REPO, "profiles")
+    for name in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
+        if name.endswith("_traffic.json"):
+            try:
+                d = json.load(open(os.path.join(pdir, name)))
+                for k, v in d.items():
+                    if k.startswith("k_arith<double"):
+                        best = float(v)
+            except Exception:
+                pass
+    return best
+
+
 def peaks():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -521,7 +540,8 @@ def run_gpu(args):
                    "l2": "inputs >> L2 (126 MB): no flush needed", "input_residency": "HBM"},
         "roofline": {"bound": "hbm", "kernel": "k_arith<double> (Float64 add, fused validity AND + popcount)",
                      "achieved": dom.get("achieved_gbs"), "peak": peak, "unit": "GB/s", "frac": dom.get("frac"),
-                     "traffic": None, "peak_source": peak_src, "per_op": roof_ops},
+                     "traffic": profiled_traffic(n), "traffic_source": "profiles/*_traffic.json (ncu --set full, per launch)",
+                     "algorithmic_bytes": ab["add"], "peak_source": peak_src, "per_op": roof_ops},
         "kernels": kstats,
         "gpu_launches": launches,
         "clocks": clocks,
