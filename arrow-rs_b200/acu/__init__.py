@@ -162,6 +162,18 @@ def host_descriptor(h):
     return d
 
 
+class Utf8Column:
+    """A Utf8 / Binary column on the host: offsets (np.int32 | np.int64, rows + 1), value bytes (np.uint8) and a
+    HostArray carrying only the validity / length (GenericByteArray, arrow-array/src/array/byte_array.rs)."""
+
+    def __init__(self, offsets, data, nulls):
+        self.offsets, self.data, self.nulls = offsets, data, nulls
+
+    @property
+    def length(self):
+        return len(self.offsets) - 1
+
+
 class DeviceArray:
     """A HostArray's buffers uploaded to HBM (DeviceBuffer pair) with the same offsets."""
 
@@ -416,6 +428,140 @@ class Context:
                 self.free(p)
             dn.free()
             dp.free()
+
+    # -- RecordBatch level (filter.rs:225-244, take.rs:1123-1133) ----------------------------
+    # A batch is a list of columns; a column is a HostArray (primitive / boolean) or a
+    # Utf8Column(offsets, data, nulls). Results keep the column order and kinds.
+    def _upload_columns(self, columns):
+        cols = (abi.Column * len(columns))()
+        owned = []
+        for c, col in enumerate(columns):
+            if isinstance(col, Utf8Column):
+                d_off = self.malloc(col.offsets.nbytes + 16)
+                self.h2d(d_off, col.offsets)
+                d_data = self.malloc(col.data.nbytes + 16)
+                if col.data.nbytes:
+                    self.h2d(d_data, col.data)
+                dn = self.upload(col.nulls)
+                owned += [("ptr", d_off), ("ptr", d_data), ("arr", dn)]
+                cols[c].kind, cols[c].width = abi.COL_BYTES, col.offsets.dtype.itemsize
+                cols[c].array = dn.descriptor()
+                cols[c].array.values = d_off
+                cols[c].array.values_offset = 0
+                cols[c].data = d_data
+            else:
+                dv = self.upload(col)
+                owned.append(("arr", dv))
+                cols[c].kind = abi.COL_BOOLEAN if col.dtype == BOOL else abi.COL_PRIMITIVE
+                cols[c].width = 0 if col.dtype == BOOL else col.width()
+                cols[c].array = dv.descriptor()
+        return cols, owned
+
+    def _alloc_column_outs(self, columns, rows, data_caps):
+        outs = (abi.ColumnOut * len(columns))()
+        for c, col in enumerate(columns):
+            if isinstance(col, Utf8Column):
+                outs[c].array.values = self.malloc((rows + 1) * col.offsets.dtype.itemsize + 16)
+                outs[c].array.validity = self.malloc(bitmap_bytes(rows) + 8)
+                outs[c].data = self.malloc(data_caps[c] + 16)
+                outs[c].data_capacity = data_caps[c]
+            else:
+                outs[c].array.values = self.malloc((bitmap_bytes(rows) if col.dtype == BOOL else rows * col.width()) + 16)
+                outs[c].array.validity = self.malloc(bitmap_bytes(rows) + 8)
+        return outs
+
+    def _download_columns(self, columns, outs):
+        res = []
+        for c, col in enumerate(columns):
+            o = outs[c]
+            n = o.array.len
+            validity = self.d2h(o.array.validity, bitmap_bytes(n)) if o.array.has_validity else None
+            nc = o.array.null_count if o.array.has_validity else 0
+            if isinstance(col, Utf8Column):
+                offs = self.d2h(o.array.values, (n + 1) * col.offsets.dtype.itemsize, col.offsets.dtype)
+                data = self.d2h(o.data, o.data_len)
+                res.append(Utf8Column(offs, data, HostArray(U8, np.zeros(0, np.uint8), n, validity, 0, 0, nc)))
+            elif col.dtype == BOOL:
+                res.append(HostArray(BOOL, self.d2h(o.array.values, bitmap_bytes(n)), n, validity, 0, 0, nc))
+            else:
+                res.append(HostArray(col.dtype, self.d2h(o.array.values, n * col.width(), NP_DTYPES[col.dtype]), n, validity, 0, 0, nc))
+        return res
+
+    def _free_columns(self, owned, outs):
+        for kind, x in owned:
+            if kind == "ptr":
+                self.free(x)
+            else:
+                x.free()
+        if outs is not None:
+            for o in outs:
+                for p in (o.array.values, o.array.validity, o.data):
+                    if p:
+                        self.free(p)
+
+    def filter_record_batch(self, columns, predicate):
+        """arrow::compute::filter_record_batch: one plan, every column, one synchronisation."""
+        cols, owned = self._upload_columns(columns)
+        dp = self.upload(predicate)
+        plan = C.c_void_p()
+        outs = None
+        try:
+            pd = dp.descriptor()
+            self.check(self.lib.acu_filter_plan_create(self.h, C.byref(pd), C.byref(plan)))
+            count = self.lib.acu_filter_plan_count(plan)
+            caps = [int(col.data.nbytes) if isinstance(col, Utf8Column) else 0 for col in columns]
+            outs = self._alloc_column_outs(columns, count, caps)
+            self.check(self.lib.acu_filter_record_batch(self.h, plan, len(columns), cols, outs))
+            return self._download_columns(columns, outs)
+        finally:
+            if plan:
+                self.lib.acu_filter_plan_destroy(self.h, plan)
+            self._free_columns(owned, outs)
+            dp.free()
+
+    def take_record_batch(self, columns, indices, check_bounds=False, data_capacity=None):
+        """arrow::compute::take_record_batch / take_arrays."""
+        cols, owned = self._upload_columns(columns)
+        di = self.upload(indices)
+        outs = None
+        try:
+            m = indices.length
+            caps = []
+            for col in columns:
+                if isinstance(col, Utf8Column):
+                    lens = np.diff(col.offsets.astype(np.int64)) if len(col.offsets) > 1 else np.zeros(0, np.int64)
+                    caps.append(int(data_capacity) if data_capacity is not None else int((lens.max() if lens.size else 0) * m))
+                else:
+                    caps.append(0)
+            outs = self._alloc_column_outs(columns, m, caps)
+            idd = di.descriptor()
+            self.check(self.lib.acu_take_record_batch(self.h, len(columns), cols, C.byref(idd), indices.dtype, int(check_bounds), outs))
+            return self._download_columns(columns, outs)
+        finally:
+            self._free_columns(owned, outs)
+            di.free()
+
+    def aggregate_columns(self, ops, columns):
+        """[sum|min|max](column) for several primitive columns with one synchronisation -> [(value|None)]."""
+        n = len(columns)
+        das = [self.upload(c) for c in columns]
+        try:
+            arrs = (abi.Array * n)(*[d.descriptor() for d in das])
+            dts = (C.c_int32 * n)(*[c.dtype for c in columns])
+            opv = (C.c_int32 * n)(*ops)
+            bits, cnts = (C.c_uint64 * n)(), (C.c_int64 * n)()
+            self.check(self.lib.acu_aggregate_columns(self.h, n, dts, opv, arrs, bits, cnts))
+            out = []
+            for i, c in enumerate(columns):
+                if cnts[i] == 0:
+                    out.append(None)
+                else:
+                    raw = np.array([bits[i]], dtype=np.uint64).view(np.uint8)[: abi.DTYPE_SIZE[c.dtype]]
+                    out.append(raw.view(NP_DTYPES[c.dtype])[0].item())
+            return out
+        finally:
+            for d in das:
+                d.free()
 
     # -- numeric (arrow-arith/src/numeric.rs) -----------------------------------------------
     def arith(self, op, a, b):

@@ -79,6 +79,29 @@ class ArrayOut(C.Structure):
     ]
 
 
+COL_PRIMITIVE, COL_BOOLEAN, COL_BYTES = range(3)
+MAX_BATCH_COLUMNS = 64
+
+
+class Column(C.Structure):
+    """acu_column: one column of a RecordBatch (include/arrow_cuda.h)."""
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("width", C.c_int32),
+        ("array", Array),
+        ("data", C.c_void_p),
+    ]
+
+
+class ColumnOut(C.Structure):
+    _fields_ = [
+        ("array", ArrayOut),
+        ("data", C.c_void_p),
+        ("data_capacity", C.c_int64),
+        ("data_len", C.c_int64),
+    ]
+
+
 def bitmap_bytes(n):
     return ((n + 63) // 64) * 8
 
@@ -132,6 +155,9 @@ PROTOTYPES = {
     "acu_cmp": (i32, [vp, i32, i32, P(Array), P(Array), P(ArrayOut)]),
     "acu_cast_numeric": (i32, [vp, i32, i32, i32, P(Array), P(ArrayOut)]),
     "acu_aggregate": (i32, [vp, i32, i32, P(Array), P(u64), P(i64)]),
+    "acu_filter_record_batch": (i32, [vp, vp, i32, P(Column), P(ColumnOut)]),
+    "acu_take_record_batch": (i32, [vp, i32, P(Column), P(Array), i32, i32, P(ColumnOut)]),
+    "acu_aggregate_columns": (i32, [vp, i32, P(i32), P(i32), P(Array), P(u64), P(i64)]),
     "acu_comm_get_unique_id": (i32, [vp]),
     "acu_comm_init": (i32, [vp, vp, i32, i32]),
     "acu_comm_destroy": (i32, [vp]),

@@ -26,11 +26,11 @@ __global__ void __launch_bounds__(256) k_bitmap_and(const uint8_t *__restrict__ 
 }
 
 acu_status acu_bitmap_and_launch(acu_ctx *ctx, const uint8_t *a, int64_t aoff, const uint8_t *b,
-                                 int64_t boff, int64_t len, uint64_t *out, bool count) {
+                                 int64_t boff, int64_t len, uint64_t *out, bool count, unsigned long long *res) {
   if (len <= 0) return ACU_OK;
   int64_t words = (len + 63) >> 6;
   ACU_LAUNCH(ctx, k_bitmap_and, acu_grid(ctx, (words + 255) / 256, 8), 256, 0, a, aoff, b, boff, len, out,
-             count ? ctx->d_res : nullptr);
+             count ? (res ? res : ctx->d_res) : nullptr);
   return ACU_OK;
 }
 

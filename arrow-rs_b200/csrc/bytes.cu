@@ -45,21 +45,6 @@ __device__ __forceinline__ uint64_t ld_index(const void *idx, int kind, int64_t 
   }
 }
 
-// len[j] of the j-th output slot
-__global__ void __launch_bounds__(256) k_lengths(const void *offs, int ob, const void *idx, int kind, int64_t m,
-                                                 const uint8_t *out_valid /* bit offset 0 or NULL */,
-                                                 int64_t *__restrict__ len) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
-    int64_t l = 0;
-    if (!out_valid || ld_bit(out_valid, j)) {
-      const int64_t i = (int64_t)ld_index(idx, kind, j);
-      l = ld_off(offs, ob, i + 1) - ld_off(offs, ob, i);
-    }
-    len[j] = l;
-  }
-}
-
 // ---- device-wide inclusive scan of int64 (in place) ------------------------------------
 __global__ void __launch_bounds__(1024) k_scan_block(int64_t *__restrict__ data, int64_t n, int64_t *__restrict__ block_tot) {
   __shared__ int64_t warp_tot[32];
@@ -112,38 +97,6 @@ acu_status scan_inclusive(acu_ctx *ctx, int64_t *data, int64_t n, int64_t *tmp /
     ACU_LAUNCH(ctx, k_scan_add, (unsigned)blocks, 1024, 0, data, n, tmp);
   }
   return ACU_OK;
-}
-
-// offsets[0] = 0, offsets[j+1] = incl[j]; records the first j whose running total exceeds `limit`
-__global__ void __launch_bounds__(256) k_write_offsets(const int64_t *__restrict__ incl, int64_t m, void *out_offs, int ob,
-                                                       int64_t limit, unsigned long long *res) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  unsigned long long err = ~0ull;
-  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
-    const int64_t v = incl[j];
-    if (v > limit && (unsigned long long)j < err) err = (unsigned long long)j;
-    if (ob == 4) static_cast<int32_t *>(out_offs)[j + 1] = (int32_t)v;
-    else static_cast<int64_t *>(out_offs)[j + 1] = v;
-    if (j == 0) { if (ob == 4) static_cast<int32_t *>(out_offs)[0] = 0; else static_cast<int64_t *>(out_offs)[0] = 0; }
-  }
-  if (err != ~0ull) atomicMin(res + RES_ERR_INDEX, err);
-}
-
-// One lane per output row; a warp's 32 rows are adjacent in the destination.
-__global__ void __launch_bounds__(256) k_copy_bytes(const void *offs, int ob, const uint8_t *__restrict__ data, const void *idx,
-                                                    int kind, int64_t m, const int64_t *__restrict__ incl,
-                                                    uint8_t *__restrict__ out) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
-    const int64_t end = incl[j];
-    const int64_t beg = j ? incl[j - 1] : 0;
-    const int64_t l = end - beg;
-    if (l <= 0) continue;
-    const int64_t i = (int64_t)ld_index(idx, kind, j);
-    const uint8_t *s = data + ld_off(offs, ob, i);
-    uint8_t *d = out + beg;
-    for (int64_t k = 0; k < l; ++k) d[k] = __ldg(s + k);
-  }
 }
 
 // Indices(Vec<usize>) of FilterBuilder::optimize (filter.rs:285-298): selected row ids, u64.
@@ -274,8 +227,15 @@ template <bool FAST>
 __global__ void __launch_bounds__(1024) k_bytes_offsets_copy(const BytesArgs a, const int64_t *__restrict__ block_incl,
                                                              int64_t first_block, void *out_offs, uint8_t *__restrict__ out_data,
                                                              int64_t limit, int64_t probe_row, unsigned long long *res,
-                                                             int stage_cap) {
+                                                             int stage_cap, const int64_t *__restrict__ total_ptr, int64_t out_cap) {
   extern __shared__ __align__(16) uint8_t s_out[];
+  // the byte copy is skipped (CTA-uniformly, grid-uniformly) when the total does not fit the
+  // caller's buffer or the offset type: decided on the device so that no host round trip sits
+  // between the sizing pass and this one
+  if (out_data != nullptr && total_ptr != nullptr) {
+    const int64_t total = __ldg(total_ptr);
+    if (total > out_cap || total > limit) out_data = nullptr;
+  }
   __shared__ uint64_t warp_tot[33];
   const int64_t blk = first_block + blockIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -337,7 +297,7 @@ __global__ void __launch_bounds__(1024) k_bytes_offsets_copy(const BytesArgs a, 
       }
     }
   }
-  if (err != ~0ull) atomicMin(res + RES_ERR_INDEX, err);
+  if (err != ~0ull) atomicMin(res + RES_ERR2, err);
   if (staged) {  // CTA-uniform
     __syncthreads();
     const uint32_t nbytes = (uint32_t)(cta_end - stage_origin);  // staged span, starts 16-B aligned in global memory
@@ -355,62 +315,88 @@ __global__ void __launch_bounds__(1024) k_bytes_offsets_copy(const BytesArgs a, 
   }
 }
 
-// lengths -> CTA totals -> scan -> offsets (+ byte copy when out_data != NULL and it fits).
-// Returns ACU_ERR_PANIC_OUT_OF_BOUNDS-style detection through *oob_row (>= 0) when detect_oob.
-acu_status gather_bytes(acu_ctx *ctx, int32_t ob, const void *offsets, const uint8_t *data, const void *idx, int kind,
-                        int64_t m, int64_t n_src, const uint8_t *out_valid, bool detect_oob, void *out_offsets,
-                        uint8_t *out_data, int64_t out_cap, int64_t *out_len, int64_t *oob_row) {
-  if (oob_row) *oob_row = -1;
+// lengths -> CTA totals -> scan -> offsets (+ byte copy when out_data != NULL and it fits), queued
+// on the ctx stream without synchronising; gather_finalize reads the fetched result block:
+// RES_ERR_INDEX = lowest out-of-bounds row (detect_oob), RES_AUX0 = total value bytes,
+// RES_ERR2 = lowest row whose running total exceeds the offset type.
+struct GatherState {
+  BytesArgs a;
+  int64_t blocks = 0;
+  int64_t *block_tot = nullptr;
+  void *out_offsets = nullptr;
+  uint8_t *out_data = nullptr;
+  int64_t out_cap = 0;
+  int64_t limit = 0;
+  bool detect_oob = false;
+};
+
+size_t gather_scratch_bytes(int64_t m) {
   const int64_t blocks = (m + SCAN_ELEMS - 1) / SCAN_ELEMS;
-  void *scratch;
-  ACU_TRY(acu_scratch(ctx, (size_t)(2 * blocks + blocks / SCAN_ELEMS + 4096) * 8, &scratch));
+  return (((size_t)(2 * blocks + blocks / SCAN_ELEMS + 4096) * 8) + 255) & ~(size_t)255;
+}
+
+acu_status gather_launch(acu_ctx *ctx, int32_t ob, const void *offsets, const uint8_t *data, const void *idx, int kind,
+                         int64_t m, int64_t n_src, const uint8_t *out_valid, bool detect_oob, void *out_offsets,
+                         uint8_t *out_data, int64_t out_cap, void *scratch, unsigned long long *res, GatherState *gs) {
+  const int64_t blocks = (m + SCAN_ELEMS - 1) / SCAN_ELEMS;
   int64_t *block_tot = static_cast<int64_t *>(scratch);
   BytesArgs a{offsets, data, idx, kind, (int)ob, m, n_src, reinterpret_cast<const uint32_t *>(out_valid), detect_oob ? 1 : 0};
   const bool fast = ob == 4 && kind == 4 && ((uintptr_t)idx % 4 == 0);
-  ACU_TRY(acu_res_reset(ctx));
-  if (fast) ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_block_totals<true>, (unsigned)blocks, 1024, 0, a, block_tot, ctx->d_res);
-  else ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_block_totals<false>, (unsigned)blocks, 1024, 0, a, block_tot, ctx->d_res);
+  gs->a = a;
+  gs->blocks = blocks;
+  gs->block_tot = block_tot;
+  gs->out_offsets = out_offsets;
+  gs->out_data = out_data;
+  gs->out_cap = out_cap;
+  gs->limit = ob == 4 ? (int64_t)INT32_MAX : INT64_MAX;
+  gs->detect_oob = detect_oob;
+  if (fast) ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_block_totals<true>, (unsigned)blocks, 1024, 0, a, block_tot, res);
+  else ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_block_totals<false>, (unsigned)blocks, 1024, 0, a, block_tot, res);
   ACU_TRY(scan_inclusive(ctx, block_tot, blocks, block_tot + blocks));
-  ACU_CUDA(ctx, cudaMemcpyAsync(ctx->d_res + RES_AUX0, block_tot + (blocks - 1), 8, cudaMemcpyDeviceToDevice, ctx->stream));
-  ACU_TRY(acu_res_fetch(ctx));
-  if (detect_oob && ctx->h_res[RES_ERR_INDEX] != ~0ull) {
-    if (oob_row) *oob_row = (int64_t)ctx->h_res[RES_ERR_INDEX];
-    return ACU_OK;
-  }
-  *out_len = (int64_t)ctx->h_res[RES_AUX0];
-  const int64_t limit = ob == 4 ? (int64_t)INT32_MAX : INT64_MAX;
-  uint8_t *copy_to = (out_data && *out_len <= out_cap) ? out_data : nullptr;
-  if (out_data && !copy_to && *out_len <= limit)
-    return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, (uint64_t)*out_len,
-                    "output data capacity %lld < required %lld", (long long)out_cap, (long long)*out_len);
-  ACU_TRY(acu_res_reset(ctx));
+  ACU_CUDA(ctx, cudaMemcpyAsync(res + RES_AUX0, block_tot + (blocks - 1), 8, cudaMemcpyDeviceToDevice, ctx->stream));
   const int stage_cap = 64 * 1024;
   a.detect_oob = 0;
-  uint8_t *dst = *out_len <= limit ? copy_to : nullptr;
+  static bool attr_set[2] = {false, false};  // per process is enough: the attribute is per function, per device context
+  (void)attr_set;
   if (fast) {
     ACU_CUDA(ctx, cudaFuncSetAttribute(k_bytes_offsets_copy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_cap));
     ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_offsets_copy<true>, (unsigned)blocks, 1024, stage_cap, a, block_tot, (int64_t)0, out_offsets,
-                     dst, limit, (int64_t)-1, ctx->d_res, stage_cap);
+                     out_data, gs->limit, (int64_t)-1, res, stage_cap, block_tot + (blocks - 1), out_cap);
   } else {
     ACU_CUDA(ctx, cudaFuncSetAttribute(k_bytes_offsets_copy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_cap));
     ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_offsets_copy<false>, (unsigned)blocks, 1024, stage_cap, a, block_tot, (int64_t)0, out_offsets,
-                     dst, limit, (int64_t)-1, ctx->d_res, stage_cap);
+                     out_data, gs->limit, (int64_t)-1, res, stage_cap, block_tot + (blocks - 1), out_cap);
   }
-  ACU_TRY(acu_res_fetch(ctx));
-  if (ctx->h_res[RES_ERR_INDEX] != ~0ull) {  // T::Offset::from_usize(capacity) failed (take.rs:520-523)
-    const int64_t j = (int64_t)ctx->h_res[RES_ERR_INDEX];
-    ACU_LAUNCH(ctx, k_bytes_offsets_copy<false>, 1, 1024, 0, a, block_tot, j / SCAN_ELEMS, out_offsets, static_cast<uint8_t *>(nullptr),
-               INT64_MAX, j, ctx->d_res, 0);
+  return ACU_OK;
+}
+
+// *oob_row >= 0: an out-of-bounds index at a valid slot (the caller raises the panic status).
+acu_status gather_finalize(acu_ctx *ctx, const GatherState &gs, const unsigned long long *hres, int64_t *out_len, int64_t *oob_row) {
+  if (oob_row) *oob_row = -1;
+  if (gs.detect_oob && hres[RES_ERR_INDEX] != ~0ull) {
+    if (oob_row) *oob_row = (int64_t)hres[RES_ERR_INDEX];
+    return ACU_OK;
+  }
+  *out_len = (int64_t)hres[RES_AUX0];
+  if (hres[RES_ERR2] != ~0ull) {  // T::Offset::from_usize(capacity) failed (take.rs:520-523)
+    const int64_t j = (int64_t)hres[RES_ERR2];
+    BytesArgs a = gs.a;
+    a.detect_oob = 0;
+    ACU_TRY(acu_res_reset(ctx));
+    ACU_LAUNCH(ctx, k_bytes_offsets_copy<false>, 1, 1024, 0, a, gs.block_tot, j / SCAN_ELEMS, gs.out_offsets, static_cast<uint8_t *>(nullptr),
+               INT64_MAX, j, ctx->d_res, 0, static_cast<const int64_t *>(nullptr), (int64_t)0);
     ACU_TRY(acu_res_fetch(ctx));
     const long long cap = (long long)ctx->h_res[RES_AUX1];
     return acu_fail(ctx, ACU_ERR_OFFSET_OVERFLOW, j, 0, 0, (uint64_t)cap, "%lld", cap);
   }
+  if (gs.out_data && *out_len > gs.out_cap)
+    return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, (uint64_t)*out_len,
+                    "output data capacity %lld < required %lld", (long long)gs.out_cap, (long long)*out_len);
   return ACU_OK;
 }
 
 acu_status zero_first_offset(acu_ctx *ctx, void *out_offsets, int ob) {
   ACU_CUDA(ctx, cudaMemsetAsync(out_offsets, 0, (size_t)ob, ctx->stream));
-  ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return ACU_OK;
 }
 
@@ -437,58 +423,160 @@ extern "C" acu_status acu_filter_plan_indices(acu_ctx *ctx, const acu_filter_pla
   return ACU_OK;
 }
 
+// The selected row ids of a plan (the reference's IterationStrategy::Indices, filter.rs:285-298), materialised once per
+// plan and shared by every variable-width column filtered with it: UInt32 when the predicate is short enough, else UInt64.
+acu_status acu_plan_cached_indices(acu_ctx *ctx, const acu_filter_plan *plan, const void **out_idx, int *out_kind) {
+  void **slot = acu_plan_index_cache(plan);
+  const bool narrow = acu_filter_plan_len(plan) <= (int64_t)UINT32_MAX;
+  *out_kind = narrow ? 4 : 5;
+  if (*slot == nullptr) {
+    void *mem = nullptr;
+    ACU_TRY(acu_malloc(ctx, (size_t)acu_filter_plan_count(plan) * (narrow ? 4 : 8), &mem));
+    const int64_t nwp = acu_plan_n_words_padded(plan);
+    const int grid = acu_grid(ctx, (nwp / 32 + 7) / 8, 8);
+    if (narrow)
+      ACU_LAUNCH_TIMED(ctx, ACU_K_FILTER_PLAN, k_plan_indices<uint32_t>, grid, 256, 0, acu_plan_mask(plan), acu_plan_tile_off(plan), nwp,
+                       static_cast<uint32_t *>(mem));
+    else
+      ACU_LAUNCH_TIMED(ctx, ACU_K_FILTER_PLAN, k_plan_indices<uint64_t>, grid, 256, 0, acu_plan_mask(plan), acu_plan_tile_off(plan), nwp,
+                       static_cast<uint64_t *>(mem));
+    *slot = mem;
+  }
+  *out_idx = *slot;
+  return ACU_OK;
+}
+
+size_t acu_bytes_col_scratch(int64_t out_rows) { return gather_scratch_bytes(out_rows); }
+
+// ---- one variable-width column of take / take_record_batch ------------------------------------
+struct acu_bytes_col_state {
+  GatherState gs;
+  int take_mode = 0;     // acu_take_col_launch's mode (nulls via the take kernel)
+  int nulls_kind = 0;    // 0 none, 1 = copy of indices.nulls (count in RES_COUNT), 2 = take kernel, 3 = filter_col (mode in take_mode)
+  bool gathered = false;
+};
+acu_bytes_col_state *acu_bytes_col_state_new() { return new acu_bytes_col_state(); }
+void acu_bytes_col_state_free(acu_bytes_col_state *s) { delete s; }
+
+acu_status acu_take_bytes_col_launch(acu_ctx *ctx, int32_t ob, const void *offsets, const uint8_t *data, const acu_array *nulls_of,
+                                     bool val_nulls, const acu_array *indices, acu_dtype index_dtype, bool idx_nulls,
+                                     void *out_offsets, uint8_t *out_data, int64_t out_cap, acu_array_out *out_nulls, void *scratch,
+                                     unsigned long long *res, acu_bytes_col_state *st) {
+  *st = acu_bytes_col_state();
+  if (ob != 4 && ob != 8) return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "offset width must be 4 or 8");
+  const int kind = index_kind(index_dtype);
+  if (kind < 0)  // take.rs:103
+    return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "Take only supported for integers, got %s", acu_dtype_name(index_dtype));
+  const int64_t m = indices->len;
+  out_nulls->len = m;
+  out_nulls->has_validity = 0;
+  out_nulls->null_count = 0;
+  if (m == 0) return zero_first_offset(ctx, out_offsets, ob);
+  const uint8_t *ov = nullptr;
+  bool detect_oob;
+  if (!val_nulls) {
+    // values without nulls: take_nulls = indices.nulls().cloned() (take.rs:429) is a bitmap copy, and the
+    // out-of-bounds check rides in the first bytes pass — no separate gather pass.
+    if (indices->validity) {
+      ACU_TRY(acu_bitmap_and_launch(ctx, indices->validity, indices->validity_offset, nullptr, 0, m,
+                                    reinterpret_cast<uint64_t *>(out_nulls->validity), true, res));
+      st->nulls_kind = 1;
+      if (idx_nulls) ov = out_nulls->validity;
+    }
+    detect_oob = true;
+  } else {
+    ACU_TRY(acu_take_col_launch(ctx, 0, nulls_of, false, true, indices, index_dtype, idx_nulls, out_nulls, res, &st->take_mode));
+    st->nulls_kind = 2;
+    if (st->take_mode & 1) ov = out_nulls->validity;
+    detect_oob = false;  // the take kernel reports it
+  }
+  ACU_TRY(gather_launch(ctx, ob, offsets, data, indices->values, kind, m, nulls_of->len, ov, detect_oob, out_offsets, out_data, out_cap,
+                        scratch, res, &st->gs));
+  st->gathered = true;
+  return ACU_OK;
+}
+
+acu_status acu_take_bytes_col_finalize(acu_ctx *ctx, const acu_array *nulls_of, const acu_array *indices, acu_dtype index_dtype,
+                                       const acu_bytes_col_state *st, const unsigned long long *hres, int64_t *out_data_len,
+                                       acu_array_out *out_nulls) {
+  *out_data_len = 0;
+  const int64_t m = indices->len;
+  if (!st->gathered) return ACU_OK;
+  if (st->nulls_kind == 2) ACU_TRY(acu_take_col_finalize(ctx, nulls_of, indices, index_dtype, st->take_mode, hres, out_nulls));
+  int64_t oob_row = -1;
+  ACU_TRY(gather_finalize(ctx, st->gs, hres, out_data_len, &oob_row));
+  if (oob_row >= 0) {  // the reference panics on a bounds-checked slice index (take.rs:517)
+    uint64_t raw = 0;
+    const int sz = acu_dtype_size(index_dtype);
+    ACU_CUDA(ctx, cudaMemcpyAsync(&raw, static_cast<const uint8_t *>(indices->values) + (size_t)oob_row * sz, sz, cudaMemcpyDeviceToHost, ctx->stream));
+    ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    uint64_t widened = raw;
+    if (index_dtype == ACU_I8) widened = (uint32_t)(int32_t)(int8_t)raw;
+    else if (index_dtype == ACU_I16) widened = (uint32_t)(int32_t)(int16_t)raw;
+    else if (index_dtype == ACU_I32) widened = (uint32_t)raw;
+    return acu_fail(ctx, ACU_ERR_PANIC_OUT_OF_BOUNDS, oob_row, widened, 0, (uint64_t)nulls_of->len, "Out-of-bounds index %llu",
+                    (unsigned long long)widened);
+  }
+  if (st->nulls_kind == 1) {
+    out_nulls->has_validity = 1;
+    out_nulls->null_count = m - (int64_t)hres[RES_COUNT];
+  }
+  return ACU_OK;
+}
+
 extern "C" acu_status acu_take_bytes(acu_ctx *ctx, int32_t offset_bytes, const void *offsets, const uint8_t *data,
                                      const acu_array *nulls_of, const acu_array *indices, acu_dtype index_dtype,
                                      int32_t check_bounds, void *out_offsets, uint8_t *out_data,
                                      int64_t out_data_capacity, int64_t *out_data_len, acu_array_out *out_nulls) {
   ACU_ENTER(ctx);
   *out_data_len = 0;
-  if (offset_bytes != 4 && offset_bytes != 8)
-    return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "offset width must be 4 or 8");
-  const int64_t m = indices->len;
-  acu_status st;
-  const int64_t vnc = acu_resolve_null_count(ctx, nulls_of, &st);
-  ACU_TRY(st);
-  const int kind = index_kind(index_dtype);
-  if (!check_bounds && kind >= 0 && !(nulls_of->validity && vnc > 0)) {
-    // values without nulls: take_nulls = indices.nulls().cloned() (take.rs:429) is a bitmap copy, and the
-    // out-of-bounds check rides in the first bytes pass — no separate gather pass.
-    out_nulls->len = m;
-    out_nulls->has_validity = 0;
-    out_nulls->null_count = 0;
-    if (m == 0) return zero_first_offset(ctx, out_offsets, offset_bytes);
-    if (indices->validity) {
-      ACU_TRY(acu_res_reset(ctx));
-      ACU_TRY(acu_bitmap_and_launch(ctx, indices->validity, indices->validity_offset, nullptr, 0, m,
-                                    reinterpret_cast<uint64_t *>(out_nulls->validity), true));
-      ACU_TRY(acu_res_fetch(ctx));
-      out_nulls->has_validity = 1;
-      out_nulls->null_count = m - (int64_t)ctx->h_res[RES_COUNT];
-    }
-    const uint8_t *ov = (out_nulls->has_validity && out_nulls->null_count > 0) ? out_nulls->validity : nullptr;
-    int64_t oob_row = -1;
-    ACU_TRY(gather_bytes(ctx, offset_bytes, offsets, data, indices->values, kind, m, nulls_of->len, ov, true, out_offsets, out_data,
-                         out_data_capacity, out_data_len, &oob_row));
-    if (oob_row >= 0) {  // the reference panics on a bounds-checked slice index (take.rs:517)
-      uint64_t raw = 0;
-      const int sz = acu_dtype_size(index_dtype);
-      ACU_CUDA(ctx, cudaMemcpyAsync(&raw, static_cast<const uint8_t *>(indices->values) + (size_t)oob_row * sz, sz, cudaMemcpyDeviceToHost, ctx->stream));
-      ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-      uint64_t widened = raw;
-      if (index_dtype == ACU_I8) widened = (uint32_t)(int32_t)(int8_t)raw;
-      else if (index_dtype == ACU_I16) widened = (uint32_t)(int32_t)(int16_t)raw;
-      else if (index_dtype == ACU_I32) widened = (uint32_t)raw;
-      return acu_fail(ctx, ACU_ERR_PANIC_OUT_OF_BOUNDS, oob_row, widened, 0, (uint64_t)nulls_of->len, "Out-of-bounds index %llu",
-                      (unsigned long long)widened);
-    }
-    return ACU_OK;
-  }
-  // take_nulls + bounds handling (elem_bytes = 0: no value gather)
-  ACU_TRY(acu_take_common(ctx, 0, nulls_of, false, indices, index_dtype, check_bounds, out_nulls));
-  if (m == 0) return zero_first_offset(ctx, out_offsets, offset_bytes);
-  const uint8_t *ov = (out_nulls->has_validity && out_nulls->null_count > 0) ? out_nulls->validity : nullptr;
-  return gather_bytes(ctx, offset_bytes, offsets, data, indices->values, index_kind(index_dtype), m, nulls_of->len, ov, false, out_offsets,
-                      out_data, out_data_capacity, out_data_len, nullptr);
+  if (index_kind(index_dtype) < 0)  // take.rs:103
+    return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "Take only supported for integers, got %s", acu_dtype_name(index_dtype));
+  acu_status s;
+  const int64_t vnc = acu_resolve_null_count(ctx, nulls_of, &s);
+  ACU_TRY(s);
+  const int64_t inc = acu_resolve_null_count(ctx, indices, &s);
+  ACU_TRY(s);
+  const bool idx_nulls = indices->validity && inc > 0;
+  if (check_bounds) ACU_TRY(acu_take_check_bounds(ctx, indices, index_dtype, idx_nulls, nulls_of->len));
+  void *scratch;
+  ACU_TRY(acu_scratch(ctx, gather_scratch_bytes(indices->len), &scratch));
+  acu_bytes_col_state st;
+  ACU_TRY(acu_res_reset(ctx));
+  ACU_TRY(acu_take_bytes_col_launch(ctx, offset_bytes, offsets, data, nulls_of, nulls_of->validity && vnc > 0, indices, index_dtype, idx_nulls,
+                                    out_offsets, out_data, out_data_capacity, out_nulls, scratch, acu_dres(ctx, 0), &st));
+  ACU_TRY(acu_res_fetch(ctx));
+  return acu_take_bytes_col_finalize(ctx, nulls_of, indices, index_dtype, &st, acu_hres(ctx, 0), out_data_len, out_nulls);
+}
+
+// ---- one variable-width column of filter / filter_record_batch ---------------------------------
+acu_status acu_filter_bytes_col_launch(acu_ctx *ctx, const acu_filter_plan *plan, int32_t ob, const void *offsets, const uint8_t *data,
+                                       const acu_array *nulls_of, void *out_offsets, uint8_t *out_data, int64_t out_cap,
+                                       acu_array_out *out_nulls, void *scratch, unsigned long long *res, acu_bytes_col_state *st) {
+  *st = acu_bytes_col_state();
+  if (ob != 4 && ob != 8) return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "offset width must be 4 or 8");
+  const int64_t count = acu_filter_plan_count(plan);
+  // nulls first (FilterPredicate::filter_nulls); also validates the predicate length
+  ACU_TRY(acu_filter_col_launch(ctx, plan, 2, 0, nulls_of, out_nulls, res, &st->take_mode));
+  st->nulls_kind = 3;
+  if (count == 0) return zero_first_offset(ctx, out_offsets, ob);
+  const void *idx;
+  int kind;
+  ACU_TRY(acu_plan_cached_indices(ctx, plan, &idx, &kind));
+  // null slots are copied too (filter.rs:891-892): no output-validity masking of the lengths
+  ACU_TRY(gather_launch(ctx, ob, offsets, data, idx, kind, count, nulls_of->len, nullptr, false, out_offsets, out_data, out_cap, scratch,
+                        res, &st->gs));
+  st->gathered = true;
+  return ACU_OK;
+}
+
+acu_status acu_filter_bytes_col_finalize(acu_ctx *ctx, const acu_filter_plan *plan, const acu_array *nulls_of,
+                                         const acu_bytes_col_state *st, const unsigned long long *hres, int64_t *out_data_len,
+                                         acu_array_out *out_nulls) {
+  *out_data_len = 0;
+  if (st->nulls_kind == 3) acu_filter_col_finalize(plan, nulls_of, st->take_mode, hres, out_nulls);
+  if (!st->gathered) return ACU_OK;
+  return gather_finalize(ctx, st->gs, hres, out_data_len, nullptr);
 }
 
 extern "C" acu_status acu_filter_bytes(acu_ctx *ctx, const acu_filter_plan *plan, int32_t offset_bytes,
@@ -497,41 +585,12 @@ extern "C" acu_status acu_filter_bytes(acu_ctx *ctx, const acu_filter_plan *plan
                                        int64_t *out_data_len, acu_array_out *out_nulls) {
   ACU_ENTER(ctx);
   *out_data_len = 0;
-  if (offset_bytes != 4 && offset_bytes != 8)
-    return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "offset width must be 4 or 8");
-  const int64_t plen = acu_filter_plan_len(plan), count = acu_filter_plan_count(plan);
-  if (plen > nulls_of->len)
-    return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, (uint64_t)nulls_of->len,
-                    "Filter predicate of length %lld is larger than target array of length %lld", (long long)plen,
-                    (long long)nulls_of->len);
-  out_nulls->len = count;
-  out_nulls->has_validity = 0;
-  out_nulls->null_count = 0;
-  if (count == 0) return zero_first_offset(ctx, out_offsets, offset_bytes);
-  // selected row ids (the reference's `Indices` strategy), then the same gather as take
-  void *idx_mem = nullptr;
-  ACU_TRY(acu_malloc(ctx, (size_t)count * 8, &idx_mem));
-  acu_status st = ACU_OK;
-  do {
-    const int64_t nwp = acu_plan_n_words_padded(plan);
-    k_plan_indices<uint64_t><<<acu_grid(ctx, (nwp / 32 + 7) / 8, 8), 256, 0, ctx->stream>>>(
-        acu_plan_mask(plan), acu_plan_tile_off(plan), nwp, static_cast<uint64_t *>(idx_mem));
-    ctx->launches++;
-    if (acu_filter_plan_strategy(plan) == ACU_FILTER_ALL) {  // values.slice(0, count)
-      out_nulls->has_validity = nulls_of->validity != nullptr;
-      if (nulls_of->validity) {
-        if ((st = acu_res_reset(ctx)) != ACU_OK) break;
-        if ((st = acu_bitmap_and_launch(ctx, nulls_of->validity, nulls_of->validity_offset, nullptr, 0, count,
-                                        reinterpret_cast<uint64_t *>(out_nulls->validity), true)) != ACU_OK) break;
-        if ((st = acu_res_fetch(ctx)) != ACU_OK) break;
-        out_nulls->null_count = count - (int64_t)ctx->h_res[RES_COUNT];
-      }
-    } else {
-      if ((st = acu_filter_nulls_internal(ctx, plan, nulls_of, out_nulls)) != ACU_OK) break;
-    }
-    st = gather_bytes(ctx, offset_bytes, offsets, data, idx_mem, 5, count, nulls_of->len, nullptr, false, out_offsets, out_data,
-                      out_data_capacity, out_data_len, nullptr);
-  } while (0);
-  acu_status st2 = acu_free(ctx, idx_mem);
-  return st != ACU_OK ? st : st2;
+  void *scratch;
+  ACU_TRY(acu_scratch(ctx, gather_scratch_bytes(acu_filter_plan_count(plan)), &scratch));
+  acu_bytes_col_state st;
+  ACU_TRY(acu_res_reset(ctx));
+  ACU_TRY(acu_filter_bytes_col_launch(ctx, plan, offset_bytes, offsets, data, nulls_of, out_offsets, out_data, out_data_capacity, out_nulls,
+                                      scratch, acu_dres(ctx, 0), &st));
+  ACU_TRY(acu_res_fetch(ctx));
+  return acu_filter_bytes_col_finalize(ctx, plan, nulls_of, &st, acu_hres(ctx, 0), out_data_len, out_nulls);
 }

@@ -24,7 +24,9 @@ enum {  // slots of the device/pinned result block
   RES_AUX1 = 3,
   RES_AUX2 = 4,
   RES_AUX3 = 5,
-  RES_SLOTS = 16
+  RES_ERR2 = 6,      // second lowest-failing-row slot (atomicMin), init UINT64_MAX
+  RES_SLOTS = 16,
+  RES_BLOCKS = 64    // result blocks: one per column of a record-batch call (block 0 for single-array calls)
 };
 
 struct acu_ctx {
@@ -37,7 +39,7 @@ struct acu_ctx {
   int64_t bytes_allocated = 0;
   std::unordered_map<void *, size_t> allocs;
   std::unordered_map<const void *, int> occupancy;  // resident CTAs per SM, per kernel
-  unsigned long long *d_res = nullptr;  // RES_SLOTS u64 on the device
+  unsigned long long *d_res = nullptr;  // RES_BLOCKS x RES_SLOTS u64 on the device
   unsigned long long *h_res = nullptr;  // pinned mirror
   void *d_scratch = nullptr;            // grows on demand (block partials, scans)
   size_t scratch_bytes = 0;
@@ -66,6 +68,10 @@ acu_status acu_cuda_fail(acu_ctx *ctx, cudaError_t e, const char *what);
 acu_status acu_scratch(acu_ctx *ctx, size_t bytes, void **out);  // >= bytes, 256-B aligned
 acu_status acu_res_reset(acu_ctx *ctx);                          // zero slots, ERR_INDEX = ~0
 acu_status acu_res_fetch(acu_ctx *ctx);                          // D2H + stream sync
+acu_status acu_res_reset_n(acu_ctx *ctx, int blocks);            // the same for the first `blocks` result blocks
+acu_status acu_res_fetch_n(acu_ctx *ctx, int blocks);
+static inline unsigned long long *acu_dres(acu_ctx *ctx, int block) { return ctx->d_res + (size_t)block * RES_SLOTS; }
+static inline const unsigned long long *acu_hres(const acu_ctx *ctx, int block) { return ctx->h_res + (size_t)block * RES_SLOTS; }
 int64_t acu_resolve_null_count(acu_ctx *ctx, const acu_array *a, acu_status *st);
 
 #define ACU_CUDA(ctx, expr)                                         \

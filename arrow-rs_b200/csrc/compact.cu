@@ -39,6 +39,7 @@ struct acu_filter_plan {
   uint32_t *tile_count = nullptr; // scratch of the scan
   uint64_t *chunk_total = nullptr;
   void *storage = nullptr;
+  mutable void *index_cache = nullptr;  // selected row ids (u32 / u64), built on first use by a variable-width column
 };
 
 namespace {
@@ -466,20 +467,6 @@ acu_status check_len(acu_ctx *ctx, const acu_filter_plan *plan, int64_t values_l
   return ACU_OK;
 }
 
-// `values.slice(0, count)` nulls for IterationStrategy::All (filter.rs:546)
-acu_status slice_nulls(acu_ctx *ctx, const acu_array *a, int64_t count, acu_array_out *out) {
-  out->has_validity = 0;
-  out->null_count = 0;
-  if (!a->validity || count == 0) { out->has_validity = a->validity != nullptr; return ACU_OK; }
-  ACU_TRY(acu_res_reset(ctx));
-  ACU_TRY(acu_bitmap_and_launch(ctx, a->validity, a->validity_offset, nullptr, 0, count,
-                                reinterpret_cast<uint64_t *>(out->validity), true));
-  ACU_TRY(acu_res_fetch(ctx));
-  out->has_validity = 1;
-  out->null_count = count - (int64_t)ctx->h_res[RES_COUNT];
-  return ACU_OK;
-}
-
 template <int W>
 acu_status launch_filter(acu_ctx *ctx, const FilterArgs &fa) {
   if (fa.aligned16) {
@@ -497,12 +484,11 @@ acu_status launch_filter(acu_ctx *ctx, const FilterArgs &fa) {
 
 // out (zeroed by this call) = bits of `src` selected by the plan; optional popcount into res.
 acu_status launch_compress(acu_ctx *ctx, const acu_filter_plan *plan, const uint8_t *src, int64_t soff, uint8_t *out,
-                           bool count) {
+                           unsigned long long *res) {
   const int64_t n_words_padded = ((plan->n_tiles * TILE_WORDS + 31) / 32) * 32;
   ACU_CUDA(ctx, cudaMemsetAsync(out, 0, acu_bitmap_bytes(plan->count), ctx->stream));
   ACU_LAUNCH_TIMED(ctx, ACU_K_FILTER, k_compress_bits, acu_wave_grid(ctx, k_compress_bits, 256, 0, (n_words_padded / 32 + 7) / 8),
-                   256, 0, src, soff, plan->len, plan->mask, plan->tile_off, n_words_padded, reinterpret_cast<uint32_t *>(out),
-                   count ? ctx->d_res : nullptr);
+                   256, 0, src, soff, plan->len, plan->mask, plan->tile_off, n_words_padded, reinterpret_cast<uint32_t *>(out), res);
   return ACU_OK;
 }
 
@@ -572,6 +558,7 @@ acu_status acu_filter_plan_create(acu_ctx *ctx, const acu_array *pred, acu_filte
 void acu_filter_plan_destroy(acu_ctx *ctx, acu_filter_plan *plan) {
   if (!plan) return;
   if (plan->storage) acu_free(ctx, plan->storage);
+  if (plan->index_cache) acu_free(ctx, plan->index_cache);
   delete plan;
 }
 int64_t acu_filter_plan_count(const acu_filter_plan *plan) { return plan->count; }
@@ -581,78 +568,106 @@ int32_t acu_filter_plan_strategy(const acu_filter_plan *plan) { return plan->str
 acu_status acu_filter_primitive(acu_ctx *ctx, const acu_filter_plan *plan, int32_t elem_bytes,
                                 const acu_array *values, acu_array_out *out) {
   ACU_ENTER(ctx);
-  ACU_TRY(check_len(ctx, plan, values->len));
-  out->len = plan->count;
-  out->has_validity = 0;
-  out->null_count = 0;
-  if (plan->strategy == ACU_FILTER_NONE) return ACU_OK;
-  if (plan->strategy == ACU_FILTER_ALL) {
-    ACU_CUDA(ctx, cudaMemcpyAsync(out->values, values->values, (size_t)plan->count * elem_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
-    ACU_TRY(slice_nulls(ctx, values, plan->count, out));
-    ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return ACU_OK;
-  }
-  FilterArgs fa{};
-  fa.values = static_cast<const uint8_t *>(values->values);
-  fa.out = static_cast<uint8_t *>(out->values);
-  fa.mask = plan->mask;
-  fa.tile_off = plan->tile_off;
-  fa.n_tiles = plan->n_tiles;
-  fa.aligned16 = ((uintptr_t)values->values % 16) == 0;
-  switch (elem_bytes) {
-    case 1: ACU_TRY(launch_filter<1>(ctx, fa)); break;
-    case 2: ACU_TRY(launch_filter<2>(ctx, fa)); break;
-    case 4: ACU_TRY(launch_filter<4>(ctx, fa)); break;
-    case 8: ACU_TRY(launch_filter<8>(ctx, fa)); break;
-    case 16: ACU_TRY(launch_filter<16>(ctx, fa)); break;
-    case 32: ACU_TRY(launch_filter<32>(ctx, fa)); break;
-    default:
-      return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "filter: unsupported element width %d", elem_bytes);
-  }
-  return acu_filter_nulls_internal(ctx, plan, values, out);
+  int mode = 0;
+  ACU_TRY(acu_res_reset(ctx));
+  ACU_TRY(acu_filter_col_launch(ctx, plan, 0, elem_bytes, values, out, acu_dres(ctx, 0), &mode));
+  ACU_TRY(acu_res_fetch(ctx));
+  acu_filter_col_finalize(plan, values, mode, acu_hres(ctx, 0), out);
+  return ACU_OK;
 }
 
 acu_status acu_filter_boolean(acu_ctx *ctx, const acu_filter_plan *plan, const acu_array *values,
                               acu_array_out *out) {
   ACU_ENTER(ctx);
-  ACU_TRY(check_len(ctx, plan, values->len));
-  out->len = plan->count;
-  out->has_validity = 0;
-  out->null_count = 0;
-  if (plan->strategy == ACU_FILTER_NONE) return ACU_OK;
-  if (plan->strategy == ACU_FILTER_ALL) {
-    ACU_TRY(acu_bitmap_and_launch(ctx, static_cast<const uint8_t *>(values->values), values->values_offset, nullptr, 0,
-                                  plan->count, static_cast<uint64_t *>(out->values), false));
-    ACU_TRY(slice_nulls(ctx, values, plan->count, out));
-    ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return ACU_OK;
-  }
-  ACU_TRY(launch_compress(ctx, plan, static_cast<const uint8_t *>(values->values), values->values_offset,
-                          static_cast<uint8_t *>(out->values), false));
-  return acu_filter_nulls_internal(ctx, plan, values, out);
+  int mode = 0;
+  ACU_TRY(acu_res_reset(ctx));
+  ACU_TRY(acu_filter_col_launch(ctx, plan, 1, 0, values, out, acu_dres(ctx, 0), &mode));
+  ACU_TRY(acu_res_fetch(ctx));
+  acu_filter_col_finalize(plan, values, mode, acu_hres(ctx, 0), out);
+  return ACU_OK;
 }
 
 }  // extern "C"
 
-// FilterPredicate::filter_nulls (filter.rs:512-533): bit-compact the validity, count, drop
-// the buffer when the result has no nulls. Synchronises the stream.
-acu_status acu_filter_nulls_internal(acu_ctx *ctx, const acu_filter_plan *plan, const acu_array *a,
-                                     acu_array_out *out) {
+// One column of filter / filter_record_batch: queue the value kernel (kind 0 = primitive of
+// elem_bytes, 1 = boolean, 2 = validity only) and the validity compaction on the ctx stream
+// WITHOUT synchronising. *mode tells acu_filter_col_finalize how to read the result block:
+// 0 = no validity work, 1 = compacted validity + popcount, 2 = IterationStrategy::All slice.
+acu_status acu_filter_col_launch(acu_ctx *ctx, const acu_filter_plan *plan, int kind, int32_t elem_bytes,
+                                 const acu_array *values, acu_array_out *out, unsigned long long *res, int *mode) {
+  *mode = 0;
+  ACU_TRY(check_len(ctx, plan, values->len));
+  out->len = plan->count;
   out->has_validity = 0;
   out->null_count = 0;
-  acu_status st;
-  const int64_t nc = acu_resolve_null_count(ctx, a, &st);
-  ACU_TRY(st);
-  if (a->validity && nc > 0 && plan->count > 0) {
-    ACU_TRY(acu_res_reset(ctx));
-    ACU_TRY(launch_compress(ctx, plan, a->validity, a->validity_offset, out->validity, true));
-    ACU_TRY(acu_res_fetch(ctx));
-    const int64_t null_count = plan->count - (int64_t)ctx->h_res[RES_COUNT];
-    if (null_count > 0) { out->has_validity = 1; out->null_count = null_count; }  // filter.rs:523-525
-  } else {
-    ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    acu_kstats_drain(ctx);
+  if (plan->strategy == ACU_FILTER_NONE || plan->count == 0) return ACU_OK;
+  // a validity buffer with a cached null_count of 0 is dropped (filter.rs:513-516); an unknown
+  // null_count (-1) is compacted and counted: the result is the same, NullBuffer-wise
+  const bool has_nulls = values->validity != nullptr && values->null_count != 0;
+  if (plan->strategy == ACU_FILTER_ALL) {  // values.slice(0, count) (filter.rs:546)
+    if (kind == 0)
+      ACU_CUDA(ctx, cudaMemcpyAsync(out->values, values->values, (size_t)plan->count * elem_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    else if (kind == 1)
+      ACU_TRY(acu_bitmap_and_launch(ctx, static_cast<const uint8_t *>(values->values), values->values_offset, nullptr, 0,
+                                    plan->count, static_cast<uint64_t *>(out->values), false));
+    if (values->validity) {
+      ACU_TRY(acu_bitmap_and_launch(ctx, values->validity, values->validity_offset, nullptr, 0, plan->count,
+                                    reinterpret_cast<uint64_t *>(out->validity), true, res));
+      *mode = 2;
+    }
+    return ACU_OK;
   }
+  if (kind == 0) {
+    FilterArgs fa{};
+    fa.values = static_cast<const uint8_t *>(values->values);
+    fa.out = static_cast<uint8_t *>(out->values);
+    fa.mask = plan->mask;
+    fa.tile_off = plan->tile_off;
+    fa.n_tiles = plan->n_tiles;
+    fa.aligned16 = ((uintptr_t)values->values % 16) == 0;
+    switch (elem_bytes) {
+      case 1: ACU_TRY(launch_filter<1>(ctx, fa)); break;
+      case 2: ACU_TRY(launch_filter<2>(ctx, fa)); break;
+      case 4: ACU_TRY(launch_filter<4>(ctx, fa)); break;
+      case 8: ACU_TRY(launch_filter<8>(ctx, fa)); break;
+      case 16: ACU_TRY(launch_filter<16>(ctx, fa)); break;
+      case 32: ACU_TRY(launch_filter<32>(ctx, fa)); break;
+      default:
+        return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "filter: unsupported element width %d", elem_bytes);
+    }
+  } else if (kind == 1) {
+    ACU_TRY(launch_compress(ctx, plan, static_cast<const uint8_t *>(values->values), values->values_offset,
+                            static_cast<uint8_t *>(out->values), nullptr));
+  }
+  if (has_nulls) {  // FilterPredicate::filter_nulls (filter.rs:512-533)
+    ACU_TRY(launch_compress(ctx, plan, values->validity, values->validity_offset, out->validity, res));
+    *mode = 1;
+  }
+  return ACU_OK;
+}
+
+void acu_filter_col_finalize(const acu_filter_plan *plan, const acu_array *values, int mode,
+                             const unsigned long long *hres, acu_array_out *out) {
+  (void)values;
+  out->has_validity = 0;
+  out->null_count = 0;
+  if (mode == 1) {  // None when the filtered validity has no nulls (filter.rs:523-525)
+    const int64_t null_count = plan->count - (int64_t)hres[RES_COUNT];
+    if (null_count > 0) { out->has_validity = 1; out->null_count = null_count; }
+  } else if (mode == 2) {  // the slice keeps its NullBuffer
+    out->has_validity = 1;
+    out->null_count = plan->count - (int64_t)hres[RES_COUNT];
+  }
+}
+
+// FilterPredicate::filter_nulls for any array kind (bytes.cu). Synchronises the stream.
+acu_status acu_filter_nulls_internal(acu_ctx *ctx, const acu_filter_plan *plan, const acu_array *a,
+                                     acu_array_out *out) {
+  int mode = 0;
+  ACU_TRY(acu_res_reset(ctx));
+  ACU_TRY(acu_filter_col_launch(ctx, plan, 2, 0, a, out, acu_dres(ctx, 0), &mode));
+  ACU_TRY(acu_res_fetch(ctx));
+  acu_filter_col_finalize(plan, a, mode, acu_hres(ctx, 0), out);
   return ACU_OK;
 }
 
@@ -660,4 +675,5 @@ acu_status acu_filter_nulls_internal(acu_ctx *ctx, const acu_filter_plan *plan, 
 const uint64_t *acu_plan_mask(const acu_filter_plan *p) { return p->mask; }
 const uint64_t *acu_plan_tile_off(const acu_filter_plan *p) { return p->tile_off; }
 int64_t acu_plan_n_tiles(const acu_filter_plan *p) { return p->n_tiles; }
+void **acu_plan_index_cache(const acu_filter_plan *p) { return &p->index_cache; }
 int64_t acu_plan_n_words_padded(const acu_filter_plan *p) { return ((p->n_tiles * TILE_WORDS + 31) / 32) * 32; }

@@ -61,23 +61,30 @@ acu_status acu_scratch(acu_ctx *ctx, size_t bytes, void **out) {
   return ACU_OK;
 }
 
-__global__ void k_res_reset(unsigned long long *res) {
+__global__ void k_res_reset(unsigned long long *res, int slots) {
   int i = threadIdx.x;
-  if (i < RES_SLOTS) res[i] = (i == RES_ERR_INDEX) ? ~0ull : 0ull;
+  if (i < slots) res[i] = ((i % RES_SLOTS) == RES_ERR_INDEX || (i % RES_SLOTS) == RES_ERR2) ? ~0ull : 0ull;
 }
 
-acu_status acu_res_reset(acu_ctx *ctx) {
-  ACU_LAUNCH(ctx, k_res_reset, 1, 32, 0, ctx->d_res);
+acu_status acu_res_reset_n(acu_ctx *ctx, int blocks) {
+  if (blocks < 1) blocks = 1;
+  if (blocks > RES_BLOCKS) blocks = RES_BLOCKS;
+  ACU_LAUNCH(ctx, k_res_reset, 1, blocks * RES_SLOTS, 0, ctx->d_res, blocks * RES_SLOTS);
   return ACU_OK;
 }
 
-acu_status acu_res_fetch(acu_ctx *ctx) {
-  ACU_CUDA(ctx, cudaMemcpyAsync(ctx->h_res, ctx->d_res, RES_SLOTS * sizeof(unsigned long long),
+acu_status acu_res_fetch_n(acu_ctx *ctx, int blocks) {
+  if (blocks < 1) blocks = 1;
+  if (blocks > RES_BLOCKS) blocks = RES_BLOCKS;
+  ACU_CUDA(ctx, cudaMemcpyAsync(ctx->h_res, ctx->d_res, (size_t)blocks * RES_SLOTS * sizeof(unsigned long long),
                                 cudaMemcpyDeviceToHost, ctx->stream));
   ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   acu_kstats_drain(ctx);
   return ACU_OK;
 }
+
+acu_status acu_res_reset(acu_ctx *ctx) { return acu_res_reset_n(ctx, 1); }
+acu_status acu_res_fetch(acu_ctx *ctx) { return acu_res_fetch_n(ctx, 1); }
 
 // ---- per-kernel-class device time ---------------------------------------------------------
 int acu_kstats_begin(acu_ctx *ctx, int cls) {
@@ -122,8 +129,8 @@ acu_status acu_ctx_create(int32_t device, acu_ctx **out) {
   bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreate(&ctx->ev_start) == cudaSuccess &&
             cudaEventCreate(&ctx->ev_stop) == cudaSuccess &&
-            cudaMalloc(&ctx->d_res, RES_SLOTS * sizeof(unsigned long long)) == cudaSuccess &&
-            cudaHostAlloc(&ctx->h_res, RES_SLOTS * sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
+            cudaMalloc(&ctx->d_res, (size_t)RES_BLOCKS * RES_SLOTS * sizeof(unsigned long long)) == cudaSuccess &&
+            cudaHostAlloc(&ctx->h_res, (size_t)RES_BLOCKS * RES_SLOTS * sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
   for (int i = 0; ok && i < ACU_TIMER_SLOTS; ++i)
     ok = cudaEventCreate(&ctx->tev[i][0]) == cudaSuccess && cudaEventCreate(&ctx->tev[i][1]) == cudaSuccess;
   for (int i = 0; ok && i < acu_ctx::KEV_PAIRS; ++i)

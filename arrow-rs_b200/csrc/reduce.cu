@@ -15,6 +15,7 @@
 #include <type_traits>
 
 #include "bitmap.cuh"
+#include "internal.cuh"
 
 namespace {
 
@@ -150,58 +151,75 @@ __global__ void __launch_bounds__(256) k_reduce(const T *__restrict__ v, int64_t
 }
 
 template <class T, int OP>
-acu_status reduce_launch(acu_ctx *ctx, const acu_array *a, const uint8_t *valid) {
+acu_status reduce_launch(acu_ctx *ctx, const acu_array *a, const uint8_t *valid, void *scratch, unsigned long long *res) {
   using A = typename AccOf<T, OP>::type;
   const int64_t strips = (a->len + 63) >> 6;
   const int grid = acu_wave_grid(ctx, k_reduce<T, OP>, 256, 0, (strips / 32 + 1 + 7) / 8);
-  void *scratch;
-  ACU_TRY(acu_scratch(ctx, 256 + (size_t)grid * sizeof(A), &scratch));
+  static_assert(sizeof(A) <= 16, "partials must fit the per-column scratch");
   unsigned int *ticket = static_cast<unsigned int *>(scratch);
   A *partial = reinterpret_cast<A *>(static_cast<uint8_t *>(scratch) + 256);
   ACU_CUDA(ctx, cudaMemsetAsync(ticket, 0, 4, ctx->stream));
   ACU_LAUNCH_TIMED(ctx, ACU_K_REDUCE, (k_reduce<T, OP>), grid, 256, 0, static_cast<const T *>(a->values), a->len, valid, a->validity_offset,
-             partial, ticket, ctx->d_res);
+             partial, ticket, res);
   return ACU_OK;
 }
 
 template <class T>
-acu_status aggregate_typed(acu_ctx *ctx, acu_agg_op op, const acu_array *a, uint64_t *out_bits, int64_t *out_valid) {
-  *out_bits = 0;
-  *out_valid = 0;
-  if (a->len == 0) return ACU_OK;  // None
-  acu_status st;
-  const int64_t nc = acu_resolve_null_count(ctx, a, &st);
-  ACU_TRY(st);
-  *out_valid = a->len - nc;
-  if (nc == a->len) return ACU_OK;  // aggregate.rs:320-323
-  const uint8_t *valid = (a->validity && nc > 0) ? a->validity : nullptr;
-  ACU_TRY(acu_res_reset(ctx));
+acu_status reduce_typed(acu_ctx *ctx, acu_agg_op op, const acu_array *a, const uint8_t *valid, void *scratch, unsigned long long *res) {
   switch (op) {
-    case ACU_SUM: ACU_TRY((reduce_launch<T, ACU_SUM>(ctx, a, valid))); break;
-    case ACU_MIN: ACU_TRY((reduce_launch<T, ACU_MIN>(ctx, a, valid))); break;
-    default: ACU_TRY((reduce_launch<T, ACU_MAX>(ctx, a, valid))); break;
+    case ACU_SUM: return reduce_launch<T, ACU_SUM>(ctx, a, valid, scratch, res);
+    case ACU_MIN: return reduce_launch<T, ACU_MIN>(ctx, a, valid, scratch, res);
+    default: return reduce_launch<T, ACU_MAX>(ctx, a, valid, scratch, res);
   }
-  ACU_TRY(acu_res_fetch(ctx));
-  *out_bits = ctx->h_res[RES_AUX0];
-  return ACU_OK;
 }
 
 }  // namespace
 
+// per-column scratch of one queued reduction: ticket + one partial per CTA of the widest grid
+size_t acu_reduce_col_scratch(const acu_ctx *ctx) { return 256 + (size_t)ctx->sm_count * 8 * 8 * 16 + 4096; }
+
+// Queue sum / min / max of one column on the ctx stream (no sync). The caller has resolved the
+// null count: nc == len (or len == 0) means None and nothing is launched (*launched = 0). The
+// result lands in res[RES_AUX0] as the native bit pattern.
+acu_status acu_reduce_col_launch(acu_ctx *ctx, acu_dtype dtype, acu_agg_op op, const acu_array *a, int64_t nc, void *scratch,
+                                 unsigned long long *res, int *launched) {
+  *launched = 0;
+  if (a->len == 0 || nc == a->len) return ACU_OK;  // aggregate.rs:320-323
+  const uint8_t *valid = (a->validity && nc > 0) ? a->validity : nullptr;
+  *launched = 1;
+  switch (dtype) {
+    case ACU_I8: return reduce_typed<int8_t>(ctx, op, a, valid, scratch, res);
+    case ACU_I16: return reduce_typed<int16_t>(ctx, op, a, valid, scratch, res);
+    case ACU_I32: return reduce_typed<int32_t>(ctx, op, a, valid, scratch, res);
+    case ACU_I64: return reduce_typed<int64_t>(ctx, op, a, valid, scratch, res);
+    case ACU_U8: return reduce_typed<uint8_t>(ctx, op, a, valid, scratch, res);
+    case ACU_U16: return reduce_typed<uint16_t>(ctx, op, a, valid, scratch, res);
+    case ACU_U32: return reduce_typed<uint32_t>(ctx, op, a, valid, scratch, res);
+    case ACU_U64: return reduce_typed<uint64_t>(ctx, op, a, valid, scratch, res);
+    case ACU_F32: return reduce_typed<float>(ctx, op, a, valid, scratch, res);
+    case ACU_F64: return reduce_typed<double>(ctx, op, a, valid, scratch, res);
+  }
+  *launched = 0;
+  return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "aggregate: dtype %d", (int)dtype);
+}
+
 extern "C" acu_status acu_aggregate(acu_ctx *ctx, acu_dtype dtype, acu_agg_op op, const acu_array *a,
                                     uint64_t *out_bits, int64_t *out_valid_count) {
   ACU_ENTER(ctx);
-  switch (dtype) {
-    case ACU_I8: return aggregate_typed<int8_t>(ctx, op, a, out_bits, out_valid_count);
-    case ACU_I16: return aggregate_typed<int16_t>(ctx, op, a, out_bits, out_valid_count);
-    case ACU_I32: return aggregate_typed<int32_t>(ctx, op, a, out_bits, out_valid_count);
-    case ACU_I64: return aggregate_typed<int64_t>(ctx, op, a, out_bits, out_valid_count);
-    case ACU_U8: return aggregate_typed<uint8_t>(ctx, op, a, out_bits, out_valid_count);
-    case ACU_U16: return aggregate_typed<uint16_t>(ctx, op, a, out_bits, out_valid_count);
-    case ACU_U32: return aggregate_typed<uint32_t>(ctx, op, a, out_bits, out_valid_count);
-    case ACU_U64: return aggregate_typed<uint64_t>(ctx, op, a, out_bits, out_valid_count);
-    case ACU_F32: return aggregate_typed<float>(ctx, op, a, out_bits, out_valid_count);
-    case ACU_F64: return aggregate_typed<double>(ctx, op, a, out_bits, out_valid_count);
-  }
-  return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "aggregate: dtype %d", (int)dtype);
+  *out_bits = 0;
+  *out_valid_count = 0;
+  if (a->len == 0) return ACU_OK;  // None
+  acu_status st;
+  const int64_t nc = acu_resolve_null_count(ctx, a, &st);
+  ACU_TRY(st);
+  *out_valid_count = a->len - nc;
+  void *scratch;
+  ACU_TRY(acu_scratch(ctx, acu_reduce_col_scratch(ctx), &scratch));
+  int launched = 0;
+  ACU_TRY(acu_res_reset(ctx));
+  ACU_TRY(acu_reduce_col_launch(ctx, dtype, op, a, nc, scratch, acu_dres(ctx, 0), &launched));
+  if (!launched) return ACU_OK;
+  ACU_TRY(acu_res_fetch(ctx));
+  *out_bits = ctx->h_res[RES_AUX0];
+  return ACU_OK;
 }

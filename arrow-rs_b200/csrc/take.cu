@@ -314,28 +314,7 @@ acu_status acu_take_common(acu_ctx *ctx, int32_t elem_bytes, const acu_array *va
   const int64_t inc = acu_resolve_null_count(ctx, indices, &st);
   ACU_TRY(st);
   const bool idx_nulls = indices->validity && inc > 0;
-  if (check_bounds && m > 0 && (uint64_t)values->len <= index_max(index_dtype)) {  // T::Native::from_usize(len)
-    ACU_TRY(acu_res_reset(ctx));
-    const int grid = acu_grid(ctx, (m + 255) / 256, 8);
-    const uint8_t *iv = idx_nulls ? indices->validity : nullptr;
-    const bool sgn = acu_dtype_is_signed(index_dtype);
-#define ACU_CB_CASE(IT)                                                                                                   \
-  case IT:                                                                                                                \
-    if (sgn) ACU_LAUNCH(ctx, (k_check_bounds<IT, true>), grid, 256, 0, indices->values, m, values->len, iv, indices->validity_offset, ctx->d_res); \
-    else ACU_LAUNCH(ctx, (k_check_bounds<IT, false>), grid, 256, 0, indices->values, m, values->len, iv, indices->validity_offset, ctx->d_res);    \
-    break;
-    switch (kind) { ACU_CB_CASE(0) ACU_CB_CASE(1) ACU_CB_CASE(2) ACU_CB_CASE(3) ACU_CB_CASE(4) ACU_CB_CASE(5) default: break; }
-#undef ACU_CB_CASE
-    ACU_TRY(acu_res_fetch(ctx));
-    if (ctx->h_res[RES_ERR_INDEX] != ~0ull) {
-      const int64_t j = (int64_t)ctx->h_res[RES_ERR_INDEX];
-      uint64_t raw;
-      char text[32];
-      ACU_TRY(fetch_index(ctx, indices, index_dtype, j, &raw, text, sizeof text));
-      return acu_fail(ctx, ACU_ERR_COMPUTE, j, raw, 0, (uint64_t)values->len,
-                      "Array index out of bounds, cannot get item at index %s from %lld entries", text, (long long)values->len);
-    }
-  }
+  if (check_bounds) ACU_TRY(acu_take_check_bounds(ctx, indices, index_dtype, idx_nulls, values->len));
   out->len = m;
   out->has_validity = 0;
   out->null_count = 0;
@@ -343,7 +322,27 @@ acu_status acu_take_common(acu_ctx *ctx, int32_t elem_bytes, const acu_array *va
   const int64_t vnc = acu_resolve_null_count(ctx, values, &st);
   ACU_TRY(st);
   const bool val_nulls = values->validity && vnc > 0;  // take_nulls (take.rs:419-430)
+  int mode = 0;
+  ACU_TRY(acu_res_reset(ctx));
+  ACU_TRY(acu_take_col_launch(ctx, elem_bytes, values, boolean_values, val_nulls, indices, index_dtype, idx_nulls, out, acu_dres(ctx, 0), &mode));
+  ACU_TRY(acu_res_fetch(ctx));
+  return acu_take_col_finalize(ctx, values, indices, index_dtype, mode, acu_hres(ctx, 0), out);
+}
 
+// One column of take / take_record_batch: queue the gather on the ctx stream without
+// synchronising. val_nulls / idx_nulls = "has a validity buffer with at least one null"
+// (exact, the NullBuffer decision depends on it). *mode: bit 0 = an output validity was
+// produced, bit 1 = it came from take_bits(values.nulls) (None when it has no nulls).
+acu_status acu_take_col_launch(acu_ctx *ctx, int32_t elem_bytes, const acu_array *values, bool boolean_values, bool val_nulls,
+                               const acu_array *indices, acu_dtype index_dtype, bool idx_nulls, acu_array_out *out,
+                               unsigned long long *res, int *mode) {
+  *mode = 0;
+  const int kind = index_kind(index_dtype);
+  const int64_t m = indices->len;
+  out->len = m;
+  out->has_validity = 0;
+  out->null_count = 0;
+  if (m == 0) return ACU_OK;
   TakeArgs ta{};
   ta.values = (elem_bytes > 0 && !boolean_values) ? values->values : nullptr;
   ta.n_values = values->len;
@@ -355,13 +354,19 @@ acu_status acu_take_common(acu_ctx *ctx, int32_t elem_bytes, const acu_array *va
   ta.idx_has_nulls = idx_nulls;
   ta.out = out->values;
   if (val_nulls || indices->validity) ta.out_valid = reinterpret_cast<uint32_t *>(out->validity);
-  ta.res = ctx->d_res;
+  ta.res = res;
   ta.use_bulk = ((uintptr_t)indices->values % 16) == 0;
-  ACU_TRY(acu_res_reset(ctx));
   ACU_TRY(launch_take(ctx, ta.values ? elem_bytes : 1, kind, ta));
-  ACU_TRY(acu_res_fetch(ctx));
-  if (ctx->h_res[RES_ERR_INDEX] != ~0ull) {
-    const int64_t j = (int64_t)ctx->h_res[RES_ERR_INDEX];
+  *mode = (ta.out_valid ? 1 : 0) | (val_nulls ? 2 : 0);
+  return ACU_OK;
+}
+
+acu_status acu_take_col_finalize(acu_ctx *ctx, const acu_array *values, const acu_array *indices, acu_dtype index_dtype, int mode,
+                                 const unsigned long long *hres, acu_array_out *out) {
+  const int64_t m = indices->len;
+  if (m == 0) return ACU_OK;
+  if (hres[RES_ERR_INDEX] != ~0ull) {
+    const int64_t j = (int64_t)hres[RES_ERR_INDEX];
     uint64_t raw;
     char text[32];
     ACU_TRY(fetch_index(ctx, indices, index_dtype, j, &raw, text, sizeof text));
@@ -376,9 +381,9 @@ acu_status acu_take_common(acu_ctx *ctx, int32_t elem_bytes, const acu_array *va
     return acu_fail(ctx, ACU_ERR_PANIC_OUT_OF_BOUNDS, j, widened, 0, (uint64_t)values->len, "Out-of-bounds index %llu",
                     (unsigned long long)widened);
   }
-  if (ta.out_valid) {
-    const int64_t null_count = m - (int64_t)ctx->h_res[RES_COUNT];
-    if (val_nulls) {  // NullBuffer::from_unsliced_buffer: None when no nulls (null.rs:266-270)
+  if (mode & 1) {
+    const int64_t null_count = m - (int64_t)hres[RES_COUNT];
+    if (mode & 2) {  // NullBuffer::from_unsliced_buffer: None when no nulls (null.rs:266-270)
       if (null_count > 0) { out->has_validity = 1; out->null_count = null_count; }
     } else {
       out->has_validity = 1;
@@ -387,6 +392,36 @@ acu_status acu_take_common(acu_ctx *ctx, int32_t elem_bytes, const acu_array *va
   }
   return ACU_OK;
 }
+
+// TakeOptions{check_bounds:true} (take.rs:167-209) for one index array against `values_len` rows; synchronises.
+acu_status acu_take_check_bounds(acu_ctx *ctx, const acu_array *indices, acu_dtype index_dtype, bool idx_nulls, int64_t values_len) {
+  const int kind = index_kind(index_dtype);
+  const int64_t m = indices->len;
+  if (!(m > 0 && (uint64_t)values_len <= index_max(index_dtype))) return ACU_OK;  // T::Native::from_usize(len)
+  ACU_TRY(acu_res_reset(ctx));
+  const int grid = acu_grid(ctx, (m + 255) / 256, 8);
+  const uint8_t *iv = idx_nulls ? indices->validity : nullptr;
+  const bool sgn = acu_dtype_is_signed(index_dtype);
+#define ACU_CB_CASE(IT)                                                                                                   \
+  case IT:                                                                                                                \
+    if (sgn) ACU_LAUNCH(ctx, (k_check_bounds<IT, true>), grid, 256, 0, indices->values, m, values_len, iv, indices->validity_offset, ctx->d_res); \
+    else ACU_LAUNCH(ctx, (k_check_bounds<IT, false>), grid, 256, 0, indices->values, m, values_len, iv, indices->validity_offset, ctx->d_res);    \
+    break;
+  switch (kind) { ACU_CB_CASE(0) ACU_CB_CASE(1) ACU_CB_CASE(2) ACU_CB_CASE(3) ACU_CB_CASE(4) ACU_CB_CASE(5) default: break; }
+#undef ACU_CB_CASE
+  ACU_TRY(acu_res_fetch(ctx));
+  if (ctx->h_res[RES_ERR_INDEX] != ~0ull) {
+    const int64_t j = (int64_t)ctx->h_res[RES_ERR_INDEX];
+    uint64_t raw;
+    char text[32];
+    ACU_TRY(fetch_index(ctx, indices, index_dtype, j, &raw, text, sizeof text));
+    return acu_fail(ctx, ACU_ERR_COMPUTE, j, raw, 0, (uint64_t)values_len,
+                    "Array index out of bounds, cannot get item at index %s from %lld entries", text, (long long)values_len);
+  }
+  return ACU_OK;
+}
+
+int acu_take_index_kind(acu_dtype t) { return index_kind(t); }
 
 extern "C" acu_status acu_take_primitive(acu_ctx *ctx, int32_t elem_bytes, const acu_array *values,
                                          const acu_array *indices, acu_dtype index_dtype,

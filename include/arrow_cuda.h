@@ -314,6 +314,57 @@ acu_status acu_aggregate(acu_ctx *ctx, acu_dtype dtype, acu_agg_op op, const acu
                          uint64_t *out_bits, int64_t *out_valid_count);
 
 /* ------------------------------------------------------------------------- */
+/* RecordBatch level — filter_record_batch / take_record_batch / per-column   */
+/* aggregates with ONE stream synchronisation per call                        */
+/* ------------------------------------------------------------------------- */
+/* A column of a RecordBatch (arrow-array/src/record_batch.rs:224). PRIMITIVE: `array`
+ * as for acu_filter_primitive with element width `width`; BOOLEAN: `array.values` is a
+ * bitmap; BYTES (Utf8/Binary/LargeUtf8/LargeBinary): `array.values` = the offsets
+ * buffer (i32 if width == 4, i64 if width == 8, array.len + 1 entries), `data` = the
+ * value bytes, `array.validity/len/null_count` the nulls. */
+typedef enum acu_column_kind { ACU_COL_PRIMITIVE = 0, ACU_COL_BOOLEAN = 1, ACU_COL_BYTES = 2 } acu_column_kind;
+
+typedef struct acu_column {
+  int32_t kind;          /* acu_column_kind */
+  int32_t width;         /* PRIMITIVE: element bytes (1,2,4,8,16,32); BYTES: offset bytes (4|8) */
+  acu_array array;
+  const uint8_t *data;   /* BYTES only */
+} acu_column;
+
+/* Caller-owned output of one column. `array.values` receives the values (PRIMITIVE /
+ * BOOLEAN) or the new offsets (BYTES, rows + 1 entries); `data` (capacity
+ * `data_capacity`) the value bytes; `data_len` is set to the bytes required/written. */
+typedef struct acu_column_out {
+  acu_array_out array;
+  uint8_t *data;
+  int64_t data_capacity;
+  int64_t data_len;
+} acu_column_out;
+
+/* filter_record_batch (filter.rs:225-244) / FilterPredicate::filter_record_batch
+ * (filter.rs:459-478): every column filtered with the same plan (the predicate is
+ * scanned once), all kernels queued back to back, one synchronisation. Columns keep
+ * their order; on error the status/detail of the first failing column is returned (the
+ * reference propagates that column's ArrowError). At most ACU_MAX_BATCH_COLUMNS columns. */
+#define ACU_MAX_BATCH_COLUMNS 64
+acu_status acu_filter_record_batch(acu_ctx *ctx, const acu_filter_plan *plan, int32_t n_columns,
+                                   const acu_column *columns, acu_column_out *outs);
+
+/* take_record_batch (take.rs:1123-1133) / take_arrays (take.rs:155-164): every column
+ * gathered with the same indices; check_bounds as in acu_take_primitive. Null counts of
+ * the columns and of the indices should be cached (>= 0); unknown ones are counted
+ * first (one extra synchronisation each). */
+acu_status acu_take_record_batch(acu_ctx *ctx, int32_t n_columns, const acu_column *columns,
+                                 const acu_array *indices, acu_dtype index_dtype, int32_t check_bounds,
+                                 acu_column_out *outs);
+
+/* sum/min/max of n columns (acu_aggregate semantics per column) with one
+ * synchronisation: dtypes[i]/ops[i] describe arrays[i]. */
+acu_status acu_aggregate_columns(acu_ctx *ctx, int32_t n_columns, const acu_dtype *dtypes,
+                                 const acu_agg_op *ops, const acu_array *arrays, uint64_t *out_bits,
+                                 int64_t *out_valid_counts);
+
+/* ------------------------------------------------------------------------- */
 /* multi-GPU: row-range shards, NCCL only for the final scalar reduce        */
 /* ------------------------------------------------------------------------- */
 #define ACU_NCCL_UNIQUE_ID_BYTES 128

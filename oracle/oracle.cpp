@@ -1160,6 +1160,10 @@ acu_status orc_take_bytes(int32_t offset_bytes, const void *offsets, const uint8
   };
   put(0, 0);
   if (m == 0) return ACU_OK;  // take_impl: new_empty_array (offsets = [0])
+  // take_nulls runs first (take.rs:509): with nulls in the values it is take_bits over the validity, whose
+  // bounds-checked BooleanBuffer::value panics on an out-of-bounds index at a valid slot (take.rs:472, :482)
+  if (nulls_of->validity && resolve_null_count(nulls_of) > 0)
+    if (acu_status st = check_panic(nulls_of->len, indices, index_dtype)) return st;
   take_nulls(nulls_of, indices, index_dtype, out_nulls);
   const int64_t limit = offset_bytes == 4 ? (int64_t)INT32_MAX : INT64_MAX;
   int64_t cap = 0;
