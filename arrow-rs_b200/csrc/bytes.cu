@@ -18,6 +18,9 @@
 #include "internal.cuh"
 
 #define SCAN_ELEMS 4096
+#define BY_THREADS 512                 // CTA of the bytes kernels: 512 threads x 4 consecutive rows,
+#define BY_ROWS (BY_THREADS * 4)       // two CTAs resident per SM so that one loads while the other assembles
+#define BY_STAGE_CAP (48 * 1024)
 #define PLAN_TILE_WORDS 64
 #define PLAN_SCAN_CHUNK 4096
 
@@ -136,10 +139,11 @@ int index_kind(acu_dtype t) {
 }
 
 // ---- fused lengths / scan / offsets / copy -------------------------------------------------
-// CTA = 1024 threads x 4 rounds of 1024 consecutive rows (SCAN_ELEMS = 4096 rows): lane l <-> row
-// l of a warp's 32-row group, so index loads, offset stores and the warp's 32 validity bits (one
-// aligned u32) are all coalesced. FAST = i32 offsets + 32-bit indices: all per-row arithmetic in
-// 32 bits.
+// CTA = BY_THREADS threads x 4 CONSECUTIVE rows (BY_ROWS rows): a thread's four indices are
+// one 128-bit load, its four new offsets one 128-bit store, its four validity bits a nibble of
+// one u32, and the CTA-wide scan runs once over per-thread sums (two barriers) instead of once
+// per row round. All eight source-offset loads of a thread are issued before any is used.
+// FAST = i32 offsets + 32-bit indices with 16-B aligned index / offset buffers.
 struct BytesArgs {
   const void *offs;        // source offsets (i32 or i64)
   const uint8_t *data;     // source value bytes
@@ -152,68 +156,204 @@ struct BytesArgs {
   int detect_oob;          // report an out-of-bounds index at a valid slot through res[RES_ERR_INDEX]
 };
 
+// Source byte range of the four rows j0 .. j0+3 (j0 % 4 == 0): begin[k], len[k] (0 for rows past the
+// end, null output slots and out-of-bounds indices, whose lowest row goes to *oob_row).
 template <bool FAST>
-__device__ __forceinline__ uint64_t row_span(const BytesArgs &a, int64_t j, bool valid, int64_t *src_begin, bool *oob) {
-  *src_begin = 0;
-  *oob = false;
-  if (j >= a.m || !valid) return 0;
-  uint64_t i;
-  if (FAST) i = __ldg(static_cast<const uint32_t *>(a.idx) + j);
-  else i = ld_index(a.idx, a.kind, j);
-  if (i >= (uint64_t)a.n_src) { *oob = true; return 0; }
-  if (FAST) {
-    const int32_t s = __ldg(static_cast<const int32_t *>(a.offs) + i), e = __ldg(static_cast<const int32_t *>(a.offs) + i + 1);
-    *src_begin = s;
-    return (uint32_t)(e - s);
+__device__ __forceinline__ void rows4(const BytesArgs &a, int64_t j0, int64_t begin[4], uint64_t len[4], unsigned long long *oob_row) {
+  uint32_t vbits = 0xFu;
+  if (a.out_valid && j0 < a.m) vbits = (__ldg(a.out_valid + (j0 >> 5)) >> (j0 & 31)) & 0xFu;
+  if constexpr (FAST) {  // 32-bit indices, i32 offsets: everything per row in 32 bits
+    uint32_t ix[4] = {0, 0, 0, 0};
+    const int rows = a.m - j0 >= 4 ? 4 : (a.m > j0 ? (int)(a.m - j0) : 0);
+    if (rows == 4) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4 *>(static_cast<const uint32_t *>(a.idx) + j0));
+      ix[0] = q.x; ix[1] = q.y; ix[2] = q.z; ix[3] = q.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k < rows) ix[k] = __ldg(static_cast<const uint32_t *>(a.idx) + j0 + k);
+    }
+    const uint32_t n32 = a.n_src > (int64_t)0xffffffffll ? 0xffffffffu : (uint32_t)a.n_src;  // n_src >= 2^32: no u32 index is out of bounds
+    const bool all_in = a.n_src > (int64_t)0xffffffffll;
+    const int32_t *offs = static_cast<const int32_t *>(a.offs);
+    int32_t s[4], e[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      bool use = (k < rows) && ((vbits >> k) & 1u);
+      if (use && !all_in && ix[k] >= n32) {
+        use = false;
+        if ((unsigned long long)(j0 + k) < *oob_row) *oob_row = (unsigned long long)(j0 + k);
+      }
+      s[k] = 0;
+      e[k] = 0;
+      if (use) {
+        s[k] = __ldg(offs + ix[k]);
+        e[k] = __ldg(offs + ix[k] + 1);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      begin[k] = s[k];
+      len[k] = (uint32_t)(e[k] - s[k]);
+    }
+    return;
   }
-  const int64_t s = ld_off(a.offs, a.ob, (int64_t)i);
-  *src_begin = s;
-  return (uint64_t)(ld_off(a.offs, a.ob, (int64_t)i + 1) - s);
+  uint64_t ix[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (j0 + k < a.m) ix[k] = ld_index(a.idx, a.kind, j0 + k);
+  bool use[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    use[k] = (j0 + k < a.m) && ((vbits >> k) & 1u);
+    if (use[k] && ix[k] >= (uint64_t)a.n_src) {
+      use[k] = false;
+      if ((unsigned long long)(j0 + k) < *oob_row) *oob_row = (unsigned long long)(j0 + k);
+    }
+  }
+  int64_t s[4], e[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {  // all loads first
+    s[k] = 0;
+    e[k] = 0;
+    if (use[k]) {
+      s[k] = ld_off(a.offs, a.ob, (int64_t)ix[k]);
+      e[k] = ld_off(a.offs, a.ob, (int64_t)ix[k] + 1);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    begin[k] = s[k];
+    len[k] = (uint64_t)(e[k] - s[k]);
+  }
 }
 
-__device__ __forceinline__ bool slot_valid(const BytesArgs &a, int64_t j, int lane) {
-  if (!a.out_valid) return true;
-  if (j - lane >= a.m) return false;
-  return (__ldg(a.out_valid + ((j - lane) >> 5)) >> lane) & 1u;  // j - lane is a multiple of 32
+// CTA-wide exclusive scan of one u64 per thread (up to 1024 threads); returns the thread's exclusive
+// prefix, *total = the CTA total. Two barriers.
+__device__ __forceinline__ uint64_t cta_scan_excl(uint64_t v, uint64_t *warp_tot /* [33] shared */, uint64_t *total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint64_t incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint64_t y = __shfl_up_sync(ACU_FULL_MASK, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) warp_tot[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    const uint64_t w = lane < (int)(blockDim.x >> 5) ? warp_tot[lane] : 0ull;
+    uint64_t wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint64_t y = __shfl_up_sync(ACU_FULL_MASK, wi, o);
+      if (lane >= o) wi += y;
+    }
+    warp_tot[lane] = wi - w;
+    if (lane == 31) warp_tot[32] = wi;
+  }
+  __syncthreads();
+  *total = warp_tot[32];
+  return warp_tot[wid] + incl - v;
 }
 
 // pass 1: total value bytes of each CTA's 4096 rows (+ out-of-bounds detection)
 template <bool FAST>
-__global__ void __launch_bounds__(1024) k_bytes_block_totals(const BytesArgs a, int64_t *__restrict__ block_tot,
+__global__ void __launch_bounds__(BY_THREADS) k_bytes_block_totals(const BytesArgs a, int64_t *__restrict__ block_tot,
                                                              unsigned long long *__restrict__ res) {
   __shared__ uint64_t warp_tot[32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int64_t base = (int64_t)blockIdx.x * SCAN_ELEMS + threadIdx.x;
-  uint64_t sum = 0;
+  const int64_t j0 = (int64_t)blockIdx.x * BY_ROWS + (int64_t)threadIdx.x * 4;
+  int64_t begin[4];
+  uint64_t len[4];
   unsigned long long err = ~0ull;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int64_t j = base + k * 1024;
-    int64_t sb;
-    bool oob;
-    sum += row_span<FAST>(a, j, slot_valid(a, j, lane), &sb, &oob);
-    if (oob && a.detect_oob && (unsigned long long)j < err) err = (unsigned long long)j;
-  }
+  rows4<FAST>(a, j0, begin, len, &err);
+  uint64_t sum = len[0] + len[1] + len[2] + len[3];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(ACU_FULL_MASK, sum, o);
   if (lane == 0) warp_tot[wid] = sum;
   __syncthreads();
   if (wid == 0) {
-    uint64_t t = warp_tot[lane];
+    uint64_t t = lane < BY_THREADS / 32 ? warp_tot[lane] : 0ull;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(ACU_FULL_MASK, t, o);
     if (lane == 0) block_tot[blockIdx.x] = (int64_t)t;
   }
-  if (err != ~0ull) atomicMin(res + RES_ERR_INDEX, err);
+  if (a.detect_oob && err != ~0ull) atomicMin(res + RES_ERR_INDEX, err);
 }
 
-// pass 2 (after the inclusive scan of the CTA totals): offsets + byte copy. Source bytes are
-// fetched 8 at a time with two aligned loads + funnel shift (ld_bits64 on a byte position): no
-// dependent byte loads. The CTA's output bytes [cta_begin, cta_end) are built in shared memory
-// laid out relative to the 16-B aligned global address and written back as whole 128-bit stores
-// (STAGED); CTAs whose output does not fit the staging buffer store bytes directly.
-template <bool FAST, bool STAGED>
-__device__ __forceinline__ void copy_row(uint8_t *__restrict__ dst, const uint8_t *__restrict__ data, int64_t src, uint64_t len) {
+// Byte stream of one thread into the CTA's staging buffer: bytes are queued in a small
+// accumulator (fewer than 4 pending bytes between pushes) and leave as whole aligned 32-bit
+// words. A word shared with a neighbouring thread (the first one when the thread's output does
+// not start on a word boundary, and the last partial one) is merged with atomicOr into the
+// zero-initialised buffer; every other word is exclusively this thread's and is stored plainly.
+// push8 is branch-free apart from the two predicated stores.
+struct WordEmitter {
+  uint32_t *w;
+  uint32_t acc;   // pending bytes (low nacc bytes valid, rest zero)
+  uint32_t nacc;  // 0..3
+  bool shared_first;
+  __device__ __forceinline__ void init(uint8_t *stage, uint32_t pos) {
+    w = reinterpret_cast<uint32_t *>(stage) + (pos >> 2);
+    nacc = pos & 3u;
+    acc = 0;
+    shared_first = nacc != 0;
+  }
+  __device__ __forceinline__ void store(uint32_t v) {
+    if (shared_first) { atomicOr(w, v); shared_first = false; }
+    else *w = v;
+    ++w;
+  }
+  // v: up to 8 bytes (bytes at positions >= nb are zero), nb in 0..8
+  __device__ __forceinline__ void push8(uint64_t v, uint32_t nb) {
+    const uint32_t sh = nacc * 8u;                       // 0, 8, 16, 24
+    const uint32_t vlo = (uint32_t)v, vhi = (uint32_t)(v >> 32);
+    const uint32_t x0 = acc | (vlo << sh);
+    const uint32_t x1 = __funnelshift_l(vlo, vhi, sh);   // (vhi:vlo << sh) >> 32
+    const uint32_t x2 = __funnelshift_l(vhi, 0u, sh);    // bytes pushed past 64 bits (zero when sh == 0)
+    const uint32_t t = nacc + nb;                        // 0..11 bytes available
+    if (t >= 4u) store(x0);
+    if (t >= 8u) store(x1);
+    acc = t >= 8u ? x2 : (t >= 4u ? x1 : x0);
+    nacc = t & 3u;
+  }
+  __device__ __forceinline__ void finish() {
+    if (acc != 0u) atomicOr(w, acc);
+  }
+};
+
+// Up to 8 bytes of data[pos .. pos+nb) (nb in 0..8) as a little-endian u64, zero above nb. Only
+// aligned 8-byte words that contain at least one requested byte are read.
+__device__ __forceinline__ uint64_t load_upto8(const uint8_t *__restrict__ data, int64_t pos, uint32_t nb) {
+  const uintptr_t addr = (uintptr_t)data + (uintptr_t)pos;
+  const uint64_t *p = reinterpret_cast<const uint64_t *>(addr & ~(uintptr_t)7);
+  const uint32_t sh = (uint32_t)(addr & 7u) * 8u;
+  uint64_t lo = 0, hi = 0;
+  if (nb) lo = __ldg(p);
+  if (sh + nb * 8u > 64u) hi = __ldg(p + 1);
+  uint64_t w = (lo >> sh) | ((hi << 1) << (63u - sh));
+  const uint64_t mask = nb >= 8u ? ~0ull : ((1ull << (nb * 8u)) - 1ull);
+  return w & mask;
+}
+
+// The first nb (0..16) bytes of data[pos ..) as two little-endian u64 (zero above nb): three aligned
+// 8-byte loads, each predicated on containing a requested byte, shared by both halves.
+__device__ __forceinline__ void load_upto16(const uint8_t *__restrict__ data, int64_t pos, uint32_t nb, uint64_t *w0, uint64_t *w1) {
+  const uintptr_t addr = (uintptr_t)data + (uintptr_t)pos;
+  const uint64_t *p = reinterpret_cast<const uint64_t *>(addr & ~(uintptr_t)7);
+  const uint32_t sh = (uint32_t)(addr & 7u) * 8u, bits = sh + nb * 8u;
+  uint64_t x = 0, y = 0, z = 0;
+  if (nb) x = __ldg(p);
+  if (bits > 64u) y = __ldg(p + 1);
+  if (bits > 128u) z = __ldg(p + 2);
+  const uint64_t lo = (x >> sh) | ((y << 1) << (63u - sh));
+  const uint64_t hi = (y >> sh) | ((z << 1) << (63u - sh));
+  const uint32_t n0 = nb < 8u ? nb : 8u, n1 = nb - n0;
+  *w0 = lo & (n0 >= 8u ? ~0ull : ((1ull << (n0 * 8u)) - 1ull));
+  *w1 = hi & (n1 >= 8u ? ~0ull : ((1ull << (n1 * 8u)) - 1ull));
+}
+
+template <bool STAGED>
+__device__ __forceinline__ void copy_row_direct(uint8_t *__restrict__ dst, const uint8_t *__restrict__ data, int64_t src, uint64_t len) {
   for (uint64_t c = 0; c < len; c += 8) {
     const uint64_t w = ld_bits64(data, (src + (int64_t)c) << 3, (src + (int64_t)len) << 3);
     const int nb = (int)((len - c) < 8 ? (len - c) : 8);
@@ -223,94 +363,115 @@ __device__ __forceinline__ void copy_row(uint8_t *__restrict__ dst, const uint8_
   }
 }
 
+// pass 2 (after the inclusive scan of the CTA totals): offsets + byte copy. Source bytes are
+// fetched 8 at a time with two aligned loads + funnel shift (ld_bits64 on a byte position). The
+// CTA's output bytes [cta_begin, cta_end) are assembled in shared memory laid out relative to the
+// 16-B aligned global address and written back as whole 128-bit stores (STAGED); CTAs whose
+// output does not fit the staging buffer store bytes directly.
 template <bool FAST>
-__global__ void __launch_bounds__(1024) k_bytes_offsets_copy(const BytesArgs a, const int64_t *__restrict__ block_incl,
+__global__ void __launch_bounds__(BY_THREADS, 2) k_bytes_offsets_copy(const BytesArgs a, const int64_t *__restrict__ block_incl,
                                                              int64_t first_block, void *out_offs, uint8_t *__restrict__ out_data,
                                                              int64_t limit, int64_t probe_row, unsigned long long *res,
                                                              int stage_cap, const int64_t *__restrict__ total_ptr, int64_t out_cap) {
   extern __shared__ __align__(16) uint8_t s_out[];
-  // the byte copy is skipped (CTA-uniformly, grid-uniformly) when the total does not fit the
-  // caller's buffer or the offset type: decided on the device so that no host round trip sits
-  // between the sizing pass and this one
+  __shared__ uint64_t warp_tot[33];
+  // the byte copy is skipped (grid-uniformly) when the total does not fit the caller's buffer or
+  // the offset type: decided on the device so that no host round trip sits between the sizing
+  // pass and this one
   if (out_data != nullptr && total_ptr != nullptr) {
     const int64_t total = __ldg(total_ptr);
     if (total > out_cap || total > limit) out_data = nullptr;
   }
-  __shared__ uint64_t warp_tot[33];
   const int64_t blk = first_block + blockIdx.x;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t cta_begin = blk ? block_incl[blk - 1] : 0, cta_end = block_incl[blk];
   const int64_t stage_origin = cta_begin - (int64_t)((uintptr_t)(out_data + cta_begin) & 15);  // global byte that maps to s_out[0]
   const bool staged = out_data != nullptr && probe_row < 0 && (cta_end - stage_origin) <= (int64_t)stage_cap;
-  uint64_t running = 0;  // bytes of the previous rounds, relative to cta_begin
+  const uint32_t nbytes = staged ? (uint32_t)(cta_end - stage_origin) : 0u;  // staged span, starts 16-B aligned in global memory
+  const uint32_t lead = (uint32_t)(cta_begin - stage_origin);                // bytes of the first chunk owned by the previous CTA
+  if (staged) {  // zero the words the emitters OR into
+    const uint32_t chunks = (nbytes + 15) >> 4;
+    for (uint32_t c = threadIdx.x; c < chunks; c += BY_THREADS) reinterpret_cast<uint4 *>(s_out)[c] = make_uint4(0, 0, 0, 0);
+  }
+  const int64_t j0 = blk * BY_ROWS + (int64_t)threadIdx.x * 4;
+  int64_t begin[4];
+  uint64_t len[4];
+  unsigned long long oob = ~0ull;
+  rows4<FAST>(a, j0, begin, len, &oob);
+  uint64_t cta_total;
+  const uint64_t rel = cta_scan_excl(len[0] + len[1] + len[2] + len[3], warp_tot, &cta_total);  // also orders the zeroing before the emitters
+  int64_t end[4];
+  end[0] = cta_begin + (int64_t)(rel + len[0]);
+  end[1] = end[0] + (int64_t)len[1];
+  end[2] = end[1] + (int64_t)len[2];
+  end[3] = end[2] + (int64_t)len[3];
   unsigned long long err = ~0ull;
-  for (int k = 0; k < 4; ++k) {
-    const int64_t j = blk * SCAN_ELEMS + k * 1024 + threadIdx.x;
-    int64_t src;
-    bool oob;
-    const uint64_t len = row_span<FAST>(a, j, slot_valid(a, j, lane), &src, &oob);
-    uint64_t incl = len;
-    if (FAST) {  // a CTA's 4096 rows of an i32-offset array never exceed 2^31 bytes... per row; sums fit 44 bits: scan in 64 but shuffle cheaply
-      uint32_t lo = (uint32_t)len;  // FAST lengths fit 32 bits; a round's total (1024 rows) may not -> widen after the warp scan
-      uint64_t acc = lo;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint64_t y = __shfl_up_sync(ACU_FULL_MASK, acc, o);
-        if (lane >= o) acc += y;
-      }
-      incl = acc;
-    } else {
+  for (int k = 3; k >= 0; --k)
+    if (j0 + k < a.m && end[k] > limit) err = (unsigned long long)(j0 + k);
+  if (probe_row >= 0) {
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint64_t y = __shfl_up_sync(ACU_FULL_MASK, incl, o);
-        if (lane >= o) incl += y;
-      }
-    }
-    __syncthreads();  // warp_tot of the previous round has been consumed
-    if (lane == 31) warp_tot[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-      uint64_t w = warp_tot[lane], wi = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint64_t y = __shfl_up_sync(ACU_FULL_MASK, wi, o);
-        if (lane >= o) wi += y;
-      }
-      warp_tot[lane] = wi - w;
-      if (lane == 31) warp_tot[32] = wi;  // round total
-    }
-    __syncthreads();
-    const uint64_t rel = running + warp_tot[wid] + incl - len;  // first output byte of this row, relative to cta_begin
-    running += warp_tot[32];
-    if (j < a.m) {
-      const int64_t end = cta_begin + (int64_t)(rel + len);
-      if (end > limit && (unsigned long long)j < err) err = (unsigned long long)j;
-      if (j == probe_row) res[RES_AUX1] = (unsigned long long)end;
-      if (probe_row < 0) {
-        if (a.ob == 4) static_cast<int32_t *>(out_offs)[j + 1] = (int32_t)end;
-        else static_cast<int64_t *>(out_offs)[j + 1] = end;
-        if (j == 0) { if (a.ob == 4) static_cast<int32_t *>(out_offs)[0] = 0; else static_cast<int64_t *>(out_offs)[0] = 0; }
-        if (out_data && len) {
-          if (staged) copy_row<FAST, true>(s_out + (uint32_t)(cta_begin - stage_origin + (int64_t)rel), a.data, src, len);
-          else copy_row<FAST, false>(out_data + cta_begin + (int64_t)rel, a.data, src, len);
-        }
-      }
-    }
+    for (int k = 0; k < 4; ++k)
+      if (probe_row == j0 + k) res[RES_AUX1] = (unsigned long long)end[k];
+    return;
   }
   if (err != ~0ull) atomicMin(res + RES_ERR2, err);
-  if (staged) {  // CTA-uniform
+  // new offsets: out[j0] = end of the previous row, out[j0+1..j0+3] = the first three ends (one aligned 128-bit store);
+  // the thread holding the last row also writes out[m]
+  if (j0 <= a.m) {
+    const int64_t first = cta_begin + (int64_t)rel;
+    if (FAST && j0 + 3 <= a.m && ((uintptr_t)out_offs & 15) == 0) {
+      *reinterpret_cast<int4 *>(static_cast<int32_t *>(out_offs) + j0) = make_int4((int32_t)first, (int32_t)end[0], (int32_t)end[1], (int32_t)end[2]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (j0 + k <= a.m) {
+          const int64_t v = k == 0 ? first : end[k - 1];
+          if (a.ob == 4) static_cast<int32_t *>(out_offs)[j0 + k] = (int32_t)v;
+          else static_cast<int64_t *>(out_offs)[j0 + k] = v;
+        }
+    }
+    if (j0 + 4 == a.m) {
+      if (a.ob == 4) static_cast<int32_t *>(out_offs)[a.m] = (int32_t)end[3];
+      else static_cast<int64_t *>(out_offs)[a.m] = end[3];
+    }
+  }
+  if (out_data == nullptr) return;  // grid-uniform
+  if (staged) {
+    WordEmitter em;
+    em.init(s_out, lead + (uint32_t)rel);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      // the first 16 bytes of every row without branches (short strings are the common case) ...
+      const uint32_t l32 = len[k] > 16 ? 16u : (uint32_t)len[k];
+      const uint32_t n0 = l32 < 8u ? l32 : 8u, n1 = l32 - n0;
+      uint64_t w0, w1;
+      load_upto16(a.data, begin[k], l32, &w0, &w1);
+      em.push8(w0, n0);
+      em.push8(w1, n1);
+      // ... the rest of a long row 8 bytes at a time
+      for (uint64_t c = 16; c < len[k]; c += 8) {
+        const uint32_t nb = (uint32_t)((len[k] - c) < 8 ? (len[k] - c) : 8);
+        em.push8(load_upto8(a.data, begin[k] + (int64_t)c, nb), nb);
+      }
+    }
+    em.finish();
     __syncthreads();
-    const uint32_t nbytes = (uint32_t)(cta_end - stage_origin);  // staged span, starts 16-B aligned in global memory
-    const uint32_t lead = (uint32_t)(cta_begin - stage_origin);  // bytes of the first chunk owned by the previous CTA
     uint8_t *g = out_data + stage_origin;
     const uint32_t chunks = (nbytes + 15) >> 4;
-    for (uint32_t c = threadIdx.x; c < chunks; c += 1024) {
+    for (uint32_t c = threadIdx.x; c < chunks; c += BY_THREADS) {
       const uint32_t b0 = c << 4;
       if (b0 >= lead && b0 + 16 <= nbytes) {
         *reinterpret_cast<uint4 *>(g + b0) = *reinterpret_cast<const uint4 *>(s_out + b0);
       } else {  // partial first / last chunk: only this CTA's bytes
         for (uint32_t x = b0 < lead ? lead : b0; x < b0 + 16 && x < nbytes; ++x) g[x] = s_out[x];
       }
+    }
+  } else {
+    int64_t pos = cta_begin + (int64_t)rel;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (len[k]) copy_row_direct<false>(out_data + pos, a.data, begin[k], len[k]);
+      pos += (int64_t)len[k];
     }
   }
 }
@@ -331,17 +492,17 @@ struct GatherState {
 };
 
 size_t gather_scratch_bytes(int64_t m) {
-  const int64_t blocks = (m + SCAN_ELEMS - 1) / SCAN_ELEMS;
+  const int64_t blocks = (m + BY_ROWS - 1) / BY_ROWS;
   return (((size_t)(2 * blocks + blocks / SCAN_ELEMS + 4096) * 8) + 255) & ~(size_t)255;
 }
 
 acu_status gather_launch(acu_ctx *ctx, int32_t ob, const void *offsets, const uint8_t *data, const void *idx, int kind,
                          int64_t m, int64_t n_src, const uint8_t *out_valid, bool detect_oob, void *out_offsets,
                          uint8_t *out_data, int64_t out_cap, void *scratch, unsigned long long *res, GatherState *gs) {
-  const int64_t blocks = (m + SCAN_ELEMS - 1) / SCAN_ELEMS;
+  const int64_t blocks = (m + BY_ROWS - 1) / BY_ROWS;
   int64_t *block_tot = static_cast<int64_t *>(scratch);
   BytesArgs a{offsets, data, idx, kind, (int)ob, m, n_src, reinterpret_cast<const uint32_t *>(out_valid), detect_oob ? 1 : 0};
-  const bool fast = ob == 4 && kind == 4 && ((uintptr_t)idx % 4 == 0);
+  const bool fast = ob == 4 && kind == 4 && ((uintptr_t)idx % 16 == 0) && ((uintptr_t)offsets % 4 == 0);
   gs->a = a;
   gs->blocks = blocks;
   gs->block_tot = block_tot;
@@ -350,21 +511,21 @@ acu_status gather_launch(acu_ctx *ctx, int32_t ob, const void *offsets, const ui
   gs->out_cap = out_cap;
   gs->limit = ob == 4 ? (int64_t)INT32_MAX : INT64_MAX;
   gs->detect_oob = detect_oob;
-  if (fast) ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_block_totals<true>, (unsigned)blocks, 1024, 0, a, block_tot, res);
-  else ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_block_totals<false>, (unsigned)blocks, 1024, 0, a, block_tot, res);
+  if (fast) ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_block_totals<true>, (unsigned)blocks, BY_THREADS, 0, a, block_tot, res);
+  else ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_block_totals<false>, (unsigned)blocks, BY_THREADS, 0, a, block_tot, res);
   ACU_TRY(scan_inclusive(ctx, block_tot, blocks, block_tot + blocks));
   ACU_CUDA(ctx, cudaMemcpyAsync(res + RES_AUX0, block_tot + (blocks - 1), 8, cudaMemcpyDeviceToDevice, ctx->stream));
-  const int stage_cap = 64 * 1024;
+  const int stage_cap = BY_STAGE_CAP;
   a.detect_oob = 0;
   static bool attr_set[2] = {false, false};  // per process is enough: the attribute is per function, per device context
   (void)attr_set;
   if (fast) {
     ACU_CUDA(ctx, cudaFuncSetAttribute(k_bytes_offsets_copy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_cap));
-    ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_offsets_copy<true>, (unsigned)blocks, 1024, stage_cap, a, block_tot, (int64_t)0, out_offsets,
+    ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_offsets_copy<true>, (unsigned)blocks, BY_THREADS, stage_cap, a, block_tot, (int64_t)0, out_offsets,
                      out_data, gs->limit, (int64_t)-1, res, stage_cap, block_tot + (blocks - 1), out_cap);
   } else {
     ACU_CUDA(ctx, cudaFuncSetAttribute(k_bytes_offsets_copy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_cap));
-    ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_offsets_copy<false>, (unsigned)blocks, 1024, stage_cap, a, block_tot, (int64_t)0, out_offsets,
+    ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_offsets_copy<false>, (unsigned)blocks, BY_THREADS, stage_cap, a, block_tot, (int64_t)0, out_offsets,
                      out_data, gs->limit, (int64_t)-1, res, stage_cap, block_tot + (blocks - 1), out_cap);
   }
   return ACU_OK;
@@ -383,7 +544,7 @@ acu_status gather_finalize(acu_ctx *ctx, const GatherState &gs, const unsigned l
     BytesArgs a = gs.a;
     a.detect_oob = 0;
     ACU_TRY(acu_res_reset(ctx));
-    ACU_LAUNCH(ctx, k_bytes_offsets_copy<false>, 1, 1024, 0, a, gs.block_tot, j / SCAN_ELEMS, gs.out_offsets, static_cast<uint8_t *>(nullptr),
+    ACU_LAUNCH(ctx, k_bytes_offsets_copy<false>, 1, BY_THREADS, 0, a, gs.block_tot, j / BY_ROWS, gs.out_offsets, static_cast<uint8_t *>(nullptr),
                INT64_MAX, j, ctx->d_res, 0, static_cast<const int64_t *>(nullptr), (int64_t)0);
     ACU_TRY(acu_res_fetch(ctx));
     const long long cap = (long long)ctx->h_res[RES_AUX1];
@@ -461,16 +622,18 @@ void acu_bytes_col_state_free(acu_bytes_col_state *s) { delete s; }
 acu_status acu_take_bytes_col_launch(acu_ctx *ctx, int32_t ob, const void *offsets, const uint8_t *data, const acu_array *nulls_of,
                                      bool val_nulls, const acu_array *indices, acu_dtype index_dtype, bool idx_nulls,
                                      void *out_offsets, uint8_t *out_data, int64_t out_cap, acu_array_out *out_nulls, void *scratch,
-                                     unsigned long long *res, acu_bytes_col_state *st) {
+                                     unsigned long long *res, acu_bytes_col_state *st, int nulls_mode) {
   *st = acu_bytes_col_state();
   if (ob != 4 && ob != 8) return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "offset width must be 4 or 8");
   const int kind = index_kind(index_dtype);
   if (kind < 0)  // take.rs:103
     return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "Take only supported for integers, got %s", acu_dtype_name(index_dtype));
   const int64_t m = indices->len;
-  out_nulls->len = m;
-  out_nulls->has_validity = 0;
-  out_nulls->null_count = 0;
+  if (nulls_mode < 0) {
+    out_nulls->len = m;
+    out_nulls->has_validity = 0;
+    out_nulls->null_count = 0;
+  }
   if (m == 0) return zero_first_offset(ctx, out_offsets, ob);
   const uint8_t *ov = nullptr;
   bool detect_oob;
@@ -485,7 +648,8 @@ acu_status acu_take_bytes_col_launch(acu_ctx *ctx, int32_t ob, const void *offse
     }
     detect_oob = true;
   } else {
-    ACU_TRY(acu_take_col_launch(ctx, 0, nulls_of, false, true, indices, index_dtype, idx_nulls, out_nulls, res, &st->take_mode));
+    if (nulls_mode >= 0) st->take_mode = nulls_mode;  // the validity gather was queued by the record-batch driver
+    else ACU_TRY(acu_take_col_launch(ctx, 0, nulls_of, false, true, indices, index_dtype, idx_nulls, out_nulls, res, &st->take_mode));
     st->nulls_kind = 2;
     if (st->take_mode & 1) ov = out_nulls->validity;
     detect_oob = false;  // the take kernel reports it
@@ -544,7 +708,7 @@ extern "C" acu_status acu_take_bytes(acu_ctx *ctx, int32_t offset_bytes, const v
   acu_bytes_col_state st;
   ACU_TRY(acu_res_reset(ctx));
   ACU_TRY(acu_take_bytes_col_launch(ctx, offset_bytes, offsets, data, nulls_of, nulls_of->validity && vnc > 0, indices, index_dtype, idx_nulls,
-                                    out_offsets, out_data, out_data_capacity, out_nulls, scratch, acu_dres(ctx, 0), &st));
+                                    out_offsets, out_data, out_data_capacity, out_nulls, scratch, acu_dres(ctx, 0), &st, -1));
   ACU_TRY(acu_res_fetch(ctx));
   return acu_take_bytes_col_finalize(ctx, nulls_of, indices, index_dtype, &st, acu_hres(ctx, 0), out_data_len, out_nulls);
 }
@@ -552,12 +716,15 @@ extern "C" acu_status acu_take_bytes(acu_ctx *ctx, int32_t offset_bytes, const v
 // ---- one variable-width column of filter / filter_record_batch ---------------------------------
 acu_status acu_filter_bytes_col_launch(acu_ctx *ctx, const acu_filter_plan *plan, int32_t ob, const void *offsets, const uint8_t *data,
                                        const acu_array *nulls_of, void *out_offsets, uint8_t *out_data, int64_t out_cap,
-                                       acu_array_out *out_nulls, void *scratch, unsigned long long *res, acu_bytes_col_state *st) {
+                                       acu_array_out *out_nulls, void *scratch, unsigned long long *res, acu_bytes_col_state *st,
+                                       int nulls_mode) {
   *st = acu_bytes_col_state();
   if (ob != 4 && ob != 8) return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "offset width must be 4 or 8");
   const int64_t count = acu_filter_plan_count(plan);
-  // nulls first (FilterPredicate::filter_nulls); also validates the predicate length
-  ACU_TRY(acu_filter_col_launch(ctx, plan, 2, 0, nulls_of, out_nulls, res, &st->take_mode));
+  // nulls first (FilterPredicate::filter_nulls); also validates the predicate length. nulls_mode >= 0: already queued by
+  // the record-batch driver together with the other columns' validity compactions.
+  if (nulls_mode >= 0) st->take_mode = nulls_mode;
+  else ACU_TRY(acu_filter_col_launch(ctx, plan, 2, 0, nulls_of, out_nulls, res, &st->take_mode));
   st->nulls_kind = 3;
   if (count == 0) return zero_first_offset(ctx, out_offsets, ob);
   const void *idx;
@@ -590,7 +757,7 @@ extern "C" acu_status acu_filter_bytes(acu_ctx *ctx, const acu_filter_plan *plan
   acu_bytes_col_state st;
   ACU_TRY(acu_res_reset(ctx));
   ACU_TRY(acu_filter_bytes_col_launch(ctx, plan, offset_bytes, offsets, data, nulls_of, out_offsets, out_data, out_data_capacity, out_nulls,
-                                      scratch, acu_dres(ctx, 0), &st));
+                                      scratch, acu_dres(ctx, 0), &st, -1));
   ACU_TRY(acu_res_fetch(ctx));
   return acu_filter_bytes_col_finalize(ctx, plan, nulls_of, &st, acu_hres(ctx, 0), out_data_len, out_nulls);
 }

@@ -22,6 +22,8 @@
 //             window assembles output words (atomicOr only on the two boundary words), and
 //             the popcount gives filter_nulls' null count. Also used for boolean VALUES
 //             (filter_bits / filter_boolean).
+#include <vector>
+
 #include "bitmap.cuh"
 #include "internal.cuh"
 
@@ -161,8 +163,14 @@ struct FilterArgs {
   int aligned16;
 };
 
+// Up to BATCH_COLS columns per launch: blockIdx.y selects the column (all columns of a record batch share the plan,
+// hence the grid.x size), so a filter_record_batch costs one launch per element width instead of one per column.
+constexpr int BATCH_COLS = 8;
+struct FilterBatch { FilterArgs col[BATCH_COLS]; };
+
 template <int W>
-__global__ void __launch_bounds__(256, 4) k_filter_values(const FilterArgs a) {
+__global__ void __launch_bounds__(256, 4) k_filter_values(const FilterBatch batch) {
+  const FilterArgs &a = batch.col[blockIdx.y];
   constexpr int CPT = TILE_ROWS * W / 16;   // 16-byte chunks per tile
   constexpr int ITERS = CPT / 32;           // chunk rounds per warp
   constexpr int BATCH = ITERS < 8 ? ITERS : 8;
@@ -290,7 +298,8 @@ template <int W> struct AsyncCfg {
 };
 
 template <int W>
-__global__ void __launch_bounds__(256) k_filter_values_async(const FilterArgs a) {
+__global__ void __launch_bounds__(256) k_filter_values_async(const FilterBatch batch) {
+  const FilterArgs &a = batch.col[blockIdx.y];
   using C = AsyncCfg<W>;
   constexpr int RPC = W <= 16 ? 16 / W : 1;
   constexpr int CPR = W <= 16 ? 1 : W / 16;
@@ -389,10 +398,29 @@ __global__ void __launch_bounds__(256) k_filter_values_async(const FilterArgs a)
 
 // ---- bit compaction (validity / boolean values): software PEXT --------------------------
 // One lane per mask word; a warp covers 32 consecutive words (two tiles).
-__global__ void __launch_bounds__(256) k_compress_bits(const uint8_t *__restrict__ src, int64_t soff, int64_t len,
-                                                       const uint64_t *__restrict__ mask,
-                                                       const uint64_t *__restrict__ tile_off, int64_t n_words_padded,
-                                                       uint32_t *__restrict__ out, unsigned long long *__restrict__ res) {
+struct CompressArgs {
+  const uint8_t *src;       // bitmap to compact (validity or boolean values)
+  int64_t soff;             // its bit offset
+  uint32_t *out;            // compacted bits (bit offset 0), zeroed by k_zero_outputs
+  unsigned long long *res;  // result block for the popcount, or NULL
+  uint64_t out_bytes;       // bytes of `out` to zero
+};
+struct CompressBatch { CompressArgs col[BATCH_COLS]; };
+
+// zero the outputs of a compress batch (the compaction ORs into boundary words)
+__global__ void __launch_bounds__(256) k_zero_outputs(const CompressBatch batch) {
+  const CompressArgs &c = batch.col[blockIdx.y];
+  uint64_t *o = reinterpret_cast<uint64_t *>(c.out);  // bitmaps are whole u64 words (acu_bitmap_bytes)
+  const uint64_t words = c.out_bytes >> 3;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (uint64_t)gridDim.x * blockDim.x) o[i] = 0ull;
+}
+
+__global__ void __launch_bounds__(256) k_compress_bits(const CompressBatch batch, int64_t len, const uint64_t *__restrict__ mask,
+                                                       const uint64_t *__restrict__ tile_off, int64_t n_words_padded) {
+  const uint8_t *__restrict__ src = batch.col[blockIdx.y].src;
+  const int64_t soff = batch.col[blockIdx.y].soff;
+  uint32_t *__restrict__ out = batch.col[blockIdx.y].out;
+  unsigned long long *__restrict__ res = batch.col[blockIdx.y].res;
   __shared__ uint32_t s_win[8][68];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -468,28 +496,63 @@ acu_status check_len(acu_ctx *ctx, const acu_filter_plan *plan, int64_t values_l
 }
 
 template <int W>
-acu_status launch_filter(acu_ctx *ctx, const FilterArgs &fa) {
+acu_status launch_filter(acu_ctx *ctx, const FilterBatch &fb, int n_cols) {
+  const FilterArgs &fa = fb.col[0];
   if (fa.aligned16) {
     constexpr size_t smem = 8 * (size_t)AsyncCfg<W>::PASS_BYTES;  // 8 warps x per-warp landing buffer
     if (ctx->occupancy.find(reinterpret_cast<const void *>(k_filter_values_async<W>)) == ctx->occupancy.end())  // first use on this device
       ACU_CUDA(ctx, cudaFuncSetAttribute(k_filter_values_async<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ACU_LAUNCH_TIMED(ctx, ACU_K_FILTER, (k_filter_values_async<W>),
-                     acu_wave_grid(ctx, k_filter_values_async<W>, 256, smem, (fa.n_tiles + 7) / 8), 256, smem, fa);
+    const int gx = acu_wave_grid(ctx, k_filter_values_async<W>, 256, smem, (fa.n_tiles + 7) / 8);
+    ACU_LAUNCH_TIMED(ctx, ACU_K_FILTER, (k_filter_values_async<W>), dim3(gx, n_cols), 256, smem, fb);
   } else {
-    ACU_LAUNCH_TIMED(ctx, ACU_K_FILTER, (k_filter_values<W>), acu_wave_grid(ctx, k_filter_values<W>, 256, 0, (fa.n_tiles + 7) / 8),
-                     256, 0, fa);
+    const int gx = acu_wave_grid(ctx, k_filter_values<W>, 256, 0, (fa.n_tiles + 7) / 8);
+    ACU_LAUNCH_TIMED(ctx, ACU_K_FILTER, (k_filter_values<W>), dim3(gx, n_cols), 256, 0, fb);
   }
   return ACU_OK;
 }
 
-// out (zeroed by this call) = bits of `src` selected by the plan; optional popcount into res.
-acu_status launch_compress(acu_ctx *ctx, const acu_filter_plan *plan, const uint8_t *src, int64_t soff, uint8_t *out,
-                           unsigned long long *res) {
+acu_status launch_filter_width(acu_ctx *ctx, int32_t elem_bytes, const FilterBatch &fb, int n_cols) {
+  switch (elem_bytes) {
+    case 1: return launch_filter<1>(ctx, fb, n_cols);
+    case 2: return launch_filter<2>(ctx, fb, n_cols);
+    case 4: return launch_filter<4>(ctx, fb, n_cols);
+    case 8: return launch_filter<8>(ctx, fb, n_cols);
+    case 16: return launch_filter<16>(ctx, fb, n_cols);
+    case 32: return launch_filter<32>(ctx, fb, n_cols);
+    default:
+      return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "filter: unsupported element width %d", elem_bytes);
+  }
+}
+
+// out (zeroed here) = bits of each `src` selected by the plan; optional popcounts into the columns' result blocks.
+acu_status launch_compress(acu_ctx *ctx, const acu_filter_plan *plan, const CompressBatch &cb, int n_cols) {
   const int64_t n_words_padded = ((plan->n_tiles * TILE_WORDS + 31) / 32) * 32;
-  ACU_CUDA(ctx, cudaMemsetAsync(out, 0, acu_bitmap_bytes(plan->count), ctx->stream));
-  ACU_LAUNCH_TIMED(ctx, ACU_K_FILTER, k_compress_bits, acu_wave_grid(ctx, k_compress_bits, 256, 0, (n_words_padded / 32 + 7) / 8),
-                   256, 0, src, soff, plan->len, plan->mask, plan->tile_off, n_words_padded, reinterpret_cast<uint32_t *>(out), res);
+  const int64_t words = (int64_t)acu_bitmap_bytes(plan->count) / 8;
+  ACU_LAUNCH(ctx, k_zero_outputs, dim3(acu_grid(ctx, (words + 255) / 256, 4), n_cols), 256, 0, cb);
+  const int gx = acu_wave_grid(ctx, k_compress_bits, 256, 0, (n_words_padded / 32 + 7) / 8);
+  ACU_LAUNCH_TIMED(ctx, ACU_K_FILTER, k_compress_bits, dim3(gx, n_cols), 256, 0, cb, plan->len, plan->mask, plan->tile_off, n_words_padded);
   return ACU_OK;
+}
+
+CompressArgs compress_args(const acu_filter_plan *plan, const uint8_t *src, int64_t soff, void *out, unsigned long long *res) {
+  CompressArgs c;
+  c.src = src;
+  c.soff = soff;
+  c.out = static_cast<uint32_t *>(out);
+  c.res = res;
+  c.out_bytes = acu_bitmap_bytes(plan->count);
+  return c;
+}
+
+FilterArgs filter_args(const acu_filter_plan *plan, const acu_array *values, acu_array_out *out) {
+  FilterArgs fa{};
+  fa.values = static_cast<const uint8_t *>(values->values);
+  fa.out = static_cast<uint8_t *>(out->values);
+  fa.mask = plan->mask;
+  fa.tile_off = plan->tile_off;
+  fa.n_tiles = plan->n_tiles;
+  fa.aligned16 = ((uintptr_t)values->values % 16) == 0;
+  return fa;
 }
 
 }  // namespace
@@ -618,32 +681,73 @@ acu_status acu_filter_col_launch(acu_ctx *ctx, const acu_filter_plan *plan, int 
     return ACU_OK;
   }
   if (kind == 0) {
-    FilterArgs fa{};
-    fa.values = static_cast<const uint8_t *>(values->values);
-    fa.out = static_cast<uint8_t *>(out->values);
-    fa.mask = plan->mask;
-    fa.tile_off = plan->tile_off;
-    fa.n_tiles = plan->n_tiles;
-    fa.aligned16 = ((uintptr_t)values->values % 16) == 0;
-    switch (elem_bytes) {
-      case 1: ACU_TRY(launch_filter<1>(ctx, fa)); break;
-      case 2: ACU_TRY(launch_filter<2>(ctx, fa)); break;
-      case 4: ACU_TRY(launch_filter<4>(ctx, fa)); break;
-      case 8: ACU_TRY(launch_filter<8>(ctx, fa)); break;
-      case 16: ACU_TRY(launch_filter<16>(ctx, fa)); break;
-      case 32: ACU_TRY(launch_filter<32>(ctx, fa)); break;
-      default:
-        return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "filter: unsupported element width %d", elem_bytes);
-    }
-  } else if (kind == 1) {
-    ACU_TRY(launch_compress(ctx, plan, static_cast<const uint8_t *>(values->values), values->values_offset,
-                            static_cast<uint8_t *>(out->values), nullptr));
+    FilterBatch fb{};
+    fb.col[0] = filter_args(plan, values, out);
+    ACU_TRY(launch_filter_width(ctx, elem_bytes, fb, 1));
   }
+  CompressBatch cb{};
+  int nc = 0;
+  if (kind == 1)
+    cb.col[nc++] = compress_args(plan, static_cast<const uint8_t *>(values->values), values->values_offset, out->values, nullptr);
   if (has_nulls) {  // FilterPredicate::filter_nulls (filter.rs:512-533)
-    ACU_TRY(launch_compress(ctx, plan, values->validity, values->validity_offset, out->validity, res));
+    cb.col[nc++] = compress_args(plan, values->validity, values->validity_offset, out->validity, res);
     *mode = 1;
   }
+  if (nc) ACU_TRY(launch_compress(ctx, plan, cb, nc));
   return ACU_OK;
+}
+
+// All columns of a record batch (kinds[c]: 0 primitive, 1 boolean, 2 validity only): the same work as
+// acu_filter_col_launch per column, but the value kernels of equal-width columns and all the bit compactions
+// share launches (blockIdx.y = column). res_block(c) = result block of column c.
+acu_status acu_filter_cols_launch(acu_ctx *ctx, const acu_filter_plan *plan, int n, const int *kinds, const int32_t *widths,
+                                  const acu_array *const *values, acu_array_out *const *outs, unsigned long long *const *res, int *modes) {
+  for (int c = 0; c < n; ++c) {
+    modes[c] = 0;
+    ACU_TRY(check_len(ctx, plan, values[c]->len));
+    outs[c]->len = plan->count;
+    outs[c]->has_validity = 0;
+    outs[c]->null_count = 0;
+  }
+  if (plan->strategy == ACU_FILTER_NONE || plan->count == 0) return ACU_OK;
+  if (plan->strategy == ACU_FILTER_ALL) {  // slices: per column
+    for (int c = 0; c < n; ++c) ACU_TRY(acu_filter_col_launch(ctx, plan, kinds[c], widths[c], values[c], outs[c], res[c], &modes[c]));
+    return ACU_OK;
+  }
+  // value kernels grouped by (element width, alignment class)
+  std::vector<char> done(n, 0);
+  for (int c = 0; c < n; ++c) {
+    if (kinds[c] != 0 || done[c]) continue;
+    FilterBatch fb{};
+    int k = 0;
+    const int al = ((uintptr_t)values[c]->values % 16) == 0;
+    for (int d = c; d < n && k < BATCH_COLS; ++d) {
+      if (kinds[d] != 0 || done[d] || widths[d] != widths[c] || (((uintptr_t)values[d]->values % 16) == 0) != al) continue;
+      fb.col[k++] = filter_args(plan, values[d], outs[d]);
+      done[d] = 1;
+    }
+    ACU_TRY(launch_filter_width(ctx, widths[c], fb, k));
+  }
+  // bit compactions: boolean values and every validity buffer that may hold nulls
+  CompressBatch cb{};
+  int k = 0;
+  auto flush = [&]() -> acu_status {
+    if (k) ACU_TRY(launch_compress(ctx, plan, cb, k));
+    k = 0;
+    return ACU_OK;
+  };
+  for (int c = 0; c < n; ++c) {
+    if (kinds[c] == 1) {
+      cb.col[k++] = compress_args(plan, static_cast<const uint8_t *>(values[c]->values), values[c]->values_offset, outs[c]->values, nullptr);
+      if (k == BATCH_COLS) ACU_TRY(flush());
+    }
+    if (values[c]->validity != nullptr && values[c]->null_count != 0) {
+      cb.col[k++] = compress_args(plan, values[c]->validity, values[c]->validity_offset, outs[c]->validity, res[c]);
+      modes[c] = 1;
+      if (k == BATCH_COLS) ACU_TRY(flush());
+    }
+  }
+  return flush();
 }
 
 void acu_filter_col_finalize(const acu_filter_plan *plan, const acu_array *values, int mode,

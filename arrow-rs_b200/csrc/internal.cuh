@@ -36,7 +36,8 @@ acu_status acu_take_col_finalize(acu_ctx *ctx, const acu_array *values, const ac
 acu_status acu_take_check_bounds(acu_ctx *ctx, const acu_array *indices, acu_dtype index_dtype, bool idx_nulls, int64_t values_len);
 int acu_take_index_kind(acu_dtype t);  // -1 for non-integer index types
 
-// Variable-width columns (bytes.cu), same launch / finalize split. `scratch` must hold
+// Variable-width columns (bytes.cu), same launch / finalize split. nulls_mode < 0: the column's validity work is queued
+// here; >= 0: it was queued by the record-batch driver (acu_filter_cols_launch / acu_take_cols_launch) with that mode. `scratch` must hold
 // acu_bytes_col_scratch(output rows) bytes and stay untouched until the stream has drained.
 struct acu_bytes_col_state;
 acu_bytes_col_state *acu_bytes_col_state_new();
@@ -46,13 +47,14 @@ acu_status acu_plan_cached_indices(acu_ctx *ctx, const acu_filter_plan *plan, co
 acu_status acu_take_bytes_col_launch(acu_ctx *ctx, int32_t ob, const void *offsets, const uint8_t *data, const acu_array *nulls_of,
                                      bool val_nulls, const acu_array *indices, acu_dtype index_dtype, bool idx_nulls,
                                      void *out_offsets, uint8_t *out_data, int64_t out_cap, acu_array_out *out_nulls, void *scratch,
-                                     unsigned long long *res, acu_bytes_col_state *st);
+                                     unsigned long long *res, acu_bytes_col_state *st, int nulls_mode);
 acu_status acu_take_bytes_col_finalize(acu_ctx *ctx, const acu_array *nulls_of, const acu_array *indices, acu_dtype index_dtype,
                                        const acu_bytes_col_state *st, const unsigned long long *hres, int64_t *out_data_len,
                                        acu_array_out *out_nulls);
 acu_status acu_filter_bytes_col_launch(acu_ctx *ctx, const acu_filter_plan *plan, int32_t ob, const void *offsets, const uint8_t *data,
                                        const acu_array *nulls_of, void *out_offsets, uint8_t *out_data, int64_t out_cap,
-                                       acu_array_out *out_nulls, void *scratch, unsigned long long *res, acu_bytes_col_state *st);
+                                       acu_array_out *out_nulls, void *scratch, unsigned long long *res, acu_bytes_col_state *st,
+                                       int nulls_mode);
 acu_status acu_filter_bytes_col_finalize(acu_ctx *ctx, const acu_filter_plan *plan, const acu_array *nulls_of,
                                          const acu_bytes_col_state *st, const unsigned long long *hres, int64_t *out_data_len,
                                          acu_array_out *out_nulls);
@@ -61,3 +63,12 @@ acu_status acu_filter_bytes_col_finalize(acu_ctx *ctx, const acu_filter_plan *pl
 size_t acu_reduce_col_scratch(const acu_ctx *ctx);
 acu_status acu_reduce_col_launch(acu_ctx *ctx, acu_dtype dtype, acu_agg_op op, const acu_array *a, int64_t nc, void *scratch,
                                  unsigned long long *res, int *launched);
+
+// Record-batch variants: the same per-column work with kernels of like columns sharing launches (blockIdx.y = column).
+acu_status acu_filter_cols_launch(acu_ctx *ctx, const acu_filter_plan *plan, int n, const int *kinds, const int32_t *widths,
+                                  const acu_array *const *values, acu_array_out *const *outs, unsigned long long *const *res, int *modes);
+acu_status acu_take_cols_launch(acu_ctx *ctx, int n, const int32_t *elem_bytes, const acu_array *const *values, const char *boolean,
+                                const char *val_nulls, const acu_array *indices, acu_dtype index_dtype, bool idx_nulls,
+                                acu_array_out *const *outs, unsigned long long *const *res, int *modes);
+acu_status acu_reduce_cols_launch(acu_ctx *ctx, int n, const acu_dtype *dtypes, const acu_agg_op *ops, const acu_array *arrays,
+                                  const int64_t *nc, uint8_t *scratch, size_t scratch_per_col, unsigned long long *const *res, int *launched);

@@ -49,32 +49,39 @@ extern "C" acu_status acu_filter_record_batch(acu_ctx *ctx, const acu_filter_pla
   for (int32_t c = 0; c < n_columns; ++c) n_bytes_cols += columns[c].kind == ACU_COL_BYTES;
   uint8_t *scratch = nullptr;
   if (n_bytes_cols) ACU_TRY(acu_scratch(ctx, per_col * n_bytes_cols, reinterpret_cast<void **>(&scratch)));
-  std::vector<int> mode(n_columns, 0);
+  std::vector<int> mode(n_columns, 0), kinds(n_columns, 0);
+  std::vector<int32_t> widths(n_columns, 0);
+  std::vector<const acu_array *> vals(n_columns);
+  std::vector<acu_array_out *> outp(n_columns);
+  std::vector<unsigned long long *> resp(n_columns);
   std::vector<StatePtr> bstate(n_columns);
+  for (int32_t c = 0; c < n_columns; ++c) {
+    const acu_column &col = columns[c];
+    if (col.kind != ACU_COL_PRIMITIVE && col.kind != ACU_COL_BOOLEAN && col.kind != ACU_COL_BYTES) return bad_kind(ctx, c, col.kind);
+    kinds[c] = col.kind == ACU_COL_PRIMITIVE ? 0 : col.kind == ACU_COL_BOOLEAN ? 1 : 2;
+    widths[c] = col.width;
+    vals[c] = &col.array;
+    outp[c] = &outs[c].array;
+    resp[c] = acu_dres(ctx, c);
+  }
   ACU_TRY(acu_res_reset_n(ctx, n_columns));
+  auto drain = [&](acu_status st, int32_t c) {
+    cudaStreamSynchronize(ctx->stream);
+    acu_kstats_drain(ctx);
+    return column_failed(ctx, st, c);
+  };
+  {  // values of fixed-width columns + every validity compaction, like columns sharing launches
+    acu_status st = acu_filter_cols_launch(ctx, plan, n_columns, kinds.data(), widths.data(), vals.data(), outp.data(), resp.data(), mode.data());
+    if (st != ACU_OK) return drain(st, 0);
+  }
   size_t k = 0;
   for (int32_t c = 0; c < n_columns; ++c) {
     const acu_column &col = columns[c];
-    acu_status st;
-    switch (col.kind) {
-      case ACU_COL_PRIMITIVE:
-        st = acu_filter_col_launch(ctx, plan, 0, col.width, &col.array, &outs[c].array, acu_dres(ctx, c), &mode[c]);
-        break;
-      case ACU_COL_BOOLEAN:
-        st = acu_filter_col_launch(ctx, plan, 1, 0, &col.array, &outs[c].array, acu_dres(ctx, c), &mode[c]);
-        break;
-      case ACU_COL_BYTES:
-        bstate[c].reset(acu_bytes_col_state_new());
-        st = acu_filter_bytes_col_launch(ctx, plan, col.width, col.array.values, col.data, &col.array, outs[c].array.values, outs[c].data,
-                                         outs[c].data_capacity, &outs[c].array, scratch + per_col * k++, acu_dres(ctx, c), bstate[c].get());
-        break;
-      default: st = bad_kind(ctx, c, col.kind);
-    }
-    if (st != ACU_OK) {
-      cudaStreamSynchronize(ctx->stream);
-      acu_kstats_drain(ctx);
-      return column_failed(ctx, st, c);
-    }
+    if (col.kind != ACU_COL_BYTES) continue;
+    bstate[c].reset(acu_bytes_col_state_new());
+    acu_status st = acu_filter_bytes_col_launch(ctx, plan, col.width, col.array.values, col.data, &col.array, outs[c].array.values, outs[c].data,
+                                                outs[c].data_capacity, &outs[c].array, scratch + per_col * k++, acu_dres(ctx, c), bstate[c].get(), mode[c]);
+    if (st != ACU_OK) return drain(st, c);
   }
   ACU_TRY(acu_res_fetch_n(ctx, n_columns));
   for (int32_t c = 0; c < n_columns; ++c) {
@@ -119,34 +126,50 @@ extern "C" acu_status acu_take_record_batch(acu_ctx *ctx, int32_t n_columns, con
   for (int32_t c = 0; c < n_columns; ++c) n_bytes_cols += columns[c].kind == ACU_COL_BYTES;
   uint8_t *scratch = nullptr;
   if (n_bytes_cols) ACU_TRY(acu_scratch(ctx, per_col * n_bytes_cols, reinterpret_cast<void **>(&scratch)));
-  std::vector<int> mode(n_columns, 0);
+  std::vector<int> mode(n_columns, -1);
   std::vector<StatePtr> bstate(n_columns);
+  // fixed-width / boolean columns, and the validity gather of variable-width columns whose values have nulls:
+  // like columns share launches
+  std::vector<int32_t> eb;
+  std::vector<const acu_array *> vals;
+  std::vector<char> isbool, vnulls;
+  std::vector<acu_array_out *> outp;
+  std::vector<unsigned long long *> resp;
+  std::vector<int> who;
+  for (int32_t c = 0; c < n_columns; ++c) {
+    const acu_column &col = columns[c];
+    if (col.kind != ACU_COL_PRIMITIVE && col.kind != ACU_COL_BOOLEAN && col.kind != ACU_COL_BYTES) return bad_kind(ctx, c, col.kind);
+    if (col.kind == ACU_COL_BYTES && !val_nulls[c]) continue;  // nulls = indices.nulls().cloned(): queued with the bytes pass
+    eb.push_back(col.kind == ACU_COL_PRIMITIVE ? col.width : 0);
+    vals.push_back(&col.array);
+    isbool.push_back(col.kind == ACU_COL_BOOLEAN);
+    vnulls.push_back(val_nulls[c]);
+    outp.push_back(&outs[c].array);
+    resp.push_back(acu_dres(ctx, c));
+    who.push_back(c);
+  }
   ACU_TRY(acu_res_reset_n(ctx, n_columns));
+  auto drain = [&](acu_status s, int32_t c) {
+    cudaStreamSynchronize(ctx->stream);
+    acu_kstats_drain(ctx);
+    return column_failed(ctx, s, c);
+  };
+  if (!who.empty()) {
+    std::vector<int> modes(who.size(), 0);
+    st = acu_take_cols_launch(ctx, (int)who.size(), eb.data(), vals.data(), isbool.data(), vnulls.data(), indices, index_dtype, idx_nulls,
+                              outp.data(), resp.data(), modes.data());
+    if (st != ACU_OK) return drain(st, who[0]);
+    for (size_t i = 0; i < who.size(); ++i) mode[who[i]] = modes[i];
+  }
   size_t k = 0;
   for (int32_t c = 0; c < n_columns; ++c) {
     const acu_column &col = columns[c];
-    switch (col.kind) {
-      case ACU_COL_PRIMITIVE:
-        st = acu_take_col_launch(ctx, col.width, &col.array, false, val_nulls[c], indices, index_dtype, idx_nulls, &outs[c].array,
-                                 acu_dres(ctx, c), &mode[c]);
-        break;
-      case ACU_COL_BOOLEAN:
-        st = acu_take_col_launch(ctx, 0, &col.array, true, val_nulls[c], indices, index_dtype, idx_nulls, &outs[c].array, acu_dres(ctx, c),
-                                 &mode[c]);
-        break;
-      case ACU_COL_BYTES:
-        bstate[c].reset(acu_bytes_col_state_new());
-        st = acu_take_bytes_col_launch(ctx, col.width, col.array.values, col.data, &col.array, val_nulls[c], indices, index_dtype, idx_nulls,
-                                       outs[c].array.values, outs[c].data, outs[c].data_capacity, &outs[c].array, scratch + per_col * k++,
-                                       acu_dres(ctx, c), bstate[c].get());
-        break;
-      default: st = bad_kind(ctx, c, col.kind);
-    }
-    if (st != ACU_OK) {
-      cudaStreamSynchronize(ctx->stream);
-      acu_kstats_drain(ctx);
-      return column_failed(ctx, st, c);
-    }
+    if (col.kind != ACU_COL_BYTES) continue;
+    bstate[c].reset(acu_bytes_col_state_new());
+    st = acu_take_bytes_col_launch(ctx, col.width, col.array.values, col.data, &col.array, val_nulls[c], indices, index_dtype, idx_nulls,
+                                   outs[c].array.values, outs[c].data, outs[c].data_capacity, &outs[c].array, scratch + per_col * k++,
+                                   acu_dres(ctx, c), bstate[c].get(), val_nulls[c] ? mode[c] : -1);
+    if (st != ACU_OK) return drain(st, c);
   }
   ACU_TRY(acu_res_fetch_n(ctx, n_columns));
   for (int32_t c = 0; c < n_columns; ++c) {
@@ -179,14 +202,14 @@ extern "C" acu_status acu_aggregate_columns(acu_ctx *ctx, int32_t n_columns, con
   uint8_t *scratch;
   ACU_TRY(acu_scratch(ctx, per_col * n_columns, reinterpret_cast<void **>(&scratch)));
   std::vector<int> launched(n_columns, 0);
+  std::vector<unsigned long long *> resp(n_columns);
+  for (int32_t c = 0; c < n_columns; ++c) resp[c] = acu_dres(ctx, c);
   ACU_TRY(acu_res_reset_n(ctx, n_columns));
-  for (int32_t c = 0; c < n_columns; ++c) {
-    st = acu_reduce_col_launch(ctx, dtypes[c], ops[c], &arrays[c], nc[c], scratch + per_col * c, acu_dres(ctx, c), &launched[c]);
-    if (st != ACU_OK) {
-      cudaStreamSynchronize(ctx->stream);
-      acu_kstats_drain(ctx);
-      return column_failed(ctx, st, c);
-    }
+  st = acu_reduce_cols_launch(ctx, n_columns, dtypes, ops, arrays, nc.data(), scratch, per_col, resp.data(), launched.data());
+  if (st != ACU_OK) {
+    cudaStreamSynchronize(ctx->stream);
+    acu_kstats_drain(ctx);
+    return st;
   }
   ACU_TRY(acu_res_fetch_n(ctx, n_columns));
   for (int32_t c = 0; c < n_columns; ++c)

@@ -73,11 +73,28 @@ template <class A> __device__ __forceinline__ A shfl_down_any(A v, int o) {
   }
 }
 
+constexpr int REDUCE_BATCH_COLS = 8;
+struct ReduceArgs {
+  const void *v;            // values (native type of the launch)
+  int64_t n;
+  const uint8_t *valid;     // validity (NULL: no nulls)
+  int64_t voff;
+  void *partial;            // one accumulator per CTA
+  unsigned long long *res;  // result block: RES_COUNT valid rows, RES_AUX0 result bits, RES_AUX3 ticket (zero on entry and on exit)
+};
+struct ReduceBatch { ReduceArgs col[REDUCE_BATCH_COLS]; };
+
 template <class T, int OP>
-__global__ void __launch_bounds__(256) k_reduce(const T *__restrict__ v, int64_t n, const uint8_t *__restrict__ valid,
-                                                int64_t voff, typename AccOf<T, OP>::type *__restrict__ partial,
-                                                unsigned int *__restrict__ ticket, unsigned long long *__restrict__ res) {
+__global__ void __launch_bounds__(256) k_reduce(const ReduceBatch batch) {
   using A = typename AccOf<T, OP>::type;
+  // blockIdx.y = column of the batch (same dtype and op); the ticket is a slot of the column's result block
+  const T *__restrict__ v = static_cast<const T *>(batch.col[blockIdx.y].v);
+  const int64_t n = batch.col[blockIdx.y].n;
+  const uint8_t *__restrict__ valid = batch.col[blockIdx.y].valid;
+  const int64_t voff = batch.col[blockIdx.y].voff;
+  A *__restrict__ partial = static_cast<A *>(batch.col[blockIdx.y].partial);
+  unsigned long long *__restrict__ res = batch.col[blockIdx.y].res;
+  unsigned int *__restrict__ ticket = reinterpret_cast<unsigned int *>(res + RES_AUX3);
   constexpr int U = 8;  // strips (64 rows) in flight per warp: 8 x 2 loads per lane
   __shared__ A s_part[8];
   __shared__ bool s_last;
@@ -151,32 +168,55 @@ __global__ void __launch_bounds__(256) k_reduce(const T *__restrict__ v, int64_t
 }
 
 template <class T, int OP>
-acu_status reduce_launch(acu_ctx *ctx, const acu_array *a, const uint8_t *valid, void *scratch, unsigned long long *res) {
+acu_status reduce_launch(acu_ctx *ctx, const ReduceBatch &rb, int n_cols, int64_t max_len) {
   using A = typename AccOf<T, OP>::type;
-  const int64_t strips = (a->len + 63) >> 6;
-  const int grid = acu_wave_grid(ctx, k_reduce<T, OP>, 256, 0, (strips / 32 + 1 + 7) / 8);
   static_assert(sizeof(A) <= 16, "partials must fit the per-column scratch");
-  unsigned int *ticket = static_cast<unsigned int *>(scratch);
-  A *partial = reinterpret_cast<A *>(static_cast<uint8_t *>(scratch) + 256);
-  ACU_CUDA(ctx, cudaMemsetAsync(ticket, 0, 4, ctx->stream));
-  ACU_LAUNCH_TIMED(ctx, ACU_K_REDUCE, (k_reduce<T, OP>), grid, 256, 0, static_cast<const T *>(a->values), a->len, valid, a->validity_offset,
-             partial, ticket, res);
+  const int64_t strips = (max_len + 63) >> 6;
+  const int grid = acu_wave_grid(ctx, k_reduce<T, OP>, 256, 0, (strips / 32 + 1 + 7) / 8);
+  ACU_LAUNCH_TIMED(ctx, ACU_K_REDUCE, (k_reduce<T, OP>), dim3(grid, n_cols), 256, 0, rb);
   return ACU_OK;
 }
 
 template <class T>
-acu_status reduce_typed(acu_ctx *ctx, acu_agg_op op, const acu_array *a, const uint8_t *valid, void *scratch, unsigned long long *res) {
+acu_status reduce_typed(acu_ctx *ctx, acu_agg_op op, const ReduceBatch &rb, int n_cols, int64_t max_len) {
   switch (op) {
-    case ACU_SUM: return reduce_launch<T, ACU_SUM>(ctx, a, valid, scratch, res);
-    case ACU_MIN: return reduce_launch<T, ACU_MIN>(ctx, a, valid, scratch, res);
-    default: return reduce_launch<T, ACU_MAX>(ctx, a, valid, scratch, res);
+    case ACU_SUM: return reduce_launch<T, ACU_SUM>(ctx, rb, n_cols, max_len);
+    case ACU_MIN: return reduce_launch<T, ACU_MIN>(ctx, rb, n_cols, max_len);
+    default: return reduce_launch<T, ACU_MAX>(ctx, rb, n_cols, max_len);
   }
+}
+
+acu_status reduce_dispatch(acu_ctx *ctx, acu_dtype dtype, acu_agg_op op, const ReduceBatch &rb, int n_cols, int64_t max_len) {
+  switch (dtype) {
+    case ACU_I8: return reduce_typed<int8_t>(ctx, op, rb, n_cols, max_len);
+    case ACU_I16: return reduce_typed<int16_t>(ctx, op, rb, n_cols, max_len);
+    case ACU_I32: return reduce_typed<int32_t>(ctx, op, rb, n_cols, max_len);
+    case ACU_I64: return reduce_typed<int64_t>(ctx, op, rb, n_cols, max_len);
+    case ACU_U8: return reduce_typed<uint8_t>(ctx, op, rb, n_cols, max_len);
+    case ACU_U16: return reduce_typed<uint16_t>(ctx, op, rb, n_cols, max_len);
+    case ACU_U32: return reduce_typed<uint32_t>(ctx, op, rb, n_cols, max_len);
+    case ACU_U64: return reduce_typed<uint64_t>(ctx, op, rb, n_cols, max_len);
+    case ACU_F32: return reduce_typed<float>(ctx, op, rb, n_cols, max_len);
+    case ACU_F64: return reduce_typed<double>(ctx, op, rb, n_cols, max_len);
+  }
+  return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "aggregate: dtype %d", (int)dtype);
+}
+
+ReduceArgs reduce_args(const acu_array *a, int64_t nc, void *scratch, unsigned long long *res) {
+  ReduceArgs r;
+  r.v = a->values;
+  r.n = a->len;
+  r.valid = (a->validity && nc > 0) ? a->validity : nullptr;
+  r.voff = a->validity_offset;
+  r.partial = scratch;
+  r.res = res;
+  return r;
 }
 
 }  // namespace
 
-// per-column scratch of one queued reduction: ticket + one partial per CTA of the widest grid
-size_t acu_reduce_col_scratch(const acu_ctx *ctx) { return 256 + (size_t)ctx->sm_count * 8 * 8 * 16 + 4096; }
+// per-column scratch of one queued reduction: one partial per CTA of the widest grid
+size_t acu_reduce_col_scratch(const acu_ctx *ctx) { return (size_t)ctx->sm_count * 8 * 8 * 16 + 4096; }
 
 // Queue sum / min / max of one column on the ctx stream (no sync). The caller has resolved the
 // null count: nc == len (or len == 0) means None and nothing is launched (*launched = 0). The
@@ -185,22 +225,36 @@ acu_status acu_reduce_col_launch(acu_ctx *ctx, acu_dtype dtype, acu_agg_op op, c
                                  unsigned long long *res, int *launched) {
   *launched = 0;
   if (a->len == 0 || nc == a->len) return ACU_OK;  // aggregate.rs:320-323
-  const uint8_t *valid = (a->validity && nc > 0) ? a->validity : nullptr;
+  ReduceBatch rb{};
+  rb.col[0] = reduce_args(a, nc, scratch, res);
+  ACU_TRY(reduce_dispatch(ctx, dtype, op, rb, 1, a->len));
   *launched = 1;
-  switch (dtype) {
-    case ACU_I8: return reduce_typed<int8_t>(ctx, op, a, valid, scratch, res);
-    case ACU_I16: return reduce_typed<int16_t>(ctx, op, a, valid, scratch, res);
-    case ACU_I32: return reduce_typed<int32_t>(ctx, op, a, valid, scratch, res);
-    case ACU_I64: return reduce_typed<int64_t>(ctx, op, a, valid, scratch, res);
-    case ACU_U8: return reduce_typed<uint8_t>(ctx, op, a, valid, scratch, res);
-    case ACU_U16: return reduce_typed<uint16_t>(ctx, op, a, valid, scratch, res);
-    case ACU_U32: return reduce_typed<uint32_t>(ctx, op, a, valid, scratch, res);
-    case ACU_U64: return reduce_typed<uint64_t>(ctx, op, a, valid, scratch, res);
-    case ACU_F32: return reduce_typed<float>(ctx, op, a, valid, scratch, res);
-    case ACU_F64: return reduce_typed<double>(ctx, op, a, valid, scratch, res);
+  return ACU_OK;
+}
+
+// Several columns: those with the same (dtype, op) share a launch (blockIdx.y = column).
+acu_status acu_reduce_cols_launch(acu_ctx *ctx, int n, const acu_dtype *dtypes, const acu_agg_op *ops, const acu_array *arrays,
+                                  const int64_t *nc, uint8_t *scratch, size_t scratch_per_col, unsigned long long *const *res, int *launched) {
+  char done[ACU_MAX_BATCH_COLUMNS] = {0};
+  for (int c = 0; c < n; ++c) {
+    launched[c] = 0;
+    if (arrays[c].len == 0 || nc[c] == arrays[c].len) done[c] = 1;  // None
   }
-  *launched = 0;
-  return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "aggregate: dtype %d", (int)dtype);
+  for (int c = 0; c < n; ++c) {
+    if (done[c]) continue;
+    ReduceBatch rb{};
+    int k = 0;
+    int64_t max_len = 0;
+    for (int d = c; d < n && k < REDUCE_BATCH_COLS; ++d) {
+      if (done[d] || dtypes[d] != dtypes[c] || ops[d] != ops[c]) continue;
+      rb.col[k++] = reduce_args(&arrays[d], nc[d], scratch + scratch_per_col * d, res[d]);
+      if (arrays[d].len > max_len) max_len = arrays[d].len;
+      done[d] = 1;
+      launched[d] = 1;
+    }
+    ACU_TRY(reduce_dispatch(ctx, dtypes[c], ops[c], rb, k, max_len));
+  }
+  return ACU_OK;
 }
 
 extern "C" acu_status acu_aggregate(acu_ctx *ctx, acu_dtype dtype, acu_agg_op op, const acu_array *a,

@@ -107,8 +107,14 @@ template <int IT> __device__ __forceinline__ typename WideOf<IT>::type widen(typ
 }
 
 // BOOL: take_boolean (bit gather of boolean VALUES, no value gather); else take_primitive.
+// Up to TAKE_BATCH_COLS columns per launch (blockIdx.y = column): the columns of a take_record_batch share the
+// index array, hence the grid.x size.
+constexpr int TAKE_BATCH_COLS = 8;
+struct TakeBatch { TakeArgs col[TAKE_BATCH_COLS]; };
+
 template <int W, int IT, bool BOOL>
-__global__ void __launch_bounds__(256, 3) k_take(const TakeArgs a) {
+__global__ void __launch_bounds__(256, 3) k_take(const TakeBatch batch) {
+  const TakeArgs a = batch.col[blockIdx.y];
   using V = typename VecOf<W>::type;
   using I = typename IdxOf<IT>::raw;
   // warp-private double-buffered index tiles: no CTA-wide barrier anywhere in the loop
@@ -254,14 +260,15 @@ uint64_t index_max(acu_dtype t) {
 }
 
 template <int W>
-acu_status launch_take_w(acu_ctx *ctx, int kind, const TakeArgs &ta) {
+acu_status launch_take_w(acu_ctx *ctx, int kind, const TakeBatch &tb, int n_cols) {
+  const TakeArgs &ta = tb.col[0];
   const int64_t tiles = ((ta.m + TAKE_WTILE - 1) / TAKE_WTILE + 7) / 8;  // CTAs: 8 warp tiles each
 #define ACU_TAKE_CASE(IT)                                                                                   \
   case IT:                                                                                                                   \
     if (W == 1 && ta.vbits)                                                                                                  \
-      ACU_LAUNCH_TIMED(ctx, ACU_K_TAKE, (k_take<1, IT, true>), acu_wave_grid(ctx, k_take<1, IT, true>, 256, 0, tiles), 256, 0, ta); \
+      ACU_LAUNCH_TIMED(ctx, ACU_K_TAKE, (k_take<1, IT, true>), dim3(acu_wave_grid(ctx, k_take<1, IT, true>, 256, 0, tiles), n_cols), 256, 0, tb); \
     else                                                                                                                     \
-      ACU_LAUNCH_TIMED(ctx, ACU_K_TAKE, (k_take<W, IT, false>), acu_wave_grid(ctx, k_take<W, IT, false>, 256, 0, tiles), 256, 0, ta); \
+      ACU_LAUNCH_TIMED(ctx, ACU_K_TAKE, (k_take<W, IT, false>), dim3(acu_wave_grid(ctx, k_take<W, IT, false>, 256, 0, tiles), n_cols), 256, 0, tb); \
     break;
   switch (kind) {
     ACU_TAKE_CASE(0) ACU_TAKE_CASE(1) ACU_TAKE_CASE(2) ACU_TAKE_CASE(3) ACU_TAKE_CASE(4) ACU_TAKE_CASE(5)
@@ -271,14 +278,14 @@ acu_status launch_take_w(acu_ctx *ctx, int kind, const TakeArgs &ta) {
   return ACU_OK;
 }
 
-acu_status launch_take(acu_ctx *ctx, int elem_bytes, int kind, const TakeArgs &ta) {
+acu_status launch_take(acu_ctx *ctx, int elem_bytes, int kind, const TakeBatch &tb, int n_cols) {
   switch (elem_bytes) {
-    case 1: return launch_take_w<1>(ctx, kind, ta);
-    case 2: return launch_take_w<2>(ctx, kind, ta);
-    case 4: return launch_take_w<4>(ctx, kind, ta);
-    case 8: return launch_take_w<8>(ctx, kind, ta);
-    case 16: return launch_take_w<16>(ctx, kind, ta);
-    case 32: return launch_take_w<32>(ctx, kind, ta);
+    case 1: return launch_take_w<1>(ctx, kind, tb, n_cols);
+    case 2: return launch_take_w<2>(ctx, kind, tb, n_cols);
+    case 4: return launch_take_w<4>(ctx, kind, tb, n_cols);
+    case 8: return launch_take_w<8>(ctx, kind, tb, n_cols);
+    case 16: return launch_take_w<16>(ctx, kind, tb, n_cols);
+    case 32: return launch_take_w<32>(ctx, kind, tb, n_cols);
     default: return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "take: unsupported element width %d", elem_bytes);
   }
 }
@@ -333,31 +340,69 @@ acu_status acu_take_common(acu_ctx *ctx, int32_t elem_bytes, const acu_array *va
 // synchronising. val_nulls / idx_nulls = "has a validity buffer with at least one null"
 // (exact, the NullBuffer decision depends on it). *mode: bit 0 = an output validity was
 // produced, bit 1 = it came from take_bits(values.nulls) (None when it has no nulls).
-acu_status acu_take_col_launch(acu_ctx *ctx, int32_t elem_bytes, const acu_array *values, bool boolean_values, bool val_nulls,
-                               const acu_array *indices, acu_dtype index_dtype, bool idx_nulls, acu_array_out *out,
-                               unsigned long long *res, int *mode) {
-  *mode = 0;
-  const int kind = index_kind(index_dtype);
-  const int64_t m = indices->len;
-  out->len = m;
-  out->has_validity = 0;
-  out->null_count = 0;
-  if (m == 0) return ACU_OK;
+static TakeArgs take_args(int32_t elem_bytes, const acu_array *values, bool boolean_values, bool val_nulls, const acu_array *indices,
+                          bool idx_nulls, acu_array_out *out, unsigned long long *res) {
   TakeArgs ta{};
   ta.values = (elem_bytes > 0 && !boolean_values) ? values->values : nullptr;
   ta.n_values = values->len;
   if (val_nulls) { ta.vvalid = values->validity; ta.vvoff = values->validity_offset; }
   if (boolean_values) { ta.vbits = static_cast<const uint8_t *>(values->values); ta.vboff = values->values_offset; ta.out_bits = static_cast<uint32_t *>(out->values); }
   ta.idx = indices->values;
-  ta.m = m;
+  ta.m = indices->len;
   if (idx_nulls || (!val_nulls && indices->validity)) { ta.ivalid = indices->validity; ta.ivoff = indices->validity_offset; }
   ta.idx_has_nulls = idx_nulls;
   ta.out = out->values;
   if (val_nulls || indices->validity) ta.out_valid = reinterpret_cast<uint32_t *>(out->validity);
   ta.res = res;
   ta.use_bulk = ((uintptr_t)indices->values % 16) == 0;
-  ACU_TRY(launch_take(ctx, ta.values ? elem_bytes : 1, kind, ta));
-  *mode = (ta.out_valid ? 1 : 0) | (val_nulls ? 2 : 0);
+  return ta;
+}
+
+acu_status acu_take_col_launch(acu_ctx *ctx, int32_t elem_bytes, const acu_array *values, bool boolean_values, bool val_nulls,
+                               const acu_array *indices, acu_dtype index_dtype, bool idx_nulls, acu_array_out *out,
+                               unsigned long long *res, int *mode) {
+  *mode = 0;
+  const int kind = index_kind(index_dtype);
+  out->len = indices->len;
+  out->has_validity = 0;
+  out->null_count = 0;
+  if (indices->len == 0) return ACU_OK;
+  TakeBatch tb{};
+  tb.col[0] = take_args(elem_bytes, values, boolean_values, val_nulls, indices, idx_nulls, out, res);
+  ACU_TRY(launch_take(ctx, tb.col[0].values ? elem_bytes : 1, kind, tb, 1));
+  *mode = (tb.col[0].out_valid ? 1 : 0) | (val_nulls ? 2 : 0);
+  return ACU_OK;
+}
+
+// All columns of a take_record_batch: columns that run the same kernel instantiation (element width / boolean /
+// validity-only) share a launch. elem_bytes[c] == 0 with boolean[c] == 0 is the validity-only gather of a
+// variable-width column.
+acu_status acu_take_cols_launch(acu_ctx *ctx, int n, const int32_t *elem_bytes, const acu_array *const *values, const char *boolean,
+                                const char *val_nulls, const acu_array *indices, acu_dtype index_dtype, bool idx_nulls,
+                                acu_array_out *const *outs, unsigned long long *const *res, int *modes) {
+  const int kind = index_kind(index_dtype);
+  for (int c = 0; c < n; ++c) {
+    modes[c] = 0;
+    outs[c]->len = indices->len;
+    outs[c]->has_validity = 0;
+    outs[c]->null_count = 0;
+  }
+  if (indices->len == 0) return ACU_OK;
+  auto klass = [&](int c) { return boolean[c] ? -1 : (elem_bytes[c] > 0 ? elem_bytes[c] : 0); };  // kernel instantiation of column c
+  char done[ACU_MAX_BATCH_COLUMNS] = {0};
+  for (int c = 0; c < n; ++c) {
+    if (done[c]) continue;
+    TakeBatch tb{};
+    int k = 0;
+    for (int d = c; d < n && k < TAKE_BATCH_COLS; ++d) {
+      if (done[d] || klass(d) != klass(c)) continue;
+      tb.col[k] = take_args(elem_bytes[d], values[d], boolean[d] != 0, val_nulls[d] != 0, indices, idx_nulls, outs[d], res[d]);
+      modes[d] = (tb.col[k].out_valid ? 1 : 0) | (val_nulls[d] ? 2 : 0);
+      done[d] = 1;
+      ++k;
+    }
+    ACU_TRY(launch_take(ctx, klass(c) > 0 ? klass(c) : 1, kind, tb, k));
+  }
   return ACU_OK;
 }
 

@@ -257,6 +257,31 @@ def test_filter_bytes_fuzz(gpu, oracle):
                               f"filter_bytes n={n} p={true_p}")
 
 
+def test_bytes_long_and_mixed_rows(gpu, oracle):
+    """Rows longer than the 16-byte fast window, CTAs whose output exceeds the shared-memory staging
+    buffer (direct-store path), empty rows, and i64 offsets (LargeUtf8) + every index width."""
+    rng = np.random.default_rng(14)
+    for n, max_len, odt in [(5000, 200, np.int32), (3000, 40, np.int64), (6000, 17, np.int32), (2500, 1, np.int32)]:
+        lens = rng.integers(0, max_len + 1, n)
+        lens[rng.random(n) < 0.2] = 0
+        offsets = np.zeros(n + 1, dtype=odt)
+        offsets[1:] = np.cumsum(lens)
+        data = rng.integers(0, 256, int(offsets[-1]) + 16).astype(np.uint8)
+        for null_p in (None, 0.1):
+            mask = rng.random(n) >= null_p if null_p is not None else None
+            nulls = HostArray(abi.U8, np.zeros(0, np.uint8), n, None if mask is None else acu.pack_bits(mask), 0, 0,
+                              0 if mask is None else int(n - mask.sum()))
+            pred = rand_bool(rng, n, 0.6, None)
+            assert_same_bytes(gpu.filter_bytes(offsets, data, nulls, pred), oracle.filter_bytes(offsets, data, nulls, pred),
+                              f"filter_bytes long n={n} max_len={max_len}")
+            for idt in (abi.U32, abi.I64, abi.U16, abi.I8):
+                hi = min(n, int(np.iinfo(acu.NP_DTYPES[idt]).max))
+                m = 7000
+                idx = HostArray.from_numpy(idt, rng.integers(0, hi, m).astype(acu.NP_DTYPES[idt]), rng.random(m) >= 0.1)
+                assert_same_bytes(gpu.take_bytes(offsets, data, nulls, idx), oracle.take_bytes(offsets, data, nulls, idx),
+                                  f"take_bytes long n={n} max_len={max_len} idx={idt}")
+
+
 # ---- numeric -------------------------------------------------------------------------------
 ARITH_OPS = ["add", "add_wrapping", "sub", "sub_wrapping", "mul", "mul_wrapping", "div", "rem"]
 
