@@ -621,6 +621,34 @@ class Context:
             da.free()
             db.free()
 
+    # -- boolean (arrow-arith/src/boolean.rs) -------------------------------------------------
+    def boolean(self, op, a, b=None):
+        da = self.upload(a)
+        db = self.upload(b) if b is not None else None
+        n = max(a.length, 1)
+        out = self.alloc_out(bitmap_bytes(n), n)
+        try:
+            ad = da.descriptor()
+            bd = db.descriptor() if db is not None else None
+            self.check(self.lib.acu_boolean(self.h, op, C.byref(ad), C.byref(bd) if bd is not None else None, C.byref(out)))
+            res, out = self.download_out(out, BOOL), None
+            return res
+        finally:
+            if out is not None:
+                self._free_out(out)
+            da.free()
+            if db is not None:
+                db.free()
+
+    def and_(self, a, b): return self.boolean(abi.BOOL_AND, a, b)
+    def or_(self, a, b): return self.boolean(abi.BOOL_OR, a, b)
+    def and_not(self, a, b): return self.boolean(abi.BOOL_AND_NOT, a, b)
+    def and_kleene(self, a, b): return self.boolean(abi.BOOL_AND_KLEENE, a, b)
+    def or_kleene(self, a, b): return self.boolean(abi.BOOL_OR_KLEENE, a, b)
+    def not_(self, a): return self.boolean(abi.BOOL_NOT, a)
+    def is_null(self, a): return self.boolean(abi.BOOL_IS_NULL, a)
+    def is_not_null(self, a): return self.boolean(abi.BOOL_IS_NOT_NULL, a)
+
     def eq(self, a, b): return self.cmp(EQ, a, b)
     def neq(self, a, b): return self.cmp(NEQ, a, b)
     def lt(self, a, b): return self.cmp(LT, a, b)

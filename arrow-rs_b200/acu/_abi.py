@@ -80,6 +80,7 @@ class ArrayOut(C.Structure):
 
 
 COL_PRIMITIVE, COL_BOOLEAN, COL_BYTES = range(3)
+BOOL_AND, BOOL_OR, BOOL_AND_NOT, BOOL_AND_KLEENE, BOOL_OR_KLEENE, BOOL_NOT, BOOL_IS_NULL, BOOL_IS_NOT_NULL = range(8)
 MAX_BATCH_COLUMNS = 64
 
 
@@ -154,6 +155,7 @@ PROTOTYPES = {
     "acu_neg": (i32, [vp, i32, i32, P(Array), P(ArrayOut)]),
     "acu_cmp": (i32, [vp, i32, i32, P(Array), P(Array), P(ArrayOut)]),
     "acu_cast_numeric": (i32, [vp, i32, i32, i32, P(Array), P(ArrayOut)]),
+    "acu_boolean": (i32, [vp, i32, P(Array), P(Array), P(ArrayOut)]),
     "acu_aggregate": (i32, [vp, i32, i32, P(Array), P(u64), P(i64)]),
     "acu_filter_record_batch": (i32, [vp, vp, i32, P(Column), P(ColumnOut)]),
     "acu_take_record_batch": (i32, [vp, i32, P(Column), P(Array), i32, i32, P(ColumnOut)]),

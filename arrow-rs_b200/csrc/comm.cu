@@ -143,11 +143,11 @@ acu_status acu_comm_allreduce_aggregates(acu_ctx *ctx, acu_dtype dtype, acu_agg_
   ACU_ENTER(ctx);
   if (ctx->world <= 1 || !ctx->nccl_comm || n <= 0) return ACU_OK;
   NcclApi *api = nccl_api();
-  uint8_t *buf;
-  ACU_TRY(acu_scratch(ctx, (size_t)n * 16, reinterpret_cast<void **>(&buf)));
-  // staging: [n x 8 B values][n x int64 counts]
-  uint64_t stage[64];
   if (n > 32) return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "at most 32 aggregates per all-reduce");
+  // staging lives in the upper half of the ctx result blocks: pinned on the host side, so both copies are
+  // truly asynchronous; layout [n x 8 B values][n x int64 counts]
+  uint64_t *stage = reinterpret_cast<uint64_t *>(ctx->h_res + (size_t)(RES_BLOCKS / 2) * RES_SLOTS);
+  uint8_t *buf = reinterpret_cast<uint8_t *>(ctx->d_res + (size_t)(RES_BLOCKS / 2) * RES_SLOTS);
   const bool is_unsigned = dtype == ACU_U8 || dtype == ACU_U16 || dtype == ACU_U32 || dtype == ACU_U64;
   int nccl_type, nccl_op;
   for (int i = 0; i < n; ++i) {
@@ -166,22 +166,27 @@ acu_status acu_comm_allreduce_aggregates(acu_ctx *ctx, acu_dtype dtype, acu_agg_
   }
   if (op == ACU_SUM) {
     nccl_op = NCCL_SUM;
-    nccl_type = dtype == ACU_F64 ? NCCL_FLOAT64 : dtype == ACU_F32 ? NCCL_FLOAT32 : (is_unsigned ? NCCL_UINT64 : NCCL_INT64);
+    nccl_type = dtype == ACU_F64 ? NCCL_FLOAT64 : dtype == ACU_F32 ? NCCL_FLOAT32 : NCCL_INT64;  // two's complement: one sum for both signs
   } else {
     nccl_op = op == ACU_MIN ? NCCL_MIN : NCCL_MAX;
     nccl_type = is_unsigned ? NCCL_UINT64 : NCCL_INT64;
   }
   ACU_CUDA(ctx, cudaMemcpyAsync(buf, stage, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
-  ACU_NCCL(ctx, api->GroupStart());
-  if (nccl_type == NCCL_FLOAT32) {
-    // f32 partials occupy the low 4 bytes of each 8-byte slot: reduce 2n floats (the high
-    // halves are zero and stay zero under sum)
-    ACU_NCCL(ctx, api->AllReduce(buf, buf, (size_t)n * 2, NCCL_FLOAT32, nccl_op, ctx->nccl_comm, ctx->stream));
+  if (nccl_op == NCCL_SUM && nccl_type == NCCL_INT64) {
+    // integer sums and the valid counts are both int64 sums: ONE all-reduce over 2n words
+    ACU_NCCL(ctx, api->AllReduce(buf, buf, (size_t)n * 2, NCCL_INT64, NCCL_SUM, ctx->nccl_comm, ctx->stream));
   } else {
-    ACU_NCCL(ctx, api->AllReduce(buf, buf, (size_t)n, nccl_type, nccl_op, ctx->nccl_comm, ctx->stream));
+    ACU_NCCL(ctx, api->GroupStart());
+    if (nccl_type == NCCL_FLOAT32) {
+      // f32 partials occupy the low 4 bytes of each 8-byte slot: reduce 2n floats (the high
+      // halves are zero and stay zero under sum)
+      ACU_NCCL(ctx, api->AllReduce(buf, buf, (size_t)n * 2, NCCL_FLOAT32, nccl_op, ctx->nccl_comm, ctx->stream));
+    } else {
+      ACU_NCCL(ctx, api->AllReduce(buf, buf, (size_t)n, nccl_type, nccl_op, ctx->nccl_comm, ctx->stream));
+    }
+    ACU_NCCL(ctx, api->AllReduce(buf + (size_t)n * 8, buf + (size_t)n * 8, (size_t)n, NCCL_INT64, NCCL_SUM, ctx->nccl_comm, ctx->stream));
+    ACU_NCCL(ctx, api->GroupEnd());
   }
-  ACU_NCCL(ctx, api->AllReduce(buf + (size_t)n * 8, buf + (size_t)n * 8, (size_t)n, NCCL_INT64, NCCL_SUM, ctx->nccl_comm, ctx->stream));
-  ACU_NCCL(ctx, api->GroupEnd());
   ACU_CUDA(ctx, cudaMemcpyAsync(stage, buf, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
   ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   for (int i = 0; i < n; ++i) {

@@ -454,6 +454,62 @@ inline const char *dtype_display(DataType t) {
   static const char *n[] = {"Int8", "Int16", "Int32", "Int64", "UInt8", "UInt16", "UInt32", "UInt64", "Float32", "Float64", "Boolean", "Utf8"};
   return n[(int)t];
 }
+// One acu_column per column of a RecordBatch (include/arrow_cuda.h: acu_column)
+inline acu_column column_view(const Array &a) {
+  acu_column c{};
+  c.array = a.view();
+  if (a.data_type() == DataType::Boolean) {
+    c.kind = ACU_COL_BOOLEAN;
+  } else if (a.data_type() == DataType::Utf8) {
+    const auto &s = static_cast<const StringArray &>(a);
+    c.kind = ACU_COL_BYTES;
+    c.width = 4;
+    c.array.values = s.offsets().data();
+    c.array.values_offset = 0;
+    c.data = static_cast<const uint8_t *>(s.value_data().data());
+  } else {
+    c.kind = ACU_COL_PRIMITIVE;
+    c.width = dtype_width(a.data_type());
+  }
+  return c;
+}
+
+// Output buffers of a record-batch call: values / offsets, validity and (Utf8) value bytes per column.
+struct BatchOutputs {
+  std::vector<Buffer> values, validity, data;
+  std::vector<acu_column_out> outs;
+  void allocate(const std::vector<ArrayRef> &cols, int64_t rows, const std::vector<int64_t> &data_caps) {
+    const size_t n = cols.size();
+    values.resize(n);
+    validity.resize(n);
+    data.resize(n);
+    outs.assign(n, acu_column_out{});
+    for (size_t i = 0; i < n; ++i) {
+      const DataType dt = cols[i]->data_type();
+      const size_t vbytes = dt == DataType::Boolean ? acu_bitmap_bytes(rows) : dt == DataType::Utf8 ? (size_t)(rows + 1) * 4 : (size_t)rows * dtype_width(dt);
+      values[i] = Buffer::allocate(vbytes);
+      validity[i] = Buffer::allocate(acu_bitmap_bytes(rows));
+      outs[i].array.values = values[i].data();
+      outs[i].array.validity = static_cast<uint8_t *>(validity[i].data());
+      if (dt == DataType::Utf8 && data_caps[i] >= 0) {
+        data[i] = Buffer::allocate((size_t)data_caps[i]);
+        outs[i].data = static_cast<uint8_t *>(data[i].data());
+        outs[i].data_capacity = data_caps[i];
+      }
+    }
+  }
+  std::vector<ArrayRef> wrap(const std::vector<ArrayRef> &cols) {
+    std::vector<ArrayRef> res;
+    for (size_t i = 0; i < cols.size(); ++i) {
+      const DataType dt = cols[i]->data_type();
+      const acu_array_out &o = outs[i].array;
+      if (dt == DataType::Boolean) res.push_back(std::make_shared<BooleanArray>(values[i], 0, o.len, out_nulls(o, validity[i])));
+      else if (dt == DataType::Utf8) res.push_back(std::make_shared<StringArray>(values[i], data[i], o.len, out_nulls(o, validity[i])));
+      else res.push_back(make_primitive(dt, values[i], o.len, out_nulls(o, validity[i])));
+    }
+    return res;
+  }
+};
 }  // namespace detail
 
 // ---- filter (arrow-select/src/filter.rs) ------------------------------------------------
@@ -493,15 +549,28 @@ class FilterPredicate {
     if ((st = acu_filter_primitive(c.raw(), plan_.get(), w, &v, &o)) != ACU_OK) return c.last_error(st);
     return detail::make_primitive(values.data_type(), vb, o.len, detail::out_nulls(o, nb));
   }
-  // FilterPredicate::filter_record_batch (filter.rs:459-478): one plan, every column
+  // FilterPredicate::filter_record_batch (filter.rs:459-478): one plan, every column, ONE synchronisation
+  // (acu_filter_record_batch queues the kernels of all columns back to back).
   Result<RecordBatch> filter_record_batch(const RecordBatch &batch) const {
-    std::vector<ArrayRef> cols;
-    for (const auto &col : batch.columns()) {
-      auto r = filter(*col);
-      if (r.is_err()) return r.unwrap_err();
-      cols.push_back(r.unwrap());
+    Context &c = Context::get();
+    const auto &cols = batch.columns();
+    if (cols.empty()) return RecordBatch(batch.schema(), {}, count());
+    std::vector<acu_column> in;
+    std::vector<int64_t> caps;
+    for (const auto &col : cols) {
+      in.push_back(detail::column_view(*col));
+      // a filtered Utf8 column never holds more bytes than its source
+      caps.push_back(col->data_type() == DataType::Utf8 ? (int64_t) static_cast<const StringArray &>(*col).value_data().len() : -1);
     }
-    return RecordBatch(batch.schema(), std::move(cols), count());
+    detail::BatchOutputs out;
+    out.allocate(cols, count(), caps);
+    std::vector<ArrayRef> res;
+    for (size_t first = 0; first < cols.size(); first += ACU_MAX_BATCH_COLUMNS) {
+      const int32_t n = (int32_t)std::min<size_t>(ACU_MAX_BATCH_COLUMNS, cols.size() - first);
+      acu_status st = acu_filter_record_batch(c.raw(), plan_.get(), n, in.data() + first, out.outs.data() + first);
+      if (st != ACU_OK) return c.last_error(st);
+    }
+    return RecordBatch(batch.schema(), out.wrap(cols), count());
   }
  private:
   std::shared_ptr<acu_filter_plan> plan_;
@@ -568,14 +637,45 @@ inline Result<ArrayRef> take(const Array &values, const Array &indices, std::opt
   return detail::make_primitive(values.data_type(), vb, o.len, detail::out_nulls(o, nb));
 }
 
-inline Result<RecordBatch> take_record_batch(const RecordBatch &batch, const Array &indices) {  // take.rs:1123-1133
-  std::vector<ArrayRef> cols;
-  for (const auto &col : batch.columns()) {
-    auto r = take(*col, indices, std::nullopt);
-    if (r.is_err()) return r.unwrap_err();
-    cols.push_back(r.unwrap());
+// take.rs:1123-1133: every column gathered with the same indices, one synchronisation per (up to 64-column) call.
+// Utf8 columns are sized by a first pass without a byte buffer (duplicated indices can grow a column beyond its source).
+inline Result<RecordBatch> take_record_batch(const RecordBatch &batch, const Array &indices) {
+  Context &c = Context::get();
+  const DataType it = indices.data_type();
+  if (dtype_width(it) == 0 || it == DataType::Float32 || it == DataType::Float64)
+    return ArrowError{ACU_ERR_INVALID_ARGUMENT, std::string("Invalid argument error: Take only supported for integers, got ") + detail::dtype_display(it)};
+  const auto &cols = batch.columns();
+  const int64_t m = indices.len();
+  if (cols.empty()) return RecordBatch(batch.schema(), {}, m);
+  std::vector<acu_column> in;
+  bool any_utf8 = false;
+  for (const auto &col : cols) {
+    in.push_back(detail::column_view(*col));
+    any_utf8 = any_utf8 || col->data_type() == DataType::Utf8;
   }
-  return RecordBatch::try_new(batch.schema(), std::move(cols));
+  acu_array ix = indices.view();
+  std::vector<int64_t> caps(cols.size(), -1);
+  auto run = [&](detail::BatchOutputs &out) -> acu_status {
+    for (size_t first = 0; first < cols.size(); first += ACU_MAX_BATCH_COLUMNS) {
+      const int32_t n = (int32_t)std::min<size_t>(ACU_MAX_BATCH_COLUMNS, cols.size() - first);
+      acu_status st = acu_take_record_batch(c.raw(), n, in.data() + first, &ix, (acu_dtype)dtype_code(it), 0, out.outs.data() + first);
+      if (st != ACU_OK) return st;
+    }
+    return ACU_OK;
+  };
+  if (any_utf8) {  // sizing pass (offsets + nulls only)
+    detail::BatchOutputs sizing;
+    sizing.allocate(cols, m, caps);
+    acu_status st = run(sizing);
+    if (st != ACU_OK) return c.last_error(st);
+    for (size_t i = 0; i < cols.size(); ++i)
+      if (cols[i]->data_type() == DataType::Utf8) caps[i] = sizing.outs[i].data_len;
+  }
+  detail::BatchOutputs out;
+  out.allocate(cols, m, caps);
+  acu_status st = run(out);
+  if (st != ACU_OK) return c.last_error(st);
+  return RecordBatch(batch.schema(), out.wrap(cols), m);
 }
 
 // ---- kernels::numeric (arrow-arith/src/numeric.rs) ---------------------------------------
@@ -650,6 +750,32 @@ ACU_CMP(gt, ACU_GT, ">") ACU_CMP(gt_eq, ACU_GT_EQ, ">=") ACU_CMP(distinct, ACU_D
 ACU_CMP(not_distinct, ACU_NOT_DISTINCT, "IS NOT DISTINCT FROM")
 #undef ACU_CMP
 }  // namespace cmp
+
+// ---- kernels::boolean (arrow-arith/src/boolean.rs) -------------------------------------------
+// `and`, `or`, `not` are reserved alternative tokens in C++: the mirror appends an underscore.
+namespace boolean {
+namespace detail4 {
+inline Result<BooleanArray> boolean_op(acu_bool_op op, const Array &a, const Array *b) {
+  Context &c = Context::get();
+  const int64_t n = a.len();
+  Buffer vb, nb;
+  acu_array av = a.view(), bv{};
+  if (b) bv = b->view();
+  acu_array_out o = compute::detail::make_out(vb, nb, acu_bitmap_bytes(std::max<int64_t>(n, 1)), std::max<int64_t>(n, 1));
+  acu_status st = acu_boolean(c.raw(), op, &av, b ? &bv : nullptr, &o);
+  if (st != ACU_OK) return c.last_error(st);
+  return BooleanArray(vb, 0, o.len, compute::detail::out_nulls(o, nb));
+}
+}  // namespace detail4
+inline Result<BooleanArray> and_(const BooleanArray &l, const BooleanArray &r) { return detail4::boolean_op(ACU_BOOL_AND, l, &r); }
+inline Result<BooleanArray> or_(const BooleanArray &l, const BooleanArray &r) { return detail4::boolean_op(ACU_BOOL_OR, l, &r); }
+inline Result<BooleanArray> and_not(const BooleanArray &l, const BooleanArray &r) { return detail4::boolean_op(ACU_BOOL_AND_NOT, l, &r); }
+inline Result<BooleanArray> and_kleene(const BooleanArray &l, const BooleanArray &r) { return detail4::boolean_op(ACU_BOOL_AND_KLEENE, l, &r); }
+inline Result<BooleanArray> or_kleene(const BooleanArray &l, const BooleanArray &r) { return detail4::boolean_op(ACU_BOOL_OR_KLEENE, l, &r); }
+inline Result<BooleanArray> not_(const BooleanArray &a) { return detail4::boolean_op(ACU_BOOL_NOT, a, nullptr); }
+inline Result<BooleanArray> is_null(const Array &a) { return detail4::boolean_op(ACU_BOOL_IS_NULL, a, nullptr); }
+inline Result<BooleanArray> is_not_null(const Array &a) { return detail4::boolean_op(ACU_BOOL_IS_NOT_NULL, a, nullptr); }
+}  // namespace boolean
 }  // namespace kernels
 
 // ---- cast (arrow-cast/src/cast/mod.rs) -------------------------------------------------------

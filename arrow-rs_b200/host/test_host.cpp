@@ -120,6 +120,55 @@ static void test_filter_record_batch() {
   CHECK(as_primitive<double>(out.column(2)).to_vec() == (std::vector<O<double>>{0.5, 1.5, 3.5}));
 }
 
+// take.rs:1123-1133 take_record_batch (doc example take.rs:1108-1121): every column, same indices; here with a
+// repeated index (a Utf8 column that grows) and a null index
+static void test_take_record_batch() {
+  Schema schema{{"a", DataType::Int32}, {"b", DataType::Utf8}, {"c", DataType::Boolean}};
+  std::vector<ArrayRef> cols{
+      std::make_shared<Int32Array>(Int32Array::from(std::vector<O<int32_t>>{1, N, 3, 4})),
+      std::make_shared<StringArray>(StringArray::from(std::vector<O<std::string>>{std::string("w"), std::string("xx"), N, std::string("zzzz")})),
+      std::make_shared<BooleanArray>(BooleanArray::from(std::vector<bool>{true, false, true, false}))};
+  auto batch = RecordBatch::try_new(schema, cols).unwrap();
+  auto idx = UInt32Array::from(std::vector<O<uint32_t>>{3, 3, N, 0, 1, 2});
+  auto out = take_record_batch(batch, idx).unwrap();
+  CHECK_EQ(6, out.num_rows());
+  CHECK(as_primitive<int32_t>(out.column(0)).to_vec() == (std::vector<O<int32_t>>{4, 4, N, 1, N, 3}));
+  CHECK(as_string(out.column(1)).to_vec() ==
+        (std::vector<O<std::string>>{std::string("zzzz"), std::string("zzzz"), N, std::string("w"), std::string("xx"), N}));
+  CHECK(as_boolean(out.column(2)).to_vec() == (std::vector<O<bool>>{false, false, N, true, false, true}));
+  // filter -> take -> same rows as filtering the taken batch's source positions
+  auto f = filter_record_batch(batch, BooleanArray::from(std::vector<bool>{true, false, true, true})).unwrap();
+  auto t = take_record_batch(f, UInt32Array::from(std::vector<uint32_t>{2, 0})).unwrap();
+  CHECK(as_primitive<int32_t>(t.column(0)).to_vec() == (std::vector<O<int32_t>>{4, 1}));
+  CHECK(as_string(t.column(1)).to_vec() == (std::vector<O<std::string>>{std::string("zzzz"), std::string("w")}));
+}
+
+// arrow-arith/src/boolean.rs:473 test_bool_array_and_kleene_nulls, :514 or_kleene, :422 or, :631 not (sliced), :835 is_null
+static void test_boolean_kernels() {
+  using namespace arrow_cuda::compute::kernels::boolean;
+  using OB = O<bool>;
+  auto a = BooleanArray::from(std::vector<OB>{N, N, N, false, false, false, true, true, true});
+  auto b = BooleanArray::from(std::vector<OB>{N, false, true, N, false, true, N, false, true});
+  CHECK(and_kleene(a, b).unwrap().to_vec() == (std::vector<OB>{N, false, N, false, false, false, N, false, true}));
+  CHECK(or_kleene(a, b).unwrap().to_vec() == (std::vector<OB>{N, N, true, N, false, true, true, true, true}));
+  CHECK(or_(a, b).unwrap().to_vec() == (std::vector<OB>{N, N, N, N, false, true, N, true, true}));
+  CHECK(and_(a, b).unwrap().to_vec() == (std::vector<OB>{N, N, N, N, false, false, N, false, true}));
+  auto s = BooleanArray::from(std::vector<OB>{N, true, false, N, true}).slice(1, 4);
+  CHECK(not_(s).unwrap().to_vec() == (std::vector<OB>{false, true, N, false}));
+  auto i = Int32Array::from(std::vector<O<int32_t>>{1, N, 3, N});
+  auto r = is_null(i).unwrap();
+  CHECK(r.to_vec() == (std::vector<OB>{false, true, false, true}));
+  CHECK(!r.nulls().has_value());
+  CHECK(is_not_null(i).unwrap().to_vec() == (std::vector<OB>{true, false, true, false}));
+  auto e = and_(BooleanArray::from(std::vector<bool>{true, false}), BooleanArray::from(std::vector<bool>{true}));
+  CHECK(e.is_err());
+  CHECK_EQ(e.unwrap_err().to_string(), std::string("Compute error: Cannot perform bitwise operation on arrays of different length"));
+  // the predicate never leaves the device: cmp -> and_kleene -> filter
+  auto x = Int32Array::from(std::vector<O<int32_t>>{5, 1, N, 7, 2});
+  auto m = and_kleene(arrow_cuda::compute::kernels::cmp::gt(x, new_scalar<int32_t>(1)).unwrap(), BooleanArray::from(std::vector<bool>{true, true, true, false, true})).unwrap();
+  CHECK(as_primitive<int32_t>(filter(x, m).unwrap()).to_vec() == (std::vector<O<int32_t>>{5, 2}));
+}
+
 // arrow-select/src/take.rs:1371-1440 test_take_primitive
 template <class T>
 static void take_primitive_case() {
@@ -334,6 +383,8 @@ int main() {
       {"null_mask_and_fast_path", test_null_mask_and_fast_path},
       {"filter_predicate_too_long", test_filter_predicate_too_long},
       {"filter_record_batch", test_filter_record_batch},
+      {"take_record_batch", test_take_record_batch},
+      {"boolean_kernels", test_boolean_kernels},
       {"take_primitive", test_take_primitive},
       {"take_with_offset", test_take_with_offset},
       {"take_bool", test_take_bool},

@@ -202,6 +202,9 @@ def make_arr(abi, values, validity, n, null_count):
     return a
 
 
+ALLREDUCE_WALL = [0.0, 0]  # host seconds spent inside the final-reduce call (includes waiting for the slowest rank), calls
+
+
 def hot_path_step(ctx, abi, pred, col, idx, a, b, out_filter, out_take, out_add, allreduce):
     """One pass of the hot path through the C ABI (device pointers):
     filter(col, pred) -> take(col, idx) -> add(a, b) -> sum(taken) [-> NCCL all-reduce]."""
@@ -220,7 +223,10 @@ def hot_path_step(ctx, abi, pred, col, idx, a, b, out_filter, out_take, out_add,
     ctx.check(lib.acu_aggregate(h, abi.I64, abi.SUM, C.byref(taken), C.byref(bits), C.byref(cnt)))
     if allreduce:
         pb, pc = (C.c_uint64 * 1)(bits.value), (C.c_int64 * 1)(cnt.value)
+        t0 = time.perf_counter()
         ctx.check(lib.acu_comm_allreduce_aggregates(h, abi.I64, abi.SUM, pb, pc, 1))
+        ALLREDUCE_WALL[0] += time.perf_counter() - t0
+        ALLREDUCE_WALL[1] += 1
         return pb[0], pc[0]
     return bits.value, cnt.value
 
@@ -452,6 +458,7 @@ def run_gpu(args):
         wl.step()
     barrier()
     ctx.check(lib.acu_kernel_stats_reset(h))
+    ALLREDUCE_WALL[0], ALLREDUCE_WALL[1] = 0.0, 0
     launches0 = ctx.launch_count()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -544,6 +551,7 @@ def run_gpu(args):
                      "algorithmic_bytes": ab["add"], "peak_source": peak_src, "per_op": roof_ops},
         "kernels": kstats,
         "gpu_launches": launches,
+        "final_reduce_ms_per_step": (1e3 * ALLREDUCE_WALL[0] / max(ALLREDUCE_WALL[1], 1)) if world > 1 else 0.0,
         "clocks": clocks,
         "e2e": e2e,
         "check": {"sum_bits": int(total_bits), "valid_rows": int(total_cnt)},

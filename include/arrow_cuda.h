@@ -305,6 +305,28 @@ acu_status acu_cast_numeric(acu_ctx *ctx, acu_dtype from, acu_dtype to, int32_t 
                             const acu_array *a, acu_array_out *out);
 
 /* ------------------------------------------------------------------------- */
+/* boolean — arrow-arith/src/boolean.rs (predicate construction before filter) */
+/* ------------------------------------------------------------------------- */
+typedef enum acu_bool_op {
+  ACU_BOOL_AND = 0,         /* and        boolean.rs:256  values a&b at every slot, nulls = union */
+  ACU_BOOL_OR = 1,          /* or         boolean.rs:273 */
+  ACU_BOOL_AND_NOT = 2,     /* and_not    boolean.rs:291  a & !b */
+  ACU_BOOL_AND_KLEENE = 3,  /* and_kleene boolean.rs:60   false AND null = false */
+  ACU_BOOL_OR_KLEENE = 4,   /* or_kleene  boolean.rs:156  true OR null = true */
+  ACU_BOOL_NOT = 5,         /* not        boolean.rs:310  (b == NULL) */
+  ACU_BOOL_IS_NULL = 6,     /* is_null    boolean.rs:327  any array kind: only a's validity/len are read; b == NULL */
+  ACU_BOOL_IS_NOT_NULL = 7  /* is_not_null boolean.rs:347 */
+} acu_bool_op;
+/* a, b: BooleanArrays (values = bitmaps with bit offsets). out->values receives the result
+ * bitmap (bit offset 0, whole u64 words, bits >= len zero). The result carries a validity
+ * buffer exactly when the reference's does: and/or/and_not/kleene when either input has
+ * one (even without nulls), not when `a` has one, is_null/is_not_null never. Length
+ * mismatch => ACU_ERR_COMPUTE "Cannot perform bitwise operation on arrays of different
+ * length". */
+acu_status acu_boolean(acu_ctx *ctx, acu_bool_op op, const acu_array *a, const acu_array *b,
+                       acu_array_out *out);
+
+/* ------------------------------------------------------------------------- */
 /* aggregate — arrow-arith/src/aggregate.rs                                  */
 /* ------------------------------------------------------------------------- */
 /* sum/min/max (aggregate.rs:943,1012,1027): *out_bits = the native result's bit

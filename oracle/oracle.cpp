@@ -1199,6 +1199,52 @@ acu_status orc_neg(acu_dtype dtype, int32_t checked, const acu_array *a, acu_arr
   return ACU_ERR_NOT_YET_IMPLEMENTED;
 }
 
+// arrow-arith/src/boolean.rs: and :256, or :273, and_not :291 (binary_boolean_kernel :224-243), and_kleene :60-124,
+// or_kleene :156-222, not :310-314, is_null :327-334, is_not_null :347-354 — restated row by row with Option<bool>
+// semantics rather than the reference's word-level bit formulas, so that the formulas themselves are checked.
+acu_status orc_boolean(acu_bool_op op, const acu_array *a, const acu_array *b, acu_array_out *out) {
+  const bool binary = op <= ACU_BOOL_OR_KLEENE;
+  if (binary && a->len != b->len)
+    return fail(ACU_ERR_COMPUTE, -1, 0, 0, 0, "Cannot perform bitwise operation on arrays of different length");
+  const int64_t n = a->len;
+  out->len = n;
+  out->null_count = 0;
+  const bool nulls_out = op == ACU_BOOL_NOT ? a->validity != nullptr : binary ? (a->validity != nullptr || b->validity != nullptr) : false;
+  out->has_validity = nulls_out;
+  uint8_t *ov = static_cast<uint8_t *>(out->values);
+  memset(ov, 0, acu_bitmap_bytes(n));
+  if (nulls_out) memset(out->validity, 0, acu_bitmap_bytes(n));
+  int64_t valid_rows = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const bool a_valid = !a->validity || get_bit(a->validity, a->validity_offset + i);
+    const bool av = (op == ACU_BOOL_IS_NULL || op == ACU_BOOL_IS_NOT_NULL) ? false : get_bit(static_cast<const uint8_t *>(a->values), a->values_offset + i);
+    const bool b_valid = !binary || !b->validity || get_bit(b->validity, b->validity_offset + i);
+    const bool bv = binary ? get_bit(static_cast<const uint8_t *>(b->values), b->values_offset + i) : false;
+    bool v = false, valid = true;
+    switch (op) {
+      case ACU_BOOL_AND: v = av && bv; valid = a_valid && b_valid; break;          // the raw bits combine even under nulls
+      case ACU_BOOL_OR: v = av || bv; valid = a_valid && b_valid; break;
+      case ACU_BOOL_AND_NOT: v = av && !bv; valid = a_valid && b_valid; break;
+      case ACU_BOOL_AND_KLEENE:
+        v = av && bv;
+        // known false on either side decides; otherwise both must be known
+        valid = (a_valid && b_valid) || (a_valid && !av) || (b_valid && !bv);
+        break;
+      case ACU_BOOL_OR_KLEENE:
+        v = av || bv;
+        valid = (a_valid && b_valid) || (a_valid && av) || (b_valid && bv);
+        break;
+      case ACU_BOOL_NOT: v = !av; valid = a_valid; break;
+      case ACU_BOOL_IS_NULL: v = !a_valid; break;
+      default: v = a_valid; break;
+    }
+    if (v) set_bit(ov, i);
+    if (nulls_out && valid) { set_bit(out->validity, i); ++valid_rows; }
+  }
+  if (nulls_out) out->null_count = n - valid_rows;
+  return ACU_OK;
+}
+
 acu_status orc_cmp(acu_dtype dtype, acu_cmp_op op, const acu_array *a, const acu_array *b, acu_array_out *out) {
   DISPATCH_DTYPE(dtype, cmp_typed, op, a, b, out)
   return ACU_ERR_NOT_YET_IMPLEMENTED;

@@ -394,6 +394,60 @@ mix = [{0: "-inf", 1: -F64_MAX, 2: F64_MAX, 4: "inf", 5: "nan"}.get(i % 10, floa
 case("min_inf_and_nans", G + ":1483", "min", a=arr("float64", mix), expect={"scalar": "-inf"})
 case("max_inf_and_nans", G + ":1483", "max", a=arr("float64", mix), expect={"scalar": "nan"})
 
+# =========================================================================================
+# boolean — arrow-arith/src/boolean.rs (predicate construction)
+# =========================================================================================
+B = "arrow-arith/src/boolean.rs"
+T, Fa = True, False
+case("bool_and", B + ":364", "and_", a=arr("bool", [Fa, Fa, T, T]), b=arr("bool", [Fa, T, Fa, T]), expect={"data": [Fa, Fa, Fa, T], "no_validity": True})
+case("bool_or", B + ":375", "or_", a=arr("bool", [Fa, Fa, T, T]), b=arr("bool", [Fa, T, Fa, T]), expect={"data": [Fa, T, T, T], "no_validity": True})
+case("bool_and_not", B + ":386", "and_not", a=arr("bool", [Fa, Fa, T, T]), b=arr("bool", [Fa, T, Fa, T]), expect={"data": [Fa, Fa, T, Fa]})
+case("bool_and_not_sliced", B + ":398", "and_not", a=arr("bool", [T, Fa, T, Fa, T, Fa, T], slice=(2, 3)),
+     b=arr("bool", [Fa, T, Fa, T, Fa, T, Fa], slice=(2, 3)), expect={"data": [T, Fa, T]})  # == and(a, not(b)) evaluated by hand
+case("bool_and_not_sliced_different_offsets", B + ":410", "and_not", a=arr("bool", [Fa, T, T, Fa, T, Fa, T], slice=(1, 4)),
+     b=arr("bool", [T, Fa, Fa, T, Fa, T, Fa], slice=(2, 4)), expect={"data": [T, Fa, Fa, Fa]})
+NINE_A = [None, None, None, Fa, Fa, Fa, T, T, T]
+NINE_B = [None, Fa, T, None, Fa, T, None, Fa, T]
+case("bool_or_nulls", B + ":422", "or_", a=arr("bool", NINE_A), b=arr("bool", NINE_B), expect={"data": [None, None, None, None, Fa, T, None, T, T]})
+case("bool_and_nulls", B + ":643", "and_", a=arr("bool", NINE_A), b=arr("bool", NINE_B), expect={"data": [None, None, None, None, Fa, Fa, None, Fa, T]})
+case("bool_and_kleene_nulls", B + ":473", "and_kleene", a=arr("bool", NINE_A), b=arr("bool", NINE_B),
+     expect={"data": [None, Fa, None, Fa, Fa, Fa, None, Fa, T]})
+case("bool_or_kleene_nulls", B + ":514", "or_kleene", a=arr("bool", NINE_A), b=arr("bool", NINE_B),
+     expect={"data": [None, None, T, None, Fa, T, T, T, T]})
+case("bool_or_kleene_right_sided_nulls", B + ":555", "or_kleene", a=arr("bool", [Fa, Fa, Fa, T, T, T]), b=arr("bool", [T, Fa, None, T, Fa, None]),
+     expect={"data": [T, Fa, None, T, T, T]})
+case("bool_or_kleene_left_sided_nulls", B + ":588", "or_kleene", a=arr("bool", [T, Fa, None, T, Fa, None]), b=arr("bool", [Fa, Fa, Fa, T, T, T]),
+     expect={"data": [T, Fa, None, T, T, T]})
+case("bool_kleene_no_remainder", B + ":463", "or_kleene", a=arr("bool", [T] * 1024), b=arr("bool", [None] * 1024),
+     expect={"data": [T] * 1024})
+case("bool_and_kleene_doc", B + ":50-57", "and_kleene", a=arr("bool", [T, Fa, None]), b=arr("bool", [None, None, None]), expect={"data": [None, Fa, None]})
+case("bool_or_kleene_doc", B + ":146-153", "or_kleene", a=arr("bool", [T, Fa, None]), b=arr("bool", [None, None, None]), expect={"data": [T, None, None]})
+case("bool_not", B + ":621", "not_", a=arr("bool", [Fa, T]), expect={"data": [T, Fa], "no_validity": True})
+case("bool_not_sliced", B + ":631", "not_", a=arr("bool", [None, T, Fa, None, T], slice=(1, 4)), expect={"data": [Fa, T, None, Fa]})
+TW_A = [Fa] * 10 + [T, T]
+TW_B = [Fa] * 9 + [T, Fa, T]
+case("bool_and_sliced_same_offset", B + ":684", "and_", a=arr("bool", TW_A, slice=(8, 4)), b=arr("bool", TW_B, slice=(8, 4)), expect={"data": [Fa, Fa, Fa, T]})
+case("bool_and_sliced_same_offset_mod8", B + ":705", "and_", a=arr("bool", [Fa, Fa, T, T] + [Fa] * 8, slice=(0, 4)), b=arr("bool", TW_B, slice=(8, 4)),
+     expect={"data": [Fa, Fa, Fa, T]})
+case("bool_and_sliced_offset1", B + ":726", "and_", a=arr("bool", TW_A, slice=(8, 4)), b=arr("bool", [Fa, T, Fa, T]), expect={"data": [Fa, Fa, Fa, T]})
+case("bool_and_sliced_offset2", B + ":743", "and_", a=arr("bool", [Fa, Fa, T, T]), b=arr("bool", TW_B, slice=(8, 4)), expect={"data": [Fa, Fa, Fa, T]})
+case("bool_and_nulls_offset", B + ":760", "and_", a=arr("bool", [None, Fa, T, None, T], slice=(1, 4)), b=arr("bool", [None, None, T, Fa, T, T], slice=(2, 4)),
+     expect={"data": [Fa, Fa, None, T]})
+case("bool_and_length_mismatch", B + ":232-236", "and_", a=arr("bool", [T, Fa]), b=arr("bool", [T]),
+     expect_error="Compute error: Cannot perform bitwise operation on arrays of different length")
+case("bool_and_kleene_length_mismatch", B + ":61-65", "and_kleene", a=arr("bool", [T, Fa]), b=arr("bool", [T]),
+     expect_error="Compute error: Cannot perform bitwise operation on arrays of different length")
+case("is_null_nonnull", B + ":785", "is_null", a=arr("int32", [1, 2, 3, 4]), expect={"data": [Fa] * 4, "no_validity": True})
+case("is_null_nonnull_offset", B + ":797", "is_null", a=arr("int32", [1, 2, 3, 4, 5, 6, 7, 8, 7, 6, 5, 4, 3, 2, 1], slice=(8, 4)), expect={"data": [Fa] * 4, "no_validity": True})
+case("is_not_null_nonnull", B + ":810", "is_not_null", a=arr("int32", [1, 2, 3, 4]), expect={"data": [T] * 4, "no_validity": True})
+case("is_not_null_nonnull_offset", B + ":822", "is_not_null", a=arr("int32", [1, 2, 3, 4, 5, 6, 7, 8, 7, 6, 5, 4, 3, 2, 1], slice=(8, 4)),
+     expect={"data": [T] * 4, "no_validity": True})
+case("is_null_nullable", B + ":835", "is_null", a=arr("int32", [1, None, 3, None]), expect={"data": [Fa, T, Fa, T], "no_validity": True})
+SIXTEEN = [None] * 8 + [1, None, 2, None, 3, 4, None, None]
+case("is_null_nullable_offset", B + ":847", "is_null", a=arr("int32", SIXTEEN, slice=(8, 4)), expect={"data": [Fa, T, Fa, T], "no_validity": True})
+case("is_not_null_nullable", B + ":878", "is_not_null", a=arr("int32", [1, None, 3, None]), expect={"data": [T, Fa, T, Fa], "no_validity": True})
+case("is_not_null_nullable_offset", B + ":890", "is_not_null", a=arr("int32", SIXTEEN, slice=(8, 4)), expect={"data": [T, Fa, T, Fa], "no_validity": True})
+
 out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "vectors.json")
 with open(out, "w") as f:
     json.dump({"reference": "apache/arrow-rs 59.2.0 @ cd7c6b83", "cases": cases}, f, indent=0)

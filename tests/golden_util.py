@@ -115,6 +115,8 @@ def check_array(expect, res):
             assert _match(e, got[int(k)]), f"slot {k}: expected {e!r}, got {got[int(k)]!r}"
     if expect.get("always_validity"):
         assert res.validity is not None
+    if expect.get("no_validity"):
+        assert res.validity is None
     # cached null_count must agree with the bitmap (NullBuffer invariant)
     if res.validity is not None:
         assert res.null_count == int((~res.valid_mask()).sum())
@@ -147,6 +149,10 @@ def run_case(backend, c):
         if op == "cast":
             return backend.cast(build_array(c["a"]), DT[c["to"]], c.get("safe", True))
         if op in ("sum", "min", "max"):
+            return getattr(backend, op)(build_array(c["a"]))
+        if op in ("and_", "or_", "and_not", "and_kleene", "or_kleene"):
+            return getattr(backend, op)(build_array(c["a"]), build_array(c["b"]))
+        if op in ("not_", "is_null", "is_not_null"):
             return getattr(backend, op)(build_array(c["a"]))
         raise AssertionError("unknown op " + op)
 

@@ -42,6 +42,7 @@ class Oracle:
             "orc_arith": [i32, i32, P(abi.Array), P(abi.Array), P(abi.ArrayOut)],
             "orc_neg": [i32, i32, P(abi.Array), P(abi.ArrayOut)],
             "orc_cmp": [i32, i32, P(abi.Array), P(abi.Array), P(abi.ArrayOut)],
+            "orc_boolean": [i32, P(abi.Array), P(abi.Array), P(abi.ArrayOut)],
             "orc_cast_numeric": [i32, i32, i32, P(abi.Array), P(abi.ArrayOut)],
             "orc_aggregate": [i32, i32, P(abi.Array), i32, P(u64), P(i64)],
             "orc_generate_values": [i32, u64, i64, u64, vp, i64],
@@ -174,6 +175,24 @@ class Oracle:
         ad, bd = acu.host_descriptor(a), acu.host_descriptor(b)
         self.check(self.lib.orc_cmp(a.dtype, op, C.byref(ad), C.byref(bd), C.byref(out)))
         return self._result(out, vals, valid, BOOL)
+
+    # -- boolean (arrow-arith/src/boolean.rs) -------------------------------------------------
+    def boolean(self, op, a, b=None):
+        n = max(a.length, 1)
+        out, vals, valid = self._out(bitmap_bytes(n), n)
+        ad = acu.host_descriptor(a)
+        bd = acu.host_descriptor(b) if b is not None else None
+        self.check(self.lib.orc_boolean(op, C.byref(ad), C.byref(bd) if bd is not None else None, C.byref(out)))
+        return self._result(out, vals, valid, BOOL)
+
+    def and_(self, a, b): return self.boolean(abi.BOOL_AND, a, b)
+    def or_(self, a, b): return self.boolean(abi.BOOL_OR, a, b)
+    def and_not(self, a, b): return self.boolean(abi.BOOL_AND_NOT, a, b)
+    def and_kleene(self, a, b): return self.boolean(abi.BOOL_AND_KLEENE, a, b)
+    def or_kleene(self, a, b): return self.boolean(abi.BOOL_OR_KLEENE, a, b)
+    def not_(self, a): return self.boolean(abi.BOOL_NOT, a)
+    def is_null(self, a): return self.boolean(abi.BOOL_IS_NULL, a)
+    def is_not_null(self, a): return self.boolean(abi.BOOL_IS_NOT_NULL, a)
 
     def eq(self, a, b): return self.cmp(abi.EQ, a, b)
     def neq(self, a, b): return self.cmp(abi.NEQ, a, b)

@@ -362,6 +362,43 @@ def test_cast_fuzz(gpu, oracle, frm, to):
                 assert_same(got, exp, f"cast unsafe {frm}->{to} n={n}", float_nan_ok=True)
 
 
+# ---- boolean (arrow-arith/src/boolean.rs) ----------------------------------------------------
+@pytest.mark.parametrize("op", ["and_", "or_", "and_not", "and_kleene", "or_kleene"])
+def test_boolean_binary_fuzz(gpu, oracle, op):
+    rng = np.random.default_rng(6000 + len(op))
+    for n in SIZES:
+        for an, bn in [(None, None), (0.2, None), (None, 0.2), (0.3, 0.3), (0.0, None)]:
+            a, b = rand_bool(rng, n, 0.5, an, offset=int(rng.integers(0, 70))), rand_bool(rng, n, 0.4, bn, offset=int(rng.integers(0, 9)))
+            assert_same(getattr(gpu, op)(a, b), getattr(oracle, op)(a, b), f"{op} n={n} nulls=({an},{bn})")
+    got, exp = expect_same_error(gpu, oracle, lambda be: getattr(be, op)(rand_bool(np.random.default_rng(1), 5, 0.5, None), rand_bool(np.random.default_rng(2), 6, 0.5, None)))
+    assert got is None and exp is None
+
+
+def test_boolean_unary_fuzz(gpu, oracle):
+    rng = np.random.default_rng(6100)
+    for n in SIZES:
+        for null_p in (None, 0.25, 1.0):
+            a = rand_bool(rng, n, 0.5, null_p, offset=int(rng.integers(0, 70)))
+            assert_same(gpu.not_(a), oracle.not_(a), f"not n={n}")
+            for src in (a, rand_array(rng, abi.I64, n, null_p, offset=3), rand_array(rng, abi.I8, n, null_p)):
+                assert_same(gpu.is_null(src), oracle.is_null(src), f"is_null n={n}")
+                assert_same(gpu.is_not_null(src), oracle.is_not_null(src), f"is_not_null n={n}")
+
+
+def test_predicate_pipeline_on_device(gpu, oracle):
+    """cmp -> and_kleene -> filter: the mask a query engine builds, then applies."""
+    rng = np.random.default_rng(6200)
+    n = 50_000
+    x, y = rand_array(rng, abi.F64, n, 0.1), rand_array(rng, abi.F64, n, 0.1)
+    k = rand_array(rng, abi.I64, n, 0.05, small=True)
+    zero = HostArray.from_list(abi.I64, [0], scalar=True)
+    for be_name in ("gpu",):
+        mask_g = gpu.and_kleene(gpu.lt(x, y), gpu.gt_eq(k, zero))
+        mask_o = oracle.and_kleene(oracle.lt(x, y), oracle.gt_eq(k, zero))
+        assert_same(mask_g, mask_o, "predicate")
+        assert_same(gpu.filter(k, mask_g), oracle.filter(k, mask_o), "filter by device-built predicate")
+
+
 # ---- aggregate -----------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", [abi.I8, abi.I32, abi.I64, abi.U64, abi.F32, abi.F64])
 def test_aggregate_fuzz(gpu, oracle, dtype):
