@@ -32,7 +32,10 @@ NcclApi *nccl_api() {
   if (!tried) {
     tried = true;
     const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
-    for (int i = 0; names[i] && !api.handle; ++i) api.handle = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    // a copy already in the process (e.g. the one torch bundles) wins; otherwise load the system one
+    // privately (RTLD_LOCAL) so that it can never satisfy another library's NCCL symbols
+    for (int i = 0; names[i] && !api.handle; ++i) api.handle = dlopen(names[i], RTLD_NOW | RTLD_NOLOAD);
+    for (int i = 0; names[i] && !api.handle; ++i) api.handle = dlopen(names[i], RTLD_NOW | RTLD_LOCAL);
     if (api.handle) {
       api.GetUniqueId = (int (*)(nccl_unique_id *))dlsym(api.handle, "ncclGetUniqueId");
       api.CommInitRank = (int (*)(nccl_comm_t *, int, nccl_unique_id, int))dlsym(api.handle, "ncclCommInitRank");

@@ -70,6 +70,7 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.gpu, self.samples, self.stop_flag, self.thread, self.max_mhz = gpu_index, [], False, None, None
+        self.t_mark = 0.0  # only samples taken after mark() are reported (the timed region)
 
     def start(self):
         try:
@@ -96,7 +97,7 @@ class ClockSampler:
                         rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
                     except Exception:
                         rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                    self.samples.append((float(mhz), int(rs)))
+                    self.samples.append((float(mhz), int(rs), time.perf_counter()))
                 except Exception:
                     pass
                 time.sleep(0.005)
@@ -104,10 +105,14 @@ class ClockSampler:
         self.thread = threading.Thread(target=loop, daemon=True)
         self.thread.start()
 
+    def mark(self):
+        self.t_mark = time.perf_counter()
+
     def stop(self):
         self.stop_flag = True
         if self.thread:
             self.thread.join(timeout=1.0)
+        self.samples = [(m, r) for m, r, t in self.samples if t >= self.t_mark]
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
         reasons = set()
@@ -429,40 +434,26 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     import acu
     from acu import _abi as abi
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from acu.rendezvous import Group
     ctx = acu.Context(local_rank)
     lib, h = ctx.lib, ctx.h
-    if world > 1:
-        import torch
-        idb = (C.c_uint8 * abi.NCCL_UNIQUE_ID_BYTES)()
-        if rank == 0:
-            assert lib.acu_comm_get_unique_id(idb) == abi.OK
-        t = torch.tensor(list(idb), dtype=torch.uint8, device="cuda")
-        dist.broadcast(t, 0)
-        idb = (C.c_uint8 * abi.NCCL_UNIQUE_ID_BYTES)(*t.cpu().tolist())
-        ctx.check(lib.acu_comm_init(h, idb, rank, world))
-
-    def barrier():
-        ctx.sync()
-        if dist is not None:
-            dist.barrier()
+    group = Group(ctx, rank, local_rank, world)  # NCCL unique-id exchange + acu_comm_init when world > 1
+    barrier = group.barrier
 
     n = args.rows
     wl = Workload(ctx, n, first_row=rank * n)  # weak scaling: every rank owns its own row range
     for _ in range(args.warmup):
         wl.step()
-    barrier()
-    ctx.check(lib.acu_kernel_stats_reset(h))
-    ALLREDUCE_WALL[0], ALLREDUCE_WALL[1] = 0.0, 0
-    launches0 = ctx.launch_count()
+    # the clock sampler (NVML init, a thread) starts BEFORE the barrier: anything rank 0 alone does between the
+    # barrier and its timed region would make the other ranks wait for it inside their first all-reduce
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    ctx.check(lib.acu_kernel_stats_reset(h))
+    ALLREDUCE_WALL[0], ALLREDUCE_WALL[1] = 0.0, 0
+    launches0 = ctx.launch_count()
+    barrier()
+    sampler.mark()
     ms = C.c_float(0)
     ctx.check(lib.acu_timer_start_slot(h, 1))
     for _ in range(args.steps):
@@ -472,11 +463,7 @@ def run_gpu(args):
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.launch_count() - launches0
     step_ms = ms.value / args.steps
-    if dist is not None:
-        import torch
-        t = torch.tensor([step_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # device time, max over ranks
-        step_ms = float(t.item())
+    step_ms = group.max_over_ranks(step_ms)  # device time, max over ranks
     # per-kernel-class device time inside the timed region
     kstats = {}
     for cls, name in enumerate(abi.KERNEL_CLASS_NAMES):
@@ -506,11 +493,7 @@ def run_gpu(args):
                 e2e_check = hs.step()
             ctx.sync()
             e2e_ms = (time.perf_counter() - t_begin) * 1e3 / args.e2e_steps
-            if dist is not None:
-                import torch
-                t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                e2e_ms = float(t.item())
+            e2e_ms = group.max_over_ranks(e2e_ms)
             e2e = {"value": n * world / (e2e_ms * 1e-3) / 1e6, "unit": "Mrows/s", "h2d_bytes_per_step": hs.h2d_bytes,
                    "d2h_bytes_per_step": hs.d2h_bytes, "ms_per_step": e2e_ms, "steps": args.e2e_steps, "rows_per_gpu": n,
                    "mode": args.e2e_mode, "batch_rows": args.e2e_batch_rows, "streams": args.e2e_workers,
@@ -521,9 +504,8 @@ def run_gpu(args):
             e2e = {"value": None, "unit": "Mrows/s", "skipped": f"host RAM: need {need * world >> 30} GiB pinned, {avail >> 30} GiB available"}
 
     if rank != 0:
+        group.close()
         ctx.close()
-        if dist is not None:
-            dist.destroy_process_group()
         return
     peak, peak_src = peaks()
     ab = algorithmic_bytes(n, wl.m)
@@ -551,6 +533,7 @@ def run_gpu(args):
                      "algorithmic_bytes": ab["add"], "peak_source": peak_src, "per_op": roof_ops},
         "kernels": kstats,
         "gpu_launches": launches,
+        "ms_per_step_rank0": ms.value / args.steps,
         "final_reduce_ms_per_step": (1e3 * ALLREDUCE_WALL[0] / max(ALLREDUCE_WALL[1], 1)) if world > 1 else 0.0,
         "clocks": clocks,
         "e2e": e2e,
@@ -559,9 +542,8 @@ def run_gpu(args):
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(args, from_ctx=(ctx, wl))
     print(json.dumps(line))
+    group.close()
     ctx.close()
-    if dist is not None:
-        dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------

@@ -150,3 +150,27 @@ def test_total_order_key_round_trip_and_order():
     for x, k in zip(xs, keys):
         y = shard.from_total_order_key(k, abi.F64)
         assert np.array([x]).view(np.uint64)[0] == np.array([y]).view(np.uint64)[0]
+
+
+def _rendezvous_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    from acu.rendezvous import Group
+    g = object.__new__(Group)  # the transport alone: no ctx / NCCL on a CPU box
+    g.rank, g.world = rank, world
+    payload = bytes(range(128)) if rank == 0 else b""
+    q.put((rank, g._socket_broadcast(payload)))
+
+
+def test_socket_rendezvous_world_3():
+    """The torch-free NCCL-unique-id exchange of the benches (acu/rendezvous.py): rank 0 -> every rank."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29000 + (os.getpid() % 500)
+    procs = [ctx.Process(target=_rendezvous_worker, args=(r, 3, port, q)) for r in (1, 2, 0)]  # rank 0 last: the others must retry
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=60) for _ in range(3))
+    for p in procs:
+        p.join(timeout=30)
+    assert all(got[r] == bytes(range(128)) for r in range(3))

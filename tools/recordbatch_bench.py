@@ -263,28 +263,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     import acu
     from acu import _abi as abi
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from acu.rendezvous import Group
     ctx = acu.Context(local_rank)
     lib, h = ctx.lib, ctx.h
-    if world > 1:
-        import torch
-        idb = (C.c_uint8 * abi.NCCL_UNIQUE_ID_BYTES)()
-        if rank == 0:
-            assert lib.acu_comm_get_unique_id(idb) == abi.OK
-        t = torch.tensor(list(idb), dtype=torch.uint8, device="cuda")
-        dist.broadcast(t, 0)
-        idb = (C.c_uint8 * abi.NCCL_UNIQUE_ID_BYTES)(*t.cpu().tolist())
-        ctx.check(lib.acu_comm_init(h, idb, rank, world))
-
-    def barrier():
-        ctx.sync()
-        if dist is not None:
-            dist.barrier()
+    group = Group(ctx, rank, local_rank, world)
+    barrier = group.barrier
 
     tb = Table(ctx, abi, rank, args.batches, args.batch_rows, args.selectivity, args.nulls)
     step = tb.step_per_column if args.per_column else tb.step
@@ -300,11 +283,7 @@ def main():
     ctx.check(lib.acu_timer_stop_slot(h, 1, C.byref(ms)))
     barrier()
     step_ms = ms.value / args.steps
-    if dist is not None:
-        import torch
-        t = torch.tensor([step_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_ms = float(t.item())
+    step_ms = group.max_over_ranks(step_ms)
     names = ["arith", "cmp", "cast", "filter", "filter_plan", "take", "reduce", "bytes"]
     kern = {}
     for cls, nm in enumerate(names):
@@ -325,8 +304,7 @@ def main():
             "algorithmic_bytes_per_step": alg, "achieved_gbs": alg / (step_ms * 1e-3) / 1e9, "frac_of_measured_peak": alg / (step_ms * 1e-3) / 1e9 / peak(),
             "kernel_ms_per_step": round(ksum, 3), "kernels": kern, "gpu_launches": ctx.launch_count() - launches0,
             "check": {"sums_bits": [int(x) for x in sums], "valid_counts": [int(x) for x in cnts]}}))
-    if dist is not None:
-        dist.destroy_process_group()
+    group.close()
 
 
 if __name__ == "__main__":
