@@ -52,6 +52,26 @@ pub struct acu_array_out {
     pub reserved: i32,
 }
 
+/// acu_column (include/arrow_cuda.h): one column of a RecordBatch for the record-batch entry points.
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct acu_column {
+    pub kind: i32,  // 0 primitive, 1 boolean, 2 bytes (Utf8 / Binary)
+    pub width: i32, // primitive: element bytes; bytes: offset width (4 | 8)
+    pub array: acu_array,
+    pub data: *const u8,
+}
+
+/// acu_column_out: caller-owned output buffers of one column.
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct acu_column_out {
+    pub array: acu_array_out,
+    pub data: *mut u8,
+    pub data_capacity: i64,
+    pub data_len: i64,
+}
+
 extern "C" {
     pub fn acu_abi_version() -> i32;
     pub fn acu_ctx_create(device: i32, out: *mut *mut acu_ctx) -> acu_status;
@@ -90,6 +110,13 @@ extern "C" {
     pub fn acu_cmp(ctx: *mut acu_ctx, dtype: i32, op: i32, a: *const acu_array, b: *const acu_array, out: *mut acu_array_out) -> acu_status;
     pub fn acu_cast_numeric(ctx: *mut acu_ctx, from: i32, to: i32, safe: i32, a: *const acu_array, out: *mut acu_array_out) -> acu_status;
     pub fn acu_aggregate(ctx: *mut acu_ctx, dtype: i32, op: i32, a: *const acu_array, out_bits: *mut u64, out_valid: *mut i64) -> acu_status;
+    pub fn acu_boolean(ctx: *mut acu_ctx, op: i32, a: *const acu_array, b: *const acu_array, out: *mut acu_array_out) -> acu_status;
+    pub fn acu_filter_record_batch(ctx: *mut acu_ctx, plan: *const acu_filter_plan, n_columns: i32, columns: *const acu_column,
+                                   outs: *mut acu_column_out) -> acu_status;
+    pub fn acu_take_record_batch(ctx: *mut acu_ctx, n_columns: i32, columns: *const acu_column, indices: *const acu_array,
+                                 index_dtype: i32, check_bounds: i32, outs: *mut acu_column_out) -> acu_status;
+    pub fn acu_aggregate_columns(ctx: *mut acu_ctx, n_columns: i32, dtypes: *const i32, ops: *const i32, arrays: *const acu_array,
+                                 out_bits: *mut u64, out_valid_counts: *mut i64) -> acu_status;
     pub fn acu_comm_get_unique_id(out_id: *mut u8) -> acu_status;
     pub fn acu_comm_init(ctx: *mut acu_ctx, id: *const u8, rank: i32, world: i32) -> acu_status;
     pub fn acu_comm_destroy(ctx: *mut acu_ctx) -> acu_status;

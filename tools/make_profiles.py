@@ -28,4 +28,14 @@ for r in raw[2:]:
     rd, wr = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
     traffic[name] = float(r[rd].replace(",", "")) * scale[units[rd]] + float(r[wr].replace(",", "")) * scale[units[wr]]
 json.dump(traffic, open(f"profiles/{rnd}_traffic.json", "w"), indent=1)
+# keep the columns the summary reads (the raw page has ~1500 metric columns)
+keep = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "launch__registers_per_thread", "launch__grid_size", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct", "smsp__inst_executed.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "lts__t_sectors_srcunit_tex_op_read.sum"]
+keep = [k for k in keep if k in h]
+with open(f"profiles/{rnd}_fullset.csv", "w", newline="") as f:
+    wr_ = csv.writer(f)
+    for r in raw:
+        wr_.writerow([r[h.index(k)] for k in keep])
 print("wrote profiles/", rnd)
