@@ -113,6 +113,7 @@ vp, i32, i64, u64, f32, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_
 # name -> (restype, argtypes). Every symbol include/arrow_cuda.h declares.
 PROTOTYPES = {
     "acu_abi_version": (i32, []),
+    "acu_abi_sizeof": (i32, [i32]),
     "acu_ctx_create": (i32, [i32, P(vp)]),
     "acu_ctx_destroy": (None, [vp]),
     "acu_ctx_sync": (i32, [vp]),

@@ -113,6 +113,16 @@ void acu_kstats_drain(acu_ctx *ctx) {
 extern "C" {
 
 int32_t acu_abi_version(void) { return ACU_ABI_VERSION; }
+int32_t acu_abi_sizeof(int32_t which) {
+  switch (which) {
+    case 0: return (int32_t)sizeof(acu_array);
+    case 1: return (int32_t)sizeof(acu_array_out);
+    case 2: return (int32_t)sizeof(acu_error_detail);
+    case 3: return (int32_t)sizeof(acu_column);
+    case 4: return (int32_t)sizeof(acu_column_out);
+    default: return -1;
+  }
+}
 
 acu_status acu_ctx_create(int32_t device, acu_ctx **out) {
   *out = nullptr;

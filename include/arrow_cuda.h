@@ -136,6 +136,9 @@ static inline size_t acu_bitmap_bytes(int64_t len) { return (size_t)((len + 63) 
 /* Context, memory, timing                                                   */
 /* ------------------------------------------------------------------------- */
 int32_t acu_abi_version(void);
+/* sizeof() of the ABI structs as this library was compiled, for binding self-checks:
+ * 0 acu_array, 1 acu_array_out, 2 acu_error_detail, 3 acu_column, 4 acu_column_out; -1 otherwise. */
+int32_t acu_abi_sizeof(int32_t which);
 acu_status acu_ctx_create(int32_t device, acu_ctx **out);
 void acu_ctx_destroy(acu_ctx *ctx);
 acu_status acu_ctx_sync(acu_ctx *ctx);

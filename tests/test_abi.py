@@ -36,6 +36,12 @@ def test_struct_layouts_match_header():
     assert C.sizeof(abi.Array) == 56
     assert C.sizeof(abi.ArrayOut) == 40
     assert C.sizeof(abi.ErrorDetail) == 8 + 8 + 8 + 8 + 8 + 256
+    assert C.sizeof(abi.Column) == 72 and C.sizeof(abi.ColumnOut) == 64
+    # ... and as the library itself was compiled (callable without a GPU)
+    lib = abi.load_library()
+    for which, t in enumerate([abi.Array, abi.ArrayOut, abi.ErrorDetail, abi.Column, abi.ColumnOut]):
+        assert lib.acu_abi_sizeof(which) == C.sizeof(t), t.__name__
+    assert lib.acu_abi_sizeof(99) == -1
 
 
 def test_no_cpu_fallback_without_gpu():

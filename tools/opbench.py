@@ -111,6 +111,15 @@ def main():
         I, J = b.arr(di, va, n, n - nva), b.arr(dj, vb, n, n - nvb)
         b.timed("add i64 checked", [abi.K_ARITH], 24 * n + 3 * n / 8, n, lambda: ctx.check(lib.acu_arith(h, abi.I64, abi.ADD, C.byref(I), C.byref(J), C.byref(o))))
         b.timed("add_wrapping i64", [abi.K_ARITH], 24 * n + 3 * n / 8, n, lambda: ctx.check(lib.acu_arith(h, abi.I64, abi.ADD_WRAPPING, C.byref(I), C.byref(J), C.byref(o))))
+        # predicate construction (arrow-arith/src/boolean.rs): bitmaps only, 1e9 rows
+        bl, nbl = b.bits(50, 0.5, n)
+        br, nbr = b.bits(51, 0.5, n)
+        BL, BR = b.arr(bl, va, n, n - nva), b.arr(br, vb, n, n - nvb)
+        b.timed("and_kleene bool (nulls both sides)", [abi.K_CMP], 6 * n / 8, n,
+                lambda: ctx.check(lib.acu_boolean(h, abi.BOOL_AND_KLEENE, C.byref(BL), C.byref(BR), C.byref(o))))
+        b.timed("is_not_null", [abi.K_CMP], 2 * n / 8, n, lambda: ctx.check(lib.acu_boolean(h, abi.BOOL_IS_NOT_NULL, C.byref(A), None, C.byref(o))))
+        ctx.free(bl)
+        ctx.free(br)
         # aggregates over a full column
         bits_, cnt_ = C.c_uint64(0), C.c_int64(0)
         for name, dt, arr_, op in [("sum i64", abi.I64, I, abi.SUM), ("min f64", abi.F64, A, abi.MIN), ("sum f64", abi.F64, A, abi.SUM)]:
