@@ -686,6 +686,20 @@ class Context:
         finally:
             da.free()
 
+    def sum_checked(self, a):
+        """arrow::compute::sum_checked (aggregate.rs:897): the in-order checked fold; raises ArrowError on overflow."""
+        da = self.upload(a)
+        try:
+            bits, cnt = C.c_uint64(0), C.c_int64(0)
+            ad = da.descriptor()
+            self.check(self.lib.acu_sum_checked(self.h, a.dtype, C.byref(ad), C.byref(bits), C.byref(cnt)))
+            if cnt.value == 0:
+                return None
+            raw = np.array([bits.value], dtype=np.uint64).view(np.uint8)[: abi.DTYPE_SIZE[a.dtype]]
+            return raw.view(NP_DTYPES[a.dtype])[0].item()
+        finally:
+            da.free()
+
     def sum(self, a): return self.aggregate(SUM, a)
     def min(self, a): return self.aggregate(MIN, a)
     def max(self, a): return self.aggregate(MAX, a)

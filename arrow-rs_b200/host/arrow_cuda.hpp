@@ -816,6 +816,18 @@ std::optional<T> aggregate(acu_agg_op op, const PrimitiveArray<T> &a) {
 template <class T> std::optional<T> sum(const PrimitiveArray<T> &a) { return detail::aggregate(ACU_SUM, a); }
 template <class T> std::optional<T> min(const PrimitiveArray<T> &a) { return detail::aggregate(ACU_MIN, a); }
 template <class T> std::optional<T> max(const PrimitiveArray<T> &a) { return detail::aggregate(ACU_MAX, a); }
+// sum_checked (aggregate.rs:897-937): Ok(None) when every row is null, Err(ArithmeticOverflow) at the first overflowing add
+template <class T> Result<std::optional<T>> sum_checked(const PrimitiveArray<T> &a) {
+  uint64_t bits = 0;
+  int64_t valid = 0;
+  acu_array v = a.view();
+  acu_status st = acu_sum_checked(Context::get().raw(), NativeOf<T>::code, &v, &bits, &valid);
+  if (st != ACU_OK) return Context::get().last_error(st);
+  if (valid == 0) return std::optional<T>(std::nullopt);
+  T out;
+  std::memcpy(&out, &bits, sizeof(T));
+  return std::optional<T>(out);
+}
 
 }  // namespace compute
 

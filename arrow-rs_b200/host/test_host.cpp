@@ -169,6 +169,18 @@ static void test_boolean_kernels() {
   CHECK(as_primitive<int32_t>(filter(x, m).unwrap()).to_vec() == (std::vector<O<int32_t>>{5, 2}));
 }
 
+// aggregate.rs:1993 test_sum_checked_overflow (+ the wrapping twin :1985)
+static void test_sum_checked() {
+  auto a = Int32Array::from(std::vector<int32_t>{2147483647, 1});
+  CHECK_EQ(sum(a).value(), (int32_t)-2147483648LL);
+  auto r = sum_checked(a);
+  CHECK(r.is_err());
+  CHECK_EQ(r.unwrap_err().to_string(), std::string("Arithmetic overflow: Overflow happened on: 2147483647 + 1"));
+  auto ok = sum_checked(Int64Array::from(std::vector<O<int64_t>>{5, N, 7})).unwrap();
+  CHECK(ok.has_value() && *ok == 12);
+  CHECK(!sum_checked(Int64Array::from(std::vector<O<int64_t>>{N, N})).unwrap().has_value());
+}
+
 // arrow-select/src/take.rs:1371-1440 test_take_primitive
 template <class T>
 static void take_primitive_case() {
@@ -385,6 +397,7 @@ int main() {
       {"filter_record_batch", test_filter_record_batch},
       {"take_record_batch", test_take_record_batch},
       {"boolean_kernels", test_boolean_kernels},
+      {"sum_checked", test_sum_checked},
       {"take_primitive", test_take_primitive},
       {"take_with_offset", test_take_with_offset},
       {"take_bool", test_take_bool},

@@ -338,6 +338,13 @@ acu_status acu_boolean(acu_ctx *ctx, acu_bool_op op, const acu_array *a, const a
 acu_status acu_aggregate(acu_ctx *ctx, acu_dtype dtype, acu_agg_op op, const acu_array *a,
                          uint64_t *out_bits, int64_t *out_valid_count);
 
+/* sum_checked (aggregate.rs:897-937): the in-order checked fold. Integers:
+ * ACU_ERR_ARITHMETIC_OVERFLOW "Overflow happened on: {acc} + {value}" at the first valid
+ * row whose running sum leaves the native range (index = that row) — also when the final
+ * total would fit. Floats never fail (add_checked is the plain add): same as ACU_SUM. */
+acu_status acu_sum_checked(acu_ctx *ctx, acu_dtype dtype, const acu_array *a, uint64_t *out_bits,
+                           int64_t *out_valid_count);
+
 /* ------------------------------------------------------------------------- */
 /* RecordBatch level — filter_record_batch / take_record_batch / per-column   */
 /* aggregates with ONE stream synchronisation per call                        */

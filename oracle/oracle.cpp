@@ -942,6 +942,35 @@ acu_status cast_from(acu_dtype to, int32_t safe, const acu_array *a, acu_array_o
 
 }  // namespace
 
+// sum_checked (arrow-arith/src/aggregate.rs:897-937): try_fold(add_checked) over the valid values in order;
+// the error is add_checked's (arrow-array/src/arithmetic.rs:163-170). Floats: add_checked = plain add, in order.
+template <class T>
+acu_status sum_checked_typed(const acu_array *a, uint64_t *out_bits, int64_t *out_valid) {
+  const T *v = static_cast<const T *>(a->values);
+  const int64_t len = a->len, nc = resolve_null_count(a);
+  *out_valid = len - nc;
+  *out_bits = 0;
+  if (nc == len) return ACU_OK;  // Ok(None)
+  T acc = T();
+  for (int64_t i = 0; i < len; ++i) {
+    if (a->validity && !get_bit(a->validity, a->validity_offset + i)) continue;
+    if constexpr (std::is_floating_point<T>::value) {
+      acc = acc + v[i];
+    } else {
+      T r;
+      if (__builtin_add_overflow(acc, v[i], &r)) {
+        char ls[40], rs[40];
+        fmt_native(ls, sizeof ls, acc);
+        fmt_native(rs, sizeof rs, v[i]);
+        return fail(ACU_ERR_ARITHMETIC_OVERFLOW, i, to_bits(acc), to_bits(v[i]), 0, "Overflow happened on: %s + %s", ls, rs);
+      }
+      acc = r;
+    }
+  }
+  *out_bits = to_bits(acc);
+  return ACU_OK;
+}
+
 extern "C" {
 
 const acu_error_detail *orc_last_error(void) { return &g_err; }
@@ -1259,6 +1288,11 @@ acu_status orc_cast_numeric(acu_dtype from, acu_dtype to, int32_t safe, const ac
 acu_status orc_aggregate(acu_dtype dtype, acu_agg_op op, const acu_array *a, int32_t vector_bytes,
                          uint64_t *out_bits, int64_t *out_valid_count) {
   DISPATCH_DTYPE(dtype, aggregate_typed, op, a, vector_bytes, out_bits, out_valid_count)
+  return ACU_ERR_NOT_YET_IMPLEMENTED;
+}
+
+acu_status orc_sum_checked(acu_dtype dtype, const acu_array *a, uint64_t *out_bits, int64_t *out_valid_count) {
+  DISPATCH_DTYPE(dtype, sum_checked_typed, a, out_bits, out_valid_count)
   return ACU_ERR_NOT_YET_IMPLEMENTED;
 }
 

@@ -448,6 +448,15 @@ case("is_null_nullable_offset", B + ":847", "is_null", a=arr("int32", SIXTEEN, s
 case("is_not_null_nullable", B + ":878", "is_not_null", a=arr("int32", [1, None, 3, None]), expect={"data": [T, Fa, T, Fa], "no_validity": True})
 case("is_not_null_nullable_offset", B + ":890", "is_not_null", a=arr("int32", SIXTEEN, slice=(8, 4)), expect={"data": [T, Fa, T, Fa], "no_validity": True})
 
+A = "arrow-arith/src/aggregate.rs"
+case("sum_checked_overflow", A + ":1993", "sum_checked", a=arr("int32", [I32_MAX, 1]),
+     expect_error="Arithmetic overflow: Overflow happened on: 2147483647 + 1")
+case("sum_checked_prefix_overflow_even_if_total_fits", A + ":897-937", "sum_checked", a=arr("int32", [I32_MAX, 1, -5]),
+     expect_error="Arithmetic overflow: Overflow happened on: 2147483647 + 1")  # try_fold stops at the first failing add
+case("sum_checked_nulls_skipped", A + ":918-934", "sum_checked", a=arr("int64", [I64_MAX, None, -1, 1]), expect={"scalar": I64_MAX})
+case("sum_checked_all_null", A + ":902-904", "sum_checked", a=arr("int32", [None, None]), expect={"scalar": None})
+case("sum_checked_ok", A + ":897", "sum_checked", a=arr("int32", [1, 2, 3, 4, 5]), expect={"scalar": 15})
+
 out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "vectors.json")
 with open(out, "w") as f:
     json.dump({"reference": "apache/arrow-rs 59.2.0 @ cd7c6b83", "cases": cases}, f, indent=0)

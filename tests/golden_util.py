@@ -148,7 +148,7 @@ def run_case(backend, c):
             return getattr(backend, op)(build_array(c["a"]), build_array(c["b"]))
         if op == "cast":
             return backend.cast(build_array(c["a"]), DT[c["to"]], c.get("safe", True))
-        if op in ("sum", "min", "max"):
+        if op in ("sum", "min", "max", "sum_checked"):
             return getattr(backend, op)(build_array(c["a"]))
         if op in ("and_", "or_", "and_not", "and_kleene", "or_kleene"):
             return getattr(backend, op)(build_array(c["a"]), build_array(c["b"]))
@@ -178,7 +178,7 @@ def run_case(backend, c):
         assert count == e["count"]
     elif op in ("filter_utf8", "take_utf8"):
         assert strings_of(*res) == e["strings"]
-    elif op in ("sum", "min", "max"):
+    elif op in ("sum", "min", "max", "sum_checked"):
         assert _match(e["scalar"], res), f"expected {e['scalar']!r}, got {res!r}"
     else:
         check_array(e, res)

@@ -45,6 +45,7 @@ class Oracle:
             "orc_boolean": [i32, P(abi.Array), P(abi.Array), P(abi.ArrayOut)],
             "orc_cast_numeric": [i32, i32, i32, P(abi.Array), P(abi.ArrayOut)],
             "orc_aggregate": [i32, i32, P(abi.Array), i32, P(u64), P(i64)],
+            "orc_sum_checked": [i32, P(abi.Array), P(u64), P(i64)],
             "orc_generate_values": [i32, u64, i64, u64, vp, i64],
             "orc_generate_bits": [u64, i64, C.c_double, vp, i64],
         }
@@ -214,6 +215,15 @@ class Oracle:
         bits, cnt = u64(0), i64(0)
         ad = acu.host_descriptor(a)
         self.check(self.lib.orc_aggregate(a.dtype, op, C.byref(ad), vector_bytes, C.byref(bits), C.byref(cnt)))
+        if cnt.value == 0:
+            return None
+        raw = np.array([bits.value], dtype=np.uint64).view(np.uint8)[: abi.DTYPE_SIZE[a.dtype]]
+        return raw.view(acu.NP_DTYPES[a.dtype])[0].item()
+
+    def sum_checked(self, a):
+        bits, cnt = u64(0), i64(0)
+        ad = acu.host_descriptor(a)
+        self.check(self.lib.orc_sum_checked(a.dtype, C.byref(ad), C.byref(bits), C.byref(cnt)))
         if cnt.value == 0:
             return None
         raw = np.array([bits.value], dtype=np.uint64).view(np.uint8)[: abi.DTYPE_SIZE[a.dtype]]

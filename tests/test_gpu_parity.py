@@ -282,6 +282,26 @@ def test_bytes_long_and_mixed_rows(gpu, oracle):
                                   f"take_bytes long n={n} max_len={max_len} idx={idt}")
 
 
+def test_dictionary_filter_take_on_keys(gpu, oracle):
+    """filter_dict (filter.rs:999-1007) and take_dict (take.rs:932-938) touch only the KEYS and share the dictionary
+    values, so at the C ABI a dictionary column is its Int32 key array: decode(filter(keys)) == filter(decode(keys)),
+    and the same for take (decode = the Dictionary<Int32,Utf8> -> Utf8 cast, dictionary.rs:310-317)."""
+    rng = np.random.default_rng(15)
+    d_off, d_data, d_nulls = rand_strings(rng, 300, 0.1)  # the dictionary (with null entries)
+    for n in [0, 1, 1000, 20000]:
+        keys = HostArray.from_numpy(abi.I32, rng.integers(0, 300, n).astype(np.int32), rng.random(n) >= 0.1)
+        decoded = gpu.take_bytes(d_off, d_data, d_nulls, keys)
+        pred = rand_bool(rng, n, 0.3, 0.05)
+        fk = gpu.filter(keys, pred)
+        assert_same(fk, oracle.filter(keys, pred), f"filter_dict keys n={n}")
+        assert_same_bytes(gpu.take_bytes(d_off, d_data, d_nulls, fk), gpu.filter_bytes(decoded[0], decoded[1], decoded[2], pred), f"filter_dict n={n}")
+        if n:
+            idx = HostArray.from_numpy(abi.U32, rng.integers(0, n, 777).astype(np.uint32), rng.random(777) >= 0.1)
+            tk = gpu.take(keys, idx)
+            assert_same(tk, oracle.take(keys, idx), f"take_dict keys n={n}")
+            assert_same_bytes(gpu.take_bytes(d_off, d_data, d_nulls, tk), gpu.take_bytes(decoded[0], decoded[1], decoded[2], idx), f"take_dict n={n}")
+
+
 # ---- numeric -------------------------------------------------------------------------------
 ARITH_OPS = ["add", "add_wrapping", "sub", "sub_wrapping", "mul", "mul_wrapping", "div", "rem"]
 
@@ -423,6 +443,33 @@ def test_aggregate_fuzz(gpu, oracle, dtype):
                     assert abs(g - e) <= tol, f"sum dtype={dtype} n={n}: {g} vs {e}"
             else:
                 assert gpu.sum(a) == oracle.sum(a), f"sum dtype={dtype} n={n}"
+
+
+@pytest.mark.parametrize("dtype", [abi.I8, abi.I16, abi.I32, abi.I64, abi.U8, abi.U32, abi.U64])
+def test_sum_checked_fuzz(gpu, oracle, dtype):
+    """sum_checked = the in-order checked fold (aggregate.rs:897-937): same value, or the same error text / failing row /
+    operands as the oracle's sequential fold — including prefixes that overflow while the total would fit."""
+    rng = np.random.default_rng(8100 + dtype)
+    npdt = acu.NP_DTYPES[dtype]
+    info = np.iinfo(npdt)
+    for n in [0, 1, 15, 16, 17, 4095, 4096, 4097, 20000, 70001]:
+        for null_p in (None, 0.2, 1.0):
+            for regime in ("small", "edge", "full"):
+                if regime == "small":      # never overflows
+                    span = max(1, int(info.max // max(n, 1) // 2))
+                    vals = rng.integers(max(info.min, -span), span, n, dtype=np.int64 if info.min < 0 else np.uint64, endpoint=True).astype(npdt)
+                elif regime == "edge":     # mostly zeros with a few extreme values: late, sparse overflows
+                    vals = np.zeros(n, dtype=npdt)
+                    if n:
+                        k = max(1, n // 500)
+                        vals[rng.integers(0, n, k)] = rng.choice(np.array([info.max, info.min, info.max - 1, 1], dtype=npdt), k)
+                else:
+                    vals = rng.integers(info.min, info.max, n, dtype=npdt, endpoint=True)
+                a = HostArray.from_numpy(dtype, vals, None if null_p is None else rng.random(n) >= null_p, bit_offset=int(rng.integers(0, 9)))
+                if n > 40:
+                    a = a.slice(7, n - 20)
+                got, exp = expect_same_error(gpu, oracle, lambda be: be.sum_checked(a))
+                assert got == exp, f"sum_checked dtype={dtype} n={n} {regime}: {got} != {exp}"
 
 
 def test_generators_match_host_twin(gpu, oracle):
