@@ -298,7 +298,7 @@ template <int W> struct AsyncCfg {
 };
 
 template <int W>
-__global__ void __launch_bounds__(256) k_filter_values_async(const FilterBatch batch) {
+__global__ void __launch_bounds__(256, 6) k_filter_values_async(const FilterBatch batch) {
   const FilterArgs &a = batch.col[blockIdx.y];
   using C = AsyncCfg<W>;
   constexpr int RPC = W <= 16 ? 16 / W : 1;
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(256) k_zero_outputs(const CompressBatch batch)
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (uint64_t)gridDim.x * blockDim.x) o[i] = 0ull;
 }
 
-__global__ void __launch_bounds__(256) k_compress_bits(const CompressBatch batch, int64_t len, const uint64_t *__restrict__ mask,
+__global__ void __launch_bounds__(256, 8) k_compress_bits(const CompressBatch batch, int64_t len, const uint64_t *__restrict__ mask,
                                                        const uint64_t *__restrict__ tile_off, int64_t n_words_padded) {
   const uint8_t *__restrict__ src = batch.col[blockIdx.y].src;
   const int64_t soff = batch.col[blockIdx.y].soff;
