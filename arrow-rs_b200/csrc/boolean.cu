@@ -32,38 +32,58 @@ struct BoolArgs {
 };
 
 template <int OP>
+__device__ __forceinline__ void bool_word(bool has_an, bool has_bn, uint64_t A, uint64_t B, uint64_t AN, uint64_t BN, uint64_t lenmask, uint64_t *v, uint64_t *n) {
+  *n = lenmask;
+  if (OP == ACU_BOOL_AND) { *v = A & B; *n = AN & BN; }
+  else if (OP == ACU_BOOL_OR) { *v = A | B; *n = AN & BN; }
+  else if (OP == ACU_BOOL_AND_NOT) { *v = A & ~B; *n = AN & BN; }
+  else if (OP == ACU_BOOL_AND_KLEENE) {
+    *v = A & B;
+    if (has_an && has_bn) *n = (AN | (BN & ~B)) & (BN | (AN & ~A));  // boolean.rs:99-118
+    else if (has_an) *n = AN | ~B;                                   // boolean.rs:71-84
+    else if (has_bn) *n = BN | ~A;                                   // boolean.rs:85-95
+  } else if (OP == ACU_BOOL_OR_KLEENE) {
+    *v = A | B;
+    if (has_an && has_bn) *n = (AN | (BN & B)) & (BN | (AN & A));    // boolean.rs:195-214
+    else if (has_an) *n = AN | B;
+    else if (has_bn) *n = BN | A;
+  } else if (OP == ACU_BOOL_NOT) { *v = ~A; *n = AN; }
+  else if (OP == ACU_BOOL_IS_NULL) { *v = ~AN; }
+  else { *v = AN; }
+  *v &= lenmask;
+  *n &= lenmask;
+}
+
+// ALIGNED: every input bitmap starts on a u64 word (8-byte aligned base, bit offset a multiple of 64 — the
+// common case: unsliced arrays and slices on 64-row boundaries): plain coalesced u64 loads, no funnel shifts.
+template <int OP, bool ALIGNED>
 __global__ void __launch_bounds__(256) k_boolean(const BoolArgs a) {
   const int64_t words = (a.len + 63) >> 6;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const uint64_t *av = reinterpret_cast<const uint64_t *>(a.av) + (a.aoff >> 6), *bv = reinterpret_cast<const uint64_t *>(a.bv) + (a.boff >> 6);
+  const uint64_t *an = reinterpret_cast<const uint64_t *>(a.an) + (a.anoff >> 6), *bn = reinterpret_cast<const uint64_t *>(a.bn) + (a.bnoff >> 6);
   unsigned cnt = 0;
+#pragma unroll 2
   for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += stride) {
     const int64_t pos = w << 6;
     const int64_t left = a.len - pos;
     const uint64_t lenmask = left >= 64 ? ~0ull : ((1ull << left) - 1ull);
-    const uint64_t A = a.av ? ld_bits64(a.av, a.aoff + pos, a.aoff + a.len) : 0ull;
-    const uint64_t B = a.bv ? ld_bits64(a.bv, a.boff + pos, a.boff + a.len) : 0ull;
-    const uint64_t AN = a.an ? ld_bits64(a.an, a.anoff + pos, a.anoff + a.len) : lenmask;
-    const uint64_t BN = a.bn ? ld_bits64(a.bn, a.bnoff + pos, a.bnoff + a.len) : lenmask;
-    uint64_t v, n = lenmask;
-    if (OP == ACU_BOOL_AND) { v = A & B; n = AN & BN; }
-    else if (OP == ACU_BOOL_OR) { v = A | B; n = AN & BN; }
-    else if (OP == ACU_BOOL_AND_NOT) { v = A & ~B; n = AN & BN; }
-    else if (OP == ACU_BOOL_AND_KLEENE) {
-      v = A & B;
-      if (a.an && a.bn) n = (AN | (BN & ~B)) & (BN | (AN & ~A));  // boolean.rs:99-118
-      else if (a.an) n = AN | ~B;                                 // boolean.rs:71-84
-      else if (a.bn) n = BN | ~A;                                 // boolean.rs:85-95
-    } else if (OP == ACU_BOOL_OR_KLEENE) {
-      v = A | B;
-      if (a.an && a.bn) n = (AN | (BN & B)) & (BN | (AN & A));    // boolean.rs:195-214
-      else if (a.an) n = AN | B;
-      else if (a.bn) n = BN | A;
-    } else if (OP == ACU_BOOL_NOT) { v = ~A; n = AN; }
-    else if (OP == ACU_BOOL_IS_NULL) { v = ~AN; }
-    else { v = AN; }
-    a.out_v[w] = v & lenmask;
+    uint64_t A, B, AN, BN;
+    if (ALIGNED) {
+      A = a.av ? __ldg(av + w) : 0ull;
+      B = a.bv ? __ldg(bv + w) : 0ull;
+      AN = a.an ? __ldg(an + w) : lenmask;
+      BN = a.bn ? __ldg(bn + w) : lenmask;
+    } else {
+      A = a.av ? ld_bits64(a.av, a.aoff + pos, a.aoff + a.len) : 0ull;
+      B = a.bv ? ld_bits64(a.bv, a.boff + pos, a.boff + a.len) : 0ull;
+      AN = a.an ? ld_bits64(a.an, a.anoff + pos, a.anoff + a.len) : lenmask;
+      BN = a.bn ? ld_bits64(a.bn, a.bnoff + pos, a.bnoff + a.len) : lenmask;
+    }
+    uint64_t v, n;
+    bool_word<OP>(a.an != nullptr, a.bn != nullptr, A, B, AN, BN, lenmask, &v, &n);
+    a.out_v[w] = v;
     if (a.out_n) {
-      n &= lenmask;
       a.out_n[w] = n;
       cnt += __popcll(n);
     }
@@ -77,7 +97,11 @@ __global__ void __launch_bounds__(256) k_boolean(const BoolArgs a) {
 template <int OP>
 acu_status launch(acu_ctx *ctx, const BoolArgs &a) {
   const int64_t words = (a.len + 63) >> 6;
-  ACU_LAUNCH_TIMED(ctx, ACU_K_CMP, k_boolean<OP>, acu_grid(ctx, (words + 255) / 256, 16), 256, 0, a);
+  auto word_aligned = [](const uint8_t *p, int64_t off) { return p == nullptr || (((uintptr_t)p & 7) == 0 && (off & 63) == 0); };
+  // (the aligned loads read whole words: the last one may extend past len inside the allocation's 64-bit padding)
+  const bool aligned = word_aligned(a.av, a.aoff) && word_aligned(a.an, a.anoff) && word_aligned(a.bv, a.boff) && word_aligned(a.bn, a.bnoff);
+  if (aligned) ACU_LAUNCH_TIMED(ctx, ACU_K_CMP, (k_boolean<OP, true>), acu_grid(ctx, (words + 255) / 256, 16), 256, 0, a);
+  else ACU_LAUNCH_TIMED(ctx, ACU_K_CMP, (k_boolean<OP, false>), acu_grid(ctx, (words + 255) / 256, 16), 256, 0, a);
   return ACU_OK;
 }
 

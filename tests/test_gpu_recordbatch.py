@@ -137,3 +137,23 @@ def test_pipeline_filter_take_sum_matches_oracle(gpu, oracle):
     check_columns(t_gpu, f_or_cols, lambda col: oracle_take(oracle, col, idx), "pipeline take")
     sums = gpu.aggregate_columns([abi.SUM] * 3, t_gpu[:3])
     assert sums == [oracle.sum(oracle_take(oracle, c, idx)) for c in f_or_cols[:3]]
+
+
+def test_many_columns_share_launches(gpu, oracle):
+    """More equal-width columns than one batched launch holds (8), mixed with other widths: every column still right;
+    more than ACU_MAX_BATCH_COLUMNS in one call is an argument error (the C++ mirror splits such batches)."""
+    rng = np.random.default_rng(4242)
+    n = 5000
+    cols = [rand_array(rng, abi.I32 if c % 3 else abi.I64, n, 0.1 if c % 2 else None) for c in range(21)]
+    cols += [rand_bool(rng, n, 0.5, 0.1) for _ in range(10)]
+    pred = rand_bool(rng, n, 0.4, None)
+    check_columns(gpu.filter_record_batch(cols, pred), cols, lambda col: oracle_filter(oracle, col, pred), "31 columns filter")
+    idx = HostArray.from_numpy(abi.U32, rng.integers(0, n, 3000).astype(np.uint32), rng.random(3000) >= 0.05)
+    check_columns(gpu.take_record_batch(cols, idx), cols, lambda col: oracle_take(oracle, col, idx), "31 columns take")
+    ops = [abi.SUM, abi.MIN, abi.MAX] * 7
+    got = gpu.aggregate_columns(ops, cols[:21])
+    exp = [getattr(oracle, ("sum", "min", "max")[op])(col) for op, col in zip(ops, cols[:21])]
+    assert got == exp
+    with pytest.raises(acu.ArrowError) as e:
+        gpu.filter_record_batch([cols[0]] * 65, pred)
+    assert e.value.status == abi.ERR_INVALID_ARGUMENT
