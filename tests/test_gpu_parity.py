@@ -302,6 +302,110 @@ def test_dictionary_filter_take_on_keys(gpu, oracle):
             assert_same_bytes(gpu.take_bytes(d_off, d_data, d_nulls, tk), gpu.take_bytes(decoded[0], decoded[1], decoded[2], idx), f"take_dict n={n}")
 
 
+# ---- 16 / 32-byte elements: Decimal128/256, intervals, and Utf8View / BinaryView ----------------
+def _wide_column(gpu, raw_u64, n, width, mask):
+    """Device descriptor of n `width`-byte records (given as uint64 lanes) with an optional validity mask."""
+    import ctypes as C  # noqa: F401
+    dv = gpu.malloc(raw_u64.nbytes + 64)
+    if raw_u64.nbytes:
+        gpu.h2d(dv, raw_u64)
+    dn = None
+    if mask is not None:
+        bits = acu.pack_bits(mask)
+        dn = gpu.malloc(len(bits) + 8)
+        gpu.h2d(dn, bits)
+    a = abi.Array()
+    a.values, a.validity, a.len, a.null_count = dv, dn, n, 0 if mask is None else int(n - mask.sum())
+    return a, [p for p in (dv, dn) if p]
+
+
+def _wide_result(gpu, out, width):
+    n = out.len
+    vals = gpu.d2h(out.values, n * width, np.uint64).reshape(n, width // 8)
+    valid = acu.unpack_bits(gpu.d2h(out.validity, abi.bitmap_bytes(n)), 0, n) if out.has_validity else np.ones(n, dtype=bool)
+    return vals, valid
+
+
+@pytest.mark.parametrize("width", [16, 32])
+def test_take_wide_elements(gpu, oracle, width):
+    import ctypes as C
+    rng = np.random.default_rng(90 + width)
+    lanes = width // 8
+    for n, m in [(1, 5), (100, 0), (4097, 9000), (9000, 4097)]:
+        raw = rng.integers(0, 2**63, n * lanes, dtype=np.uint64)
+        mask = rng.random(n) >= 0.2
+        col, owned = _wide_column(gpu, raw, n, width, mask)
+        idx_h = HostArray.from_numpy(abi.U32, rng.integers(0, n, m).astype(np.uint32), rng.random(m) >= 0.1)
+        di = gpu.upload(idx_h)
+        out = gpu.alloc_out(m * width, m)
+        idd = di.descriptor()
+        gpu.check(gpu.lib.acu_take_primitive(gpu.h, width, C.byref(col), C.byref(idd), abi.U32, 0, C.byref(out)))
+        vals, valid = _wide_result(gpu, out, width)
+        ix, iv = idx_h.value_array(), idx_h.valid_mask()
+        assert np.array_equal(valid, mask[ix] & iv)
+        assert np.array_equal(vals[iv], raw.reshape(n, lanes)[ix[iv]])  # the value is gathered wherever the index is valid
+        gpu._free_out(out)
+        di.free()
+        for p in owned:
+            gpu.free(p)
+
+
+def test_byte_view_filter_take(gpu, oracle):
+    """Utf8View / BinaryView: filter_byte_view (filter.rs:931-944) and take_byte_view (take.rs:630-640) run
+    filter_native / take_native over the 16-byte views and share the data buffers, i.e. they ARE the 16-byte primitive
+    kernels. Views are built here as arrow's u128 layout (len | 12 inline bytes, or len | prefix | buffer | offset)."""
+    import ctypes as C
+    rng = np.random.default_rng(77)
+    n = 6000
+    strings = ["".join(chr(c) for c in rng.integers(97, 123, rng.integers(0, 30))) for _ in range(n)]
+    buf = bytearray()
+    views = np.zeros((n, 4), dtype=np.uint32)
+    for i, s in enumerate(strings):
+        b = s.encode()
+        views[i, 0] = len(b)
+        if len(b) <= 12:
+            views[i, 1:4] = np.frombuffer(b.ljust(12, b"\0"), dtype=np.uint32)
+        else:
+            views[i, 1] = np.frombuffer(b[:4], dtype=np.uint32)[0]
+            views[i, 2], views[i, 3] = 0, len(buf)
+            buf += b
+
+    def decode(v):
+        out = []
+        for row in v.view(np.uint32).reshape(-1, 4):
+            ln = int(row[0])
+            out.append(row[1:4].tobytes()[:ln].decode() if ln <= 12 else bytes(buf[int(row[3]): int(row[3]) + ln]).decode())
+        return out
+
+    mask = rng.random(n) >= 0.1
+    col, owned = _wide_column(gpu, views.view(np.uint64).reshape(-1), n, 16, mask)
+    pred = rand_bool(rng, n, 0.3, 0.05)
+    dp = gpu.upload(pred)
+    plan = C.c_void_p()
+    pd = dp.descriptor()
+    gpu.check(gpu.lib.acu_filter_plan_create(gpu.h, C.byref(pd), C.byref(plan)))
+    count = gpu.lib.acu_filter_plan_count(plan)
+    out = gpu.alloc_out(count * 16, count)
+    gpu.check(gpu.lib.acu_filter_primitive(gpu.h, plan, 16, C.byref(col), C.byref(out)))
+    vals, valid = _wide_result(gpu, out, 16)
+    sel = pred.value_array() & pred.valid_mask()
+    assert decode(vals) == [s for s, k in zip(strings, sel) if k] and np.array_equal(valid, mask[sel])
+    gpu.lib.acu_filter_plan_destroy(gpu.h, plan)
+    gpu._free_out(out)
+    idx_h = HostArray.from_numpy(abi.I64, rng.integers(0, n, 5000).astype(np.int64))
+    di = gpu.upload(idx_h)
+    out = gpu.alloc_out(5000 * 16, 5000)
+    idd = di.descriptor()
+    gpu.check(gpu.lib.acu_take_primitive(gpu.h, 16, C.byref(col), C.byref(idd), abi.I64, 1, C.byref(out)))
+    vals, valid = _wide_result(gpu, out, 16)
+    assert decode(vals) == [strings[i] for i in idx_h.value_array()] and np.array_equal(valid, mask[idx_h.value_array()])
+    gpu._free_out(out)
+    di.free()
+    dp.free()
+    for p in owned:
+        gpu.free(p)
+
+
 # ---- numeric -------------------------------------------------------------------------------
 ARITH_OPS = ["add", "add_wrapping", "sub", "sub_wrapping", "mul", "mul_wrapping", "div", "rem"]
 
