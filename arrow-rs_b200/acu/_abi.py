@@ -162,6 +162,9 @@ PROTOTYPES = {
     "acu_filter_record_batch": (i32, [vp, vp, i32, P(Column), P(ColumnOut)]),
     "acu_take_record_batch": (i32, [vp, i32, P(Column), P(Array), i32, i32, P(ColumnOut)]),
     "acu_aggregate_columns": (i32, [vp, i32, P(i32), P(i32), P(Array), P(u64), P(i64)]),
+    "acu_bitmap_copy": (i32, [vp, vp, i64, vp, i64, i64, P(i64)]),
+    "acu_bitmap_fill": (i32, [vp, vp, i64, i64, i32]),
+    "acu_offsets_append": (i32, [vp, i32, vp, i64, i64, i64, vp, i64, P(i64), P(i64)]),
     "acu_comm_get_unique_id": (i32, [vp]),
     "acu_comm_init": (i32, [vp, vp, i32, i32]),
     "acu_comm_destroy": (i32, [vp]),

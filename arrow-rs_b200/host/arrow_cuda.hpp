@@ -678,6 +678,152 @@ inline Result<RecordBatch> take_record_batch(const RecordBatch &batch, const Arr
   return RecordBatch(batch.schema(), out.wrap(cols), m);
 }
 
+// ---- BatchCoalescer (arrow-select/src/coalesce.rs:148-590) -----------------------------------
+// Output batches hold exactly target_batch_size rows, in input order; in-progress columns live in HBM at
+// their final capacity and rows are appended in place (InProgressArray::copy_rows): fixed-width values by
+// device-to-device copy, validity / boolean bits by acu_bitmap_copy at the current bit position (nothing is
+// materialised until the first null arrives, like NullBufferBuilder), Utf8 by acu_offsets_append + byte copy.
+class BatchCoalescer {
+ public:
+  BatchCoalescer(Schema schema, int64_t target_batch_size) : schema_(std::move(schema)), target_(target_batch_size) {
+    for (const auto &f : schema_) cols_.push_back(fresh(f.data_type));
+  }
+  const Schema &schema() const { return schema_; }
+  int64_t get_buffered_rows() const { return buffered_; }
+  bool is_empty() const { return buffered_ == 0 && completed_.empty(); }
+  bool has_completed_batch() const { return !completed_.empty(); }
+  std::optional<RecordBatch> next_completed_batch() {
+    if (completed_.empty()) return std::nullopt;
+    RecordBatch b = std::move(completed_.front());
+    completed_.erase(completed_.begin());
+    return b;
+  }
+  // coalesce.rs:325-533
+  Result<int64_t> push_batch(const RecordBatch &batch) {
+    if (batch.num_columns() != cols_.size())
+      return ArrowError{ACU_ERR_INVALID_ARGUMENT, "Invalid argument error: Batch has " + std::to_string(batch.num_columns()) +
+                                                       " columns but BatchCoalescer expects " + std::to_string(cols_.size())};
+    int64_t num_rows = batch.num_rows(), offset = 0;
+    while (num_rows > target_ - buffered_) {
+      const int64_t remaining = target_ - buffered_;
+      for (size_t c = 0; c < cols_.size(); ++c) {
+        auto st = copy_rows(cols_[c], *batch.column(c), offset, remaining);
+        if (st.is_err()) return st.unwrap_err();
+      }
+      buffered_ += remaining;
+      offset += remaining;
+      num_rows -= remaining;
+      finish_buffered_batch();
+    }
+    if (num_rows > 0)
+      for (size_t c = 0; c < cols_.size(); ++c) {
+        auto st = copy_rows(cols_[c], *batch.column(c), offset, num_rows);
+        if (st.is_err()) return st.unwrap_err();
+      }
+    buffered_ += num_rows;
+    if (buffered_ >= target_) finish_buffered_batch();
+    return buffered_;
+  }
+  // "semantically equivalent of calling push_batch with the results from filter_record_batch" (coalesce.rs:236-237)
+  Result<int64_t> push_batch_with_filter(const RecordBatch &batch, const BooleanArray &filter) {
+    auto f = filter_record_batch(batch, filter);
+    if (f.is_err()) return f.unwrap_err();
+    return push_batch(f.unwrap());
+  }
+  Result<int64_t> push_batch_with_indices(const RecordBatch &batch, const Array &indices) {  // coalesce.rs:289-298
+    auto t = take_record_batch(batch, indices);
+    if (t.is_err()) return t.unwrap_err();
+    return push_batch(t.unwrap());
+  }
+  void finish_buffered_batch() {  // coalesce.rs:547-570
+    if (buffered_ == 0) return;
+    std::vector<ArrayRef> arrays;
+    for (size_t c = 0; c < cols_.size(); ++c) {
+      InProgress &p = cols_[c];
+      std::optional<NullBuffer> nulls;
+      if (p.materialised && p.null_count > 0) nulls = NullBuffer{p.valid, 0, buffered_, p.null_count};
+      if (p.dt == DataType::Boolean) arrays.push_back(std::make_shared<BooleanArray>(p.values, 0, buffered_, nulls));
+      else if (p.dt == DataType::Utf8) arrays.push_back(std::make_shared<StringArray>(p.values, p.data, buffered_, nulls));
+      else arrays.push_back(detail::make_primitive(p.dt, p.values, buffered_, nulls));
+      p = fresh(p.dt);
+    }
+    completed_.push_back(RecordBatch(schema_, std::move(arrays), buffered_));
+    buffered_ = 0;
+  }
+
+ private:
+  struct InProgress {
+    DataType dt;
+    Buffer values, valid, data;
+    bool materialised = false;
+    int64_t null_count = 0, data_len = 0, data_cap = 0;
+  };
+  InProgress fresh(DataType dt) const {
+    InProgress p;
+    p.dt = dt;
+    p.valid = Buffer::allocate(acu_bitmap_bytes(target_));
+    if (dt == DataType::Boolean) p.values = Buffer::allocate(acu_bitmap_bytes(target_));
+    else if (dt == DataType::Utf8) {
+      p.values = Buffer::allocate((size_t)(target_ + 1) * 4);
+      p.data_cap = 1 << 16;
+      p.data = Buffer::allocate((size_t)p.data_cap);
+      const int32_t zero = 0;
+      acu_memcpy_h2d(Context::get().raw(), p.values.data(), &zero, 4);
+    } else p.values = Buffer::allocate((size_t)target_ * dtype_width(dt));
+    return p;
+  }
+  Result<int64_t> copy_rows(InProgress &p, const Array &src, int64_t offset, int64_t n) {
+    Context &c = Context::get();
+    acu_ctx *h = c.raw();
+    const acu_array v = src.view();
+    acu_status st;
+    int64_t nulls_here = 0;
+    if (v.validity && v.null_count != 0) {
+      int64_t set = 0;
+      if ((st = acu_bitmap_count(h, v.validity, v.validity_offset + offset, nullptr, 0, n, &set)) != ACU_OK) return c.last_error(st);
+      nulls_here = n - set;
+    }
+    uint8_t *valid = static_cast<uint8_t *>(p.valid.data());
+    if (nulls_here) {
+      if (!p.materialised) {
+        if ((st = acu_bitmap_fill(h, valid, 0, buffered_, 1)) != ACU_OK) return c.last_error(st);
+        p.materialised = true;
+      }
+      if ((st = acu_bitmap_copy(h, v.validity, v.validity_offset + offset, valid, buffered_, n, nullptr)) != ACU_OK) return c.last_error(st);
+      p.null_count += nulls_here;
+    } else if (p.materialised) {
+      if ((st = acu_bitmap_fill(h, valid, buffered_, n, 1)) != ACU_OK) return c.last_error(st);
+    }
+    if (p.dt == DataType::Boolean) {
+      st = acu_bitmap_copy(h, static_cast<const uint8_t *>(v.values), v.values_offset + offset, static_cast<uint8_t *>(p.values.data()), buffered_, n, nullptr);
+    } else if (p.dt == DataType::Utf8) {
+      const auto &s = static_cast<const StringArray &>(src);
+      int64_t s0 = 0, s1 = 0;
+      if ((st = acu_offsets_append(h, 4, s.offsets().data(), offset, n, p.data_len, p.values.data(), buffered_, &s0, &s1)) != ACU_OK) return c.last_error(st);
+      const int64_t nbytes = s1 - s0;
+      if (p.data_len + nbytes > p.data_cap) {
+        while (p.data_cap < p.data_len + nbytes) p.data_cap *= 2;
+        Buffer bigger = Buffer::allocate((size_t)p.data_cap);
+        if (p.data_len) acu_memcpy_d2d(h, bigger.data(), p.data.data(), (size_t)p.data_len);
+        acu_ctx_sync(h);  // the old bytes buffer is released when `p.data` is reassigned
+        p.data = bigger;
+      }
+      st = acu_memcpy_d2d(h, static_cast<uint8_t *>(p.data.data()) + p.data_len, static_cast<const uint8_t *>(s.value_data().data()) + s0, (size_t)nbytes);
+      p.data_len += nbytes;
+    } else {
+      const int w = dtype_width(p.dt);
+      st = acu_memcpy_d2d(h, static_cast<uint8_t *>(p.values.data()) + (size_t)buffered_ * w, static_cast<const uint8_t *>(v.values) + (size_t)offset * w, (size_t)n * w);
+    }
+    if (st != ACU_OK) return c.last_error(st);
+    return n;
+  }
+  Schema schema_;
+  int64_t target_;
+  std::vector<InProgress> cols_;
+  int64_t buffered_ = 0;
+  std::vector<RecordBatch> completed_;
+};
+
 // ---- kernels::numeric (arrow-arith/src/numeric.rs) ---------------------------------------
 namespace kernels {
 namespace numeric {

@@ -181,6 +181,58 @@ static void test_sum_checked() {
   CHECK(!sum_checked(Int64Array::from(std::vector<O<int64_t>>{N, N})).unwrap().has_value());
 }
 
+// arrow-select/src/coalesce.rs:42-110 (struct doc example), :239-257 (push_batch_with_filter), :271-288 (push_batch_with_indices)
+static void test_batch_coalescer() {
+  Schema schema{{"a", DataType::Int32}};
+  auto rb = [&](std::vector<O<int32_t>> v) {
+    return RecordBatch::try_new(schema, {std::make_shared<Int32Array>(Int32Array::from(v))}).unwrap();
+  };
+  BatchCoalescer co(schema, 4);
+  co.push_batch(rb({1, 2, 3})).unwrap();
+  CHECK(!co.next_completed_batch().has_value());
+  co.push_batch(rb({4, 5, 6})).unwrap();
+  auto b = co.next_completed_batch();
+  CHECK(b.has_value());
+  CHECK(as_primitive<int32_t>(b->column(0)).to_vec() == (std::vector<O<int32_t>>{1, 2, 3, 4}));
+  CHECK(!co.next_completed_batch().has_value());
+  co.finish_buffered_batch();
+  CHECK(as_primitive<int32_t>(co.next_completed_batch()->column(0)).to_vec() == (std::vector<O<int32_t>>{5, 6}));
+  CHECK(co.is_empty());
+
+  BatchCoalescer cf(schema, 1000);
+  auto filter = BooleanArray::from(std::vector<bool>{true, false, true});
+  cf.push_batch_with_filter(rb({1, N, 3}), filter).unwrap();
+  cf.push_batch_with_filter(rb({4, 5, 6}), filter).unwrap();
+  cf.finish_buffered_batch();
+  auto fb = cf.next_completed_batch();
+  CHECK(as_primitive<int32_t>(fb->column(0)).to_vec() == (std::vector<O<int32_t>>{1, 3, 4, 6}));
+  CHECK(!fb->column(0)->nulls().has_value());  // the only null was filtered out: NullBufferBuilder never materialised
+
+  BatchCoalescer ci(schema, 1000);
+  ci.push_batch(rb({0, 0, 0})).unwrap();
+  ci.push_batch_with_indices(rb({1, 1, 4, 5, 1, 4}), UInt64Array::from(std::vector<uint64_t>{0, 1, 4, 2, 5, 3})).unwrap();
+  ci.finish_buffered_batch();
+  CHECK(as_primitive<int32_t>(ci.next_completed_batch()->column(0)).to_vec() == (std::vector<O<int32_t>>{0, 0, 0, 1, 1, 1, 4, 4, 5}));
+
+  // strings + nulls across an output boundary
+  Schema s2{{"s", DataType::Utf8}, {"b", DataType::Boolean}};
+  BatchCoalescer cs(s2, 3);
+  auto sb = [&](std::vector<O<std::string>> v, std::vector<O<bool>> w) {
+    return RecordBatch::try_new(s2, {std::make_shared<StringArray>(StringArray::from(v)), std::make_shared<BooleanArray>(BooleanArray::from(w))}).unwrap();
+  };
+  cs.push_batch(sb({std::string("ab"), N}, {true, N})).unwrap();
+  cs.push_batch(sb({std::string("cde"), std::string(""), std::string("f")}, {false, true, N})).unwrap();
+  cs.finish_buffered_batch();
+  auto b1 = cs.next_completed_batch(), b2 = cs.next_completed_batch();
+  CHECK(as_string(b1->column(0)).to_vec() == (std::vector<O<std::string>>{std::string("ab"), N, std::string("cde")}));
+  CHECK(as_boolean(b1->column(1)).to_vec() == (std::vector<O<bool>>{true, N, false}));
+  CHECK(as_string(b2->column(0)).to_vec() == (std::vector<O<std::string>>{std::string(""), std::string("f")}));
+  CHECK(as_boolean(b2->column(1)).to_vec() == (std::vector<O<bool>>{true, N}));
+  auto bad = cs.push_batch(rb({1}));
+  CHECK(bad.is_err());
+  CHECK_EQ(bad.unwrap_err().to_string(), std::string("Invalid argument error: Batch has 1 columns but BatchCoalescer expects 2"));
+}
+
 // arrow-select/src/take.rs:1371-1440 test_take_primitive
 template <class T>
 static void take_primitive_case() {
@@ -398,6 +450,7 @@ int main() {
       {"take_record_batch", test_take_record_batch},
       {"boolean_kernels", test_boolean_kernels},
       {"sum_checked", test_sum_checked},
+      {"batch_coalescer", test_batch_coalescer},
       {"take_primitive", test_take_primitive},
       {"take_with_offset", test_take_with_offset},
       {"take_bool", test_take_bool},

@@ -397,6 +397,27 @@ acu_status acu_aggregate_columns(acu_ctx *ctx, int32_t n_columns, const acu_dtyp
                                  int64_t *out_valid_counts);
 
 /* ------------------------------------------------------------------------- */
+/* appending row ranges — the pieces of BatchCoalescer / concat               */
+/* (arrow-select/src/coalesce.rs:258-533 InProgressArray::copy_rows)          */
+/* ------------------------------------------------------------------------- */
+/* Values of a fixed-width column append with acu_memcpy_d2d. Bits (validity, boolean
+ * values): dst bits [dst_offset, dst_offset+len) = src bits [src_offset, ..+len), every
+ * other bit of dst preserved (dst 8-byte aligned, capacity a whole number of u64 words).
+ * *out_set_bits (optional; forces a synchronisation) = number of set bits copied. */
+acu_status acu_bitmap_copy(acu_ctx *ctx, const uint8_t *src, int64_t src_offset, uint8_t *dst,
+                           int64_t dst_offset, int64_t len, int64_t *out_set_bits);
+/* dst bits [dst_offset, dst_offset+len) = value (0 | 1), other bits preserved. */
+acu_status acu_bitmap_fill(acu_ctx *ctx, uint8_t *dst, int64_t dst_offset, int64_t len, int32_t value);
+/* Utf8/Binary offsets of `count` rows starting at source row `first`, rebased so that the
+ * first one equals `base` (the destination's byte total so far):
+ * dst[dst_first + j] = base + src[first + j] - src[first], j = 0..count. Returns the source
+ * byte range [*out_src_begin, *out_src_end) to append with acu_memcpy_d2d.
+ * ACU_ERR_OFFSET_OVERFLOW when the running total leaves the offset type. */
+acu_status acu_offsets_append(acu_ctx *ctx, int32_t offset_bytes, const void *src_offsets, int64_t first,
+                              int64_t count, int64_t base, void *dst_offsets, int64_t dst_first,
+                              int64_t *out_src_begin, int64_t *out_src_end);
+
+/* ------------------------------------------------------------------------- */
 /* multi-GPU: row-range shards, NCCL only for the final scalar reduce        */
 /* ------------------------------------------------------------------------- */
 #define ACU_NCCL_UNIQUE_ID_BYTES 128
