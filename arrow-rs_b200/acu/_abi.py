@@ -103,6 +103,40 @@ class ColumnOut(C.Structure):
     ]
 
 
+# ---- Arrow C Data Interface / C Device Data Interface (include/arrow_cuda.h) ----------------------
+DEVICE_CPU, DEVICE_CUDA, DEVICE_CUDA_HOST = 1, 2, 3
+
+
+class ArrowSchema(C.Structure):
+    pass
+
+
+ArrowSchema._fields_ = [
+    ("format", C.c_char_p), ("name", C.c_char_p), ("metadata", C.c_char_p), ("flags", C.c_int64), ("n_children", C.c_int64),
+    ("children", C.POINTER(C.POINTER(ArrowSchema))), ("dictionary", C.POINTER(ArrowSchema)),
+    ("release", C.CFUNCTYPE(None, C.POINTER(ArrowSchema))), ("private_data", C.c_void_p),
+]
+
+
+class ArrowArray(C.Structure):
+    pass
+
+
+ArrowArray._fields_ = [
+    ("length", C.c_int64), ("null_count", C.c_int64), ("offset", C.c_int64), ("n_buffers", C.c_int64), ("n_children", C.c_int64),
+    ("buffers", C.POINTER(C.c_void_p)), ("children", C.POINTER(C.POINTER(ArrowArray))), ("dictionary", C.POINTER(ArrowArray)),
+    ("release", C.CFUNCTYPE(None, C.POINTER(ArrowArray))), ("private_data", C.c_void_p),
+]
+
+
+class ArrowDeviceArray(C.Structure):
+    _fields_ = [("array", ArrowArray), ("device_id", C.c_int64), ("device_type", C.c_int32), ("sync_event", C.c_void_p),
+                ("reserved", C.c_int64 * 3)]
+
+
+RELEASE_OWNER = C.CFUNCTYPE(None, C.c_void_p)
+
+
 def bitmap_bytes(n):
     return ((n + 63) // 64) * 8
 
@@ -165,6 +199,8 @@ PROTOTYPES = {
     "acu_bitmap_copy": (i32, [vp, vp, i64, vp, i64, i64, P(i64)]),
     "acu_bitmap_fill": (i32, [vp, vp, i64, i64, i32]),
     "acu_offsets_append": (i32, [vp, i32, vp, i64, i64, i64, vp, i64, P(i64), P(i64)]),
+    "acu_export_column": (i32, [vp, P(Column), i32, i32, RELEASE_OWNER, vp, P(ArrowDeviceArray), P(ArrowSchema)]),
+    "acu_import_column": (i32, [P(ArrowDeviceArray), P(ArrowSchema), P(Column), P(i32)]),
     "acu_comm_get_unique_id": (i32, [vp]),
     "acu_comm_init": (i32, [vp, vp, i32, i32]),
     "acu_comm_destroy": (i32, [vp]),

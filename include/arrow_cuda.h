@@ -418,6 +418,68 @@ acu_status acu_offsets_append(acu_ctx *ctx, int32_t offset_bytes, const void *sr
                               int64_t *out_src_begin, int64_t *out_src_end);
 
 /* ------------------------------------------------------------------------- */
+/* Arrow C Data Interface / C Device Data Interface                           */
+/* ------------------------------------------------------------------------- */
+/* The structs of the Arrow specification (the reference's FFI_ArrowArray / FFI_ArrowSchema,
+ * arrow-data/src/ffi.rs:37-69, arrow-schema/src/ffi.rs). Guarded like the specification's
+ * own header so that they can coexist with <arrow/c/abi.h>. */
+#ifndef ARROW_C_DATA_INTERFACE
+#define ARROW_C_DATA_INTERFACE
+struct ArrowSchema {
+  const char *format;
+  const char *name;
+  const char *metadata;
+  int64_t flags;
+  int64_t n_children;
+  struct ArrowSchema **children;
+  struct ArrowSchema *dictionary;
+  void (*release)(struct ArrowSchema *);
+  void *private_data;
+};
+struct ArrowArray {
+  int64_t length;
+  int64_t null_count;
+  int64_t offset;
+  int64_t n_buffers;
+  int64_t n_children;
+  const void **buffers;
+  struct ArrowArray **children;
+  struct ArrowArray *dictionary;
+  void (*release)(struct ArrowArray *);
+  void *private_data;
+};
+#endif
+#ifndef ARROW_C_DEVICE_DATA_INTERFACE
+#define ARROW_C_DEVICE_DATA_INTERFACE
+typedef int32_t ArrowDeviceType;
+#define ARROW_DEVICE_CPU 1
+#define ARROW_DEVICE_CUDA 2
+#define ARROW_DEVICE_CUDA_HOST 3
+struct ArrowDeviceArray {
+  struct ArrowArray array;
+  int64_t device_id;
+  ArrowDeviceType device_type;
+  void *sync_event;
+  int64_t reserved[3];
+};
+#endif
+/* Export a column (no copy): buffers[0] = validity, [1] = values | offsets, [2] = bytes, one
+ * logical offset (= the validity / boolean bit offset; `values` pointers are stepped back by
+ * it, so the column must be a slice of a buffer whose row 0 is addressable — true of every
+ * array this library or Arrow produces). `dtype` names the primitive type for the schema
+ * format. The consumer's call of out_array->array.release invokes release_owner(owner) exactly
+ * once. ctx may be NULL for ARROW_DEVICE_CPU columns. For device columns the ctx stream is
+ * synchronised and sync_event is NULL. */
+acu_status acu_export_column(acu_ctx *ctx, const acu_column *col, acu_dtype dtype, int32_t device_type,
+                             void (*release_owner)(void *), void *owner,
+                             struct ArrowDeviceArray *out_array, struct ArrowSchema *out_schema);
+/* View an imported (device or host) array as an acu_column: pointers into the producer's
+ * buffers, valid until the caller invokes in->array.release. Flat primitive / boolean /
+ * (large) utf8 / binary formats; anything else => ACU_ERR_NOT_YET_IMPLEMENTED. */
+acu_status acu_import_column(const struct ArrowDeviceArray *in, const struct ArrowSchema *schema,
+                             acu_column *out, acu_dtype *out_dtype);
+
+/* ------------------------------------------------------------------------- */
 /* multi-GPU: row-range shards, NCCL only for the final scalar reduce        */
 /* ------------------------------------------------------------------------- */
 #define ACU_NCCL_UNIQUE_ID_BYTES 128
