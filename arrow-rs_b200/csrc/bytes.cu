@@ -517,8 +517,6 @@ acu_status gather_launch(acu_ctx *ctx, int32_t ob, const void *offsets, const ui
   ACU_CUDA(ctx, cudaMemcpyAsync(res + RES_AUX0, block_tot + (blocks - 1), 8, cudaMemcpyDeviceToDevice, ctx->stream));
   const int stage_cap = BY_STAGE_CAP;
   a.detect_oob = 0;
-  static bool attr_set[2] = {false, false};  // per process is enough: the attribute is per function, per device context
-  (void)attr_set;
   if (fast) {
     ACU_CUDA(ctx, cudaFuncSetAttribute(k_bytes_offsets_copy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_cap));
     ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_offsets_copy<true>, (unsigned)blocks, BY_THREADS, stage_cap, a, block_tot, (int64_t)0, out_offsets,
