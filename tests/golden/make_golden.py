@@ -448,6 +448,23 @@ case("is_null_nullable_offset", B + ":847", "is_null", a=arr("int32", SIXTEEN, s
 case("is_not_null_nullable", B + ":878", "is_not_null", a=arr("int32", [1, None, 3, None]), expect={"data": [T, Fa, T, Fa], "no_validity": True})
 case("is_not_null_nullable_offset", B + ":890", "is_not_null", a=arr("int32", SIXTEEN, slice=(8, 4)), expect={"data": [T, Fa, T, Fa], "no_validity": True})
 
+T2 = "arrow-select/src/take.rs"
+FIVE = ["one", None, "three", "four", "five"]
+case("take_string", T2 + ":1702-1726", "take_utf8", values={"strings": FIVE}, indices=arr("uint32", [3, None, 1, 3, 4]),
+     expect={"strings": ["four", None, None, "four", "five"]})
+case("take_large_string", T2 + ":1728-1731", "take_utf8", values={"strings": FIVE, "large": True}, indices=arr("uint32", [3, None, 1, 3, 4]),
+     expect={"strings": ["four", None, None, "four", "five"]})
+case("take_slice_string", T2 + ":1733-1744", "take_utf8", values={"strings": ["hello", None, "world", None, "hi"]},
+     indices=arr("int32", [0, 1, None, 0, 2], slice=(1, 4)), expect={"strings": [None, None, "hello", "world"]})
+SEVEN = ["aaa", "bbb", None, "ccccc", "dd", None, "eeee"]
+case("take_bytes_sliced_values_fast_path", T2 + ":1750-1775", "take_utf8", values={"strings": SEVEN, "slice": [2, 5]},
+     indices=arr("int32", [1, 2, 4, 1]), expect={"strings": ["ccccc", "dd", "eeee", "ccccc"]})
+case("take_bytes_sliced_values_nullable_path", T2 + ":1777-1783", "take_utf8", values={"strings": SEVEN, "slice": [2, 5]},
+     indices=arr("int32", [1, None, 0, 4, 3]), expect={"strings": ["ccccc", None, None, "eeee", None]})
+F2 = "arrow-select/src/filter.rs"
+case("filter_string_array_sliced_values", F2 + ":893-928", "filter_utf8", values={"strings": SEVEN, "slice": [2, 5]},
+     predicate=arr("bool", [True, True, False, True, True]), expect={"strings": [None, "ccccc", None, "eeee"]})
+
 A = "arrow-arith/src/aggregate.rs"
 case("sum_checked_overflow", A + ":1993", "sum_checked", a=arr("int32", [I32_MAX, 1]),
      expect_error="Arithmetic overflow: Overflow happened on: 2147483647 + 1")

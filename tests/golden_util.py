@@ -53,8 +53,9 @@ def build_array(spec):
 
 
 def build_strings(spec):
+    """{"strings": [...], "large": bool (i64 offsets), "slice": [offset, len] (value offsets then no longer start at 0)}"""
     strings = spec["strings"]
-    offsets = np.zeros(len(strings) + 1, dtype=np.int32)
+    offsets = np.zeros(len(strings) + 1, dtype=np.int64 if spec.get("large") else np.int32)
     chunks = []
     for i, s in enumerate(strings):
         b = b"" if s is None else s.encode()
@@ -64,7 +65,13 @@ def build_strings(spec):
     mask = [s is not None for s in strings]
     nulls = HostArray.from_list(abi.U8, [0 if m else None for m in mask])
     nulls.values = np.zeros(0, np.uint8)
-    return offsets, data[: offsets[-1] + 16], nulls
+    data = data[: offsets[-1] + 16]
+    if "slice" in spec:  # Array::slice of a byte array: offsets window + validity bit offset, same data buffer
+        off, ln = spec["slice"]
+        offsets = offsets[off: off + ln + 1]
+        nulls = nulls.slice(off, ln)
+        nulls.values = np.zeros(0, np.uint8)
+    return offsets, data, nulls
 
 
 def strings_of(offsets, data, nulls):

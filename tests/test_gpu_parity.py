@@ -302,6 +302,26 @@ def test_dictionary_filter_take_on_keys(gpu, oracle):
             assert_same_bytes(gpu.take_bytes(d_off, d_data, d_nulls, tk), gpu.take_bytes(decoded[0], decoded[1], decoded[2], idx), f"take_dict n={n}")
 
 
+def test_take_bytes_offset_overflow(gpu, oracle):
+    """take.rs:2877-2910 test_take_bytes_offset_overflow(_nullable): one 1 MB value selected i32::MAX / 1e6 + 1 times
+    => Err(OffsetOverflowError(capacity)) on the no-null fast path and on the nullable path, with the reference's
+    capacity (the running total at the first index that no longer fits i32). Sizing mode: no bytes are copied."""
+    value_len = 1_000_000
+    n = (2**31 - 1) // value_len + 1
+    offsets = np.array([0, value_len], dtype=np.int32)
+    data = np.full(value_len + 16, ord("a"), dtype=np.uint8)
+    nulls = HostArray(abi.U8, np.zeros(0, np.uint8), 1, None, 0, 0, 0)
+    for idx in (HostArray.from_numpy(abi.I32, np.zeros(n, dtype=np.int32)),
+                HostArray.from_numpy(abi.I32, np.zeros(n + 1, dtype=np.int32), np.arange(n + 1) != 0)):
+        errs = []
+        for be in (gpu, oracle):
+            with pytest.raises(acu.ArrowError) as e:
+                be.take_bytes(offsets, data, nulls, idx)
+            errs.append(e.value)
+        assert errs[0].status == errs[1].status == abi.ERR_OFFSET_OVERFLOW
+        assert str(errs[0]) == str(errs[1]) == f"Offset overflow error: {n * value_len}"
+
+
 # ---- 16 / 32-byte elements: Decimal128/256, intervals, and Utf8View / BinaryView ----------------
 def _wide_column(gpu, raw_u64, n, width, mask):
     """Device descriptor of n `width`-byte records (given as uint64 lanes) with an optional validity mask."""
