@@ -174,3 +174,45 @@ def test_socket_rendezvous_world_3():
     for p in procs:
         p.join(timeout=30)
     assert all(got[r] == bytes(range(128)) for r in range(3))
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_shard_outputs_concatenate_to_the_global_result(world):
+    """with contiguous 64-row-aligned row ranges, the filter output of shard g is the g-th contiguous
+    piece of the global filter output (values, validity, Utf8 strings), global offsets = exclusive scan of the counts."""
+    sys.path.insert(0, os.path.join(REPO, "arrow-rs_b200"))
+    sys.path.insert(0, HERE)
+    import acu
+    from acu import _abi as abi
+    from acu import HostArray, shard
+    from golden_util import strings_of
+    from oracle import Oracle
+    orc = Oracle()
+    rng = np.random.default_rng(world)
+    n = 10_000 + world
+    vals = rng.integers(-1000, 1000, n).astype(np.int64)
+    valid = rng.random(n) >= 0.1
+    pred = rng.random(n) < 0.3
+    lens = rng.integers(0, 9, n)
+    offs = np.zeros(n + 1, dtype=np.int32)
+    offs[1:] = np.cumsum(lens)
+    data = rng.integers(97, 123, int(offs[-1]) + 16).astype(np.uint8)
+
+    def strings(lo, hi):
+        o = (offs[lo:hi + 1] - offs[lo]).astype(np.int32)
+        d = data[offs[lo]: offs[hi] + 16].copy()
+        nl = HostArray(abi.U8, np.zeros(0, np.uint8), hi - lo, acu.pack_bits(valid[lo:hi]), 0, 0, int((~valid[lo:hi]).sum()))
+        return o, d, nl
+
+    whole = orc.filter(HostArray.from_numpy(abi.I64, vals, valid), HostArray.bool_from_numpy(pred))
+    whole_s = strings_of(*orc.filter_bytes(*strings(0, n), HostArray.bool_from_numpy(pred)))
+    pieces, pieces_s, counts = [], [], []
+    for lo, hi in shard.shard_ranges(n, world):
+        assert lo % 64 == 0
+        p = HostArray.bool_from_numpy(pred[lo:hi])
+        f = orc.filter(HostArray.from_numpy(abi.I64, vals[lo:hi], valid[lo:hi]), p)
+        pieces += f.to_list()
+        pieces_s += strings_of(*orc.filter_bytes(*strings(lo, hi), p))
+        counts.append(f.length)
+    assert pieces == whole.to_list() and pieces_s == whole_s
+    assert sum(counts) == whole.length and list(np.cumsum([0] + counts[:-1])) == [sum(counts[:g]) for g in range(world)]
