@@ -53,3 +53,35 @@ def test_no_cpu_fallback_without_gpu():
         lib.acu_ctx_destroy(h)
         pytest.skip("CUDA device present")
     assert st == abi.ERR_CUDA and not h.value
+
+
+def _build_c_example(tmp_path):
+    """The header is plain C (C11, -pedantic) and the library links from C: examples/hot_path.c."""
+    import subprocess
+    exe = str(tmp_path / "hot_path")
+    cmd = ["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(abi.REPO, "include"),
+           os.path.join(abi.REPO, "examples", "hot_path.c"), "-L" + os.path.dirname(abi.LIB_PATH), "-larrow_cuda",
+           "-Wl,-rpath," + os.path.dirname(abi.LIB_PATH), "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_c_example_compiles_and_fails_loudly_without_gpu(tmp_path):
+    import subprocess
+    exe = _build_c_example(tmp_path)
+    ctx = C.c_void_p()
+    if abi.load_library().acu_ctx_create(0, C.byref(ctx)) == abi.OK:
+        abi.load_library().acu_ctx_destroy(ctx)
+        pytest.skip("a GPU is present: covered by test_c_example_runs_on_gpu")
+    r = subprocess.run([exe, "1000"], capture_output=True, text=True)
+    assert r.returncode != 0 and "acu_ctx_create" in r.stderr  # no CPU fallback
+
+
+@pytest.mark.gpu
+def test_c_example_runs_on_gpu(tmp_path):
+    import subprocess
+    exe = _build_c_example(tmp_path)
+    r = subprocess.run([exe, "3000000"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert "rows 3000000, selected" in r.stdout
