@@ -615,7 +615,35 @@ def cpu_baseline(args, from_ctx=None, steps=1):
     run(plan_mt, threads)  # warm-up (page faults, output allocation)
     best_mt = min(run(plan_mt, threads) for _ in range(max(1, steps)))
     best_1t = run(plan_1t, 1) if threads > 1 else best_mt
-    return {"value": n / best_mt / 1e6, "unit": "Mrows/s", "cores": threads, "kind": "port",
+    # secondary, labelled figure: the same step through pyarrow (Arrow C++ 24, a different implementation of the same
+    # format — not arrow-rs and not the oracle), one call per op over the whole sample like arrow-rs would be driven
+    secondary = None
+    try:
+        import pyarrow as pa
+        import pyarrow.compute as pc
+
+        def pa_prim(t, values, valid):
+            return pa.Array.from_buffers(t, n, [pa.py_buffer(valid) if valid is not None else None, pa.py_buffer(values)], null_count=-1 if valid is not None else 0)
+
+        p_col = pa_prim(pa.int64(), data["i64"], data["i64_valid"])
+        p_a, p_b = pa_prim(pa.float64(), data["a"], data["a_valid"]), pa_prim(pa.float64(), data["b"], data["b_valid"])
+        p_pred = pa.Array.from_buffers(pa.bool_(), n, [None, pa.py_buffer(data["pred"])], null_count=0)
+        p_idx = pa.array(plan_1t[1][0].value_array(), type=pa.uint32())
+
+        def pa_step():
+            t0 = time.perf_counter()
+            pc.filter(p_col, p_pred, null_selection_behavior="drop")
+            tk = pc.take(p_col, p_idx, boundscheck=False)
+            pc.add(p_a, p_b)
+            pc.sum(tk)
+            return time.perf_counter() - t0
+
+        pa_step()
+        secondary = {"impl": f"pyarrow {pa.__version__} (Arrow C++; labelled secondary baseline, not arrow-rs)", "value": n / min(pa_step() for _ in range(2)) / 1e6,
+                     "unit": "Mrows/s", "threads": "one call per op over the whole sample (pyarrow's own kernel threading)"}
+    except Exception as e:  # pyarrow is optional
+        secondary = {"impl": "pyarrow", "skipped": repr(e)[:120]}
+    return {"value": n / best_mt / 1e6, "unit": "Mrows/s", "cores": threads, "kind": "port", "secondary": secondary,
             "sample": f"first {n} rows of the same synthetic table (1/{max(1, args.rows // n)} of the workload), same step "
                       f"(filter+take+add+sum), row-partitioned over {threads} threads; oracle/ C++ restatement of arrow-rs (no Rust toolchain here)",
             "value_1_thread": n / best_1t / 1e6, "host_cores": cores, "seconds": best_mt}
