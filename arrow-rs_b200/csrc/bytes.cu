@@ -316,6 +316,25 @@ struct WordEmitter {
     acc = t >= 8u ? x2 : (t >= 4u ? x1 : x0);
     nacc = t & 3u;
   }
+  // EXPERIMENT (off by default, -DACU_BYTES_PUSH16): a whole <= 16-byte row in one step — one 5-word
+  // shift instead of two 3-word ones. v = (w1:w0), bytes at positions >= nb are zero, nb in 0..16.
+  __device__ __forceinline__ void push16(uint64_t w0, uint64_t w1, uint32_t nb) {
+    const uint32_t sh = nacc * 8u;
+    const uint32_t v0 = (uint32_t)w0, v1 = (uint32_t)(w0 >> 32), v2 = (uint32_t)w1, v3 = (uint32_t)(w1 >> 32);
+    const uint32_t x0 = acc | (v0 << sh);
+    const uint32_t x1 = __funnelshift_l(v0, v1, sh);
+    const uint32_t x2 = __funnelshift_l(v1, v2, sh);
+    const uint32_t x3 = __funnelshift_l(v2, v3, sh);
+    const uint32_t x4 = __funnelshift_l(v3, 0u, sh);
+    const uint32_t t = nacc + nb;  // 0..19 bytes available
+    if (t >= 4u) store(x0);
+    if (t >= 8u) store(x1);
+    if (t >= 12u) store(x2);
+    if (t >= 16u) store(x3);
+    const uint32_t k = t >> 2;     // words that left
+    acc = k == 0u ? x0 : k == 1u ? x1 : k == 2u ? x2 : k == 3u ? x3 : x4;
+    nacc = t & 3u;
+  }
   __device__ __forceinline__ void finish() {
     if (acc != 0u) atomicOr(w, acc);
   }
@@ -446,8 +465,12 @@ __global__ void __launch_bounds__(BY_THREADS, 2) k_bytes_offsets_copy(const Byte
       const uint32_t n0 = l32 < 8u ? l32 : 8u, n1 = l32 - n0;
       uint64_t w0, w1;
       load_upto16(a.data, begin[k], l32, &w0, &w1);
+#ifdef ACU_BYTES_PUSH16
+      em.push16(w0, w1, l32);
+#else
       em.push8(w0, n0);
       em.push8(w1, n1);
+#endif
       // ... the rest of a long row 8 bytes at a time
       for (uint64_t c = 16; c < len[k]; c += 8) {
         const uint32_t nb = (uint32_t)((len[k] - c) < 8 ? (len[k] - c) : 8);
