@@ -417,6 +417,27 @@ class HostPipelined:
             ctx.lib.acu_host_free(ctx.h, p)
 
 
+def numa_bind(gpu_index):
+    """Opt-in (ACU_BENCH_NUMA=1): run this rank's host threads, and therefore first-touch its pinned buffers, on the CPUs
+    NVML reports as local to the GPU. Returns the previous affinity (to restore) or None when nothing was changed."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[gpu_index]) if vis else gpu_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        before = os.sched_getaffinity(0)
+        cpus &= before
+        if not cpus or cpus == before:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return before
+    except Exception:
+        return None
+
+
 def algorithmic_bytes(n, m):
     """each input read once, each output written once, bitmaps ceil(rows/8)."""
     return {
@@ -483,6 +504,7 @@ def run_gpu(args):
             avail = 64 << 30
         need = n * 34 + (64 << 20)
         if need * world < avail * 0.6:
+            all_cpus = numa_bind(local_rank) if os.environ.get("ACU_BENCH_NUMA") == "1" else None  # opt-in experiment
             hs = HostStaged(wl) if args.e2e_mode == "serial" else HostPipelined(wl, local_rank, args.e2e_batch_rows, args.e2e_workers)
             e2e_check = hs.step()
             barrier()
@@ -500,6 +522,8 @@ def run_gpu(args):
                    "timer": "host perf_counter around steps that end with a stream sync (spans several streams)",
                    "check": {"sum_bits": int(e2e_check[0]), "valid_rows": int(e2e_check[1])}}
             hs.free()
+            if all_cpus:
+                os.sched_setaffinity(0, all_cpus)  # the CPU baseline below uses every host core again
         else:
             e2e = {"value": None, "unit": "Mrows/s", "skipped": f"host RAM: need {need * world >> 30} GiB pinned, {avail >> 30} GiB available"}
 
