@@ -607,27 +607,50 @@ def cpu_baseline(args, from_ctx=None, steps=1):
             ncs.append(tuple(int(hi - lo - acu.unpack_bits(data[k][lo // 8:], 0, hi - lo).sum()) for k in ("i64_valid", "a_valid", "b_valid")))
         return ranges, idxs, ncs
 
-    def run(parts_plan, nthreads):
+    def prepare(parts_plan):
+        """Per range: input descriptors + caller-owned, pre-faulted output buffers (the CPU arm gets what the GPU arm
+        gets: outputs allocated once outside the timed region; a warm allocator would hand arrow-rs recycled pages)."""
         ranges, idxs, ncs = parts_plan
-
-        def work(k):
-            lo, hi = ranges[k]
+        jobs = []
+        for k, (lo, hi) in enumerate(ranges):
             m = hi - lo
             col = HostArray(abi.I64, data["i64"][lo:hi], m, data["i64_valid"][lo // 8:], 0, 0, ncs[k][0])
             pred = HostArray(BOOL, data["pred"][lo // 8:], m, None, 0, 0, 0)
             a = HostArray(abi.F64, data["a"][lo:hi], m, data["a_valid"][lo // 8:], 0, 0, ncs[k][1])
             b = HostArray(abi.F64, data["b"][lo:hi], m, data["b_valid"][lo // 8:], 0, 0, ncs[k][2])
-            orc.filter(col, pred)
-            t = orc.take(col, idxs[k])
-            orc.add(a, b)
-            orc.sum(t)
+            sel = idxs[k].length
+            bufs = {"f_v": np.ones(sel * 8 + 64, np.uint8), "f_n": np.ones(abi.bitmap_bytes(sel) + 64, np.uint8), "t_v": np.ones(sel * 8 + 64, np.uint8),
+                    "t_n": np.ones(abi.bitmap_bytes(sel) + 64, np.uint8), "s_v": np.ones(m * 8 + 64, np.uint8), "s_n": np.ones(abi.bitmap_bytes(m) + 64, np.uint8)}
+            outs = {}
+            for name in ("f", "t", "s"):
+                o = abi.ArrayOut()
+                o.values, o.validity = bufs[name + "_v"].ctypes.data, bufs[name + "_n"].ctypes.data
+                outs[name] = o
+            jobs.append({"keep": (col, pred, a, b, idxs[k], bufs), "col": acu.host_descriptor(col), "pred": acu.host_descriptor(pred),
+                         "a": acu.host_descriptor(a), "b": acu.host_descriptor(b), "idx": acu.host_descriptor(idxs[k]), "outs": outs})
+        return jobs
+
+    def run(jobs, nthreads):
+        lib = orc.lib
+
+        def work(j):
+            cnt, strat = C.c_int64(0), C.c_int32(0)
+            o = j["outs"]
+            orc.check(lib.orc_filter_primitive(C.byref(j["pred"]), 8, C.byref(j["col"]), C.byref(o["f"]), C.byref(cnt), C.byref(strat)))
+            orc.check(lib.orc_take_primitive(8, C.byref(j["col"]), C.byref(j["idx"]), abi.U32, 0, C.byref(o["t"])))
+            orc.check(lib.orc_arith(abi.F64, abi.ADD, C.byref(j["a"]), C.byref(j["b"]), C.byref(o["s"])))
+            t = abi.Array()
+            t.values, t.validity = o["t"].values, o["t"].validity if o["t"].has_validity else None
+            t.len, t.null_count = o["t"].len, o["t"].null_count if o["t"].has_validity else 0
+            bits, vc = C.c_uint64(0), C.c_int64(0)
+            orc.check(lib.orc_aggregate(abi.I64, abi.SUM, C.byref(t), 16, C.byref(bits), C.byref(vc)))
 
         t0 = time.perf_counter()
         if nthreads == 1:
-            for k in range(len(ranges)):
-                work(k)
+            for j in jobs:
+                work(j)
         else:
-            ts = [threading.Thread(target=work, args=(k,)) for k in range(len(ranges))]  # ctypes releases the GIL
+            ts = [threading.Thread(target=work, args=(j,)) for j in jobs]  # ctypes releases the GIL
             for t in ts:
                 t.start()
             for t in ts:
@@ -636,9 +659,16 @@ def cpu_baseline(args, from_ctx=None, steps=1):
 
     plan_mt = plan_ranges(threads)
     plan_1t = plan_ranges(1) if threads > 1 else plan_mt  # ONE call over the whole array, as arrow-rs would run it
-    run(plan_mt, threads)  # warm-up (page faults, output allocation)
-    best_mt = min(run(plan_mt, threads) for _ in range(max(1, steps)))
-    best_1t = run(plan_1t, 1) if threads > 1 else best_mt
+    jobs_mt = prepare(plan_mt)
+    run(jobs_mt, threads)  # warm-up
+    best_mt = min(run(jobs_mt, threads) for _ in range(max(1, steps)))
+    if threads > 1:
+        del jobs_mt
+        jobs_1t = prepare(plan_1t)
+        run(jobs_1t, 1)
+        best_1t = min(run(jobs_1t, 1) for _ in range(2))
+    else:
+        best_1t = best_mt
     # secondary, labelled figure: the same step through pyarrow (Arrow C++ 24, a different implementation of the same
     # format — not arrow-rs and not the oracle), one call per op over the whole sample like arrow-rs would be driven
     secondary = None
@@ -669,7 +699,7 @@ def cpu_baseline(args, from_ctx=None, steps=1):
         secondary = {"impl": "pyarrow", "skipped": repr(e)[:120]}
     return {"value": n / best_mt / 1e6, "unit": "Mrows/s", "cores": threads, "kind": "port", "secondary": secondary,
             "sample": f"first {n} rows of the same synthetic table (1/{max(1, args.rows // n)} of the workload), same step "
-                      f"(filter+take+add+sum), row-partitioned over {threads} threads; oracle/ C++ restatement of arrow-rs (no Rust toolchain here)",
+                      f"(filter+take+add+sum), row-partitioned over {threads} threads, outputs pre-allocated; oracle/ C++ restatement of arrow-rs (no Rust toolchain here)",
             "value_1_thread": n / best_1t / 1e6, "host_cores": cores, "seconds": best_mt}
 
 
