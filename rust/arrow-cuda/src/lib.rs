@@ -137,5 +137,62 @@ pub fn filter<T: ArrowPrimitiveType>(ctx: &Context, values: &PrimitiveArray<T>, 
     let _ = DataType::Null;
     Ok(Arc::new(PrimitiveArray::<T>::new(vals, nulls).with_data_type(values.data_type().clone())))
 }
-// take / cmp / cast / aggregate follow the same pattern over acu_take_primitive / acu_cmp /
-// acu_cast_numeric / acu_aggregate (see INTEGRATION.md §2 for the full mapping table).
+/// Shared tail of every call that returns a primitive array: download values (+ validity when the
+/// result carries a NullBuffer) and re-attach the logical DataType.
+fn finish_primitive<T: ArrowPrimitiveType>(out: &ffi::acu_array_out, values: &DeviceBuffer, valid: &DeviceBuffer, data_type: &DataType) -> ArrayRef {
+    let vals = ScalarBuffer::<T::Native>::new(values.to_host(), 0, out.len as usize);
+    let nulls = (out.has_validity != 0).then(|| unsafe {
+        NullBuffer::new_unchecked(BooleanBuffer::new(valid.to_host(), 0, out.len as usize), out.null_count as usize)
+    });
+    Arc::new(PrimitiveArray::<T>::new(vals, nulls).with_data_type(data_type.clone()))
+}
+
+/// `arrow::compute::take(values, indices, options)` (arrow-select/src/take.rs:89-105) for primitive values and any
+/// integer index type `I`; `index_dtype` is the acu_dtype code of `I` (include/arrow_cuda.h).
+pub fn take<T: ArrowPrimitiveType, I: ArrowPrimitiveType>(ctx: &Context, values: &PrimitiveArray<T>, indices: &PrimitiveArray<I>,
+                                                          index_dtype: i32, check_bounds: bool) -> Result<ArrayRef, ArrowError> {
+    let (v, ix) = (upload_primitive(ctx, values, false)?, upload_primitive(ctx, indices, false)?);
+    let (m, width) = (indices.len(), std::mem::size_of::<T::Native>());
+    let out_values = DeviceBuffer::from_host(ctx, &vec![0u8; m.max(1) * width])?;
+    let out_valid = DeviceBuffer::from_host(ctx, &vec![0u8; (m + 63) / 64 * 8 + 8])?;
+    let mut out = ffi::acu_array_out { values: out_values.ptr, validity: out_valid.ptr as *mut u8, len: 0, null_count: 0, has_validity: 0, reserved: 0 };
+    let st = unsafe { ffi::acu_take_primitive(ctx.raw, width as i32, &v.view, &ix.view, index_dtype, check_bounds as i32, &mut out) };
+    if st != ffi::ACU_OK { return Err(ctx.error(st)); } // ACU_ERR_PANIC_OUT_OF_BOUNDS panics inside error(), like take.rs:447
+    Ok(finish_primitive::<T>(&out, &out_values, &out_valid, values.data_type()))
+}
+
+/// `arrow::compute::kernels::cmp::{eq, neq, lt, lt_eq, gt, gt_eq, distinct, not_distinct}` (arrow-ord/src/cmp.rs:79-202):
+/// `op` is the acu_cmp_op code; floats compare by IEEE totalOrder like the reference.
+pub fn compare<T: ArrowPrimitiveType>(ctx: &Context, dtype: i32, op: i32, lhs: &dyn Datum, rhs: &dyn Datum) -> Result<BooleanArray, ArrowError> {
+    let (l, l_s) = lhs.get();
+    let (r, r_s) = rhs.get();
+    let l = l.as_any().downcast_ref::<PrimitiveArray<T>>().ok_or_else(|| ArrowError::InvalidArgumentError("type mismatch".into()))?;
+    let r = r.as_any().downcast_ref::<PrimitiveArray<T>>().ok_or_else(|| ArrowError::InvalidArgumentError("type mismatch".into()))?;
+    let (a, b) = (upload_primitive(ctx, l, l_s)?, upload_primitive(ctx, r, r_s)?);
+    let n = if l_s { r.len() } else { l.len() };
+    let bytes = (n.max(1) + 63) / 64 * 8 + 8;
+    let (out_bits, out_valid) = (DeviceBuffer::from_host(ctx, &vec![0u8; bytes])?, DeviceBuffer::from_host(ctx, &vec![0u8; bytes])?);
+    let mut out = ffi::acu_array_out { values: out_bits.ptr, validity: out_valid.ptr as *mut u8, len: 0, null_count: 0, has_validity: 0, reserved: 0 };
+    let st = unsafe { ffi::acu_cmp(ctx.raw, dtype, op, &a.view, &b.view, &mut out) };
+    if st != ffi::ACU_OK { return Err(ctx.error(st)); }
+    let values = BooleanBuffer::new(out_bits.to_host(), 0, out.len as usize);
+    let nulls = (out.has_validity != 0).then(|| unsafe {
+        NullBuffer::new_unchecked(BooleanBuffer::new(out_valid.to_host(), 0, out.len as usize), out.null_count as usize)
+    });
+    Ok(BooleanArray::new(values, nulls))
+}
+
+/// `arrow::compute::{sum, min, max}` (arrow-arith/src/aggregate.rs:943,1012,1027): `None` iff no valid row.
+pub fn aggregate<T: ArrowPrimitiveType>(ctx: &Context, dtype: i32, op: i32, array: &PrimitiveArray<T>) -> Result<Option<T::Native>, ArrowError>
+where T::Native: Copy {
+    let a = upload_primitive(ctx, array, false)?;
+    let (mut bits, mut valid) = (0u64, 0i64);
+    let st = unsafe { ffi::acu_aggregate(ctx.raw, dtype, op, &a.view, &mut bits, &mut valid) };
+    if st != ffi::ACU_OK { return Err(ctx.error(st)); }
+    if valid == 0 { return Ok(None); }
+    // the result is the native value's bit pattern, zero-extended to 64 bits (little endian)
+    Ok(Some(unsafe { std::ptr::read_unaligned(&bits as *const u64 as *const T::Native) }))
+}
+// cast and the RecordBatch-level calls (acu_cast_numeric, acu_filter_record_batch, acu_take_record_batch) follow the
+// same pattern; INTEGRATION.md §2 has the full mapping table. A production shim keeps arrays in `DeviceBuffer`s between
+// calls instead of uploading / downloading around every kernel as these reference-shaped wrappers do.
