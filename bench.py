@@ -34,23 +34,42 @@ SEED_VALUES, SEED_B, SEED_VALID_A, SEED_VALID_B, SEED_PRED = 42, 43, 44, 45, 46 
 SELECTIVITY, NULL_DENSITY = 0.10, 0.05
 
 
-def profiled_traffic(rows):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
-    (profiles/rNN_traffic.json, taken at 1e9 rows per GPU); null for other sizes."""
-    if rows != 1_000_000_000:
+def so_sha16():
+    import hashlib
+    p = os.path.join(REPO, "arrow-rs_b200", "libarrow_cuda.so")
+    try:
+        return hashlib.sha256(open(p, "rb").read()).hexdigest()[:16]
+    except Exception:
         return None
-    best = None
+
+
+def profiled_traffic(rows):
+    """Per-launch dram__bytes_read.sum + dram__bytes_write.sum of the step's kernels from the newest committed
+    ncu --set full capture (profiles/rNN_traffic.json: {"so_sha16", "rows", "kernels": {name: bytes}}; the r01 file is a flat
+    {name: bytes}). Returns (dict kernel-prefix -> bytes, source file, sha of the .so the capture was taken on) or ({}, None, None)
+    for other row counts."""
     pdir = os.path.join(REPO, "profiles")
+    best, src, sha = {}, None, None
     for name in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
         if name.endswith("_traffic.json"):
             try:
                 d = json.load(open(os.path.join(pdir, name)))
-                for k, v in d.items():
-                    if k.startswith("k_arith<double"):
-                        best = float(v)
+                if "kernels" in d:
+                    if int(d.get("rows", 0)) != rows:
+                        continue
+                    best, src, sha = {k: float(v) for k, v in d["kernels"].items()}, name, d.get("so_sha16")
+                elif rows == 1_000_000_000:
+                    best, src, sha = {k: float(v) for k, v in d.items() if isinstance(v, (int, float))}, name, None
             except Exception:
                 pass
-    return best
+    return best, src, sha
+
+
+def traffic_of(traffic, prefix):
+    for k, v in traffic.items():
+        if k.startswith(prefix):
+            return v
+    return None
 
 
 def peaks():
@@ -130,27 +149,33 @@ class ClockSampler:
 class Workload:
     """Device-resident synthetic table for one rank (deterministic)."""
 
-    def __init__(self, ctx, rows, first_row):
+    def __init__(self, ctx, rows, first_row, share=None):
+        """share: another Workload of the same first_row with >= rows rows — view its first `rows` rows (same device
+        buffers, own counts / indices) instead of generating a table (used to check a prefix against the oracle)."""
         import acu
         from acu import _abi as abi
         self.ctx, self.abi, self.acu, self.n = ctx, abi, acu, rows
         lib, h = ctx.lib, ctx.h
         bb = abi.bitmap_bytes(rows)
         self.bb = bb
-        self.d_i64 = ctx.malloc(rows * 8)
-        self.d_i64_valid = ctx.malloc(bb)
-        self.d_pred = ctx.malloc(bb)
-        self.d_a = ctx.malloc(rows * 8)
-        self.d_b = ctx.malloc(rows * 8)
-        self.d_a_valid = ctx.malloc(bb)
-        self.d_b_valid = ctx.malloc(bb)
-        ctx.check(lib.acu_generate_values(h, 0, SEED_VALUES, first_row, 0, self.d_i64, rows))
-        ctx.check(lib.acu_generate_values(h, 2, SEED_VALUES, first_row, 0, self.d_a, rows))
-        ctx.check(lib.acu_generate_values(h, 2, SEED_B, first_row, 0, self.d_b, rows))
-        ctx.check(lib.acu_generate_bits(h, SEED_VALID_A, first_row, 1.0 - NULL_DENSITY, self.d_i64_valid, rows))
-        ctx.check(lib.acu_generate_bits(h, SEED_VALID_A + 100, first_row, 1.0 - NULL_DENSITY, self.d_a_valid, rows))
-        ctx.check(lib.acu_generate_bits(h, SEED_VALID_B, first_row, 1.0 - NULL_DENSITY, self.d_b_valid, rows))
-        ctx.check(lib.acu_generate_bits(h, SEED_PRED, first_row, SELECTIVITY, self.d_pred, rows))
+        if share is not None:
+            for k in ("d_i64", "d_i64_valid", "d_pred", "d_a", "d_b", "d_a_valid", "d_b_valid"):
+                setattr(self, k, getattr(share, k))
+        else:
+            self.d_i64 = ctx.malloc(rows * 8)
+            self.d_i64_valid = ctx.malloc(bb)
+            self.d_pred = ctx.malloc(bb)
+            self.d_a = ctx.malloc(rows * 8)
+            self.d_b = ctx.malloc(rows * 8)
+            self.d_a_valid = ctx.malloc(bb)
+            self.d_b_valid = ctx.malloc(bb)
+            ctx.check(lib.acu_generate_values(h, 0, SEED_VALUES, first_row, 0, self.d_i64, rows))
+            ctx.check(lib.acu_generate_values(h, 2, SEED_VALUES, first_row, 0, self.d_a, rows))
+            ctx.check(lib.acu_generate_values(h, 2, SEED_B, first_row, 0, self.d_b, rows))
+            ctx.check(lib.acu_generate_bits(h, SEED_VALID_A, first_row, 1.0 - NULL_DENSITY, self.d_i64_valid, rows))
+            ctx.check(lib.acu_generate_bits(h, SEED_VALID_A + 100, first_row, 1.0 - NULL_DENSITY, self.d_a_valid, rows))
+            ctx.check(lib.acu_generate_bits(h, SEED_VALID_B, first_row, 1.0 - NULL_DENSITY, self.d_b_valid, rows))
+            ctx.check(lib.acu_generate_bits(h, SEED_PRED, first_row, SELECTIVITY, self.d_pred, rows))
         ctx.sync()
         # exact null counts (cached like NullBuffer does) and the output capacity
         self.nc_i64 = rows - self._count(self.d_i64_valid)
@@ -159,16 +184,23 @@ class Workload:
         self.m = self._count(self.d_pred)
         # outputs (caller-owned, reused every step)
         mb = abi.bitmap_bytes(self.m)
-        self.out_filter = self._out(self.m * 8, mb)
-        self.out_take = self._out(self.m * 8, mb)
-        self.out_add = self._out(rows * 8, bb)
+        if share is not None:
+            self.out_filter, self.out_take, self.out_add = share.out_filter, share.out_take, share.out_add
+        else:
+            self.out_filter = self._out(self.m * 8, mb)
+            self.out_take = self._out(self.m * 8, mb)
+            self.out_add = self._out(rows * 8, bb)
         # take's indices are an INPUT (as for the CPU arm): the selected rows of the predicate, ascending
         # (index distribution A of SURVEY.md §8(d): what a filter -> take pipeline produces)
         self.d_idx = ctx.malloc(self.m * 4)
+        self.rebuild_indices()
+
+    def rebuild_indices(self):
+        ctx, lib, h = self.ctx, self.ctx.lib, self.ctx.h
         pred = self.arr(self.d_pred, None, self.n, 0)
         plan = C.c_void_p()
         ctx.check(lib.acu_filter_plan_create(h, C.byref(pred), C.byref(plan)))
-        ctx.check(lib.acu_filter_plan_indices(h, plan, abi.U32, self.d_idx))
+        ctx.check(lib.acu_filter_plan_indices(h, plan, self.abi.U32, self.d_idx))
         lib.acu_filter_plan_destroy(h, plan)
 
     def _count(self, d_bits):
@@ -205,6 +237,31 @@ def make_arr(abi, values, validity, n, null_count):
     a.validity, a.validity_offset = validity, 0
     a.len, a.null_count, a.is_scalar = n, null_count, 0
     return a
+
+
+def gpu_checksums(ctx, abi, wl):
+    """Run one rank-local step (no all-reduce) and fold its outputs into the same checksums oracle/refbench.cpp computes
+    on the CPU (RefBench.CHECK_KEYS): row / null counts and wrapping Int64 sums of every output buffer's bit patterns
+    (all slots, validity ignored) — computed on the device with acu_aggregate."""
+    lib, h = ctx.lib, ctx.h
+    wl.rebuild_indices()  # the e2e arm used d_idx as scratch for its batch-local indices
+    pred = wl.arr(wl.d_pred, None, wl.n, 0)
+    col = wl.arr(wl.d_i64, wl.d_i64_valid, wl.n, wl.nc_i64)
+    idx = wl.arr(wl.d_idx, None, wl.m, 0)
+    a = wl.arr(wl.d_a, wl.d_a_valid, wl.n, wl.nc_a)
+    b = wl.arr(wl.d_b, wl.d_b_valid, wl.n, wl.nc_b)
+    bits, cnt = hot_path_step(ctx, abi, pred, col, idx, a, b, wl.out_filter, wl.out_take, wl.out_add, allreduce=False)
+
+    def wsum(out):
+        arr = make_arr(abi, out.values, None, out.len, 0)
+        sb, sc = C.c_uint64(0), C.c_int64(0)
+        ctx.check(lib.acu_aggregate(h, abi.I64, abi.SUM, C.byref(arr), C.byref(sb), C.byref(sc)))
+        return int(sb.value) if sc.value else 0
+
+    nulls = lambda o: int(o.null_count) if o.has_validity else 0  # noqa: E731
+    return {"filter_rows": int(wl.out_filter.len), "filter_nulls": nulls(wl.out_filter), "filter_values_wsum": wsum(wl.out_filter),
+            "take_nulls": nulls(wl.out_take), "take_values_wsum": wsum(wl.out_take), "add_nulls": nulls(wl.out_add),
+            "add_bits_wsum": wsum(wl.out_add), "sum_valid_rows": int(cnt), "sum_bits": int(bits), "valid_rows": int(cnt)}
 
 
 ALLREDUCE_WALL = [0.0, 0]  # host seconds spent inside the final-reduce call (includes waiting for the slowest rank), calls
@@ -533,14 +590,23 @@ def run_gpu(args):
         return
     peak, peak_src = peaks()
     ab = algorithmic_bytes(n, wl.m)
+    traffic, traffic_src, traffic_sha = profiled_traffic(n)
+    sha = so_sha16()
     roof_ops = {}
-    for op, cls in [("add", "arith"), ("filter", "filter"), ("take", "take"), ("sum", "reduce"), ("filter_plan", "filter_plan")]:
+    # (op, kernel class, ncu kernel-name prefixes whose per-launch DRAM traffic adds up to the op's real traffic)
+    for op, cls, kprefix in [("add", "arith", ["k_arith<double"]), ("filter", "filter", ["k_filter_fused<8", "k_filter_values_async<8", "k_compress_bits"]),
+                             ("take", "take", ["k_take<8"]), ("sum", "reduce", ["k_reduce<long"]), ("filter_plan", "filter_plan", ["k_plan_mask"])]:
         if cls in kstats:
-            t_ms = kstats[cls]["ms_per_step"]  # all kernels of the class (filter = values + validity compaction; plan = mask/scan + indices)
+            t_ms = kstats[cls]["ms_per_step"]  # all kernels of the class
             gbs = ab[op] / (t_ms * 1e-3) / 1e9
-            roof_ops[op] = {"ms": t_ms, "algorithmic_bytes": ab[op], "achieved_gbs": gbs, "frac": gbs / peak,
+            tr = [traffic_of(traffic, p) for p in kprefix]
+            tr = sum(x for x in tr if x is not None) if any(x is not None for x in tr) else None
+            roof_ops[op] = {"bound": "hbm", "ms": t_ms, "algorithmic_bytes": ab[op], "achieved": gbs, "achieved_gbs": gbs, "peak": peak, "unit": "GB/s",
+                            "frac": gbs / peak, "traffic": tr, "frac_real_traffic": (tr / (t_ms * 1e-3) / 1e9 / peak) if tr else None,
                             "mrows_s": (n if op in ("add", "filter", "filter_plan") else wl.m) / (t_ms * 1e-3) / 1e6}
     dom = roof_ops.get("add", {})
+    # rank-local outputs of one more step, folded into checksums the CPU arm reproduces (oracle/refbench.cpp)
+    gpu_chk = gpu_checksums(ctx, abi, wl)
     line = {
         "metric": "Mrows/sec filter+take+add on 1e9-row Int64/Float64; % HBM roofline",
         "value": n * world / (step_ms * 1e-3) / 1e6,
@@ -548,141 +614,181 @@ def run_gpu(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "i64 (filter/take/sum) + f64 (add)", "data": "synthetic",
-        "config": {"workload": "filter(Int64, 10% selected, 5% nulls) -> take(UInt32 monotone indices, M=count) -> add(Float64, 5% nulls x2) -> sum(Int64)",
-                   "rows_per_gpu": n, "selected_rows": wl.m, "parallelism": f"row-range shards x{world}, NCCL all-reduce of the sum only",
+        "config": {"workload": WORKLOAD, "rows_per_gpu": n, "parallelism": f"row-range shards x{world}, NCCL all-reduce of the sum only",
                    "l2": "inputs >> L2 (126 MB): no flush needed", "input_residency": "HBM"},
+        "selected_rows": wl.m,
         "roofline": {"bound": "hbm", "kernel": "k_arith<double> (Float64 add, fused validity AND + popcount)",
                      "achieved": dom.get("achieved_gbs"), "peak": peak, "unit": "GB/s", "frac": dom.get("frac"),
-                     "traffic": profiled_traffic(n), "traffic_source": "profiles/*_traffic.json (ncu --set full, per launch)",
+                     "traffic": dom.get("traffic"), "traffic_source": f"profiles/{traffic_src} (ncu --set full, per launch)" if traffic_src else None,
+                     "traffic_so_sha16": traffic_sha, "so_sha16": sha, "traffic_same_build": (traffic_sha == sha) if traffic_sha else None,
                      "algorithmic_bytes": ab["add"], "peak_source": peak_src, "per_op": roof_ops},
+        "roofline_filter": roof_ops.get("filter"), "roofline_take": roof_ops.get("take"),
         "kernels": kstats,
         "gpu_launches": launches,
         "ms_per_step_rank0": ms.value / args.steps,
         "final_reduce_ms_per_step": (1e3 * ALLREDUCE_WALL[0] / max(ALLREDUCE_WALL[1], 1)) if world > 1 else 0.0,
         "clocks": clocks,
         "e2e": e2e,
-        "check": {"sum_bits": int(total_bits), "valid_rows": int(total_cnt)},
+        "check": {"sum_bits": int(total_bits), "valid_rows": int(total_cnt), "rank0_local": gpu_chk},
     }
     if not args.no_cpu:
-        line["cpu_baseline"] = cpu_baseline(args, from_ctx=(ctx, wl))
+        base, _, cpu_chk = cpu_reference(args, args.cpu_steps, 2)
+        line["cpu_baseline"] = base
+        ok, keys, bad = compare_checks(gpu_chk, cpu_chk) if base["same_config"] else (None, [], {})
+        if not base["same_config"]:  # the CPU arm ran a prefix of the table: run the GPU on the same prefix and compare that
+            sub = Workload(ctx, base["rows"], first_row=0, share=wl)
+            ok, keys, bad = compare_checks(gpu_checksums(ctx, abi, sub), cpu_chk)
+        line["check_vs_oracle"] = bool(ok)
+        line["check"]["vs_oracle"] = {"equal": bool(ok), "rows": base["rows"], "compared": keys, "mismatch": {k: [str(a), str(b)] for k, (a, b) in bad.items()}}
+        if not ok:
+            print(json.dumps(line))
+            raise SystemExit("bench.py: GPU outputs differ from the oracle's: " + json.dumps(line["check"]["vs_oracle"]))
+    if not args.no_configs and world == 1:
+        line["configs"] = config_subresults(ctx, abi, wl, args, peak, traffic)
     print(json.dumps(line))
     group.close()
     ctx.close()
 
 
+def config_subresults(ctx, abi, wl, args, peak, traffic):
+    """Driver-visible sub-results for BASELINE.json configs #2-#5 (kernel-only CUDA-event time vs algorithmic bytes,
+    SURVEY.md §8(d)); the headline step above is configs #2 + #3 combined. Untimed with respect to `value`."""
+    sys.path.insert(0, os.path.join(REPO, "tools"))
+    import opbench
+    lib, h, n = ctx.lib, ctx.h, wl.n
+    b = opbench.Bench(ctx, 3)
+    b.quiet = True
+    A = wl.arr(wl.d_a, wl.d_a_valid, n, wl.nc_a)
+    Bv = wl.arr(wl.d_b, wl.d_b_valid, n, wl.nc_b)
+    o = wl.out_add
+    out = {}
+    try:
+        # config #3: mul, lt, eq Float64 (add is the headline roofline)
+        b.timed("cfg3 mul f64", [abi.K_ARITH], 24.375 * n, n, lambda: ctx.check(lib.acu_arith(h, abi.F64, abi.MUL, C.byref(A), C.byref(Bv), C.byref(o))))
+        for name, op in [("cfg3 lt f64", abi.LT), ("cfg3 eq f64", abi.EQ)]:
+            b.timed(name, [abi.K_CMP], 16.5 * n, n, lambda op=op: ctx.check(lib.acu_cmp(h, abi.F64, op, C.byref(A), C.byref(Bv), C.byref(o))))
+        # config #2, index distribution B: uniform random UInt32 indices, M = 1e8 (or n/10)
+        m = min(100_000_000, max(n // 10, 1))
+        col = wl.arr(wl.d_i64, wl.d_i64_valid, n, wl.nc_i64)
+        drand = b.gen(3, 47, m, 4, param=n)
+        ix = b.arr(drand, None, m, 0)
+        ot = b.out(m * 8, m)
+        b.timed("cfg2 take i64 uniform random", [abi.K_TAKE], 20.25 * m, m,
+                lambda: ctx.check(lib.acu_take_primitive(h, 8, C.byref(col), C.byref(ix), abi.U32, 0, C.byref(ot))), note="index distribution B")
+        ctx.free(drand)
+        # config #4: cast Int64 -> Float64 and Dictionary<Int32,Utf8> -> Utf8, 1e8 rows
+        ns = min(100_000_000, n)
+        Is = b.arr(wl.d_i64, wl.d_i64_valid, ns, -1)
+        b.timed("cfg4 cast i64->f64", [abi.K_CAST], 16.25 * ns, ns, lambda: ctx.check(lib.acu_cast_numeric(h, abi.I64, abi.F64, 1, C.byref(Is), C.byref(ot))))
+        ctx._free_out(ot)
+        D = 4096
+        rng = np.random.default_rng(1)
+        lens = rng.integers(4, 13, D)
+        offs = np.zeros(D + 1, dtype=np.int32)
+        offs[1:] = np.cumsum(lens)
+        data = rng.integers(97, 123, int(offs[-1]) + 16).astype(np.uint8)
+        d_off, d_data = ctx.malloc(offs.nbytes + 64), ctx.malloc(data.nbytes + 64)
+        ctx.h2d(d_off, offs)
+        ctx.h2d(d_data, data)
+        dkeys = b.gen(4, 48, ns, 4, param=D)
+        kv, nkv = b.bits(49, 0.95, ns)
+        keys = b.arr(dkeys, kv, ns, ns - nkv)
+        dict_nulls = b.arr(None, None, D, 0)
+        d_out_off, d_out_data = ctx.malloc((ns + 1) * 4 + 64), ctx.malloc(ns * 13 + 64)
+        on = abi.ArrayOut()
+        on.validity = ctx.malloc(abi.bitmap_bytes(ns) + 64)
+        total = C.c_int64(0)
+        b.timed("cfg4 cast dict<i32,utf8>->utf8", [abi.K_TAKE, abi.K_BYTES], 4 * ns + ns / 8 + 4 * (D + 1) + float(offs[-1]) + 4 * (ns + 1) + 0.95 * ns * 8 + ns / 8, ns,
+                lambda: ctx.check(lib.acu_take_bytes(h, 4, d_off, d_data, C.byref(dict_nulls), C.byref(keys), abi.I32, 0, d_out_off, d_out_data, ns * 13, C.byref(total), C.byref(on))),
+                note="D=4096, lengths 4..12, 5 % null keys")
+        for p in (d_off, d_data, dkeys, kv, d_out_off, d_out_data, on.validity):
+            ctx.free(p)
+        for r in b.rows:
+            key = r["op"].split(" ", 1)
+            out.setdefault(key[0], {})[key[1]] = {"rows": r["rows"], "kernel_ms": r["kernel_ms"], "call_ms": r["call_ms"], "algorithmic_bytes": r["algorithmic_bytes"],
+                                                  "achieved_gbs": r["achieved_gbs"], "frac": r["frac_of_measured_peak"], "mrows_s": r["mrows_s"], "note": r["note"],
+                                                  "traffic": None}
+    except Exception as e:  # sub-results never take the headline down
+        out["error"] = repr(e)[:300]
+    # config #5: RecordBatch pipeline (tools/recordbatch_bench.py body), one GPU's share: 15 x 2^26-row 8-column batches
+    try:
+        if n >= 1_000_000_000:
+            import recordbatch_bench as rbb
+            tb = rbb.Table(ctx, abi, 0, 15, 1 << 26, SELECTIVITY, NULL_DENSITY)
+            for _ in range(2):
+                tb.step()
+            ctx.check(lib.acu_kernel_stats_reset(h))
+            ms = C.c_float(0)
+            reps = 3
+            ctx.check(lib.acu_timer_start_slot(h, 3))
+            for _ in range(reps):
+                sums, cnts, alg = tb.step()
+            ctx.check(lib.acu_timer_stop_slot(h, 3, C.byref(ms)))
+            step_ms = ms.value / reps
+            ksum = 0.0
+            for cls in range(len(abi.KERNEL_CLASS_NAMES)):
+                tot, cnt = C.c_double(0), C.c_int64(0)
+                ctx.check(lib.acu_kernel_stats(h, cls, C.byref(tot), C.byref(cnt)))
+                ksum += tot.value / reps
+            rows = 15 * (1 << 26)
+            out["cfg5"] = {"filter_record_batch -> take_record_batch -> 6 sums": {
+                "rows": rows, "ms_per_step": step_ms, "kernel_ms": ksum, "algorithmic_bytes": alg, "achieved_gbs": alg / (step_ms * 1e-3) / 1e9,
+                "frac": alg / (step_ms * 1e-3) / 1e9 / peak, "mrows_s": rows / (step_ms * 1e-3) / 1e6, "traffic": None,
+                "note": "one GPU's share of BASELINE configs[4]: 15 batches of 2^26 rows x {3 Int64, 3 Float64, 2 Utf8}, every batch resident in HBM; "
+                        "frac is whole-pipeline algorithmic bytes / step time (host launch gaps included)"}}
+    except Exception as e:
+        out["cfg5_error"] = repr(e)[:300]
+    return out
+
+
 # ------------------------------------------------------------------------------------------
 # CPU reference arm (oracle port of the arrow-rs algorithms; test infrastructure used as the
-# timed CPU baseline only)
+# timed CPU baseline only). The harness is native (oracle/refbench.cpp): a persistent pool of
+# pinned threads, every thread generating / first-touching its own row range, the timer inside C
+# around the barriers. No Python, thread creation or allocation in the timed region.
 # ------------------------------------------------------------------------------------------
-def cpu_baseline(args, from_ctx=None, steps=1):
-    """Times the oracle on a bounded sample: `cpu_rows` rows, row-partitioned over all host cores."""
-    import acu
-    from acu import _abi as abi
-    from acu import HostArray, BOOL
-    from oracle import Oracle
-    orc = Oracle()
-    n = min(args.cpu_rows, args.rows)
-    cores = os.cpu_count() or 1
-    threads = max(1, min(cores, args.cpu_threads or cores))
-    if from_ctx is not None:  # identical data: first n rows of the device table
-        ctx, wl = from_ctx
-        bb = abi.bitmap_bytes(n)
-        data = {"i64": ctx.d2h(wl.d_i64, n * 8, np.int64), "i64_valid": ctx.d2h(wl.d_i64_valid, bb), "pred": ctx.d2h(wl.d_pred, bb),
-                "a": ctx.d2h(wl.d_a, n * 8, np.float64), "b": ctx.d2h(wl.d_b, n * 8, np.float64),
-                "a_valid": ctx.d2h(wl.d_a_valid, bb), "b_valid": ctx.d2h(wl.d_b_valid, bb)}
-    else:
+SEEDS7 = (SEED_VALUES, SEED_VALUES, SEED_B, SEED_VALID_A, SEED_VALID_A + 100, SEED_VALID_B, SEED_PRED)
+REF_BYTES_PER_ROW = 36.0  # inputs 24 + bitmaps 0.5 + indices 0.4 + outputs 9.6 + slack
+
+
+def host_available_bytes():
+    try:
+        import psutil
+        return int(psutil.virtual_memory().available)
+    except Exception:
+        return 64 << 30
+
+
+def reference_rows(args):
+    """Rows the CPU arm runs per step: the full per-GPU table (same config) when the host has the RAM for it
+    (36 B/row), else the largest 64-row multiple that fits in 60 % of the available RAM (stated in the line)."""
+    if args.cpu_rows:
+        return min(args.cpu_rows, args.rows), "--cpu-rows"
+    fit = int(host_available_bytes() * 0.6 / REF_BYTES_PER_ROW) // 64 * 64
+    if fit >= args.rows:
+        return args.rows, None
+    return max(fit, 64), f"host RAM: {host_available_bytes() >> 30} GiB available, {int(args.rows * REF_BYTES_PER_ROW) >> 30} GiB needed for the full table"
+
+
+def pyarrow_secondary(orc, n):
+    """Labelled secondary figure: the same step through pyarrow (Arrow C++ — a different implementation of the same
+    format, not arrow-rs and not the oracle), one call per op over an n-row sample."""
+    try:
+        import pyarrow as pa
+        import pyarrow.compute as pc
+        from acu import unpack_bits
         data = {"i64": orc.generate_values(0, SEED_VALUES, 0, 0, n, np.int64), "i64_valid": orc.generate_bits(SEED_VALID_A, 0, 1 - NULL_DENSITY, n),
                 "pred": orc.generate_bits(SEED_PRED, 0, SELECTIVITY, n), "a": orc.generate_values(2, SEED_VALUES, 0, 0, n, np.float64),
                 "b": orc.generate_values(2, SEED_B, 0, 0, n, np.float64), "a_valid": orc.generate_bits(SEED_VALID_A + 100, 0, 1 - NULL_DENSITY, n),
                 "b_valid": orc.generate_bits(SEED_VALID_B, 0, 1 - NULL_DENSITY, n)}
-    def plan_ranges(parts):
-        """Contiguous row ranges aligned to 64 rows (bitmaps split on u64 words) + per-range take indices (an INPUT
-        of take, not timed) + cached null counts (a NullBuffer carries them, arrow-buffer/src/buffer/null.rs:34-37)."""
-        per = ((n + parts - 1) // parts + 63) // 64 * 64
-        ranges = [(lo, min(lo + per, n)) for lo in range(0, n, per)]
-        idxs, ncs = [], []
-        for lo, hi in ranges:
-            sel = np.nonzero(acu.unpack_bits(data["pred"][lo // 8:], 0, hi - lo))[0].astype(np.uint32)
-            idxs.append(HostArray.from_numpy(abi.U32, sel))
-            ncs.append(tuple(int(hi - lo - acu.unpack_bits(data[k][lo // 8:], 0, hi - lo).sum()) for k in ("i64_valid", "a_valid", "b_valid")))
-        return ranges, idxs, ncs
-
-    def prepare(parts_plan):
-        """Per range: input descriptors + caller-owned, pre-faulted output buffers (the CPU arm gets what the GPU arm
-        gets: outputs allocated once outside the timed region; a warm allocator would hand arrow-rs recycled pages)."""
-        ranges, idxs, ncs = parts_plan
-        jobs = []
-        for k, (lo, hi) in enumerate(ranges):
-            m = hi - lo
-            col = HostArray(abi.I64, data["i64"][lo:hi], m, data["i64_valid"][lo // 8:], 0, 0, ncs[k][0])
-            pred = HostArray(BOOL, data["pred"][lo // 8:], m, None, 0, 0, 0)
-            a = HostArray(abi.F64, data["a"][lo:hi], m, data["a_valid"][lo // 8:], 0, 0, ncs[k][1])
-            b = HostArray(abi.F64, data["b"][lo:hi], m, data["b_valid"][lo // 8:], 0, 0, ncs[k][2])
-            sel = idxs[k].length
-            bufs = {"f_v": np.ones(sel * 8 + 64, np.uint8), "f_n": np.ones(abi.bitmap_bytes(sel) + 64, np.uint8), "t_v": np.ones(sel * 8 + 64, np.uint8),
-                    "t_n": np.ones(abi.bitmap_bytes(sel) + 64, np.uint8), "s_v": np.ones(m * 8 + 64, np.uint8), "s_n": np.ones(abi.bitmap_bytes(m) + 64, np.uint8)}
-            outs = {}
-            for name in ("f", "t", "s"):
-                o = abi.ArrayOut()
-                o.values, o.validity = bufs[name + "_v"].ctypes.data, bufs[name + "_n"].ctypes.data
-                outs[name] = o
-            jobs.append({"keep": (col, pred, a, b, idxs[k], bufs), "col": acu.host_descriptor(col), "pred": acu.host_descriptor(pred),
-                         "a": acu.host_descriptor(a), "b": acu.host_descriptor(b), "idx": acu.host_descriptor(idxs[k]), "outs": outs})
-        return jobs
-
-    def run(jobs, nthreads):
-        lib = orc.lib
-
-        def work(j):
-            cnt, strat = C.c_int64(0), C.c_int32(0)
-            o = j["outs"]
-            orc.check(lib.orc_filter_primitive(C.byref(j["pred"]), 8, C.byref(j["col"]), C.byref(o["f"]), C.byref(cnt), C.byref(strat)))
-            orc.check(lib.orc_take_primitive(8, C.byref(j["col"]), C.byref(j["idx"]), abi.U32, 0, C.byref(o["t"])))
-            orc.check(lib.orc_arith(abi.F64, abi.ADD, C.byref(j["a"]), C.byref(j["b"]), C.byref(o["s"])))
-            t = abi.Array()
-            t.values, t.validity = o["t"].values, o["t"].validity if o["t"].has_validity else None
-            t.len, t.null_count = o["t"].len, o["t"].null_count if o["t"].has_validity else 0
-            bits, vc = C.c_uint64(0), C.c_int64(0)
-            orc.check(lib.orc_aggregate(abi.I64, abi.SUM, C.byref(t), 16, C.byref(bits), C.byref(vc)))
-
-        t0 = time.perf_counter()
-        if nthreads == 1:
-            for j in jobs:
-                work(j)
-        else:
-            ts = [threading.Thread(target=work, args=(j,)) for j in jobs]  # ctypes releases the GIL
-            for t in ts:
-                t.start()
-            for t in ts:
-                t.join()
-        return time.perf_counter() - t0
-
-    plan_mt = plan_ranges(threads)
-    plan_1t = plan_ranges(1) if threads > 1 else plan_mt  # ONE call over the whole array, as arrow-rs would run it
-    jobs_mt = prepare(plan_mt)
-    run(jobs_mt, threads)  # warm-up
-    best_mt = min(run(jobs_mt, threads) for _ in range(max(1, steps)))
-    if threads > 1:
-        del jobs_mt
-        jobs_1t = prepare(plan_1t)
-        run(jobs_1t, 1)
-        best_1t = min(run(jobs_1t, 1) for _ in range(2))
-    else:
-        best_1t = best_mt
-    # secondary, labelled figure: the same step through pyarrow (Arrow C++ 24, a different implementation of the same
-    # format — not arrow-rs and not the oracle), one call per op over the whole sample like arrow-rs would be driven
-    secondary = None
-    try:
-        import pyarrow as pa
-        import pyarrow.compute as pc
 
         def pa_prim(t, values, valid):
-            return pa.Array.from_buffers(t, n, [pa.py_buffer(valid) if valid is not None else None, pa.py_buffer(values)], null_count=-1 if valid is not None else 0)
+            return pa.Array.from_buffers(t, n, [pa.py_buffer(valid), pa.py_buffer(values)], null_count=-1)
 
         p_col = pa_prim(pa.int64(), data["i64"], data["i64_valid"])
         p_a, p_b = pa_prim(pa.float64(), data["a"], data["a_valid"]), pa_prim(pa.float64(), data["b"], data["b_valid"])
         p_pred = pa.Array.from_buffers(pa.bool_(), n, [None, pa.py_buffer(data["pred"])], null_count=0)
-        p_idx = pa.array(plan_1t[1][0].value_array(), type=pa.uint32())
+        p_idx = pa.array(np.nonzero(unpack_bits(data["pred"], 0, n))[0].astype(np.uint32), type=pa.uint32())
 
         def pa_step():
             t0 = time.perf_counter()
@@ -693,14 +799,52 @@ def cpu_baseline(args, from_ctx=None, steps=1):
             return time.perf_counter() - t0
 
         pa_step()
-        secondary = {"impl": f"pyarrow {pa.__version__} (Arrow C++; labelled secondary baseline, not arrow-rs)", "value": n / min(pa_step() for _ in range(2)) / 1e6,
-                     "unit": "Mrows/s", "threads": "one call per op over the whole sample (pyarrow's own kernel threading)"}
+        return {"impl": f"pyarrow {pa.__version__} (Arrow C++; labelled secondary baseline, not arrow-rs)", "value": n / min(pa_step() for _ in range(2)) / 1e6,
+                "unit": "Mrows/s", "rows": n, "threads": "one call per op over the whole sample (pyarrow's own kernel threading)"}
     except Exception as e:  # pyarrow is optional
-        secondary = {"impl": "pyarrow", "skipped": repr(e)[:120]}
-    return {"value": n / best_mt / 1e6, "unit": "Mrows/s", "cores": threads, "kind": "port", "secondary": secondary,
-            "sample": f"first {n} rows of the same synthetic table (1/{max(1, args.rows // n)} of the workload), same step "
-                      f"(filter+take+add+sum), row-partitioned over {threads} threads, outputs pre-allocated; oracle/ C++ restatement of arrow-rs (no Rust toolchain here)",
-            "value_1_thread": n / best_1t / 1e6, "host_cores": cores, "seconds": best_mt}
+        return {"impl": "pyarrow", "skipped": repr(e)[:120]}
+
+
+def cpu_reference(args, steps, warmup, secondary=True, one_thread=True):
+    """Run the native reference harness: `warmup` untimed + `steps` timed passes of the hot-path step over
+    reference_rows(args) rows. Returns (cpu_baseline dict, per-step seconds, checksums of the outputs)."""
+    from oracle import Oracle, RefBench
+    orc = Oracle()
+    n, why = reference_rows(args)
+    with RefBench(n, SEEDS7, SELECTIVITY, NULL_DENSITY, threads=args.cpu_threads or 0, oracle=orc) as rb:
+        for _ in range(max(warmup, 1)):
+            rb.step()
+        runs = [rb.step() for _ in range(max(steps, 1))]
+        secs = [r[0] for r in runs]
+        chk = rb.check()
+        chk["sum_bits"], chk["valid_rows"] = int(runs[-1][1]), int(runs[-1][2])
+        threads, gen_s = rb.threads, rb.generate_seconds
+    med, best = float(np.median(secs)), float(min(secs))
+    base = {"value": n / med / 1e6, "unit": "Mrows/s", "cores": threads, "kind": "port",
+            "sample": (f"{n} rows = " + ("the full per-GPU table (same config)" if n == args.rows else f"first {n} rows of the table [{why}]") +
+                       f"; same step (filter+take+add+sum) row-partitioned over {threads} pinned native threads (oracle/refbench.cpp: each thread first-touches "
+                       "its own range, outputs pre-allocated, timer inside C); oracle/ C++ restatement of arrow-rs (no Rust toolchain here)"),
+            "rows": n, "same_config": n == args.rows, "host_cores": os.cpu_count() or 1, "seconds_median": med, "seconds_min": best,
+            "value_best": n / best / 1e6, "spread": (max(secs) - best) / med if med else None, "timed_steps": len(secs), "generate_seconds": gen_s}
+    if one_thread and threads > 1:  # arrow-rs kernels themselves are single-threaded: ONE call per op over a 1e8-row sample
+        n1 = min(n, 100_000_000)
+        with RefBench(n1, SEEDS7, SELECTIVITY, NULL_DENSITY, threads=1, oracle=orc) as rb1:
+            rb1.step()
+            base["value_1_thread"] = n1 / min(rb1.step()[0] for _ in range(2)) / 1e6
+            base["rows_1_thread"] = n1
+    if secondary:
+        base["secondary"] = pyarrow_secondary(orc, min(n, 100_000_000))
+    return base, secs, chk
+
+
+def compare_checks(gpu_chk, cpu_chk):
+    """True when every checksum both sides report is identical (bit-exact integer quantities)."""
+    keys = [k for k in cpu_chk if k in gpu_chk]
+    bad = {k: (gpu_chk[k], cpu_chk[k]) for k in keys if int(gpu_chk[k]) != int(cpu_chk[k])}
+    return (len(keys) > 0 and not bad), keys, bad
+
+
+WORKLOAD = "filter(Int64, 10% selected, 5% nulls) -> take(UInt32 monotone indices, M=count) -> add(Float64, 5% nulls x2) -> sum(Int64)"
 
 
 def run_reference(args):
@@ -708,27 +852,22 @@ def run_reference(args):
     if rank != 0:
         return  # other ranks exit 0 without work
     # the reference arm never touches the GPU
-    times = []
-    base = None
-    for i in range(args.warmup + args.steps):
-        base = cpu_baseline(args, from_ctx=None, steps=1)
-        if i >= args.warmup:
-            times.append(base["seconds"])
-        if sum(times) > 150:  # keep the whole run within a few minutes
-            break
-    n = min(args.cpu_rows, args.rows)
-    sec = float(np.mean(times)) if times else base["seconds"]
+    base, secs, chk = cpu_reference(args, args.steps, args.warmup, secondary=False, one_thread=True)
+    n = base["rows"]
+    sec = base["seconds_median"]
     value = n / sec / 1e6
-    base["value"] = value
     line = {
         "impl": "reference",
         "metric": "Mrows/sec filter+take+add on 1e9-row Int64/Float64; % HBM roofline",
-        "value": value, "unit": "Mrows/s", "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup,
+        "value": value, "unit": "Mrows/s", "n_gpus": args.gpus, "steps": len(secs), "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "i64 (filter/take/sum) + f64 (add)", "data": "synthetic",
-        "config": {"workload": "filter(Int64, 10% selected, 5% nulls) -> take(UInt32 monotone indices, M=count) -> add(Float64, 5% nulls x2) -> sum(Int64)",
-                   "rows_per_step": n, "note": "CPU restatement of arrow-rs (oracle/), bounded sample of the 1e9-row workload"},
+        "config": {"workload": WORKLOAD, "rows_per_gpu": args.rows, "parallelism": f"row-range shards x{args.gpus}, NCCL all-reduce of the sum only",
+                   "l2": "inputs >> L2 (126 MB): no flush needed", "input_residency": "HBM"},
+        "rows_per_step": n, "same_config": base["same_config"],
+        "timing": {"seconds": secs, "median": sec, "min": base["seconds_min"], "spread": base["spread"]},
         "cpu_baseline": base,
+        "check": chk,
         "e2e": {"value": value, "unit": "Mrows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -747,7 +886,9 @@ def main():
     ap.add_argument("--e2e-batch-rows", type=int, default=1 << 26)
     ap.add_argument("--e2e-workers", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-rows", type=int, default=100_000_000)
+    ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU arm's step (0 = the full table when host RAM allows)")
+    ap.add_argument("--cpu-steps", type=int, default=5, help="timed CPU steps of the cpu_baseline leg of the GPU arm")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config sub-results (configs #2-#5)")
     ap.add_argument("--cpu-threads", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -48,7 +48,14 @@ class Oracle:
             "orc_sum_checked": [i32, P(abi.Array), P(u64), P(i64)],
             "orc_generate_values": [i32, u64, i64, u64, vp, i64],
             "orc_generate_bits": [u64, i64, C.c_double, vp, i64],
+            "orc_bench_create": [i64, i64, i32, P(u64), C.c_double, C.c_double, i32, P(vp), P(C.c_double)],
+            "orc_bench_step": [vp, P(C.c_double), P(u64), P(i64)],
+            "orc_bench_check": [vp, P(u64)],
         }
+        lib.orc_bench_threads.restype = i32
+        lib.orc_bench_threads.argtypes = [vp]
+        lib.orc_bench_destroy.restype = None
+        lib.orc_bench_destroy.argtypes = [vp]
         for name, args in sigs.items():
             fn = getattr(lib, name)
             fn.restype = i32
@@ -243,3 +250,44 @@ class Oracle:
         out = np.zeros(bitmap_bytes(n) + 8, dtype=np.uint8)
         self.check(self.lib.orc_generate_bits(seed, first_row, p, out.ctypes.data, n))
         return out
+
+
+class RefBench:
+    """The native multi-threaded harness of oracle/refbench.cpp: the hot-path step (filter -> take -> add -> sum) of
+    the CPU restatement over a row-partitioned synthetic table, persistent pinned threads, timer inside C.
+    seeds = (values i64, a, b, i64 validity, a validity, b validity, predicate)."""
+
+    CHECK_KEYS = ("filter_rows", "filter_nulls", "filter_values_wsum", "take_nulls", "take_values_wsum", "add_nulls",
+                  "add_bits_wsum", "sum_valid_rows")
+
+    def __init__(self, rows, seeds, selectivity, null_density, threads=0, first_row=0, pin=True, oracle=None):
+        self.orc = oracle or Oracle()
+        self.h = vp()
+        gen = C.c_double(0)
+        arr = (u64 * 7)(*seeds)
+        self.orc.check(self.orc.lib.orc_bench_create(rows, first_row, threads, arr, selectivity, null_density, int(pin),
+                                                     C.byref(self.h), C.byref(gen)))
+        self.rows, self.generate_seconds = rows, gen.value
+        self.threads = self.orc.lib.orc_bench_threads(self.h)
+
+    def step(self):
+        """-> (seconds, sum_bits, valid_rows)"""
+        s, bits, valid = C.c_double(0), u64(0), i64(0)
+        self.orc.check(self.orc.lib.orc_bench_step(self.h, C.byref(s), C.byref(bits), C.byref(valid)))
+        return s.value, bits.value, valid.value
+
+    def check(self):
+        out = (u64 * 8)()
+        self.orc.check(self.orc.lib.orc_bench_check(self.h, out))
+        return dict(zip(self.CHECK_KEYS, [int(x) for x in out]))
+
+    def close(self):
+        if self.h:
+            self.orc.lib.orc_bench_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()

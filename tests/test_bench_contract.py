@@ -36,3 +36,41 @@ def test_reference_arm_other_ranks_exit_quietly():
     """Under torchrun (N > 1) rank 0 alone runs and prints the reference arm."""
     out = run_reference({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"}, ("--gpus", "2"))
     assert out.strip() == ""
+
+
+def test_refbench_checksums_match_single_call_oracle():
+    """oracle/refbench.cpp (the native multi-threaded harness behind cpu_baseline / --impl reference) must compute exactly
+    what one oracle call per op over the whole table computes: its folded checksums are partition-independent."""
+    sys.path.insert(0, os.path.join(REPO, "arrow-rs_b200"))
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import numpy as np
+    import acu
+    from acu import _abi as abi
+    from acu import HostArray, BOOL
+    from oracle import Oracle, RefBench
+    n, seeds = 200_003, (42, 42, 43, 44, 144, 45, 46)
+    orc = Oracle()
+    chks = []
+    for threads in (1, 3, 8):
+        with RefBench(n, seeds, 0.1, 0.05, threads=threads, oracle=orc) as rb:
+            _, bits, valid = rb.step()
+            c = rb.check()
+            c["sum_bits"], c["valid_rows"] = bits, valid
+            chks.append(c)
+    assert chks[0] == chks[1] == chks[2]
+    # the same quantities from single calls through the Python oracle wrapper
+    col = HostArray(abi.I64, orc.generate_values(0, 42, 0, 0, n, np.int64), n, orc.generate_bits(44, 0, 0.95, n), 0, 0, -1)
+    pred = HostArray(BOOL, orc.generate_bits(46, 0, 0.1, n), n, None, 0, 0, 0)
+    a = HostArray(abi.F64, orc.generate_values(2, 42, 0, 0, n, np.float64), n, orc.generate_bits(144, 0, 0.95, n), 0, 0, -1)
+    b = HostArray(abi.F64, orc.generate_values(2, 43, 0, 0, n, np.float64), n, orc.generate_bits(45, 0, 0.95, n), 0, 0, -1)
+    f = orc.filter(col, pred)
+    idx = HostArray.from_numpy(abi.U32, np.nonzero(pred.value_array())[0].astype(np.uint32))
+    t = orc.take(col, idx)
+    s = orc.add(a, b)
+    wsum = lambda x: int(np.asarray(x).view(np.uint64).sum(dtype=np.uint64))  # noqa: E731
+    c = chks[0]
+    assert c["filter_rows"] == f.length and c["filter_nulls"] == f.null_count and c["filter_values_wsum"] == wsum(f.values[: f.length])
+    assert c["take_nulls"] == t.null_count and c["take_values_wsum"] == wsum(t.values[: t.length])
+    assert c["add_nulls"] == s.null_count and c["add_bits_wsum"] == wsum(s.values[: s.length])
+    total = orc.sum(t)
+    assert c["sum_bits"] == (int(total) & 0xFFFFFFFFFFFFFFFF) and c["valid_rows"] == t.length - t.null_count

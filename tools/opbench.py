@@ -31,6 +31,7 @@ class Bench:
         self.ctx, self.lib, self.h, self.reps, self.rows = ctx, ctx.lib, ctx.h, reps, []
         self.peak = peak()
         self.only = None
+        self.quiet = False
 
     def arr(self, values, validity, n, nc, voff=0, scalar=0):
         a = abi.Array()
@@ -76,7 +77,8 @@ class Bench:
                "algorithmic_bytes": alg_bytes, "achieved_gbs": round(gbs, 1), "frac_of_measured_peak": round(gbs / self.peak, 4),
                "mrows_s": round(rows / (k_ms * 1e-3) / 1e6, 1), "note": note}
         self.rows.append(row)
-        print(json.dumps(row), flush=True)
+        if not self.quiet:
+            print(json.dumps(row), flush=True)
 
 
 def main():
