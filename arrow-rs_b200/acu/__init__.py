@@ -621,6 +621,74 @@ class Context:
             da.free()
             db.free()
 
+    # -- fused compare -> filter (cmp.rs:220-382 feeding filter.rs:254-273) -------------------
+    def filter_cmp(self, values, op, a, b):
+        """filter(values, &cmp::op(a, b)?) with the predicate never materialised: the comparison writes the filter plan."""
+        assert a.dtype == b.dtype
+        dv, da, db = self.upload(values), self.upload(a), self.upload(b)
+        plan = C.c_void_p()
+        out = None
+        try:
+            ad, bd = da.descriptor(), db.descriptor()
+            self.check(self.lib.acu_filter_plan_create_cmp(self.h, a.dtype, op, C.byref(ad), C.byref(bd), C.byref(plan)))
+            count = self.lib.acu_filter_plan_count(plan)
+            out = self.alloc_out(count * values.width(), count)
+            vd = dv.descriptor()
+            if values.dtype == BOOL:
+                self.check(self.lib.acu_filter_boolean(self.h, plan, C.byref(vd), C.byref(out)))
+            else:
+                self.check(self.lib.acu_filter_primitive(self.h, plan, values.width(), C.byref(vd), C.byref(out)))
+            strategy = self.lib.acu_filter_plan_strategy(plan)
+            res, out = self.download_out(out, values.dtype), None
+            return res, (count, strategy)
+        finally:
+            if out is not None:
+                self._free_out(out)
+            if plan:
+                self.lib.acu_filter_plan_destroy(self.h, plan)
+            dv.free()
+            da.free()
+            db.free()
+
+    # -- nullif / zip (arrow-select/src/nullif.rs, zip.rs) ------------------------------------
+    def nullif(self, left, right):
+        """arrow::compute::nullif(left, right): same values, validity &= !(right is Some(true))."""
+        dl, dr = self.upload(left), self.upload(right)
+        out = self.alloc_out(0, max(left.length, 1))
+        try:
+            ld, rd = dl.descriptor(), dr.descriptor()
+            self.check(self.lib.acu_nullif(self.h, C.byref(ld), C.byref(rd), C.byref(out)))
+            n = out.len
+            validity = self.d2h(out.validity, bitmap_bytes(n)) if out.has_validity else None
+            if n == 0:  # the array is returned as it is
+                return left
+            # the result shares left's value buffer (logical slice starting at row 0)
+            vals = left.values if left.dtype == BOOL else left.values[:n]
+            return HostArray(left.dtype, vals, n, validity, 0, left.values_offset if left.dtype == BOOL else 0,
+                             out.null_count if out.has_validity else 0)
+        finally:
+            self._free_out(out)
+            dl.free()
+            dr.free()
+
+    def zip(self, mask, truthy, falsy):
+        """arrow::compute::zip(mask, truthy, falsy) for primitive arrays / scalars."""
+        assert truthy.dtype == falsy.dtype and truthy.dtype != BOOL
+        dm, dt, df = self.upload(mask), self.upload(truthy), self.upload(falsy)
+        n = mask.length
+        out = self.alloc_out(n * truthy.width(), max(n, 1))
+        try:
+            md, td, fd = dm.descriptor(), dt.descriptor(), df.descriptor()
+            self.check(self.lib.acu_zip(self.h, truthy.width(), C.byref(md), C.byref(td), C.byref(fd), C.byref(out)))
+            res, out = self.download_out(out, truthy.dtype), None
+            return res
+        finally:
+            if out is not None:
+                self._free_out(out)
+            dm.free()
+            dt.free()
+            df.free()
+
     # -- boolean (arrow-arith/src/boolean.rs) -------------------------------------------------
     def boolean(self, op, a, b=None):
         da = self.upload(a)

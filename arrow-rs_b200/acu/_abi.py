@@ -175,6 +175,9 @@ PROTOTYPES = {
     "acu_generate_bits": (i32, [vp, u64, i64, f64, vp, i64]),
     "acu_bitmap_count": (i32, [vp, vp, i64, vp, i64, i64, P(i64)]),
     "acu_filter_plan_create": (i32, [vp, P(Array), P(vp)]),
+    "acu_filter_plan_create_cmp": (i32, [vp, i32, i32, P(Array), P(Array), P(vp)]),
+    "acu_nullif": (i32, [vp, P(Array), P(Array), P(ArrayOut)]),
+    "acu_zip": (i32, [vp, i32, P(Array), P(Array), P(Array), P(ArrayOut)]),
     "acu_filter_plan_destroy": (None, [vp, vp]),
     "acu_filter_plan_indices": (i32, [vp, vp, i32, vp]),
     "acu_filter_plan_count": (i64, [vp]),

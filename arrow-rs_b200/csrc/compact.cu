@@ -22,6 +22,7 @@
 //             window assembles output words (atomicOr only on the two boundary words), and
 //             the popcount gives filter_nulls' null count. Also used for boolean VALUES
 //             (filter_bits / filter_boolean).
+#include <cstdlib>
 #include <vector>
 
 #include "bitmap.cuh"
@@ -161,6 +162,13 @@ struct FilterArgs {
   const uint64_t *tile_off;
   int64_t n_tiles;
   int aligned16;
+  // fused validity compaction (k_filter_fused only): source validity bitmap (NULL = none), its bit offset, the
+  // predicate length, the compacted output bitmap (zeroed by the host wrapper) and the result block for the popcount
+  const uint8_t *vsrc;
+  int64_t voff;
+  int64_t vlen;
+  uint32_t *vout;
+  unsigned long long *res;
 };
 
 // Up to BATCH_COLS columns per launch: blockIdx.y selects the column (all columns of a record batch share the plan,
@@ -396,6 +404,188 @@ __global__ void __launch_bounds__(256, 6) k_filter_values_async(const FilterBatc
   }
 }
 
+// ---- one-pass filter: values + validity in the same kernel ---------------------------------
+// k_filter_fused<W>: the value compaction of k_filter_values_async with (a) a lane owning a whole 32-byte DRAM sector
+// per round (two predicated 16-byte cp.async: 4 Int64 rows per lane instead of 2, which halves the per-row cost of the
+// mask / rank bookkeeping — the round-1 kernel was ISSUE-bound: 75 % issue-active, 0.77 warp instructions per row) and
+// (b) FilterPredicate::filter_nulls (filter.rs:512-533) fused in: the warp that owns a 1024-row tile already holds the
+// tile's 16 mask words and their popcount prefix, so lanes 0..15 PEXT the source validity words with them, the bits are
+// assembled in a warp-private shared-memory window and leave as whole 32-bit words (atomicOr only on the two words a
+// tile shares with its neighbours; the output bitmap is zeroed by a memset node before the launch), and the popcount
+// (= the filtered null count) goes to the column's result block. The mask is read ONCE for values and validity, and
+// k_zero_outputs + k_compress_bits are gone from the primitive path.
+template <int W> struct FusedCfg {
+  static constexpr int RPU = 32 / W;                       // rows per 32-byte unit (one lane, one round)
+  static constexpr int TILE_BYTES = TILE_ROWS * W;
+  static constexpr int PASS_BYTES = TILE_BYTES < 4096 ? TILE_BYTES : 4096;  // per-warp landing buffer
+  static constexpr int ROUNDS = PASS_BYTES / 1024;         // 32 lanes x 32 B per round
+  static constexpr int PASSES = TILE_BYTES / PASS_BYTES;
+  static constexpr int PASS_ROWS = PASS_BYTES / W;
+  static constexpr uint32_t UNIT_MASK = RPU == 32 ? 0xffffffffu : ((1u << RPU) - 1u);
+  static constexpr int HALF = RPU >= 2 ? RPU / 2 : 1;      // rows per 16-byte half (W = 32: the row spans both halves)
+  static constexpr uint32_t HALF_MASK = (1u << HALF) - 1u;
+};
+
+__device__ __forceinline__ uint64_t pext64_sparse(uint64_t v, uint64_t m, uint32_t cnt) {
+  // PEXT(v, m) looping over the RARER kind of selected bit (validity bitmaps are mostly ones).
+  const uint64_t ones = m & v, zeros = m & ~v;
+  const bool clear_mode = __popcll(zeros) <= __popcll(ones);
+  uint64_t it = clear_mode ? zeros : ones, acc = 0;
+  while (it) {
+    const int b = __ffsll((long long)it) - 1;
+    it &= it - 1;
+    acc |= 1ull << __popcll(m & ((1ull << b) - 1ull));
+  }
+  const uint64_t full = cnt == 64 ? ~0ull : ((1ull << cnt) - 1ull);
+  return clear_mode ? (full & ~acc) : acc;
+}
+
+template <int W>
+__global__ void __launch_bounds__(256, 6) k_filter_fused(const FilterBatch batch) {
+  const FilterArgs &a = batch.col[blockIdx.y];
+  using C = FusedCfg<W>;
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  __shared__ uint64_t s_m[8][TILE_WORDS];
+  __shared__ uint32_t s_p[8][TILE_WORDS];
+  __shared__ uint32_t s_win[8][36];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint4 *buf = reinterpret_cast<uint4 *>(s_raw + (size_t)wid * C::PASS_BYTES);
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const uint8_t *__restrict__ vsrc = a.vsrc;
+  unsigned valid_cnt = 0;
+
+  int64_t t = warp;
+  uint64_t m_next = 0, off_next = 0, end_next = 0;
+  if (t < a.n_tiles) {
+    if (lane < TILE_WORDS) m_next = __ldg(a.mask + t * TILE_WORDS + lane);
+    off_next = __ldg(a.tile_off + t);
+    end_next = __ldg(a.tile_off + t + 1);
+  }
+  for (; t < a.n_tiles; t += nwarps) {
+    const uint64_t m = m_next, out0 = off_next, cnt = end_next - off_next;
+    const int64_t tn = t + nwarps;
+    if (tn < a.n_tiles) {
+      m_next = (lane < TILE_WORDS) ? __ldg(a.mask + tn * TILE_WORDS + lane) : 0ull;
+      off_next = __ldg(a.tile_off + tn);
+      end_next = __ldg(a.tile_off + tn + 1);
+    }
+    if (cnt == 0) continue;  // warp-uniform
+    const uint32_t c = __popcll(m);
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < TILE_WORDS; o <<= 1) {
+      uint32_t y = __shfl_up_sync(ACU_FULL_MASK, incl, o);
+      if (lane >= o) incl += y;
+    }
+    if (lane < TILE_WORDS) { s_m[wid][lane] = m; s_p[wid][lane] = incl - c; }
+    // the validity words of the tile go in flight before the value loads (consumed after them)
+    uint64_t v = 0;
+    if (vsrc && c) v = ld_bits64(vsrc, a.voff + t * TILE_ROWS + (int64_t)lane * 64, a.voff + a.vlen);
+    __syncwarp();
+    const uint8_t *src = a.values + (size_t)t * TILE_ROWS * W;
+    uint8_t *dst = a.out + (size_t)out0 * W;
+#pragma unroll 1
+    for (int pass = 0; pass < C::PASSES; ++pass) {
+      const int row_base = pass * C::PASS_ROWS;
+      const uint8_t *psrc = src + (size_t)pass * C::PASS_BYTES + (size_t)lane * 32;
+      // ---- issue: every needed 16-byte half of the pass goes in flight (landing layout [round][half][lane]: conflict-free LDS.128) ----
+#pragma unroll
+      for (int j = 0; j < C::ROUNDS; ++j) {
+        const int r = row_base + (j * 32 + lane) * C::RPU;
+        const uint32_t bits = (uint32_t)(s_m[wid][r >> 6] >> (r & 63)) & C::UNIT_MASK;
+        if (W == 32 ? bits : (bits & C::HALF_MASK)) cp_async16(buf + (j * 2 + 0) * 32 + lane, psrc + (size_t)j * 1024);
+        if (W == 32 ? bits : (bits >> C::HALF)) cp_async16(buf + (j * 2 + 1) * 32 + lane, psrc + (size_t)j * 1024 + 16);
+      }
+      cp_async_wait_all();
+      __syncwarp();
+      // ---- consume: rank and store the selected elements ----
+#pragma unroll
+      for (int j = 0; j < C::ROUNDS; ++j) {
+        const int r = row_base + (j * 32 + lane) * C::RPU;
+        const uint64_t word = s_m[wid][r >> 6];
+        uint32_t bits = (uint32_t)(word >> (r & 63)) & C::UNIT_MASK;
+        if (!bits) continue;
+        const uint32_t rank = s_p[wid][r >> 6] + __popcll(word & ((1ull << (r & 63)) - 1ull));
+        if constexpr (W == 8) {
+          const uint4 v0 = buf[(j * 2 + 0) * 32 + lane], v1 = buf[(j * 2 + 1) * 32 + lane];
+          uint64_t *o = reinterpret_cast<uint64_t *>(dst) + rank;
+          if (bits & 1u) *o++ = (uint64_t)v0.x | ((uint64_t)v0.y << 32);
+          if (bits & 2u) *o++ = (uint64_t)v0.z | ((uint64_t)v0.w << 32);
+          if (bits & 4u) *o++ = (uint64_t)v1.x | ((uint64_t)v1.y << 32);
+          if (bits & 8u) *o = (uint64_t)v1.z | ((uint64_t)v1.w << 32);
+        } else if constexpr (W == 4) {
+          const uint4 v0 = buf[(j * 2 + 0) * 32 + lane], v1 = buf[(j * 2 + 1) * 32 + lane];
+          uint32_t *o = reinterpret_cast<uint32_t *>(dst) + rank;
+          if (bits & 1u) *o++ = v0.x;
+          if (bits & 2u) *o++ = v0.y;
+          if (bits & 4u) *o++ = v0.z;
+          if (bits & 8u) *o++ = v0.w;
+          if (bits & 16u) *o++ = v1.x;
+          if (bits & 32u) *o++ = v1.y;
+          if (bits & 64u) *o++ = v1.z;
+          if (bits & 128u) *o = v1.w;
+        } else if constexpr (W == 16) {
+          uint64_t *o = reinterpret_cast<uint64_t *>(dst + (size_t)rank * 16);
+          if (bits & 1u) { const uint4 x = buf[(j * 2 + 0) * 32 + lane]; o[0] = (uint64_t)x.x | ((uint64_t)x.y << 32); o[1] = (uint64_t)x.z | ((uint64_t)x.w << 32); o += 2; }
+          if (bits & 2u) { const uint4 x = buf[(j * 2 + 1) * 32 + lane]; o[0] = (uint64_t)x.x | ((uint64_t)x.y << 32); o[1] = (uint64_t)x.z | ((uint64_t)x.w << 32); }
+        } else if constexpr (W == 32) {
+          const uint4 v0 = buf[(j * 2 + 0) * 32 + lane], v1 = buf[(j * 2 + 1) * 32 + lane];
+          uint64_t *o = reinterpret_cast<uint64_t *>(dst + (size_t)rank * 32);
+          o[0] = (uint64_t)v0.x | ((uint64_t)v0.y << 32);
+          o[1] = (uint64_t)v0.z | ((uint64_t)v0.w << 32);
+          o[2] = (uint64_t)v1.x | ((uint64_t)v1.y << 32);
+          o[3] = (uint64_t)v1.z | ((uint64_t)v1.w << 32);
+        } else {  // W = 1, 2: walk the set bits, elements straight from the landing buffer
+          const uint8_t *lb = reinterpret_cast<const uint8_t *>(buf);
+          uint8_t *o = dst + (size_t)rank * W;
+          while (bits) {
+            const int e = __ffs((int)bits) - 1;
+            bits &= bits - 1;
+            const int byte = e * W;
+            const uint8_t *p = lb + ((size_t)((j * 2 + (byte >> 4)) * 32 + lane) << 4) + (byte & 15);
+            if constexpr (W == 2) *reinterpret_cast<uint16_t *>(o) = *reinterpret_cast<const uint16_t *>(p);
+            else *o = *p;
+            o += W;
+          }
+        }
+      }
+      __syncwarp();  // the landing buffer is reused by the next pass / tile
+    }
+    // ---- validity: PEXT(source validity, mask) per word, assembled in a warp-private window ----
+    if (vsrc) {
+      const uint64_t bits = c ? pext64_sparse(v, m, c) : 0ull;
+      valid_cnt += __popcll(bits);
+      const uint32_t lead = (uint32_t)(out0 & 31);
+      const uint32_t nwords = (lead + (uint32_t)cnt + 31) >> 5;  // <= 33
+      for (uint32_t i = lane; i < nwords; i += 32) s_win[wid][i] = 0;
+      __syncwarp();
+      if (c) {
+        const uint32_t p = lead + incl - c;
+        const uint32_t sh = p & 31;
+        atomicOr(&s_win[wid][p >> 5], (uint32_t)(bits << sh));
+        if (sh + c > 32) {
+          const uint64_t rest = bits >> (32 - sh);
+          atomicOr(&s_win[wid][(p >> 5) + 1], (uint32_t)rest);
+          if (sh + c > 64) atomicOr(&s_win[wid][(p >> 5) + 2], (uint32_t)(rest >> 32));
+        }
+      }
+      __syncwarp();
+      uint32_t *o = a.vout + (out0 >> 5);
+      for (uint32_t i = lane; i < nwords; i += 32) {
+        const uint32_t word = s_win[wid][i];
+        if (i == 0 || i == nwords - 1) { if (word) atomicOr(o + i, word); }  // shared with neighbouring tiles
+        else o[i] = word;
+      }
+      __syncwarp();
+    }
+  }
+  if (vsrc && a.res) {
+    valid_cnt = warp_sum(valid_cnt);
+    if (lane == 0 && valid_cnt) atomicAdd(a.res + RES_COUNT, (unsigned long long)valid_cnt);
+  }
+}
+
 // ---- bit compaction (validity / boolean values): software PEXT --------------------------
 // One lane per mask word; a warp covers 32 consecutive words (two tiles).
 struct CompressArgs {
@@ -499,11 +689,20 @@ template <int W>
 acu_status launch_filter(acu_ctx *ctx, const FilterBatch &fb, int n_cols) {
   const FilterArgs &fa = fb.col[0];
   if (fa.aligned16) {
-    constexpr size_t smem = 8 * (size_t)AsyncCfg<W>::PASS_BYTES;  // 8 warps x per-warp landing buffer
-    if (ctx->occupancy.find(reinterpret_cast<const void *>(k_filter_values_async<W>)) == ctx->occupancy.end())  // first use on this device
-      ACU_CUDA(ctx, cudaFuncSetAttribute(k_filter_values_async<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int gx = acu_wave_grid(ctx, k_filter_values_async<W>, 256, smem, (fa.n_tiles + 7) / 8);
-    ACU_LAUNCH_TIMED(ctx, ACU_K_FILTER, (k_filter_values_async<W>), dim3(gx, n_cols), 256, smem, fb);
+    static const bool legacy = getenv("ACU_FILTER_LEGACY") != nullptr;  // round-1 two-pass kernels, kept for A/B measurements
+    if (legacy) {
+      constexpr size_t smem = 8 * (size_t)AsyncCfg<W>::PASS_BYTES;  // 8 warps x per-warp landing buffer
+      if (ctx->occupancy.find(reinterpret_cast<const void *>(k_filter_values_async<W>)) == ctx->occupancy.end())  // first use on this device
+        ACU_CUDA(ctx, cudaFuncSetAttribute(k_filter_values_async<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int gx = acu_wave_grid(ctx, k_filter_values_async<W>, 256, smem, (fa.n_tiles + 7) / 8);
+      ACU_LAUNCH_TIMED(ctx, ACU_K_FILTER, (k_filter_values_async<W>), dim3(gx, n_cols), 256, smem, fb);
+      return ACU_OK;
+    }
+    constexpr size_t smem = 8 * (size_t)FusedCfg<W>::PASS_BYTES;
+    if (ctx->occupancy.find(reinterpret_cast<const void *>(k_filter_fused<W>)) == ctx->occupancy.end())
+      ACU_CUDA(ctx, cudaFuncSetAttribute(k_filter_fused<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int gx = acu_wave_grid(ctx, k_filter_fused<W>, 256, smem, (fa.n_tiles + 7) / 8);
+    ACU_LAUNCH_TIMED(ctx, ACU_K_FILTER, (k_filter_fused<W>), dim3(gx, n_cols), 256, smem, fb);
   } else {
     const int gx = acu_wave_grid(ctx, k_filter_values<W>, 256, 0, (fa.n_tiles + 7) / 8);
     ACU_LAUNCH_TIMED(ctx, ACU_K_FILTER, (k_filter_values<W>), dim3(gx, n_cols), 256, 0, fb);
@@ -544,7 +743,14 @@ CompressArgs compress_args(const acu_filter_plan *plan, const uint8_t *src, int6
   return c;
 }
 
-FilterArgs filter_args(const acu_filter_plan *plan, const acu_array *values, acu_array_out *out) {
+// true when the column's validity compaction rides in the value kernel (k_filter_fused)
+bool fuses_validity(const acu_array *values) {
+  static const bool legacy = getenv("ACU_FILTER_LEGACY") != nullptr;
+  return !legacy && ((uintptr_t)values->values % 16) == 0;
+}
+
+FilterArgs filter_args(const acu_filter_plan *plan, const acu_array *values, acu_array_out *out, bool has_nulls,
+                       unsigned long long *res) {
   FilterArgs fa{};
   fa.values = static_cast<const uint8_t *>(values->values);
   fa.out = static_cast<uint8_t *>(out->values);
@@ -552,6 +758,13 @@ FilterArgs filter_args(const acu_filter_plan *plan, const acu_array *values, acu
   fa.tile_off = plan->tile_off;
   fa.n_tiles = plan->n_tiles;
   fa.aligned16 = ((uintptr_t)values->values % 16) == 0;
+  if (has_nulls && fuses_validity(values)) {  // FilterPredicate::filter_nulls in the same pass (filter.rs:512-533)
+    fa.vsrc = values->validity;
+    fa.voff = values->validity_offset;
+    fa.vlen = plan->len;
+    fa.vout = reinterpret_cast<uint32_t *>(out->validity);
+    fa.res = res;
+  }
   return fa;
 }
 
@@ -559,16 +772,12 @@ FilterArgs filter_args(const acu_filter_plan *plan, const acu_array *values, acu
 
 extern "C" {
 
-acu_status acu_filter_plan_create(acu_ctx *ctx, const acu_array *pred, acu_filter_plan **out_plan) {
-  *out_plan = nullptr;
-  ACU_ENTER(ctx);
+// Allocate the plan's device storage for a predicate of `len` rows.
+static acu_status plan_alloc(acu_ctx *ctx, int64_t len, acu_filter_plan **out_plan) {
   acu_filter_plan *plan = new acu_filter_plan();
-  const int64_t len = pred->len;
   plan->len = len;
-  if (len == 0) { *out_plan = plan; return ACU_OK; }
-  acu_status st;
-  const int64_t nc = acu_resolve_null_count(ctx, pred, &st);
-  if (st != ACU_OK) { delete plan; return st; }
+  *out_plan = plan;
+  if (len == 0) return ACU_OK;
   const int64_t n_tiles = (len + TILE_ROWS - 1) / TILE_ROWS;
   const int64_t n_chunks = (n_tiles + SCAN_CHUNK - 1) / SCAN_CHUNK;
   const int64_t n_words_padded = ((n_tiles * TILE_WORDS + 31) / 32) * 32;
@@ -578,42 +787,88 @@ acu_status acu_filter_plan_create(acu_ctx *ctx, const acu_array *pred, acu_filte
   const size_t mask_b = up((size_t)n_words_padded * 8), off_b = up((size_t)n_off_padded * 8),
                cnt_b = up((size_t)n_tiles * 4), ch_b = up((size_t)n_chunks * 8);
   void *mem = nullptr;
-  st = acu_malloc(ctx, mask_b + off_b + cnt_b + ch_b, &mem);
-  if (st != ACU_OK) { delete plan; return st; }
+  acu_status st = acu_malloc(ctx, mask_b + off_b + cnt_b + ch_b, &mem);
+  if (st != ACU_OK) { delete plan; *out_plan = nullptr; return st; }
   uint8_t *p = static_cast<uint8_t *>(mem);
   plan->storage = mem;
   plan->mask = reinterpret_cast<uint64_t *>(p);
   plan->tile_off = reinterpret_cast<uint64_t *>(p + mask_b);
   plan->tile_count = reinterpret_cast<uint32_t *>(p + mask_b + off_b);
   plan->chunk_total = reinterpret_cast<uint64_t *>(p + mask_b + off_b + cnt_b);
-  auto bail = [&](acu_status s) { acu_free(ctx, mem); delete plan; return s; };
-  const uint8_t *nv = (pred->validity && nc > 0) ? pred->validity : nullptr;  // filter.rs:261-264
-  {
-    acu_status s = acu_res_reset(ctx);
-    if (s != ACU_OK) return bail(s);
-  }
-  const int slot = acu_kstats_begin(ctx, ACU_K_FILTER_PLAN);
-  k_plan_mask<<<acu_grid(ctx, (n_words_padded / 32 + 7) / 8, 8), 256, 0, ctx->stream>>>(
-      static_cast<const uint8_t *>(pred->values), pred->values_offset, nv, pred->validity_offset, len, n_words_padded,
-      plan->mask, plan->tile_count, n_tiles);
+  return ACU_OK;
+}
+
+// mask + tile_count are queued on the stream: scan them into tile offsets, fetch the count, pick the strategy.
+static acu_status plan_finish(acu_ctx *ctx, acu_filter_plan *plan, int kslot) {
+  const int64_t len = plan->len, n_tiles = plan->n_tiles;
+  const int64_t n_chunks = (n_tiles + SCAN_CHUNK - 1) / SCAN_CHUNK;
+  const int64_t n_words_padded = ((n_tiles * TILE_WORDS + 31) / 32) * 32;
+  const int64_t n_off_padded = n_words_padded / TILE_WORDS + 2;
   k_plan_scan_chunks<<<(unsigned)n_chunks, 1024, 0, ctx->stream>>>(plan->tile_count, n_tiles, plan->tile_off, plan->chunk_total);
   k_plan_scan_top<<<1, 1024, 0, ctx->stream>>>(plan->chunk_total, n_chunks, ctx->d_res);
   k_plan_finalize<<<acu_grid(ctx, (n_off_padded + 255) / 256, 8), 256, 0, ctx->stream>>>(plan->tile_off, n_tiles, n_off_padded,
                                                                                      plan->chunk_total, ctx->d_res);
-  acu_kstats_end(ctx, slot);
-  ctx->launches += 4;
+  if (kslot >= 0) acu_kstats_end(ctx, kslot);
+  ctx->launches += 3;
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return bail(acu_cuda_fail(ctx, e, "filter plan kernels"));
-  {
-    acu_status s = acu_res_fetch(ctx);
-    if (s != ACU_OK) return bail(s);
-  }
+  if (e != cudaSuccess) return acu_cuda_fail(ctx, e, "filter plan kernels");
+  ACU_TRY(acu_res_fetch(ctx));
   plan->count = (int64_t)ctx->h_res[RES_COUNT];
   // IterationStrategy::default_strategy (filter.rs:346-364)
   if (plan->count == 0) plan->strategy = ACU_FILTER_NONE;
   else if (plan->count == len) plan->strategy = ACU_FILTER_ALL;
   else if ((double)plan->count / (double)len > 0.8) plan->strategy = ACU_FILTER_SLICES;
   else plan->strategy = ACU_FILTER_INDEX;
+  return ACU_OK;
+}
+
+acu_status acu_filter_plan_create(acu_ctx *ctx, const acu_array *pred, acu_filter_plan **out_plan) {
+  *out_plan = nullptr;
+  ACU_ENTER(ctx);
+  const int64_t len = pred->len;
+  acu_status st = ACU_OK;
+  int64_t nc = 0;
+  if (len > 0) {
+    nc = acu_resolve_null_count(ctx, pred, &st);
+    ACU_TRY(st);
+  }
+  acu_filter_plan *plan = nullptr;
+  ACU_TRY(plan_alloc(ctx, len, &plan));
+  if (len == 0) { *out_plan = plan; return ACU_OK; }
+  auto bail = [&](acu_status s) { acu_free(ctx, plan->storage); delete plan; return s; };
+  const int64_t n_words_padded = ((plan->n_tiles * TILE_WORDS + 31) / 32) * 32;
+  const uint8_t *nv = (pred->validity && nc > 0) ? pred->validity : nullptr;  // filter.rs:261-264
+  st = acu_res_reset(ctx);
+  if (st != ACU_OK) return bail(st);
+  const int slot = acu_kstats_begin(ctx, ACU_K_FILTER_PLAN);
+  k_plan_mask<<<acu_grid(ctx, (n_words_padded / 32 + 7) / 8, 8), 256, 0, ctx->stream>>>(
+      static_cast<const uint8_t *>(pred->values), pred->values_offset, nv, pred->validity_offset, len, n_words_padded,
+      plan->mask, plan->tile_count, plan->n_tiles);
+  ctx->launches += 1;
+  st = plan_finish(ctx, plan, slot);
+  if (st != ACU_OK) return bail(st);
+  *out_plan = plan;
+  return ACU_OK;
+}
+
+// FilterBuilder::new(&cmp::op(a, b)?) fused: the comparison kernels write mask + tile counts (see include/arrow_cuda.h).
+acu_status acu_filter_plan_create_cmp(acu_ctx *ctx, acu_dtype dtype, acu_cmp_op op, const acu_array *a, const acu_array *b,
+                                      acu_filter_plan **out_plan) {
+  *out_plan = nullptr;
+  ACU_ENTER(ctx);
+  int64_t len = 0;
+  ACU_TRY(acu_cmp_result_len(ctx, a, b, &len));
+  acu_filter_plan *plan = nullptr;
+  ACU_TRY(plan_alloc(ctx, len, &plan));
+  if (len == 0) { *out_plan = plan; return ACU_OK; }
+  auto bail = [&](acu_status s) { acu_free(ctx, plan->storage); delete plan; return s; };
+  const int64_t n_words_padded = ((plan->n_tiles * TILE_WORDS + 31) / 32) * 32;
+  acu_status st = acu_res_reset(ctx);
+  if (st != ACU_OK) return bail(st);
+  st = acu_cmp_into_plan(ctx, dtype, op, a, b, plan->mask, n_words_padded, plan->tile_count, plan->n_tiles);
+  if (st != ACU_OK) return bail(st);
+  st = plan_finish(ctx, plan, -1);
+  if (st != ACU_OK) return bail(st);
   *out_plan = plan;
   return ACU_OK;
 }
@@ -680,16 +935,22 @@ acu_status acu_filter_col_launch(acu_ctx *ctx, const acu_filter_plan *plan, int 
     }
     return ACU_OK;
   }
+  bool fused = false;
   if (kind == 0) {
     FilterBatch fb{};
-    fb.col[0] = filter_args(plan, values, out);
+    fb.col[0] = filter_args(plan, values, out, has_nulls, res);
+    fused = fb.col[0].vsrc != nullptr;
+    if (fused) {  // the kernel ORs boundary words into the bitmap
+      ACU_CUDA(ctx, cudaMemsetAsync(out->validity, 0, acu_bitmap_bytes(plan->count), ctx->stream));
+      *mode = 1;
+    }
     ACU_TRY(launch_filter_width(ctx, elem_bytes, fb, 1));
   }
   CompressBatch cb{};
   int nc = 0;
   if (kind == 1)
     cb.col[nc++] = compress_args(plan, static_cast<const uint8_t *>(values->values), values->values_offset, out->values, nullptr);
-  if (has_nulls) {  // FilterPredicate::filter_nulls (filter.rs:512-533)
+  if (has_nulls && !fused) {  // FilterPredicate::filter_nulls (filter.rs:512-533)
     cb.col[nc++] = compress_args(plan, values->validity, values->validity_offset, out->validity, res);
     *mode = 1;
   }
@@ -723,7 +984,13 @@ acu_status acu_filter_cols_launch(acu_ctx *ctx, const acu_filter_plan *plan, int
     const int al = ((uintptr_t)values[c]->values % 16) == 0;
     for (int d = c; d < n && k < BATCH_COLS; ++d) {
       if (kinds[d] != 0 || done[d] || widths[d] != widths[c] || (((uintptr_t)values[d]->values % 16) == 0) != al) continue;
-      fb.col[k++] = filter_args(plan, values[d], outs[d]);
+      const bool has_nulls = values[d]->validity != nullptr && values[d]->null_count != 0;
+      fb.col[k] = filter_args(plan, values[d], outs[d], has_nulls, res[d]);
+      if (fb.col[k].vsrc) {
+        ACU_CUDA(ctx, cudaMemsetAsync(outs[d]->validity, 0, acu_bitmap_bytes(plan->count), ctx->stream));
+        modes[d] = 1;
+      }
+      ++k;
       done[d] = 1;
     }
     ACU_TRY(launch_filter_width(ctx, widths[c], fb, k));
@@ -741,7 +1008,7 @@ acu_status acu_filter_cols_launch(acu_ctx *ctx, const acu_filter_plan *plan, int
       cb.col[k++] = compress_args(plan, static_cast<const uint8_t *>(values[c]->values), values[c]->values_offset, outs[c]->values, nullptr);
       if (k == BATCH_COLS) ACU_TRY(flush());
     }
-    if (values[c]->validity != nullptr && values[c]->null_count != 0) {
+    if (values[c]->validity != nullptr && values[c]->null_count != 0 && !(kinds[c] == 0 && fuses_validity(values[c]))) {
       cb.col[k++] = compress_args(plan, values[c]->validity, values[c]->validity_offset, outs[c]->validity, res[c]);
       modes[c] = 1;
       if (k == BATCH_COLS) ACU_TRY(flush());

@@ -458,6 +458,10 @@ struct CmpParams {
   int neg, fold;
   uint64_t *out_bits, *out_valid;
   unsigned long long *res;
+  // fused compare -> filter plan (acu_filter_plan_create_cmp): out_bits is the plan's mask and receives result & validity;
+  // tile_count[t] = selected rows of 1024-row tile t (written by the streaming kernel; the tail's tiles are counted separately)
+  int fuse;
+  uint32_t *tile_count;
 };
 
 template <class T> __device__ __forceinline__ bool pred_eq(T l, T r) {
@@ -511,6 +515,7 @@ __global__ void __launch_bounds__(256) k_cmp(const CmpParams<T> p) {
         if (p.bv) r &= ld_bits64(p.bv, p.boff + row, p.boff + n);
         if (p.fold == FOLD_DISTINCT) v = (l ^ r) | (l & r & v);              // cmp.rs:331
         else if (p.fold == FOLD_NOT_DISTINCT) v = (~(l | r) & m) | (l & r & v);  // cmp.rs:341
+        else if (p.fuse) v &= l & r;  // a null result selects nothing (filter.rs:167-171)
         p.out_bits[row >> 6] = v;
         if (p.out_valid) {
           p.out_valid[row >> 6] = l & r;
@@ -585,6 +590,13 @@ __global__ void __launch_bounds__(256, 4) k_cmp_v2(const CmpParams<T> p, const i
     if (p.neg) v = ~v;
     if (p.fold == FOLD_DISTINCT) v = (lw ^ rw) | (lw & rw & v);
     else if (p.fold == FOLD_NOT_DISTINCT) v = ~(lw | rw) | (lw & rw & v);
+    if (p.fuse) {
+      if (p.fold == FOLD_NONE) v &= lw & rw;
+      unsigned c = __popcll(v);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) c += __shfl_xor_sync(ACU_FULL_MASK, c, o);  // sum inside each 16-lane half = one 1024-row tile
+      if ((lane & 15) == 0) p.tile_count[(sbase >> 10) + (lane >> 4)] = c;
+    }
     p.out_bits[(sbase >> 6) + lane] = v;
     if (p.out_valid) {
       p.out_valid[(sbase >> 6) + lane] = lw & rw;
@@ -597,8 +609,27 @@ __global__ void __launch_bounds__(256, 4) k_cmp_v2(const CmpParams<T> p, const i
   }
 }
 
+// popcount of the 1024-row tiles [first_tile, n_tiles) of a plan mask (the ragged tail of a fused compare)
+__global__ void __launch_bounds__(256) k_tile_counts(const uint64_t *__restrict__ mask, int64_t first_tile, int64_t n_tiles,
+                                                     uint32_t *__restrict__ tile_count) {
+  const int64_t t = first_tile + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  unsigned c = 0;
+  for (int k = 0; k < 16; ++k) c += __popcll(mask[t * 16 + k]);
+  tile_count[t] = c;
+}
+
+struct CmpFuse {  // destination of a fused compare -> filter plan
+  uint64_t *mask;
+  int64_t n_words_padded;
+  uint32_t *tile_count;
+  int64_t n_tiles;
+};
+
 template <class T>
-acu_status cmp_typed(acu_ctx *ctx, acu_cmp_op op, const acu_array *l, const acu_array *r, acu_array_out *out) {
+acu_status cmp_typed(acu_ctx *ctx, acu_cmp_op op, const acu_array *l, const acu_array *r, acu_array_out *out, const CmpFuse *fuse = nullptr) {
+  acu_array_out scratch_out{};
+  if (fuse) out = &scratch_out;
   const bool ls = l->is_scalar != 0, rs = r->is_scalar != 0;
   if (l->len != r->len && !ls && !rs)  // cmp.rs:228-232
     return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0,
@@ -616,15 +647,26 @@ acu_status cmp_typed(acu_ctx *ctx, acu_cmp_op op, const acu_array *l, const acu_
   const bool ln = lnc > 0, rn = rnc > 0;  // logical_nulls().filter(null_count > 0)
   const bool fold = op == ACU_DISTINCT || op == ACU_NOT_DISTINCT;
   const bool l_null_scalar = ls && ln, r_null_scalar = rs && rn;
+  if (fuse) {  // words past the data (the plan pads its mask to a multiple of 32 words) select nothing
+    const int64_t used = (len + 63) / 64;
+    if (fuse->n_words_padded > used)
+      ACU_CUDA(ctx, cudaMemsetAsync(fuse->mask + used, 0, (size_t)(fuse->n_words_padded - used) * 8, ctx->stream));
+  }
   if (!fold && (l_null_scalar || r_null_scalar) && !(ls && rs)) {
     // a null scalar against an array: BooleanArray::new_null(len) (cmp.rs:353, :364)
+    if (fuse) {  // an all-null predicate selects nothing
+      ACU_CUDA(ctx, cudaMemsetAsync(fuse->mask, 0, (size_t)fuse->n_words_padded * 8, ctx->stream));
+      ACU_CUDA(ctx, cudaMemsetAsync(fuse->tile_count, 0, (size_t)fuse->n_tiles * 4, ctx->stream));
+      return ACU_OK;
+    }
     ACU_CUDA(ctx, cudaMemsetAsync(out->values, 0, acu_bitmap_bytes(len), ctx->stream));
     return set_new_null(ctx, len, 0, out);
   }
   CmpParams<T> p{};
   p.n = len;
   p.res = ctx->d_res;
-  p.out_bits = static_cast<uint64_t *>(out->values);
+  p.out_bits = fuse ? fuse->mask : static_cast<uint64_t *>(out->values);
+  if (fuse) { p.fuse = 1; p.tile_count = fuse->tile_count; }
   // Less / Greater family: gt and lt_eq swap the operands (cmp.rs:481-488)
   const bool swap = (op == ACU_GT || op == ACU_LT_EQ);
   const acu_array *x = swap ? r : l, *y = swap ? l : r;
@@ -638,8 +680,8 @@ acu_status cmp_typed(acu_ctx *ctx, acu_cmp_op op, const acu_array *l, const acu_
   p.fold = op == ACU_DISTINCT ? FOLD_DISTINCT : op == ACU_NOT_DISTINCT ? FOLD_NOT_DISTINCT : FOLD_NONE;
   if (xn) { if (xs && !(xs && ys)) p.a_null_scalar = 1; else { p.av = x->validity; p.aoff = x->validity_offset; } }
   if (yn) { if (ys && !(xs && ys)) p.b_null_scalar = 1; else { p.bv = y->validity; p.boff = y->validity_offset; } }
-  if (!fold && (xn || yn)) p.out_valid = reinterpret_cast<uint64_t *>(out->validity);
-  ACU_TRY(acu_res_reset(ctx));
+  if (!fold && (xn || yn) && !fuse) p.out_valid = reinterpret_cast<uint64_t *>(out->validity);
+  if (!fuse) ACU_TRY(acu_res_reset(ctx));
   const bool lt = !(op == ACU_EQ || op == ACU_NEQ || fold);
   // streaming head over whole 2048-row super-groups when the value pointers are 16-B aligned
   const bool aligned = (p.a_scalar || (uintptr_t)p.a % 16 == 0) && (p.b_scalar || (uintptr_t)p.b % 16 == 0);
@@ -663,7 +705,12 @@ acu_status cmp_typed(acu_ctx *ctx, acu_cmp_op op, const acu_array *l, const acu_
     const int64_t blocks = (strips + 31) / 32;
     if (lt) ACU_LAUNCH_TIMED(ctx, ACU_K_CMP, (k_cmp<T, true>), acu_wave_grid(ctx, k_cmp<T, true>, 256, 0, blocks), 256, 0, q);
     else ACU_LAUNCH_TIMED(ctx, ACU_K_CMP, (k_cmp<T, false>), acu_wave_grid(ctx, k_cmp<T, false>, 256, 0, blocks), 256, 0, q);
+    if (fuse) {  // the tail's tiles (head is a multiple of 2048 rows = 2 tiles)
+      const int64_t first_tile = head >> 10, rest = fuse->n_tiles - first_tile;
+      if (rest > 0) ACU_LAUNCH(ctx, k_tile_counts, (unsigned)((rest + 255) / 256), 256, 0, fuse->mask, first_tile, fuse->n_tiles, fuse->tile_count);
+    }
   }
+  if (fuse) return ACU_OK;  // stream-ordered: the plan's scan kernels follow on the same stream
   ACU_TRY(acu_res_fetch(ctx));
   if (p.out_valid) {
     out->has_validity = 1;
@@ -909,6 +956,25 @@ extern "C" acu_status acu_cmp(acu_ctx *ctx, acu_dtype dtype, acu_cmp_op op, cons
                               const acu_array *b, acu_array_out *out) {
   ACU_ENTER(ctx);
   ACU_DISPATCH(dtype, cmp_typed, ctx, op, a, b, out)
+  return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "Invalid comparison operation: dtype %d", (int)dtype);
+}
+
+// The comparison of acu_cmp written straight into a filter plan's mask / tile counts (compact.cu: acu_filter_plan_create_cmp).
+// Stream-ordered, no synchronisation. *out_len = the result length (cmp.rs:228-235).
+acu_status acu_cmp_result_len(acu_ctx *ctx, const acu_array *l, const acu_array *r, int64_t *out_len) {
+  const bool ls = l->is_scalar != 0, rs = r->is_scalar != 0;
+  if (l->len != r->len && !ls && !rs)
+    return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0,
+                    "Cannot compare arrays of different lengths, got %lld vs %lld", (long long)l->len, (long long)r->len);
+  *out_len = ls ? r->len : l->len;
+  return ACU_OK;
+}
+acu_status acu_cmp_into_plan(acu_ctx *ctx, acu_dtype dtype, acu_cmp_op op, const acu_array *a, const acu_array *b, uint64_t *mask,
+                             int64_t n_words_padded, uint32_t *tile_count, int64_t n_tiles) {
+  CmpFuse f{mask, n_words_padded, tile_count, n_tiles};
+  const CmpFuse *fuse = &f;
+  acu_array_out *out = nullptr;
+  ACU_DISPATCH(dtype, cmp_typed, ctx, op, a, b, out, fuse)
   return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "Invalid comparison operation: dtype %d", (int)dtype);
 }
 

@@ -72,3 +72,8 @@ acu_status acu_take_cols_launch(acu_ctx *ctx, int n, const int32_t *elem_bytes, 
                                 acu_array_out *const *outs, unsigned long long *const *res, int *modes);
 acu_status acu_reduce_cols_launch(acu_ctx *ctx, int n, const acu_dtype *dtypes, const acu_agg_op *ops, const acu_array *arrays,
                                   const int64_t *nc, uint8_t *scratch, size_t scratch_per_col, unsigned long long *const *res, int *launched);
+
+// Fused compare -> filter plan (elementwise.cu): the cmp kernels write the plan's mask words and per-tile counts.
+acu_status acu_cmp_result_len(acu_ctx *ctx, const acu_array *l, const acu_array *r, int64_t *out_len);
+acu_status acu_cmp_into_plan(acu_ctx *ctx, acu_dtype dtype, acu_cmp_op op, const acu_array *a, const acu_array *b, uint64_t *mask,
+                             int64_t n_words_padded, uint32_t *tile_count, int64_t n_tiles);

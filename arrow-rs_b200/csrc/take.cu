@@ -13,14 +13,14 @@
 // are written with fully coalesced stores, output validity is packed with a warp ballot
 // (lane == output bit), and the null count / out-of-bounds detection ride in the same pass.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
 #include "bitmap.cuh"
 #include "internal.cuh"
 
-#define TAKE_WTILE 256  // indices per warp tile
-#define TAKE_PER_LANE (TAKE_WTILE / 32)
+#define TAKE_WTILE_DEFAULT 256  // indices per warp tile (8 gathers per lane in flight)
 
 namespace {
 
@@ -112,8 +112,11 @@ template <int IT> __device__ __forceinline__ typename WideOf<IT>::type widen(typ
 constexpr int TAKE_BATCH_COLS = 8;
 struct TakeBatch { TakeArgs col[TAKE_BATCH_COLS]; };
 
-template <int W, int IT, bool BOOL>
-__global__ void __launch_bounds__(256, 3) k_take(const TakeBatch batch) {
+// PL = gathers per lane in flight (warp tile = 32 * PL indices), MINB = resident CTAs per SM the register budget is cut for.
+template <int W, int IT, bool BOOL, int PL = 8, int MINB = 3>
+__global__ void __launch_bounds__(256, MINB) k_take(const TakeBatch batch) {
+  constexpr int TAKE_WTILE = 32 * PL;
+  constexpr int TAKE_PER_LANE = PL;
   const TakeArgs a = batch.col[blockIdx.y];
   using V = typename VecOf<W>::type;
   using I = typename IdxOf<IT>::raw;
@@ -259,9 +262,34 @@ uint64_t index_max(acu_dtype t) {
   }
 }
 
+// Experiment hook (tools/take_sweep.sh): ACU_TAKE_VARIANT = "PL,MINB" selects another tiling of the Int64 / UInt32-index gather.
+template <int PL, int MINB>
+acu_status launch_take_variant(acu_ctx *ctx, const TakeBatch &tb, int n_cols) {
+  const int64_t tiles = ((tb.col[0].m + 32 * PL - 1) / (32 * PL) + 7) / 8;
+  ACU_LAUNCH_TIMED(ctx, ACU_K_TAKE, (k_take<8, 4, false, PL, MINB>), dim3(acu_wave_grid(ctx, k_take<8, 4, false, PL, MINB>, 256, 0, tiles), n_cols), 256, 0, tb);
+  return ACU_OK;
+}
+
 template <int W>
 acu_status launch_take_w(acu_ctx *ctx, int kind, const TakeBatch &tb, int n_cols) {
   const TakeArgs &ta = tb.col[0];
+  constexpr int TAKE_WTILE = TAKE_WTILE_DEFAULT;
+  if (W == 8 && kind == 4 && !ta.vbits) {
+    static const char *var = getenv("ACU_TAKE_VARIANT");
+    if (var) {
+      int pl = 0, mb = 0;
+      if (sscanf(var, "%d,%d", &pl, &mb) == 2) {
+        if (pl == 8 && mb == 4) return launch_take_variant<8, 4>(ctx, tb, n_cols);
+        if (pl == 8 && mb == 5) return launch_take_variant<8, 5>(ctx, tb, n_cols);
+        if (pl == 8 && mb == 6) return launch_take_variant<8, 6>(ctx, tb, n_cols);
+        if (pl == 4 && mb == 6) return launch_take_variant<4, 6>(ctx, tb, n_cols);
+        if (pl == 4 && mb == 8) return launch_take_variant<4, 8>(ctx, tb, n_cols);
+        if (pl == 16 && mb == 2) return launch_take_variant<16, 2>(ctx, tb, n_cols);
+        if (pl == 16 && mb == 3) return launch_take_variant<16, 3>(ctx, tb, n_cols);
+        if (pl == 16 && mb == 4) return launch_take_variant<16, 4>(ctx, tb, n_cols);
+      }
+    }
+  }
   const int64_t tiles = ((ta.m + TAKE_WTILE - 1) / TAKE_WTILE + 7) / 8;  // CTAs: 8 warp tiles each
 #define ACU_TAKE_CASE(IT)                                                                                   \
   case IT:                                                                                                                   \

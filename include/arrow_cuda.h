@@ -247,6 +247,32 @@ acu_status acu_filter_bytes(acu_ctx *ctx, const acu_filter_plan *plan, int32_t o
                             void *out_offsets, uint8_t *out_data, int64_t out_data_capacity,
                             int64_t *out_data_len, acu_array_out *out_nulls);
 
+/* FilterBuilder::new(&cmp::op(a, b)?) without the BooleanArray in between (arrow-ord/src/cmp.rs:220-382
+ * feeding arrow-select/src/filter.rs:254-273): the comparison writes the plan's normalised mask (result & result validity —
+ * a null comparison result selects nothing, prep_null_mask_filter filter.rs:167-171) and the per-tile counts directly;
+ * the 2 x N/8-byte result bitmaps are never written to or re-read from HBM. The plan is identical to
+ * acu_filter_plan_create(acu_cmp(dtype, op, a, b)). Errors as acu_cmp. */
+acu_status acu_filter_plan_create_cmp(acu_ctx *ctx, acu_dtype dtype, acu_cmp_op op, const acu_array *a,
+                                      const acu_array *b, acu_filter_plan **out_plan);
+
+/* ------------------------------------------------------------------------- */
+/* nullif / zip — arrow-select/src/nullif.rs, zip.rs                         */
+/* ------------------------------------------------------------------------- */
+/* nullif(left, right) (nullif.rs:44-113): the result shares left's value buffers; only the validity changes:
+ * out->validity = left.validity & !(right.values & right.validity) (bit offset 0), out->null_count, out->has_validity = 0
+ * when no slot is null (ArrayDataBuilder::build drops an all-valid NullBuffer). `left` may be an array of any kind: only
+ * its validity / len are read; out->values is not touched. Length mismatch => ACU_ERR_COMPUTE. */
+acu_status acu_nullif(acu_ctx *ctx, const acu_array *left, const acu_array *right /* boolean */, acu_array_out *out);
+
+/* zip(mask, truthy, falsy) (zip.rs:99-226) for fixed-width values of elem_bytes in {1,2,4,8,16,32}: out[i] = truthy[i] where
+ * mask[i] is Some(true), else falsy[i]; either side may be a scalar (is_scalar, len 1); value bytes are copied blindly from
+ * the chosen side (also under nulls); the result carries a validity buffer iff some input has nulls and the result has at
+ * least one. Both sides scalar = ScalarZipper (zip.rs:248-440): with one null scalar every slot holds the other value and
+ * the validity (always present) is the mask / its negation. ACU_ERR_INVALID_ARGUMENT "all arrays should have the same
+ * length" / "scalar arrays must have 1 element". */
+acu_status acu_zip(acu_ctx *ctx, int32_t elem_bytes, const acu_array *mask /* boolean */, const acu_array *truthy,
+                   const acu_array *falsy, acu_array_out *out);
+
 /* ------------------------------------------------------------------------- */
 /* take — arrow-select/src/take.rs                                           */
 /* ------------------------------------------------------------------------- */

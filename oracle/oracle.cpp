@@ -1319,4 +1319,111 @@ acu_status orc_generate_bits(uint64_t seed, int64_t first_row, double p, uint8_t
   return ACU_OK;
 }
 
+// nullif (arrow-select/src/nullif.rs:44-113): only the validity changes; `out->validity` receives
+// left.nulls & !(right.values & right.nulls) and the builder drops it when it holds no nulls
+// (arrow-data/src/data.rs:2238-2251 `.filter(|b| b.null_count() != 0)`).
+acu_status orc_nullif(const acu_array *left, const acu_array *right, acu_array_out *out) {
+  if (left->len != right->len)  // :47-51
+    return fail(ACU_ERR_COMPUTE, -1, 0, 0, 0, "Cannot perform comparison operation on arrays of different length");
+  const int64_t len = left->len;
+  out->len = len;
+  out->has_validity = 0;
+  out->null_count = 0;
+  if (len == 0) return ACU_OK;  // :54-56
+  const uint8_t *rv = static_cast<const uint8_t *>(right->values);
+  int64_t valid = 0;
+  for (int64_t i = 0, w = 0; i < len; i += 64, ++w) {
+    uint64_t r = load_bits(rv, right->values_offset + i, right->values_offset + len);
+    if (right->validity) r &= load_bits(right->validity, right->validity_offset + i, right->validity_offset + len);  // :70-73
+    uint64_t t;
+    if (left->validity) {  // bitwise_bin_op_helper(l & !r) (:78-92)
+      t = load_bits(left->validity, left->validity_offset + i, left->validity_offset + len) & ~r;
+    } else {               // bitwise_unary_op_helper(!r) (:94-103); bits past len are not counted
+      t = ~r;
+    }
+    int64_t n = len - i;
+    if (n < 64) t &= (~0ull) >> (64 - n);
+    valid += __builtin_popcountll(t);
+    memcpy(out->validity + 8 * w, &t, 8);
+  }
+  out->null_count = len - valid;
+  out->has_validity = out->null_count > 0;
+  return ACU_OK;
+}
+
+// zip (arrow-select/src/zip.rs:99-226) for fixed-width values of `elem_bytes` bytes. Array path: MutableArrayData extends
+// runs of truthy (SlicesIterator over the null-cleaned mask) and fills the gaps with falsy (:156-226); values are copied
+// blindly, validity is tracked iff some input has nulls (arrow-data/src/transform/mod.rs:470) and dropped when the result has
+// none (:927-936). Both sides scalar: PrimitiveScalarImpl::create_output (:392-440).
+acu_status orc_zip(int32_t elem_bytes, const acu_array *mask, const acu_array *truthy, const acu_array *falsy, acu_array_out *out) {
+  const bool ts = truthy->is_scalar != 0, fs = falsy->is_scalar != 0;
+  if (ts && truthy->len != 1) return fail(ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "scalar arrays must have 1 element");
+  if (!ts && truthy->len != mask->len) return fail(ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "all arrays should have the same length");
+  if (fs && falsy->len != 1) return fail(ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "scalar arrays must have 1 element");
+  if (!fs && falsy->len != mask->len) return fail(ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "all arrays should have the same length");
+  const int64_t len = mask->len;
+  const size_t w = (size_t)elem_bytes;
+  out->len = len;
+  out->has_validity = 0;
+  out->null_count = 0;
+  if (len == 0) return ACU_OK;
+  // maybe_prep_null_mask_filter (:662-671)
+  Predicate p;
+  {
+    const uint8_t *vals = static_cast<const uint8_t *>(mask->values);
+    const bool mask_nulls = mask->validity && resolve_null_count(mask) > 0;
+    p.len = len;
+    p.mask.assign((size_t)((len + 63) / 64) + 1, 0);
+    for (int64_t i = 0, k = 0; i < len; i += 64, ++k) {
+      uint64_t v = load_bits(vals, mask->values_offset + i, mask->values_offset + len);
+      if (mask_nulls) v &= load_bits(mask->validity, mask->validity_offset + i, mask->validity_offset + len);
+      p.mask[k] = v;
+    }
+  }
+  const uint8_t *tv = static_cast<const uint8_t *>(truthy->values), *fv = static_cast<const uint8_t *>(falsy->values);
+  uint8_t *dst = static_cast<uint8_t *>(out->values);
+  auto is_null0 = [](const acu_array *a) { return a->validity && !get_bit(a->validity, a->validity_offset); };
+  if (ts && fs) {
+    const bool tn = is_null0(truthy), fn = is_null0(falsy);
+    const uint8_t *pb = p.bytes();
+    if (!tn && !fn) {
+      for (int64_t i = 0; i < len; ++i) memcpy(dst + (size_t)i * w, get_bit(pb, i) ? tv : fv, w);
+      return ACU_OK;  // nulls: None
+    }
+    memset(out->validity, 0, acu_bitmap_bytes(len));
+    if (!tn || !fn) {  // vec![value; len] + NullBuffer::new(predicate | !predicate)
+      const uint8_t *val = !tn ? tv : fv;
+      for (int64_t i = 0; i < len; ++i) memcpy(dst + (size_t)i * w, val, w);
+      for (int64_t i = 0; i < len; ++i)
+        if (get_bit(pb, i) == !tn) set_bit(out->validity, i);
+    } else {
+      memset(dst, 0, (size_t)len * w);  // T::default_value(), NullBuffer::new_null
+    }
+    out->has_validity = 1;  // PrimitiveArray::try_new(scalars, Some(nulls)) keeps the buffer even without nulls
+    out->null_count = len - count_bits(out->validity, 0, len);
+    return ACU_OK;
+  }
+  const bool use_nulls = resolve_null_count(truthy) > 0 || resolve_null_count(falsy) > 0;
+  if (use_nulls) memset(out->validity, 0, acu_bitmap_bytes(len));
+  auto extend = [&](const acu_array *src, const uint8_t *sv, bool scalar, int64_t start, int64_t end) {  // try_extend(idx, start, end) / one by one for scalars
+    for (int64_t i = start; i < end; ++i) {
+      const int64_t j = scalar ? 0 : i;
+      memcpy(dst + (size_t)i * w, sv + (size_t)j * w, w);
+      if (use_nulls && (!src->validity || get_bit(src->validity, src->validity_offset + j))) set_bit(out->validity, i);
+    }
+  };
+  int64_t filled = 0;
+  for_each_slice(p, [&](int64_t s, int64_t e) {
+    if (s > filled) extend(falsy, fv, fs, filled, s);
+    extend(truthy, tv, ts, s, e);
+    filled = e;
+  });
+  if (filled < len) extend(falsy, fv, fs, filled, len);
+  if (use_nulls) {
+    const int64_t nc = len - count_bits(out->validity, 0, len);
+    if (nc > 0) { out->has_validity = 1; out->null_count = nc; }
+  }
+  return ACU_OK;
+}
+
 }  // extern "C"

@@ -474,6 +474,69 @@ case("sum_checked_nulls_skipped", A + ":918-934", "sum_checked", a=arr("int64", 
 case("sum_checked_all_null", A + ":902-904", "sum_checked", a=arr("int32", [None, None]), expect={"scalar": None})
 case("sum_checked_ok", A + ":897", "sum_checked", a=arr("int32", [1, 2, 3, 4, 5]), expect={"scalar": 15})
 
+# =========================================================================================
+# nullif — arrow-select/src/nullif.rs
+# =========================================================================================
+NI = "arrow-select/src/nullif.rs"
+case("nullif_doc_example", NI + ":31-43", "nullif", left=arr("int32", [None, 8, 1, 9]), right=arr("bool", [False, True, False, None]),
+     expect={"data": [None, None, 1, 9]})
+case("nullif_int_array", NI + ":127", "nullif", left=arr("int32", [15, None, 8, 1, 9]), right=arr("bool", [False, None, True, False, None]),
+     expect={"data": [15, None, None, 1, 9]})
+COMP7 = [False, False, False, None, True, False, None]
+case("nullif_int_array_offset", NI + ":166", "nullif", left=arr("int32", [None, 15, 8, 1, 9], slice=(1, 3)),
+     right=arr("bool", COMP7, slice=(2, 3)), expect={"data": [15, 8, None]})
+case("nullif_int_large_left_offset", NI + ":228", "nullif", left=arr("int32", [-1] * 16 + [None, 15, 8, 1, 9], slice=(17, 3)),
+     right=arr("bool", COMP7, slice=(2, 3)), expect={"data": [15, 8, None]})
+case("nullif_int_large_right_offset", NI + ":278", "nullif", left=arr("int32", [None, 15, 8, 1, 9], slice=(1, 3)),
+     right=arr("bool", [False] * 19 + [None, True, False, None], slice=(18, 3)), expect={"data": [15, 8, None]})
+case("nullif_boolean_offset", NI + ":327", "nullif", left=arr("bool", [None, True, False, True, True], slice=(1, 3)),
+     right=arr("bool", COMP7, slice=(2, 3)), expect={"data": [True, False, None]})
+case("nullif_no_nulls", NI + ":466", "nullif", left=arr("int32", [15, 7, 8, 1, 9]), right=arr("bool", [False, None, True, False, None]),
+     expect={"data": [15, 7, None, 1, 9]})
+case("nullif_nothing_nulled_has_no_null_buffer", NI + ":105-112", "nullif", left=arr("int32", [15, 7, 8]), right=arr("bool", [False, None, False]),
+     expect={"data": [15, 7, 8], "no_validity": True})
+case("nullif_empty", NI + ":477", "nullif", left=arr("int32", []), right=arr("bool", []), expect={"data": []})
+case("nullif_length_mismatch", NI + ":47-51", "nullif", left=arr("int32", [1, 2]), right=arr("bool", [True]),
+     expect_error="Compute error: Cannot perform comparison operation on arrays of different length")
+
+# =========================================================================================
+# zip — arrow-select/src/zip.rs
+# =========================================================================================
+Z = "arrow-select/src/zip.rs"
+ZA, ZB = [5, None, 7, None, 1], [None, 3, 6, 7, 3]
+M1, M2 = [True, True, False, False, True], [False, False, True, True, False]
+case("zip_doc_example", Z + ":50-69", "zip", mask=arr("bool", [True, True, False, None, True]), truthy=arr("int32", [1, None, 3, 4, 5]),
+     falsy=arr("int32", [10, 20, 30, 40, 50]), expect={"data": [1, None, 30, 40, 5]})
+case("zip_doc_example_scalar", Z + ":79-97", "zip", mask=arr("bool", [True, True, False, None, True]), truthy=arr("int32", [1, None, 3, 4, 5]),
+     falsy=arr("int32", [42], scalar=True), expect={"data": [1, None, 42, 42, 5]})
+case("zip_kernel_one", Z + ":870", "zip", mask=arr("bool", M1), truthy=arr("int32", ZA), falsy=arr("int32", ZB), expect={"data": [5, None, 6, 7, 1]})
+case("zip_kernel_two", Z + ":881", "zip", mask=arr("bool", M2), truthy=arr("int32", ZA), falsy=arr("int32", ZB), expect={"data": [None, 3, 7, None, 3]})
+case("zip_kernel_scalar_falsy_1", Z + ":892", "zip", mask=arr("bool", M1), truthy=arr("int32", ZA), falsy=arr("int32", [42], scalar=True),
+     expect={"data": [5, None, 42, 42, 1]})
+case("zip_kernel_scalar_falsy_2", Z + ":905", "zip", mask=arr("bool", M2), truthy=arr("int32", ZA), falsy=arr("int32", [42], scalar=True),
+     expect={"data": [42, 42, 7, None, 42]})
+case("zip_kernel_scalar_truthy_1", Z + ":918", "zip", mask=arr("bool", M1), truthy=arr("int32", [42], scalar=True), falsy=arr("int32", ZA),
+     expect={"data": [42, 42, 7, None, 42]})
+case("zip_kernel_scalar_truthy_2", Z + ":931", "zip", mask=arr("bool", M2), truthy=arr("int32", [42], scalar=True), falsy=arr("int32", ZA),
+     expect={"data": [5, None, 42, 42, 1]})
+case("zip_kernel_scalar_both_mask_ends_with_true", Z + ":944", "zip", mask=arr("bool", M1), truthy=arr("int32", [42], scalar=True),
+     falsy=arr("int32", [123], scalar=True), expect={"data": [42, 42, 123, 123, 42], "no_validity": True})
+case("zip_kernel_scalar_both_mask_ends_with_false", Z + ":956", "zip", mask=arr("bool", [True, True, False, True, False, False]),
+     truthy=arr("int32", [42], scalar=True), falsy=arr("int32", [123], scalar=True), expect={"data": [42, 42, 123, 42, 123, 123]})
+case("zip_kernel_primitive_scalar_none_1", Z + ":975", "zip", mask=arr("bool", M1), truthy=arr("int32", [42], scalar=True),
+     falsy=arr("int32", [None], scalar=True), expect={"data": [42, 42, None, None, 42]})
+case("zip_kernel_primitive_scalar_none_2", Z + ":987", "zip", mask=arr("bool", M2), truthy=arr("int32", [42], scalar=True),
+     falsy=arr("int32", [None], scalar=True), expect={"data": [None, None, 42, 42, None]})
+case("zip_kernel_primitive_scalar_both_null", Z + ":999", "zip", mask=arr("bool", M2), truthy=arr("int32", [None], scalar=True),
+     falsy=arr("int32", [None], scalar=True), expect={"data": [None] * 5})
+MN = {"dtype": "bool", "raw_values": [True, True, False, True, False, False], "raw_validity": [True, True, True, False, True, True]}
+case("zip_primitive_array_mask_nulls_treated_as_false", Z + ":1011", "zip", mask=MN, truthy=arr("int32", [1, 2, 3, 4, 5, 6]),
+     falsy=arr("int32", [7, 8, 9, 10, 11, 12]), expect={"data": [1, 2, 9, 10, 11, 12], "no_validity": True})
+case("zip_primitive_scalar_mask_nulls_treated_as_false", Z + ":1038", "zip", mask=MN, truthy=arr("int32", [42], scalar=True),
+     falsy=arr("int32", [123], scalar=True), expect={"data": [42, 42, 123, 123, 123, 123]})
+case("zip_length_mismatch", Z + ":128-132", "zip", mask=arr("bool", [True, False]), truthy=arr("int32", [1, 2, 3]), falsy=arr("int32", [1, 2]),
+     expect_error="Invalid argument error: all arrays should have the same length")
+
 out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "vectors.json")
 with open(out, "w") as f:
     json.dump({"reference": "apache/arrow-rs 59.2.0 @ cd7c6b83", "cases": cases}, f, indent=0)

@@ -37,7 +37,10 @@ def build_array(spec):
     if "raw_values" in spec:  # explicit values buffer + validity (values under nulls are preserved)
         vals = [decode_value(v) for v in spec["raw_values"]]
         mask = np.array(spec["raw_validity"], dtype=bool)
-        h = HostArray.from_numpy(dtype, np.array(vals, dtype=acu.NP_DTYPES[dtype]), mask)
+        if dtype == BOOL:
+            h = HostArray.bool_from_numpy(np.array(vals, dtype=bool), mask)
+        else:
+            h = HostArray.from_numpy(dtype, np.array(vals, dtype=acu.NP_DTYPES[dtype]), mask)
     else:
         items = [None if v is None else decode_value(v) for v in spec["data"]]
         h = HostArray.from_list(dtype, items, force_validity=spec.get("force_validity", False))
@@ -159,6 +162,10 @@ def run_case(backend, c):
             return getattr(backend, op)(build_array(c["a"]))
         if op in ("and_", "or_", "and_not", "and_kleene", "or_kleene"):
             return getattr(backend, op)(build_array(c["a"]), build_array(c["b"]))
+        if op == "nullif":
+            return backend.nullif(build_array(c["left"]), build_array(c["right"]))
+        if op == "zip":
+            return backend.zip(build_array(c["mask"]), build_array(c["truthy"]), build_array(c["falsy"]))
         if op in ("not_", "is_null", "is_not_null"):
             return getattr(backend, op)(build_array(c["a"]))
         raise AssertionError("unknown op " + op)

@@ -46,6 +46,8 @@ class Oracle:
             "orc_cast_numeric": [i32, i32, i32, P(abi.Array), P(abi.ArrayOut)],
             "orc_aggregate": [i32, i32, P(abi.Array), i32, P(u64), P(i64)],
             "orc_sum_checked": [i32, P(abi.Array), P(u64), P(i64)],
+            "orc_nullif": [P(abi.Array), P(abi.Array), P(abi.ArrayOut)],
+            "orc_zip": [i32, P(abi.Array), P(abi.Array), P(abi.Array), P(abi.ArrayOut)],
             "orc_generate_values": [i32, u64, i64, u64, vp, i64],
             "orc_generate_bits": [u64, i64, C.c_double, vp, i64],
             "orc_bench_create": [i64, i64, i32, P(u64), C.c_double, C.c_double, i32, P(vp), P(C.c_double)],
@@ -183,6 +185,32 @@ class Oracle:
         ad, bd = acu.host_descriptor(a), acu.host_descriptor(b)
         self.check(self.lib.orc_cmp(a.dtype, op, C.byref(ad), C.byref(bd), C.byref(out)))
         return self._result(out, vals, valid, BOOL)
+
+    # -- fused compare -> filter: by definition filter(values, cmp(a, b)) ------------------------
+    def filter_cmp(self, values, op, a, b):
+        pred = self.cmp(op, a, b)
+        return self.filter(values, pred), self.filter_plan(pred)
+
+    # -- nullif / zip --------------------------------------------------------------------------
+    def nullif(self, left, right):
+        n = max(left.length, 1)
+        out, vals, valid = self._out(0, n)
+        ld, rd = acu.host_descriptor(left), acu.host_descriptor(right)
+        self.check(self.lib.orc_nullif(C.byref(ld), C.byref(rd), C.byref(out)))
+        m = out.len
+        if m == 0:
+            return left
+        validity = valid[: bitmap_bytes(m)].copy() if out.has_validity else None
+        v = left.values if left.dtype == BOOL else left.values[:m]
+        return HostArray(left.dtype, v, m, validity, 0, left.values_offset if left.dtype == BOOL else 0,
+                         out.null_count if out.has_validity else 0)
+
+    def zip(self, mask, truthy, falsy):
+        n = mask.length
+        out, vals, valid = self._out(n * truthy.width(), max(n, 1))
+        md, td, fd = acu.host_descriptor(mask), acu.host_descriptor(truthy), acu.host_descriptor(falsy)
+        self.check(self.lib.orc_zip(truthy.width(), C.byref(md), C.byref(td), C.byref(fd), C.byref(out)))
+        return self._result(out, vals, valid, truthy.dtype)
 
     # -- boolean (arrow-arith/src/boolean.rs) -------------------------------------------------
     def boolean(self, op, a, b=None):
