@@ -174,6 +174,67 @@ class Utf8Column:
         return len(self.offsets) - 1
 
 
+class ViewColumn:
+    """A Utf8View / BinaryView column on the host (GenericByteViewArray, arrow-array/src/array/byte_view_array.rs): `views` is an
+    (n, 16) uint8 array — length u32 | 12 inline bytes, or length | 4-byte prefix | buffer index u32 | offset u32
+    (arrow-data/src/byte_view.rs) — `buffers` the data buffers (uint8 arrays), `nulls` a HostArray carrying validity / length /
+    scalar-ness."""
+
+    def __init__(self, views, buffers, nulls):
+        self.views, self.buffers, self.nulls = views, buffers, nulls
+
+    @property
+    def length(self):
+        return self.nulls.length
+
+    @staticmethod
+    def from_values(items, block_size=64, scalar=False, garbage_under_nulls=None):
+        """items: list of bytes / str / None. Long values (> 12 bytes) are appended to data buffers of `block_size` bytes
+        (a new buffer is started when one is full, like GenericByteViewBuilder)."""
+        n = len(items)
+        views = np.zeros((n, 16), dtype=np.uint8)
+        buffers, cur = [], bytearray()
+        for i, it in enumerate(items):
+            if it is None:
+                if garbage_under_nulls is not None:
+                    views[i] = garbage_under_nulls[i % len(garbage_under_nulls)]
+                continue
+            b = it.encode() if isinstance(it, str) else bytes(it)
+            views[i, :4] = np.frombuffer(np.uint32(len(b)).tobytes(), dtype=np.uint8)
+            if len(b) <= 12:
+                views[i, 4:4 + len(b)] = np.frombuffer(b, dtype=np.uint8)
+            else:
+                if len(cur) + len(b) > block_size and len(cur):
+                    buffers.append(np.frombuffer(bytes(cur), dtype=np.uint8).copy())
+                    cur = bytearray()
+                views[i, 4:8] = np.frombuffer(b[:4], dtype=np.uint8)
+                views[i, 8:12] = np.frombuffer(np.uint32(len(buffers)).tobytes(), dtype=np.uint8)
+                views[i, 12:16] = np.frombuffer(np.uint32(len(cur)).tobytes(), dtype=np.uint8)
+                cur += b
+        if len(cur):
+            buffers.append(np.frombuffer(bytes(cur), dtype=np.uint8).copy())
+        mask = np.array([it is not None for it in items], dtype=bool)
+        nulls = HostArray.from_list(U8, [0 if m else None for m in mask])
+        nulls.values = np.zeros(0, np.uint8)
+        if scalar:
+            nulls.is_scalar = True
+        return ViewColumn(views, buffers, nulls)
+
+    def values(self):
+        out, mask = [], self.nulls.valid_mask()
+        for i in range(self.length):
+            if not mask[i]:
+                out.append(None)
+                continue
+            ln = int(np.frombuffer(self.views[i, :4].tobytes(), dtype=np.uint32)[0])
+            if ln <= 12:
+                out.append(bytes(self.views[i, 4:4 + ln]))
+            else:
+                bi, off = (int(x) for x in np.frombuffer(self.views[i, 8:16].tobytes(), dtype=np.uint32))
+                out.append(bytes(self.buffers[bi][off:off + ln]))
+        return out
+
+
 class DeviceArray:
     """A HostArray's buffers uploaded to HBM (DeviceBuffer pair) with the same offsets."""
 
@@ -620,6 +681,79 @@ class Context:
                 self._free_out(out)
             da.free()
             db.free()
+
+    # -- cmp on Utf8 / Binary and Utf8View / BinaryView operands (cmp.rs:783-898) -----------------
+    def _upload_nulls(self, nulls, owned):
+        d = abi.Array()
+        d.len, d.is_scalar = nulls.length, 1 if nulls.is_scalar else 0
+        d.validity_offset = nulls.validity_offset
+        d.null_count = nulls.null_count if nulls.validity is not None else 0
+        if nulls.validity is not None:
+            dn = self.malloc(nulls.validity.nbytes + 8)
+            self.h2d(dn, nulls.validity)
+            owned.append(dn)
+            d.validity = dn
+        return d
+
+    def cmp_bytes(self, op, a, b):
+        """a, b: Utf8Column (offsets, data, nulls); nulls.is_scalar marks a Datum scalar."""
+        assert a.offsets.dtype == b.offsets.dtype
+        owned = []
+        n = max(a.nulls.length if not a.nulls.is_scalar else 0, b.nulls.length if not b.nulls.is_scalar else 0, 1)
+        out = self.alloc_out(bitmap_bytes(n), n)
+        try:
+            descs = []
+            for col in (a, b):
+                d = abi.BytesArray()
+                d_off, d_data = self.malloc(col.offsets.nbytes + 16), self.malloc(col.data.nbytes + 16)
+                owned += [d_off, d_data]
+                self.h2d(d_off, col.offsets)
+                if col.data.nbytes:
+                    self.h2d(d_data, col.data)
+                d.offsets, d.data, d.nulls = d_off, d_data, self._upload_nulls(col.nulls, owned)
+                descs.append(d)
+            self.check(self.lib.acu_cmp_bytes(self.h, a.offsets.dtype.itemsize, op, C.byref(descs[0]), C.byref(descs[1]), C.byref(out)))
+            res, out = self.download_out(out, BOOL), None
+            return res
+        finally:
+            if out is not None:
+                self._free_out(out)
+            for p in owned:
+                self.free(p)
+
+    def cmp_view(self, op, a, b):
+        """a, b: ViewColumn."""
+        owned = []
+        n = max(a.length if not a.nulls.is_scalar else 0, b.length if not b.nulls.is_scalar else 0, 1)
+        out = self.alloc_out(bitmap_bytes(n), n)
+        try:
+            descs, keep = [], []
+            for col in (a, b):
+                d = abi.ViewArray()
+                views = np.ascontiguousarray(col.views)
+                d_views = self.malloc(views.nbytes + 16)
+                owned.append(d_views)
+                if views.nbytes:
+                    self.h2d(d_views, views)
+                ptrs = []
+                for buf in col.buffers:
+                    db = self.malloc(buf.nbytes + 16)
+                    owned.append(db)
+                    self.h2d(db, buf)
+                    ptrs.append(db)
+                table = (C.c_void_p * max(len(ptrs), 1))(*ptrs)
+                keep.append(table)
+                d.views, d.buffers, d.n_buffers = d_views, table, len(ptrs)
+                d.nulls = self._upload_nulls(col.nulls, owned)
+                descs.append(d)
+            self.check(self.lib.acu_cmp_byte_view(self.h, op, C.byref(descs[0]), C.byref(descs[1]), C.byref(out)))
+            res, out = self.download_out(out, BOOL), None
+            return res
+        finally:
+            if out is not None:
+                self._free_out(out)
+            for p in owned:
+                self.free(p)
 
     # -- fused compare -> filter (cmp.rs:220-382 feeding filter.rs:254-273) -------------------
     def filter_cmp(self, values, op, a, b):

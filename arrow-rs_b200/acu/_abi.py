@@ -79,6 +79,16 @@ class ArrayOut(C.Structure):
     ]
 
 
+class BytesArray(C.Structure):
+    """acu_bytes_array: a Utf8 / Binary operand of acu_cmp_bytes."""
+    _fields_ = [("offsets", C.c_void_p), ("data", C.c_void_p), ("nulls", Array)]
+
+
+class ViewArray(C.Structure):
+    """acu_view_array: a Utf8View / BinaryView operand of acu_cmp_byte_view."""
+    _fields_ = [("views", C.c_void_p), ("buffers", C.POINTER(C.c_void_p)), ("n_buffers", C.c_int32), ("reserved", C.c_int32), ("nulls", Array)]
+
+
 COL_PRIMITIVE, COL_BOOLEAN, COL_BYTES = range(3)
 BOOL_AND, BOOL_OR, BOOL_AND_NOT, BOOL_AND_KLEENE, BOOL_OR_KLEENE, BOOL_NOT, BOOL_IS_NULL, BOOL_IS_NOT_NULL = range(8)
 MAX_BATCH_COLUMNS = 64
@@ -192,6 +202,8 @@ PROTOTYPES = {
     "acu_arith": (i32, [vp, i32, i32, P(Array), P(Array), P(ArrayOut)]),
     "acu_neg": (i32, [vp, i32, i32, P(Array), P(ArrayOut)]),
     "acu_cmp": (i32, [vp, i32, i32, P(Array), P(Array), P(ArrayOut)]),
+    "acu_cmp_bytes": (i32, [vp, i32, i32, P(BytesArray), P(BytesArray), P(ArrayOut)]),
+    "acu_cmp_byte_view": (i32, [vp, i32, P(ViewArray), P(ViewArray), P(ArrayOut)]),
     "acu_cast_numeric": (i32, [vp, i32, i32, i32, P(Array), P(ArrayOut)]),
     "acu_boolean": (i32, [vp, i32, P(Array), P(Array), P(ArrayOut)]),
     "acu_aggregate": (i32, [vp, i32, i32, P(Array), P(u64), P(i64)]),
@@ -209,6 +221,7 @@ PROTOTYPES = {
     "acu_comm_destroy": (i32, [vp]),
     "acu_comm_allreduce_aggregates": (i32, [vp, i32, i32, P(u64), P(i64), i32]),
     "acu_comm_allreduce_i64_sum": (i32, [vp, P(i64), i32]),
+    "acu_aggregate_allreduce": (i32, [vp, i32, i32, P(Array), P(u64), P(i64)]),
 }
 
 _lib = None

@@ -6,7 +6,7 @@
 #include <dlfcn.h>
 #include <stdio.h>
 
-#include "common.cuh"
+#include "internal.cuh"
 
 namespace {
 
@@ -67,7 +67,7 @@ acu_status nccl_fail(acu_ctx *ctx, int rc, const char *what) {
     if (_rc != 0) return nccl_fail((ctx), _rc, #expr);     \
   } while (0)
 
-inline int64_t key64(uint64_t bits, acu_dtype t) {  // native bits -> order-preserving int64 key
+__host__ __device__ inline int64_t key64(uint64_t bits, acu_dtype t) {  // native bits -> order-preserving int64 key
   switch (t) {
     case ACU_I8: return (int8_t)bits;
     case ACU_I16: return (int16_t)bits;
@@ -78,7 +78,7 @@ inline int64_t key64(uint64_t bits, acu_dtype t) {  // native bits -> order-pres
     default: return (int64_t)bits;  // unsigned: reduced as uint64
   }
 }
-inline uint64_t unkey64(int64_t k, acu_dtype t) {
+__host__ __device__ inline uint64_t unkey64(int64_t k, acu_dtype t) {
   switch (t) {
     case ACU_I8: return (uint8_t)k;
     case ACU_I16: return (uint16_t)k;
@@ -89,6 +89,26 @@ inline uint64_t unkey64(int64_t k, acu_dtype t) {
   }
 }
 
+
+// Encode a shard's partial aggregate for the all-reduce (what acu_comm_allreduce_aggregates does on the host): identity for
+// a shard without valid rows, sign extension for narrow signed sums, totalOrder keys for signed / float min / max.
+__host__ __device__ inline uint64_t encode_partial(uint64_t bits, bool empty, acu_dtype dtype, acu_agg_op op) {
+  const bool is_unsigned = dtype == ACU_U8 || dtype == ACU_U16 || dtype == ACU_U32 || dtype == ACU_U64;
+  if (op == ACU_SUM) {
+    uint64_t v = dtype == ACU_F32 ? (empty ? 0 : (bits & 0xffffffffull)) : (empty ? 0 : bits);
+    if (dtype != ACU_F32 && dtype != ACU_F64 && !is_unsigned) v = (uint64_t)key64(v, dtype);
+    return v;
+  }
+  if (is_unsigned) return empty ? (op == ACU_MIN ? ~0ull : 0ull) : bits;
+  return (uint64_t)(empty ? (op == ACU_MIN ? INT64_MAX : INT64_MIN) : key64(bits, dtype));
+}
+
+__global__ void k_stage_partial(const unsigned long long *res, int launched, long long valid_count, int dtype, int op, uint64_t *buf) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const uint64_t bits = launched ? res[RES_AUX0] : 0ull;
+  buf[0] = encode_partial(bits, valid_count == 0, (acu_dtype)dtype, (acu_agg_op)op);
+  buf[1] = (uint64_t)valid_count;
+}
 }  // namespace
 
 extern "C" {
@@ -151,6 +171,8 @@ acu_status acu_comm_allreduce_aggregates(acu_ctx *ctx, acu_dtype dtype, acu_agg_
   // truly asynchronous; layout [n x 8 B values][n x int64 counts]
   uint64_t *stage = reinterpret_cast<uint64_t *>(ctx->h_res + (size_t)(RES_BLOCKS / 2) * RES_SLOTS);
   uint8_t *buf = reinterpret_cast<uint8_t *>(ctx->d_res + (size_t)(RES_BLOCKS / 2) * RES_SLOTS);
+  ctx->res_clean = false;  // the staging overwrites result blocks: the next reset re-initialises all of them
+  ctx->res_dirty_blocks = RES_BLOCKS;
   const bool is_unsigned = dtype == ACU_U8 || dtype == ACU_U16 || dtype == ACU_U32 || dtype == ACU_U64;
   int nccl_type, nccl_op;
   for (int i = 0; i < n; ++i) {
@@ -202,6 +224,54 @@ acu_status acu_comm_allreduce_aggregates(acu_ctx *ctx, acu_dtype dtype, acu_agg_
     } else {
       partial_bits[i] = unkey64((int64_t)stage[i], dtype);
     }
+  }
+  return ACU_OK;
+}
+
+// sum / min / max of this rank's shard combined over all ranks with ONE synchronisation (see include/arrow_cuda.h).
+acu_status acu_aggregate_allreduce(acu_ctx *ctx, acu_dtype dtype, acu_agg_op op, const acu_array *a, uint64_t *out_bits,
+                                   int64_t *out_valid_count) {
+  if (ctx->world <= 1 || !ctx->nccl_comm) return acu_aggregate(ctx, dtype, op, a, out_bits, out_valid_count);
+  ACU_ENTER(ctx);
+  NcclApi *api = nccl_api();
+  *out_bits = 0;
+  *out_valid_count = 0;
+  acu_status st;
+  const int64_t nc = a->len ? acu_resolve_null_count(ctx, a, &st) : 0;
+  if (a->len) ACU_TRY(st);
+  const int64_t valid = a->len - nc;
+  void *scratch;
+  ACU_TRY(acu_scratch(ctx, acu_reduce_col_scratch(ctx), &scratch));
+  int launched = 0;
+  ACU_TRY(acu_res_reset(ctx));
+  ACU_TRY(acu_reduce_col_launch(ctx, dtype, op, a, nc, scratch, acu_dres(ctx, 0), &launched));
+  uint64_t *stage = reinterpret_cast<uint64_t *>(ctx->h_res + (size_t)(RES_BLOCKS / 2) * RES_SLOTS);
+  uint64_t *buf = reinterpret_cast<uint64_t *>(ctx->d_res + (size_t)(RES_BLOCKS / 2) * RES_SLOTS);
+  ACU_LAUNCH(ctx, k_stage_partial, 1, 32, 0, acu_dres(ctx, 0), launched, (long long)valid, (int)dtype, (int)op, buf);
+  const bool is_unsigned = dtype == ACU_U8 || dtype == ACU_U16 || dtype == ACU_U32 || dtype == ACU_U64;
+  if (op == ACU_SUM && dtype != ACU_F32 && dtype != ACU_F64) {
+    ACU_NCCL(ctx, api->AllReduce(buf, buf, 2, NCCL_INT64, NCCL_SUM, ctx->nccl_comm, ctx->stream));  // value and count: one int64 sum
+  } else {
+    ACU_NCCL(ctx, api->GroupStart());
+    if (op == ACU_SUM && dtype == ACU_F32) ACU_NCCL(ctx, api->AllReduce(buf, buf, 2, NCCL_FLOAT32, NCCL_SUM, ctx->nccl_comm, ctx->stream));
+    else if (op == ACU_SUM) ACU_NCCL(ctx, api->AllReduce(buf, buf, 1, NCCL_FLOAT64, NCCL_SUM, ctx->nccl_comm, ctx->stream));
+    else ACU_NCCL(ctx, api->AllReduce(buf, buf, 1, is_unsigned ? NCCL_UINT64 : NCCL_INT64, op == ACU_MIN ? NCCL_MIN : NCCL_MAX, ctx->nccl_comm, ctx->stream));
+    ACU_NCCL(ctx, api->AllReduce(buf + 1, buf + 1, 1, NCCL_INT64, NCCL_SUM, ctx->nccl_comm, ctx->stream));
+    ACU_NCCL(ctx, api->GroupEnd());
+  }
+  ACU_CUDA(ctx, cudaMemcpyAsync(stage, buf, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the only synchronisation of the call
+  acu_kstats_drain(ctx);
+  ctx->res_clean = false;  // block 0 and the staging slots were written without a fetch
+  ctx->res_dirty_blocks = RES_BLOCKS;
+  *out_valid_count = (int64_t)stage[1];
+  if (op == ACU_SUM) {
+    const int sz = acu_dtype_size(dtype);
+    *out_bits = sz == 8 ? stage[0] : (stage[0] & ((1ull << (8 * sz)) - 1ull));
+  } else if (is_unsigned) {
+    *out_bits = stage[0];
+  } else {
+    *out_bits = unkey64((int64_t)stage[0], dtype);
   }
   return ACU_OK;
 }

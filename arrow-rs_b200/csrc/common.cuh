@@ -41,6 +41,8 @@ struct acu_ctx {
   std::unordered_map<const void *, int> occupancy;  // resident CTAs per SM, per kernel
   unsigned long long *d_res = nullptr;  // RES_BLOCKS x RES_SLOTS u64 on the device
   unsigned long long *h_res = nullptr;  // pinned mirror
+  bool res_clean = false;               // the result blocks hold their initial values (see acu_res_reset_n)
+  int res_dirty_blocks = RES_BLOCKS;
   void *d_scratch = nullptr;            // grows on demand (block partials, scans)
   size_t scratch_bytes = 0;
   // NCCL (loaded with dlopen, see comm.cu)

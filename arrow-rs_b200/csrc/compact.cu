@@ -405,27 +405,15 @@ __global__ void __launch_bounds__(256, 6) k_filter_values_async(const FilterBatc
 }
 
 // ---- one-pass filter: values + validity in the same kernel ---------------------------------
-// k_filter_fused<W>: the value compaction of k_filter_values_async with (a) a lane owning a whole 32-byte DRAM sector
-// per round (two predicated 16-byte cp.async: 4 Int64 rows per lane instead of 2, which halves the per-row cost of the
-// mask / rank bookkeeping — the round-1 kernel was ISSUE-bound: 75 % issue-active, 0.77 warp instructions per row) and
-// (b) FilterPredicate::filter_nulls (filter.rs:512-533) fused in: the warp that owns a 1024-row tile already holds the
+// k_filter_fused<W>: the value compaction of k_filter_values_async with (a) the mask / rank bookkeeping strength-reduced
+// to 32-bit operations on lane-constant positions (the round-1 kernel was ISSUE-bound: 75 % issue-active, 0.77 warp
+// instructions per row; a lane's selection bits of a whole pass are packed into one register at issue time and reused
+// by the consume phase) and (b) FilterPredicate::filter_nulls (filter.rs:512-533) fused in: the warp that owns a 1024-row tile already holds the
 // tile's 16 mask words and their popcount prefix, so lanes 0..15 PEXT the source validity words with them, the bits are
 // assembled in a warp-private shared-memory window and leave as whole 32-bit words (atomicOr only on the two words a
 // tile shares with its neighbours; the output bitmap is zeroed by a memset node before the launch), and the popcount
 // (= the filtered null count) goes to the column's result block. The mask is read ONCE for values and validity, and
 // k_zero_outputs + k_compress_bits are gone from the primitive path.
-template <int W> struct FusedCfg {
-  static constexpr int RPU = 32 / W;                       // rows per 32-byte unit (one lane, one round)
-  static constexpr int TILE_BYTES = TILE_ROWS * W;
-  static constexpr int PASS_BYTES = TILE_BYTES < 4096 ? TILE_BYTES : 4096;  // per-warp landing buffer
-  static constexpr int ROUNDS = PASS_BYTES / 1024;         // 32 lanes x 32 B per round
-  static constexpr int PASSES = TILE_BYTES / PASS_BYTES;
-  static constexpr int PASS_ROWS = PASS_BYTES / W;
-  static constexpr uint32_t UNIT_MASK = RPU == 32 ? 0xffffffffu : ((1u << RPU) - 1u);
-  static constexpr int HALF = RPU >= 2 ? RPU / 2 : 1;      // rows per 16-byte half (W = 32: the row spans both halves)
-  static constexpr uint32_t HALF_MASK = (1u << HALF) - 1u;
-};
-
 __device__ __forceinline__ uint64_t pext64_sparse(uint64_t v, uint64_t m, uint32_t cnt) {
   // PEXT(v, m) looping over the RARER kind of selected bit (validity bitmaps are mostly ones).
   const uint64_t ones = m & v, zeros = m & ~v;
@@ -440,15 +428,32 @@ __device__ __forceinline__ uint64_t pext64_sparse(uint64_t v, uint64_t m, uint32
   return clear_mode ? (full & ~acc) : acc;
 }
 
-template <int W>
-__global__ void __launch_bounds__(256, 6) k_filter_fused(const FilterBatch batch) {
+// Per-lane constants of the chunk -> mask-bit mapping. Chunk c of a pass (c = j*32 + lane) covers rows
+// row_base + j*RPJ + lr, lr = lane*RPC/CPR. For W <= 8 a chunk round spans whole mask words, so the word / 32-bit half /
+// bit position of a lane's chunk differ from round to round only by a compile-time amount; for W = 16 / 32 a round is a
+// fraction of one word. Everything below is 32-bit arithmetic on 32-bit halves of the mask words.
+template <int W> struct FusedCfg {
+  using A = AsyncCfg<W>;
+  static constexpr int RPC = W <= 16 ? 16 / W : 1;
+  static constexpr int CPR = W <= 16 ? 1 : W / 16;
+  static constexpr int RPJ = 32 * RPC / CPR;                       // rows per chunk round
+  static constexpr uint32_t CHUNK_MASK = RPC == 32 ? 0xffffffffu : ((1u << RPC) - 1u);
+};
+
+template <int W, int MINB = 6>
+__global__ void __launch_bounds__(256, MINB) k_filter_fused(const FilterBatch batch) {
   const FilterArgs &a = batch.col[blockIdx.y];
-  using C = FusedCfg<W>;
+  using C = AsyncCfg<W>;
+  using F = FusedCfg<W>;
+  constexpr int RPC = F::RPC, CPR = F::CPR, RPJ = F::RPJ;
+  static_assert(RPC * C::ITERS <= 32, "the per-pass selection bits of a lane must fit one register");
   extern __shared__ __align__(16) uint8_t s_raw[];
-  __shared__ uint64_t s_m[8][TILE_WORDS];
-  __shared__ uint32_t s_p[8][TILE_WORDS];
+  __shared__ uint32_t s_h[8][2 * TILE_WORDS];   // the tile's mask as 32-bit halves ...
+  __shared__ uint32_t s_hp[8][2 * TILE_WORDS];  // ... and the exclusive popcount prefix of every half
   __shared__ uint32_t s_win[8][36];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int lr = lane * RPC / CPR;               // lane's row offset inside a chunk round
+  const int lr_half = lr >> 5, lr_bit = lr & 31; // (W <= 8: fixed for every round; W >= 16: lr < 32, lr_half = 0)
   uint4 *buf = reinterpret_cast<uint4 *>(s_raw + (size_t)wid * C::PASS_BYTES);
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -471,89 +476,87 @@ __global__ void __launch_bounds__(256, 6) k_filter_fused(const FilterBatch batch
       end_next = __ldg(a.tile_off + tn + 1);
     }
     if (cnt == 0) continue;  // warp-uniform
-    const uint32_t c = __popcll(m);
-    uint32_t incl = c;
+    // lane h owns half h of the tile's 32 halves: its popcount prefix is one 32-lane scan
+    const uint32_t src_lo = __shfl_sync(ACU_FULL_MASK, (uint32_t)m, lane >> 1);
+    const uint32_t src_hi = __shfl_sync(ACU_FULL_MASK, (uint32_t)(m >> 32), lane >> 1);
+    const uint32_t hv = (lane & 1) ? src_hi : src_lo;
+    const uint32_t hc = __popc(hv);
+    uint32_t hincl = hc;
 #pragma unroll
-    for (int o = 1; o < TILE_WORDS; o <<= 1) {
-      uint32_t y = __shfl_up_sync(ACU_FULL_MASK, incl, o);
-      if (lane >= o) incl += y;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(ACU_FULL_MASK, hincl, o);
+      if (lane >= o) hincl += y;
     }
-    if (lane < TILE_WORDS) { s_m[wid][lane] = m; s_p[wid][lane] = incl - c; }
-    // the validity words of the tile go in flight before the value loads (consumed after them)
+    s_h[wid][lane] = hv;
+    s_hp[wid][lane] = hincl - hc;
+    // the validity word of the tile goes in flight before the value loads (consumed after them)
     uint64_t v = 0;
-    if (vsrc && c) v = ld_bits64(vsrc, a.voff + t * TILE_ROWS + (int64_t)lane * 64, a.voff + a.vlen);
+    if (vsrc && m) v = ld_bits64(vsrc, a.voff + t * TILE_ROWS + (int64_t)lane * 64, a.voff + a.vlen);
     __syncwarp();
     const uint8_t *src = a.values + (size_t)t * TILE_ROWS * W;
     uint8_t *dst = a.out + (size_t)out0 * W;
 #pragma unroll 1
     for (int pass = 0; pass < C::PASSES; ++pass) {
-      const int row_base = pass * C::PASS_ROWS;
-      const uint8_t *psrc = src + (size_t)pass * C::PASS_BYTES + (size_t)lane * 32;
-      // ---- issue: every needed 16-byte half of the pass goes in flight (landing layout [round][half][lane]: conflict-free LDS.128) ----
+      const int half_base = (pass * C::PASS_ROWS) >> 5;  // first 32-bit half of the pass
+      const uint8_t *psrc = src + ((size_t)pass * C::CPP + lane) * 16;
+      const uint32_t *hh = &s_h[wid][half_base + lr_half];
+      uint32_t sel = 0;  // RPC selection bits per round, packed
+      // ---- issue: every needed chunk of the pass goes in flight (coalesced: lane <-> consecutive 16-byte chunks) ----
 #pragma unroll
-      for (int j = 0; j < C::ROUNDS; ++j) {
-        const int r = row_base + (j * 32 + lane) * C::RPU;
-        const uint32_t bits = (uint32_t)(s_m[wid][r >> 6] >> (r & 63)) & C::UNIT_MASK;
-        if (W == 32 ? bits : (bits & C::HALF_MASK)) cp_async16(buf + (j * 2 + 0) * 32 + lane, psrc + (size_t)j * 1024);
-        if (W == 32 ? bits : (bits >> C::HALF)) cp_async16(buf + (j * 2 + 1) * 32 + lane, psrc + (size_t)j * 1024 + 16);
+      for (int j = 0; j < C::ITERS; ++j) {
+        constexpr int dummy = 0; (void)dummy;
+        const int r0 = j * RPJ;                                  // compile-time row offset of the round inside the pass
+        const uint32_t bits = (hh[r0 >> 5] >> ((r0 & 31) + lr_bit)) & F::CHUNK_MASK;
+        sel |= bits << (j * RPC);
+        if (bits) cp_async16(buf + j * 32 + lane, psrc + (size_t)j * 512);
       }
       cp_async_wait_all();
       __syncwarp();
       // ---- consume: rank and store the selected elements ----
+      const uint32_t *hp = &s_hp[wid][half_base + lr_half];
 #pragma unroll
-      for (int j = 0; j < C::ROUNDS; ++j) {
-        const int r = row_base + (j * 32 + lane) * C::RPU;
-        const uint64_t word = s_m[wid][r >> 6];
-        uint32_t bits = (uint32_t)(word >> (r & 63)) & C::UNIT_MASK;
+      for (int j = 0; j < C::ITERS; ++j) {
+        const uint32_t bits = (sel >> (j * RPC)) & F::CHUNK_MASK;
         if (!bits) continue;
-        const uint32_t rank = s_p[wid][r >> 6] + __popcll(word & ((1ull << (r & 63)) - 1ull));
+        const int r0 = j * RPJ;
+        const int sh = (r0 & 31) + lr_bit;
+        const uint32_t rank = hp[r0 >> 5] + __popc(hh[r0 >> 5] & ((1u << sh) - 1u));
+        const uint4 x = buf[j * 32 + lane];
         if constexpr (W == 8) {
-          const uint4 v0 = buf[(j * 2 + 0) * 32 + lane], v1 = buf[(j * 2 + 1) * 32 + lane];
           uint64_t *o = reinterpret_cast<uint64_t *>(dst) + rank;
-          if (bits & 1u) *o++ = (uint64_t)v0.x | ((uint64_t)v0.y << 32);
-          if (bits & 2u) *o++ = (uint64_t)v0.z | ((uint64_t)v0.w << 32);
-          if (bits & 4u) *o++ = (uint64_t)v1.x | ((uint64_t)v1.y << 32);
-          if (bits & 8u) *o = (uint64_t)v1.z | ((uint64_t)v1.w << 32);
+          if (bits & 1u) *o++ = (uint64_t)x.x | ((uint64_t)x.y << 32);
+          if (bits & 2u) *o = (uint64_t)x.z | ((uint64_t)x.w << 32);
         } else if constexpr (W == 4) {
-          const uint4 v0 = buf[(j * 2 + 0) * 32 + lane], v1 = buf[(j * 2 + 1) * 32 + lane];
           uint32_t *o = reinterpret_cast<uint32_t *>(dst) + rank;
-          if (bits & 1u) *o++ = v0.x;
-          if (bits & 2u) *o++ = v0.y;
-          if (bits & 4u) *o++ = v0.z;
-          if (bits & 8u) *o++ = v0.w;
-          if (bits & 16u) *o++ = v1.x;
-          if (bits & 32u) *o++ = v1.y;
-          if (bits & 64u) *o++ = v1.z;
-          if (bits & 128u) *o = v1.w;
-        } else if constexpr (W == 16) {
-          uint64_t *o = reinterpret_cast<uint64_t *>(dst + (size_t)rank * 16);
-          if (bits & 1u) { const uint4 x = buf[(j * 2 + 0) * 32 + lane]; o[0] = (uint64_t)x.x | ((uint64_t)x.y << 32); o[1] = (uint64_t)x.z | ((uint64_t)x.w << 32); o += 2; }
-          if (bits & 2u) { const uint4 x = buf[(j * 2 + 1) * 32 + lane]; o[0] = (uint64_t)x.x | ((uint64_t)x.y << 32); o[1] = (uint64_t)x.z | ((uint64_t)x.w << 32); }
-        } else if constexpr (W == 32) {
-          const uint4 v0 = buf[(j * 2 + 0) * 32 + lane], v1 = buf[(j * 2 + 1) * 32 + lane];
-          uint64_t *o = reinterpret_cast<uint64_t *>(dst + (size_t)rank * 32);
-          o[0] = (uint64_t)v0.x | ((uint64_t)v0.y << 32);
-          o[1] = (uint64_t)v0.z | ((uint64_t)v0.w << 32);
-          o[2] = (uint64_t)v1.x | ((uint64_t)v1.y << 32);
-          o[3] = (uint64_t)v1.z | ((uint64_t)v1.w << 32);
-        } else {  // W = 1, 2: walk the set bits, elements straight from the landing buffer
-          const uint8_t *lb = reinterpret_cast<const uint8_t *>(buf);
-          uint8_t *o = dst + (size_t)rank * W;
-          while (bits) {
-            const int e = __ffs((int)bits) - 1;
-            bits &= bits - 1;
-            const int byte = e * W;
-            const uint8_t *p = lb + ((size_t)((j * 2 + (byte >> 4)) * 32 + lane) << 4) + (byte & 15);
-            if constexpr (W == 2) *reinterpret_cast<uint16_t *>(o) = *reinterpret_cast<const uint16_t *>(p);
-            else *o = *p;
-            o += W;
-          }
+          if (bits & 1u) *o++ = x.x;
+          if (bits & 2u) *o++ = x.y;
+          if (bits & 4u) *o++ = x.z;
+          if (bits & 8u) *o = x.w;
+        } else if constexpr (W == 2) {
+          uint16_t *o = reinterpret_cast<uint16_t *>(dst) + rank;
+          const uint16_t *ve = reinterpret_cast<const uint16_t *>(&x);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if ((bits >> e) & 1u) *o++ = ve[e];
+        } else if constexpr (W == 1) {
+          uint8_t *o = dst + rank;
+          const uint8_t *ve = reinterpret_cast<const uint8_t *>(&x);
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if ((bits >> e) & 1u) *o++ = ve[e];
+        } else {
+          const int half = lane % CPR;  // (j*32 + lane) % CPR, CPR divides 32
+          uint64_t *o = reinterpret_cast<uint64_t *>(dst + (size_t)rank * W + half * 16);
+          o[0] = (uint64_t)x.x | ((uint64_t)x.y << 32);
+          o[1] = (uint64_t)x.z | ((uint64_t)x.w << 32);
         }
       }
       __syncwarp();  // the landing buffer is reused by the next pass / tile
     }
     // ---- validity: PEXT(source validity, mask) per word, assembled in a warp-private window ----
     if (vsrc) {
+      const uint32_t c = __popcll(m);               // lanes >= 16 hold m = 0
+      const uint32_t wpref = s_hp[wid][(2 * lane) & 31];  // exclusive prefix of word `lane` = prefix of its low half
       const uint64_t bits = c ? pext64_sparse(v, m, c) : 0ull;
       valid_cnt += __popcll(bits);
       const uint32_t lead = (uint32_t)(out0 & 31);
@@ -561,7 +564,7 @@ __global__ void __launch_bounds__(256, 6) k_filter_fused(const FilterBatch batch
       for (uint32_t i = lane; i < nwords; i += 32) s_win[wid][i] = 0;
       __syncwarp();
       if (c) {
-        const uint32_t p = lead + incl - c;
+        const uint32_t p = lead + wpref;
         const uint32_t sh = p & 31;
         atomicOr(&s_win[wid][p >> 5], (uint32_t)(bits << sh));
         if (sh + c > 32) {
@@ -698,7 +701,17 @@ acu_status launch_filter(acu_ctx *ctx, const FilterBatch &fb, int n_cols) {
       ACU_LAUNCH_TIMED(ctx, ACU_K_FILTER, (k_filter_values_async<W>), dim3(gx, n_cols), 256, smem, fb);
       return ACU_OK;
     }
-    constexpr size_t smem = 8 * (size_t)FusedCfg<W>::PASS_BYTES;
+    constexpr size_t smem = 8 * (size_t)AsyncCfg<W>::PASS_BYTES;
+    if constexpr (W == 8) {  // experiment hook: 5 resident CTAs (48 registers, no spills) instead of 6 (40 registers)
+      static const char *minb = getenv("ACU_FILTER_MINB");
+      if (minb && atoi(minb) == 5) {
+        if (ctx->occupancy.find(reinterpret_cast<const void *>(k_filter_fused<W, 5>)) == ctx->occupancy.end())
+          ACU_CUDA(ctx, cudaFuncSetAttribute(k_filter_fused<W, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int gx5 = acu_wave_grid(ctx, k_filter_fused<W, 5>, 256, smem, (fa.n_tiles + 7) / 8);
+        ACU_LAUNCH_TIMED(ctx, ACU_K_FILTER, (k_filter_fused<W, 5>), dim3(gx5, n_cols), 256, smem, fb);
+        return ACU_OK;
+      }
+    }
     if (ctx->occupancy.find(reinterpret_cast<const void *>(k_filter_fused<W>)) == ctx->occupancy.end())
       ACU_CUDA(ctx, cudaFuncSetAttribute(k_filter_fused<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int gx = acu_wave_grid(ctx, k_filter_fused<W>, 256, smem, (fa.n_tiles + 7) / 8);

@@ -66,10 +66,19 @@ __global__ void k_res_reset(unsigned long long *res, int slots) {
   if (i < slots) res[i] = ((i % RES_SLOTS) == RES_ERR_INDEX || (i % RES_SLOTS) == RES_ERR2) ? ~0ull : 0ull;
 }
 
+// The result blocks are kept CLEAN between calls: every fetch queues their re-initialisation right behind its D2H copy
+// (off the critical path of the next call), so a call's "reset" is normally free — no launch in front of its kernels.
+// res_clean is dropped by the first reset after a fetch; a call that failed between its reset and its fetch leaves
+// res_clean false and the next reset launches k_res_reset itself. res_dirty_blocks = blocks possibly written since.
 acu_status acu_res_reset_n(acu_ctx *ctx, int blocks) {
   if (blocks < 1) blocks = 1;
   if (blocks > RES_BLOCKS) blocks = RES_BLOCKS;
-  ACU_LAUNCH(ctx, k_res_reset, 1, blocks * RES_SLOTS, 0, ctx->d_res, blocks * RES_SLOTS);
+  if (!ctx->res_clean) {
+    const int n = blocks > ctx->res_dirty_blocks ? blocks : ctx->res_dirty_blocks;
+    ACU_LAUNCH(ctx, k_res_reset, 1, n * RES_SLOTS, 0, ctx->d_res, n * RES_SLOTS);
+  }
+  ctx->res_clean = false;
+  ctx->res_dirty_blocks = blocks;
   return ACU_OK;
 }
 
@@ -78,7 +87,11 @@ acu_status acu_res_fetch_n(acu_ctx *ctx, int blocks) {
   if (blocks > RES_BLOCKS) blocks = RES_BLOCKS;
   ACU_CUDA(ctx, cudaMemcpyAsync(ctx->h_res, ctx->d_res, (size_t)blocks * RES_SLOTS * sizeof(unsigned long long),
                                 cudaMemcpyDeviceToHost, ctx->stream));
+  const int n = blocks > ctx->res_dirty_blocks ? blocks : ctx->res_dirty_blocks;
+  ACU_LAUNCH(ctx, k_res_reset, 1, n * RES_SLOTS, 0, ctx->d_res, n * RES_SLOTS);  // stream-ordered behind the copy
   ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->res_clean = true;
+  ctx->res_dirty_blocks = 0;
   acu_kstats_drain(ctx);
   return ACU_OK;
 }

@@ -324,6 +324,32 @@ acu_status acu_neg(acu_ctx *ctx, acu_dtype dtype, int32_t checked, const acu_arr
 acu_status acu_cmp(acu_ctx *ctx, acu_dtype dtype, acu_cmp_op op, const acu_array *a,
                    const acu_array *b, acu_array_out *out);
 
+/* The same eight comparisons on variable-width operands.
+ * acu_bytes_array = GenericByteArray (Utf8 / Binary: offset_bytes 4, LargeUtf8 / LargeBinary: 8; ArrayOrd cmp.rs:783-801):
+ * `offsets` points at the offset of logical row 0 (nulls.len + 1 entries), `nulls` carries len / validity / null_count /
+ * is_scalar (its `values` member is ignored). acu_view_array = GenericByteViewArray (Utf8View / BinaryView; ArrayOrd
+ * cmp.rs:803-898): `views` = 16 bytes per row (length u32, then 12 inline bytes, or 4-byte prefix + buffer index u32 + offset
+ * u32: arrow-data/src/byte_view.rs), `buffers` = a HOST array of n_buffers DEVICE pointers to the data buffers. Bytes compare
+ * like Rust's `&[u8]` (lexicographic on unsigned bytes, then length). Equality of a view array against a non-null constant of
+ * at most 4 bytes takes the reference's short-constant path (eq_inline_scalar, cmp.rs:405-435: one masked 64-bit compare per
+ * view). Null handling, result layout and errors exactly as acu_cmp. */
+typedef struct acu_bytes_array {
+  const void *offsets;
+  const uint8_t *data;
+  acu_array nulls;
+} acu_bytes_array;
+typedef struct acu_view_array {
+  const void *views;
+  const uint8_t *const *buffers;
+  int32_t n_buffers;
+  int32_t reserved;
+  acu_array nulls;
+} acu_view_array;
+acu_status acu_cmp_bytes(acu_ctx *ctx, int32_t offset_bytes, acu_cmp_op op, const acu_bytes_array *l,
+                         const acu_bytes_array *r, acu_array_out *out);
+acu_status acu_cmp_byte_view(acu_ctx *ctx, acu_cmp_op op, const acu_view_array *l, const acu_view_array *r,
+                             acu_array_out *out);
+
 /* ------------------------------------------------------------------------- */
 /* cast — arrow-cast/src/cast/mod.rs                                         */
 /* ------------------------------------------------------------------------- */
@@ -520,6 +546,12 @@ acu_status acu_comm_destroy(acu_ctx *ctx);
 acu_status acu_comm_allreduce_aggregates(acu_ctx *ctx, acu_dtype dtype, acu_agg_op op,
                                          uint64_t *partial_bits, int64_t *valid_counts,
                                          int32_t n);
+/* acu_aggregate over this rank's shard combined over all ranks in ONE call with ONE synchronisation: the partial stays in
+ * HBM, a one-thread kernel re-encodes it (identity for a shard without valid rows, totalOrder key for float / signed
+ * min / max), NCCL reduces {value, valid_count} in place on the ctx stream, and only the final pair crosses to the host
+ * (no host bounce between the reduction kernel and the collective). Without a communicator it is acu_aggregate. */
+acu_status acu_aggregate_allreduce(acu_ctx *ctx, acu_dtype dtype, acu_agg_op op, const acu_array *a,
+                                   uint64_t *out_bits, int64_t *out_valid_count);
 /* Sum int64 scalars across ranks (row counts, null counts). */
 acu_status acu_comm_allreduce_i64_sum(acu_ctx *ctx, int64_t *values, int32_t n);
 

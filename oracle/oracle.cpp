@@ -644,8 +644,10 @@ inline uint64_t side_bits(const acu_array *s, int64_t i, int64_t len) {  // bit_
   return load_bits(s->validity, s->validity_offset + i, s->validity_offset + len);
 }
 
-template <class T>
-acu_status cmp_typed(acu_cmp_op op, const acu_array *l, const acu_array *r, acu_array_out *out) {
+// compare_op (cmp.rs:220-382) for any operand kind: `l` / `r` carry len / validity / scalar-ness, `cmp_vals(len, out)` fills
+// the value bits through apply() (cmp.rs:438-502).
+template <class V>
+acu_status cmp_generic(acu_cmp_op op, const acu_array *l, const acu_array *r, acu_array_out *out, V &&cmp_vals) {
   const bool ls = l->is_scalar != 0, rs = r->is_scalar != 0;
   if (l->len != r->len && !ls && !rs)  // cmp.rs:228-232
     return fail(ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0,
@@ -660,7 +662,7 @@ acu_status cmp_typed(acu_cmp_op op, const acu_array *l, const acu_array *r, acu_
   const size_t obytes = acu_bitmap_bytes(len);
   auto values = [&]() {
     if (l->len == 0 || r->len == 0) memset(ov, 0, obytes);  // apply returns None => new_unset
-    else cmp_values<T>(op, l, r, len, ov);
+    else cmp_vals(len, ov);
   };
   auto new_null_bool = [&]() {  // BooleanArray::new_null(len)
     memset(ov, 0, obytes);
@@ -722,6 +724,86 @@ acu_status cmp_typed(acu_cmp_op op, const acu_array *l, const acu_array *r, acu_
     values();
   }
   return ACU_OK;
+}
+
+template <class T>
+acu_status cmp_typed(acu_cmp_op op, const acu_array *l, const acu_array *r, acu_array_out *out) {
+  return cmp_generic(op, l, r, out, [&](int64_t len, uint8_t *ov) { cmp_values<T>(op, l, r, len, ov); });
+}
+
+// apply() over any item accessor: eq / lt closures on logical row indices (cmp.rs:481-488)
+template <class EQ, class LT>
+void cmp_rows(acu_cmp_op op, int64_t len, bool ls, bool rs, uint8_t *out, EQ &&eq, LT &&lt) {
+  auto L = [&](int64_t i) { return ls ? (int64_t)0 : i; };
+  auto R = [&](int64_t i) { return rs ? (int64_t)0 : i; };
+  switch (op) {
+    case ACU_EQ: case ACU_NOT_DISTINCT: collect_bool(len, false, out, [&](int64_t i) { return eq(L(i), R(i)); }); break;
+    case ACU_NEQ: case ACU_DISTINCT: collect_bool(len, true, out, [&](int64_t i) { return eq(L(i), R(i)); }); break;
+    case ACU_LT: collect_bool(len, false, out, [&](int64_t i) { return lt(false, L(i), R(i)); }); break;
+    case ACU_LT_EQ: collect_bool(len, true, out, [&](int64_t i) { return lt(true, R(i), L(i)); }); break;   // !(r < l)
+    case ACU_GT: collect_bool(len, false, out, [&](int64_t i) { return lt(true, R(i), L(i)); }); break;      // r < l
+    case ACU_GT_EQ: collect_bool(len, true, out, [&](int64_t i) { return lt(false, L(i), R(i)); }); break;  // !(l < r)
+  }
+}
+
+// `&[u8]` ordering of Rust: lexicographic on unsigned bytes, then length (cmp.rs:783-801 is_eq / is_lt)
+inline bool bytes_eq(const uint8_t *a, int64_t la, const uint8_t *b, int64_t lb) { return la == lb && (la == 0 || memcmp(a, b, (size_t)la) == 0); }
+inline bool bytes_lt(const uint8_t *a, int64_t la, const uint8_t *b, int64_t lb) {
+  const int64_t n = la < lb ? la : lb;
+  const int c = n ? memcmp(a, b, (size_t)n) : 0;
+  return c != 0 ? c < 0 : la < lb;
+}
+
+// GenericByteViewArray item comparison (cmp.rs:803-898). A view is 16 bytes: length u32, then 12 inline bytes, or
+// prefix (4 B) + buffer index u32 + offset u32 (arrow-data/src/byte_view.rs).
+struct ViewSide {
+  const uint8_t *views;             // 16 bytes per row
+  const uint8_t *const *buffers;    // data buffers
+  int32_t n_buffers;
+};
+inline unsigned __int128 view_at(const ViewSide &s, int64_t i) {
+  unsigned __int128 v;
+  memcpy(&v, s.views + 16 * i, 16);
+  return v;
+}
+inline const uint8_t *view_bytes(const ViewSide &s, int64_t i, uint32_t *len) {  // GenericByteViewArray::value_unchecked
+  const uint8_t *v = s.views + 16 * i;
+  memcpy(len, v, 4);
+  if (*len <= 12) return v + 4;
+  uint32_t buf, off;
+  memcpy(&buf, v + 8, 4);
+  memcpy(&off, v + 12, 4);
+  return s.buffers[buf] + off;
+}
+inline unsigned __int128 bswap128(unsigned __int128 x) {
+  const uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
+  return ((unsigned __int128)__builtin_bswap64(lo) << 64) | (unsigned __int128)__builtin_bswap64(hi);
+}
+inline unsigned __int128 inline_key_fast(unsigned __int128 raw) {  // byte_view_array.rs:872-874
+  return (bswap128(raw) << 32) | (unsigned __int128)(uint32_t)raw;
+}
+inline bool view_is_eq(const ViewSide &l, int64_t li, const ViewSide &r, int64_t ri) {  // cmp.rs:810-862
+  const unsigned __int128 lv = view_at(l, li), rv = view_at(r, ri);
+  if (l.n_buffers == 0 && r.n_buffers == 0) return lv == rv;
+  if (lv == rv && (uint32_t)lv <= 12) return true;
+  const uint32_t ll = (uint32_t)lv, rl = (uint32_t)rv;
+  if (ll != rl) return false;
+  if (ll == 0) return true;
+  if ((uint32_t)(lv >> 32) != (uint32_t)(rv >> 32)) return false;
+  if (ll <= 12) return false;
+  uint32_t a, b;
+  const uint8_t *pa = view_bytes(l, li, &a), *pb = view_bytes(r, ri, &b);
+  return memcmp(pa, pb, ll) == 0;
+}
+inline bool view_is_lt(const ViewSide &l, int64_t li, const ViewSide &r, int64_t ri) {  // cmp.rs:864-893
+  const unsigned __int128 lv = view_at(l, li), rv = view_at(r, ri);
+  if (l.n_buffers == 0 && r.n_buffers == 0) return inline_key_fast(lv) < inline_key_fast(rv);
+  if ((uint32_t)lv <= 12 && (uint32_t)rv <= 12) return inline_key_fast(lv) < inline_key_fast(rv);
+  const uint32_t lp = (uint32_t)(lv >> 32), rp = (uint32_t)(rv >> 32);
+  if (lp != rp) return __builtin_bswap32(lp) < __builtin_bswap32(rp);
+  uint32_t a, b;
+  const uint8_t *pa = view_bytes(l, li, &a), *pb = view_bytes(r, ri, &b);
+  return bytes_lt(pa, a, pb, b);
 }
 
 // ---- cast: arrow-cast/src/cast/mod.rs:2550-2614 + num-traits 0.2.19 cast -----------------
@@ -1424,6 +1506,60 @@ acu_status orc_zip(int32_t elem_bytes, const acu_array *mask, const acu_array *t
     if (nc > 0) { out->has_validity = 1; out->null_count = nc; }
   }
   return ACU_OK;
+}
+
+// cmp::{eq..not_distinct} on GenericByteArray operands (Utf8 / Binary with i32 offsets, Large* with i64): cmp.rs:220-382 with
+// ArrayOrd for &GenericByteArray (:783-801). *_nulls carry len / validity / is_scalar of each side.
+acu_status orc_cmp_bytes(int32_t offset_bytes, acu_cmp_op op, const void *l_offsets, const uint8_t *l_data, const acu_array *l_nulls,
+                         const void *r_offsets, const uint8_t *r_data, const acu_array *r_nulls, acu_array_out *out) {
+  auto off = [&](const void *o, int64_t i) -> int64_t {
+    return offset_bytes == 4 ? (int64_t)static_cast<const int32_t *>(o)[i] : static_cast<const int64_t *>(o)[i];
+  };
+  const bool ls = l_nulls->is_scalar != 0, rs = r_nulls->is_scalar != 0;
+  return cmp_generic(op, l_nulls, r_nulls, out, [&](int64_t len, uint8_t *ov) {
+    cmp_rows(op, len, ls, rs, ov,
+             [&](int64_t i, int64_t j) { return bytes_eq(l_data + off(l_offsets, i), off(l_offsets, i + 1) - off(l_offsets, i),
+                                                         r_data + off(r_offsets, j), off(r_offsets, j + 1) - off(r_offsets, j)); },
+             [&](bool swapped, int64_t i, int64_t j) {  // swapped: i indexes the RIGHT operand
+               const void *ao = swapped ? r_offsets : l_offsets, *bo = swapped ? l_offsets : r_offsets;
+               const uint8_t *ad = swapped ? r_data : l_data, *bd = swapped ? l_data : r_data;
+               return bytes_lt(ad + off(ao, i), off(ao, i + 1) - off(ao, i), bd + off(bo, j), off(bo, j + 1) - off(bo, j));
+             });
+  });
+}
+
+// cmp on GenericByteViewArray operands (Utf8View / BinaryView): cmp.rs:803-898, plus the inline-constant fast path
+// eq_inline_scalar (:405-435), which yields the same bits as the generic path for valid views.
+acu_status orc_cmp_byte_view(acu_cmp_op op, const void *l_views, const uint8_t *const *l_buffers, int32_t l_n_buffers,
+                             const acu_array *l_nulls, const void *r_views, const uint8_t *const *r_buffers, int32_t r_n_buffers,
+                             const acu_array *r_nulls, acu_array_out *out) {
+  const ViewSide L{static_cast<const uint8_t *>(l_views), l_buffers, l_n_buffers}, R{static_cast<const uint8_t *>(r_views), r_buffers, r_n_buffers};
+  const bool ls = l_nulls->is_scalar != 0, rs = r_nulls->is_scalar != 0;
+  // eq_inline_scalar (cmp.rs:282-300, :405-435): == / != of an array against a non-null constant of <= 4 bytes compares the
+  // low 64 bits of every view (length + prefix) under a mask; nulls = the array side's (when it has any)
+  if ((op == ACU_EQ || op == ACU_NEQ) && ls != rs) {
+    const acu_array *arr = ls ? r_nulls : l_nulls, *sc = ls ? l_nulls : r_nulls;
+    const ViewSide &A = ls ? R : L, &S = ls ? L : R;
+    if (sc->len >= 1 && !(sc->validity && resolve_null_count(sc) > 0)) {
+      const unsigned __int128 nv = view_at(S, 0);
+      const uint32_t needle_len = (uint32_t)nv;
+      if (needle_len <= 4) {
+        const uint64_t significant = ~0ull >> (32 - needle_len * 8);
+        const uint64_t needle = (uint64_t)nv & significant;
+        const int64_t len = arr->len;
+        out->len = len;
+        out->has_validity = 0;
+        out->null_count = 0;
+        collect_bool(len, op == ACU_NEQ, static_cast<uint8_t *>(out->values), [&](int64_t i) { return ((uint64_t)view_at(A, i) & significant) == needle; });
+        if (arr->validity && resolve_null_count(arr) > 0) clone_nulls(arr, len, out);
+        return ACU_OK;
+      }
+    }
+  }
+  return cmp_generic(op, l_nulls, r_nulls, out, [&](int64_t len, uint8_t *ov) {
+    cmp_rows(op, len, ls, rs, ov, [&](int64_t i, int64_t j) { return view_is_eq(L, i, R, j); },
+             [&](bool swapped, int64_t i, int64_t j) { return swapped ? view_is_lt(R, i, L, j) : view_is_lt(L, i, R, j); });
+  });
 }
 
 }  // extern "C"

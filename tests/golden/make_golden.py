@@ -537,6 +537,61 @@ case("zip_primitive_scalar_mask_nulls_treated_as_false", Z + ":1038", "zip", mas
 case("zip_length_mismatch", Z + ":128-132", "zip", mask=arr("bool", [True, False]), truthy=arr("int32", [1, 2, 3]), falsy=arr("int32", [1, 2]),
      expect_error="Invalid argument error: all arrays should have the same length")
 
+# =========================================================================================
+# cmp on Binary / Utf8 / Utf8View — arrow-ord/src/comparison.rs (test_binary!, test_utf8!, test_utf8_view! macros)
+# byte strings are lists of ints when not ASCII
+# =========================================================================================
+CP = "arrow-ord/src/comparison.rs"
+FF8, FF9 = [0xff, 0xf8], [0xff, 0xf9]
+BL = ["arrow", "datafusion", "flight", "parquet"]
+for name, line, op, left, right, exp in [
+    ("binary_array_eq", 968, "eq", ["arrow", "arrow", "arrow", "arrow", FF8], ["arrow", "parquet", "datafusion", "flight", FF8], [True, False, False, False, True]),
+    ("binary_array_neq", 984, "neq", ["arrow", "arrow", "arrow", "arrow", FF8], ["arrow", "parquet", "datafusion", "flight", FF9], [False, True, True, True, True]),
+    ("binary_array_lt", 999, "lt", BL + [FF8], ["flight"] * 4 + [FF9], [True, True, False, False, True]),
+    ("binary_array_lt_eq", 1014, "lt_eq", BL + [FF8], ["flight"] * 4 + [[0xff, 0xf8, 0xf9]], [True, True, True, False, True]),
+    ("binary_array_gt", 1029, "gt", BL + [FF9], ["flight"] * 4 + [FF8], [False, False, False, True, True]),
+    ("binary_array_gt_eq", 1044, "gt_eq", BL + [FF8], ["flight"] * 4 + [FF8], [False, False, True, True, True]),
+]:
+    for large in (False, True):
+        case(name + ("_large" if large else ""), f"{CP}:{line}", "cmp_bytes", cmp=op, large=large, left={"bytes": left}, right={"bytes": right}, expect={"data": exp})
+for name, line, op, left, right, exp in [
+    ("binary_array_eq_scalar", 976, "eq", ["arrow", "parquet", "datafusion", "flight", FF8], "arrow", [True, False, False, False, False]),
+    ("binary_array_neq_scalar", 991, "neq", ["arrow", "parquet", "datafusion", "flight", FF8], "arrow", [False, True, True, True, True]),
+    ("binary_array_lt_scalar", 1006, "lt", BL + [FF8], "flight", [True, True, False, False, False]),
+    ("binary_array_lt_eq_scalar", 1021, "lt_eq", BL + [FF8], "flight", [True, True, True, False, False]),
+    ("binary_array_gt_scalar", 1036, "gt", BL + [FF8], "flight", [False, False, False, True, True]),
+    ("binary_array_gt_eq_scalar", 1051, "gt_eq", BL + [FF8], "flight", [False, False, True, True, True]),
+]:
+    case(name, f"{CP}:{line}", "cmp_bytes", cmp=op, large=False, left={"bytes": left}, right={"bytes": [right], "scalar": True}, expect={"data": exp})
+case("binary_eq_scalar_on_slice", CP + ":937", "cmp_bytes", cmp="eq", large=False, left={"bytes": ["hi", None, "hello", "world"], "slice": [1, 3]},
+     right={"bytes": ["hello"], "scalar": True}, expect={"data": [None, True, False]})
+case("utf8_eq_scalar_on_slice", CP + ":1147", "cmp_bytes", cmp="eq", large=False, left={"bytes": ["hi", None, "hello", "world", ""], "slice": [1, 4]},
+     right={"bytes": ["hello"], "scalar": True}, expect={"data": [None, True, False, False]})
+case("utf8_eq_empty_scalar_on_slice", CP + ":1157", "cmp_bytes", cmp="eq", large=False, left={"bytes": ["hi", None, "hello", "world", ""], "slice": [1, 4]},
+     right={"bytes": [""], "scalar": True}, expect={"data": [None, False, False, True]})
+UA = ["arrow", "arrow", "arrow", "arrow"]
+UB = ["arrow", "parquet", "datafusion", "flight"]
+for name, line, op, left, right, exp in [
+    ("utf8_array_eq", 1246, "eq", UA, UB, [True, False, False, False]), ("utf8_array_neq", 1282, "neq", UA, UB, [False, True, True, True]),
+    ("utf8_array_lt", 1318, "lt", BL, ["flight"] * 4, [True, True, False, False]), ("utf8_array_lt_eq", 1354, "lt_eq", BL, ["flight"] * 4, [True, True, True, False]),
+    ("utf8_array_gt", 1383, "gt", BL, ["flight"] * 4, [False, False, False, True]), ("utf8_array_gt_eq", 1419, "gt_eq", BL, ["flight"] * 4, [False, False, True, True]),
+]:
+    case(name, f"{CP}:{line}", "cmp_bytes", cmp=op, large=False, left={"bytes": left}, right={"bytes": right}, expect={"data": exp})
+    case(name + "_large", f"{CP}:{line}", "cmp_bytes", cmp=op, large=True, left={"bytes": left}, right={"bytes": right}, expect={"data": exp})
+LARGE_1, LARGE_2, SMALL_1, SMALL_2 = "prefix-larger than 12 bytes string", "prefix-larger but different string", "pref1", "pref2"
+TA1, TA2 = [LARGE_1, LARGE_1, SMALL_1, SMALL_1, LARGE_1], [LARGE_1, LARGE_2, SMALL_1, SMALL_2, SMALL_1]
+for name, line, op, exp in [("utf8_view_array_eq", 1253, "eq", [True, False, True, False, False]), ("utf8_view_array_neq", 1289, "neq", [False, True, False, True, True]),
+                            ("utf8_view_array_lt", 1325, "lt", [False, False, False, True, False]), ("utf8_view_array_lt_eq", 1361, "lt_eq", [True, False, True, True, False]),
+                            ("utf8_view_array_gt", 1390, "gt", [False, True, False, False, True]), ("utf8_view_array_gt_eq", 1426, "gt_eq", [True, True, True, False, True])]:
+    case(name, f"{CP}:{line}", "cmp_view", cmp=op, left={"bytes": TA1}, right={"bytes": TA2}, expect={"data": exp})
+for name, line, op, sc, exp in [
+    ("utf8_view_array_eq_large_scalar", 1267, "eq", LARGE_1, [True, False, False, False, False]), ("utf8_view_array_eq_small_scalar", 1274, "eq", SMALL_1, [False, False, True, False, True]),
+    ("utf8_view_array_neq_scalar", 1303, "neq", LARGE_1, [False, True, True, True, True]), ("utf8_view_array_lt_scalar", 1339, "lt", LARGE_1, [False, True, True, True, True]),
+    ("utf8_view_array_lt_scalar_small", 1346, "lt", SMALL_1, [False, False, False, False, False]), ("utf8_view_array_lt_eq_scalar", 1375, "lt_eq", LARGE_1, [True, True, True, True, True]),
+    ("utf8_view_array_gt_scalar", 1404, "gt", LARGE_1, [False, False, False, False, False]), ("utf8_view_array_gt_scalar_small", 1411, "gt", SMALL_1, [True, True, False, True, False]),
+    ("utf8_view_array_gt_eq_scalar", 1440, "gt_eq", LARGE_1, [True, False, False, False, False]), ("utf8_view_array_gt_eq_scalar_small", 1447, "gt_eq", SMALL_1, [True, True, True, True, True])]:
+    case(name, f"{CP}:{line}", "cmp_view", cmp=op, left={"bytes": TA2}, right={"bytes": [sc], "scalar": True}, expect={"data": exp})
+
 out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "vectors.json")
 with open(out, "w") as f:
     json.dump({"reference": "apache/arrow-rs 59.2.0 @ cd7c6b83", "cases": cases}, f, indent=0)

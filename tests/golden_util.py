@@ -77,6 +77,34 @@ def build_strings(spec):
     return offsets, data, nulls
 
 
+def _to_bytes(x):
+    if x is None:
+        return None
+    return x.encode() if isinstance(x, str) else bytes(x)
+
+
+def build_bytes_column(spec, large=False):
+    """{"bytes": [str | [ints] | None ...], "scalar": bool, "slice": [offset, len]} -> acu.Utf8Column"""
+    items = [_to_bytes(x) for x in spec["bytes"]]
+    offsets = np.zeros(len(items) + 1, dtype=np.int64 if large else np.int32)
+    for i, b in enumerate(items):
+        offsets[i + 1] = offsets[i] + len(b or b"")
+    data = np.frombuffer(b"".join(b or b"" for b in items) + b"\0" * 16, dtype=np.uint8).copy()
+    nulls = HostArray.from_list(abi.U8, [0 if b is not None else None for b in items])
+    nulls.values = np.zeros(0, np.uint8)
+    if "slice" in spec:
+        off, ln = spec["slice"]
+        offsets = offsets[off: off + ln + 1]
+        nulls = nulls.slice(off, ln)
+        nulls.values = np.zeros(0, np.uint8)
+    nulls.is_scalar = bool(spec.get("scalar"))
+    return acu.Utf8Column(offsets, data, nulls)
+
+
+def build_view_column(spec):
+    return acu.ViewColumn.from_values([_to_bytes(x) for x in spec["bytes"]], 64, scalar=bool(spec.get("scalar")))
+
+
 def strings_of(offsets, data, nulls):
     mask = nulls.valid_mask()
     out = []
@@ -162,6 +190,11 @@ def run_case(backend, c):
             return getattr(backend, op)(build_array(c["a"]))
         if op in ("and_", "or_", "and_not", "and_kleene", "or_kleene"):
             return getattr(backend, op)(build_array(c["a"]), build_array(c["b"]))
+        if op == "cmp_bytes":
+            return backend.cmp_bytes(getattr(abi, c["cmp"].upper()), build_bytes_column(c["left"], c.get("large", False)),
+                                     build_bytes_column(c["right"], c.get("large", False)))
+        if op == "cmp_view":
+            return backend.cmp_view(getattr(abi, c["cmp"].upper()), build_view_column(c["left"]), build_view_column(c["right"]))
         if op == "nullif":
             return backend.nullif(build_array(c["left"]), build_array(c["right"]))
         if op == "zip":

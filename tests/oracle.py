@@ -46,6 +46,8 @@ class Oracle:
             "orc_cast_numeric": [i32, i32, i32, P(abi.Array), P(abi.ArrayOut)],
             "orc_aggregate": [i32, i32, P(abi.Array), i32, P(u64), P(i64)],
             "orc_sum_checked": [i32, P(abi.Array), P(u64), P(i64)],
+            "orc_cmp_bytes": [i32, i32, vp, vp, P(abi.Array), vp, vp, P(abi.Array), P(abi.ArrayOut)],
+            "orc_cmp_byte_view": [i32, vp, P(vp), i32, P(abi.Array), vp, P(vp), i32, P(abi.Array), P(abi.ArrayOut)],
             "orc_nullif": [P(abi.Array), P(abi.Array), P(abi.ArrayOut)],
             "orc_zip": [i32, P(abi.Array), P(abi.Array), P(abi.Array), P(abi.ArrayOut)],
             "orc_generate_values": [i32, u64, i64, u64, vp, i64],
@@ -184,6 +186,29 @@ class Oracle:
         out, vals, valid = self._out(bitmap_bytes(n), n)
         ad, bd = acu.host_descriptor(a), acu.host_descriptor(b)
         self.check(self.lib.orc_cmp(a.dtype, op, C.byref(ad), C.byref(bd), C.byref(out)))
+        return self._result(out, vals, valid, BOOL)
+
+    # -- cmp on Utf8 / Binary (Utf8Column) and Utf8View / BinaryView (ViewColumn) operands -----------
+    def cmp_bytes(self, op, a, b):
+        """a, b: acu.Utf8Column (offsets, data, nulls); nulls.is_scalar marks a Datum scalar."""
+        assert a.offsets.dtype == b.offsets.dtype
+        n = max(a.nulls.length if not a.nulls.is_scalar else 0, b.nulls.length if not b.nulls.is_scalar else 0, 1)
+        out, vals, valid = self._out(bitmap_bytes(n), n)
+        ad, bd = acu.host_descriptor(a.nulls), acu.host_descriptor(b.nulls)
+        self.check(self.lib.orc_cmp_bytes(a.offsets.dtype.itemsize, op, a.offsets.ctypes.data, a.data.ctypes.data, C.byref(ad),
+                                          b.offsets.ctypes.data, b.data.ctypes.data, C.byref(bd), C.byref(out)))
+        return self._result(out, vals, valid, BOOL)
+
+    def cmp_view(self, op, a, b):
+        """a, b: acu.ViewColumn."""
+        n = max(a.length if not a.nulls.is_scalar else 0, b.length if not b.nulls.is_scalar else 0, 1)
+        out, vals, valid = self._out(bitmap_bytes(n), n)
+        ad, bd = acu.host_descriptor(a.nulls), acu.host_descriptor(b.nulls)
+        ab = (vp * max(len(a.buffers), 1))(*[x.ctypes.data for x in a.buffers])
+        bb = (vp * max(len(b.buffers), 1))(*[x.ctypes.data for x in b.buffers])
+        av, bv = np.ascontiguousarray(a.views), np.ascontiguousarray(b.views)
+        self.check(self.lib.orc_cmp_byte_view(op, av.ctypes.data, ab, len(a.buffers), C.byref(ad), bv.ctypes.data, bb, len(b.buffers),
+                                              C.byref(bd), C.byref(out)))
         return self._result(out, vals, valid, BOOL)
 
     # -- fused compare -> filter: by definition filter(values, cmp(a, b)) ------------------------
