@@ -560,6 +560,83 @@ class Context:
                     if p:
                         self.free(p)
 
+    # -- Arrow IPC stream -> HBM (arrow-ipc/src/reader.rs StreamReader) ---------------------------
+    def ipc_read_stream(self, stream_bytes, on_batch=None):
+        """StreamReader over an in-memory IPC stream: every RecordBatch body is ONE host->device copy and its columns are
+        views into that device buffer. Returns (schema, batches): schema = [(name, kind, width, dtype, nullable)], batches =
+        lists of downloaded columns (HostArray / Utf8Column) — or whatever `on_batch(columns_descriptor_array, rows)` returns
+        when given (the descriptors are only valid inside the callback)."""
+        buf = np.frombuffer(bytes(stream_bytes), dtype=np.uint8).copy()
+        h = C.c_void_p()
+        n = C.c_int32(0)
+        self.check(self.lib.acu_ipc_stream_open(self.h, buf.ctypes.data, len(buf), C.byref(h), C.byref(n)))
+        try:
+            schema = []
+            for i in range(n.value):
+                kind, width, dtype, nullable, name = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_char_p()
+                self.lib.acu_ipc_stream_field(h, i, C.byref(kind), C.byref(width), C.byref(dtype), C.byref(nullable), C.byref(name))
+                schema.append((name.value.decode(), kind.value, width.value, dtype.value, bool(nullable.value)))
+            batches = []
+            cols = (abi.Column * max(n.value, 1))()
+            while True:
+                rows = C.c_int64(0)
+                self.check(self.lib.acu_ipc_stream_next(self.h, h, cols, C.byref(rows)))
+                if rows.value < 0:
+                    break
+                if on_batch is not None:
+                    batches.append(on_batch(cols, rows.value))
+                    continue
+                out = []
+                for i, (name, kind, width, dtype, _) in enumerate(schema):
+                    c, m = cols[i], rows.value
+                    validity = self.d2h(c.array.validity, bitmap_bytes(m)) if c.array.validity else None
+                    nc = c.array.null_count if c.array.validity else 0
+                    if kind == abi.COL_BYTES:
+                        odt = np.int32 if width == 4 else np.int64
+                        offs = self.d2h(c.array.values, (m + 1) * width, odt)
+                        data = self.d2h(c.data, int(offs[-1]) if m else 0)
+                        out.append(Utf8Column(offs, data, HostArray(U8, np.zeros(0, np.uint8), m, validity, 0, 0, nc)))
+                    elif kind == abi.COL_BOOLEAN:
+                        out.append(HostArray(BOOL, self.d2h(c.array.values, bitmap_bytes(m)), m, validity, 0, 0, nc))
+                    else:
+                        out.append(HostArray(dtype, self.d2h(c.array.values, m * width, NP_DTYPES[dtype]), m, validity, 0, 0, nc))
+                batches.append(out)
+            return schema, batches
+        finally:
+            self.lib.acu_ipc_stream_close(self.h, h)
+
+    # -- concat / concat_batches (arrow-select/src/concat.rs:495-640) ---------------------------
+    def concat(self, columns):
+        """arrow::compute::concat(&[..]): columns = HostArrays or Utf8Columns of one type."""
+        cols, owned = self._upload_columns(columns) if columns else ((abi.Column * 1)(), [])
+        outs = None
+        try:
+            rows = sum(c.length for c in columns)
+            proto = columns[:1] if columns else [HostArray(U8, np.zeros(0, np.uint8), 0)]
+            caps = [sum(int(c.data.nbytes) for c in columns)] if columns and isinstance(columns[0], Utf8Column) else [0]
+            outs = self._alloc_column_outs(proto, max(rows, 1), caps)
+            self.check(self.lib.acu_concat(self.h, len(columns), cols, outs))
+            return self._download_columns(proto, outs)[0]
+        finally:
+            self._free_columns(owned, outs)
+
+    def concat_batches(self, batches):
+        """arrow::compute::concat_batches(schema, batches): batches = lists of columns (same schema)."""
+        ncols = len(batches[0]) if batches else 0
+        flat = [c for b in batches for c in b]
+        cols, owned = self._upload_columns(flat) if flat else ((abi.Column * 1)(), [])
+        outs = None
+        try:
+            rows = sum(b[0].length for b in batches) if ncols else 0
+            proto = list(batches[0]) if batches else []
+            caps = [sum(int(b[c].data.nbytes) for b in batches) if isinstance(proto[c], Utf8Column) else 0 for c in range(ncols)]
+            outs = self._alloc_column_outs(proto, max(rows, 1), caps) if ncols else (abi.ColumnOut * 1)()
+            n = C.c_int64(0)
+            self.check(self.lib.acu_concat_batches(self.h, len(batches), ncols, cols, outs, C.byref(n)))
+            return self._download_columns(proto, outs) if ncols else []
+        finally:
+            self._free_columns(owned, outs if ncols else None)
+
     def filter_record_batch(self, columns, predicate):
         """arrow::compute::filter_record_batch: one plan, every column, one synchronisation."""
         cols, owned = self._upload_columns(columns)

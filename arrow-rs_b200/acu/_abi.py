@@ -211,6 +211,12 @@ PROTOTYPES = {
     "acu_filter_record_batch": (i32, [vp, vp, i32, P(Column), P(ColumnOut)]),
     "acu_take_record_batch": (i32, [vp, i32, P(Column), P(Array), i32, i32, P(ColumnOut)]),
     "acu_aggregate_columns": (i32, [vp, i32, P(i32), P(i32), P(Array), P(u64), P(i64)]),
+    "acu_ipc_stream_open": (i32, [vp, vp, i64, P(vp), P(i32)]),
+    "acu_ipc_stream_field": (i32, [vp, i32, P(i32), P(i32), P(i32), P(i32), P(C.c_char_p)]),
+    "acu_ipc_stream_next": (i32, [vp, vp, P(Column), P(i64)]),
+    "acu_ipc_stream_close": (None, [vp, vp]),
+    "acu_concat": (i32, [vp, i32, P(Column), P(ColumnOut)]),
+    "acu_concat_batches": (i32, [vp, i32, i32, P(Column), P(ColumnOut), P(i64)]),
     "acu_bitmap_copy": (i32, [vp, vp, i64, vp, i64, i64, P(i64)]),
     "acu_bitmap_fill": (i32, [vp, vp, i64, i64, i32]),
     "acu_offsets_append": (i32, [vp, i32, vp, i64, i64, i64, vp, i64, P(i64), P(i64)]),

@@ -13,7 +13,6 @@
 //      offsets; i32 overflow reports the first running total above i32::MAX (take.rs:520-523);
 //   4. copy: one warp per 32 rows, each lane streams its row's bytes.
 #include <stdio.h>
-#include <stdlib.h>
 
 #include "bitmap.cuh"
 #include "internal.cuh"
@@ -500,200 +499,6 @@ __global__ void __launch_bounds__(BY_THREADS, 2) k_bytes_offsets_copy(const Byte
   }
 }
 
-// ---- pass 2, warp-centric (FAST layout: i32 offsets, 32-bit indices) ------------------------------------------------
-// k_bytes_offsets_copy above spends ~220 instructions per row on ~8-byte strings (divergent emitters, 64-bit arithmetic).
-// This kernel does the same work with uniform control flow: a CTA still owns BY_ROWS = 2048 output rows (so pass 1 and
-// the scan of the CTA totals are unchanged), but each of its 8 warps owns 256 consecutive rows, 8 per lane with lane ==
-// row % 32 — index loads, offset stores and validity words are naturally coalesced — and the only CTA barrier is the one
-// that turns the 8 warp totals into warp base offsets. Bytes: every row's first 16 bytes are fetched as five aligned
-// 32-bit words (predicated on holding a requested byte), funnel-shifted to the row start, masked to the row length,
-// funnel-shifted again to the destination byte and OR-ed (ATOMS.OR, predicated on non-zero) into a warp-private
-// zero-initialised shared-memory ring that mirrors the 16-byte alignment of the output; rows longer than 16 bytes repeat
-// that for further 16-byte pieces (the loop trip count is warp-uniform). After each 32-row round the completed 16-byte
-// chunks leave as 128-bit stores and are re-zeroed; a chunk this warp shares with another writer (its first and last one)
-// is written byte-wise. Rounds whose output does not fit the ring fall back to direct byte copies.
-#define BW_WARPS 8
-#define BW_WROWS (BY_ROWS / BW_WARPS)   // 256 rows per warp
-#define BW_ITERS (BW_WROWS / 32)        // 8 rounds of 32 rows
-#define BW_WIN 2048                     // ring bytes per warp (power of two)
-#define BW_WINW (BW_WIN / 4)
-
-__device__ __forceinline__ uint32_t bytemask_n(int n) {  // low n bytes set (n <= 0: none, n >= 4: all)
-  return n >= 4 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << (8 * n)) - 1u));
-}
-
-__global__ void __launch_bounds__(256, 3) k_bytes_copy_warp(const BytesArgs a, const int64_t *__restrict__ block_incl, int32_t *__restrict__ out_offs,
-                                                            uint8_t *__restrict__ out_data, int64_t limit, unsigned long long *res,
-                                                            const int64_t *__restrict__ total_ptr, int64_t out_cap) {
-  __shared__ __align__(16) uint32_t s_win[BW_WARPS][BW_WINW];
-  if (out_data != nullptr && total_ptr != nullptr) {  // decided on the device: no host round trip between the passes
-    const int64_t total = __ldg(total_ptr);
-    if (total > out_cap || total > limit) out_data = nullptr;
-  }
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int64_t blk = blockIdx.x;
-  const int64_t cta_begin = blk ? block_incl[blk - 1] : 0;
-  const int64_t row0 = blk * BY_ROWS + (int64_t)wid * BW_WROWS;
-  uint32_t *win = s_win[wid];
-  for (int i = lane; i < BW_WIN / 16; i += 32) reinterpret_cast<uint4 *>(win)[i] = make_uint4(0, 0, 0, 0);
-  // ---- lengths of the warp's 256 rows (8 per lane, lane == row % 32) ----
-  const uint32_t *idx = static_cast<const uint32_t *>(a.idx);
-  const int32_t *offs = static_cast<const int32_t *>(a.offs);
-  const uint32_t n32 = a.n_src > (int64_t)0xffffffffll ? 0xffffffffu : (uint32_t)a.n_src;
-  const bool all_in = a.n_src > (int64_t)0xffffffffll;
-  uint32_t ix[BW_ITERS];
-  bool use[BW_ITERS];
-#pragma unroll
-  for (int i = 0; i < BW_ITERS; ++i) {
-    const int64_t j = row0 + i * 32 + lane;
-    const bool live = j < a.m;
-    ix[i] = live ? __ldg(idx + j) : 0u;
-    uint32_t vw = ~0u;
-    if (a.out_valid && row0 + i * 32 < a.m) vw = __ldg(a.out_valid + ((row0 + i * 32) >> 5));
-    use[i] = live && ((vw >> lane) & 1u) && (all_in || ix[i] < n32);  // out-of-bounds rows were reported by pass 1
-  }
-  int32_t beg[BW_ITERS];
-  uint32_t len[BW_ITERS];
-#pragma unroll
-  for (int i = 0; i < BW_ITERS; ++i) {  // all 16 gathers of a lane in flight
-    int32_t s0 = 0, e0 = 0;
-    if (use[i]) { s0 = __ldg(offs + ix[i]); e0 = __ldg(offs + ix[i] + 1); }
-    beg[i] = s0;
-    len[i] = (uint32_t)(e0 - s0);
-  }
-  // ---- exclusive prefix in row order: one warp scan per round + a running total ----
-  uint64_t run = 0;
-  uint32_t tot[BW_ITERS];
-  uint64_t pre64[BW_ITERS];
-#pragma unroll
-  for (int i = 0; i < BW_ITERS; ++i) {
-    uint32_t incl = len[i];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t y = __shfl_up_sync(ACU_FULL_MASK, incl, o);
-      if (lane >= o) incl += y;
-    }
-    // a round's 32 lengths can exceed 32 bits only for > 128 MB rows: the i32 limit check below uses 64-bit totals
-    tot[i] = __shfl_sync(ACU_FULL_MASK, incl, 31);
-    pre64[i] = run + (incl - len[i]);
-    run += tot[i];
-  }
-  __shared__ uint64_t s_wtot64[BW_WARPS];
-  if (lane == 0) s_wtot64[wid] = run;
-  __syncthreads();
-  int64_t wbase = cta_begin;
-  for (int w = 0; w < wid; ++w) wbase += (int64_t)s_wtot64[w];
-  // ---- new offsets (+ first i32 overflow) ----
-  unsigned long long err = ~0ull;
-#pragma unroll
-  for (int i = BW_ITERS - 1; i >= 0; --i) {
-    const int64_t j = row0 + i * 32 + lane;
-    const int64_t start = wbase + (int64_t)pre64[i];
-    if (j < a.m && start + (int64_t)len[i] > limit) err = (unsigned long long)j;
-    if (j <= a.m) out_offs[j] = (int32_t)start;  // row m: the end of the last row
-  }
-  if (err != ~0ull) atomicMin(res + RES_ERR2, err);
-  if (out_data == nullptr) return;  // grid-uniform
-  // ---- byte copy through the ring ----
-  const uint32_t A = (uint32_t)((uintptr_t)out_data & 15);  // ring positions mirror the output's 16-byte alignment
-  uint8_t *gbase = out_data - A;                               // gbase + apos is the global address of ring position apos
-  int64_t own_start = wbase + A;                               // first position this warp owns (apos space)
-  int64_t flush_pos = own_start & ~(int64_t)15;                // chunks below are done
-  const uint8_t *__restrict__ data = a.data;
-  __syncwarp();
-#pragma unroll 1
-  for (int i = 0; i < BW_ITERS; ++i) {
-    const int64_t round_begin = wbase + A + (int64_t)__shfl_sync(ACU_FULL_MASK, (unsigned long long)pre64[i], 0);
-    const int64_t round_end = round_begin + (int64_t)tot[i];
-    const int64_t d0 = wbase + A + (int64_t)pre64[i];  // this lane's destination (apos)
-    const uint32_t L = len[i];
-    if (tot[i] == 0) continue;  // warp-uniform
-    if ((uint64_t)tot[i] > (uint64_t)(BW_WIN - 64)) {
-      // ---- direct path: drain the ring (byte-wise for the partial chunk), then plain byte copies ----
-      {
-        const int64_t pend_end = round_begin;  // bytes [flush_pos .. round_begin) are pending in the ring
-        for (int64_t c = flush_pos + (int64_t)lane * 16; c < pend_end; c += 32 * 16) {
-          const uint32_t wi = (uint32_t)(c >> 2) & (BW_WINW - 1);
-          const uint4 q = *reinterpret_cast<const uint4 *>(win + wi);
-          if (c >= own_start && c + 16 <= pend_end) {
-            *reinterpret_cast<uint4 *>(gbase + c) = q;
-          } else {
-            const uint8_t *qb = reinterpret_cast<const uint8_t *>(&q);
-            for (int b = 0; b < 16; ++b)
-              if (c + b >= own_start && c + b < pend_end) gbase[c + b] = qb[b];
-          }
-          *reinterpret_cast<uint4 *>(win + wi) = make_uint4(0, 0, 0, 0);
-        }
-        __syncwarp();
-      }
-      if (L) copy_row_direct<false>(gbase + d0, data, beg[i], L);
-      own_start = round_end;
-      flush_pos = round_end & ~(int64_t)15;
-      __syncwarp();
-      continue;
-    }
-    // ---- ring path: OR every row's 16-byte pieces into place ----
-    const uint32_t maxlen = __reduce_max_sync(ACU_FULL_MASK, L);
-    for (uint32_t c = 0; c < maxlen; c += 16) {
-      const int n = (int)L - (int)c;  // bytes of this piece still to copy (<= 0: none)
-      if (n > 0) {
-        const uintptr_t saddr = (uintptr_t)data + (uintptr_t)((int64_t)beg[i] + c);
-        const uint32_t *sp = reinterpret_cast<const uint32_t *>(saddr & ~(uintptr_t)3);
-        const uint32_t ssh = (uint32_t)(saddr & 3u) * 8u;
-        const int nb = n > 16 ? 16 : n;
-        const int span = (int)(saddr & 3u) + nb;  // bytes from the first aligned word's start to the piece's end
-        uint32_t w0 = __ldg(sp), w1 = 0, w2 = 0, w3 = 0, w4 = 0;
-        if (span > 4) w1 = __ldg(sp + 1);
-        if (span > 8) w2 = __ldg(sp + 2);
-        if (span > 12) w3 = __ldg(sp + 3);
-        if (span > 16) w4 = __ldg(sp + 4);
-        uint32_t e0 = __funnelshift_r(w0, w1, ssh) & bytemask_n(nb);
-        uint32_t e1 = __funnelshift_r(w1, w2, ssh) & bytemask_n(nb - 4);
-        uint32_t e2 = __funnelshift_r(w2, w3, ssh) & bytemask_n(nb - 8);
-        uint32_t e3 = __funnelshift_r(w3, w4, ssh) & bytemask_n(nb - 12);
-        const int64_t d = d0 + c;
-        const uint32_t dsh = (uint32_t)(d & 3) * 8u;
-        const uint32_t wi = (uint32_t)(d >> 2);
-        const uint32_t x0 = e0 << dsh;
-        const uint32_t x1 = __funnelshift_l(e0, e1, dsh);
-        const uint32_t x2 = __funnelshift_l(e1, e2, dsh);
-        const uint32_t x3 = __funnelshift_l(e2, e3, dsh);
-        const uint32_t x4 = __funnelshift_l(e3, 0u, dsh);
-        if (x0) atomicOr(win + ((wi + 0) & (BW_WINW - 1)), x0);
-        if (x1) atomicOr(win + ((wi + 1) & (BW_WINW - 1)), x1);
-        if (x2) atomicOr(win + ((wi + 2) & (BW_WINW - 1)), x2);
-        if (x3) atomicOr(win + ((wi + 3) & (BW_WINW - 1)), x3);
-        if (x4) atomicOr(win + ((wi + 4) & (BW_WINW - 1)), x4);
-      }
-    }
-    __syncwarp();
-    // ---- flush the chunks completed by this round ----
-    const int64_t done = round_end & ~(int64_t)15;
-    for (int64_t c = flush_pos + (int64_t)lane * 16; c < done; c += 32 * 16) {
-      const uint32_t wi = (uint32_t)(c >> 2) & (BW_WINW - 1);
-      const uint4 q = *reinterpret_cast<const uint4 *>(win + wi);
-      if (c >= own_start) {
-        *reinterpret_cast<uint4 *>(gbase + c) = q;
-      } else {  // the chunk that holds the warp's first byte (or the end of a direct round): only the owned bytes
-        const uint8_t *qb = reinterpret_cast<const uint8_t *>(&q);
-        for (int b = 0; b < 16; ++b)
-          if (c + b >= own_start) gbase[c + b] = qb[b];
-      }
-      *reinterpret_cast<uint4 *>(win + wi) = make_uint4(0, 0, 0, 0);
-    }
-    flush_pos = done > flush_pos ? done : flush_pos;
-    __syncwarp();
-  }
-  // ---- the warp's last partial chunk ----
-  const int64_t wend = wbase + A + (int64_t)run;
-  if (flush_pos < wend && lane == 0) {
-    const uint32_t wi = (uint32_t)(flush_pos >> 2) & (BW_WINW - 1);
-    const uint8_t *qb = reinterpret_cast<const uint8_t *>(win + wi);
-    for (int b = 0; b < 16; ++b)
-      if (flush_pos + b >= own_start && flush_pos + b < wend) gbase[flush_pos + b] = qb[b];
-  }
-}
-
 // lengths -> CTA totals -> scan -> offsets (+ byte copy when out_data != NULL and it fits), queued
 // on the ctx stream without synchronising; gather_finalize reads the fetched result block:
 // RES_ERR_INDEX = lowest out-of-bounds row (detect_oob), RES_AUX0 = total value bytes,
@@ -735,11 +540,7 @@ acu_status gather_launch(acu_ctx *ctx, int32_t ob, const void *offsets, const ui
   ACU_CUDA(ctx, cudaMemcpyAsync(res + RES_AUX0, block_tot + (blocks - 1), 8, cudaMemcpyDeviceToDevice, ctx->stream));
   const int stage_cap = BY_STAGE_CAP;
   a.detect_oob = 0;
-  static const bool legacy_bytes = getenv("ACU_BYTES_LEGACY") != nullptr;  // round-1 CTA-staged kernel, kept for A/B measurements
-  if (fast && !legacy_bytes && ((uintptr_t)out_offsets % 4 == 0)) {
-    ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_copy_warp, (unsigned)blocks, 256, 0, a, block_tot, static_cast<int32_t *>(out_offsets), out_data,
-                     gs->limit, res, block_tot + (blocks - 1), out_cap);
-  } else if (fast) {
+  if (fast) {
     ACU_CUDA(ctx, cudaFuncSetAttribute(k_bytes_offsets_copy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_cap));
     ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_offsets_copy<true>, (unsigned)blocks, BY_THREADS, stage_cap, a, block_tot, (int64_t)0, out_offsets,
                      out_data, gs->limit, (int64_t)-1, res, stage_cap, block_tot + (blocks - 1), out_cap);

@@ -440,7 +440,7 @@ template <int W> struct FusedCfg {
   static constexpr uint32_t CHUNK_MASK = RPC == 32 ? 0xffffffffu : ((1u << RPC) - 1u);
 };
 
-template <int W, int MINB = 6>
+template <int W, int MINB = 5>
 __global__ void __launch_bounds__(256, MINB) k_filter_fused(const FilterBatch batch) {
   const FilterArgs &a = batch.col[blockIdx.y];
   using C = AsyncCfg<W>;
@@ -450,14 +450,14 @@ __global__ void __launch_bounds__(256, MINB) k_filter_fused(const FilterBatch ba
   extern __shared__ __align__(16) uint8_t s_raw[];
   __shared__ uint32_t s_h[8][2 * TILE_WORDS];   // the tile's mask as 32-bit halves ...
   __shared__ uint32_t s_hp[8][2 * TILE_WORDS];  // ... and the exclusive popcount prefix of every half
-  __shared__ uint32_t s_win[8][36];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int lr = lane * RPC / CPR;               // lane's row offset inside a chunk round
   const int lr_half = lr >> 5, lr_bit = lr & 31; // (W <= 8: fixed for every round; W >= 16: lr < 32, lr_half = 0)
-  uint4 *buf = reinterpret_cast<uint4 *>(s_raw + (size_t)wid * C::PASS_BYTES);
+  uint4 *lbuf = reinterpret_cast<uint4 *>(s_raw + (size_t)wid * C::PASS_BYTES) + lane;  // the lane's slot of round 0
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const uint8_t *__restrict__ vsrc = a.vsrc;
+  const bool v_aligned = vsrc && (((uintptr_t)vsrc & 7) == 0) && ((a.voff & 63) == 0);  // validity words are plain aligned u64 loads
   unsigned valid_cnt = 0;
 
   int64_t t = warp;
@@ -491,7 +491,10 @@ __global__ void __launch_bounds__(256, MINB) k_filter_fused(const FilterBatch ba
     s_hp[wid][lane] = hincl - hc;
     // the validity word of the tile goes in flight before the value loads (consumed after them)
     uint64_t v = 0;
-    if (vsrc && m) v = ld_bits64(vsrc, a.voff + t * TILE_ROWS + (int64_t)lane * 64, a.voff + a.vlen);
+    if (vsrc && m) {
+      if (v_aligned) v = __ldg(reinterpret_cast<const uint64_t *>(vsrc) + ((a.voff + t * TILE_ROWS) >> 6) + lane);  // bits past vlen: masked by m
+      else v = ld_bits64(vsrc, a.voff + t * TILE_ROWS + (int64_t)lane * 64, a.voff + a.vlen);
+    }
     __syncwarp();
     const uint8_t *src = a.values + (size_t)t * TILE_ROWS * W;
     uint8_t *dst = a.out + (size_t)out0 * W;
@@ -499,33 +502,32 @@ __global__ void __launch_bounds__(256, MINB) k_filter_fused(const FilterBatch ba
     for (int pass = 0; pass < C::PASSES; ++pass) {
       const int half_base = (pass * C::PASS_ROWS) >> 5;  // first 32-bit half of the pass
       const uint8_t *psrc = src + ((size_t)pass * C::CPP + lane) * 16;
+      asm volatile("" : "+l"(psrc));  // keep the lane's source address in registers: every round is [psrc + immediate]
       const uint32_t *hh = &s_h[wid][half_base + lr_half];
       uint32_t sel = 0;  // RPC selection bits per round, packed
       // ---- issue: every needed chunk of the pass goes in flight (coalesced: lane <-> consecutive 16-byte chunks) ----
 #pragma unroll
       for (int j = 0; j < C::ITERS; ++j) {
-        constexpr int dummy = 0; (void)dummy;
         const int r0 = j * RPJ;                                  // compile-time row offset of the round inside the pass
         const uint32_t bits = (hh[r0 >> 5] >> ((r0 & 31) + lr_bit)) & F::CHUNK_MASK;
         sel |= bits << (j * RPC);
-        if (bits) cp_async16(buf + j * 32 + lane, psrc + (size_t)j * 512);
+        if (bits) cp_async16(lbuf + j * 32, psrc + (size_t)j * 512);
       }
       cp_async_wait_all();
       __syncwarp();
-      // ---- consume: rank and store the selected elements ----
+      // ---- consume: rank and store the selected elements (no branch: every store is predicated) ----
       const uint32_t *hp = &s_hp[wid][half_base + lr_half];
 #pragma unroll
       for (int j = 0; j < C::ITERS; ++j) {
         const uint32_t bits = (sel >> (j * RPC)) & F::CHUNK_MASK;
-        if (!bits) continue;
         const int r0 = j * RPJ;
         const int sh = (r0 & 31) + lr_bit;
         const uint32_t rank = hp[r0 >> 5] + __popc(hh[r0 >> 5] & ((1u << sh) - 1u));
-        const uint4 x = buf[j * 32 + lane];
+        const uint4 x = lbuf[j * 32];
         if constexpr (W == 8) {
           uint64_t *o = reinterpret_cast<uint64_t *>(dst) + rank;
-          if (bits & 1u) *o++ = (uint64_t)x.x | ((uint64_t)x.y << 32);
-          if (bits & 2u) *o = (uint64_t)x.z | ((uint64_t)x.w << 32);
+          if (bits & 1u) o[0] = (uint64_t)x.x | ((uint64_t)x.y << 32);
+          if (bits & 2u) o[bits & 1u] = (uint64_t)x.z | ((uint64_t)x.w << 32);
         } else if constexpr (W == 4) {
           uint32_t *o = reinterpret_cast<uint32_t *>(dst) + rank;
           if (bits & 1u) *o++ = x.x;
@@ -545,42 +547,33 @@ __global__ void __launch_bounds__(256, MINB) k_filter_fused(const FilterBatch ba
           for (int e = 0; e < 16; ++e)
             if ((bits >> e) & 1u) *o++ = ve[e];
         } else {
-          const int half = lane % CPR;  // (j*32 + lane) % CPR, CPR divides 32
-          uint64_t *o = reinterpret_cast<uint64_t *>(dst + (size_t)rank * W + half * 16);
-          o[0] = (uint64_t)x.x | ((uint64_t)x.y << 32);
-          o[1] = (uint64_t)x.z | ((uint64_t)x.w << 32);
+          if (bits) {
+            const int half = lane % CPR;  // (j*32 + lane) % CPR, CPR divides 32
+            uint64_t *o = reinterpret_cast<uint64_t *>(dst + (size_t)rank * W + half * 16);
+            o[0] = (uint64_t)x.x | ((uint64_t)x.y << 32);
+            o[1] = (uint64_t)x.z | ((uint64_t)x.w << 32);
+          }
         }
       }
       __syncwarp();  // the landing buffer is reused by the next pass / tile
     }
-    // ---- validity: PEXT(source validity, mask) per word, assembled in a warp-private window ----
+    // ---- validity: PEXT(source validity, mask) per word; the (<= 3) output words a lane touches are merged with RED.OR ----
+    // (fire-and-forget into the zeroed bitmap: no shared-memory window, no warp barriers, no dependent latency)
     if (vsrc) {
       const uint32_t c = __popcll(m);               // lanes >= 16 hold m = 0
-      const uint32_t wpref = s_hp[wid][(2 * lane) & 31];  // exclusive prefix of word `lane` = prefix of its low half
-      const uint64_t bits = c ? pext64_sparse(v, m, c) : 0ull;
-      valid_cnt += __popcll(bits);
-      const uint32_t lead = (uint32_t)(out0 & 31);
-      const uint32_t nwords = (lead + (uint32_t)cnt + 31) >> 5;  // <= 33
-      for (uint32_t i = lane; i < nwords; i += 32) s_win[wid][i] = 0;
-      __syncwarp();
       if (c) {
-        const uint32_t p = lead + wpref;
-        const uint32_t sh = p & 31;
-        atomicOr(&s_win[wid][p >> 5], (uint32_t)(bits << sh));
-        if (sh + c > 32) {
-          const uint64_t rest = bits >> (32 - sh);
-          atomicOr(&s_win[wid][(p >> 5) + 1], (uint32_t)rest);
-          if (sh + c > 64) atomicOr(&s_win[wid][(p >> 5) + 2], (uint32_t)(rest >> 32));
-        }
+        const uint64_t bits = pext64_sparse(v, m, c);
+        valid_cnt += __popcll(bits);
+        const uint64_t p = out0 + s_hp[wid][(2 * lane) & 31];  // first output bit of this word's selected rows
+        const uint32_t sh = (uint32_t)p & 31u;
+        uint32_t *o = a.vout + (p >> 5);
+        const uint32_t w0 = (uint32_t)(bits << sh);
+        const uint64_t rest = sh ? (bits >> (32u - sh)) : (bits >> 32);
+        if (w0) atomicOr(o, w0);
+        if ((uint32_t)rest) atomicOr(o + 1, (uint32_t)rest);
+        if ((uint32_t)(rest >> 32)) atomicOr(o + 2, (uint32_t)(rest >> 32));
       }
-      __syncwarp();
-      uint32_t *o = a.vout + (out0 >> 5);
-      for (uint32_t i = lane; i < nwords; i += 32) {
-        const uint32_t word = s_win[wid][i];
-        if (i == 0 || i == nwords - 1) { if (word) atomicOr(o + i, word); }  // shared with neighbouring tiles
-        else o[i] = word;
-      }
-      __syncwarp();
+      __syncwarp();  // s_hp is rewritten by the next tile
     }
   }
   if (vsrc && a.res) {
@@ -689,11 +682,10 @@ acu_status check_len(acu_ctx *ctx, const acu_filter_plan *plan, int64_t values_l
 }
 
 template <int W>
-acu_status launch_filter(acu_ctx *ctx, const FilterBatch &fb, int n_cols) {
+acu_status launch_filter(acu_ctx *ctx, const FilterBatch &fb, int n_cols, bool fused) {
   const FilterArgs &fa = fb.col[0];
   if (fa.aligned16) {
-    static const bool legacy = getenv("ACU_FILTER_LEGACY") != nullptr;  // round-1 two-pass kernels, kept for A/B measurements
-    if (legacy) {
+    if (!fused) {  // sparse predicates (and ACU_FILTER_LEGACY=1): the round-1 value kernel; validity goes through k_compress_bits
       constexpr size_t smem = 8 * (size_t)AsyncCfg<W>::PASS_BYTES;  // 8 warps x per-warp landing buffer
       if (ctx->occupancy.find(reinterpret_cast<const void *>(k_filter_values_async<W>)) == ctx->occupancy.end())  // first use on this device
         ACU_CUDA(ctx, cudaFuncSetAttribute(k_filter_values_async<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -702,16 +694,6 @@ acu_status launch_filter(acu_ctx *ctx, const FilterBatch &fb, int n_cols) {
       return ACU_OK;
     }
     constexpr size_t smem = 8 * (size_t)AsyncCfg<W>::PASS_BYTES;
-    if constexpr (W == 8) {  // experiment hook: 5 resident CTAs (48 registers, no spills) instead of 6 (40 registers)
-      static const char *minb = getenv("ACU_FILTER_MINB");
-      if (minb && atoi(minb) == 5) {
-        if (ctx->occupancy.find(reinterpret_cast<const void *>(k_filter_fused<W, 5>)) == ctx->occupancy.end())
-          ACU_CUDA(ctx, cudaFuncSetAttribute(k_filter_fused<W, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int gx5 = acu_wave_grid(ctx, k_filter_fused<W, 5>, 256, smem, (fa.n_tiles + 7) / 8);
-        ACU_LAUNCH_TIMED(ctx, ACU_K_FILTER, (k_filter_fused<W, 5>), dim3(gx5, n_cols), 256, smem, fb);
-        return ACU_OK;
-      }
-    }
     if (ctx->occupancy.find(reinterpret_cast<const void *>(k_filter_fused<W>)) == ctx->occupancy.end())
       ACU_CUDA(ctx, cudaFuncSetAttribute(k_filter_fused<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int gx = acu_wave_grid(ctx, k_filter_fused<W>, 256, smem, (fa.n_tiles + 7) / 8);
@@ -723,14 +705,14 @@ acu_status launch_filter(acu_ctx *ctx, const FilterBatch &fb, int n_cols) {
   return ACU_OK;
 }
 
-acu_status launch_filter_width(acu_ctx *ctx, int32_t elem_bytes, const FilterBatch &fb, int n_cols) {
+acu_status launch_filter_width(acu_ctx *ctx, int32_t elem_bytes, const FilterBatch &fb, int n_cols, bool fused) {
   switch (elem_bytes) {
-    case 1: return launch_filter<1>(ctx, fb, n_cols);
-    case 2: return launch_filter<2>(ctx, fb, n_cols);
-    case 4: return launch_filter<4>(ctx, fb, n_cols);
-    case 8: return launch_filter<8>(ctx, fb, n_cols);
-    case 16: return launch_filter<16>(ctx, fb, n_cols);
-    case 32: return launch_filter<32>(ctx, fb, n_cols);
+    case 1: return launch_filter<1>(ctx, fb, n_cols, fused);
+    case 2: return launch_filter<2>(ctx, fb, n_cols, fused);
+    case 4: return launch_filter<4>(ctx, fb, n_cols, fused);
+    case 8: return launch_filter<8>(ctx, fb, n_cols, fused);
+    case 16: return launch_filter<16>(ctx, fb, n_cols, fused);
+    case 32: return launch_filter<32>(ctx, fb, n_cols, fused);
     default:
       return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "filter: unsupported element width %d", elem_bytes);
   }
@@ -756,10 +738,16 @@ CompressArgs compress_args(const acu_filter_plan *plan, const uint8_t *src, int6
   return c;
 }
 
-// true when the column's validity compaction rides in the value kernel (k_filter_fused)
-bool fuses_validity(const acu_array *values) {
+// The one-pass kernel (k_filter_fused: values + validity) is used for 16-byte aligned value buffers unless the predicate is
+// very sparse (< 4 % selected: almost no value bytes move, the per-tile validity work dominates and the round-1 pair
+// k_filter_values_async + k_compress_bits is ~20 % faster — measured, profiles/r02_filter_ab.md). ACU_FILTER_LEGACY=1 forces
+// the round-1 kernels for A/B measurements.
+bool plan_uses_fused(const acu_filter_plan *plan) {
   static const bool legacy = getenv("ACU_FILTER_LEGACY") != nullptr;
-  return !legacy && ((uintptr_t)values->values % 16) == 0;
+  return !legacy && plan->count * 25 >= plan->len;
+}
+bool fuses_validity(const acu_filter_plan *plan, const acu_array *values) {
+  return plan_uses_fused(plan) && ((uintptr_t)values->values % 16) == 0;
 }
 
 FilterArgs filter_args(const acu_filter_plan *plan, const acu_array *values, acu_array_out *out, bool has_nulls,
@@ -771,7 +759,7 @@ FilterArgs filter_args(const acu_filter_plan *plan, const acu_array *values, acu
   fa.tile_off = plan->tile_off;
   fa.n_tiles = plan->n_tiles;
   fa.aligned16 = ((uintptr_t)values->values % 16) == 0;
-  if (has_nulls && fuses_validity(values)) {  // FilterPredicate::filter_nulls in the same pass (filter.rs:512-533)
+  if (has_nulls && fuses_validity(plan, values)) {  // FilterPredicate::filter_nulls in the same pass (filter.rs:512-533)
     fa.vsrc = values->validity;
     fa.voff = values->validity_offset;
     fa.vlen = plan->len;
@@ -957,7 +945,7 @@ acu_status acu_filter_col_launch(acu_ctx *ctx, const acu_filter_plan *plan, int 
       ACU_CUDA(ctx, cudaMemsetAsync(out->validity, 0, acu_bitmap_bytes(plan->count), ctx->stream));
       *mode = 1;
     }
-    ACU_TRY(launch_filter_width(ctx, elem_bytes, fb, 1));
+    ACU_TRY(launch_filter_width(ctx, elem_bytes, fb, 1, plan_uses_fused(plan)));
   }
   CompressBatch cb{};
   int nc = 0;
@@ -1006,7 +994,7 @@ acu_status acu_filter_cols_launch(acu_ctx *ctx, const acu_filter_plan *plan, int
       ++k;
       done[d] = 1;
     }
-    ACU_TRY(launch_filter_width(ctx, widths[c], fb, k));
+    ACU_TRY(launch_filter_width(ctx, widths[c], fb, k, plan_uses_fused(plan)));
   }
   // bit compactions: boolean values and every validity buffer that may hold nulls
   CompressBatch cb{};
@@ -1021,7 +1009,7 @@ acu_status acu_filter_cols_launch(acu_ctx *ctx, const acu_filter_plan *plan, int
       cb.col[k++] = compress_args(plan, static_cast<const uint8_t *>(values[c]->values), values[c]->values_offset, outs[c]->values, nullptr);
       if (k == BATCH_COLS) ACU_TRY(flush());
     }
-    if (values[c]->validity != nullptr && values[c]->null_count != 0 && !(kinds[c] == 0 && fuses_validity(values[c]))) {
+    if (values[c]->validity != nullptr && values[c]->null_count != 0 && !(kinds[c] == 0 && fuses_validity(plan, values[c]))) {
       cb.col[k++] = compress_args(plan, values[c]->validity, values[c]->validity_offset, outs[c]->validity, res[c]);
       modes[c] = 1;
       if (k == BATCH_COLS) ACU_TRY(flush());

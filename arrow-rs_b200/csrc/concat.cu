@@ -11,6 +11,8 @@
 //
 // One thread per destination u64 word; boundary words are merged with atomicOr / atomicAnd so that
 // two appends never need the destination to start on a word.
+#include <vector>
+
 #include "bitmap.cuh"
 
 namespace {
@@ -127,5 +129,100 @@ extern "C" acu_status acu_offsets_append(acu_ctx *ctx, int32_t offset_bytes, con
     const long long total = (long long)(base + (s1 - s0));
     return acu_fail(ctx, ACU_ERR_OFFSET_OVERFLOW, (int64_t)ctx->h_res[RES_ERR_INDEX], 0, 0, (uint64_t)total, "%lld", total);
   }
+  return ACU_OK;
+}
+
+// ---- concat / concat_batches (arrow-select/src/concat.rs:495-640) ------------------------------------------------------
+// concat_primitives / concat_boolean / concat_bytes are builder.append_array per input (concat.rs:334-368):
+//   values   : raw copies in input order (bytes under null slots included)                primitive_builder.rs:290-303
+//   booleans : bit ranges appended at the running row                                     boolean_builder.rs append_array
+//   bytes    : offsets rebased on the running byte total (OffsetOverflowError(shift + last) when the type overflows),
+//              each input's value bytes [offsets[0], offsets[len])                        generic_bytes_builder.rs:169-206
+//   nulls    : NullBufferBuilder — materialised iff some input has null_count > 0 (null.rs:209-218), then Some(..)
+// One input returns array.slice(0, len) in the reference (zero copy, its NullBuffer kept as it is); with caller-owned
+// outputs that is a copy that keeps the input's NullBuffer presence.
+static acu_status concat_one_field(acu_ctx *ctx, int32_t n, const acu_column *cols, int64_t stride, acu_column_out *out) {
+  if (n <= 0)  // concat.rs:496-499
+    return acu_fail(ctx, ACU_ERR_COMPUTE, -1, 0, 0, 0, "concat requires input of at least one array");
+  const acu_column &c0 = cols[0];
+  for (int i = 1; i < n; ++i) {
+    const acu_column &c = cols[(size_t)i * stride];
+    if (c.kind != c0.kind || c.width != c0.width)  // concat.rs:505-535 (the reference lists the DataTypes; the C ABI only knows kind / width)
+      return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, i, 0, 0, 0,
+                      "It is not possible to concatenate arrays of different data types (kind %d width %d, kind %d width %d).",
+                      c0.kind, c0.width, c.kind, c.width);
+  }
+  if (c0.kind == ACU_COL_BYTES && c0.width != 4 && c0.width != 8)
+    return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "offset width must be 4 or 8");
+  int64_t total = 0;
+  bool any_nulls = false;
+  int64_t null_total = 0;
+  std::vector<int64_t> ncs((size_t)n);
+  for (int i = 0; i < n; ++i) {
+    const acu_column &c = cols[(size_t)i * stride];
+    acu_status st = ACU_OK;
+    ncs[i] = c.array.len ? acu_resolve_null_count(ctx, &c.array, &st) : 0;
+    ACU_TRY(st);
+    any_nulls = any_nulls || ncs[i] > 0;
+    null_total += ncs[i];
+    total += c.array.len;
+  }
+  const bool keep_single = n == 1 && c0.array.validity != nullptr;  // slice(0, len): the NullBuffer survives as it is
+  out->array.len = total;
+  out->array.null_count = 0;
+  out->array.has_validity = 0;
+  out->data_len = 0;
+  int64_t row = 0, bytes = 0;
+  if (c0.kind == ACU_COL_BYTES) ACU_CUDA(ctx, cudaMemsetAsync(out->array.values, 0, (size_t)c0.width, ctx->stream));  // offsets[0] = 0
+  for (int i = 0; i < n; ++i) {
+    const acu_column &c = cols[(size_t)i * stride];
+    const int64_t len = c.array.len;
+    if (len == 0) continue;
+    if (c.kind == ACU_COL_PRIMITIVE) {
+      ACU_CUDA(ctx, cudaMemcpyAsync(static_cast<uint8_t *>(out->array.values) + (size_t)row * c.width, c.array.values, (size_t)len * c.width,
+                                    cudaMemcpyDeviceToDevice, ctx->stream));
+    } else if (c.kind == ACU_COL_BOOLEAN) {
+      ACU_TRY(acu_bitmap_copy(ctx, static_cast<const uint8_t *>(c.array.values), c.array.values_offset, static_cast<uint8_t *>(out->array.values),
+                              row, len, nullptr));
+    } else {
+      int64_t sb = 0, se = 0;
+      ACU_TRY(acu_offsets_append(ctx, c.width, c.array.values, 0, len, bytes, out->array.values, row, &sb, &se));
+      if (bytes + (se - sb) > out->data_capacity)
+        return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, (uint64_t)(bytes + (se - sb)), "output data capacity %lld < required %lld",
+                        (long long)out->data_capacity, (long long)(bytes + (se - sb)));
+      if (se > sb)
+        ACU_CUDA(ctx, cudaMemcpyAsync(out->data + bytes, c.data + sb, (size_t)(se - sb), cudaMemcpyDeviceToDevice, ctx->stream));
+      bytes += se - sb;
+    }
+    if (any_nulls || keep_single) {
+      if (c.array.validity) ACU_TRY(acu_bitmap_copy(ctx, c.array.validity, c.array.validity_offset, out->array.validity, row, len, nullptr));
+      else ACU_TRY(acu_bitmap_fill(ctx, out->array.validity, row, len, 1));
+    }
+    row += len;
+  }
+  ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  out->data_len = bytes;
+  if (any_nulls || keep_single) {
+    out->array.has_validity = 1;
+    out->array.null_count = null_total;
+  }
+  return ACU_OK;
+}
+
+extern "C" acu_status acu_concat(acu_ctx *ctx, int32_t n_arrays, const acu_column *arrays, acu_column_out *out) {
+  ACU_ENTER(ctx);
+  return concat_one_field(ctx, n_arrays, arrays, 1, out);
+}
+
+extern "C" acu_status acu_concat_batches(acu_ctx *ctx, int32_t n_batches, int32_t n_columns, const acu_column *columns, acu_column_out *outs,
+                                         int64_t *out_rows) {
+  ACU_ENTER(ctx);
+  if (out_rows) *out_rows = 0;
+  if (n_batches <= 0) {  // RecordBatch::new_empty(schema) (concat.rs:620-622)
+    for (int c = 0; c < n_columns; ++c) { outs[c].array.len = 0; outs[c].array.null_count = 0; outs[c].array.has_validity = 0; outs[c].data_len = 0; }
+    return ACU_OK;
+  }
+  for (int c = 0; c < n_columns; ++c) ACU_TRY(concat_one_field(ctx, n_batches, columns + c, n_columns, &outs[c]));
+  if (out_rows && n_columns > 0) *out_rows = outs[0].array.len;
   return ACU_OK;
 }

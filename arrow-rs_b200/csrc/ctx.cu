@@ -26,6 +26,8 @@ acu_status acu_fail(acu_ctx *ctx, acu_status st, int64_t index, uint64_t lhs, ui
     case ACU_ERR_OFFSET_OVERFLOW: prefix = "Offset overflow error: "; break;
     case ACU_ERR_CAST: prefix = "Cast error: "; break;
     case ACU_ERR_NOT_YET_IMPLEMENTED: prefix = "Not yet implemented: "; break;
+    case ACU_ERR_IPC: prefix = "Ipc error: "; break;
+    case ACU_ERR_PARSE: prefix = "Parser error: "; break;
     default: break;
   }
   size_t n = strlen(prefix);

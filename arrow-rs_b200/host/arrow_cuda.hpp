@@ -23,6 +23,7 @@
 
 #include <cstdint>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <optional>
@@ -253,6 +254,8 @@ class PrimitiveArray : public Array {
     return v;
   }
   T value(int64_t i) const { return values()[(size_t)i]; }
+  const Buffer &buffer() const { return values_; }
+  int64_t elem_offset() const { return elem_offset_; }
   std::vector<std::optional<T>> to_vec() const {
     auto vals = values();
     auto valid = valid_mask();
@@ -306,6 +309,7 @@ class BooleanArray : public Array {
     return v;
   }
   bool value(int64_t i) const { return values()[(size_t)i]; }
+  const Buffer &bits() const { return bits_; }
   std::vector<std::optional<bool>> to_vec() const {
     auto vals = values();
     auto valid = valid_mask();
@@ -889,7 +893,28 @@ Result<BooleanArray> compare_op(acu_cmp_op op, const char *sym, const L &lhs, co
   return BooleanArray(vb, 0, o.len, compute::detail::out_nulls(o, nb));
 }
 }  // namespace detail3
+// GenericByteArray operands (cmp.rs:783-801): Utf8 arrays and scalars through acu_cmp_bytes
+inline acu_bytes_array bytes_view(const StringArray &a, bool scalar) {
+  acu_bytes_array b{};
+  b.offsets = a.offsets().data();
+  b.data = static_cast<const uint8_t *>(a.value_data().data());
+  b.nulls = a.view(scalar);
+  return b;
+}
+inline Result<BooleanArray> compare_strings(acu_cmp_op op, const StringArray &l, bool ls, const StringArray &r, bool rs) {
+  Context &c = Context::get();
+  const int64_t n = ls ? r.len() : l.len();
+  Buffer vb, nb;
+  acu_bytes_array a = bytes_view(l, ls), b = bytes_view(r, rs);
+  acu_array_out o = compute::detail::make_out(vb, nb, acu_bitmap_bytes(std::max<int64_t>(n, 1)), std::max<int64_t>(n, 1));
+  acu_status st = acu_cmp_bytes(c.raw(), 4, op, &a, &b, &o);
+  if (st != ACU_OK) return c.last_error(st);
+  return BooleanArray(vb, 0, o.len, compute::detail::out_nulls(o, nb));
+}
 #define ACU_CMP(NAME, OP, SYM) \
+  inline Result<BooleanArray> NAME(const StringArray &l, const StringArray &r) { return compare_strings(OP, l, false, r, false); } \
+  inline Result<BooleanArray> NAME(const StringArray &l, const Scalar<StringArray> &r) { return compare_strings(OP, l, false, r.array, true); } \
+  inline Result<BooleanArray> NAME(const Scalar<StringArray> &l, const StringArray &r) { return compare_strings(OP, l.array, true, r, false); } \
   template <class L, class R> Result<BooleanArray> NAME(const L &lhs, const R &rhs) { return detail3::compare_op(OP, SYM, lhs, rhs); }
 ACU_CMP(eq, ACU_EQ, "==") ACU_CMP(neq, ACU_NEQ, "!=") ACU_CMP(lt, ACU_LT, "<") ACU_CMP(lt_eq, ACU_LT_EQ, "<=")
 ACU_CMP(gt, ACU_GT, ">") ACU_CMP(gt_eq, ACU_GT_EQ, ">=") ACU_CMP(distinct, ACU_DISTINCT, "IS DISTINCT FROM")
@@ -975,11 +1000,250 @@ template <class T> Result<std::optional<T>> sum_checked(const PrimitiveArray<T> 
   return std::optional<T>(out);
 }
 
+
+// ---- nullif / zip (arrow-select/src/nullif.rs:44-113, zip.rs:99-226) -------------------------------------------
+namespace detail {
+// The same buffers with another NullBuffer (ArrayData::into_builder().nulls(..): nullif shares the value buffers)
+inline ArrayRef with_nulls(const Array &a, std::optional<NullBuffer> nulls);
+}  // namespace detail
+
+// nullif(left, right): validity &= !(right is Some(true)); values shared (zero copy)
+inline Result<ArrayRef> nullif(const Array &left, const BooleanArray &right) {
+  Context &c = Context::get();
+  Buffer vb, nb;
+  acu_array l = left.view(), r = right.view();
+  acu_array_out o = detail::make_out(vb, nb, 16, std::max<int64_t>(left.len(), 1));
+  acu_status st = acu_nullif(c.raw(), &l, &r, &o);
+  if (st != ACU_OK) return c.last_error(st);
+  if (left.len() == 0) return detail::with_nulls(left, left.nulls());
+  return detail::with_nulls(left, detail::out_nulls(o, nb));
+}
+
+// zip(mask, truthy, falsy) for primitive arrays / scalars of one type
+template <class L, class R>
+Result<ArrayRef> zip(const BooleanArray &mask, const L &truthy, const R &falsy) {
+  const auto &t = datum_array(truthy);
+  const auto &f = datum_array(falsy);
+  if (t.data_type() != f.data_type())  // zip.rs:117-121
+    return ArrowError{ACU_ERR_INVALID_ARGUMENT, "Invalid argument error: arguments need to have the same data type"};
+  Context &c = Context::get();
+  const int64_t n = mask.len();
+  Buffer vb, nb;
+  acu_array m = mask.view(), tv = t.view(datum_is_scalar(truthy)), fv = f.view(datum_is_scalar(falsy));
+  acu_array_out o = detail::make_out(vb, nb, (size_t)std::max<int64_t>(n, 1) * dtype_width(t.data_type()), std::max<int64_t>(n, 1));
+  acu_status st = acu_zip(c.raw(), dtype_width(t.data_type()), &m, &tv, &fv, &o);
+  if (st != ACU_OK) return c.last_error(st);
+  return detail::make_primitive(t.data_type(), vb, o.len, detail::out_nulls(o, nb));
+}
+
+// ---- concat / concat_batches (arrow-select/src/concat.rs:495-640) -----------------------------------------------
+inline Result<ArrayRef> concat(const std::vector<const Array *> &arrays) {
+  Context &c = Context::get();
+  if (arrays.empty()) return ArrowError{ACU_ERR_COMPUTE, "Compute error: concat requires input of at least one array"};
+  const DataType dt = arrays[0]->data_type();
+  for (const Array *a : arrays)
+    if (a->data_type() != dt)  // concat.rs:505-535
+      return ArrowError{ACU_ERR_INVALID_ARGUMENT, std::string("Invalid argument error: It is not possible to concatenate arrays of different data types (") +
+                                                       detail::dtype_display(dt) + ", " + detail::dtype_display(a->data_type()) + ")."};
+  std::vector<acu_column> cols;
+  int64_t rows = 0, bytes = 0;
+  for (const Array *a : arrays) {
+    cols.push_back(detail::column_view(*a));
+    rows += a->len();
+    if (dt == DataType::Utf8) bytes += (int64_t)static_cast<const StringArray *>(a)->value_data().len();
+  }
+  std::vector<ArrayRef> proto{detail::with_nulls(*arrays[0], arrays[0]->nulls())};
+  detail::BatchOutputs outs;
+  outs.allocate(proto, std::max<int64_t>(rows, 1), {bytes});
+  acu_status st = acu_concat(c.raw(), (int32_t)cols.size(), cols.data(), outs.outs.data());
+  if (st != ACU_OK) return c.last_error(st);
+  return outs.wrap(proto)[0];
+}
+
+inline Result<RecordBatch> concat_batches(const Schema &schema, const std::vector<const RecordBatch *> &batches) {
+  if (batches.empty()) {  // RecordBatch::new_empty(schema)
+    std::vector<ArrayRef> empty;
+    for (const Field &f : schema) {
+      if (f.data_type == DataType::Boolean) empty.push_back(std::make_shared<BooleanArray>(BooleanArray::from(std::vector<bool>{})));
+      else if (f.data_type == DataType::Utf8) empty.push_back(std::make_shared<StringArray>(StringArray::from(std::vector<std::string>{})));
+      else empty.push_back(detail::make_primitive(f.data_type, Buffer::allocate(16), 0, std::nullopt));
+    }
+    return RecordBatch(schema, std::move(empty), 0);
+  }
+  std::vector<ArrayRef> cols;
+  for (size_t i = 0; i < schema.size(); ++i) {
+    std::vector<const Array *> field;
+    for (const RecordBatch *b : batches) field.push_back(b->column(i).get());
+    auto r = concat(field);
+    if (r.is_err()) return r.unwrap_err();
+    cols.push_back(r.unwrap());
+  }
+  return RecordBatch::try_new(schema, std::move(cols));
+}
 }  // namespace compute
 
 // downcast helpers (as_primitive::<T>() etc.)
 template <class T> const PrimitiveArray<T> &as_primitive(const ArrayRef &a) { return dynamic_cast<const PrimitiveArray<T> &>(*a); }
 inline const BooleanArray &as_boolean(const ArrayRef &a) { return dynamic_cast<const BooleanArray &>(*a); }
 inline const StringArray &as_string(const ArrayRef &a) { return dynamic_cast<const StringArray &>(*a); }
+
+
+namespace compute { namespace detail {
+inline ArrayRef with_nulls(const Array &a, std::optional<NullBuffer> nulls) {
+  if (a.data_type() == DataType::Boolean) {
+    const auto &b = static_cast<const BooleanArray &>(a);
+    acu_array v = b.view();
+    return std::make_shared<BooleanArray>(b.bits(), v.values_offset, b.len(), std::move(nulls));
+  }
+  if (a.data_type() == DataType::Utf8) {
+    const auto &s = static_cast<const StringArray &>(a);
+    return std::make_shared<StringArray>(s.offsets(), s.value_data(), s.len(), std::move(nulls));
+  }
+  switch (a.data_type()) {
+#define ACU_WN(DT, T) case DataType::DT: { const auto &p = static_cast<const PrimitiveArray<T> &>(a); \
+    return std::make_shared<PrimitiveArray<T>>(p.buffer(), p.len(), std::move(nulls), p.elem_offset()); }
+    ACU_WN(Int8, int8_t) ACU_WN(Int16, int16_t) ACU_WN(Int32, int32_t) ACU_WN(Int64, int64_t) ACU_WN(UInt8, uint8_t)
+    ACU_WN(UInt16, uint16_t) ACU_WN(UInt32, uint32_t) ACU_WN(UInt64, uint64_t) ACU_WN(Float32, float)
+#undef ACU_WN
+    default: { const auto &p = static_cast<const PrimitiveArray<double> &>(a);
+      return std::make_shared<PrimitiveArray<double>>(p.buffer(), p.len(), std::move(nulls), p.elem_offset()); }
+  }
+}
+} }  // namespace compute::detail
+
+// ---------------------------------------------------------------------------------------
+// ipc::StreamReader (arrow-ipc/src/reader.rs:1529-1671): record batches decoded straight into HBM.
+// Every batch's body is ONE host->device copy; the columns own a share of that device buffer.
+// ---------------------------------------------------------------------------------------
+namespace ipc {
+class StreamReader {
+ public:
+  // StreamReader::try_new(reader, None) over an in-memory stream
+  static Result<StreamReader> try_new(std::vector<uint8_t> stream) {
+    StreamReader r;
+    r.bytes_ = std::make_shared<std::vector<uint8_t>>(std::move(stream));
+    Context &c = Context::get();
+    acu_ipc_stream *s = nullptr;
+    int32_t n = 0;
+    acu_status st = acu_ipc_stream_open(c.raw(), r.bytes_->data(), (int64_t)r.bytes_->size(), &s, &n);
+    if (st != ACU_OK) return c.last_error(st);
+    r.stream_ = std::shared_ptr<acu_ipc_stream>(s, [](acu_ipc_stream *q) { acu_ipc_stream_close(Context::get().raw(), q); });
+    for (int32_t i = 0; i < n; ++i) {
+      int32_t kind, width, dtype, nullable;
+      const char *name;
+      acu_ipc_stream_field(s, i, &kind, &width, &dtype, &nullable, &name);
+      Field f;
+      f.name = name;
+      f.nullable = nullable != 0;
+      if (kind == ACU_COL_BOOLEAN) f.data_type = DataType::Boolean;
+      else if (kind == ACU_COL_BYTES && width == 4) f.data_type = DataType::Utf8;
+      else if (kind == ACU_COL_PRIMITIVE) f.data_type = (DataType)dtype;
+      else return ArrowError{ACU_ERR_NOT_YET_IMPLEMENTED, "Not yet implemented: IPC field '" + f.name + "': LargeUtf8 in the C++ mirror"};
+      r.schema_.push_back(f);
+    }
+    return r;
+  }
+  const Schema &schema() const { return schema_; }
+  bool is_finished() const { return finished_; }
+  // Iterator::next: Ok(None) at the end of the stream
+  Result<std::optional<RecordBatch>> next() {
+    Context &c = Context::get();
+    std::vector<acu_column> cols(schema_.size());
+    int64_t rows = -1;
+    acu_status st = acu_ipc_stream_next(c.raw(), stream_.get(), cols.data(), &rows);
+    if (st != ACU_OK) return c.last_error(st);
+    if (rows < 0) { finished_ = true; return std::optional<RecordBatch>(); }
+    // the views point into the stream's device buffer, which the next call reuses: give the batch its own copy
+    std::vector<ArrayRef> out;
+    for (size_t i = 0; i < cols.size(); ++i) {
+      const acu_column &col = cols[i];
+      const DataType dt = schema_[i].data_type;
+      std::optional<NullBuffer> nulls;
+      if (col.array.validity) {
+        Buffer nb = Buffer::allocate(acu_bitmap_bytes(rows));
+        acu_memcpy_d2d(c.raw(), nb.data(), col.array.validity, (size_t)((rows + 7) / 8));
+        nulls = NullBuffer{nb, 0, rows, col.array.null_count};
+      }
+      if (dt == DataType::Boolean) {
+        Buffer vb = Buffer::allocate(acu_bitmap_bytes(rows));
+        acu_memcpy_d2d(c.raw(), vb.data(), col.array.values, (size_t)((rows + 7) / 8));
+        out.push_back(std::make_shared<BooleanArray>(vb, 0, rows, nulls));
+      } else if (dt == DataType::Utf8) {
+        Buffer ob = Buffer::allocate((size_t)(rows + 1) * 4);
+        acu_memcpy_d2d(c.raw(), ob.data(), col.array.values, (size_t)(rows + 1) * 4);
+        int32_t last = 0;
+        if (rows > 0) acu_memcpy_d2h(c.raw(), &last, static_cast<const int32_t *>(col.array.values) + rows, 4);
+        Buffer db = Buffer::allocate((size_t)last);
+        if (last) acu_memcpy_d2d(c.raw(), db.data(), col.data, (size_t)last);
+        out.push_back(std::make_shared<StringArray>(ob, db, rows, nulls));
+      } else {
+        const size_t bytes = (size_t)rows * dtype_width(dt);
+        Buffer vb = Buffer::allocate(bytes);
+        if (bytes) acu_memcpy_d2d(c.raw(), vb.data(), col.array.values, bytes);
+        out.push_back(compute::detail::make_primitive(dt, vb, rows, nulls));
+      }
+    }
+    return std::optional<RecordBatch>(RecordBatch(schema_, std::move(out), rows));
+  }
+ private:
+  std::shared_ptr<std::vector<uint8_t>> bytes_;
+  std::shared_ptr<acu_ipc_stream> stream_;
+  Schema schema_;
+  bool finished_ = false;
+};
+}  // namespace ipc
+
+// ---------------------------------------------------------------------------------------
+// parquet::arrow::arrow_reader::{ArrowPredicate, ArrowPredicateFn, RowFilter} (parquet/src/arrow/arrow_reader/filter.rs:29-200):
+// the caller of the hot path. Predicates are applied in order, each one to the rows that survived the previous ones (late
+// materialisation: evaluate_predicate, parquet/src/arrow/arrow_reader/mod.rs), `false` and `null` both drop the row; the
+// final selection is applied to the projected batch with filter_record_batch. Here every intermediate lives in HBM.
+// ---------------------------------------------------------------------------------------
+namespace parquet {
+class ArrowPredicate {
+ public:
+  virtual ~ArrowPredicate() = default;
+  // columns (indices into the batch) this predicate needs: ProjectionMask
+  virtual const std::vector<size_t> &projection() const = 0;
+  // must return a BooleanArray of batch.num_rows() rows
+  virtual Result<BooleanArray> evaluate(const RecordBatch &batch) = 0;
+};
+class ArrowPredicateFn : public ArrowPredicate {
+ public:
+  using Fn = std::function<Result<BooleanArray>(const RecordBatch &)>;
+  ArrowPredicateFn(std::vector<size_t> projection, Fn f) : projection_(std::move(projection)), f_(std::move(f)) {}
+  const std::vector<size_t> &projection() const override { return projection_; }
+  Result<BooleanArray> evaluate(const RecordBatch &batch) override { return f_(batch); }
+ private:
+  std::vector<size_t> projection_;
+  Fn f_;
+};
+class RowFilter {
+ public:
+  explicit RowFilter(std::vector<std::shared_ptr<ArrowPredicate>> predicates) : predicates_(std::move(predicates)) {}
+  // Decode-time filtering of one (already decoded, device-resident) batch: returns the rows for which every predicate is true.
+  Result<RecordBatch> apply(const RecordBatch &batch) const {
+    RecordBatch cur = batch;
+    for (const auto &p : predicates_) {
+      Schema ps;
+      std::vector<ArrayRef> pc;
+      for (size_t i : p->projection()) { ps.push_back(cur.schema()[i]); pc.push_back(cur.column(i)); }
+      RecordBatch projected(ps, pc, cur.num_rows());
+      auto mask = p->evaluate(projected);
+      if (mask.is_err()) return mask.unwrap_err();
+      BooleanArray m = mask.unwrap();
+      if (m.len() != cur.num_rows())  // arrow_reader/mod.rs: "ArrowPredicate predicate returned {} rows, expected {}"
+        return ArrowError{ACU_ERR_INVALID_ARGUMENT, "Parquet argument error: General error: ArrowPredicate predicate returned " +
+                                                         std::to_string(m.len()) + " rows, expected " + std::to_string(cur.num_rows())};
+      auto next = compute::filter_record_batch(cur, m);  // prep_null_mask_filter: null selects nothing
+      if (next.is_err()) return next.unwrap_err();
+      cur = next.unwrap();
+    }
+    return cur;
+  }
+ private:
+  std::vector<std::shared_ptr<ArrowPredicate>> predicates_;
+};
+}  // namespace parquet
 
 }  // namespace arrow_cuda

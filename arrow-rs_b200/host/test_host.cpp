@@ -5,6 +5,7 @@
 // Build: see arrow-rs_b200/host/Makefile.  Run: ./test_host   (exit code 0 = all passed)
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <limits>
 
@@ -431,6 +432,139 @@ static void test_aggregates() {
   CHECK(std::isnan(mn) && std::signbit(mn));
 }
 
+
+// arrow-select/src/nullif.rs:127 test_nullif_int_array, :466 test_nullif_no_nulls
+static void test_nullif() {
+  auto a = Int32Array::from(std::vector<O<int32_t>>{15, N, 8, 1, 9});
+  auto comp = BooleanArray::from(std::vector<O<bool>>{false, N, true, false, N});
+  auto res = nullif(a, comp).unwrap();
+  CHECK((as_primitive<int32_t>(res).to_vec() == std::vector<O<int32_t>>{15, N, N, 1, 9}));
+  auto b = Int32Array::from(std::vector<int32_t>{15, 7, 8, 1, 9});
+  res = nullif(b, comp).unwrap();
+  CHECK((as_primitive<int32_t>(res).to_vec() == std::vector<O<int32_t>>{15, 7, N, 1, 9}));
+  CHECK((as_primitive<int32_t>(res).values() == std::vector<int32_t>{15, 7, 8, 1, 9}));  // values are shared untouched
+  auto err = nullif(b, BooleanArray::from(std::vector<bool>{true})).unwrap_err();
+  CHECK_EQ(err.message, std::string("Compute error: Cannot perform comparison operation on arrays of different length"));
+}
+
+// arrow-select/src/zip.rs:870 test_zip_kernel_one, :892 scalar_falsy_1, :975 primitive_scalar_none_1
+static void test_zip() {
+  auto a = Int32Array::from(std::vector<O<int32_t>>{5, N, 7, N, 1});
+  auto b = Int32Array::from(std::vector<O<int32_t>>{N, 3, 6, 7, 3});
+  auto mask = BooleanArray::from(std::vector<bool>{true, true, false, false, true});
+  auto out = zip(mask, a, b).unwrap();
+  CHECK((as_primitive<int32_t>(out).to_vec() == std::vector<O<int32_t>>{5, N, 6, 7, 1}));
+  out = zip(mask, a, new_scalar<int32_t>(42)).unwrap();
+  CHECK((as_primitive<int32_t>(out).to_vec() == std::vector<O<int32_t>>{5, N, 42, 42, 1}));
+  out = zip(mask, new_scalar<int32_t>(42), new_null_scalar<int32_t>()).unwrap();
+  CHECK((as_primitive<int32_t>(out).to_vec() == std::vector<O<int32_t>>{42, 42, N, N, 42}));
+  auto err = zip(mask, Int32Array::from(std::vector<int32_t>{1, 2}), b).unwrap_err();
+  CHECK_EQ(err.message, std::string("Invalid argument error: all arrays should have the same length"));
+}
+
+// arrow-select/src/concat.rs:880 test_concat_primitive_arrays, :832 test_concat_string_arrays, :698 test_concat_empty_vec
+static void test_concat() {
+  auto a = Int64Array::from(std::vector<O<int64_t>>{-1, -1, 2, N, N});
+  auto b = Int64Array::from(std::vector<O<int64_t>>{101, 102, 103, N});
+  auto c = Int64Array::from(std::vector<int64_t>{256, 512, 1024});
+  auto arr = concat({&a, &b, &c}).unwrap();
+  CHECK((as_primitive<int64_t>(arr).to_vec() == std::vector<O<int64_t>>{-1, -1, 2, N, N, 101, 102, 103, N, 256, 512, 1024}));
+  auto sa = a.slice(1, 3), sb = b.slice(1, 3);
+  arr = concat({&sa, &sb}).unwrap();
+  CHECK((as_primitive<int64_t>(arr).to_vec() == std::vector<O<int64_t>>{-1, 2, N, 102, 103, N}));
+  auto s1 = StringArray::from(std::vector<std::string>{"hello", "world"});
+  auto s2 = StringArray::from(std::vector<std::string>{"2", "3", "4"});
+  auto s3 = StringArray::from(std::vector<O<std::string>>{std::string("foo"), std::string("bar"), N, std::string("baz")});
+  arr = concat({&s1, &s2, &s3}).unwrap();
+  CHECK((as_string(arr).to_vec() == std::vector<O<std::string>>{std::string("hello"), std::string("world"), std::string("2"), std::string("3"),
+                                                                std::string("4"), std::string("foo"), std::string("bar"), N, std::string("baz")}));
+  CHECK_EQ(concat({}).unwrap_err().message, std::string("Compute error: concat requires input of at least one array"));
+  Schema schema{{"a", DataType::Int64, true}, {"s", DataType::Utf8, true}};
+  auto b1 = RecordBatch::try_new(schema, {std::make_shared<Int64Array>(c), std::make_shared<StringArray>(StringArray::from(std::vector<std::string>{"x", "y", "z"}))}).unwrap();
+  auto b2 = RecordBatch::try_new(schema, {std::make_shared<Int64Array>(b), std::make_shared<StringArray>(s3)}).unwrap();
+  auto cb = concat_batches(schema, {&b1, &b2}).unwrap();
+  CHECK_EQ(7, cb.num_rows());
+  CHECK((as_primitive<int64_t>(cb.column(0)).to_vec() == std::vector<O<int64_t>>{256, 512, 1024, 101, 102, 103, N}));
+}
+
+// arrow-ord/src/comparison.rs:1246 test_utf8_array_eq, :1318 test_utf8_array_lt, :1147 test_utf8_eq_scalar_on_slice
+static void test_cmp_utf8() {
+  auto l = StringArray::from(std::vector<std::string>{"arrow", "arrow", "arrow", "arrow"});
+  auto r = StringArray::from(std::vector<std::string>{"arrow", "parquet", "datafusion", "flight"});
+  CHECK((cmpk::eq(l, r).unwrap().to_vec() == std::vector<O<bool>>{true, false, false, false}));
+  CHECK((cmpk::neq(l, r).unwrap().to_vec() == std::vector<O<bool>>{false, true, true, true}));
+  auto l2 = StringArray::from(std::vector<std::string>{"arrow", "datafusion", "flight", "parquet"});
+  auto f = StringArray::from(std::vector<std::string>{"flight", "flight", "flight", "flight"});
+  CHECK((cmpk::lt(l2, f).unwrap().to_vec() == std::vector<O<bool>>{true, true, false, false}));
+  CHECK((cmpk::gt_eq(l2, f).unwrap().to_vec() == std::vector<O<bool>>{false, false, true, true}));
+  auto sc = Scalar<StringArray>(StringArray::from(std::vector<std::string>{"flight"}));
+  CHECK((cmpk::lt_eq(l2, sc).unwrap().to_vec() == std::vector<O<bool>>{true, true, true, false}));
+  auto withnull = StringArray::from(std::vector<O<std::string>>{N, std::string("hello"), std::string("world"), std::string("")});
+  auto hello = Scalar<StringArray>(StringArray::from(std::vector<std::string>{"hello"}));
+  CHECK((cmpk::eq(withnull, hello).unwrap().to_vec() == std::vector<O<bool>>{N, true, false, false}));
+}
+
+// parquet/src/arrow/arrow_reader/filter.rs:63-106 (ArrowPredicateFn doc example "b > 0") + RowFilter semantics :138-170
+static void test_row_filter() {
+  Schema schema{{"a", DataType::Int64, true}, {"b", DataType::Int64, true}};
+  auto a = std::make_shared<Int64Array>(Int64Array::from(std::vector<O<int64_t>>{1, 2, 3, N, 5, 6}));
+  auto b = std::make_shared<Int64Array>(Int64Array::from(std::vector<O<int64_t>>{-1, 4, 0, 7, N, 9}));
+  auto batch = RecordBatch::try_new(schema, {a, b}).unwrap();
+  auto p1 = std::make_shared<parquet::ArrowPredicateFn>(std::vector<size_t>{1}, [](const RecordBatch &rb) {
+    return cmpk::gt(as_primitive<int64_t>(rb.column(0)), new_scalar<int64_t>(0));  // b > 0 (null => dropped)
+  });
+  auto p2 = std::make_shared<parquet::ArrowPredicateFn>(std::vector<size_t>{0}, [](const RecordBatch &rb) {
+    return cmpk::lt(as_primitive<int64_t>(rb.column(0)), new_scalar<int64_t>(6));  // a < 6, evaluated on the surviving rows only
+  });
+  auto out = parquet::RowFilter({p1, p2}).apply(batch).unwrap();
+  CHECK_EQ(1, out.num_rows());  // rows with b > 0: (2,4) (null,7) (6,9); of those a < 6: (2,4) — a null `a` is dropped
+  CHECK((as_primitive<int64_t>(out.column(0)).to_vec() == std::vector<O<int64_t>>{2}));
+  CHECK((as_primitive<int64_t>(out.column(1)).to_vec() == std::vector<O<int64_t>>{4}));
+  auto bad = std::make_shared<parquet::ArrowPredicateFn>(std::vector<size_t>{0}, [](const RecordBatch &) {
+    return Result<BooleanArray>(BooleanArray::from(std::vector<bool>{true}));
+  });
+  CHECK(parquet::RowFilter({bad}).apply(batch).is_err());
+}
+
+// arrow-ipc/src/reader.rs:1587-1671 StreamReader over a stream written by another Arrow implementation (the Python test
+// writes it with pyarrow into $ACU_TEST_IPC_FILE: a: int64 [1, null, 3], s: utf8 ["x", null, "hello"], b: bool [true,
+// false, null], f: float32 [1.5, 2.5, 3.5]; then a second batch = rows 1..3 of the first)
+static void test_ipc_stream_reader() {
+  const char *path = std::getenv("ACU_TEST_IPC_FILE");
+  if (!path) { std::printf("  (ACU_TEST_IPC_FILE not set: ipc stream test skipped)\n"); return; }
+  std::FILE *fp = std::fopen(path, "rb");
+  CHECK(fp != nullptr);
+  if (!fp) return;
+  std::vector<uint8_t> bytes;
+  uint8_t buf[4096];
+  size_t n;
+  while ((n = std::fread(buf, 1, sizeof buf, fp)) > 0) bytes.insert(bytes.end(), buf, buf + n);
+  std::fclose(fp);
+  auto reader = ipc::StreamReader::try_new(bytes).unwrap();
+  CHECK_EQ(4u, reader.schema().size());
+  CHECK_EQ(std::string("s"), reader.schema()[1].name);
+  auto b1 = reader.next().unwrap();
+  CHECK(b1.has_value());
+  CHECK_EQ(3, b1->num_rows());
+  CHECK((as_primitive<int64_t>(b1->column(0)).to_vec() == std::vector<O<int64_t>>{1, N, 3}));
+  CHECK((as_string(b1->column(1)).to_vec() == std::vector<O<std::string>>{std::string("x"), N, std::string("hello")}));
+  CHECK((as_boolean(b1->column(2)).to_vec() == std::vector<O<bool>>{true, false, N}));
+  CHECK((as_primitive<float>(b1->column(3)).to_vec() == std::vector<O<float>>{1.5f, 2.5f, 3.5f}));
+  CHECK(!b1->column(3)->nulls().has_value());  // null_count 0 => no NullBuffer (reader.rs:271)
+  auto b2 = reader.next().unwrap();
+  CHECK(b2.has_value());
+  CHECK_EQ(2, b2->num_rows());
+  CHECK((as_primitive<int64_t>(b2->column(0)).to_vec() == std::vector<O<int64_t>>{N, 3}));
+  CHECK((as_string(b2->column(1)).to_vec() == std::vector<O<std::string>>{N, std::string("hello")}));
+  // the decoded batch feeds the hot path directly: filter by (a is not null)
+  auto kept = filter_record_batch(*b2, arrow_cuda::compute::kernels::boolean::is_not_null(*b2->column(0)).unwrap()).unwrap();
+  CHECK_EQ(1, kept.num_rows());
+  auto end = reader.next().unwrap();
+  CHECK(!end.has_value());
+  CHECK(reader.is_finished());
+  CHECK_EQ(ipc::StreamReader::try_new(std::vector<uint8_t>{}).unwrap_err().message, std::string("Ipc error: Expected schema message, found empty stream."));
+}
+
 int main() {
   try {
     Context::get(0);
@@ -463,6 +597,12 @@ int main() {
       {"distinct", test_distinct},
       {"cast_from_int64", test_cast_from_int64},
       {"aggregates", test_aggregates},
+      {"nullif", test_nullif},
+      {"zip", test_zip},
+      {"concat", test_concat},
+      {"cmp_utf8", test_cmp_utf8},
+      {"row_filter", test_row_filter},
+      {"ipc_stream_reader", test_ipc_stream_reader},
   };
   for (auto &t : tests) {
     int before = g_failed;

@@ -58,6 +58,8 @@ enum {
   ACU_ERR_CAST = 6,                /* ArrowError::CastError                     */
   ACU_ERR_NOT_YET_IMPLEMENTED = 7, /* ArrowError::NotYetImplemented             */
   ACU_ERR_PANIC_OUT_OF_BOUNDS = 8, /* the reference panics (take.rs:447,454)    */
+  ACU_ERR_IPC = 9,                 /* ArrowError::IpcError                      */
+  ACU_ERR_PARSE = 10,              /* ArrowError::ParseError                    */
   ACU_ERR_CUDA = 100,              /* CUDA runtime error (detail.cuda_error)    */
   ACU_ERR_NCCL = 101,              /* NCCL error                                */
   ACU_ERR_OUT_OF_MEMORY = 102
@@ -469,6 +471,19 @@ acu_status acu_offsets_append(acu_ctx *ctx, int32_t offset_bytes, const void *sr
                               int64_t count, int64_t base, void *dst_offsets, int64_t dst_first,
                               int64_t *out_src_begin, int64_t *out_src_end);
 
+/* concat (arrow-select/src/concat.rs:495-577): n columns of the same kind / width appended in order into the caller-owned
+ * `out` (capacities: total rows * width; boolean / validity bitmaps acu_bitmap_bytes(total rows); BYTES: total rows + 1
+ * offsets and out->data_capacity value bytes). Values and the bytes under null slots are copied as they are; the result
+ * carries a validity buffer iff some input has nulls (NullBufferBuilder semantics) — a single input keeps its NullBuffer
+ * presence (the reference returns array.slice(0, len)). Errors: no input => ACU_ERR_COMPUTE "concat requires input of at
+ * least one array"; mixed kinds / widths => ACU_ERR_INVALID_ARGUMENT; i32 offsets overflowing => ACU_ERR_OFFSET_OVERFLOW
+ * (generic_bytes_builder.rs:185-189). Inputs without a cached null_count cost one count each. */
+acu_status acu_concat(acu_ctx *ctx, int32_t n_arrays, const acu_column *arrays, acu_column_out *out);
+/* concat_batches (concat.rs:607-640): columns[b * n_columns + c] = column c of batch b; outs[c] = concat of field c over the
+ * batches; *out_rows = rows of the result. No batch => every field is empty. */
+acu_status acu_concat_batches(acu_ctx *ctx, int32_t n_batches, int32_t n_columns, const acu_column *columns,
+                              acu_column_out *outs, int64_t *out_rows);
+
 /* ------------------------------------------------------------------------- */
 /* Arrow C Data Interface / C Device Data Interface                           */
 /* ------------------------------------------------------------------------- */
@@ -530,6 +545,27 @@ acu_status acu_export_column(acu_ctx *ctx, const acu_column *col, acu_dtype dtyp
  * (large) utf8 / binary formats; anything else => ACU_ERR_NOT_YET_IMPLEMENTED. */
 acu_status acu_import_column(const struct ArrowDeviceArray *in, const struct ArrowSchema *schema,
                              acu_column *out, acu_dtype *out_dtype);
+
+/* ------------------------------------------------------------------------- */
+/* Arrow IPC stream -> HBM (arrow-ipc/src/reader.rs StreamReader)            */
+/* ------------------------------------------------------------------------- */
+/* StreamReader::try_new (reader.rs:1587-1640) over an in-memory IPC stream (`stream` must stay valid until close): reads the
+ * schema message. Flat primitive / boolean / Utf8 / Binary / LargeUtf8 / LargeBinary fields, uncompressed little-endian
+ * bodies; anything else => ACU_ERR_NOT_YET_IMPLEMENTED naming the field. Errors keep the reference's texts ("Expected schema
+ * message, found empty stream.", "Expected a schema as the first message in the stream, got: RecordBatch", ...). */
+typedef struct acu_ipc_stream acu_ipc_stream;
+acu_status acu_ipc_stream_open(acu_ctx *ctx, const uint8_t *stream, int64_t stream_len, acu_ipc_stream **out,
+                               int32_t *out_n_fields);
+/* Field i of the schema: kind (acu_column_kind), width (element / offset bytes), dtype (acu_dtype, -1 for boolean and byte
+ * fields), nullable, name (owned by the stream). */
+acu_status acu_ipc_stream_field(const acu_ipc_stream *s, int32_t i, int32_t *kind, int32_t *width, int32_t *dtype,
+                                int32_t *nullable, const char **name);
+/* StreamReader::next (maybe_next, reader.rs:1646-1671): decodes the next RecordBatch message. Its body goes to HBM with ONE
+ * host->device copy into a buffer owned by the stream, and out_columns[0..n_fields) are VIEWS into that buffer (IPC body
+ * buffers are 8-byte aligned Arrow buffers: nothing is re-laid out); they stay valid until the next call or close. The
+ * validity pointer is NULL when the field node's null_count is 0 (reader.rs:271). *out_rows = -1 at the end of the stream. */
+acu_status acu_ipc_stream_next(acu_ctx *ctx, acu_ipc_stream *s, acu_column *out_columns, int64_t *out_rows);
+void acu_ipc_stream_close(acu_ctx *ctx, acu_ipc_stream *s);
 
 /* ------------------------------------------------------------------------- */
 /* multi-GPU: row-range shards, NCCL only for the final scalar reduce        */

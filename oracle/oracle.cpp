@@ -1562,4 +1562,73 @@ acu_status orc_cmp_byte_view(acu_cmp_op op, const void *l_views, const uint8_t *
   });
 }
 
+// concat (arrow-select/src/concat.rs:495-577) over host columns: concat_primitives / concat_boolean / concat_bytes are
+// builder.append_array per input (:334-368). acu_column as in include/arrow_cuda.h with HOST pointers.
+acu_status orc_concat(int32_t n, const acu_column *cols, acu_column_out *out) {
+  if (n <= 0) return fail(ACU_ERR_COMPUTE, -1, 0, 0, 0, "concat requires input of at least one array");  // :496-499
+  for (int i = 1; i < n; ++i)
+    if (cols[i].kind != cols[0].kind || cols[i].width != cols[0].width)
+      return fail(ACU_ERR_INVALID_ARGUMENT, i, 0, 0, 0,
+                  "It is not possible to concatenate arrays of different data types (kind %d width %d, kind %d width %d).",
+                  cols[0].kind, cols[0].width, cols[i].kind, cols[i].width);
+  const int kind = cols[0].kind, w = cols[0].width;
+  int64_t total = 0;
+  bool materialized = false;  // NullBufferBuilder::append_buffer materialises on the first buffer with nulls (null.rs:209-218)
+  for (int i = 0; i < n; ++i) {
+    total += cols[i].array.len;
+    if (cols[i].array.validity && resolve_null_count(&cols[i].array) > 0) materialized = true;
+  }
+  const bool single = n == 1;  // array.slice(0, len): buffers shared, NullBuffer kept as it is (:500-503)
+  const bool keep = single && cols[0].array.validity != nullptr;
+  out->array.len = total;
+  out->array.has_validity = 0;
+  out->array.null_count = 0;
+  out->data_len = 0;
+  if (materialized || keep) memset(out->array.validity, 0, acu_bitmap_bytes(total));
+  if (kind == ACU_COL_BOOLEAN) memset(out->array.values, 0, acu_bitmap_bytes(total));
+  int64_t row = 0, bytes = 0;
+  if (kind == ACU_COL_BYTES) memset(out->array.values, 0, (size_t)w);
+  for (int i = 0; i < n; ++i) {
+    const acu_column &c = cols[i];
+    const int64_t len = c.array.len;
+    if (kind == ACU_COL_PRIMITIVE) {
+      memcpy(static_cast<uint8_t *>(out->array.values) + (size_t)row * w, c.array.values, (size_t)len * w);  // extend_from_slice(values)
+    } else if (kind == ACU_COL_BOOLEAN) {
+      const uint8_t *src = static_cast<const uint8_t *>(c.array.values);
+      for (int64_t k = 0; k < len; ++k)
+        if (get_bit(src, c.array.values_offset + k)) set_bit(static_cast<uint8_t *>(out->array.values), row + k);
+    } else if (len > 0) {  // GenericByteBuilder::append_array (generic_bytes_builder.rs:169-206)
+      auto off = [&](int64_t k) -> int64_t { return w == 4 ? (int64_t)static_cast<const int32_t *>(c.array.values)[k] : static_cast<const int64_t *>(c.array.values)[k]; };
+      const int64_t first = off(0), last = off(len);
+      const int64_t limit = w == 4 ? (int64_t)INT32_MAX : INT64_MAX;
+      if (bytes != first) {  // shifting all the offsets: checked_add(shift, last)
+        const int64_t shift = bytes - first;
+        if (shift + last > limit || (w == 4 && shift + last < (int64_t)INT32_MIN))
+          return fail(ACU_ERR_OFFSET_OVERFLOW, -1, 0, 0, (uint64_t)(shift + last), "%" PRId64, shift + last);
+      }
+      for (int64_t k = 1; k <= len; ++k) {
+        const int64_t v = bytes + (off(k) - first);
+        if (w == 4) static_cast<int32_t *>(out->array.values)[row + k] = (int32_t)v;
+        else static_cast<int64_t *>(out->array.values)[row + k] = v;
+      }
+      if (bytes + (last - first) > out->data_capacity)
+        return fail(ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, (uint64_t)(bytes + (last - first)), "output data capacity %" PRId64 " < required %" PRId64,
+                    out->data_capacity, bytes + (last - first));
+      memcpy(out->data + bytes, c.data + first, (size_t)(last - first));
+      bytes += last - first;
+    }
+    if (materialized || keep) {
+      for (int64_t k = 0; k < len; ++k)
+        if (!c.array.validity || get_bit(c.array.validity, c.array.validity_offset + k)) set_bit(out->array.validity, row + k);
+    }
+    row += len;
+  }
+  out->data_len = bytes;
+  if (materialized || keep) {
+    out->array.has_validity = 1;
+    out->array.null_count = total - count_bits(out->array.validity, 0, total);
+  }
+  return ACU_OK;
+}
+
 }  // extern "C"

@@ -592,6 +592,30 @@ for name, line, op, sc, exp in [
     ("utf8_view_array_gt_eq_scalar", 1440, "gt_eq", LARGE_1, [True, False, False, False, False]), ("utf8_view_array_gt_eq_scalar_small", 1447, "gt_eq", SMALL_1, [True, True, True, True, True])]:
     case(name, f"{CP}:{line}", "cmp_view", cmp=op, left={"bytes": TA2}, right={"bytes": [sc], "scalar": True}, expect={"data": exp})
 
+# =========================================================================================
+# concat — arrow-select/src/concat.rs
+# =========================================================================================
+CC = "arrow-select/src/concat.rs"
+case("concat_empty_vec", CC + ":698", "concat", arrays=[], expect_error="Compute error: concat requires input of at least one array")
+case("concat_one_element_vec", CC + ":718", "concat", arrays=[arr("int64", [-1, 2, None])], expect={"data": [-1, 2, None]})
+case("concat_primitive_arrays", CC + ":880", "concat",
+     arrays=[arr("int64", [-1, -1, 2, None, None]), arr("int64", [101, 102, 103, None]), arr("int64", [256, 512, 1024])],
+     expect={"data": [-1, -1, 2, None, None, 101, 102, 103, None, 256, 512, 1024]})
+case("concat_primitive_array_slices", CC + ":907", "concat",
+     arrays=[arr("int64", [-1, -1, 2, None, None], slice=(1, 3)), arr("int64", [101, 102, 103, None], slice=(1, 3))],
+     expect={"data": [-1, 2, None, 102, 103, None]})
+case("concat_boolean_primitive_arrays", CC + ":930", "concat",
+     arrays=[arr("bool", [True, True, False, None, None, False]), arr("bool", [None, False, True, False])],
+     expect={"data": [True, True, False, None, None, False, None, False, True, False]})
+case("concat_no_nulls_has_no_null_buffer", CC + ":334-343", "concat", arrays=[arr("int32", [1, 2]), arr("int32", [3])],
+     expect={"data": [1, 2, 3], "no_validity": True})
+case("concat_string_arrays", CC + ":832", "concat_utf8",
+     arrays=[{"strings": ["hello", "world"]}, {"strings": ["2", "3", "4"]}, {"strings": ["foo", "bar", None, "baz"]}],
+     expect={"strings": ["hello", "world", "2", "3", "4", "foo", "bar", None, "baz"]})
+case("concat_string_array_slices", CC + ":355-368", "concat_utf8",
+     arrays=[{"strings": ["hello", "world", "x"], "slice": [1, 2]}, {"strings": ["a", None, "bcd", "e"], "slice": [1, 3]}],
+     expect={"strings": ["world", "x", None, "bcd", "e"]})
+
 out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "vectors.json")
 with open(out, "w") as f:
     json.dump({"reference": "apache/arrow-rs 59.2.0 @ cd7c6b83", "cases": cases}, f, indent=0)

@@ -190,6 +190,11 @@ def run_case(backend, c):
             return getattr(backend, op)(build_array(c["a"]))
         if op in ("and_", "or_", "and_not", "and_kleene", "or_kleene"):
             return getattr(backend, op)(build_array(c["a"]), build_array(c["b"]))
+        if op == "concat":
+            return backend.concat([build_array(a) for a in c["arrays"]])
+        if op == "concat_utf8":
+            r = backend.concat([acu.Utf8Column(*build_strings(a)) for a in c["arrays"]])
+            return r.offsets, r.data, r.nulls
         if op == "cmp_bytes":
             return backend.cmp_bytes(getattr(abi, c["cmp"].upper()), build_bytes_column(c["left"], c.get("large", False)),
                                      build_bytes_column(c["right"], c.get("large", False)))
@@ -223,7 +228,7 @@ def run_case(backend, c):
         arr, count = res
         assert arr.to_list() == e["positions"]
         assert count == e["count"]
-    elif op in ("filter_utf8", "take_utf8"):
+    elif op in ("filter_utf8", "take_utf8", "concat_utf8"):
         assert strings_of(*res) == e["strings"]
     elif op in ("sum", "min", "max", "sum_checked"):
         assert _match(e["scalar"], res), f"expected {e['scalar']!r}, got {res!r}"

@@ -48,6 +48,7 @@ class Oracle:
             "orc_sum_checked": [i32, P(abi.Array), P(u64), P(i64)],
             "orc_cmp_bytes": [i32, i32, vp, vp, P(abi.Array), vp, vp, P(abi.Array), P(abi.ArrayOut)],
             "orc_cmp_byte_view": [i32, vp, P(vp), i32, P(abi.Array), vp, P(vp), i32, P(abi.Array), P(abi.ArrayOut)],
+            "orc_concat": [i32, P(abi.Column), P(abi.ColumnOut)],
             "orc_nullif": [P(abi.Array), P(abi.Array), P(abi.ArrayOut)],
             "orc_zip": [i32, P(abi.Array), P(abi.Array), P(abi.Array), P(abi.ArrayOut)],
             "orc_generate_values": [i32, u64, i64, u64, vp, i64],
@@ -187,6 +188,49 @@ class Oracle:
         ad, bd = acu.host_descriptor(a), acu.host_descriptor(b)
         self.check(self.lib.orc_cmp(a.dtype, op, C.byref(ad), C.byref(bd), C.byref(out)))
         return self._result(out, vals, valid, BOOL)
+
+    # -- concat ---------------------------------------------------------------------------------
+    def concat(self, columns):
+        n = len(columns)
+        cols = (abi.Column * max(n, 1))()
+        keep = []
+        for c, col in enumerate(columns):
+            if isinstance(col, acu.Utf8Column):
+                cols[c].kind, cols[c].width = abi.COL_BYTES, col.offsets.dtype.itemsize
+                cols[c].array = acu.host_descriptor(col.nulls)
+                cols[c].array.values = col.offsets.ctypes.data
+                cols[c].data = col.data.ctypes.data
+            else:
+                cols[c].kind = abi.COL_BOOLEAN if col.dtype == BOOL else abi.COL_PRIMITIVE
+                cols[c].width = 0 if col.dtype == BOOL else col.width()
+                cols[c].array = acu.host_descriptor(col)
+            keep.append(col)
+        rows = sum(col.length for col in columns)
+        out = abi.ColumnOut()
+        proto = columns[0] if columns else HostArray(acu.U8, np.zeros(0, np.uint8), 0)
+        valid = np.zeros(bitmap_bytes(max(rows, 1)) + 8, dtype=np.uint8)
+        out.array.validity = valid.ctypes.data
+        if isinstance(proto, acu.Utf8Column):
+            offs = np.zeros(rows + 2, dtype=proto.offsets.dtype)
+            cap = sum(int(c.data.nbytes) for c in columns)
+            data = np.zeros(cap + 16, dtype=np.uint8)
+            out.array.values, out.data, out.data_capacity = offs.ctypes.data, data.ctypes.data, cap
+        else:
+            vals = np.zeros((bitmap_bytes(max(rows, 1)) if proto.dtype == BOOL else rows * proto.width()) + 16, dtype=np.uint8)
+            out.array.values = vals.ctypes.data
+        self.check(self.lib.orc_concat(n, cols, C.byref(out)))
+        m = out.array.len
+        validity = valid[: bitmap_bytes(m)].copy() if out.array.has_validity else None
+        nc = out.array.null_count if out.array.has_validity else 0
+        if isinstance(proto, acu.Utf8Column):
+            return acu.Utf8Column(offs[: m + 1].copy(), data[: out.data_len].copy(), HostArray(acu.U8, np.zeros(0, np.uint8), m, validity, 0, 0, nc))
+        if proto.dtype == BOOL:
+            return HostArray(BOOL, vals[: bitmap_bytes(m)].copy(), m, validity, 0, 0, nc)
+        return HostArray(proto.dtype, vals[: m * proto.width()].copy().view(acu.NP_DTYPES[proto.dtype]), m, validity, 0, 0, nc)
+
+    def concat_batches(self, batches):
+        ncols = len(batches[0]) if batches else 0
+        return [self.concat([b[c] for b in batches]) for c in range(ncols)]
 
     # -- cmp on Utf8 / Binary (Utf8Column) and Utf8View / BinaryView (ViewColumn) operands -----------
     def cmp_bytes(self, op, a, b):

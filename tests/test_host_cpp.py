@@ -31,6 +31,23 @@ def test_host_binary_refuses_to_run_without_gpu():
 def test_host_mirror_reference_tests_pass():
     if not os.path.exists(BIN):
         subprocess.run(["make", "-s", "-C", HOST], check=True)
-    r = subprocess.run([BIN], capture_output=True, text=True, timeout=300)
+    env = dict(os.environ)
+    try:  # an IPC stream written by another Arrow implementation for the StreamReader test
+        import io
+        import tempfile
+        import pyarrow as pa
+        t = pa.table({"a": pa.array([1, None, 3], type=pa.int64()), "s": pa.array(["x", None, "hello"]),
+                      "b": pa.array([True, False, None]), "f": pa.array([1.5, 2.5, 3.5], type=pa.float32())})
+        sink = io.BytesIO()
+        with pa.ipc.new_stream(sink, t.schema) as w:
+            w.write_table(t)
+            w.write_table(t.slice(1, 2))
+        f = tempfile.NamedTemporaryFile(suffix=".arrows", delete=False)
+        f.write(sink.getvalue())
+        f.close()
+        env["ACU_TEST_IPC_FILE"] = f.name
+    except ImportError:
+        pass
+    r = subprocess.run([BIN], capture_output=True, text=True, timeout=300, env=env)
     print(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
