@@ -221,7 +221,7 @@ PROTOTYPES = {
     "acu_bitmap_fill": (i32, [vp, vp, i64, i64, i32]),
     "acu_offsets_append": (i32, [vp, i32, vp, i64, i64, i64, vp, i64, P(i64), P(i64)]),
     "acu_export_column": (i32, [vp, P(Column), i32, i32, RELEASE_OWNER, vp, P(ArrowDeviceArray), P(ArrowSchema)]),
-    "acu_import_column": (i32, [P(ArrowDeviceArray), P(ArrowSchema), P(Column), P(i32)]),
+    "acu_import_column": (i32, [vp, P(ArrowDeviceArray), P(ArrowSchema), P(Column), P(i32)]),
     "acu_comm_get_unique_id": (i32, [vp]),
     "acu_comm_init": (i32, [vp, vp, i32, i32]),
     "acu_comm_destroy": (i32, [vp]),

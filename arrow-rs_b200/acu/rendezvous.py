@@ -44,38 +44,69 @@ class Group:
             self._torch_dist = dist
         ctx.check(lib.acu_comm_init(h, idb, rank, world))
 
-    def _socket_broadcast(self, payload):
+    @staticmethod
+    def _recv_exact(sock, n):
+        """Read exactly n bytes or raise: recv() returning b'' means the peer closed the connection."""
+        buf = b""
+        while len(buf) < n:
+            chunk = sock.recv(n - len(buf))
+            if not chunk:
+                raise ConnectionError(f"rendezvous peer closed the connection after {len(buf)} of {n} bytes")
+            buf += chunk
+        return buf
+
+    def _socket_broadcast(self, payload, timeout=120.0):
+        """Rank 0 hands the NCCL unique id to every other rank over TCP. A client introduces itself with
+        (job nonce, rank); rank 0 answers each DISTINCT valid rank once and ignores stray connections, so a port scanner or a
+        stale process cannot consume a slot. Every wait is bounded by `timeout` seconds."""
         addr = os.environ.get("MASTER_ADDR", "127.0.0.1")
         port = int(os.environ.get("MASTER_PORT", "29500")) + 17
+        nonce = (os.environ.get("TORCHELASTIC_RUN_ID", "") + ":" + os.environ.get("MASTER_PORT", "29500")).encode()[:64].ljust(64, b"\0")
         if self.rank == 0:
             srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
             srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
             srv.bind((addr, port))
-            srv.listen(self.world)
-            for _ in range(self.world - 1):
-                conn, _ = srv.accept()
-                conn.sendall(struct.pack("<I", len(payload)) + payload)
-                conn.close()
-            srv.close()
+            srv.listen(self.world + 8)
+            deadline = time.time() + timeout
+            served = set()
+            try:
+                while len(served) < self.world - 1:
+                    left = deadline - time.time()
+                    if left <= 0:
+                        raise TimeoutError(f"rendezvous: only ranks {sorted(served)} of {self.world - 1} peers connected within {timeout:.0f} s")
+                    srv.settimeout(left)
+                    try:
+                        conn, _ = srv.accept()
+                    except socket.timeout:
+                        continue
+                    try:
+                        conn.settimeout(5.0)
+                        hello = self._recv_exact(conn, 68)
+                        peer = struct.unpack("<I", hello[64:])[0]
+                        if hello[:64] == nonce and 0 < peer < self.world and peer not in served:
+                            conn.sendall(struct.pack("<I", len(payload)) + payload)
+                            served.add(peer)
+                    except (OSError, ConnectionError):
+                        pass  # a stray or broken connection does not consume a slot
+                    finally:
+                        conn.close()
+            finally:
+                srv.close()
             return payload
-        deadline = time.time() + 120
+        deadline = time.time() + timeout
         while True:
             try:
                 s = socket.create_connection((addr, port), timeout=5)
-                break
-            except OSError:
+                s.settimeout(max(deadline - time.time(), 1.0))
+                s.sendall(nonce + struct.pack("<I", self.rank))
+                n = struct.unpack("<I", self._recv_exact(s, 4))[0]
+                data = self._recv_exact(s, n)
+                s.close()
+                return data
+            except (OSError, ConnectionError):
                 if time.time() > deadline:
                     raise
                 time.sleep(0.1)
-        buf = b""
-        while len(buf) < 4:
-            buf += s.recv(4 - len(buf))
-        n = struct.unpack("<I", buf)[0]
-        data = b""
-        while len(data) < n:
-            data += s.recv(n - len(data))
-        s.close()
-        return data
 
     def barrier(self):
         self.ctx.sync()

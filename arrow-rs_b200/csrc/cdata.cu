@@ -68,6 +68,14 @@ extern "C" acu_status acu_export_column(acu_ctx *ctx, const acu_column *col, acu
                                         void (*release_owner)(void *), void *owner, struct ArrowDeviceArray *out_array,
                                         struct ArrowSchema *out_schema) {
   if (!col || !out_array) return ctx ? acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "export: NULL argument") : ACU_ERR_INVALID_ARGUMENT;
+  out_array->array.release = nullptr;  // stays NULL on every error path: the caller of a failed export has nothing to release
+  if (device_type != ARROW_DEVICE_CPU) {
+    // a device column needs the ctx: no event is handed over (sync_event = NULL), so the data must be complete when this
+    // returns — synchronise BEFORE anything is allocated or published
+    if (!ctx) return ACU_ERR_INVALID_ARGUMENT;
+    ACU_ENTER(ctx);
+    ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   const acu_array &a = col->array;
   // one logical offset for every buffer: the bit offset of the validity (and of boolean values)
   int64_t offset = a.validity ? a.validity_offset : 0;
@@ -103,10 +111,6 @@ extern "C" acu_status acu_export_column(acu_ctx *ctx, const acu_column *col, acu
   out_array->device_type = device_type;
   out_array->device_id = (device_type == ARROW_DEVICE_CPU || !ctx) ? -1 : ctx->device;
   out_array->sync_event = nullptr;
-  if (ctx && device_type != ARROW_DEVICE_CPU) {  // no event is handed over: the data is complete when this returns
-    ACU_ENTER(ctx);
-    ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  }
   if (out_schema) {
     memset(out_schema, 0, sizeof(*out_schema));
     out_schema->format = format_of(col->kind, col->width, dtype);
@@ -118,9 +122,22 @@ extern "C" acu_status acu_export_column(acu_ctx *ctx, const acu_column *col, acu
   return ACU_OK;
 }
 
-extern "C" acu_status acu_import_column(const struct ArrowDeviceArray *in, const struct ArrowSchema *schema, acu_column *out,
+extern "C" acu_status acu_import_column(acu_ctx *ctx, const struct ArrowDeviceArray *in, const struct ArrowSchema *schema, acu_column *out,
                                         acu_dtype *out_dtype) {
-  if (!in || !schema || !out || !in->array.release || !schema->release) return ACU_ERR_INVALID_ARGUMENT;
+  if (!in || !schema || !out || !in->array.release || !schema->release)
+    return ctx ? acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "import: NULL argument or released array") : ACU_ERR_INVALID_ARGUMENT;
+  // Arrow C Device Data Interface: the consumer must know where the buffers live and must wait on a non-NULL sync_event
+  // before touching them
+  if (in->device_type == ARROW_DEVICE_CUDA || in->device_type == ARROW_DEVICE_CUDA_HOST) {
+    if (!ctx) return ACU_ERR_INVALID_ARGUMENT;  // device memory cannot be consumed without a stream to order against
+    ACU_ENTER(ctx);
+    if (in->device_type == ARROW_DEVICE_CUDA && in->device_id != ctx->device)
+      return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "import: array lives on CUDA device %lld, this context drives device %d",
+                      (long long)in->device_id, ctx->device);
+    if (in->sync_event) ACU_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, *static_cast<cudaEvent_t *>(in->sync_event), 0));
+  } else if (in->device_type != ARROW_DEVICE_CPU) {
+    return ctx ? acu_fail(ctx, ACU_ERR_NOT_YET_IMPLEMENTED, -1, 0, 0, 0, "import: ArrowDeviceType %d", (int)in->device_type) : ACU_ERR_NOT_YET_IMPLEMENTED;
+  }
   int32_t kind, width;
   acu_dtype dtype;
   if (!parse_format(schema->format, &kind, &width, &dtype)) return ACU_ERR_NOT_YET_IMPLEMENTED;  // nested / temporal / decimal formats

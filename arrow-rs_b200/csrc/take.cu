@@ -177,6 +177,9 @@ __global__ void __launch_bounds__(256, MINB) k_take(const TakeBatch batch) {
       const int j = k * 32 + lane;
       live[k] = j0 + j < a.m;
       ix[k] = live[k] ? widen<IT>(s_idx[wid][buf][j]) : 0;
+      // take() converts the indices with ToIndices BEFORE take_native (take.rs:100): i32 is REINTERPRETED as u32 and i8 / i16
+      // are widened with `as u32`, so `index.as_usize()` (take.rs:442) zero-extends — a negative i32 index is the in-bounds
+      // row 2^32 + idx when values.len() exceeds it, exactly as here
       inb[k] = live[k] && (uint64_t)ix[k] < (uint64_t)a.n_values;
     }
     // ---- 8 independent gathers in flight per lane ----
@@ -262,34 +265,10 @@ uint64_t index_max(acu_dtype t) {
   }
 }
 
-// Experiment hook (tools/take_sweep.sh): ACU_TAKE_VARIANT = "PL,MINB" selects another tiling of the Int64 / UInt32-index gather.
-template <int PL, int MINB>
-acu_status launch_take_variant(acu_ctx *ctx, const TakeBatch &tb, int n_cols) {
-  const int64_t tiles = ((tb.col[0].m + 32 * PL - 1) / (32 * PL) + 7) / 8;
-  ACU_LAUNCH_TIMED(ctx, ACU_K_TAKE, (k_take<8, 4, false, PL, MINB>), dim3(acu_wave_grid(ctx, k_take<8, 4, false, PL, MINB>, 256, 0, tiles), n_cols), 256, 0, tb);
-  return ACU_OK;
-}
-
 template <int W>
 acu_status launch_take_w(acu_ctx *ctx, int kind, const TakeBatch &tb, int n_cols) {
   const TakeArgs &ta = tb.col[0];
   constexpr int TAKE_WTILE = TAKE_WTILE_DEFAULT;
-  if (W == 8 && kind == 4 && !ta.vbits) {
-    static const char *var = getenv("ACU_TAKE_VARIANT");
-    if (var) {
-      int pl = 0, mb = 0;
-      if (sscanf(var, "%d,%d", &pl, &mb) == 2) {
-        if (pl == 8 && mb == 4) return launch_take_variant<8, 4>(ctx, tb, n_cols);
-        if (pl == 8 && mb == 5) return launch_take_variant<8, 5>(ctx, tb, n_cols);
-        if (pl == 8 && mb == 6) return launch_take_variant<8, 6>(ctx, tb, n_cols);
-        if (pl == 4 && mb == 6) return launch_take_variant<4, 6>(ctx, tb, n_cols);
-        if (pl == 4 && mb == 8) return launch_take_variant<4, 8>(ctx, tb, n_cols);
-        if (pl == 16 && mb == 2) return launch_take_variant<16, 2>(ctx, tb, n_cols);
-        if (pl == 16 && mb == 3) return launch_take_variant<16, 3>(ctx, tb, n_cols);
-        if (pl == 16 && mb == 4) return launch_take_variant<16, 4>(ctx, tb, n_cols);
-      }
-    }
-  }
   const int64_t tiles = ((ta.m + TAKE_WTILE - 1) / TAKE_WTILE + 7) / 8;  // CTAs: 8 warp tiles each
 #define ACU_TAKE_CASE(IT)                                                                                   \
   case IT:                                                                                                                   \
@@ -369,7 +348,7 @@ acu_status acu_take_common(acu_ctx *ctx, int32_t elem_bytes, const acu_array *va
 // (exact, the NullBuffer decision depends on it). *mode: bit 0 = an output validity was
 // produced, bit 1 = it came from take_bits(values.nulls) (None when it has no nulls).
 static TakeArgs take_args(int32_t elem_bytes, const acu_array *values, bool boolean_values, bool val_nulls, const acu_array *indices,
-                          bool idx_nulls, acu_array_out *out, unsigned long long *res) {
+                          acu_dtype /*index_dtype*/, bool idx_nulls, acu_array_out *out, unsigned long long *res) {
   TakeArgs ta{};
   ta.values = (elem_bytes > 0 && !boolean_values) ? values->values : nullptr;
   ta.n_values = values->len;
@@ -396,7 +375,7 @@ acu_status acu_take_col_launch(acu_ctx *ctx, int32_t elem_bytes, const acu_array
   out->null_count = 0;
   if (indices->len == 0) return ACU_OK;
   TakeBatch tb{};
-  tb.col[0] = take_args(elem_bytes, values, boolean_values, val_nulls, indices, idx_nulls, out, res);
+  tb.col[0] = take_args(elem_bytes, values, boolean_values, val_nulls, indices, index_dtype, idx_nulls, out, res);
   ACU_TRY(launch_take(ctx, tb.col[0].values ? elem_bytes : 1, kind, tb, 1));
   *mode = (tb.col[0].out_valid ? 1 : 0) | (val_nulls ? 2 : 0);
   return ACU_OK;
@@ -424,7 +403,7 @@ acu_status acu_take_cols_launch(acu_ctx *ctx, int n, const int32_t *elem_bytes, 
     int k = 0;
     for (int d = c; d < n && k < TAKE_BATCH_COLS; ++d) {
       if (done[d] || klass(d) != klass(c)) continue;
-      tb.col[k] = take_args(elem_bytes[d], values[d], boolean[d] != 0, val_nulls[d] != 0, indices, idx_nulls, outs[d], res[d]);
+      tb.col[k] = take_args(elem_bytes[d], values[d], boolean[d] != 0, val_nulls[d] != 0, indices, index_dtype, idx_nulls, outs[d], res[d]);
       modes[d] = (tb.col[k].out_valid ? 1 : 0) | (val_nulls[d] ? 2 : 0);
       done[d] = 1;
       ++k;

@@ -535,15 +535,19 @@ struct ArrowDeviceArray {
  * it, so the column must be a slice of a buffer whose row 0 is addressable — true of every
  * array this library or Arrow produces). `dtype` names the primitive type for the schema
  * format. The consumer's call of out_array->array.release invokes release_owner(owner) exactly
- * once. ctx may be NULL for ARROW_DEVICE_CPU columns. For device columns the ctx stream is
- * synchronised and sync_event is NULL. */
+ * once. ctx may be NULL only for ARROW_DEVICE_CPU columns. For device columns the ctx stream is
+ * synchronised first and sync_event is NULL. On any error out_array->array.release is NULL (nothing to release). */
 acu_status acu_export_column(acu_ctx *ctx, const acu_column *col, acu_dtype dtype, int32_t device_type,
                              void (*release_owner)(void *), void *owner,
                              struct ArrowDeviceArray *out_array, struct ArrowSchema *out_schema);
 /* View an imported (device or host) array as an acu_column: pointers into the producer's
  * buffers, valid until the caller invokes in->array.release. Flat primitive / boolean /
- * (large) utf8 / binary formats; anything else => ACU_ERR_NOT_YET_IMPLEMENTED. */
-acu_status acu_import_column(const struct ArrowDeviceArray *in, const struct ArrowSchema *schema,
+ * (large) utf8 / binary formats; anything else => ACU_ERR_NOT_YET_IMPLEMENTED.
+ * Device rules of the C Device Data Interface: for ARROW_DEVICE_CUDA / CUDA_HOST arrays `ctx` is required, a CUDA array's
+ * device_id must be the ctx's device (ACU_ERR_INVALID_ARGUMENT otherwise), and a non-NULL sync_event (a cudaEvent_t*) is
+ * waited on by the ctx stream before any later kernel of this ctx can touch the buffers. ARROW_DEVICE_CPU arrays yield HOST
+ * pointers (in->device_type tells the caller; ctx may be NULL); other device types => ACU_ERR_NOT_YET_IMPLEMENTED. */
+acu_status acu_import_column(acu_ctx *ctx, const struct ArrowDeviceArray *in, const struct ArrowSchema *schema,
                              acu_column *out, acu_dtype *out_dtype);
 
 /* ------------------------------------------------------------------------- */

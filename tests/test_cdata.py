@@ -143,7 +143,7 @@ def test_import_what_pyarrow_exports(lib, pa_arr, dtype):
         dev, sch = abi.ArrowDeviceArray(), abi.ArrowSchema()
         view._export_to_c_device(C.addressof(dev), C.addressof(sch))
         col, got_dtype = abi.Column(), C.c_int32(-1)
-        assert lib.acu_import_column(C.byref(dev), C.byref(sch), C.byref(col), C.byref(got_dtype)) == abi.OK
+        assert lib.acu_import_column(None, C.byref(dev), C.byref(sch), C.byref(col), C.byref(got_dtype)) == abi.OK
         assert col.array.len == len(view)
         if dtype is not None:
             assert got_dtype.value == dtype
@@ -162,7 +162,7 @@ def test_import_rejects_what_the_path_does_not_cover(lib):
     dev, sch = abi.ArrowDeviceArray(), abi.ArrowSchema()
     nested._export_to_c_device(C.addressof(dev), C.addressof(sch))
     col, dt = abi.Column(), C.c_int32(0)
-    assert lib.acu_import_column(C.byref(dev), C.byref(sch), C.byref(col), C.byref(dt)) == abi.ERR_NOT_YET_IMPLEMENTED
+    assert lib.acu_import_column(None, C.byref(dev), C.byref(sch), C.byref(col), C.byref(dt)) == abi.ERR_NOT_YET_IMPLEMENTED
     dev.array.release(C.byref(dev.array))
     sch.release(C.byref(sch))
 
@@ -193,8 +193,27 @@ def test_device_array_export_import_and_compute(gpu, oracle):
     gpu.check(gpu.lib.acu_export_column(gpu.h, C.byref(col), abi.I64, abi.DEVICE_CUDA, cb, 7, C.byref(dev), C.byref(sch)))
     assert dev.device_type == abi.DEVICE_CUDA and dev.device_id == 0 and sch.format == b"l" and dev.array.length == count
     back, dt = abi.Column(), C.c_int32(-1)
-    assert gpu.lib.acu_import_column(C.byref(dev), C.byref(sch), C.byref(back), C.byref(dt)) == abi.OK
+    assert gpu.lib.acu_import_column(gpu.h, C.byref(dev), C.byref(sch), C.byref(back), C.byref(dt)) == abi.OK
     assert dt.value == abi.I64 and back.array.values == out.values  # zero copy: the very same device pointer
+    # C Device Data Interface rules: device memory needs a ctx, and the right device
+    assert gpu.lib.acu_import_column(None, C.byref(dev), C.byref(sch), C.byref(abi.Column()), C.byref(C.c_int32())) == abi.ERR_INVALID_ARGUMENT
+    dev.device_id = 5
+    with pytest.raises(acu.ArrowError) as e:
+        gpu.check(gpu.lib.acu_import_column(gpu.h, C.byref(dev), C.byref(sch), C.byref(abi.Column()), C.byref(C.c_int32())))
+    assert "CUDA device 5" in str(e.value)
+    dev.device_id = 0
+    try:  # a producer-side event: the import must order the ctx stream behind it
+        from cuda.bindings import runtime as cudart
+        err, ev = cudart.cudaEventCreate()
+        assert int(err) == 0
+        cudart.cudaEventRecord(ev, 0)
+        holder = C.c_void_p(int(ev))
+        dev.sync_event = C.addressof(holder)
+        assert gpu.lib.acu_import_column(gpu.h, C.byref(dev), C.byref(sch), C.byref(back), C.byref(dt)) == abi.OK
+        dev.sync_event = None
+        cudart.cudaEventDestroy(ev)
+    except ImportError:
+        pass
     # next kernel on the imported column: sum
     bits, cnt = C.c_uint64(0), C.c_int64(0)
     gpu.check(gpu.lib.acu_aggregate(gpu.h, abi.I64, abi.SUM, C.byref(back.array), C.byref(bits), C.byref(cnt)))
@@ -209,3 +228,16 @@ def test_device_array_export_import_and_compute(gpu, oracle):
     assert pc.filter(pav, pa.array(pred.to_list()), null_selection_behavior="drop").to_pylist() == exp.to_list()
     dv.free()
     dp.free()
+
+
+def test_export_of_a_device_column_needs_a_ctx_and_leaves_nothing_to_release(lib):
+    """A failed export must not publish a live-looking ArrowArray (release stays NULL), and a device column cannot be
+    exported without the ctx whose stream has to be synchronised first."""
+    vals = np.arange(4, dtype=np.int64)
+    colc = abi.Column()
+    colc.kind, colc.width = abi.COL_PRIMITIVE, 8
+    colc.array.values, colc.array.len = vals.ctypes.data, 4
+    arr, sch = abi.ArrowDeviceArray(), abi.ArrowSchema()
+    cb = abi.RELEASE_OWNER(lambda owner: None)
+    assert lib.acu_export_column(None, C.byref(colc), abi.I64, abi.DEVICE_CUDA, cb, 1, C.byref(arr), C.byref(sch)) == abi.ERR_INVALID_ARGUMENT
+    assert not arr.array.release

@@ -216,3 +216,36 @@ def test_shard_outputs_concatenate_to_the_global_result(world):
         counts.append(f.length)
     assert pieces == whole.to_list() and pieces_s == whole_s
     assert sum(counts) == whole.length and list(np.cumsum([0] + counts[:-1])) == [sum(counts[:g]) for g in range(world)]
+
+
+def test_socket_rendezvous_ignores_strays_and_serves_each_rank_once(monkeypatch):
+    """acu/rendezvous.py: the NCCL unique id exchange over TCP (no torch): a stray connection must not consume a slot, a
+    peer that closes early must raise instead of spinning, every rank gets the payload."""
+    import threading
+    import time
+    sys.path.insert(0, os.path.join(REPO, "arrow-rs_b200"))
+    from acu.rendezvous import Group
+    port = _free_port()
+    monkeypatch.setenv("MASTER_ADDR", "127.0.0.1")
+    monkeypatch.setenv("MASTER_PORT", str(port - 17))
+    world, payload, got = 3, bytes(range(128)), {}
+
+    def run(rank):
+        g = Group.__new__(Group)
+        g.rank, g.world = rank, world
+        got[rank] = g._socket_broadcast(payload if rank == 0 else b"", timeout=20.0)
+
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    ts[0].start()
+    time.sleep(0.3)
+    with socket.create_connection(("127.0.0.1", port), timeout=5) as stray:  # connects, sends garbage, leaves
+        stray.sendall(b"hello")
+    for t in ts[1:]:
+        t.start()
+    for t in ts:
+        t.join(timeout=30)
+    assert got == {0: payload, 1: payload, 2: payload}
+    with pytest.raises(ConnectionError):
+        a, b = socket.socketpair()
+        b.close()
+        Group._recv_exact(a, 4)
