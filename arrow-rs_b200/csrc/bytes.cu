@@ -13,6 +13,7 @@
 //      offsets; i32 overflow reports the first running total above i32::MAX (take.rs:520-523);
 //   4. copy: one warp per 32 rows, each lane streams its row's bytes.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "bitmap.cuh"
 #include "internal.cuh"
@@ -499,6 +500,219 @@ __global__ void __launch_bounds__(BY_THREADS, 2) k_bytes_offsets_copy(const Byte
   }
 }
 
+// ---- dictionary gather: take_bytes from a SMALL source (Dictionary<Int32,Utf8> -> Utf8, cast/dictionary.rs:310-317) ----
+// A gather of 32 random dictionary rows through global memory costs 32 L1 wavefronts per load instruction whatever its
+// width (one 128-byte line per lane): with two offset loads and the value bytes per row that alone is ~5 cycles per row
+// per SM, i.e. the 1.4 ms the generic kernels need for 1e8 rows. Here the dictionary is first re-laid out as a table of
+// 16-byte zero-padded entries + one length byte per entry (k_dict_table; sources with an entry longer than 16 bytes keep
+// the generic path), every CTA keeps that table in shared memory (D x 17 bytes: 70 KB for D = 4096) and the gathers become
+// LDS.128 / LDS.U8 (a few cycles per warp). Rows are owned by warps (lane == row % 32, 128 rows per warp, 2048 per CTA
+// round so that the scan of the per-2048-row totals is the generic one); a row's bytes reach their final position by two
+// funnel shifts and predicated ATOMS.OR into a warp-private zeroed ring that mirrors the output's 16-byte alignment, and
+// completed 16-byte chunks leave as 128-bit stores. No CTA barrier in the copy except the one that turns the 16 warp
+// totals into warp base offsets.
+#define DG_THREADS 512
+#define DG_WARPS (DG_THREADS / 32)
+#define DG_WROWS (BY_ROWS / DG_WARPS)   // 128 rows per warp and round
+#define DG_ITERS (DG_WROWS / 32)        // 4 x 32 rows
+#define DG_WIN 1024                     // ring bytes per warp (power of two; a 32-row round writes <= 512 bytes)
+#define DG_WINW (DG_WIN / 4)
+#define DG_MAX_ENTRIES 8192
+
+__global__ void __launch_bounds__(256) k_dict_table(const int32_t *__restrict__ offs, const uint8_t *__restrict__ data, int64_t n_src,
+                                                    uint4 *__restrict__ table, uint8_t *__restrict__ lens, int *__restrict__ too_long) {
+  const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n_src) return;
+  const int32_t s = __ldg(offs + d), e = __ldg(offs + d + 1);
+  const int32_t len = e - s;
+  uint32_t w[4] = {0, 0, 0, 0};
+  if (len < 0 || len > 16) {
+    atomicOr(too_long, 1);
+  } else {
+    for (int k = 0; k < len; ++k) w[k >> 2] |= (uint32_t)__ldg(data + s + k) << (8 * (k & 3));
+  }
+  table[d] = make_uint4(w[0], w[1], w[2], w[3]);
+  lens[d] = (uint8_t)(len < 0 || len > 16 ? 0 : len);
+}
+
+struct DictArgs {
+  const uint32_t *keys;       // 32-bit keys (ToIndices of i32 / u32)
+  int64_t m;                  // output rows
+  uint32_t n_src;             // dictionary entries (<= DG_MAX_ENTRIES)
+  const uint32_t *out_valid;  // output validity (bit offset 0) or NULL: null slots get zero length
+  int detect_oob;
+  const uint4 *table;
+  const uint8_t *lens;
+  const int *too_long;        // set by k_dict_table: the kernels return immediately and the generic path runs
+};
+
+// pass 1: byte total of every 2048-row block (+ out-of-bounds keys at valid slots)
+__global__ void __launch_bounds__(DG_THREADS) k_dict_block_totals(const DictArgs a, int64_t blocks, int64_t *__restrict__ block_tot,
+                                                                  unsigned long long *__restrict__ res) {
+  extern __shared__ __align__(16) uint8_t s_dyn[];
+  __shared__ uint32_t s_wsum[DG_WARPS];
+  if (*a.too_long) return;
+  uint8_t *s_len = s_dyn;
+  for (uint32_t i = threadIdx.x; i < a.n_src; i += DG_THREADS) s_len[i] = a.lens[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned long long err = ~0ull;
+  for (int64_t blk = blockIdx.x; blk < blocks; blk += gridDim.x) {
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < BY_ROWS / DG_THREADS; ++k) {
+      const int64_t j = blk * BY_ROWS + (int64_t)k * DG_THREADS + threadIdx.x;
+      if (j < a.m) {
+        const uint32_t key = __ldg(a.keys + j);
+        bool use = true;
+        if (a.out_valid) use = (__ldg(a.out_valid + (j >> 5)) >> (j & 31)) & 1u;
+        if (use && key >= a.n_src) {
+          use = false;
+          if ((unsigned long long)j < err) err = (unsigned long long)j;
+        }
+        if (use) sum += s_len[key];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(ACU_FULL_MASK, sum, o);
+    if (lane == 0) s_wsum[wid] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t t = 0;
+      for (int w = 0; w < DG_WARPS; ++w) t += s_wsum[w];
+      block_tot[blk] = (int64_t)t;
+    }
+    __syncthreads();
+  }
+  if (a.detect_oob && err != ~0ull) atomicMin(res + RES_ERR_INDEX, err);
+}
+
+// pass 2: new offsets + bytes
+__global__ void __launch_bounds__(DG_THREADS) k_dict_copy(const DictArgs a, const int64_t *__restrict__ block_incl, int64_t blocks,
+                                                          int32_t *__restrict__ out_offs, uint8_t *__restrict__ out_data, int64_t limit,
+                                                          unsigned long long *res, const int64_t *__restrict__ total_ptr, int64_t out_cap) {
+  extern __shared__ __align__(16) uint8_t s_dyn[];
+  __shared__ __align__(16) uint32_t s_win[DG_WARPS][DG_WINW];
+  __shared__ uint32_t s_wtot[DG_WARPS];
+  if (*a.too_long) return;
+  if (out_data != nullptr && total_ptr != nullptr) {  // decided on the device: no host round trip between the passes
+    const int64_t total = __ldg(total_ptr);
+    if (total > out_cap || total > limit) out_data = nullptr;
+  }
+  uint4 *s_tab = reinterpret_cast<uint4 *>(s_dyn);
+  uint8_t *s_len = s_dyn + (size_t)a.n_src * 16;
+  for (uint32_t i = threadIdx.x; i < a.n_src; i += DG_THREADS) { s_tab[i] = a.table[i]; s_len[i] = a.lens[i]; }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t *win = s_win[wid];
+  for (int i = lane; i < DG_WIN / 16; i += 32) reinterpret_cast<uint4 *>(win)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  const uint32_t A = (uint32_t)((uintptr_t)out_data & 15);  // ring positions mirror the output's 16-byte alignment
+  uint8_t *gbase = out_data - A;
+  unsigned long long err = ~0ull;
+  for (int64_t blk = blockIdx.x; blk < blocks; blk += gridDim.x) {
+    const int64_t cta_begin = blk ? block_incl[blk - 1] : 0;
+    const int64_t row0 = blk * BY_ROWS + (int64_t)wid * DG_WROWS;
+    uint32_t key[DG_ITERS], len[DG_ITERS], pre[DG_ITERS], tot[DG_ITERS];
+#pragma unroll
+    for (int i = 0; i < DG_ITERS; ++i) {
+      const int64_t j = row0 + i * 32 + lane;
+      const bool live = j < a.m;
+      key[i] = live ? __ldg(a.keys + j) : 0u;
+      uint32_t vw = ~0u;
+      if (a.out_valid && row0 + i * 32 < a.m) vw = __ldg(a.out_valid + ((row0 + i * 32) >> 5));
+      const bool use = live && ((vw >> lane) & 1u) && key[i] < a.n_src;  // out-of-bounds keys were reported by pass 1
+      if (!use) key[i] = 0xffffffffu;
+      len[i] = use ? s_len[key[i]] : 0u;
+    }
+    uint32_t run = 0;
+#pragma unroll
+    for (int i = 0; i < DG_ITERS; ++i) {
+      uint32_t incl = len[i];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(ACU_FULL_MASK, incl, o);
+        if (lane >= o) incl += y;
+      }
+      tot[i] = __shfl_sync(ACU_FULL_MASK, incl, 31);
+      pre[i] = run + incl - len[i];
+      run += tot[i];
+    }
+    if (lane == 0) s_wtot[wid] = run;
+    __syncthreads();
+    int64_t wbase = cta_begin;
+    for (int w = 0; w < wid; ++w) wbase += s_wtot[w];
+    // ---- new offsets (+ first i32 overflow); the lane holding the last row also writes offsets[m] ----
+#pragma unroll
+    for (int i = DG_ITERS - 1; i >= 0; --i) {
+      const int64_t j = row0 + i * 32 + lane;
+      const int64_t start = wbase + pre[i];
+      if (j < a.m) {
+        if (start + len[i] > limit) err = (unsigned long long)j;
+        out_offs[j] = (int32_t)start;
+        if (j + 1 == a.m) out_offs[a.m] = (int32_t)(start + len[i]);
+      }
+    }
+    // ---- bytes through the ring ----
+    if (out_data != nullptr) {
+      const int64_t own_start = wbase + A;           // first ring position this warp owns in this round of 128 rows
+      int64_t flush_pos = own_start & ~(int64_t)15;  // chunks below are done
+#pragma unroll
+      for (int i = 0; i < DG_ITERS; ++i) {
+        if (tot[i] == 0) continue;  // warp-uniform
+        if (len[i]) {
+          const uint4 e = s_tab[key[i]];  // zero beyond the entry's length
+          const int64_t d = wbase + A + pre[i];
+          const uint32_t dsh = (uint32_t)(d & 3) * 8u;
+          const uint32_t wi = (uint32_t)(d >> 2);
+          const uint32_t x0 = e.x << dsh;
+          const uint32_t x1 = __funnelshift_l(e.x, e.y, dsh);
+          const uint32_t x2 = __funnelshift_l(e.y, e.z, dsh);
+          const uint32_t x3 = __funnelshift_l(e.z, e.w, dsh);
+          const uint32_t x4 = __funnelshift_l(e.w, 0u, dsh);
+          if (x0) atomicOr(win + ((wi + 0) & (DG_WINW - 1)), x0);
+          if (x1) atomicOr(win + ((wi + 1) & (DG_WINW - 1)), x1);
+          if (x2) atomicOr(win + ((wi + 2) & (DG_WINW - 1)), x2);
+          if (x3) atomicOr(win + ((wi + 3) & (DG_WINW - 1)), x3);
+          if (x4) atomicOr(win + ((wi + 4) & (DG_WINW - 1)), x4);
+        }
+        __syncwarp();
+        // completed 16-byte chunks of this round: [flush_pos, done)
+        const int64_t round_end = wbase + A + (int64_t)__shfl_sync(ACU_FULL_MASK, pre[i], 0) + tot[i];  // lane 0's prefix = the round's first byte
+        const int64_t done = round_end & ~(int64_t)15;
+        for (int64_t c = flush_pos + (int64_t)lane * 16; c < done; c += 32 * 16) {
+          const uint32_t ci = (uint32_t)(c >> 2) & (DG_WINW - 1);
+          const uint4 q = *reinterpret_cast<const uint4 *>(win + ci);
+          if (c >= own_start) {
+            *reinterpret_cast<uint4 *>(gbase + c) = q;
+          } else {  // the chunk that holds the warp's first byte: only the owned bytes
+            const uint8_t *qb = reinterpret_cast<const uint8_t *>(&q);
+            for (int b = 0; b < 16; ++b)
+              if (c + b >= own_start) gbase[c + b] = qb[b];
+          }
+          *reinterpret_cast<uint4 *>(win + ci) = make_uint4(0, 0, 0, 0);
+        }
+        if (done > flush_pos) flush_pos = done;
+        __syncwarp();
+      }
+      // the warp's last partial chunk (shared with the next warp's first bytes): byte-wise, then re-zeroed
+      const int64_t wend = wbase + A + run;
+      if (flush_pos < wend) {
+        const uint32_t ci = (uint32_t)(flush_pos >> 2) & (DG_WINW - 1);
+        if (lane == 0) {
+          const uint8_t *qb = reinterpret_cast<const uint8_t *>(win + ci);
+          for (int b = 0; b < 16; ++b)
+            if (flush_pos + b >= own_start && flush_pos + b < wend) gbase[flush_pos + b] = qb[b];
+        }
+        __syncwarp();
+        if (lane == 0) *reinterpret_cast<uint4 *>(win + ci) = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+      }
+    }
+    __syncthreads();  // s_wtot is rewritten by the next round
+  }
+  if (err != ~0ull) atomicMin(res + RES_ERR2, err);
+}
+
 // lengths -> CTA totals -> scan -> offsets (+ byte copy when out_data != NULL and it fits), queued
 // on the ctx stream without synchronising; gather_finalize reads the fetched result block:
 // RES_ERR_INDEX = lowest out-of-bounds row (detect_oob), RES_AUX0 = total value bytes,
@@ -514,10 +728,12 @@ struct GatherState {
   bool detect_oob = false;
 };
 
-size_t gather_scratch_bytes(int64_t m) {
+size_t gather_block_bytes(int64_t m) {
   const int64_t blocks = (m + BY_ROWS - 1) / BY_ROWS;
   return (((size_t)(2 * blocks + blocks / SCAN_ELEMS + 4096) * 8) + 255) & ~(size_t)255;
 }
+// block totals / scan scratch + the dictionary table of the small-source path (16-byte entries, length bytes, flag)
+size_t gather_scratch_bytes(int64_t m) { return gather_block_bytes(m) + (size_t)DG_MAX_ENTRIES * 17 + 256; }
 
 acu_status gather_launch(acu_ctx *ctx, int32_t ob, const void *offsets, const uint8_t *data, const void *idx, int kind,
                          int64_t m, int64_t n_src, const uint8_t *out_valid, bool detect_oob, void *out_offsets,
@@ -534,6 +750,34 @@ acu_status gather_launch(acu_ctx *ctx, int32_t ob, const void *offsets, const ui
   gs->out_cap = out_cap;
   gs->limit = ob == 4 ? (int64_t)INT32_MAX : INT64_MAX;
   gs->detect_oob = detect_oob;
+  // small source (a dictionary): table in shared memory, see k_dict_copy
+  static const bool no_dict = getenv("ACU_BYTES_NO_DICT") != nullptr;  // A/B measurements
+  if (fast && !no_dict && n_src <= DG_MAX_ENTRIES && n_src > 0 && m >= 65536 && ((uintptr_t)out_offsets % 4 == 0)) {
+    uint8_t *extra = static_cast<uint8_t *>(scratch) + gather_block_bytes(m);
+    uint4 *table = reinterpret_cast<uint4 *>(extra);
+    uint8_t *lens = extra + (size_t)DG_MAX_ENTRIES * 16;
+    int *flag = reinterpret_cast<int *>(extra + (size_t)DG_MAX_ENTRIES * 17);
+    ACU_CUDA(ctx, cudaMemsetAsync(flag, 0, 4, ctx->stream));
+    ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_dict_table, (unsigned)((n_src + 255) / 256), 256, 0, static_cast<const int32_t *>(offsets), data, n_src, table, lens, flag);
+    int too_long = 0;
+    ACU_CUDA(ctx, cudaMemcpyAsync(&too_long, flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // entries longer than 16 bytes: the generic kernels below
+    if (!too_long) {
+      DictArgs da{static_cast<const uint32_t *>(idx), m, (uint32_t)n_src, reinterpret_cast<const uint32_t *>(out_valid), detect_oob ? 1 : 0, table, lens, flag};
+      const size_t smem1 = (size_t)n_src, smem2 = (size_t)n_src * 17;
+      ACU_CUDA(ctx, cudaFuncSetAttribute(k_dict_copy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      int per_sm = 1;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dict_copy, DG_THREADS, smem2) != cudaSuccess || per_sm < 1) per_sm = 1;
+      const int g1 = acu_grid(ctx, blocks, 4), g2 = acu_grid(ctx, blocks, per_sm);
+      ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_dict_block_totals, g1, DG_THREADS, smem1, da, blocks, block_tot, res);
+      ACU_TRY(scan_inclusive(ctx, block_tot, blocks, block_tot + blocks));
+      ACU_CUDA(ctx, cudaMemcpyAsync(res + RES_AUX0, block_tot + (blocks - 1), 8, cudaMemcpyDeviceToDevice, ctx->stream));
+      da.detect_oob = 0;
+      ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_dict_copy, g2, DG_THREADS, smem2, da, block_tot, blocks, static_cast<int32_t *>(out_offsets), out_data, gs->limit, res,
+                       block_tot + (blocks - 1), out_cap);
+      return ACU_OK;
+    }
+  }
   if (fast) ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_block_totals<true>, (unsigned)blocks, BY_THREADS, 0, a, block_tot, res);
   else ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_block_totals<false>, (unsigned)blocks, BY_THREADS, 0, a, block_tot, res);
   ACU_TRY(scan_inclusive(ctx, block_tot, blocks, block_tot + blocks));

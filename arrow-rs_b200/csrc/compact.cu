@@ -696,7 +696,13 @@ acu_status launch_filter(acu_ctx *ctx, const FilterBatch &fb, int n_cols, bool f
     constexpr size_t smem = 8 * (size_t)AsyncCfg<W>::PASS_BYTES;
     if (ctx->occupancy.find(reinterpret_cast<const void *>(k_filter_fused<W>)) == ctx->occupancy.end())
       ACU_CUDA(ctx, cudaFuncSetAttribute(k_filter_fused<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int gx = acu_wave_grid(ctx, k_filter_fused<W>, 256, smem, (fa.n_tiles + 7) / 8);
+    // every warp should own several tiles (the next tile's mask / offsets are prefetched while the current one is in
+    // flight): with the columns of a record batch in blockIdx.y the x-grid is divided by the column count
+    static const int tiles_per_warp = getenv("ACU_FILTER_TILES_PER_WARP") ? atoi(getenv("ACU_FILTER_TILES_PER_WARP")) : 4;
+    const int64_t want = (fa.n_tiles + 8 * (int64_t)tiles_per_warp - 1) / (8 * (int64_t)tiles_per_warp);
+    int gx = acu_wave_grid(ctx, k_filter_fused<W>, 256, smem, (fa.n_tiles + 7) / 8);
+    gx = (gx + n_cols - 1) / n_cols;
+    if (gx > want) gx = (int)(want < 1 ? 1 : want);
     ACU_LAUNCH_TIMED(ctx, ACU_K_FILTER, (k_filter_fused<W>), dim3(gx, n_cols), 256, smem, fb);
   } else {
     const int gx = acu_wave_grid(ctx, k_filter_values<W>, 256, 0, (fa.n_tiles + 7) / 8);

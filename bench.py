@@ -476,8 +476,10 @@ class HostPipelined:
 
 
 def numa_bind(gpu_index):
-    """Opt-in (ACU_BENCH_NUMA=1): run this rank's host threads, and therefore first-touch its pinned buffers, on the CPUs
-    NVML reports as local to the GPU. Returns the previous affinity (to restore) or None when nothing was changed."""
+    """Default for the e2e arm (ACU_BENCH_NUMA=0 disables): run this rank's host threads, and therefore allocate / first-touch
+    its pinned buffers, on the CPUs NVML reports as local to the GPU (round 1: 8 unbound ranks reached 0.41 of 8 x the
+    one-GPU e2e rate — half the GPUs streamed from the remote socket's memory). Returns the previous affinity (to restore) or
+    None when nothing was changed."""
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -562,7 +564,7 @@ def run_gpu(args):
             avail = 64 << 30
         need = n * 34 + (64 << 20)
         if need * world < avail * 0.6:
-            all_cpus = numa_bind(local_rank) if os.environ.get("ACU_BENCH_NUMA") == "1" else None  # opt-in experiment
+            all_cpus = numa_bind(local_rank) if os.environ.get("ACU_BENCH_NUMA", "1") != "0" else None
             hs = HostStaged(wl) if args.e2e_mode == "serial" else HostPipelined(wl, local_rank, args.e2e_batch_rows, args.e2e_workers)
             e2e_check = hs.step()
             barrier()
@@ -578,6 +580,7 @@ def run_gpu(args):
                    "d2h_bytes_per_step": hs.d2h_bytes, "ms_per_step": e2e_ms, "steps": args.e2e_steps, "rows_per_gpu": n,
                    "mode": args.e2e_mode, "batch_rows": args.e2e_batch_rows, "streams": args.e2e_workers,
                    "timer": "host perf_counter around steps that end with a stream sync (spans several streams)",
+                   "numa_bound_cpus": len(os.sched_getaffinity(0)) if all_cpus else None,
                    "check": {"sum_bits": int(e2e_check[0]), "valid_rows": int(e2e_check[1])}}
             hs.free()
             if all_cpus:
