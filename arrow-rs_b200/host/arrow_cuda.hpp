@@ -591,6 +591,21 @@ class FilterBuilder {  // filter.rs:254-324
   }
   FilterBuilder &optimize() { return *this; }  // the device plan is always materialised
   FilterPredicate build() { return pred_; }
+  // FilterBuilder::new(&cmp::OP(l, r)?).build() with the comparison fused into the plan pass: the BooleanArray is never
+  // materialised (acu_filter_plan_create_cmp). l / r: PrimitiveArray<T> or Scalar<PrimitiveArray<T>> of one type.
+  template <class L, class R>
+  static Result<FilterPredicate> from_cmp(acu_cmp_op op, const L &lhs, const R &rhs) {
+    const auto &l = datum_array(lhs);
+    const auto &r = datum_array(rhs);
+    if (l.data_type() != r.data_type() || dtype_width(l.data_type()) == 0)
+      return ArrowError{ACU_ERR_INVALID_ARGUMENT, "Invalid argument error: Invalid comparison operation"};
+    acu_array a = l.view(datum_is_scalar(lhs)), b = r.view(datum_is_scalar(rhs));
+    acu_filter_plan *plan = nullptr;
+    Context &c = Context::get();
+    acu_status st = acu_filter_plan_create_cmp(c.raw(), (acu_dtype)dtype_code(l.data_type()), op, &a, &b, &plan);
+    if (st != ACU_OK) return c.last_error(st);
+    return FilterPredicate(plan);
+  }
  private:
   FilterPredicate pred_;
 };

@@ -520,6 +520,11 @@ static void test_row_filter() {
   CHECK_EQ(1, out.num_rows());  // rows with b > 0: (2,4) (null,7) (6,9); of those a < 6: (2,4) — a null `a` is dropped
   CHECK((as_primitive<int64_t>(out.column(0)).to_vec() == std::vector<O<int64_t>>{2}));
   CHECK((as_primitive<int64_t>(out.column(1)).to_vec() == std::vector<O<int64_t>>{4}));
+  // the same first predicate with the comparison fused into the filter plan (no BooleanArray in HBM)
+  auto fused = FilterBuilder::from_cmp(ACU_GT, as_primitive<int64_t>(batch.column(1)), new_scalar<int64_t>(0)).unwrap();
+  auto fb = fused.filter_record_batch(batch).unwrap();
+  CHECK_EQ(3, fb.num_rows());
+  CHECK((as_primitive<int64_t>(fb.column(1)).to_vec() == std::vector<O<int64_t>>{4, 7, 9}));
   auto bad = std::make_shared<parquet::ArrowPredicateFn>(std::vector<size_t>{0}, [](const RecordBatch &) {
     return Result<BooleanArray>(BooleanArray::from(std::vector<bool>{true}));
   });
