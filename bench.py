@@ -481,21 +481,45 @@ def numa_bind(gpu_index):
     one-GPU e2e rate — half the GPUs streamed from the remote socket's memory). Returns the previous affinity (to restore) or
     None when nothing was changed."""
     try:
-        import pynvml
-        pynvml.nvmlInit()
-        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-        idx = int(vis.split(",")[gpu_index]) if vis else gpu_index
-        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
-        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
-        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
         before = os.sched_getaffinity(0)
+        cpus = set()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[gpu_index]) if vis else gpu_index
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        except Exception as e:  # fall back to sysfs: the NUMA node of the GPU's PCI device
+            NUMA_NOTE[0] = f"nvml affinity unavailable ({type(e).__name__})"
+        if not cpus:
+            try:
+                import pynvml
+                bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(gpu_index)).busId
+                bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+                bus = bus[4:] if len(bus) > 12 else bus  # 00000000:17:00.0 -> 0000:17:00.0
+                node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+                if node >= 0:
+                    spec = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+                    for part in spec.split(","):
+                        lo, _, hi = part.partition("-")
+                        cpus |= set(range(int(lo), int(hi or lo) + 1))
+            except Exception as e:
+                NUMA_NOTE[0] = (NUMA_NOTE[0] or "") + f"; sysfs numa_node unavailable ({type(e).__name__})"
         cpus &= before
         if not cpus or cpus == before:
+            NUMA_NOTE[0] = (NUMA_NOTE[0] or "") + f" no narrower GPU-local CPU set ({len(cpus)} of {len(before)})"
             return None
         os.sched_setaffinity(0, cpus)
+        NUMA_NOTE[0] = f"bound to {len(cpus)} GPU-local CPUs"
         return before
-    except Exception:
+    except Exception as e:
+        NUMA_NOTE[0] = f"failed ({type(e).__name__}: {e})"
         return None
+
+
+NUMA_NOTE = [None]
 
 
 def algorithmic_bytes(n, m):
@@ -580,7 +604,7 @@ def run_gpu(args):
                    "d2h_bytes_per_step": hs.d2h_bytes, "ms_per_step": e2e_ms, "steps": args.e2e_steps, "rows_per_gpu": n,
                    "mode": args.e2e_mode, "batch_rows": args.e2e_batch_rows, "streams": args.e2e_workers,
                    "timer": "host perf_counter around steps that end with a stream sync (spans several streams)",
-                   "numa_bound_cpus": len(os.sched_getaffinity(0)) if all_cpus else None,
+                   "numa_bound_cpus": len(os.sched_getaffinity(0)) if all_cpus else None, "numa_note": NUMA_NOTE[0],
                    "check": {"sum_bits": int(e2e_check[0]), "valid_rows": int(e2e_check[1])}}
             hs.free()
             if all_cpus:

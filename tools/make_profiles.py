@@ -27,7 +27,35 @@ for r in raw[2:]:
     name = r[h.index("Kernel Name")].split("(")[0].replace("void ", "").replace("<unnamed>::", "")
     rd, wr = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
     traffic[name] = float(r[rd].replace(",", "")) * scale[units[rd]] + float(r[wr].replace(",", "")) * scale[units[wr]]
-json.dump(traffic, open(f"profiles/{rnd}_traffic.json", "w"), indent=1)
+sha = open(f"gpurun_out/so_sha16_{rnd}.txt").read().strip() if os.path.exists(f"gpurun_out/so_sha16_{rnd}.txt") else None
+# bench.py reads this file: per-launch DRAM bytes (read + write) of the step kernels at 1e9 rows, with the hash of the
+# libarrow_cuda.so the capture was taken on (roofline.traffic_same_build)
+json.dump({"so_sha16": sha, "rows": 1000000000, "source": f"ncu --set full (gpurun_out/prof_{rnd}.ncu-rep), dram__bytes_read.sum + dram__bytes_write.sum per launch",
+           "kernels": traffic}, open(f"profiles/{rnd}_traffic.json", "w"), indent=1)
+# the ncu details page of the same capture (speed-of-light, occupancy, stall sections per kernel), as text
+if os.path.exists(f"gpurun_out/prof_{rnd}_details.txt"):
+    import shutil
+    shutil.copy(f"gpurun_out/prof_{rnd}_details.txt", f"profiles/{rnd}_ncu_details.txt")
+# SASS evidence of the memory-path instructions, from the shipped library itself (no GPU needed)
+sass = subprocess.run("cuobjdump -sass arrow-rs_b200/libarrow_cuda.so", shell=True, capture_output=True, text=True).stdout
+fn, counts = None, {}
+for line in sass.splitlines():
+    if "Function :" in line:
+        fn = line.split("Function :")[1].strip()
+        counts[fn] = {}
+    elif fn:
+        for op in ("UBLKCP", "LDGSTS", "REDG", "ATOMS", "LDG.E.128", "STG.E.128", "REDUX", "SYNCS", "HMMA", "UTCHMMA", "UTCQMMA"):
+            if op in line:
+                counts[fn][op] = counts[fn].get(op, 0) + 1
+with open(f"profiles/{rnd}_sass_excerpts.txt", "w") as f:
+    f.write(f"# cuobjdump -sass arrow-rs_b200/libarrow_cuda.so (sha256[:16] = {sha}): memory-path instruction counts per hot kernel\n")
+    f.write("# UBLKCP = cp.async.bulk (TMA engine), LDGSTS = cp.async (global -> shared), REDG = fire-and-forget global atomics,\n")
+    f.write("# REDUX = redux.sync, no HMMA / UTC*MMA: no tensor-core instruction anywhere (HBM-bound integer / byte work)\n")
+    import subprocess as sp
+    for k, v in counts.items():
+        if any(t in k for t in ("k_take", "k_filter_fused", "k_filter_values_async", "k_arith", "k_cmp_v2", "k_reduce", "k_dict_copy", "k_plan_mask", "k_cast_v2")) and v:
+            dem = sp.run(["c++filt", k], capture_output=True, text=True).stdout.strip()
+            f.write(f"{dem[:150]}: {v}\n")
 # keep the columns the summary reads (the raw page has ~1500 metric columns)
 keep = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "launch__registers_per_thread", "launch__grid_size", "sm__warps_active.avg.pct_of_peak_sustained_active",
