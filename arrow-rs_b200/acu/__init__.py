@@ -315,6 +315,14 @@ class Context:
     def sync(self):
         self.check(self.lib.acu_ctx_sync(self.h))
 
+    def async_begin(self):
+        """Open a stream-ordered section (include/arrow_cuda.h): the supported entry points only enqueue."""
+        self.check(self.lib.acu_async_begin(self.h))
+
+    def results_fetch(self):
+        """ONE D2H + ONE synchronisation; finalises the queued calls in order, raises the first error."""
+        self.check(self.lib.acu_results_fetch(self.h))
+
     def launch_count(self):
         return self.lib.acu_launch_count(self.h)
 
@@ -398,6 +406,84 @@ class Context:
             if plan:
                 self.lib.acu_filter_plan_destroy(self.h, plan)
             dp.free()
+
+    def chain(self, col, pred, idx, a, b, arith_op=ADD, agg_op=SUM, cmp_with=None):
+        """filter(col, pred) -> take(col, idx) -> arith(a, b) -> aggregate(taken) queued in ONE stream-ordered section
+        (acu_async_begin ... acu_results_fetch): one synchronisation for the five calls. With cmp_with = (op, x, y) the
+        predicate is cmp(op, x, y) computed inside the section too (`pred` is ignored). Returns
+        (filtered, taken, arith result, aggregate or None); raises the first error in call order at the fetch."""
+        ups = [self.upload(x) for x in (col, idx, a, b)]
+        dcol, didx, da, db = ups
+        plan = C.c_void_p()
+        outs = []
+        n_pred = (cmp_with[2].length if cmp_with[1].is_scalar else cmp_with[1].length) if cmp_with else pred.length
+        try:
+            if cmp_with:
+                cx, cy = self.upload(cmp_with[1]), self.upload(cmp_with[2])
+                ups += [cx, cy]
+                o_pred = self.alloc_out(bitmap_bytes(n_pred), n_pred)
+                outs.append(o_pred)
+            else:
+                dpred = self.upload(pred)
+                ups.append(dpred)
+            # outputs of a filter whose plan is pending are sized for the predicate length
+            o_f = self.alloc_out(max(n_pred, 1) * col.width(), n_pred)
+            o_t = self.alloc_out(idx.length * col.width(), idx.length)
+            n_ar = b.length if a.is_scalar and not b.is_scalar else a.length
+            o_a = self.alloc_out(n_ar * a.width(), n_ar)
+            outs += [o_f, o_t, o_a]
+            bits, cnt = C.c_uint64(0), C.c_int64(0)
+            cd, idd, ad, bd = dcol.descriptor(), didx.descriptor(), da.descriptor(), db.descriptor()
+            self.async_begin()
+            try:
+                if cmp_with:
+                    xd, yd = cx.descriptor(), cy.descriptor()
+                    self.check(self.lib.acu_cmp(self.h, cmp_with[1].dtype, cmp_with[0], C.byref(xd), C.byref(yd), C.byref(o_pred)))
+                    # the comparison's null count is still on the device: hand the plan a predicate without cached count is not
+                    # allowed inside a section, so the fused entry point is the stream-ordered way to build a plan from a cmp
+                    self.check(self.lib.acu_filter_plan_create_cmp(self.h, cmp_with[1].dtype, cmp_with[0], C.byref(xd), C.byref(yd), C.byref(plan)))
+                else:
+                    pd = dpred.descriptor()
+                    self.check(self.lib.acu_filter_plan_create(self.h, C.byref(pd), C.byref(plan)))
+                if col.dtype == BOOL:
+                    self.check(self.lib.acu_filter_boolean(self.h, plan, C.byref(cd), C.byref(o_f)))
+                    self.check(self.lib.acu_take_boolean(self.h, C.byref(cd), C.byref(idd), idx.dtype, 0, C.byref(o_t)))
+                else:
+                    self.check(self.lib.acu_filter_primitive(self.h, plan, col.width(), C.byref(cd), C.byref(o_f)))
+                    self.check(self.lib.acu_take_primitive(self.h, col.width(), C.byref(cd), C.byref(idd), idx.dtype, 0, C.byref(o_t)))
+                self.check(self.lib.acu_arith(self.h, a.dtype, arith_op, C.byref(ad), C.byref(bd), C.byref(o_a)))
+                has_v = (col.validity is not None and col.null_count != 0) or idx.validity is not None
+                taken = abi.Array()
+                taken.values, taken.values_offset = o_t.values, 0
+                taken.validity, taken.validity_offset = (o_t.validity if has_v else None), 0
+                taken.len, taken.null_count, taken.is_scalar = idx.length, (-1 if has_v else 0), 0
+                do_agg = col.dtype != BOOL
+                if do_agg:
+                    self.check(self.lib.acu_aggregate(self.h, col.dtype, agg_op, C.byref(taken), C.byref(bits), C.byref(cnt)))
+            except BaseException:
+                try:
+                    self.results_fetch()
+                except ArrowError:
+                    pass
+                raise
+            self.results_fetch()
+            pred_out = self.download_out(outs.pop(0), BOOL) if cmp_with else None
+            filtered = self.download_out(o_f, col.dtype)
+            taken_h = self.download_out(o_t, col.dtype)
+            added = self.download_out(o_a, a.dtype)
+            outs = []
+            agg = None
+            if do_agg and cnt.value != 0:
+                agg = np.array([bits.value], dtype=np.uint64).view(NP_DTYPES[col.dtype])[0].item()
+            res = (filtered, taken_h, added, agg)
+            return res + (pred_out,) if cmp_with else res
+        finally:
+            for o in outs:
+                self._free_out(o)
+            if plan:
+                self.lib.acu_filter_plan_destroy(self.h, plan)
+            for u in ups:
+                u.free()
 
     # -- take (arrow-select/src/take.rs) ----------------------------------------------------
     def take(self, values, indices, check_bounds=False):

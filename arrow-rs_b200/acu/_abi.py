@@ -225,6 +225,9 @@ PROTOTYPES = {
     "acu_comm_get_unique_id": (i32, [vp]),
     "acu_comm_init": (i32, [vp, vp, i32, i32]),
     "acu_comm_destroy": (i32, [vp]),
+    "acu_async_begin": (i32, [vp]),
+    "acu_results_fetch": (i32, [vp]),
+    "acu_async_active": (i32, [vp]),
     "acu_comm_allreduce_aggregates": (i32, [vp, i32, i32, P(u64), P(i64), i32]),
     "acu_comm_allreduce_i64_sum": (i32, [vp, P(i64), i32]),
     "acu_aggregate_allreduce": (i32, [vp, i32, i32, P(Array), P(u64), P(i64)]),

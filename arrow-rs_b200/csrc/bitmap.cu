@@ -40,6 +40,11 @@ int64_t acu_resolve_null_count(acu_ctx *ctx, const acu_array *a, acu_status *st)
   if (a->null_count >= 0) return a->null_count;
   int64_t len = a->is_scalar ? 1 : a->len;
   if (len == 0) return 0;
+  if (ctx->async_on) {
+    *st = acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0,
+                   "null_count = -1 needs a device count (a synchronisation): pass the cached null_count inside an async section");
+    return 0;
+  }
   if ((*st = acu_res_reset(ctx)) != ACU_OK) return 0;
   if ((*st = acu_bitmap_and_launch(ctx, a->validity, a->validity_offset, nullptr, 0, len, nullptr, true)) != ACU_OK) return 0;
   if ((*st = acu_res_fetch(ctx)) != ACU_OK) return 0;

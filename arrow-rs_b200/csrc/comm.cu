@@ -105,6 +105,7 @@ __host__ __device__ inline uint64_t encode_partial(uint64_t bits, bool empty, ac
 
 __global__ void k_stage_partial(const unsigned long long *res, int launched, long long valid_count, int dtype, int op, uint64_t *buf) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (valid_count < 0) valid_count = launched ? (long long)res[RES_COUNT] : 0;  // counted by k_reduce (unknown on the host)
   const uint64_t bits = launched ? res[RES_AUX0] : 0ull;
   buf[0] = encode_partial(bits, valid_count == 0, (acu_dtype)dtype, (acu_agg_op)op);
   buf[1] = (uint64_t)valid_count;
@@ -228,7 +229,9 @@ acu_status acu_comm_allreduce_aggregates(acu_ctx *ctx, acu_dtype dtype, acu_agg_
   return ACU_OK;
 }
 
-// sum / min / max of this rank's shard combined over all ranks with ONE synchronisation (see include/arrow_cuda.h).
+// sum / min / max of this rank's shard combined over all ranks with ONE synchronisation (see include/arrow_cuda.h). The
+// all-reduce runs in place on slots 8..9 of the call's own result block, so the combined value travels to the host with
+// the block (the call's fetch, or acu_results_fetch at the end of an async section): no host bounce.
 acu_status acu_aggregate_allreduce(acu_ctx *ctx, acu_dtype dtype, acu_agg_op op, const acu_array *a, uint64_t *out_bits,
                                    int64_t *out_valid_count) {
   if (ctx->world <= 1 || !ctx->nccl_comm) return acu_aggregate(ctx, dtype, op, a, out_bits, out_valid_count);
@@ -236,18 +239,20 @@ acu_status acu_aggregate_allreduce(acu_ctx *ctx, acu_dtype dtype, acu_agg_op op,
   NcclApi *api = nccl_api();
   *out_bits = 0;
   *out_valid_count = 0;
-  acu_status st;
-  const int64_t nc = a->len ? acu_resolve_null_count(ctx, a, &st) : 0;
-  if (a->len) ACU_TRY(st);
-  const int64_t valid = a->len - nc;
+  acu_status st = ACU_OK;
+  const bool deferred_nc = ctx->async_on && a->len && a->validity && a->null_count < 0;
+  const int64_t nc = deferred_nc ? 1 : (a->len ? acu_resolve_null_count(ctx, a, &st) : 0);
+  ACU_TRY(st);
+  const int64_t valid = deferred_nc ? -1 : a->len - nc;
   void *scratch;
   ACU_TRY(acu_scratch(ctx, acu_reduce_col_scratch(ctx), &scratch));
   int launched = 0;
-  ACU_TRY(acu_res_reset(ctx));
-  ACU_TRY(acu_reduce_col_launch(ctx, dtype, op, a, nc, scratch, acu_dres(ctx, 0), &launched));
-  uint64_t *stage = reinterpret_cast<uint64_t *>(ctx->h_res + (size_t)(RES_BLOCKS / 2) * RES_SLOTS);
-  uint64_t *buf = reinterpret_cast<uint64_t *>(ctx->d_res + (size_t)(RES_BLOCKS / 2) * RES_SLOTS);
-  ACU_LAUNCH(ctx, k_stage_partial, 1, 32, 0, acu_dres(ctx, 0), launched, (long long)valid, (int)dtype, (int)op, buf);
+  const int blk = acu_call_begin(ctx, &st);
+  ACU_TRY(st);
+  ACU_TRY(acu_reduce_col_launch(ctx, dtype, op, a, nc, scratch, acu_dres(ctx, blk), &launched));
+  constexpr int SLOT = 8;  // slots 8..9 of the block: {combined value, combined valid count}
+  uint64_t *buf = reinterpret_cast<uint64_t *>(acu_dres(ctx, blk) + SLOT);
+  ACU_LAUNCH(ctx, k_stage_partial, 1, 32, 0, acu_dres(ctx, blk), launched, (long long)valid, (int)dtype, (int)op, buf);
   const bool is_unsigned = dtype == ACU_U8 || dtype == ACU_U16 || dtype == ACU_U32 || dtype == ACU_U64;
   if (op == ACU_SUM && dtype != ACU_F32 && dtype != ACU_F64) {
     ACU_NCCL(ctx, api->AllReduce(buf, buf, 2, NCCL_INT64, NCCL_SUM, ctx->nccl_comm, ctx->stream));  // value and count: one int64 sum
@@ -259,21 +264,19 @@ acu_status acu_aggregate_allreduce(acu_ctx *ctx, acu_dtype dtype, acu_agg_op op,
     ACU_NCCL(ctx, api->AllReduce(buf + 1, buf + 1, 1, NCCL_INT64, NCCL_SUM, ctx->nccl_comm, ctx->stream));
     ACU_NCCL(ctx, api->GroupEnd());
   }
-  ACU_CUDA(ctx, cudaMemcpyAsync(stage, buf, 16, cudaMemcpyDeviceToHost, ctx->stream));
-  ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the only synchronisation of the call
-  acu_kstats_drain(ctx);
-  ctx->res_clean = false;  // block 0 and the staging slots were written without a fetch
-  ctx->res_dirty_blocks = RES_BLOCKS;
-  *out_valid_count = (int64_t)stage[1];
-  if (op == ACU_SUM) {
-    const int sz = acu_dtype_size(dtype);
-    *out_bits = sz == 8 ? stage[0] : (stage[0] & ((1ull << (8 * sz)) - 1ull));
-  } else if (is_unsigned) {
-    *out_bits = stage[0];
-  } else {
-    *out_bits = unkey64((int64_t)stage[0], dtype);
-  }
-  return ACU_OK;
+  return acu_call_end(ctx, blk, [dtype, op, is_unsigned, out_bits, out_valid_count](const unsigned long long *h) -> acu_status {
+    const uint64_t v = h[SLOT];
+    *out_valid_count = (int64_t)h[SLOT + 1];
+    if (op == ACU_SUM) {
+      const int sz = acu_dtype_size(dtype);
+      *out_bits = sz == 8 ? v : (v & ((1ull << (8 * sz)) - 1ull));
+    } else if (is_unsigned) {
+      *out_bits = v;
+    } else {
+      *out_bits = unkey64((int64_t)v, dtype);
+    }
+    return ACU_OK;
+  });
 }
 
 }  // extern "C"

@@ -8,7 +8,9 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <functional>
 #include <unordered_map>
+#include <vector>
 
 #include "../../include/arrow_cuda.h"
 
@@ -43,6 +45,11 @@ struct acu_ctx {
   unsigned long long *h_res = nullptr;  // pinned mirror
   bool res_clean = false;               // the result blocks hold their initial values (see acu_res_reset_n)
   int res_dirty_blocks = RES_BLOCKS;
+  // stream-ordered section (acu_async_begin ... acu_results_fetch): calls enqueue only, one result block each
+  bool async_on = false;
+  int async_blocks = 0;
+  std::vector<std::function<acu_status(const unsigned long long *)>> async_fin;  // finalisers, in call order
+  std::vector<int> async_blk;
   void *d_scratch = nullptr;            // grows on demand (block partials, scans)
   size_t scratch_bytes = 0;
   // NCCL (loaded with dlopen, see comm.cu)
@@ -72,6 +79,11 @@ acu_status acu_res_reset(acu_ctx *ctx);                          // zero slots, 
 acu_status acu_res_fetch(acu_ctx *ctx);                          // D2H + stream sync
 acu_status acu_res_reset_n(acu_ctx *ctx, int blocks);            // the same for the first `blocks` result blocks
 acu_status acu_res_fetch_n(acu_ctx *ctx, int blocks);
+// One call = acu_call_begin (its result block: block 0 after a reset, or the next free block of an async section)
+// ... kernels ... acu_call_end(fin): synchronous mode fetches and runs `fin` on the pinned block now; inside an async
+// section `fin` is queued for acu_results_fetch. `fin` turns the block into null counts / errors.
+int acu_call_begin(acu_ctx *ctx, acu_status *st);
+acu_status acu_call_end(acu_ctx *ctx, int block, std::function<acu_status(const unsigned long long *)> fin);
 static inline unsigned long long *acu_dres(acu_ctx *ctx, int block) { return ctx->d_res + (size_t)block * RES_SLOTS; }
 static inline const unsigned long long *acu_hres(const acu_ctx *ctx, int block) { return ctx->h_res + (size_t)block * RES_SLOTS; }
 int64_t acu_resolve_null_count(acu_ctx *ctx, const acu_array *a, acu_status *st);

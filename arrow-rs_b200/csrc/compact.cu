@@ -761,6 +761,7 @@ struct CompressArgs {
   uint32_t *out;            // compacted bits (bit offset 0), zeroed by k_zero_outputs
   unsigned long long *res;  // result block for the popcount, or NULL
   uint64_t out_bytes;       // bytes of `out` to zero
+  const uint64_t *count_ptr;  // pending plan (async section): the selected-row count is still on the device
 };
 struct CompressBatch { CompressArgs col[BATCH_COLS]; };
 
@@ -768,7 +769,13 @@ struct CompressBatch { CompressArgs col[BATCH_COLS]; };
 __global__ void __launch_bounds__(256) k_zero_outputs(const CompressBatch batch) {
   const CompressArgs &c = batch.col[blockIdx.y];
   uint64_t *o = reinterpret_cast<uint64_t *>(c.out);  // bitmaps are whole u64 words (acu_bitmap_bytes)
-  const uint64_t words = c.out_bytes >> 3;
+  const uint64_t words = c.count_ptr ? ((*c.count_ptr + 63) >> 6) : (c.out_bytes >> 3);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (uint64_t)gridDim.x * blockDim.x) o[i] = 0ull;
+}
+// the same for one bitmap whose length (rows) is read from the device: zeroing the validity output of a fused filter
+// whose plan is pending, without touching more than the caller sized for the rows actually selected
+__global__ void __launch_bounds__(256) k_zero_bitmap_dev(uint64_t *__restrict__ o, const uint64_t *__restrict__ count_ptr) {
+  const uint64_t words = (*count_ptr + 63) >> 6;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (uint64_t)gridDim.x * blockDim.x) o[i] = 0ull;
 }
 
@@ -910,7 +917,7 @@ acu_status launch_filter_width(acu_ctx *ctx, int32_t elem_bytes, const FilterBat
 // out (zeroed here) = bits of each `src` selected by the plan; optional popcounts into the columns' result blocks.
 acu_status launch_compress(acu_ctx *ctx, const acu_filter_plan *plan, const CompressBatch &cb, int n_cols) {
   const int64_t n_words_padded = ((plan->n_tiles * TILE_WORDS + 31) / 32) * 32;
-  const int64_t words = (int64_t)acu_bitmap_bytes(plan->count) / 8;
+  const int64_t words = (int64_t)acu_bitmap_bytes(plan->count < 0 ? plan->len : plan->count) / 8;
   ACU_LAUNCH(ctx, k_zero_outputs, dim3(acu_grid(ctx, (words + 255) / 256, 4), n_cols), 256, 0, cb);
   const int gx = acu_wave_grid(ctx, k_compress_bits, 256, 0, (n_words_padded / 32 + 7) / 8);
   ACU_LAUNCH_TIMED(ctx, ACU_K_FILTER, k_compress_bits, dim3(gx, n_cols), 256, 0, cb, plan->len, plan->mask, plan->tile_off, n_words_padded);
@@ -923,7 +930,8 @@ CompressArgs compress_args(const acu_filter_plan *plan, const uint8_t *src, int6
   c.soff = soff;
   c.out = static_cast<uint32_t *>(out);
   c.res = res;
-  c.out_bytes = acu_bitmap_bytes(plan->count);
+  c.out_bytes = acu_bitmap_bytes(plan->count < 0 ? plan->len : plan->count);
+  c.count_ptr = plan->count < 0 ? plan->tile_off + plan->n_tiles : nullptr;  // pending (async section): tile_off[n_tiles] = count
   return c;
 }
 
@@ -933,7 +941,7 @@ CompressArgs compress_args(const acu_filter_plan *plan, const uint8_t *src, int6
 // the round-1 kernels for A/B measurements.
 bool plan_uses_fused(const acu_filter_plan *plan) {
   static const bool legacy = getenv("ACU_FILTER_LEGACY") != nullptr;
-  return !legacy && plan->count * 25 >= plan->len;
+  return !legacy && (plan->count < 0 || plan->count * 25 >= plan->len);  // count < 0: not fetched yet (async section)
 }
 bool fuses_validity(const acu_filter_plan *plan, const acu_array *values) {
   return plan_uses_fused(plan) && ((uintptr_t)values->values % 16) == 0;
@@ -989,27 +997,33 @@ static acu_status plan_alloc(acu_ctx *ctx, int64_t len, acu_filter_plan **out_pl
 }
 
 // mask + tile_count are queued on the stream: scan them into tile offsets, fetch the count, pick the strategy.
-static acu_status plan_finish(acu_ctx *ctx, acu_filter_plan *plan, int kslot) {
+static acu_status plan_finish(acu_ctx *ctx, acu_filter_plan *plan, int kslot, int blk) {
   const int64_t len = plan->len, n_tiles = plan->n_tiles;
   const int64_t n_chunks = (n_tiles + SCAN_CHUNK - 1) / SCAN_CHUNK;
   const int64_t n_words_padded = ((n_tiles * TILE_WORDS + 31) / 32) * 32;
   const int64_t n_off_padded = n_words_padded / TILE_WORDS + 2;
+  unsigned long long *res = acu_dres(ctx, blk);
   k_plan_scan_chunks<<<(unsigned)n_chunks, 1024, 0, ctx->stream>>>(plan->tile_count, n_tiles, plan->tile_off, plan->chunk_total);
-  k_plan_scan_top<<<1, 1024, 0, ctx->stream>>>(plan->chunk_total, n_chunks, ctx->d_res);
+  k_plan_scan_top<<<1, 1024, 0, ctx->stream>>>(plan->chunk_total, n_chunks, res);
   k_plan_finalize<<<acu_grid(ctx, (n_off_padded + 255) / 256, 8), 256, 0, ctx->stream>>>(plan->tile_off, n_tiles, n_off_padded,
-                                                                                     plan->chunk_total, ctx->d_res);
+                                                                                     plan->chunk_total, res);
   if (kslot >= 0) acu_kstats_end(ctx, kslot);
   ctx->launches += 3;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return acu_cuda_fail(ctx, e, "filter plan kernels");
-  ACU_TRY(acu_res_fetch(ctx));
-  plan->count = (int64_t)ctx->h_res[RES_COUNT];
-  // IterationStrategy::default_strategy (filter.rs:346-364)
-  if (plan->count == 0) plan->strategy = ACU_FILTER_NONE;
-  else if (plan->count == len) plan->strategy = ACU_FILTER_ALL;
-  else if ((double)plan->count / (double)len > 0.8) plan->strategy = ACU_FILTER_SLICES;
-  else plan->strategy = ACU_FILTER_INDEX;
-  return ACU_OK;
+  // inside an async section the count stays on the device until acu_results_fetch: the plan is usable at once (the value
+  // kernels read tile_off on the device), count / strategy are filled in by the finaliser
+  plan->count = -1;
+  plan->strategy = ACU_FILTER_INDEX;
+  return acu_call_end(ctx, blk, [plan, len](const unsigned long long *h) -> acu_status {
+    plan->count = (int64_t)h[RES_COUNT];
+    // IterationStrategy::default_strategy (filter.rs:346-364)
+    if (plan->count == 0) plan->strategy = ACU_FILTER_NONE;
+    else if (plan->count == len) plan->strategy = ACU_FILTER_ALL;
+    else if ((double)plan->count / (double)len > 0.8) plan->strategy = ACU_FILTER_SLICES;
+    else plan->strategy = ACU_FILTER_INDEX;
+    return ACU_OK;
+  });
 }
 
 acu_status acu_filter_plan_create(acu_ctx *ctx, const acu_array *pred, acu_filter_plan **out_plan) {
@@ -1028,14 +1042,14 @@ acu_status acu_filter_plan_create(acu_ctx *ctx, const acu_array *pred, acu_filte
   auto bail = [&](acu_status s) { acu_free(ctx, plan->storage); delete plan; return s; };
   const int64_t n_words_padded = ((plan->n_tiles * TILE_WORDS + 31) / 32) * 32;
   const uint8_t *nv = (pred->validity && nc > 0) ? pred->validity : nullptr;  // filter.rs:261-264
-  st = acu_res_reset(ctx);
+  const int blk = acu_call_begin(ctx, &st);
   if (st != ACU_OK) return bail(st);
   const int slot = acu_kstats_begin(ctx, ACU_K_FILTER_PLAN);
   k_plan_mask<<<acu_grid(ctx, (n_words_padded / 32 + 7) / 8, 8), 256, 0, ctx->stream>>>(
       static_cast<const uint8_t *>(pred->values), pred->values_offset, nv, pred->validity_offset, len, n_words_padded,
       plan->mask, plan->tile_count, plan->n_tiles);
   ctx->launches += 1;
-  st = plan_finish(ctx, plan, slot);
+  st = plan_finish(ctx, plan, slot, blk);
   if (st != ACU_OK) return bail(st);
   *out_plan = plan;
   return ACU_OK;
@@ -1053,11 +1067,12 @@ acu_status acu_filter_plan_create_cmp(acu_ctx *ctx, acu_dtype dtype, acu_cmp_op 
   if (len == 0) { *out_plan = plan; return ACU_OK; }
   auto bail = [&](acu_status s) { acu_free(ctx, plan->storage); delete plan; return s; };
   const int64_t n_words_padded = ((plan->n_tiles * TILE_WORDS + 31) / 32) * 32;
-  acu_status st = acu_res_reset(ctx);
+  acu_status st = ACU_OK;
+  const int blk = acu_call_begin(ctx, &st);
   if (st != ACU_OK) return bail(st);
   st = acu_cmp_into_plan(ctx, dtype, op, a, b, plan->mask, n_words_padded, plan->tile_count, plan->n_tiles);
   if (st != ACU_OK) return bail(st);
-  st = plan_finish(ctx, plan, -1);
+  st = plan_finish(ctx, plan, -1, blk);
   if (st != ACU_OK) return bail(st);
   *out_plan = plan;
   return ACU_OK;
@@ -1077,22 +1092,28 @@ acu_status acu_filter_primitive(acu_ctx *ctx, const acu_filter_plan *plan, int32
                                 const acu_array *values, acu_array_out *out) {
   ACU_ENTER(ctx);
   int mode = 0;
-  ACU_TRY(acu_res_reset(ctx));
-  ACU_TRY(acu_filter_col_launch(ctx, plan, 0, elem_bytes, values, out, acu_dres(ctx, 0), &mode));
-  ACU_TRY(acu_res_fetch(ctx));
-  acu_filter_col_finalize(plan, values, mode, acu_hres(ctx, 0), out);
-  return ACU_OK;
+  acu_status st = ACU_OK;
+  const int blk = acu_call_begin(ctx, &st);
+  ACU_TRY(st);
+  ACU_TRY(acu_filter_col_launch(ctx, plan, 0, elem_bytes, values, out, acu_dres(ctx, blk), &mode));
+  return acu_call_end(ctx, blk, [plan, mode, out](const unsigned long long *h) -> acu_status {
+    acu_filter_col_finalize(plan, nullptr, mode, h, out);
+    return ACU_OK;
+  });
 }
 
 acu_status acu_filter_boolean(acu_ctx *ctx, const acu_filter_plan *plan, const acu_array *values,
                               acu_array_out *out) {
   ACU_ENTER(ctx);
   int mode = 0;
-  ACU_TRY(acu_res_reset(ctx));
-  ACU_TRY(acu_filter_col_launch(ctx, plan, 1, 0, values, out, acu_dres(ctx, 0), &mode));
-  ACU_TRY(acu_res_fetch(ctx));
-  acu_filter_col_finalize(plan, values, mode, acu_hres(ctx, 0), out);
-  return ACU_OK;
+  acu_status st = ACU_OK;
+  const int blk = acu_call_begin(ctx, &st);
+  ACU_TRY(st);
+  ACU_TRY(acu_filter_col_launch(ctx, plan, 1, 0, values, out, acu_dres(ctx, blk), &mode));
+  return acu_call_end(ctx, blk, [plan, mode, out](const unsigned long long *h) -> acu_status {
+    acu_filter_col_finalize(plan, nullptr, mode, h, out);
+    return ACU_OK;
+  });
 }
 
 }  // extern "C"
@@ -1108,10 +1129,13 @@ acu_status acu_filter_col_launch(acu_ctx *ctx, const acu_filter_plan *plan, int 
   out->len = plan->count;
   out->has_validity = 0;
   out->null_count = 0;
-  if (plan->strategy == ACU_FILTER_NONE || plan->count == 0) return ACU_OK;
+  const bool pending = plan->count < 0;  // async section: the count is still on the device, outputs are sized for plan->len
+  if (!pending && (plan->strategy == ACU_FILTER_NONE || plan->count == 0)) return ACU_OK;
   // a validity buffer with a cached null_count of 0 is dropped (filter.rs:513-516); an unknown
   // null_count (-1) is compacted and counted: the result is the same, NullBuffer-wise
-  const bool has_nulls = values->validity != nullptr && values->null_count != 0;
+  // (a pending plan may turn out to select everything, where the reference slices and KEEPS the NullBuffer even without
+  // nulls: the validity is then compacted whenever it exists and the finaliser decides, mode 3)
+  const bool has_nulls = values->validity != nullptr && (values->null_count != 0 || pending);
   if (plan->strategy == ACU_FILTER_ALL) {  // values.slice(0, count) (filter.rs:546)
     if (kind == 0)
       ACU_CUDA(ctx, cudaMemcpyAsync(out->values, values->values, (size_t)plan->count * elem_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1131,8 +1155,12 @@ acu_status acu_filter_col_launch(acu_ctx *ctx, const acu_filter_plan *plan, int 
     fb.col[0] = filter_args(plan, values, out, has_nulls, res);
     fused = fb.col[0].vsrc != nullptr;
     if (fused) {  // the kernel ORs boundary words into the bitmap
-      ACU_CUDA(ctx, cudaMemsetAsync(out->validity, 0, acu_bitmap_bytes(plan->count), ctx->stream));
-      *mode = 1;
+      if (pending)
+        ACU_LAUNCH(ctx, k_zero_bitmap_dev, acu_grid(ctx, (plan->len / 64 + 255) / 256, 2), 256, 0, reinterpret_cast<uint64_t *>(out->validity),
+                   plan->tile_off + plan->n_tiles);
+      else
+        ACU_CUDA(ctx, cudaMemsetAsync(out->validity, 0, acu_bitmap_bytes(plan->count), ctx->stream));
+      *mode = pending ? 3 : 1;
     }
     ACU_TRY(launch_filter_width(ctx, elem_bytes, fb, 1, plan_uses_fused(plan)));
   }
@@ -1142,7 +1170,7 @@ acu_status acu_filter_col_launch(acu_ctx *ctx, const acu_filter_plan *plan, int 
     cb.col[nc++] = compress_args(plan, static_cast<const uint8_t *>(values->values), values->values_offset, out->values, nullptr);
   if (has_nulls && !fused) {  // FilterPredicate::filter_nulls (filter.rs:512-533)
     cb.col[nc++] = compress_args(plan, values->validity, values->validity_offset, out->validity, res);
-    *mode = 1;
+    *mode = pending ? 3 : 1;
   }
   if (nc) ACU_TRY(launch_compress(ctx, plan, cb, nc));
   return ACU_OK;
@@ -1210,11 +1238,15 @@ acu_status acu_filter_cols_launch(acu_ctx *ctx, const acu_filter_plan *plan, int
 void acu_filter_col_finalize(const acu_filter_plan *plan, const acu_array *values, int mode,
                              const unsigned long long *hres, acu_array_out *out) {
   (void)values;
+  out->len = plan->count;  // (known only now when the call was queued in an async section)
   out->has_validity = 0;
   out->null_count = 0;
   if (mode == 1) {  // None when the filtered validity has no nulls (filter.rs:523-525)
     const int64_t null_count = plan->count - (int64_t)hres[RES_COUNT];
     if (null_count > 0) { out->has_validity = 1; out->null_count = null_count; }
+  } else if (mode == 3) {  // queued with a pending plan: IterationStrategy::All keeps the NullBuffer, the others drop an empty one
+    const int64_t null_count = plan->count - (int64_t)hres[RES_COUNT];
+    if (null_count > 0 || (plan->count == plan->len && plan->count > 0)) { out->has_validity = 1; out->null_count = null_count; }
   } else if (mode == 2) {  // the slice keeps its NullBuffer
     out->has_validity = 1;
     out->null_count = plan->count - (int64_t)hres[RES_COUNT];

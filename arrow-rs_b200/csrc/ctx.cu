@@ -73,6 +73,9 @@ __global__ void k_res_reset(unsigned long long *res, int slots) {
 // res_clean is dropped by the first reset after a fetch; a call that failed between its reset and its fetch leaves
 // res_clean false and the next reset launches k_res_reset itself. res_dirty_blocks = blocks possibly written since.
 acu_status acu_res_reset_n(acu_ctx *ctx, int blocks) {
+  if (ctx->async_on)  // entry points that have not been split into enqueue + finalise would synchronise here
+    return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0,
+                    "this entry point synchronises and is not available between acu_async_begin and acu_results_fetch");
   if (blocks < 1) blocks = 1;
   if (blocks > RES_BLOCKS) blocks = RES_BLOCKS;
   if (!ctx->res_clean) {
@@ -97,6 +100,64 @@ acu_status acu_res_fetch_n(acu_ctx *ctx, int blocks) {
   acu_kstats_drain(ctx);
   return ACU_OK;
 }
+
+int acu_call_begin(acu_ctx *ctx, acu_status *st) {
+  if (!ctx->async_on) {
+    *st = acu_res_reset(ctx);
+    return 0;
+  }
+  if (ctx->async_blocks >= RES_BLOCKS) {
+    *st = acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "more than %d calls queued in one async section", (int)RES_BLOCKS);
+    return 0;
+  }
+  *st = ACU_OK;
+  return ctx->async_blocks++;
+}
+
+acu_status acu_call_end(acu_ctx *ctx, int block, std::function<acu_status(const unsigned long long *)> fin) {
+  if (!ctx->async_on) {
+    ACU_TRY(acu_res_fetch(ctx));
+    return fin(acu_hres(ctx, 0));
+  }
+  ctx->async_fin.push_back(std::move(fin));
+  ctx->async_blk.push_back(block);
+  return ACU_OK;
+}
+
+extern "C" acu_status acu_async_begin(acu_ctx *ctx) {
+  ACU_ENTER(ctx);
+  if (ctx->async_on) return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "acu_async_begin: a section is already open");
+  ACU_TRY(acu_res_reset_n(ctx, RES_BLOCKS));  // every block clean (free when the last fetch left them so)
+  ctx->async_on = true;
+  ctx->async_blocks = 0;
+  ctx->async_fin.clear();
+  ctx->async_blk.clear();
+  return ACU_OK;
+}
+
+extern "C" acu_status acu_results_fetch(acu_ctx *ctx) {
+  ACU_ENTER(ctx);
+  if (!ctx->async_on) return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, 0, "acu_results_fetch: no async section is open");
+  ctx->async_on = false;
+  acu_status first = acu_res_fetch_n(ctx, ctx->async_blocks > 0 ? ctx->async_blocks : 1);  // ONE D2H copy + ONE synchronisation
+  acu_error_detail first_err = ctx->err;
+  if (first == ACU_OK) {
+    for (size_t i = 0; i < ctx->async_fin.size(); ++i) {  // in call order: a plan's count is known before its filters finalise
+      const acu_status st = ctx->async_fin[i](acu_hres(ctx, ctx->async_blk[i]));
+      if (st != ACU_OK && first == ACU_OK) {
+        first = st;
+        first_err = ctx->err;
+      }
+    }
+  }
+  if (first != ACU_OK) ctx->err = first_err;
+  ctx->async_fin.clear();
+  ctx->async_blk.clear();
+  ctx->async_blocks = 0;
+  return first;
+}
+
+extern "C" int32_t acu_async_active(const acu_ctx *ctx) { return ctx->async_on ? 1 : 0; }
 
 acu_status acu_res_reset(acu_ctx *ctx) { return acu_res_reset_n(ctx, 1); }
 acu_status acu_res_fetch(acu_ctx *ctx) { return acu_res_fetch_n(ctx, 1); }

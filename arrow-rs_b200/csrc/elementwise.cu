@@ -389,7 +389,9 @@ acu_status arith_typed(acu_ctx *ctx, acu_arith_op op, const acu_array *a, const 
     }
   }
   p.n = len;
-  ACU_TRY(acu_res_reset(ctx));
+  const int blk = acu_call_begin(ctx, &st);
+  ACU_TRY(st);
+  p.res = acu_dres(ctx, blk);
   if (is_fp<T>::value) {
     if (op == ACU_DIV || op == ACU_REM) ACU_TRY((launch_arith<T, CLS_DIVREM>(ctx, p)));
     else ACU_TRY((launch_arith<T, CLS_WRAP>(ctx, p)));
@@ -400,14 +402,16 @@ acu_status arith_typed(acu_ctx *ctx, acu_arith_op op, const acu_array *a, const 
   } else {
     ACU_TRY((launch_arith<T, CLS_WRAP>(ctx, p)));
   }
-  ACU_TRY(acu_res_fetch(ctx));
-  if (checked && ctx->h_res[RES_ERR_INDEX] != ~0ull)
-    return arith_error<T>(ctx, op, false, a, b, (int64_t)ctx->h_res[RES_ERR_INDEX]);
-  if (p.out_valid) {
-    out->has_validity = 1;
-    out->null_count = len - (int64_t)ctx->h_res[RES_COUNT];
-  }
-  return ACU_OK;
+  const acu_array ca = *a, cb = *b;  // the finaliser may run later (acu_results_fetch)
+  const bool has_valid = p.out_valid != nullptr;
+  return acu_call_end(ctx, blk, [ctx, op, checked, ca, cb, has_valid, len, out](const unsigned long long *h) -> acu_status {
+    if (checked && h[RES_ERR_INDEX] != ~0ull) return arith_error<T>(ctx, op, false, &ca, &cb, (int64_t)h[RES_ERR_INDEX]);
+    if (has_valid) {
+      out->has_validity = 1;
+      out->null_count = len - (int64_t)h[RES_COUNT];
+    }
+    return ACU_OK;
+  });
 }
 
 template <class T>
@@ -681,7 +685,12 @@ acu_status cmp_typed(acu_ctx *ctx, acu_cmp_op op, const acu_array *l, const acu_
   if (xn) { if (xs && !(xs && ys)) p.a_null_scalar = 1; else { p.av = x->validity; p.aoff = x->validity_offset; } }
   if (yn) { if (ys && !(xs && ys)) p.b_null_scalar = 1; else { p.bv = y->validity; p.boff = y->validity_offset; } }
   if (!fold && (xn || yn) && !fuse) p.out_valid = reinterpret_cast<uint64_t *>(out->validity);
-  if (!fuse) ACU_TRY(acu_res_reset(ctx));
+  int blk = 0;
+  if (!fuse) {
+    blk = acu_call_begin(ctx, &st);
+    ACU_TRY(st);
+    p.res = acu_dres(ctx, blk);
+  }
   const bool lt = !(op == ACU_EQ || op == ACU_NEQ || fold);
   // streaming head over whole 2048-row super-groups when the value pointers are 16-B aligned
   const bool aligned = (p.a_scalar || (uintptr_t)p.a % 16 == 0) && (p.b_scalar || (uintptr_t)p.b % 16 == 0);
@@ -711,12 +720,14 @@ acu_status cmp_typed(acu_ctx *ctx, acu_cmp_op op, const acu_array *l, const acu_
     }
   }
   if (fuse) return ACU_OK;  // stream-ordered: the plan's scan kernels follow on the same stream
-  ACU_TRY(acu_res_fetch(ctx));
-  if (p.out_valid) {
-    out->has_validity = 1;
-    out->null_count = len - (int64_t)ctx->h_res[RES_COUNT];
-  }
-  return ACU_OK;
+  const bool has_valid = p.out_valid != nullptr;
+  return acu_call_end(ctx, blk, [has_valid, len, out](const unsigned long long *h) -> acu_status {
+    if (has_valid) {
+      out->has_validity = 1;
+      out->null_count = len - (int64_t)h[RES_COUNT];
+    }
+    return ACU_OK;
+  });
 }
 
 // ---------------------------------------------------------------------------------------

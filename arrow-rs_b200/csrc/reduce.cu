@@ -263,17 +263,27 @@ extern "C" acu_status acu_aggregate(acu_ctx *ctx, acu_dtype dtype, acu_agg_op op
   *out_bits = 0;
   *out_valid_count = 0;
   if (a->len == 0) return ACU_OK;  // None
-  acu_status st;
-  const int64_t nc = acu_resolve_null_count(ctx, a, &st);
+  acu_status st = ACU_OK;
+  // inside an async section an unknown null count (the array was produced earlier in the same section) is not resolved by
+  // a round trip: the kernel consults the validity and counts the valid rows itself (RES_COUNT)
+  const bool deferred_nc = ctx->async_on && a->validity && a->null_count < 0;
+  const int64_t nc = deferred_nc ? 1 : acu_resolve_null_count(ctx, a, &st);
   ACU_TRY(st);
-  *out_valid_count = a->len - nc;
+  if (!deferred_nc) *out_valid_count = a->len - nc;
   void *scratch;
   ACU_TRY(acu_scratch(ctx, acu_reduce_col_scratch(ctx), &scratch));
   int launched = 0;
-  ACU_TRY(acu_res_reset(ctx));
-  ACU_TRY(acu_reduce_col_launch(ctx, dtype, op, a, nc, scratch, acu_dres(ctx, 0), &launched));
-  if (!launched) return ACU_OK;
-  ACU_TRY(acu_res_fetch(ctx));
-  *out_bits = ctx->h_res[RES_AUX0];
-  return ACU_OK;
+  const int blk = acu_call_begin(ctx, &st);
+  ACU_TRY(st);
+  ACU_TRY(acu_reduce_col_launch(ctx, dtype, op, a, nc, scratch, acu_dres(ctx, blk), &launched));
+  if (!launched && !ctx->async_on) return ACU_OK;
+  return acu_call_end(ctx, blk, [launched, deferred_nc, out_bits, out_valid_count](const unsigned long long *h) -> acu_status {
+    if (!launched) return ACU_OK;
+    if (deferred_nc) {
+      *out_valid_count = (int64_t)h[RES_COUNT];
+      if (*out_valid_count == 0) return ACU_OK;  // every row null: None (aggregate.rs:320-323)
+    }
+    *out_bits = h[RES_AUX0];
+    return ACU_OK;
+  });
 }

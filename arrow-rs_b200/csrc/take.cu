@@ -337,10 +337,13 @@ acu_status acu_take_common(acu_ctx *ctx, int32_t elem_bytes, const acu_array *va
   ACU_TRY(st);
   const bool val_nulls = values->validity && vnc > 0;  // take_nulls (take.rs:419-430)
   int mode = 0;
-  ACU_TRY(acu_res_reset(ctx));
-  ACU_TRY(acu_take_col_launch(ctx, elem_bytes, values, boolean_values, val_nulls, indices, index_dtype, idx_nulls, out, acu_dres(ctx, 0), &mode));
-  ACU_TRY(acu_res_fetch(ctx));
-  return acu_take_col_finalize(ctx, values, indices, index_dtype, mode, acu_hres(ctx, 0), out);
+  const int blk = acu_call_begin(ctx, &st);
+  ACU_TRY(st);
+  ACU_TRY(acu_take_col_launch(ctx, elem_bytes, values, boolean_values, val_nulls, indices, index_dtype, idx_nulls, out, acu_dres(ctx, blk), &mode));
+  const acu_array v = *values, ix = *indices;  // the finaliser may run later (acu_results_fetch): keep copies of the descriptors
+  return acu_call_end(ctx, blk, [ctx, v, ix, index_dtype, mode, out](const unsigned long long *h) -> acu_status {
+    return acu_take_col_finalize(ctx, &v, &ix, index_dtype, mode, h, out);
+  });
 }
 
 // One column of take / take_record_batch: queue the gather on the ctx stream without

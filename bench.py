@@ -267,30 +267,47 @@ def gpu_checksums(ctx, abi, wl):
 ALLREDUCE_WALL = [0.0, 0]  # host seconds spent inside the final-reduce call (includes waiting for the slowest rank), calls
 
 
+STREAM_ORDERED = os.environ.get("ACU_BENCH_SYNC", "0") != "1"
+
+
 def hot_path_step(ctx, abi, pred, col, idx, a, b, out_filter, out_take, out_add, allreduce):
     """One pass of the hot path through the C ABI (device pointers):
-    filter(col, pred) -> take(col, idx) -> add(a, b) -> sum(taken) [-> NCCL all-reduce]."""
+    filter(col, pred) -> take(col, idx) -> add(a, b) -> sum(taken) [-> NCCL all-reduce].
+    By default the five calls are queued in ONE stream-ordered section (acu_async_begin ... acu_results_fetch: one D2H and
+    one synchronisation per step); ACU_BENCH_SYNC=1 uses the synchronous form of the same entry points (one sync each)."""
     lib, h = ctx.lib, ctx.h
     plan = C.c_void_p()
-    ctx.check(lib.acu_filter_plan_create(h, C.byref(pred), C.byref(plan)))
+    bits, cnt = C.c_uint64(0), C.c_int64(0)
+    if STREAM_ORDERED:
+        ctx.check(lib.acu_async_begin(h))
     try:
+        ctx.check(lib.acu_filter_plan_create(h, C.byref(pred), C.byref(plan)))
         ctx.check(lib.acu_filter_primitive(h, plan, 8, C.byref(col), C.byref(out_filter)))
+        ctx.check(lib.acu_take_primitive(h, 8, C.byref(col), C.byref(idx), abi.U32, 0, C.byref(out_take)))
+        ctx.check(lib.acu_arith(h, abi.F64, abi.ADD, C.byref(a), C.byref(b), C.byref(out_add)))
+        if STREAM_ORDERED:
+            # the taken column's null count is still on the device: -1 makes the reduction count its valid rows itself
+            has_v = bool(col.validity) and col.null_count != 0 or bool(idx.validity)
+            taken = make_arr(abi, out_take.values, out_take.validity if has_v else None, idx.len, -1 if has_v else 0)
+        else:
+            taken = make_arr(abi, out_take.values, out_take.validity if out_take.has_validity else None, out_take.len,
+                             out_take.null_count if out_take.has_validity else 0)
+        # multi-GPU: sum of the shard + NCCL all-reduce of {sum, valid_count} in place on the call's result block — the
+        # partial never bounces through the host between the reduction kernel and the collective (world 1: acu_aggregate)
+        t0 = time.perf_counter()
+        agg = lib.acu_aggregate_allreduce if allreduce else lib.acu_aggregate
+        ctx.check(agg(h, abi.I64, abi.SUM, C.byref(taken), C.byref(bits), C.byref(cnt)))
+        if STREAM_ORDERED:
+            ctx.check(lib.acu_results_fetch(h))
+        if allreduce:
+            ALLREDUCE_WALL[0] += time.perf_counter() - t0
+            ALLREDUCE_WALL[1] += 1
+    except BaseException:
+        if STREAM_ORDERED and lib.acu_async_active(h):
+            lib.acu_results_fetch(h)  # close the section before the plan goes away
+        raise
     finally:
         lib.acu_filter_plan_destroy(h, plan)
-    ctx.check(lib.acu_take_primitive(h, 8, C.byref(col), C.byref(idx), abi.U32, 0, C.byref(out_take)))
-    ctx.check(lib.acu_arith(h, abi.F64, abi.ADD, C.byref(a), C.byref(b), C.byref(out_add)))
-    taken = make_arr(abi, out_take.values, out_take.validity if out_take.has_validity else None, out_take.len,
-                     out_take.null_count if out_take.has_validity else 0)
-    bits, cnt = C.c_uint64(0), C.c_int64(0)
-    if allreduce:
-        # sum of the shard + NCCL all-reduce of {sum, valid_count} in ONE call with one synchronisation: the partial never
-        # bounces through the host between the reduction kernel and the collective (world 1: plain acu_aggregate)
-        t0 = time.perf_counter()
-        ctx.check(lib.acu_aggregate_allreduce(h, abi.I64, abi.SUM, C.byref(taken), C.byref(bits), C.byref(cnt)))
-        ALLREDUCE_WALL[0] += time.perf_counter() - t0
-        ALLREDUCE_WALL[1] += 1
-        return bits.value, cnt.value
-    ctx.check(lib.acu_aggregate(h, abi.I64, abi.SUM, C.byref(taken), C.byref(bits), C.byref(cnt)))
     return bits.value, cnt.value
 
 
@@ -654,8 +671,13 @@ def run_gpu(args):
         "kernels": kstats,
         "gpu_launches": launches,
         "ms_per_step_rank0": ms.value / args.steps,
-        "final_reduce_ms_per_step": (1e3 * ALLREDUCE_WALL[0] / max(ALLREDUCE_WALL[1], 1) - kstats.get("reduce", {}).get("ms_per_step", 0.0)) if world > 1 else 0.0,
-        "final_reduce_note": "host wall time of acu_aggregate_allreduce (reduction kernel + staging kernel + NCCL all-reduce + D2H + the wait for the slowest rank) minus the reduction kernel's device time",
+        "stream_ordered": STREAM_ORDERED,
+        "sync_gap_ms_per_step": step_ms - sum(v.get("ms_per_step", 0.0) for v in kstats.values()),
+        "sync_gap_note": "step time minus the CUDA-event time of the step's kernel classes = launch gaps + the ONE result fetch"
+                         + (" + NCCL all-reduce of {sum, count} in place on the result block + the wait for the slowest rank" if world > 1 else ""),
+        "final_reduce_ms_per_step": ((step_ms - sum(v.get("ms_per_step", 0.0) for v in kstats.values())) if STREAM_ORDERED else
+                                     (1e3 * ALLREDUCE_WALL[0] / max(ALLREDUCE_WALL[1], 1) - kstats.get("reduce", {}).get("ms_per_step", 0.0))) if world > 1 else 0.0,
+        "final_reduce_note": "stream-ordered step: everything of the step that is not kernel time (upper bound of the all-reduce cost); ACU_BENCH_SYNC=1: host wall time of acu_aggregate_allreduce minus the reduction kernel's device time",
         "clocks": clocks,
         "e2e": e2e,
         "check": {"sum_bits": int(total_bits), "valid_rows": int(total_cnt), "rank0_local": gpu_chk},

@@ -23,7 +23,8 @@
  *
  * Calls are synchronous with respect to the host: every entry point that returns a
  * host-visible scalar (count, null_count, error index) synchronises the ctx stream
- * before returning. One acu_ctx = one device + one stream + scratch; a ctx must not
+ * before returning (stream-ordered sections, acu_async_begin below, defer that to ONE
+ * synchronisation for a chain of calls). One acu_ctx = one device + one stream + scratch; a ctx must not
  * be used from two host threads at once, distinct ctxs are independent (the
  * reference kernels are pure, re-entrant functions: arrow-array/src/array/mod.rs:99).
  *
@@ -166,6 +167,28 @@ acu_status acu_host_free(acu_ctx *ctx, void *host);
 /* Bytes currently allocated through acu_malloc on this ctx (observability; the
  * reference's MemoryPool tracking, arrow-buffer/src/pool.rs:73-85). */
 int64_t acu_bytes_allocated(const acu_ctx *ctx);
+
+/* ---- Stream-ordered sections -------------------------------------------------------------------------------------
+ * The reference functions are synchronous (arrow-array/src/array/mod.rs:99) and so is every entry point by default. A
+ * caller that chains several kernels (filter -> take -> add -> sum) can instead open a SECTION: between acu_async_begin
+ * and acu_results_fetch the entry points listed below only ENQUEUE their kernels on the ctx stream and return at once;
+ * each call owns one of the ctx's 64 result blocks (count, null count, lowest failing row stay in HBM).
+ * acu_results_fetch copies all blocks to the host in ONE transfer with ONE synchronisation, then finalises the queued
+ * calls in call order: it fills the acu_array_out / scalar outputs the calls were given (len, has_validity, null_count,
+ * aggregate bits), fills acu_filter_plan count / strategy, and returns the FIRST error in call order with its exact
+ * reference text (the outputs of the calls after a failed one are unspecified, as after any failed call).
+ *   - stream-ordered inside a section: acu_filter_plan_create, acu_filter_plan_create_cmp, acu_filter_primitive,
+ *     acu_filter_boolean, acu_take_primitive / acu_take_boolean (check_bounds = 0), acu_arith, acu_cmp, acu_aggregate,
+ *     acu_aggregate_allreduce. Any other entry point fails with ACU_ERR_INVALID_ARGUMENT (it would synchronise).
+ *   - every output descriptor, scalar output pointer and plan passed to a queued call must stay alive until the fetch;
+ *     input arrays must carry their cached null_count (-1 would need a device count = a synchronisation), except for
+ *     acu_aggregate*, which then counts the valid rows on the device (an array produced earlier in the same section);
+ *   - a plan created inside the section can be used by filters queued after it: their outputs must then be sized for
+ *     plan LEN rows (the count is still on the device); out->len is set by the fetch;
+ *   - at most 64 calls per section. */
+acu_status acu_async_begin(acu_ctx *ctx);
+acu_status acu_results_fetch(acu_ctx *ctx);
+int32_t acu_async_active(const acu_ctx *ctx);
 
 /* CUDA-event timers on the ctx stream (events see exactly the stream kernels run on).
  * ACU_TIMER_SLOTS independent slots so that a step timer can bracket per-op timers. */
