@@ -505,19 +505,25 @@ __global__ void __launch_bounds__(BY_THREADS, 2) k_bytes_offsets_copy(const Byte
 // width (one 128-byte line per lane): with two offset loads and the value bytes per row that alone is ~5 cycles per row
 // per SM, i.e. the 1.4 ms the generic kernels need for 1e8 rows. Here the dictionary is first re-laid out as a table of
 // 16-byte zero-padded entries + one length byte per entry (k_dict_table; sources with an entry longer than 16 bytes keep
-// the generic path), every CTA keeps that table in shared memory (D x 17 bytes: 70 KB for D = 4096) and the gathers become
-// LDS.128 / LDS.U8 (a few cycles per warp). Rows are owned by warps (lane == row % 32, 128 rows per warp, 2048 per CTA
-// round so that the scan of the per-2048-row totals is the generic one); a row's bytes reach their final position by two
-// funnel shifts and predicated ATOMS.OR into a warp-private zeroed ring that mirrors the output's 16-byte alignment, and
-// completed 16-byte chunks leave as 128-bit stores. No CTA barrier in the copy except the one that turns the 16 warp
-// totals into warp base offsets.
+// the generic path) and every CTA keeps that table in shared memory (D x 17 bytes: 70 KB for D = 4096): the gathers become
+// LDS.128 / LDS.U8.
+//   pass 1 (k_dict_block_totals): a WARP owns a 2048-row block — 16 x (one 128-bit load of 4 keys per lane, 4 LDS.U8),
+//     one redux.sync, no CTA barrier.
+//   pass 2 (k_dict_copy): a CTA owns a 2048-row block (16 warps x 4 x 32 rows, lane == row % 32 so that the 32 rows of
+//     an instruction land ~8 bytes apart: ~2-way bank conflicts). The four 32-row scans of a warp are two packed 16-bit
+//     scans; a row's bytes reach their position in a zeroed 32-KB shared-memory IMAGE of the CTA's output (which mirrors
+//     the output's 16-byte alignment) by funnel shifts + predicated ATOMS.OR; the image leaves as coalesced 128-bit stores
+//     (only the first / last chunk of a CTA, shared with its neighbours, is written bytewise) and is re-zeroed on the way.
+//     All positions inside a round are 32-bit. The first version of this path (warp-private rings, 64-bit positions,
+//     bytewise head / tail per warp) needed 1047 warp instructions per 128 rows and was issue-bound (ncu: 67 % issue
+//     slots busy, 1.07 ms per 1e8 rows, profiles/r02_dict_notes.md).
 #define DG_THREADS 512
 #define DG_WARPS (DG_THREADS / 32)
 #define DG_WROWS (BY_ROWS / DG_WARPS)   // 128 rows per warp and round
 #define DG_ITERS (DG_WROWS / 32)        // 4 x 32 rows
-#define DG_WIN 1024                     // ring bytes per warp (power of two; a 32-row round writes <= 512 bytes)
-#define DG_WINW (DG_WIN / 4)
+#define DG_IMG_BYTES (BY_ROWS * 16 + 32)  // image of one CTA round: <= 2048 x 16 bytes + alignment slack
 #define DG_MAX_ENTRIES 8192
+static_assert(DG_ITERS == 4, "k_dict_copy packs the four 32-row scans of a warp into two registers");
 
 __global__ void __launch_bounds__(256) k_dict_table(const int32_t *__restrict__ offs, const uint8_t *__restrict__ data, int64_t n_src,
                                                     uint4 *__restrict__ table, uint8_t *__restrict__ lens, int *__restrict__ too_long) {
@@ -536,7 +542,7 @@ __global__ void __launch_bounds__(256) k_dict_table(const int32_t *__restrict__ 
 }
 
 struct DictArgs {
-  const uint32_t *keys;       // 32-bit keys (ToIndices of i32 / u32)
+  const uint32_t *keys;       // 32-bit keys (ToIndices of i32 / u32), 16-byte aligned
   int64_t m;                  // output rows
   uint32_t n_src;             // dictionary entries (<= DG_MAX_ENTRIES)
   const uint32_t *out_valid;  // output validity (bit offset 0) or NULL: null slots get zero length
@@ -546,169 +552,225 @@ struct DictArgs {
   const int *too_long;        // set by k_dict_table: the kernels return immediately and the generic path runs
 };
 
-// pass 1: byte total of every 2048-row block (+ out-of-bounds keys at valid slots)
+// pass 1: byte total of every 2048-row block (+ out-of-bounds keys at valid slots); a warp per block
 __global__ void __launch_bounds__(DG_THREADS) k_dict_block_totals(const DictArgs a, int64_t blocks, int64_t *__restrict__ block_tot,
                                                                   unsigned long long *__restrict__ res) {
   extern __shared__ __align__(16) uint8_t s_dyn[];
-  __shared__ uint32_t s_wsum[DG_WARPS];
   if (*a.too_long) return;
   uint8_t *s_len = s_dyn;
   for (uint32_t i = threadIdx.x; i < a.n_src; i += DG_THREADS) s_len[i] = a.lens[i];
   __syncthreads();
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * DG_THREADS + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * DG_THREADS) >> 5;
+  const uint32_t n_src = a.n_src;
   unsigned long long err = ~0ull;
-  for (int64_t blk = blockIdx.x; blk < blocks; blk += gridDim.x) {
+  for (int64_t blk = warp; blk < blocks; blk += nwarps) {
+    const int64_t base = blk * BY_ROWS;
     uint32_t sum = 0;
+    if (base + BY_ROWS <= a.m) {  // a whole block: 16 x (4 keys per lane)
+      const uint4 *kp = reinterpret_cast<const uint4 *>(a.keys + base) + lane;
+      const uint32_t *vp = a.out_valid ? a.out_valid + (base >> 5) + (lane >> 3) : nullptr;
+      const int vsh = (lane & 7) * 4;
+#pragma unroll 1
+      for (int it0 = 0; it0 < BY_ROWS / 128; it0 += 8) {  // 8 x 128-bit key loads (+ 8 validity words) in flight per lane
+        uint4 k[8];
+        uint32_t vb[8];
 #pragma unroll
-    for (int k = 0; k < BY_ROWS / DG_THREADS; ++k) {
-      const int64_t j = blk * BY_ROWS + (int64_t)k * DG_THREADS + threadIdx.x;
-      if (j < a.m) {
+        for (int u = 0; u < 8; ++u) {
+          k[u] = __ldg(kp + (it0 + u) * 32);
+          vb[u] = vp ? __ldg(vp + (it0 + u) * 4) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t v4 = (vb[u] >> vsh) & 0xfu;
+          const uint32_t kk[4] = {k[u].x, k[u].y, k[u].z, k[u].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if ((v4 >> e) & 1u) {
+              if (kk[e] < n_src) sum += s_len[kk[e]];
+              else {
+                const unsigned long long j = (unsigned long long)(base + (it0 + u) * 128 + lane * 4 + e);
+                if (j < err) err = j;
+              }
+            }
+          }
+        }
+      }
+    } else {  // the ragged last block
+      for (int r = lane; r < BY_ROWS; r += 32) {
+        const int64_t j = base + r;
+        if (j >= a.m) break;
         const uint32_t key = __ldg(a.keys + j);
         bool use = true;
         if (a.out_valid) use = (__ldg(a.out_valid + (j >> 5)) >> (j & 31)) & 1u;
-        if (use && key >= a.n_src) {
-          use = false;
-          if ((unsigned long long)j < err) err = (unsigned long long)j;
+        if (use) {
+          if (key < n_src) sum += s_len[key];
+          else if ((unsigned long long)j < err) err = (unsigned long long)j;
         }
-        if (use) sum += s_len[key];
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(ACU_FULL_MASK, sum, o);
-    if (lane == 0) s_wsum[wid] = sum;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t t = 0;
-      for (int w = 0; w < DG_WARPS; ++w) t += s_wsum[w];
-      block_tot[blk] = (int64_t)t;
-    }
-    __syncthreads();
+    sum = __reduce_add_sync(ACU_FULL_MASK, sum);
+    if (lane == 0) block_tot[blk] = (int64_t)sum;
   }
   if (a.detect_oob && err != ~0ull) atomicMin(res + RES_ERR_INDEX, err);
 }
 
-// pass 2: new offsets + bytes
-__global__ void __launch_bounds__(DG_THREADS) k_dict_copy(const DictArgs a, const int64_t *__restrict__ block_incl, int64_t blocks,
-                                                          int32_t *__restrict__ out_offs, uint8_t *__restrict__ out_data, int64_t limit,
-                                                          unsigned long long *res, const int64_t *__restrict__ total_ptr, int64_t out_cap) {
+// OR `x` into the shared-memory word at byte address `saddr + OFF` (RED: no return value)
+template <int OFF>
+__device__ __forceinline__ void red_or(uint32_t saddr, uint32_t x) {
+  asm volatile("red.shared.or.b32 [%0+%2], %1;" ::"r"(saddr), "r"(x), "n"(OFF) : "memory");
+}
+
+// pass 2: new offsets + bytes. A CTA round is a dependent chain (keys -> lengths -> scan -> barrier -> image -> barrier ->
+// flush -> barrier) with only two CTAs per SM, so the NEXT round's keys, validity words and base offset are loaded at the
+// top of the current round (software prefetch): without it every round exposes a full DRAM latency (measured 0.78 ms vs
+// profiles/r02_dict_notes.md for 1e8 rows).
+struct DictRound {
+  uint32_t key[DG_ITERS];  // raw keys (~0 for rows past the end)
+  uint32_t vw;             // lane i < 4: validity word of the warp's i-th 32-row group (all ones without a bitmap)
+  int64_t cta_begin;
+  uint32_t rows_here;
+};
+
+__device__ __forceinline__ void dict_round_load(const DictArgs &a, const int64_t *__restrict__ block_incl, int64_t blk, DictRound &r) {
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t base = blk * BY_ROWS;
+  const int64_t left = a.m - base;
+  r.rows_here = left < BY_ROWS ? (uint32_t)left : (uint32_t)BY_ROWS;
+  r.cta_begin = blk ? __ldg(block_incl + blk - 1) : 0;
+  const uint32_t r0 = wid * DG_WROWS + lane;
+  const uint32_t *kp = a.keys + base + r0;
+#pragma unroll
+  for (int i = 0; i < DG_ITERS; ++i) r.key[i] = (r0 + i * 32 < r.rows_here) ? __ldg(kp + i * 32) : 0xffffffffu;
+  r.vw = 0xffffffffu;
+  if (a.out_valid) r.vw = (lane < DG_ITERS && wid * DG_WROWS + lane * 32 < r.rows_here) ? __ldg(a.out_valid + (base >> 5) + wid * DG_ITERS + lane) : 0u;
+}
+
+__global__ void __launch_bounds__(DG_THREADS, 2) k_dict_copy(const DictArgs a, const int64_t *__restrict__ block_incl, int64_t blocks,
+                                                             int32_t *__restrict__ out_offs, uint8_t *__restrict__ out_data, int64_t limit,
+                                                             unsigned long long *res, const int64_t *__restrict__ total_ptr, int64_t out_cap) {
   extern __shared__ __align__(16) uint8_t s_dyn[];
-  __shared__ __align__(16) uint32_t s_win[DG_WARPS][DG_WINW];
   __shared__ uint32_t s_wtot[DG_WARPS];
   if (*a.too_long) return;
   if (out_data != nullptr && total_ptr != nullptr) {  // decided on the device: no host round trip between the passes
     const int64_t total = __ldg(total_ptr);
     if (total > out_cap || total > limit) out_data = nullptr;
   }
+  const uint32_t n_src = a.n_src;  // the shared-memory table has n_src + 1 entries: the last one is the empty string
   uint4 *s_tab = reinterpret_cast<uint4 *>(s_dyn);
-  uint8_t *s_len = s_dyn + (size_t)a.n_src * 16;
-  for (uint32_t i = threadIdx.x; i < a.n_src; i += DG_THREADS) { s_tab[i] = a.table[i]; s_len[i] = a.lens[i]; }
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  uint32_t *win = s_win[wid];
-  for (int i = lane; i < DG_WIN / 16; i += 32) reinterpret_cast<uint4 *>(win)[i] = make_uint4(0, 0, 0, 0);
+  uint8_t *s_len = s_dyn + ((size_t)n_src + 1) * 16;
+  uint32_t *s_img = reinterpret_cast<uint32_t *>(s_dyn + ((size_t)n_src + 1) * 16 + ((n_src + 16u) & ~15u));
+  DictRound cur;
+  if ((int64_t)blockIdx.x < blocks) dict_round_load(a, block_incl, blockIdx.x, cur);
+  for (uint32_t i = threadIdx.x; i < n_src; i += DG_THREADS) { s_tab[i] = a.table[i]; s_len[i] = a.lens[i]; }
+  if (threadIdx.x == 0) { s_tab[n_src] = make_uint4(0, 0, 0, 0); s_len[n_src] = 0; }
+  for (uint32_t i = threadIdx.x; i < DG_IMG_BYTES / 16; i += DG_THREADS) reinterpret_cast<uint4 *>(s_img)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
-  const uint32_t A = (uint32_t)((uintptr_t)out_data & 15);  // ring positions mirror the output's 16-byte alignment
-  uint8_t *gbase = out_data - A;
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t r0 = wid * DG_WROWS + lane;  // this lane's rows of a round: r0 + 32 i
+  const uint32_t img = (uint32_t)__cvta_generic_to_shared(s_img);
+  uint4 *img4 = reinterpret_cast<uint4 *>(s_img);
   unsigned long long err = ~0ull;
   for (int64_t blk = blockIdx.x; blk < blocks; blk += gridDim.x) {
-    const int64_t cta_begin = blk ? block_incl[blk - 1] : 0;
-    const int64_t row0 = blk * BY_ROWS + (int64_t)wid * DG_WROWS;
-    uint32_t key[DG_ITERS], len[DG_ITERS], pre[DG_ITERS], tot[DG_ITERS];
+    const int64_t base = blk * BY_ROWS;
+    const uint32_t rows_here = cur.rows_here;
+    const int64_t cta_begin = cur.cta_begin;
+    uint32_t key[DG_ITERS], len[DG_ITERS];
 #pragma unroll
     for (int i = 0; i < DG_ITERS; ++i) {
-      const int64_t j = row0 + i * 32 + lane;
-      const bool live = j < a.m;
-      key[i] = live ? __ldg(a.keys + j) : 0u;
-      uint32_t vw = ~0u;
-      if (a.out_valid && row0 + i * 32 < a.m) vw = __ldg(a.out_valid + ((row0 + i * 32) >> 5));
-      const bool use = live && ((vw >> lane) & 1u) && key[i] < a.n_src;  // out-of-bounds keys were reported by pass 1
-      if (!use) key[i] = 0xffffffffu;
-      len[i] = use ? s_len[key[i]] : 0u;
+      const uint32_t vw = __shfl_sync(ACU_FULL_MASK, cur.vw, i);
+      const bool use = ((vw >> lane) & 1u) && cur.key[i] < n_src;  // (a row past the end has key ~0; OOB keys were reported by pass 1)
+      key[i] = use ? cur.key[i] : n_src;                            // entry n_src = the empty string
+      len[i] = s_len[key[i]];
     }
-    uint32_t run = 0;
+    if (blk + gridDim.x < blocks) dict_round_load(a, block_incl, blk + gridDim.x, cur);  // in flight during this round
+    // four inclusive 32-row scans as two packed 16-bit scans (a 32-row total is <= 512)
+    const uint32_t p01 = len[0] | (len[1] << 16), p23 = len[2] | (len[3] << 16);
+    uint32_t i01 = p01, i23 = p23;
 #pragma unroll
-    for (int i = 0; i < DG_ITERS; ++i) {
-      uint32_t incl = len[i];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(ACU_FULL_MASK, incl, o);
-        if (lane >= o) incl += y;
-      }
-      tot[i] = __shfl_sync(ACU_FULL_MASK, incl, 31);
-      pre[i] = run + incl - len[i];
-      run += tot[i];
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y01 = __shfl_up_sync(ACU_FULL_MASK, i01, o), y23 = __shfl_up_sync(ACU_FULL_MASK, i23, o);
+      if (lane >= (uint32_t)o) { i01 += y01; i23 += y23; }
     }
+    const uint32_t t01 = __shfl_sync(ACU_FULL_MASK, i01, 31), t23 = __shfl_sync(ACU_FULL_MASK, i23, 31);
+    const uint32_t e01 = i01 - p01, e23 = i23 - p23;  // exclusive (no borrow between the fields: each inclusive field >= its own term)
+    const uint32_t tot0 = t01 & 0xffffu, tot1 = t01 >> 16, tot2 = t23 & 0xffffu;
+    uint32_t pre[DG_ITERS];
+    pre[0] = e01 & 0xffffu;
+    pre[1] = tot0 + (e01 >> 16);
+    pre[2] = tot0 + tot1 + (e23 & 0xffffu);
+    pre[3] = tot0 + tot1 + tot2 + (e23 >> 16);
+    const uint32_t run = tot0 + tot1 + tot2 + (t23 >> 16);
     if (lane == 0) s_wtot[wid] = run;
     __syncthreads();
-    int64_t wbase = cta_begin;
-    for (int w = 0; w < wid; ++w) wbase += s_wtot[w];
-    // ---- new offsets (+ first i32 overflow); the lane holding the last row also writes offsets[m] ----
+    const uint32_t wv = lane < DG_WARPS ? s_wtot[lane] : 0u;
+    const uint32_t T = __reduce_add_sync(ACU_FULL_MASK, wv);                      // bytes of this CTA round
+    const uint32_t wbase = __reduce_add_sync(ACU_FULL_MASK, lane < wid ? wv : 0u);  // bytes of the warps before this one
+    // ---- new offsets (32-bit wrapping arithmetic on the truncated base: an overflow is reported, not stored) ----
+    const uint32_t o32 = (uint32_t)cta_begin + wbase;
+    uint32_t *op = reinterpret_cast<uint32_t *>(out_offs) + base + r0;
 #pragma unroll
-    for (int i = DG_ITERS - 1; i >= 0; --i) {
-      const int64_t j = row0 + i * 32 + lane;
-      const int64_t start = wbase + pre[i];
-      if (j < a.m) {
-        if (start + len[i] > limit) err = (unsigned long long)j;
-        out_offs[j] = (int32_t)start;
-        if (j + 1 == a.m) out_offs[a.m] = (int32_t)(start + len[i]);
-      }
+    for (int i = 0; i < DG_ITERS; ++i)
+      if (r0 + i * 32 < rows_here) op[i * 32] = o32 + pre[i];
+    if (cta_begin + T > limit) {  // the first row whose end passes the offset type (take.rs:521 "offset overflow")
+      const int64_t o0 = cta_begin + wbase;
+#pragma unroll
+      for (int i = 0; i < DG_ITERS; ++i)
+        if (r0 + i * 32 < rows_here && o0 + pre[i] + len[i] > limit && (unsigned long long)(base + r0 + i * 32) < err)
+          err = (unsigned long long)(base + r0 + i * 32);
     }
-    // ---- bytes through the ring ----
+    if (base + rows_here == a.m) {  // the last block: the lane holding the last row also writes offsets[m]
+#pragma unroll
+      for (int i = 0; i < DG_ITERS; ++i)
+        if (r0 + i * 32 + 1 == rows_here) reinterpret_cast<uint32_t *>(out_offs)[a.m] = o32 + pre[i] + len[i];
+    }
+    // ---- bytes: rows -> image (predicated RED.OR), image -> global (128-bit stores) ----
     if (out_data != nullptr) {
-      const int64_t own_start = wbase + A;           // first ring position this warp owns in this round of 128 rows
-      int64_t flush_pos = own_start & ~(int64_t)15;  // chunks below are done
+      const uint32_t A = (uint32_t)((uintptr_t)(out_data + cta_begin) & 15);  // the image mirrors the output's 16-byte alignment
 #pragma unroll
       for (int i = 0; i < DG_ITERS; ++i) {
-        if (tot[i] == 0) continue;  // warp-uniform
-        if (len[i]) {
-          const uint4 e = s_tab[key[i]];  // zero beyond the entry's length
-          const int64_t d = wbase + A + pre[i];
-          const uint32_t dsh = (uint32_t)(d & 3) * 8u;
-          const uint32_t wi = (uint32_t)(d >> 2);
-          const uint32_t x0 = e.x << dsh;
-          const uint32_t x1 = __funnelshift_l(e.x, e.y, dsh);
-          const uint32_t x2 = __funnelshift_l(e.y, e.z, dsh);
-          const uint32_t x3 = __funnelshift_l(e.z, e.w, dsh);
-          const uint32_t x4 = __funnelshift_l(e.w, 0u, dsh);
-          if (x0) atomicOr(win + ((wi + 0) & (DG_WINW - 1)), x0);
-          if (x1) atomicOr(win + ((wi + 1) & (DG_WINW - 1)), x1);
-          if (x2) atomicOr(win + ((wi + 2) & (DG_WINW - 1)), x2);
-          if (x3) atomicOr(win + ((wi + 3) & (DG_WINW - 1)), x3);
-          if (x4) atomicOr(win + ((wi + 4) & (DG_WINW - 1)), x4);
-        }
-        __syncwarp();
-        // completed 16-byte chunks of this round: [flush_pos, done)
-        const int64_t round_end = wbase + A + (int64_t)__shfl_sync(ACU_FULL_MASK, pre[i], 0) + tot[i];  // lane 0's prefix = the round's first byte
-        const int64_t done = round_end & ~(int64_t)15;
-        for (int64_t c = flush_pos + (int64_t)lane * 16; c < done; c += 32 * 16) {
-          const uint32_t ci = (uint32_t)(c >> 2) & (DG_WINW - 1);
-          const uint4 q = *reinterpret_cast<const uint4 *>(win + ci);
-          if (c >= own_start) {
-            *reinterpret_cast<uint4 *>(gbase + c) = q;
-          } else {  // the chunk that holds the warp's first byte: only the owned bytes
-            const uint8_t *qb = reinterpret_cast<const uint8_t *>(&q);
-            for (int b = 0; b < 16; ++b)
-              if (c + b >= own_start) gbase[c + b] = qb[b];
-          }
-          *reinterpret_cast<uint4 *>(win + ci) = make_uint4(0, 0, 0, 0);
-        }
-        if (done > flush_pos) flush_pos = done;
-        __syncwarp();
+        const uint4 e = s_tab[key[i]];  // zero beyond the entry's length
+        const uint32_t d = A + wbase + pre[i];
+        const uint32_t dsh = (d & 3u) * 8u;
+        const uint32_t w = img + (d & ~3u);
+        // (ptxas turns a predicated shared-memory RED into branch + BSSY/BSYNC, 5 instructions per word: the first four
+        // words are ORed unconditionally — a zero is harmless — and the fifth, non-zero only for rows longer than 12 bytes
+        // that start off a word boundary, hides behind one warp vote)
+        red_or<0>(w, e.x << dsh);
+        red_or<4>(w, __funnelshift_l(e.x, e.y, dsh));
+        red_or<8>(w, __funnelshift_l(e.y, e.z, dsh));
+        red_or<12>(w, __funnelshift_l(e.z, e.w, dsh));
+        const uint32_t x4 = __funnelshift_l(e.w, 0u, dsh);
+        if (__any_sync(ACU_FULL_MASK, x4 != 0u)) red_or<16>(w, x4);
       }
-      // the warp's last partial chunk (shared with the next warp's first bytes): byte-wise, then re-zeroed
-      const int64_t wend = wbase + A + run;
-      if (flush_pos < wend) {
-        const uint32_t ci = (uint32_t)(flush_pos >> 2) & (DG_WINW - 1);
-        if (lane == 0) {
-          const uint8_t *qb = reinterpret_cast<const uint8_t *>(win + ci);
-          for (int b = 0; b < 16; ++b)
-            if (flush_pos + b >= own_start && flush_pos + b < wend) gbase[flush_pos + b] = qb[b];
+      __syncthreads();
+      const uint32_t end = A + T;
+      const uint32_t chunks = (end + 15u) >> 4;
+      const uint32_t first_full = (A + 15u) >> 4, n_full = (end >> 4) > first_full ? (end >> 4) - first_full : 0u;
+      uint8_t *gb = out_data + cta_begin - A;  // 16-byte aligned
+      for (uint32_t c = threadIdx.x; c < chunks; c += DG_THREADS) {
+        const uint4 q = img4[c];
+        img4[c] = make_uint4(0, 0, 0, 0);
+        if (c - first_full < n_full) {
+          reinterpret_cast<uint4 *>(gb)[c] = q;
+        } else {  // first / last chunk of the round (shared with the neighbouring CTAs' bytes): whole words, then single bytes
+          const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (uint32_t w4 = 0; w4 < 4; ++w4) {
+            const uint32_t lo = (c << 4) + 4u * w4;
+            if (lo >= A && lo + 4u <= end) {
+              *reinterpret_cast<uint32_t *>(gb + lo) = qw[w4];
+            } else {
+#pragma unroll
+              for (uint32_t b = 0; b < 4; ++b)
+                if (lo + b >= A && lo + b < end) gb[lo + b] = (uint8_t)(qw[w4] >> (8u * b));
+            }
+          }
         }
-        __syncwarp();
-        if (lane == 0) *reinterpret_cast<uint4 *>(win + ci) = make_uint4(0, 0, 0, 0);
-        __syncwarp();
       }
     }
-    __syncthreads();  // s_wtot is rewritten by the next round
+    __syncthreads();  // the image is zero again, s_wtot can be rewritten
   }
   if (err != ~0ull) atomicMin(res + RES_ERR2, err);
 }
@@ -764,11 +826,11 @@ acu_status gather_launch(acu_ctx *ctx, int32_t ob, const void *offsets, const ui
     ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // entries longer than 16 bytes: the generic kernels below
     if (!too_long) {
       DictArgs da{static_cast<const uint32_t *>(idx), m, (uint32_t)n_src, reinterpret_cast<const uint32_t *>(out_valid), detect_oob ? 1 : 0, table, lens, flag};
-      const size_t smem1 = (size_t)n_src, smem2 = (size_t)n_src * 17;
+      const size_t smem1 = (size_t)n_src, smem2 = ((size_t)n_src + 1) * 16 + (((size_t)n_src + 16) & ~(size_t)15) + DG_IMG_BYTES;
       ACU_CUDA(ctx, cudaFuncSetAttribute(k_dict_copy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
       int per_sm = 1;
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dict_copy, DG_THREADS, smem2) != cudaSuccess || per_sm < 1) per_sm = 1;
-      const int g1 = acu_grid(ctx, blocks, 4), g2 = acu_grid(ctx, blocks, per_sm);
+      const int g1 = acu_grid(ctx, (blocks + DG_WARPS - 1) / DG_WARPS, 4), g2 = acu_grid(ctx, blocks, per_sm);
       ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_dict_block_totals, g1, DG_THREADS, smem1, da, blocks, block_tot, res);
       ACU_TRY(scan_inclusive(ctx, block_tot, blocks, block_tot + blocks));
       ACU_CUDA(ctx, cudaMemcpyAsync(res + RES_AUX0, block_tot + (blocks - 1), 8, cudaMemcpyDeviceToDevice, ctx->stream));

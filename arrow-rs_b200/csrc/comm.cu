@@ -241,7 +241,7 @@ acu_status acu_aggregate_allreduce(acu_ctx *ctx, acu_dtype dtype, acu_agg_op op,
   *out_valid_count = 0;
   acu_status st = ACU_OK;
   const bool deferred_nc = ctx->async_on && a->len && a->validity && a->null_count < 0;
-  const int64_t nc = deferred_nc ? 1 : (a->len ? acu_resolve_null_count(ctx, a, &st) : 0);
+  const int64_t nc = deferred_nc ? -1 : (a->len ? acu_resolve_null_count(ctx, a, &st) : 0);
   ACU_TRY(st);
   const int64_t valid = deferred_nc ? -1 : a->len - nc;
   void *scratch;

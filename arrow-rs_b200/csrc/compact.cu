@@ -582,177 +582,6 @@ __global__ void __launch_bounds__(256, MINB) k_filter_fused(const FilterBatch ba
   }
 }
 
-// ---- software-pipelined variant of k_filter_fused (ACU_FILTER_PIPE=1: A/B experiment, profiles/r02_filter_ab.md) --------
-// After the instruction diet k_filter_fused is latency-bound (stall_long_sb 31 %, no warp eligible 47 % of the cycles): a
-// warp issues a pass, waits for ALL of it, then consumes with nothing in flight. Here the landing buffer is split in two
-// halves and cp.async groups keep the NEXT sub-pass in flight while the current one is consumed — across tile borders too
-// (the next tile's mask halves live in the other slot of s_h / s_hp).
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <int W, int MINB = 5>
-__global__ void __launch_bounds__(256, MINB) k_filter_fused_pipe(const FilterBatch batch) {
-  const FilterArgs &a = batch.col[blockIdx.y];
-  using C = AsyncCfg<W>;
-  using F = FusedCfg<W>;
-  constexpr int RPC = F::RPC, CPR = F::CPR, RPJ = F::RPJ;
-  constexpr int SUB_ITERS = C::ITERS >= 2 ? C::ITERS / 2 : 1;          // chunk rounds per sub-pass
-  constexpr int SUBS = C::PASSES * (C::ITERS / SUB_ITERS);             // sub-passes per tile (even whenever > 1)
-  constexpr int SUB_ROWS = SUB_ITERS * RPJ;
-  constexpr int SUB_CHUNKS = SUB_ITERS * 32;                            // 16-byte chunks per sub-pass
-  static_assert(SUBS == 1 || SUBS % 2 == 0, "the landing halves must alternate across tile borders");
-  extern __shared__ __align__(16) uint8_t s_raw[];
-  __shared__ uint32_t s_h[8][2][2 * TILE_WORDS];
-  __shared__ uint32_t s_hp[8][2][2 * TILE_WORDS];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int lr = lane * RPC / CPR;
-  const int lr_half = lr >> 5, lr_bit = lr & 31;
-  uint4 *lbuf = reinterpret_cast<uint4 *>(s_raw + (size_t)wid * C::PASS_BYTES) + lane;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const uint8_t *__restrict__ vsrc = a.vsrc;
-  const bool v_aligned = vsrc && (((uintptr_t)vsrc & 7) == 0) && ((a.voff & 63) == 0);
-  unsigned valid_cnt = 0;
-
-  // per-tile setup into slot `s`: mask halves + their popcount prefix
-  auto setup = [&](uint64_t m, int s) {
-    const uint32_t src_lo = __shfl_sync(ACU_FULL_MASK, (uint32_t)m, lane >> 1);
-    const uint32_t src_hi = __shfl_sync(ACU_FULL_MASK, (uint32_t)(m >> 32), lane >> 1);
-    const uint32_t hv = (lane & 1) ? src_hi : src_lo;
-    const uint32_t hc = __popc(hv);
-    uint32_t hincl = hc;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t y = __shfl_up_sync(ACU_FULL_MASK, hincl, o);
-      if (lane >= o) hincl += y;
-    }
-    s_h[wid][s][lane] = hv;
-    s_hp[wid][s][lane] = hincl - hc;
-    __syncwarp();
-  };
-  // issue sub-pass `sp` of tile `t` (mask in slot s) into landing half (sp & 1); returns the packed selection bits
-  auto issue = [&](int64_t t, int sp, int s) -> uint32_t {
-    const uint32_t *hh = &s_h[wid][s][((sp * SUB_ROWS) >> 5) + lr_half];
-    const uint8_t *psrc = a.values + (size_t)t * TILE_ROWS * W + ((size_t)sp * SUB_CHUNKS + lane) * 16;
-    asm volatile("" : "+l"(psrc));
-    uint4 *dstb = lbuf + (SUBS > 1 ? (sp & 1) * SUB_CHUNKS : 0);
-    uint32_t sel = 0;
-#pragma unroll
-    for (int j = 0; j < SUB_ITERS; ++j) {
-      const int r0 = j * RPJ;
-      const uint32_t bits = (hh[r0 >> 5] >> ((r0 & 31) + lr_bit)) & F::CHUNK_MASK;
-      sel |= bits << (j * RPC);
-      if (bits) cp_async16(dstb + j * 32, psrc + (size_t)j * 512);
-    }
-    cp_async_commit();
-    return sel;
-  };
-
-  int64_t t = warp;
-  uint64_t m_cur = 0, off_cur = 0, end_cur = 0;
-  if (t < a.n_tiles) {
-    if (lane < TILE_WORDS) m_cur = __ldg(a.mask + t * TILE_WORDS + lane);
-    off_cur = __ldg(a.tile_off + t);
-    end_cur = __ldg(a.tile_off + t + 1);
-  }
-  int slot = 0;
-  uint32_t sel_cur = 0;
-  if (t < a.n_tiles) { setup(m_cur, 0); sel_cur = issue(t, 0, 0); }
-  for (; t < a.n_tiles; t += nwarps) {
-    const uint64_t m = m_cur, out0 = off_cur;
-    const int64_t tn = t + nwarps;
-    uint64_t m_nx = 0, off_nx = 0, end_nx = 0;
-    if (tn < a.n_tiles) {  // the next tile's mask / offsets (used by the last sub-pass of this tile)
-      m_nx = (lane < TILE_WORDS) ? __ldg(a.mask + tn * TILE_WORDS + lane) : 0ull;
-      off_nx = __ldg(a.tile_off + tn);
-      end_nx = __ldg(a.tile_off + tn + 1);
-    }
-    uint64_t v = 0;
-    if (vsrc && m) {
-      if (v_aligned) v = __ldg(reinterpret_cast<const uint64_t *>(vsrc) + ((a.voff + t * TILE_ROWS) >> 6) + lane);
-      else v = ld_bits64(vsrc, a.voff + t * TILE_ROWS + (int64_t)lane * 64, a.voff + a.vlen);
-    }
-    uint8_t *dst = a.out + (size_t)out0 * W;
-#pragma unroll 1
-    for (int sp = 0; sp < SUBS; ++sp) {
-      // ---- keep the following sub-pass in flight ----
-      uint32_t sel_next = 0;
-      bool issued = false;
-      if (sp + 1 < SUBS) { sel_next = issue(t, sp + 1, slot); issued = true; }
-      else if (tn < a.n_tiles) { setup(m_nx, slot ^ 1); sel_next = issue(tn, 0, slot ^ 1); issued = true; }
-      if (issued) cp_async_wait_group<1>(); else cp_async_wait_group<0>();
-      __syncwarp();
-      // ---- consume sub-pass sp ----
-      const uint32_t *hh = &s_h[wid][slot][((sp * SUB_ROWS) >> 5) + lr_half];
-      const uint32_t *hp = &s_hp[wid][slot][((sp * SUB_ROWS) >> 5) + lr_half];
-      const uint4 *srcb = lbuf + (SUBS > 1 ? (sp & 1) * SUB_CHUNKS : 0);
-#pragma unroll
-      for (int j = 0; j < SUB_ITERS; ++j) {
-        const uint32_t bits = (sel_cur >> (j * RPC)) & F::CHUNK_MASK;
-        const int r0 = j * RPJ;
-        const int sh = (r0 & 31) + lr_bit;
-        const uint32_t rank = hp[r0 >> 5] + __popc(hh[r0 >> 5] & ((1u << sh) - 1u));
-        const uint4 x = srcb[j * 32];
-        if constexpr (W == 8) {
-          uint64_t *o = reinterpret_cast<uint64_t *>(dst) + rank;
-          if (bits & 1u) o[0] = (uint64_t)x.x | ((uint64_t)x.y << 32);
-          if (bits & 2u) o[bits & 1u] = (uint64_t)x.z | ((uint64_t)x.w << 32);
-        } else if constexpr (W == 4) {
-          uint32_t *o = reinterpret_cast<uint32_t *>(dst) + rank;
-          if (bits & 1u) *o++ = x.x;
-          if (bits & 2u) *o++ = x.y;
-          if (bits & 4u) *o++ = x.z;
-          if (bits & 8u) *o = x.w;
-        } else if constexpr (W == 2) {
-          uint16_t *o = reinterpret_cast<uint16_t *>(dst) + rank;
-          const uint16_t *ve = reinterpret_cast<const uint16_t *>(&x);
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-            if ((bits >> e) & 1u) *o++ = ve[e];
-        } else if constexpr (W == 1) {
-          uint8_t *o = dst + rank;
-          const uint8_t *ve = reinterpret_cast<const uint8_t *>(&x);
-#pragma unroll
-          for (int e = 0; e < 16; ++e)
-            if ((bits >> e) & 1u) *o++ = ve[e];
-        } else {
-          if (bits) {
-            const int half = lane % CPR;
-            uint64_t *o = reinterpret_cast<uint64_t *>(dst + (size_t)rank * W + half * 16);
-            o[0] = (uint64_t)x.x | ((uint64_t)x.y << 32);
-            o[1] = (uint64_t)x.z | ((uint64_t)x.w << 32);
-          }
-        }
-      }
-      sel_cur = sel_next;
-      __syncwarp();  // this landing half is refilled two sub-passes later
-    }
-    if (vsrc) {
-      const uint32_t c = __popcll(m);
-      if (c) {
-        const uint64_t bits = pext64_sparse(v, m, c);
-        valid_cnt += __popcll(bits);
-        const uint64_t p = out0 + s_hp[wid][slot][(2 * lane) & 31];
-        const uint32_t sh = (uint32_t)p & 31u;
-        uint32_t *o = a.vout + (p >> 5);
-        const uint32_t w0 = (uint32_t)(bits << sh);
-        const uint64_t rest = sh ? (bits >> (32u - sh)) : (bits >> 32);
-        if (w0) atomicOr(o, w0);
-        if ((uint32_t)rest) atomicOr(o + 1, (uint32_t)rest);
-        if ((uint32_t)(rest >> 32)) atomicOr(o + 2, (uint32_t)(rest >> 32));
-      }
-      __syncwarp();
-    }
-    m_cur = m_nx; off_cur = off_nx; end_cur = end_nx;
-    slot ^= 1;
-  }
-  (void)end_cur;
-  if (vsrc && a.res) {
-    valid_cnt = warp_sum(valid_cnt);
-    if (lane == 0 && valid_cnt) atomicAdd(a.res + RES_COUNT, (unsigned long long)valid_cnt);
-  }
-}
-
 // ---- bit compaction (validity / boolean values): software PEXT --------------------------
 // One lane per mask word; a warp covers 32 consecutive words (two tiles).
 struct CompressArgs {
@@ -872,18 +701,6 @@ acu_status launch_filter(acu_ctx *ctx, const FilterBatch &fb, int n_cols, bool f
       return ACU_OK;
     }
     constexpr size_t smem = 8 * (size_t)AsyncCfg<W>::PASS_BYTES;
-    static const bool pipe = getenv("ACU_FILTER_PIPE") != nullptr;
-    if (pipe) {
-      if (ctx->occupancy.find(reinterpret_cast<const void *>(k_filter_fused_pipe<W>)) == ctx->occupancy.end())
-        ACU_CUDA(ctx, cudaFuncSetAttribute(k_filter_fused_pipe<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      static const int tpw = getenv("ACU_FILTER_TILES_PER_WARP") ? atoi(getenv("ACU_FILTER_TILES_PER_WARP")) : 4;
-      const int64_t want = (fa.n_tiles + 8 * (int64_t)tpw - 1) / (8 * (int64_t)tpw);
-      int gp = acu_wave_grid(ctx, k_filter_fused_pipe<W>, 256, smem, (fa.n_tiles + 7) / 8);
-      gp = (gp + n_cols - 1) / n_cols;
-      if (gp > want) gp = (int)(want < 1 ? 1 : want);
-      ACU_LAUNCH_TIMED(ctx, ACU_K_FILTER, (k_filter_fused_pipe<W>), dim3(gp, n_cols), 256, smem, fb);
-      return ACU_OK;
-    }
     if (ctx->occupancy.find(reinterpret_cast<const void *>(k_filter_fused<W>)) == ctx->occupancy.end())
       ACU_CUDA(ctx, cudaFuncSetAttribute(k_filter_fused<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // every warp should own several tiles (the next tile's mask / offsets are prefetched while the current one is in

@@ -206,7 +206,7 @@ ReduceArgs reduce_args(const acu_array *a, int64_t nc, void *scratch, unsigned l
   ReduceArgs r;
   r.v = a->values;
   r.n = a->len;
-  r.valid = (a->validity && nc > 0) ? a->validity : nullptr;
+  r.valid = (a->validity && nc != 0) ? a->validity : nullptr;  // nc < 0: unknown (counted by the kernel)
   r.voff = a->validity_offset;
   r.partial = scratch;
   r.res = res;
@@ -219,7 +219,8 @@ ReduceArgs reduce_args(const acu_array *a, int64_t nc, void *scratch, unsigned l
 size_t acu_reduce_col_scratch(const acu_ctx *ctx) { return (size_t)ctx->sm_count * 8 * 8 * 16 + 4096; }
 
 // Queue sum / min / max of one column on the ctx stream (no sync). The caller has resolved the
-// null count: nc == len (or len == 0) means None and nothing is launched (*launched = 0). The
+// null count (nc < 0: unknown, the kernel consults the validity and counts): nc == len (or len == 0) means None and
+// nothing is launched (*launched = 0). The
 // result lands in res[RES_AUX0] as the native bit pattern.
 acu_status acu_reduce_col_launch(acu_ctx *ctx, acu_dtype dtype, acu_agg_op op, const acu_array *a, int64_t nc, void *scratch,
                                  unsigned long long *res, int *launched) {
@@ -267,7 +268,7 @@ extern "C" acu_status acu_aggregate(acu_ctx *ctx, acu_dtype dtype, acu_agg_op op
   // inside an async section an unknown null count (the array was produced earlier in the same section) is not resolved by
   // a round trip: the kernel consults the validity and counts the valid rows itself (RES_COUNT)
   const bool deferred_nc = ctx->async_on && a->validity && a->null_count < 0;
-  const int64_t nc = deferred_nc ? 1 : acu_resolve_null_count(ctx, a, &st);
+  const int64_t nc = deferred_nc ? -1 : acu_resolve_null_count(ctx, a, &st);
   ACU_TRY(st);
   if (!deferred_nc) *out_valid_count = a->len - nc;
   void *scratch;

@@ -12,6 +12,17 @@ python -c "
 import json
 d=json.load(open('gpurun_out/r02g_rb_pipe.json'))
 print('rb pipe', round(d['ms_per_step'],2), round(d['kernel_ms_per_step'],2), {k:round(x['ms_per_step'],2) for k,x in d['kernels'].items()})"
+# 1b. stream-ordered sections
+(timeout 900 python -m pytest tests/test_gpu_async.py tests/test_gpu_parity.py -q -m gpu -x) 2>&1 | tail -5
+timeout 600 python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu --no-configs > gpurun_out/r02g_bench_async.json 2> gpurun_out/r02g_bench_async.err
+ACU_BENCH_SYNC=1 timeout 600 python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu --no-configs > gpurun_out/r02g_bench_sync.json 2> gpurun_out/r02g_bench_sync.err
+python - <<'P'
+import json
+for k in ("async","sync"):
+    try:
+        d=json.load(open(f"gpurun_out/r02g_bench_{k}.json")); print(k, d["ms_per_step"], d["value"], d.get("sync_gap_ms_per_step"), d["gpu_launches"], d["check"])
+    except Exception as e: print(k, "failed", e, open(f"gpurun_out/r02g_bench_{k}.err").read()[-800:])
+P
 # 2. dictionary gather: launch list + full set
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02g_dict_launches.csv python tools/opbench.py --only "dict" --reps 1 > /dev/null 2>&1
 python - <<'P'

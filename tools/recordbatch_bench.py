@@ -91,22 +91,34 @@ class Table:
             ctx.free(dh)
             self.batches.append({"cols": cols, "pred": self.arr(dp, None, n, 0), "count": count, "idx": self.arr(d_idx, None, m, 0), "m": m})
         ctx.free(d_keys)
-        cmax = max(b["count"] for b in self.batches)
-        mmax = max(b["m"] for b in self.batches)
-        self.f_out = [self.out(cmax * 8, cmax) for _ in NUMERIC]
-        self.t_out = [self.out(mmax * 8, mmax) for _ in NUMERIC]
-        self.f_str = [(ctx.malloc((cmax + 1) * 4 + 64), ctx.malloc(cmax * 13 + 64), self.out(0, cmax), cmax * 13) for _ in range(2)]
-        self.t_str = [(ctx.malloc((mmax + 1) * 4 + 64), ctx.malloc(mmax * 13 + 64), self.out(0, mmax), mmax * 13) for _ in range(2)]
+        self.cmax = max(b["count"] for b in self.batches)
+        self.mmax = max(b["m"] for b in self.batches)
+        self.lanes = [self.make_lane(ctx)]
+        self.f_out, self.t_out, self.f_str, self.t_str = self.lanes[0]["f_out"], self.lanes[0]["t_out"], self.lanes[0]["f_str"], self.lanes[0]["t_str"]
+
+    def make_lane(self, ctx):
+        """Output buffers of one stream (ctx): batches handled by different lanes are independent (like RecordBatches handed
+        to different executor threads), each lane has its own outputs, result blocks and scratch."""
+        cmax, mmax = self.cmax, self.mmax
+        out = lambda vbytes, rows: self.out(vbytes, rows, ctx)  # noqa: E731
+        return {"ctx": ctx,
+                "f_out": [out(cmax * 8, cmax) for _ in NUMERIC], "t_out": [out(mmax * 8, mmax) for _ in NUMERIC],
+                "f_str": [(ctx.malloc((cmax + 1) * 4 + 64), ctx.malloc(cmax * 13 + 64), out(0, cmax), cmax * 13) for _ in range(2)],
+                "t_str": [(ctx.malloc((mmax + 1) * 4 + 64), ctx.malloc(mmax * 13 + 64), out(0, mmax), mmax * 13) for _ in range(2)]}
+
+    def add_lane(self, ctx):
+        self.lanes.append(self.make_lane(ctx))
 
     def arr(self, values, validity, n, nc):
         a = self.abi.Array()
         a.values, a.values_offset, a.validity, a.validity_offset, a.len, a.null_count, a.is_scalar = values, 0, validity, 0, n, nc, 0
         return a
 
-    def out(self, vbytes, rows):
+    def out(self, vbytes, rows, ctx=None):
+        ctx = ctx or self.ctx
         o = self.abi.ArrayOut()
-        o.values = self.ctx.malloc(vbytes + 64) if vbytes else None
-        o.validity = self.ctx.malloc(self.abi.bitmap_bytes(rows) + 64)
+        o.values = ctx.malloc(vbytes + 64) if vbytes else None
+        o.validity = ctx.malloc(self.abi.bitmap_bytes(rows) + 64)
         return o
 
     def count(self, d_bits, n):
@@ -152,17 +164,16 @@ class Table:
         alg += 6 * (8 * m + m / 8)
         return alg
 
-    def step(self):
-        """One pass over every batch through the RecordBatch-level entry points (one synchronisation per call);
-        returns ([6 partial bit patterns], [6 valid counts], algorithmic bytes)."""
-        ctx, abi = self.ctx, self.abi
+    def run_batches(self, lane, batches, acc):
+        """filter_record_batch -> take_record_batch -> 6 sums for `batches` on one lane (ctx / stream); partials into acc."""
+        ctx, abi = lane["ctx"], self.abi
         lib, h = ctx.lib, ctx.h
-        isum, fsum, cnts, alg = [0, 0, 0], [0.0, 0.0, 0.0], [0] * 6, 0
-        f_outs, t_outs = self.outs_of(self.f_out, self.f_str), self.outs_of(self.t_out, self.t_str)
+        f_outs, t_outs = self.outs_of(lane["f_out"], lane["f_str"]), self.outs_of(lane["t_out"], lane["t_str"])
         dts = (C.c_int32 * 6)(abi.I64, abi.I64, abi.I64, abi.F64, abi.F64, abi.F64)
         ops = (C.c_int32 * 6)(*[abi.SUM] * 6)
         bits, vc = (C.c_uint64 * 6)(), (C.c_int64 * 6)()
-        for bt in self.batches:
+        isum, fsum, cnts = acc["isum"], acc["fsum"], acc["cnts"]
+        for bt in batches:
             n, cnt, m = self.rows, bt["count"], bt["m"]
             if "columns" not in bt:
                 bt["columns"] = self.columns_of(bt["cols"])
@@ -179,7 +190,7 @@ class Table:
             ctx.check(lib.acu_take_record_batch(h, 8, self.columns_of(fcols), C.byref(bt["idx"]), abi.U32, 0, t_outs))
             tin = (abi.Array * 6)(*[self.as_in(t_outs[c].array) for c in range(6)])
             ctx.check(lib.acu_aggregate_columns(h, 6, dts, ops, tin, bits, vc))
-            alg += self.alg_bytes(n, cnt, m, [f_outs[6].data_len, f_outs[7].data_len], [t_outs[6].data_len, t_outs[7].data_len])
+            acc["alg"] += self.alg_bytes(n, cnt, m, [f_outs[6].data_len, f_outs[7].data_len], [t_outs[6].data_len, t_outs[7].data_len])
             for ci in range(6):
                 if vc[ci]:
                     if ci < 3:
@@ -187,7 +198,36 @@ class Table:
                     else:
                         fsum[ci - 3] += np.frombuffer(np.uint64(bits[ci]).tobytes(), dtype=np.float64)[0]
                     cnts[ci] += vc[ci]
-        return self.final_reduce(isum, fsum, cnts, alg)
+
+    def step(self):
+        """One pass over every batch through the RecordBatch-level entry points (one synchronisation per call);
+        returns ([6 partial bit patterns], [6 valid counts], algorithmic bytes). With more than one lane (add_lane) the
+        batches are dealt round-robin to one host thread per lane: the host gaps of one lane (result fetch, descriptor
+        set-up) overlap the kernels of the other. Float64 partials are then summed per lane and across lanes (a different
+        association order than the serial loop: inside the documented Float64-sum tolerance)."""
+        accs = [{"isum": [0, 0, 0], "fsum": [0.0, 0.0, 0.0], "cnts": [0] * 6, "alg": 0} for _ in self.lanes]
+        if len(self.lanes) == 1:
+            self.run_batches(self.lanes[0], self.batches, accs[0])
+        else:
+            import threading
+            errs = []
+
+            def work(k):
+                try:
+                    self.run_batches(self.lanes[k], self.batches[k::len(self.lanes)], accs[k])
+                except BaseException as e:  # noqa: BLE001
+                    errs.append(e)
+            ths = [threading.Thread(target=work, args=(k,)) for k in range(len(self.lanes))]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+            if errs:
+                raise errs[0]
+        isum = [sum(a["isum"][i] for a in accs) & ((1 << 64) - 1) for i in range(3)]
+        fsum = [sum(a["fsum"][i] for a in accs) for i in range(3)]
+        cnts = [sum(a["cnts"][i] for a in accs) for i in range(6)]
+        return self.final_reduce(isum, fsum, cnts, sum(a["alg"] for a in accs))
 
     def final_reduce(self, isum, fsum, cnts, alg):
         # one NCCL all-reduce per dtype group (3 Int64 sums, 3 Float64 sums) after the last batch
@@ -256,6 +296,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--selectivity", type=float, default=0.10)
     ap.add_argument("--nulls", type=float, default=0.05)
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("ACU_RB_STREAMS", "2")),
+                    help="lanes (ctx + stream + host thread) the batches are dealt to; 1 = the serial loop")
     ap.add_argument("--per-column", action="store_true", help="use the single-array entry points (a synchronisation per column)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -270,27 +312,44 @@ def main():
     barrier = group.barrier
 
     tb = Table(ctx, abi, rank, args.batches, args.batch_rows, args.selectivity, args.nulls)
+    extra = [acu.Context(local_rank) for _ in range(max(args.streams, 1) - 1)] if not args.per_column else []
+    for c in extra:
+        tb.add_lane(c)
+    ctxs = [ctx] + extra
     step = tb.step_per_column if args.per_column else tb.step
     for _ in range(args.warmup):
         step()
     barrier()
-    ctx.check(lib.acu_kernel_stats_reset(h))
-    launches0 = ctx.launch_count()
+    for c in ctxs:
+        c.sync()
+        c.check(lib.acu_kernel_stats_reset(c.h))
+    launches0 = sum(c.launch_count() for c in ctxs)
     ms = C.c_float(0)
+    import time
+    t0 = time.perf_counter()
     ctx.check(lib.acu_timer_start_slot(h, 1))
     for _ in range(args.steps):
         sums, cnts, alg = step()
     ctx.check(lib.acu_timer_stop_slot(h, 1, C.byref(ms)))
+    for c in ctxs:
+        c.sync()
+    wall_ms = (time.perf_counter() - t0) * 1e3
     barrier()
-    step_ms = ms.value / args.steps
+    # one lane: CUDA events on its stream; several lanes: host clock around steps that start and end with every stream idle
+    # (each step ends with a synchronising all-reduce on lane 0 after all worker threads have joined)
+    step_ms = (ms.value if len(ctxs) == 1 else wall_ms) / args.steps
     step_ms = group.max_over_ranks(step_ms)
     names = ["arith", "cmp", "cast", "filter", "filter_plan", "take", "reduce", "bytes"]
     kern = {}
     for cls, nm in enumerate(names):
-        tot, cnt = C.c_double(0), C.c_int64(0)
-        ctx.check(lib.acu_kernel_stats(h, cls, C.byref(tot), C.byref(cnt)))
-        if cnt.value:
-            kern[nm] = {"ms_per_step": round(tot.value / args.steps, 4), "launches_per_step": cnt.value / args.steps}
+        tot_ms, tot_n = 0.0, 0
+        for c in ctxs:
+            tot, cnt = C.c_double(0), C.c_int64(0)
+            c.check(lib.acu_kernel_stats(c.h, cls, C.byref(tot), C.byref(cnt)))
+            tot_ms += tot.value
+            tot_n += cnt.value
+        if tot_n:
+            kern[nm] = {"ms_per_step": round(tot_ms / args.steps, 4), "launches_per_step": tot_n / args.steps}
     if rank == 0:
         rows = args.batches * args.batch_rows
         ksum = sum(v["ms_per_step"] for v in kern.values())
@@ -300,11 +359,14 @@ def main():
             "config": {"workload": "RecordBatch{3xInt64,3xFloat64,2xUtf8(D=4096, len 4..12)}", "batches_per_gpu": args.batches, "batch_rows": args.batch_rows,
                        "rows_per_gpu": rows, "selectivity": args.selectivity, "null_density": args.nulls, "take": "monotone half-sample of the filtered rows (UInt32)",
                        "entry_points": "per-column" if args.per_column else "record-batch (one synchronisation per call)",
+                       "streams": len(ctxs), "timer": "CUDA events on the ctx stream" if len(ctxs) == 1 else "host clock around steps bracketed by a synchronisation of every stream",
                        "collective": "2 NCCL all-reduces (3 Int64 + 3 Float64 sums with valid counts) after the last batch"},
             "algorithmic_bytes_per_step": alg, "achieved_gbs": alg / (step_ms * 1e-3) / 1e9, "frac_of_measured_peak": alg / (step_ms * 1e-3) / 1e9 / peak(),
-            "kernel_ms_per_step": round(ksum, 3), "kernels": kern, "gpu_launches": ctx.launch_count() - launches0,
+            "kernel_ms_per_step": round(ksum, 3), "kernels": kern, "gpu_launches": sum(c.launch_count() for c in ctxs) - launches0,
             "check": {"sums_bits": [int(x) for x in sums], "valid_counts": [int(x) for x in cnts]}}))
     group.close()
+    for c in extra:
+        c.close()
 
 
 if __name__ == "__main__":
