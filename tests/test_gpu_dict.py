@@ -62,3 +62,20 @@ def test_dictionary_gather_out_of_bounds_key(gpu, oracle):
     mask[77_777] = False  # under a null key an out-of-bounds value is fine (zero-length slot)
     keys = HostArray.from_numpy(abi.I32, keys_v, mask)
     check(gpu, oracle, offs, data, nulls, keys, "oob under a null key")
+
+
+def test_dictionary_gather_offset_overflow(gpu, oracle):
+    """take.rs:520-523,561-574: the running total passes i32::MAX => Err(OffsetOverflowError(capacity)), here through the
+    dictionary path (2^27 + 1000 keys of 16-byte entries), with the capacity the reference reports (the oracle's)."""
+    d, m = 4, (1 << 27) + 1000
+    offs = (np.arange(d + 1) * 16).astype(np.int32)
+    data = np.full(d * 16 + 16, ord("x"), dtype=np.uint8)
+    nulls = HostArray(acu.U8, np.zeros(0, np.uint8), d, None, 0, 0, 0)
+    keys = HostArray.from_numpy(abi.I32, (np.arange(m, dtype=np.int64) % d).astype(np.int32), None)
+    errs = []
+    for be in (gpu, oracle):
+        with pytest.raises(acu.ArrowError) as e:
+            be.take_bytes(offs, data, nulls, keys)
+        errs.append(e.value)
+    assert errs[0].status == errs[1].status == abi.ERR_OFFSET_OVERFLOW
+    assert str(errs[0]) == str(errs[1])
