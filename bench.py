@@ -767,10 +767,11 @@ def config_subresults(ctx, abi, wl, args, peak, traffic):
             import recordbatch_bench as rbb
             tb = rbb.Table(ctx, abi, 0, 15, 1 << 26, SELECTIVITY, NULL_DENSITY)
             import acu
-            lane2 = acu.Context(ctx.device) if os.environ.get("ACU_RB_STREAMS", "2") != "1" else None
-            if lane2 is not None:  # second lane (ctx + stream + host thread): host gaps of one overlap the kernels of the other
-                tb.add_lane(lane2)
-            lanes = [ctx] + ([lane2] if lane2 is not None else [])
+            # extra lanes (ctx + stream + host thread each): the host gaps of one lane overlap the kernels of the others
+            extra = [acu.Context(ctx.device) for _ in range(max(int(os.environ.get("ACU_RB_STREAMS", "3")), 1) - 1)]
+            for c in extra:
+                tb.add_lane(c)
+            lanes = [ctx] + extra
             for _ in range(2):
                 tb.step()
             for c in lanes:
@@ -794,8 +795,8 @@ def config_subresults(ctx, abi, wl, args, peak, traffic):
                 ksum += ms_c
                 if n_c:
                     kcls[abi.KERNEL_CLASS_NAMES[cls]] = round(ms_c, 3)
-            if lane2 is not None:
-                lane2.close()
+            for c in extra:
+                c.close()
             rows = 15 * (1 << 26)
             out["cfg5"] = {"filter_record_batch -> take_record_batch -> 6 sums": {
                 "rows": rows, "ms_per_step": step_ms, "kernel_ms": ksum, "kernel_ms_by_class": kcls, "algorithmic_bytes": alg, "achieved_gbs": alg / (step_ms * 1e-3) / 1e9,

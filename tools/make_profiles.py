@@ -18,7 +18,8 @@ with open(f"profiles/{rnd}_launches.csv", "w") as f:
     f.write("id,kernel,gpu__time_duration_ns\n")
     for i, k, v in launches:
         f.write(f'{i},"{k}",{v:.0f}\n')
-subprocess.run(f"ncu -i gpurun_out/prof_{rnd}.ncu-rep --page raw --csv > gpurun_out/prof_{rnd}_raw.csv 2>/dev/null", shell=True)
+if os.path.exists(f"gpurun_out/prof_{rnd}.ncu-rep"):
+    subprocess.run(f"ncu -i gpurun_out/prof_{rnd}.ncu-rep --page raw --csv > gpurun_out/prof_{rnd}_raw.csv 2>/dev/null", shell=True)
 raw = list(csv.reader(open(f"gpurun_out/prof_{rnd}_raw.csv")))
 h, units = raw[0], raw[1]
 scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}

@@ -56,7 +56,7 @@ class Bench:
         return d, c.value
 
     def timed(self, name, classes, alg_bytes, rows, fn, note=""):
-        if self.only and self.only not in name:
+        if self.only and not any(t in name for t in self.only.split("|")):
             return
         for _ in range(2):
             fn()
@@ -86,7 +86,7 @@ def main():
     ap.add_argument("--rows", type=int, default=1_000_000_000)
     ap.add_argument("--small-rows", type=int, default=100_000_000)
     ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--only", default=None, help="substring of the op names to run")
+    ap.add_argument("--only", default=None, help="substring of the op names to run (alternatives separated by |)")
     args = ap.parse_args()
     n, ns = args.rows, args.small_rows
     with acu.Context(0) as ctx:

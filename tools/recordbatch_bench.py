@@ -296,7 +296,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--selectivity", type=float, default=0.10)
     ap.add_argument("--nulls", type=float, default=0.05)
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("ACU_RB_STREAMS", "2")),
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("ACU_RB_STREAMS", "3")),
                     help="lanes (ctx + stream + host thread) the batches are dealt to; 1 = the serial loop")
     ap.add_argument("--per-column", action="store_true", help="use the single-array entry points (a synchronisation per column)")
     args = ap.parse_args()
