@@ -890,6 +890,10 @@ acu_status zero_first_offset(acu_ctx *ctx, void *out_offsets, int ob) {
 
 }  // namespace
 
+// In-place inclusive scan of n int64 values on the ctx stream (views.cu); tmp holds >= n / 4096 + n / 4096^2 + 4 values.
+acu_status acu_scan_inclusive_i64(acu_ctx *ctx, int64_t *data, int64_t n, int64_t *tmp) { return scan_inclusive(ctx, data, n, tmp); }
+
+
 extern "C" acu_status acu_filter_plan_indices(acu_ctx *ctx, const acu_filter_plan *plan, acu_dtype index_dtype,
                                               void *out_indices) {
   ACU_ENTER(ctx);

@@ -77,3 +77,6 @@ acu_status acu_reduce_cols_launch(acu_ctx *ctx, int n, const acu_dtype *dtypes, 
 acu_status acu_cmp_result_len(acu_ctx *ctx, const acu_array *l, const acu_array *r, int64_t *out_len);
 acu_status acu_cmp_into_plan(acu_ctx *ctx, acu_dtype dtype, acu_cmp_op op, const acu_array *a, const acu_array *b, uint64_t *mask,
                              int64_t n_words_padded, uint32_t *tile_count, int64_t n_tiles);
+
+// In-place inclusive scan of n int64 values (bytes.cu); tmp: >= n / 4096 + n / 4096^2 + 4 values of scratch.
+acu_status acu_scan_inclusive_i64(acu_ctx *ctx, int64_t *data, int64_t n, int64_t *tmp);

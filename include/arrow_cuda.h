@@ -375,6 +375,29 @@ acu_status acu_cmp_bytes(acu_ctx *ctx, int32_t offset_bytes, acu_cmp_op op, cons
 acu_status acu_cmp_byte_view(acu_ctx *ctx, acu_cmp_op op, const acu_view_array *l, const acu_view_array *r,
                              acu_array_out *out);
 
+/* Utf8View / BinaryView buffer management for BatchCoalescer (InProgressByteViewArray, arrow-select/src/coalesce/
+ * byte_view.rs). The reference decides per source array whether its data buffers are compacted ("gc": when they hold more
+ * than twice the bytes its views use, :366-381) and how output buffers are sized (BufferSource, :526-559); that policy stays
+ * on the host (host/arrow_cuda.hpp, acu/coalesce.py). The per-view work runs on the device:
+ *   acu_view_bytes_used   = GenericByteViewArray::total_buffer_bytes_used (arrow-array/src/array/byte_view_array.rs:749-761):
+ *                           sum of the lengths of the views longer than 12 bytes (null slots included, as in the reference).
+ *   acu_view_fit          = the "copy as many views as fit the current buffer" loop (:259-271): *out_views = leading views
+ *                           that fit `remaining_capacity` (EVERY view's length is compared with what is left, only the long
+ *                           ones consume it — the reference's loop), *out_bytes = bytes of the long views among them.
+ *   acu_view_copy_strings = append_views_and_copy_strings_inner (:298-354): out_views[i] = views[i], every view longer than
+ *                           12 bytes rewritten to {buffer_index = new_buffer_index, offset = position in dst} with its bytes
+ *                           copied to dst[dst_len ...] in view order (null slots too); *out_bytes = bytes appended. `buffers` =
+ *                           HOST array of n_buffers DEVICE pointers (the source's data buffers).
+ *   acu_view_rebase       = append_views_and_update_buffer_index (:176-216): buffer_index += delta for the long views.
+ * views / out_views: 16 bytes per row, 16-byte aligned; out_views may alias views. */
+acu_status acu_view_bytes_used(acu_ctx *ctx, const void *views, int64_t n, int64_t *out_total);
+acu_status acu_view_fit(acu_ctx *ctx, const void *views, int64_t n, int64_t remaining_capacity, int64_t *out_views,
+                        int64_t *out_bytes);
+acu_status acu_view_copy_strings(acu_ctx *ctx, const void *views, int64_t n, const uint8_t *const *buffers,
+                                 int32_t n_buffers, uint32_t new_buffer_index, uint8_t *dst, int64_t dst_len,
+                                 int64_t dst_capacity, void *out_views, int64_t *out_bytes);
+acu_status acu_view_rebase(acu_ctx *ctx, const void *views, int64_t n, uint32_t delta, void *out_views);
+
 /* ------------------------------------------------------------------------- */
 /* cast — arrow-cast/src/cast/mod.rs                                         */
 /* ------------------------------------------------------------------------- */

@@ -1631,4 +1631,75 @@ acu_status orc_concat(int32_t n, const acu_column *cols, acu_column_out *out) {
   return ACU_OK;
 }
 
+
+// ---- Utf8View / BinaryView buffer management of BatchCoalescer (arrow-select/src/coalesce/byte_view.rs) -------------------
+// A view = 16 bytes: length u32 | 12 inline bytes, or length | 4-byte prefix | buffer index u32 | offset u32.
+static inline uint32_t view_len(const uint8_t *views, int64_t i) {
+  uint32_t l;
+  memcpy(&l, views + 16 * i, 4);
+  return l;
+}
+
+// GenericByteViewArray::total_buffer_bytes_used (arrow-array/src/array/byte_view_array.rs:749-761)
+int64_t orc_view_bytes_used(const uint8_t *views, int64_t n) {
+  int64_t total = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const uint32_t len = view_len(views, i);
+    if (len > 12) total += len;
+  }
+  return total;
+}
+
+// the loop of append_views_and_copy_strings that decides how many views still go to the current buffer
+// (coalesce/byte_view.rs:259-271): every view's length is compared with what is left, long views consume it
+void orc_view_fit(const uint8_t *views, int64_t n, int64_t remaining_capacity, int64_t *out_views, int64_t *out_bytes) {
+  int64_t remaining = remaining_capacity, num = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t str_len = view_len(views, i);
+    if (remaining < str_len) break;
+    if (str_len > 12) remaining -= str_len;
+    ++num;
+  }
+  *out_views = num;
+  *out_bytes = remaining_capacity - remaining;
+}
+
+// append_views_and_copy_strings_inner (coalesce/byte_view.rs:298-354): returns the bytes appended to dst
+int64_t orc_view_copy_strings(const uint8_t *views, int64_t n, const uint8_t *const *buffers, uint32_t new_buffer_index, uint8_t *dst,
+                              int64_t dst_len, uint8_t *out_views) {
+  int64_t pos = dst_len;
+  for (int64_t i = 0; i < n; ++i) {
+    uint8_t v[16];
+    memcpy(v, views + 16 * i, 16);
+    const uint32_t len = view_len(views, i);
+    if (len > 12) {
+      uint32_t buffer_index, offset;
+      memcpy(&buffer_index, v + 8, 4);
+      memcpy(&offset, v + 12, 4);
+      const uint32_t new_offset = (uint32_t)pos;  // b.offset = dst_buffer.len() as u32
+      memcpy(v + 8, &new_buffer_index, 4);
+      memcpy(v + 12, &new_offset, 4);
+      memcpy(dst + pos, buffers[buffer_index] + offset, len);
+      pos += len;
+    }
+    memcpy(out_views + 16 * i, v, 16);
+  }
+  return pos - dst_len;
+}
+
+// append_views_and_update_buffer_index (coalesce/byte_view.rs:176-216)
+void orc_view_rebase(const uint8_t *views, int64_t n, uint32_t delta, uint8_t *out_views) {
+  for (int64_t i = 0; i < n; ++i) {
+    uint8_t v[16];
+    memcpy(v, views + 16 * i, 16);
+    if (view_len(views, i) > 12) {
+      uint32_t buffer_index;
+      memcpy(&buffer_index, v + 8, 4);
+      buffer_index += delta;
+      memcpy(v + 8, &buffer_index, 4);
+    }
+    memcpy(out_views + 16 * i, v, 16);
+  }
+}
+
 }  // extern "C"

@@ -50,6 +50,8 @@ class Oracle:
             "orc_cmp_byte_view": [i32, vp, P(vp), i32, P(abi.Array), vp, P(vp), i32, P(abi.Array), P(abi.ArrayOut)],
             "orc_concat": [i32, P(abi.Column), P(abi.ColumnOut)],
             "orc_nullif": [P(abi.Array), P(abi.Array), P(abi.ArrayOut)],
+            "orc_view_fit": [vp, i64, i64, P(i64), P(i64)],
+            "orc_view_rebase": [vp, i64, C.c_uint32, vp],
             "orc_zip": [i32, P(abi.Array), P(abi.Array), P(abi.Array), P(abi.ArrayOut)],
             "orc_generate_values": [i32, u64, i64, u64, vp, i64],
             "orc_generate_bits": [u64, i64, C.c_double, vp, i64],
@@ -388,3 +390,51 @@ class RefBench:
 
     def __exit__(self, *a):
         self.close()
+
+
+class OracleViewBackend:
+    """The per-view work of acu.coalesce_views.InProgressByteViewArray done by the CPU oracle over numpy arrays (the same policy
+    class then yields the reference's layout: views, buffer lengths / capacities, contents)."""
+
+    def __init__(self, oracle):
+        self.lib = oracle.lib
+        self.lib.orc_view_bytes_used.restype = i64
+        self.lib.orc_view_bytes_used.argtypes = [vp, i64]
+        self.lib.orc_view_copy_strings.restype = i64
+        self.lib.orc_view_copy_strings.argtypes = [vp, i64, P(vp), C.c_uint32, vp, i64, vp]
+
+    def upload(self, col):
+        views = np.ascontiguousarray(col.views).reshape(-1).copy()
+        caps = getattr(col, "buffer_capacities", None)
+        bufs = [(np.concatenate([b, np.zeros(16, np.uint8)]), int(b.nbytes), int(caps[i]) if caps else int(b.nbytes)) for i, b in enumerate(col.buffers)]
+        return {"views": views, "n": col.length, "buffers": bufs, "refs": 0}
+
+    def release_source(self, src):
+        pass
+
+    def bytes_used(self, src):
+        return self.lib.orc_view_bytes_used(src["views"].ctypes.data, src["n"])
+
+    def fit(self, src, offset, n, remaining):
+        nv, nb = i64(0), i64(0)
+        self.lib.orc_view_fit(src["views"].ctypes.data + 16 * offset, n, remaining, C.byref(nv), C.byref(nb))
+        return nv.value, nb.value
+
+    def copy_strings(self, src, offset, n, new_index, dst, dst_len, dst_cap, out_views, out_at):
+        table = (vp * max(len(src["buffers"]), 1))(*[b.ctypes.data for b, _, _ in src["buffers"]])
+        nb = self.lib.orc_view_copy_strings(src["views"].ctypes.data + 16 * offset, n, table, new_index, dst.ctypes.data, dst_len,
+                                            out_views.ctypes.data + 16 * out_at)
+        assert dst_len + nb <= dst_cap
+        return nb
+
+    def rebase(self, src, offset, n, delta, out_views, out_at):
+        self.lib.orc_view_rebase(src["views"].ctypes.data + 16 * offset, n, delta, out_views.ctypes.data + 16 * out_at)
+
+    def alloc(self, nbytes):
+        return np.zeros(max(nbytes, 16) + 16, dtype=np.uint8)
+
+    def free(self, p):
+        pass
+
+    def download(self, p, nbytes):
+        return p[:nbytes].copy()
