@@ -775,6 +775,263 @@ __global__ void __launch_bounds__(DG_THREADS, 2) k_dict_copy(const DictArgs a, c
   if (err != ~0ull) atomicMin(res + RES_ERR2, err);
 }
 
+// ---- generic gather, FAST case (i32 offsets, 32-bit indices), round 2 ------------------------------------------------------
+// The dictionary kernel's recipe applied to an arbitrary source: lane = row mod 32 (16 warps x 4 x 32 rows per 2048-row CTA
+// round), packed 16-bit scans, 32-bit positions, a zeroed 32-KB shared-memory image of the round's output filled by funnel
+// shifts + RED.OR and written back as 128-bit stores. What differs is where a row's bytes come from — two scattered offset
+// loads, then up to 16 bytes by three predicated aligned 8-byte loads (rows longer than 16 bytes loop in 16-byte pieces) —
+// and that those loads are software-pipelined over THREE rounds (indices of round r + 2, offsets of round r + 1, bytes of
+// round r in flight together), because a round is one dependent chain of three DRAM round trips. A block whose bytes do
+// not fit the image (T > 32 KB, i.e. rows averaging more than 16 bytes) takes a slow direct-copy path in the same kernel.
+#define GC_IMG_BYTES (BY_ROWS * 16)
+
+__device__ __forceinline__ uint32_t gather_rows_here(const BytesArgs &a, int64_t blk) {
+  const int64_t left = a.m - blk * BY_ROWS;
+  return left < BY_ROWS ? (uint32_t)left : (uint32_t)BY_ROWS;
+}
+
+// stage 1 (two rounds ahead): this lane's four indices + the validity words of the warp's four 32-row groups (lane i < 4;
+// all ones without a bitmap, 0 past the end)
+__device__ __forceinline__ void gather_load_idx(const BytesArgs &a, int64_t blk, uint32_t idx[DG_ITERS], uint32_t &vw) {
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t base = blk * BY_ROWS;
+  const uint32_t rows_here = gather_rows_here(a, blk);
+  const uint32_t r0 = wid * DG_WROWS + lane;
+  const uint32_t *ip = static_cast<const uint32_t *>(a.idx) + base + r0;
+#pragma unroll
+  for (int i = 0; i < DG_ITERS; ++i) idx[i] = (r0 + i * 32 < rows_here) ? __ldg(ip + i * 32) : 0u;
+  vw = 0xffffffffu;
+  if (a.out_valid) vw = (lane < DG_ITERS && wid * DG_WROWS + lane * 32 < rows_here) ? __ldg(a.out_valid + (base >> 5) + wid * DG_ITERS + lane) : 0u;
+}
+
+// stage 2 (one round ahead): source byte range of this lane's four rows (0 / 0 for rows past the end, null slots and
+// out-of-bounds indices) + the block's first output byte and its byte count (saturated to 32 bits)
+__device__ __forceinline__ void gather_load_offsets(const BytesArgs &a, const int64_t *__restrict__ block_incl, int64_t blk, const uint32_t idx[DG_ITERS],
+                                                    uint32_t vw_lanes, int32_t s[DG_ITERS], int32_t e[DG_ITERS], int64_t &cta_begin, uint32_t &T32) {
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t r0 = wid * DG_WROWS + lane;
+  const uint32_t rows_here = gather_rows_here(a, blk);
+  const bool all_in = a.n_src > (int64_t)0xffffffffll;
+  const uint32_t n32 = all_in ? 0xffffffffu : (uint32_t)a.n_src;
+  const int32_t *offs = static_cast<const int32_t *>(a.offs);
+#pragma unroll
+  for (int i = 0; i < DG_ITERS; ++i) {
+    const uint32_t vw = __shfl_sync(ACU_FULL_MASK, vw_lanes, i);
+    const bool use = (r0 + i * 32 < rows_here) && ((vw >> lane) & 1u) && (all_in || idx[i] < n32);  // OOB: reported by pass 1
+    s[i] = 0;
+    e[i] = 0;
+    if (use) {
+      s[i] = __ldg(offs + idx[i]);
+      e[i] = __ldg(offs + idx[i] + 1);
+    }
+  }
+  cta_begin = blk ? __ldg(block_incl + blk - 1) : 0;
+  const int64_t t = __ldg(block_incl + blk) - cta_begin;
+  T32 = t > (int64_t)0xffffffffll ? 0xffffffffu : (uint32_t)t;
+}
+
+__global__ void __launch_bounds__(DG_THREADS, 2) k_gather_copy(const BytesArgs a, const int64_t *__restrict__ block_incl, int64_t blocks,
+                                                               int32_t *__restrict__ out_offs, uint8_t *__restrict__ out_data, int64_t limit,
+                                                               unsigned long long *res, const int64_t *__restrict__ total_ptr, int64_t out_cap) {
+  extern __shared__ __align__(16) uint8_t s_dyn[];
+  __shared__ uint32_t s_wtot[DG_WARPS];
+  __shared__ unsigned long long s_wtot64[DG_WARPS];
+  if (out_data != nullptr && total_ptr != nullptr) {  // decided on the device: no host round trip between the passes
+    const int64_t total = __ldg(total_ptr);
+    if (total > out_cap || total > limit) out_data = nullptr;
+  }
+  uint32_t *s_img = reinterpret_cast<uint32_t *>(s_dyn);
+  uint4 *img4 = reinterpret_cast<uint4 *>(s_dyn);
+  for (uint32_t i = threadIdx.x; i < (GC_IMG_BYTES + 32) / 16; i += DG_THREADS) img4[i] = make_uint4(0, 0, 0, 0);
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t r0 = wid * DG_WROWS + lane;
+  const uint32_t img = (uint32_t)__cvta_generic_to_shared(s_img);
+  const uint8_t *__restrict__ data = a.data;
+  unsigned long long err = ~0ull;
+  // pipeline state: (s, e, first output byte, byte count) of the current round, (indices, validity words) of the next one
+  int32_t s[DG_ITERS], e[DG_ITERS];
+  uint32_t idx_n[DG_ITERS], vw_n = 0, T_c = 0;
+  int64_t begin_c = 0;
+  const int64_t stride = gridDim.x;
+  int64_t blk = blockIdx.x;
+  if (blk < blocks) {
+    uint32_t idx0[DG_ITERS], vw0;
+    gather_load_idx(a, blk, idx0, vw0);
+    gather_load_offsets(a, block_incl, blk, idx0, vw0, s, e, begin_c, T_c);
+    if (blk + stride < blocks) gather_load_idx(a, blk + stride, idx_n, vw_n);
+  }
+  __syncthreads();
+  for (; blk < blocks; blk += stride) {
+    const int64_t base = blk * BY_ROWS;
+    const uint32_t rows_here = gather_rows_here(a, blk);
+    const int64_t cta_begin = begin_c;
+    const uint32_t Tblk = T_c;
+    uint32_t len[DG_ITERS];
+    int32_t sc[DG_ITERS];
+#pragma unroll
+    for (int i = 0; i < DG_ITERS; ++i) {
+      sc[i] = s[i];
+      len[i] = (uint32_t)(e[i] - s[i]);
+    }
+    // next round's offsets (its indices arrived during the previous round) and the round after's indices
+    if (blk + stride < blocks) {
+      gather_load_offsets(a, block_incl, blk + stride, idx_n, vw_n, s, e, begin_c, T_c);
+      if (blk + 2 * stride < blocks) gather_load_idx(a, blk + 2 * stride, idx_n, vw_n);
+    }
+    if (Tblk <= (uint32_t)GC_IMG_BYTES) {
+      // ---- the first 16 bytes of every row: three predicated aligned 8-byte loads each, all issued before the scan ----
+      uint64_t w[DG_ITERS][3];
+      uint32_t sh[DG_ITERS];
+      if (out_data != nullptr) {
+#pragma unroll
+        for (int i = 0; i < DG_ITERS; ++i) {
+          const uintptr_t addr = (uintptr_t)data + (uintptr_t)(int64_t)sc[i];
+          const uint64_t *p = reinterpret_cast<const uint64_t *>(addr & ~(uintptr_t)7);
+          const uint32_t l16 = len[i] > 16u ? 16u : len[i];
+          sh[i] = (uint32_t)(addr & 7u) * 8u;
+          const uint32_t bits = sh[i] + l16 * 8u;
+          w[i][0] = l16 ? __ldg(p) : 0ull;
+          w[i][1] = bits > 64u ? __ldg(p + 1) : 0ull;
+          w[i][2] = bits > 128u ? __ldg(p + 2) : 0ull;
+        }
+      }
+      // four inclusive 32-row scans as two packed 16-bit scans (T <= 32 KB: every partial sum fits 16 bits)
+      const uint32_t p01 = len[0] | (len[1] << 16), p23 = len[2] | (len[3] << 16);
+      uint32_t i01 = p01, i23 = p23;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y01 = __shfl_up_sync(ACU_FULL_MASK, i01, o), y23 = __shfl_up_sync(ACU_FULL_MASK, i23, o);
+        if (lane >= (uint32_t)o) { i01 += y01; i23 += y23; }
+      }
+      const uint32_t t01 = __shfl_sync(ACU_FULL_MASK, i01, 31), t23 = __shfl_sync(ACU_FULL_MASK, i23, 31);
+      const uint32_t e01 = i01 - p01, e23 = i23 - p23;
+      const uint32_t tot0 = t01 & 0xffffu, tot1 = t01 >> 16, tot2 = t23 & 0xffffu;
+      uint32_t pre[DG_ITERS];
+      pre[0] = e01 & 0xffffu;
+      pre[1] = tot0 + (e01 >> 16);
+      pre[2] = tot0 + tot1 + (e23 & 0xffffu);
+      pre[3] = tot0 + tot1 + tot2 + (e23 >> 16);
+      if (lane == 0) s_wtot[wid] = tot0 + tot1 + tot2 + (t23 >> 16);
+      __syncthreads();
+      const uint32_t wv = lane < DG_WARPS ? s_wtot[lane] : 0u;
+      const uint32_t T = Tblk;
+      const uint32_t wbase = __reduce_add_sync(ACU_FULL_MASK, lane < wid ? wv : 0u);
+      // ---- new offsets ----
+      const uint32_t o32 = (uint32_t)cta_begin + wbase;
+      uint32_t *op = reinterpret_cast<uint32_t *>(out_offs) + base + r0;
+#pragma unroll
+      for (int i = 0; i < DG_ITERS; ++i)
+        if (r0 + i * 32 < rows_here) op[i * 32] = o32 + pre[i];
+      if (cta_begin + T > limit) {
+        const int64_t o0 = cta_begin + wbase;
+#pragma unroll
+        for (int i = 0; i < DG_ITERS; ++i)
+          if (r0 + i * 32 < rows_here && o0 + pre[i] + len[i] > limit && (unsigned long long)(base + r0 + i * 32) < err)
+            err = (unsigned long long)(base + r0 + i * 32);
+      }
+      if (base + rows_here == a.m) {
+#pragma unroll
+        for (int i = 0; i < DG_ITERS; ++i)
+          if (r0 + i * 32 + 1 == rows_here) reinterpret_cast<uint32_t *>(out_offs)[a.m] = o32 + pre[i] + len[i];
+      }
+      if (out_data != nullptr) {
+        const uint32_t A = (uint32_t)((uintptr_t)(out_data + cta_begin) & 15);
+#pragma unroll
+        for (int i = 0; i < DG_ITERS; ++i) {
+          const uint32_t l16 = len[i] > 16u ? 16u : len[i];
+          // 16 source bytes from the three aligned words, zero beyond the row
+          uint64_t lo = (w[i][0] >> sh[i]) | ((w[i][1] << 1) << (63u - sh[i]));
+          uint64_t hi = (w[i][1] >> sh[i]) | ((w[i][2] << 1) << (63u - sh[i]));
+          const uint32_t n0 = l16 < 8u ? l16 : 8u, n1 = l16 - n0;
+          lo &= n0 >= 8u ? ~0ull : ((1ull << (n0 * 8u)) - 1ull);
+          hi &= n1 >= 8u ? ~0ull : ((1ull << (n1 * 8u)) - 1ull);
+          const uint32_t ex = (uint32_t)lo, ey = (uint32_t)(lo >> 32), ez = (uint32_t)hi, ew = (uint32_t)(hi >> 32);
+          const uint32_t d = A + wbase + pre[i];
+          const uint32_t dsh = (d & 3u) * 8u;
+          const uint32_t wa = img + (d & ~3u);
+          red_or<0>(wa, ex << dsh);
+          red_or<4>(wa, __funnelshift_l(ex, ey, dsh));
+          red_or<8>(wa, __funnelshift_l(ey, ez, dsh));
+          const uint32_t x3 = __funnelshift_l(ez, ew, dsh), x4 = __funnelshift_l(ew, 0u, dsh);
+          if (__any_sync(ACU_FULL_MASK, (x3 | x4) != 0u)) {
+            red_or<12>(wa, x3);
+            red_or<16>(wa, x4);
+          }
+          // the rest of a long row, 8 bytes at a time
+          for (uint32_t c = 16; c < len[i]; c += 8) {
+            const uint32_t nb = len[i] - c < 8u ? len[i] - c : 8u;
+            const uint64_t v = load_upto8(data, (int64_t)sc[i] + c, nb);
+            const uint32_t dd = d + c;
+            const uint32_t ds2 = (dd & 3u) * 8u;
+            const uint32_t w2 = img + (dd & ~3u);
+            const uint32_t vx = (uint32_t)v, vy = (uint32_t)(v >> 32);
+            red_or<0>(w2, vx << ds2);
+            red_or<4>(w2, __funnelshift_l(vx, vy, ds2));
+            red_or<8>(w2, __funnelshift_l(vy, 0u, ds2));
+          }
+        }
+        __syncthreads();
+        const uint32_t end = A + T;
+        const uint32_t chunks = (end + 15u) >> 4;
+        const uint32_t first_full = (A + 15u) >> 4, n_full = (end >> 4) > first_full ? (end >> 4) - first_full : 0u;
+        uint8_t *gb = out_data + cta_begin - A;
+        for (uint32_t c = threadIdx.x; c < chunks; c += DG_THREADS) {
+          const uint4 q = img4[c];
+          img4[c] = make_uint4(0, 0, 0, 0);
+          if (c - first_full < n_full) {
+            reinterpret_cast<uint4 *>(gb)[c] = q;
+          } else {
+            const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (uint32_t w4 = 0; w4 < 4; ++w4) {
+              const uint32_t lo4 = (c << 4) + 4u * w4;
+              if (lo4 >= A && lo4 + 4u <= end) {
+                *reinterpret_cast<uint32_t *>(gb + lo4) = qw[w4];
+              } else {
+#pragma unroll
+                for (uint32_t b = 0; b < 4; ++b)
+                  if (lo4 + b >= A && lo4 + b < end) gb[lo4 + b] = (uint8_t)(qw[w4] >> (8u * b));
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();
+    } else {
+      // ---- a block of long rows: 64-bit scans, direct copies (correct for any length; rows average > 16 bytes here) ----
+      unsigned long long pre64[DG_ITERS], run = 0;
+#pragma unroll
+      for (int i = 0; i < DG_ITERS; ++i) {
+        unsigned long long inc = len[i];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned long long y = __shfl_up_sync(ACU_FULL_MASK, inc, o);
+          if (lane >= (uint32_t)o) inc += y;
+        }
+        pre64[i] = run + inc - len[i];
+        run += __shfl_sync(ACU_FULL_MASK, inc, 31);
+      }
+      if (lane == 0) s_wtot64[wid] = run;
+      __syncthreads();
+      unsigned long long wbase = 0;
+      for (uint32_t w2 = 0; w2 < wid; ++w2) wbase += s_wtot64[w2];
+      const int64_t o0 = cta_begin + (int64_t)wbase;
+#pragma unroll
+      for (int i = 0; i < DG_ITERS; ++i) {
+        if (r0 + i * 32 < rows_here) {
+          const int64_t start = o0 + (int64_t)pre64[i];
+          out_offs[base + r0 + i * 32] = (int32_t)start;
+          if (start + (int64_t)len[i] > limit && (unsigned long long)(base + r0 + i * 32) < err) err = (unsigned long long)(base + r0 + i * 32);
+          if (r0 + i * 32 + 1 == rows_here && base + rows_here == a.m) out_offs[a.m] = (int32_t)(start + (int64_t)len[i]);
+          if (out_data != nullptr && len[i]) copy_row_direct<false>(out_data + start, data, (int64_t)sc[i], (uint64_t)len[i]);
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (err != ~0ull) atomicMin(res + RES_ERR2, err);
+}
+
 // lengths -> CTA totals -> scan -> offsets (+ byte copy when out_data != NULL and it fits), queued
 // on the ctx stream without synchronising; gather_finalize reads the fetched result block:
 // RES_ERR_INDEX = lowest out-of-bounds row (detect_oob), RES_AUX0 = total value bytes,
@@ -846,7 +1103,15 @@ acu_status gather_launch(acu_ctx *ctx, int32_t ob, const void *offsets, const ui
   ACU_CUDA(ctx, cudaMemcpyAsync(res + RES_AUX0, block_tot + (blocks - 1), 8, cudaMemcpyDeviceToDevice, ctx->stream));
   const int stage_cap = BY_STAGE_CAP;
   a.detect_oob = 0;
-  if (fast) {
+  static const bool generic_v1 = getenv("ACU_BYTES_GENERIC_V1") != nullptr;  // A/B: the round-1 copy kernel
+  if (fast && !generic_v1 && ((uintptr_t)out_offsets % 4 == 0)) {
+    const size_t smem = GC_IMG_BYTES + 32;
+    ACU_CUDA(ctx, cudaFuncSetAttribute(k_gather_copy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gather_copy, DG_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_gather_copy, acu_grid(ctx, blocks, per_sm), DG_THREADS, smem, a, block_tot, blocks, static_cast<int32_t *>(out_offsets),
+                     out_data, gs->limit, res, block_tot + (blocks - 1), out_cap);
+  } else if (fast) {
     ACU_CUDA(ctx, cudaFuncSetAttribute(k_bytes_offsets_copy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_cap));
     ACU_LAUNCH_TIMED(ctx, ACU_K_BYTES, k_bytes_offsets_copy<true>, (unsigned)blocks, BY_THREADS, stage_cap, a, block_tot, (int64_t)0, out_offsets,
                      out_data, gs->limit, (int64_t)-1, res, stage_cap, block_tot + (blocks - 1), out_cap);

@@ -261,7 +261,7 @@ def test_bytes_long_and_mixed_rows(gpu, oracle):
     """Rows longer than the 16-byte fast window, CTAs whose output exceeds the shared-memory staging
     buffer (direct-store path), empty rows, and i64 offsets (LargeUtf8) + every index width."""
     rng = np.random.default_rng(14)
-    for n, max_len, odt in [(5000, 200, np.int32), (3000, 40, np.int64), (6000, 17, np.int32), (2500, 1, np.int32)]:
+    for n, max_len, odt in [(5000, 200, np.int32), (3000, 40, np.int64), (6000, 17, np.int32), (2500, 1, np.int32), (9000, 30, np.int32), (4100, 48, np.int32)]:
         lens = rng.integers(0, max_len + 1, n)
         lens[rng.random(n) < 0.2] = 0
         offsets = np.zeros(n + 1, dtype=odt)
@@ -280,6 +280,31 @@ def test_bytes_long_and_mixed_rows(gpu, oracle):
                 idx = HostArray.from_numpy(idt, rng.integers(0, hi, m).astype(acu.NP_DTYPES[idt]), rng.random(m) >= 0.1)
                 assert_same_bytes(gpu.take_bytes(offsets, data, nulls, idx), oracle.take_bytes(offsets, data, nulls, idx),
                                   f"take_bytes long n={n} max_len={max_len} idx={idt}")
+
+
+def test_bytes_many_blocks(gpu, oracle):
+    """More 2048-row blocks than resident CTAs: the persistent copy kernel's three-stage load pipeline (indices two rounds
+    ahead, offsets one round ahead) runs over several rounds per CTA, with blocks of short rows (shared-memory image path),
+    blocks of long rows (direct path) and a ragged last block in the same launch."""
+    rng = np.random.default_rng(16)
+    n = 300_000
+    lens = rng.integers(0, 25, n)
+    lens[100_000:120_000] = rng.integers(30, 90, 20_000)  # a region of long rows
+    offsets = np.zeros(n + 1, dtype=np.int32)
+    offsets[1:] = np.cumsum(lens)
+    data = rng.integers(0, 256, int(offsets[-1]) + 16).astype(np.uint8)
+    mask = rng.random(n) >= 0.1
+    nulls = HostArray(abi.U8, np.zeros(0, np.uint8), n, acu.pack_bits(mask), 0, 0, int(n - mask.sum()))
+    m = 1_400_003
+    iv = np.sort(rng.integers(0, n, m)).astype(np.uint32)  # monotone (filter-like) first half, random second half
+    iv[m // 2:] = rng.integers(0, n, m - m // 2).astype(np.uint32)
+    idx = HostArray.from_numpy(abi.U32, iv, rng.random(m) >= 0.05)
+    assert_same_bytes(gpu.take_bytes(offsets, data, nulls, idx), oracle.take_bytes(offsets, data, nulls, idx), "take_bytes 1.4M rows")
+    pred = rand_bool(rng, n, 0.7, None)
+    big_o, big_d, big_n = gpu.take_bytes(offsets, data, nulls, idx)
+    pred2 = rand_bool(rng, m, 0.6, 0.02)
+    assert_same_bytes(gpu.filter_bytes(big_o, big_d, big_n, pred2), oracle.filter_bytes(big_o, big_d, big_n, pred2), "filter_bytes 1.4M rows")
+    assert_same_bytes(gpu.filter_bytes(offsets, data, nulls, pred), oracle.filter_bytes(offsets, data, nulls, pred), "filter_bytes 300k rows")
 
 
 def test_dictionary_filter_take_on_keys(gpu, oracle):

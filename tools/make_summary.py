@@ -27,9 +27,13 @@ bench = json.load(open(f"{P}/{rnd}_bench_n1.json"))
 w(f"# Round {rnd[1:].lstrip('0')} profile summary (B200, 1e9-row step: filter -> take -> add -> sum)\n")
 w("Commands (under `gpurun`, one GPU):\n")
 w("```")
-w(f"ncu --metrics gpu__time_duration.sum --clock-control none -c 150 --csv --log-file gpurun_out/launches_{rnd}.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu")
-w(f'ncu --set full --clock-control none --import-source on -k regex:"k_arith|k_take|k_filter_values|k_compress_bits|k_reduce|k_plan_mask" -s 24 -c 6 -o gpurun_out/prof_{rnd} python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu')
+w(f"bash tools/gpu_profiles.sh {rnd}      # the whole capture; its ncu passes:")
+w(f"ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_{rnd}.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-configs")
+w(f'ncu --set full --clock-control none --import-source on -k regex:"k_arith|k_take|k_filter_fused|k_reduce|k_plan_mask" -s 20 -c 8 -o gpurun_out/prof_{rnd} python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-configs')
+w(f"ncu -i gpurun_out/prof_{rnd}.ncu-rep --page details > {P}/{rnd}_ncu_details.txt    # committed; --page raw --csv -> {rnd}_fullset.csv / {rnd}_traffic.json")
+w(f'ncu --set full --clock-control none -k regex:"k_dict_copy|k_dict_block_totals|k_cmp_v2|k_cast_v2" -c 6 python tools/opbench.py --only "dict|lt f64|cast i64" --reps 1   # -> {rnd}_ncu_details_ops.txt')
 w("python bench.py                      # the bench line itself is never taken under ncu")
+w("python bench.py --impl reference     # the CPU arm (oracle/refbench.cpp on all host cores)")
 w("python tools/opbench.py              # per-op table (configs 2-4)")
 w("python tools/recordbatch_bench.py    # config 5 (under torchrun for N > 1)")
 w("```\n")
@@ -37,8 +41,14 @@ w("```\n")
 # ---- 1. launch list ----
 rows = list(csv.DictReader(open(f"{P}/{rnd}_launches.csv")))
 # the last complete step = the last launches between two k_plan_mask occurrences
-idx = [i for i, r in enumerate(rows) if "k_plan_mask" in r["kernel"]]
-step = rows[idx[-2]:idx[-1]] if len(idx) >= 2 else rows
+idx = [i for i, r in enumerate(rows) if "k_plan_mask" in r["kernel"]] + [len(rows)]
+segs = [rows[a:b] for a, b in zip(idx[:-1], idx[1:])]
+segs = [g for g in segs if any("k_arith" in r["kernel"] for r in g) and any("k_reduce" in r["kernel"] for r in g)]
+step = segs[-2] if len(segs) >= 2 else (segs[-1] if segs else rows)
+# (cut the segment after the step's reduction + result-block reset: what follows belongs to later calls)
+ia = max(i for i, r in enumerate(step) if "k_arith" in r["kernel"])
+last = min(i for i, r in enumerate(step) if i > ia and "k_reduce" in r["kernel"])
+step = step[:last + 2] if last + 1 < len(step) and "k_res_reset" in step[last + 1]["kernel"] else step[:last + 1]
 agg = {}
 for r in step:
     k = short(r["kernel"])
@@ -46,7 +56,8 @@ for r in step:
     a[0] += 1
     a[1] += float(r["gpu__time_duration_ns"]) / 1e6
 tot = sum(v[1] for v in agg.values())
-cls_of = {"k_arith": "arith", "k_filter_values": "filter", "k_compress_bits": "filter", "k_zero_outputs": None, "k_take": "take", "k_reduce": "reduce", "k_plan": "filter_plan"}
+cls_of = {"k_arith": "arith", "k_filter_fused": "filter", "k_filter_values": "filter", "k_compress_bits": "filter", "k_zero_outputs": None, "k_zero_bitmap_dev": None,
+          "k_take": "take", "k_reduce": "reduce", "k_plan": "filter_plan"}
 w("## 1. Launch list of one step (ncu per-launch times: cold-cache, serialised — compare SHARES)\n")
 w("| kernel | launches | ncu time (ms) | share of step (ncu) | share of step (bench.py CUDA events, per kernel class) |")
 w("|---|---|---|---|---|")
