@@ -208,6 +208,16 @@ extern "C" {
     pub fn acu_ipc_stream_next(ctx: *mut acu_ctx, s: *mut acu_ipc_stream, out_columns: *mut acu_column, out_rows: *mut i64) -> acu_status;
     pub fn acu_ipc_stream_close(ctx: *mut acu_ctx, s: *mut acu_ipc_stream);
     pub fn acu_aggregate_allreduce(ctx: *mut acu_ctx, dtype: i32, op: i32, a: *const acu_array, out_bits: *mut u64, out_valid: *mut i64) -> acu_status;
+    // stream-ordered sections (include/arrow_cuda.h): the entry points listed there only enqueue between the two calls
+    pub fn acu_async_begin(ctx: *mut acu_ctx) -> acu_status;
+    pub fn acu_results_fetch(ctx: *mut acu_ctx) -> acu_status;
+    pub fn acu_async_active(ctx: *const acu_ctx) -> i32;
+    // Utf8View / BinaryView buffer management of BatchCoalescer (arrow-select/src/coalesce/byte_view.rs)
+    pub fn acu_view_bytes_used(ctx: *mut acu_ctx, views: *const c_void, n: i64, out_total: *mut i64) -> acu_status;
+    pub fn acu_view_fit(ctx: *mut acu_ctx, views: *const c_void, n: i64, remaining_capacity: i64, out_views: *mut i64, out_bytes: *mut i64) -> acu_status;
+    pub fn acu_view_copy_strings(ctx: *mut acu_ctx, views: *const c_void, n: i64, buffers: *const *const u8, n_buffers: i32, new_buffer_index: u32,
+                                 dst: *mut u8, dst_len: i64, dst_capacity: i64, out_views: *mut c_void, out_bytes: *mut i64) -> acu_status;
+    pub fn acu_view_rebase(ctx: *mut acu_ctx, views: *const c_void, n: i64, delta: u32, out_views: *mut c_void) -> acu_status;
     pub fn acu_comm_get_unique_id(out_id: *mut u8) -> acu_status;
     pub fn acu_comm_init(ctx: *mut acu_ctx, id: *const u8, rank: i32, world: i32) -> acu_status;
     pub fn acu_comm_destroy(ctx: *mut acu_ctx) -> acu_status;
