@@ -21,6 +21,27 @@ import json
 import os
 import subprocess
 import sys
+
+# The contract is ONE JSON line on stdout. Libraries loaded later (NCCL prints "NCCL version ..." when NCCL_DEBUG is set)
+# write to file descriptor 1 directly, so the real stdout is set aside and fd 1 is pointed at stderr for everything else.
+_REAL_STDOUT = None
+
+
+def isolate_stdout():
+    """Called by main() only (importing this module must not touch the importer's stdout)."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(text):
+    if _REAL_STDOUT is None:
+        print(text, flush=True)
+    else:
+        os.write(_REAL_STDOUT, (text + "\n").encode())
+
 import threading
 import time
 
@@ -692,11 +713,11 @@ def run_gpu(args):
         line["check_vs_oracle"] = bool(ok)
         line["check"]["vs_oracle"] = {"equal": bool(ok), "rows": base["rows"], "compared": keys, "mismatch": {k: [str(a), str(b)] for k, (a, b) in bad.items()}}
         if not ok:
-            print(json.dumps(line))
+            emit_line(json.dumps(line))
             raise SystemExit("bench.py: GPU outputs differ from the oracle's: " + json.dumps(line["check"]["vs_oracle"]))
     if not args.no_configs and world == 1:
         line["configs"] = config_subresults(ctx, abi, wl, args, peak, traffic)
-    print(json.dumps(line))
+    emit_line(json.dumps(line))
     group.close()
     ctx.close()
 
@@ -938,10 +959,11 @@ def run_reference(args):
         "check": chk,
         "e2e": {"value": value, "unit": "Mrows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit_line(json.dumps(line))
 
 
 def main():
+    isolate_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

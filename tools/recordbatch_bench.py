@@ -20,6 +20,27 @@ import json
 import os
 import sys
 
+# The contract is ONE JSON line on stdout. Libraries loaded later (NCCL prints "NCCL version ..." when NCCL_DEBUG is set)
+# write to file descriptor 1 directly, so the real stdout is set aside and fd 1 is pointed at stderr for everything else.
+_REAL_STDOUT = None
+
+
+def isolate_stdout():
+    """Called by main() only (importing this module must not touch the importer's stdout)."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(text):
+    if _REAL_STDOUT is None:
+        print(text, flush=True)
+    else:
+        os.write(_REAL_STDOUT, (text + "\n").encode())
+
+
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(REPO, "arrow-rs_b200"))
 import numpy as np  # noqa: E402
@@ -288,6 +309,7 @@ class Table:
 
 
 def main():
+    isolate_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--batches", type=int, default=15)
@@ -353,7 +375,7 @@ def main():
     if rank == 0:
         rows = args.batches * args.batch_rows
         ksum = sum(v["ms_per_step"] for v in kern.values())
-        print(json.dumps({
+        emit_line(json.dumps({
             "metric": "Mrows/sec filter_record_batch -> take_record_batch -> sum, 8-column RecordBatch", "value": rows * world / (step_ms * 1e-3) / 1e6,
             "unit": "Mrows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "scaling": "weak",
             "config": {"workload": "RecordBatch{3xInt64,3xFloat64,2xUtf8(D=4096, len 4..12)}", "batches_per_gpu": args.batches, "batch_rows": args.batch_rows,
