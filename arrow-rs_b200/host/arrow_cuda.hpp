@@ -843,6 +843,221 @@ class BatchCoalescer {
   std::vector<RecordBatch> completed_;
 };
 
+// ---- Utf8View / BinaryView columns: GenericByteViewArray + BatchCoalescer's InProgressByteViewArray ----------------------
+// (arrow-array/src/array/byte_view_array.rs; arrow-select/src/coalesce/byte_view.rs:39-559). A view = 16 bytes: length u32 |
+// 12 inline bytes, or length | 4-byte prefix | buffer index u32 | offset u32. The policy below (gc decision, BufferSource,
+// "fill the current buffer, then start a new one") is the reference's; the per-view work runs on the device (acu_view_*).
+struct ViewDataBuffer {
+  Buffer buffer;
+  size_t len = 0, capacity = 0;  // Buffer::len() / Buffer::capacity()
+};
+
+class StringViewArray {
+ public:
+  StringViewArray() = default;
+  StringViewArray(Buffer views, int64_t offset, int64_t len, std::vector<ViewDataBuffer> buffers, std::vector<bool> valid)
+      : views_(std::move(views)), offset_(offset), len_(len), buffers_(std::move(buffers)), valid_(std::move(valid)) {}
+  // StringViewBuilder::with_fixed_block_size(block_size): long values fill blocks of `block_size` bytes
+  static StringViewArray from(const std::vector<std::optional<std::string>> &v, size_t block_size = 8192) {
+    std::vector<uint8_t> views(v.size() * 16 + 16, 0);
+    std::vector<std::string> blocks;
+    std::string cur;
+    std::vector<bool> valid(v.size(), true);
+    for (size_t i = 0; i < v.size(); ++i) {
+      if (!v[i]) { valid[i] = false; continue; }
+      const std::string &sv = *v[i];
+      const uint32_t len = (uint32_t)sv.size();
+      memcpy(&views[16 * i], &len, 4);
+      if (len <= 12) {
+        memcpy(&views[16 * i + 4], sv.data(), len);
+      } else {
+        if (cur.size() + len > block_size && !cur.empty()) { blocks.push_back(cur); cur.clear(); }
+        const uint32_t bi = (uint32_t)blocks.size(), off = (uint32_t)cur.size();
+        memcpy(&views[16 * i + 4], sv.data(), 4);
+        memcpy(&views[16 * i + 8], &bi, 4);
+        memcpy(&views[16 * i + 12], &off, 4);
+        cur += sv;
+      }
+    }
+    if (!cur.empty()) blocks.push_back(cur);
+    std::vector<ViewDataBuffer> bufs;
+    for (const auto &b : blocks) bufs.push_back(ViewDataBuffer{Buffer::from_host(b.data(), b.size()), b.size(), std::max(block_size, b.size())});
+    return StringViewArray(Buffer::from_host(views.data(), v.size() * 16), 0, (int64_t)v.size(), std::move(bufs), std::move(valid));
+  }
+  int64_t len() const { return len_; }
+  const void *views_ptr() const { return static_cast<const uint8_t *>(views_.data()) + 16 * offset_; }
+  const std::vector<ViewDataBuffer> &data_buffers() const { return buffers_; }
+  const std::vector<bool> &valid() const { return valid_; }  // validity of rows [0, len) (host side: the test mirror)
+  bool has_nulls() const { return std::find(valid_.begin(), valid_.end(), false) != valid_.end(); }
+  StringViewArray slice(int64_t offset, int64_t len) const {
+    return StringViewArray(views_, offset_ + offset, len, buffers_, std::vector<bool>(valid_.begin() + offset, valid_.begin() + offset + len));
+  }
+  // GenericByteViewArray::total_buffer_bytes_used (byte_view_array.rs:749-761)
+  Result<int64_t> total_buffer_bytes_used() const {
+    int64_t total = 0;
+    Context &c = Context::get();
+    const acu_status st = acu_view_bytes_used(c.raw(), views_ptr(), len_, &total);
+    if (st != ACU_OK) return c.last_error(st);
+    return total;
+  }
+  std::vector<std::optional<std::string>> to_vec() const {
+    std::vector<uint8_t> views((size_t)len_ * 16 + 16);
+    if (len_) acu_memcpy_d2h(Context::get().raw(), views.data(), views_ptr(), (size_t)len_ * 16);
+    std::vector<std::string> data;
+    for (const auto &b : buffers_) {
+      std::string sdat(b.len, '\0');
+      b.buffer.to_host(sdat.data(), b.len);
+      data.push_back(std::move(sdat));
+    }
+    std::vector<std::optional<std::string>> out((size_t)len_);
+    for (int64_t i = 0; i < len_; ++i) {
+      if (!valid_[(size_t)i]) continue;
+      uint32_t len, bi, off;
+      memcpy(&len, &views[16 * i], 4);
+      if (len <= 12) out[(size_t)i] = std::string(reinterpret_cast<const char *>(&views[16 * i + 4]), len);
+      else {
+        memcpy(&bi, &views[16 * i + 8], 4);
+        memcpy(&off, &views[16 * i + 12], 4);
+        out[(size_t)i] = data[bi].substr(off, len);
+      }
+    }
+    return out;
+  }
+ private:
+  Buffer views_;
+  int64_t offset_ = 0, len_ = 0;
+  std::vector<ViewDataBuffer> buffers_;
+  std::vector<bool> valid_;
+};
+
+namespace coalesce {
+
+// BufferSource (byte_view.rs:526-559): 8 KiB doubling to 1 MiB, or the size asked for when larger
+class BufferSource {
+ public:
+  size_t next_size(size_t min_size) {
+    if (current_ < kMax) current_ *= 2;
+    if (current_ >= min_size) return current_;
+    while (current_ <= min_size && current_ < kMax) current_ *= 2;
+    return std::max(current_, min_size);
+  }
+ private:
+  static constexpr size_t kMax = 1024 * 1024;
+  size_t current_ = 4 * 1024;
+};
+
+class InProgressByteViewArray {
+ public:
+  explicit InProgressByteViewArray(int64_t batch_size) : batch_size_(batch_size) {}
+  // set_source (:357-391)
+  Result<int64_t> set_source(std::optional<StringViewArray> source) {
+    source_ = std::move(source);
+    need_gc_ = false;
+    ideal_ = 0;
+    if (source_ && !source_->data_buffers().empty()) {
+      auto used = source_->total_buffer_bytes_used();
+      if (used.is_err()) return used.unwrap_err();
+      ideal_ = (size_t)used.unwrap();
+      size_t actual = 0;
+      for (const auto &b : source_->data_buffers()) actual += b.capacity;
+      need_gc_ = ideal_ != 0 && actual > ideal_ * 2;
+    }
+    return (int64_t)ideal_;
+  }
+  bool source_needs_gc() const { return need_gc_; }
+  // copy_rows (:393-436)
+  Result<int64_t> copy_rows(int64_t offset, int64_t len) {
+    if (!source_) return ArrowError{ACU_ERR_INVALID_ARGUMENT, "Invalid argument error: Internal Error: InProgressByteViewArray: source not set"};
+    if (!views_.data()) views_ = Buffer::allocate((size_t)batch_size_ * 16);
+    const StringViewArray piece = source_->slice(offset, len);
+    valid_.insert(valid_.end(), piece.valid().begin(), piece.valid().end());
+    Context &c = Context::get();
+    acu_status st = ACU_OK;
+    if (ideal_ == 0) {
+      st = acu_view_rebase(c.raw(), piece.views_ptr(), len, 0, out_at(n_views_));
+    } else if (need_gc_) {
+      auto r = append_views_and_copy_strings(piece, ideal_);
+      if (r.is_err()) return r;
+    } else {  // append_views_and_update_buffer_index (:176-216)
+      finish_current();
+      const uint32_t starting = (uint32_t)completed_.size();
+      for (const auto &b : piece.data_buffers()) completed_.push_back(b);
+      st = acu_view_rebase(c.raw(), piece.views_ptr(), len, starting, out_at(n_views_));
+    }
+    if (st != ACU_OK) return c.last_error(st);
+    n_views_ += len;
+    return len;
+  }
+  // finish (:490-520)
+  StringViewArray finish() {
+    finish_current();
+    StringViewArray out(views_, 0, n_views_, std::move(completed_), std::move(valid_));
+    views_ = Buffer();
+    n_views_ = 0;
+    completed_.clear();
+    valid_.clear();
+    return out;
+  }
+
+ private:
+  void *out_at(int64_t row) const { return static_cast<uint8_t *>(views_.data()) + 16 * row; }
+  void finish_current() {
+    if (current_) { completed_.push_back(*current_); current_.reset(); }
+  }
+  ViewDataBuffer next_buffer(size_t min_size) {
+    const size_t cap = source_sizes_.next_size(min_size);
+    return ViewDataBuffer{Buffer::allocate(cap), 0, cap};
+  }
+  // append_views_and_copy_strings (:228-291)
+  Result<int64_t> append_views_and_copy_strings(const StringViewArray &piece, size_t view_buffer_size) {
+    if (!current_) return copy_inner(piece, 0, piece.len(), next_buffer(view_buffer_size));
+    const size_t remaining = current_->capacity - current_->len;
+    if (view_buffer_size <= remaining) {
+      ViewDataBuffer cur = *current_;
+      current_.reset();
+      return copy_inner(piece, 0, piece.len(), cur);
+    }
+    Context &c = Context::get();
+    int64_t num_to_current = 0, bytes_to_current = 0;
+    const acu_status st = acu_view_fit(c.raw(), piece.views_ptr(), piece.len(), (int64_t)remaining, &num_to_current, &bytes_to_current);
+    if (st != ACU_OK) return c.last_error(st);
+    ViewDataBuffer cur = *current_;
+    current_.reset();
+    auto r = copy_inner(piece, 0, num_to_current, cur);
+    if (r.is_err()) return r;
+    finish_current();
+    return copy_inner(piece, num_to_current, piece.len() - num_to_current, next_buffer(view_buffer_size - (size_t)bytes_to_current));
+  }
+  // append_views_and_copy_strings_inner (:298-354)
+  Result<int64_t> copy_inner(const StringViewArray &piece, int64_t first, int64_t n, ViewDataBuffer dst) {
+    if (n > 0) {
+      Context &c = Context::get();
+      std::vector<const uint8_t *> table;
+      for (const auto &b : piece.data_buffers()) table.push_back(static_cast<const uint8_t *>(b.buffer.data()));
+      int64_t bytes = 0;
+      const acu_status st = acu_view_copy_strings(c.raw(), static_cast<const uint8_t *>(piece.views_ptr()) + 16 * first, n, table.data(), (int32_t)table.size(),
+                                                  (uint32_t)completed_.size(), static_cast<uint8_t *>(dst.buffer.data()), (int64_t)dst.len,
+                                                  (int64_t)dst.capacity, out_at(n_views_ + first), &bytes);
+      if (st != ACU_OK) return c.last_error(st);
+      dst.len += (size_t)bytes;
+    }
+    current_ = dst;
+    return n;
+  }
+  int64_t batch_size_;
+  std::optional<StringViewArray> source_;
+  bool need_gc_ = false;
+  size_t ideal_ = 0;
+  Buffer views_;
+  int64_t n_views_ = 0;
+  std::vector<bool> valid_;
+  std::optional<ViewDataBuffer> current_;
+  std::vector<ViewDataBuffer> completed_;
+  BufferSource source_sizes_;
+};
+
+}  // namespace coalesce
+
 // ---- kernels::numeric (arrow-arith/src/numeric.rs) ---------------------------------------
 namespace kernels {
 namespace numeric {

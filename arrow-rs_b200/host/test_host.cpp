@@ -570,6 +570,92 @@ static void test_ipc_stream_reader() {
   CHECK_EQ(ipc::StreamReader::try_new(std::vector<uint8_t>{}).unwrap_err().message, std::string("Ipc error: Expected schema message, found empty stream."));
 }
 
+// arrow-select/src/coalesce.rs:1079-1167,1230-1304 (test_string_view_batch_large_no_compact, _large_slice_compact,
+// _many_small_compact, _many_small_boundary): expected data-buffer layouts of the coalesced StringViewArray
+static void test_string_view_coalesce() {
+  using arrow_cuda::compute::StringViewArray;
+  using arrow_cuda::compute::coalesce::InProgressByteViewArray;
+  auto repeated = [](size_t n, std::vector<O<std::string>> items) {
+    std::vector<O<std::string>> v;
+    for (size_t i = 0; i < n; ++i) v.push_back(items[i % items.size()]);
+    return StringViewArray::from(v, 8192);
+  };
+  auto layout = [](const StringViewArray &a) {
+    std::vector<std::pair<size_t, size_t>> l;
+    for (const auto &b : a.data_buffers()) l.push_back({b.len, b.capacity});
+    return l;
+  };
+  using L = std::vector<std::pair<size_t, size_t>>;
+  const std::string long_s = "This string is longer than 12 bytes";
+  auto large = repeated(1000, {long_s});
+  CHECK_EQ(5u, large.data_buffers().size());
+  {  // full buffers: adopted, not copied
+    InProgressByteViewArray ip(1000);
+    ip.set_source(large).unwrap();
+    CHECK(!ip.source_needs_gc());
+    ip.copy_rows(0, 1000).unwrap();
+    auto out = ip.finish();
+    CHECK((layout(out) == L{{8190, 8192}, {8190, 8192}, {8190, 8192}, {8190, 8192}, {2240, 8192}}));
+    CHECK(out.to_vec() == large.to_vec());
+  }
+  {  // a 22-row slice of it uses 770 of 40960 buffer bytes: garbage-collected into one 8 KiB buffer
+    InProgressByteViewArray ip(1000);
+    auto sl = large.slice(11, 22);
+    ip.set_source(sl).unwrap();
+    CHECK(ip.source_needs_gc());
+    ip.copy_rows(0, 22).unwrap();
+    auto out = ip.finish();
+    CHECK((layout(out) == L{{770, 8192}}));
+    CHECK(out.to_vec() == sl.to_vec());
+  }
+  {  // ten batches of 100 long (28 bytes) + 100 short strings: buffers of 8, 16, 32 KiB filled in turn
+    auto b = repeated(200, {std::string("This string is 28 bytes long"), std::string("small string")});
+    InProgressByteViewArray ip(8000);
+    std::vector<O<std::string>> expect;
+    for (int k = 0; k < 10; ++k) {
+      ip.set_source(b).unwrap();
+      ip.copy_rows(0, 200).unwrap();
+      auto v = b.to_vec();
+      expect.insert(expect.end(), v.begin(), v.end());
+    }
+    auto out = ip.finish();
+    CHECK((layout(out) == L{{8176, 8192}, {16380, 16384}, {3444, 32768}}));
+    CHECK(out.to_vec() == expect);
+  }
+  {  // strings that fill power-of-two buffers exactly; output batches of 900 rows cut the 100-row inputs
+    auto b = repeated(100, {std::string("This string is a power of two=32")});
+    InProgressByteViewArray ip(900);
+    int64_t buffered = 0;
+    std::vector<StringViewArray> outs;
+    for (int k = 0; k < 20; ++k) {
+      ip.set_source(b).unwrap();
+      int64_t n = 100, off = 0;
+      while (n > 900 - buffered) {
+        const int64_t rem = 900 - buffered;
+        ip.copy_rows(off, rem).unwrap();
+        off += rem; n -= rem; buffered = 0;
+        outs.push_back(ip.finish());
+      }
+      if (n > 0) { ip.copy_rows(off, n).unwrap(); buffered += n; }
+      if (buffered >= 900) { outs.push_back(ip.finish()); buffered = 0; }
+    }
+    if (buffered) outs.push_back(ip.finish());
+    CHECK_EQ(3u, outs.size());
+    CHECK_EQ(900, outs[0].len());
+    CHECK_EQ(200, outs[2].len());
+    CHECK((layout(outs[0]) == L{{8192, 8192}, {16384, 16384}, {4224, 32768}}));
+  }
+  {  // nulls and inline-only arrays
+    auto small = StringViewArray::from({std::string("foo"), N, std::string("bar")});
+    InProgressByteViewArray ip(16);
+    ip.set_source(small).unwrap();
+    ip.copy_rows(1, 2).unwrap();
+    auto out = ip.finish();
+    CHECK(out.data_buffers().empty());
+    CHECK((out.to_vec() == std::vector<O<std::string>>{N, std::string("bar")}));
+  }
+}
+
 int main() {
   try {
     Context::get(0);
@@ -608,6 +694,7 @@ int main() {
       {"cmp_utf8", test_cmp_utf8},
       {"row_filter", test_row_filter},
       {"ipc_stream_reader", test_ipc_stream_reader},
+      {"string_view_coalesce", test_string_view_coalesce},
   };
   for (auto &t : tests) {
     int before = g_failed;
