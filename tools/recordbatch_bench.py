@@ -325,6 +325,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if os.environ.get("ACU_BENCH_NUMA", "1") != "0":  # host threads (one per lane) next to the GPU, like bench.py's ranks
+        sys.path.insert(0, REPO)
+        try:
+            from bench import numa_bind
+            numa_bind(local_rank)
+        except Exception:
+            pass
     import acu
     from acu import _abi as abi
     from acu.rendezvous import Group
