@@ -181,8 +181,6 @@ PROTOTYPES = {
     "acu_timer_stop_slot": (i32, [vp, i32, P(f32)]),
     "acu_kernel_stats": (i32, [vp, i32, P(f64), P(i64)]),
     "acu_kernel_stats_reset": (i32, [vp]),
-    "acu_generate_values": (i32, [vp, i32, u64, i64, u64, vp, i64]),
-    "acu_generate_bits": (i32, [vp, u64, i64, f64, vp, i64]),
     "acu_bitmap_count": (i32, [vp, vp, i64, vp, i64, i64, P(i64)]),
     "acu_filter_plan_create": (i32, [vp, P(Array), P(vp)]),
     "acu_filter_plan_create_cmp": (i32, [vp, i32, i32, P(Array), P(Array), P(vp)]),
@@ -240,6 +238,15 @@ PROTOTYPES = {
 _lib = None
 
 
+# Synthetic-input generators of the benchmarks and tests: libarrow_cuda_testgen.so (include/arrow_cuda_testgen.h), test support
+# only. Bound onto the same handle object so that callers keep writing lib.acu_generate_*.
+TESTGEN_LIB_PATH = os.path.join(os.path.dirname(LIB_PATH), "libarrow_cuda_testgen.so")
+TESTGEN_PROTOTYPES = {
+    "acu_generate_values": (i32, [vp, i32, u64, i64, u64, vp, i64]),
+    "acu_generate_bits": (i32, [vp, u64, i64, f64, vp, i64]),
+}
+
+
 def load_library(path=None):
     """Load libarrow_cuda.so and bind every prototype. Fails loudly if the CUDA extension
     has not been built — there is no CPU fallback behind this ABI."""
@@ -258,5 +265,12 @@ def load_library(path=None):
         fn.argtypes = args
     if lib.acu_abi_version() != 1:
         raise RuntimeError("libarrow_cuda.so ABI version mismatch")
+    if os.path.exists(TESTGEN_LIB_PATH):
+        gen = C.CDLL(TESTGEN_LIB_PATH, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in TESTGEN_PROTOTYPES.items():
+            fn = getattr(gen, name)
+            fn.restype = res
+            fn.argtypes = args
+            setattr(lib, name, fn)
     _lib = lib
     return lib

@@ -10,6 +10,7 @@
 #include <stdlib.h>
 
 #include "arrow_cuda.h"
+#include "arrow_cuda_testgen.h" /* synthetic inputs: test support, not part of the product library */
 
 #define CHECK(call)                                                                              \
   do {                                                                                           \

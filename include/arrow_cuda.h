@@ -208,19 +208,6 @@ typedef enum acu_kernel_class {
 acu_status acu_kernel_stats(acu_ctx *ctx, int32_t kernel_class, double *out_total_ms, int64_t *out_launches);
 acu_status acu_kernel_stats_reset(acu_ctx *ctx);
 
-/* Deterministic synthetic inputs generated on the device:
- * element i = f(splitmix64(seed ^ (first_row + i))). The same generator exists on the
- * host in oracle/ so that any row range can be spot-checked.
- *   kind 0: raw 64-bit values (Int64 full range)
- *   kind 1: Int64 uniform in [-2^61, 2^61)
- *   kind 2: Float64 uniform in [-1e6, 1e6)
- *   kind 3: UInt32 uniform in [0, param)         (take indices, distribution B)
- *   kind 4: Int32 uniform in [0, param)
- * acu_generate_bits: bit i = splitmix64(seed ^ (first_row+i)) < p * 2^64. */
-acu_status acu_generate_values(acu_ctx *ctx, int32_t kind, uint64_t seed, int64_t first_row,
-                               uint64_t param, void *out, int64_t n);
-acu_status acu_generate_bits(acu_ctx *ctx, uint64_t seed, int64_t first_row, double p,
-                             uint8_t *out_bits, int64_t n);
 
 /* ------------------------------------------------------------------------- */
 /* Bitmaps                                                                   */

@@ -11,10 +11,20 @@ from acu import _abi as abi
 HEADER = os.path.join(abi.REPO, "include", "arrow_cuda.h")
 
 
-def declared_symbols():
-    text = open(HEADER).read()
+def declared_symbols(header=HEADER):
+    text = open(header).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(acu_[a-z0-9_]+)\s*\(", text)) - {"acu_bitmap_bytes"})
+
+
+def test_generators_live_outside_the_product_library():
+    """The synthetic-input generators of the benches / tests are a separate library (include/arrow_cuda_testgen.h)."""
+    gen_syms = declared_symbols(os.path.join(abi.REPO, "include", "arrow_cuda_testgen.h"))
+    assert gen_syms == sorted(abi.TESTGEN_PROTOTYPES)
+    product = C.CDLL(abi.LIB_PATH)
+    gen = C.CDLL(abi.TESTGEN_LIB_PATH)
+    for s in gen_syms:
+        assert not hasattr(product, s) and hasattr(gen, s)
 
 
 def test_library_is_built():
@@ -60,7 +70,7 @@ def _build_c_example(tmp_path):
     import subprocess
     exe = str(tmp_path / "hot_path")
     cmd = ["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(abi.REPO, "include"),
-           os.path.join(abi.REPO, "examples", "hot_path.c"), "-L" + os.path.dirname(abi.LIB_PATH), "-larrow_cuda",
+           os.path.join(abi.REPO, "examples", "hot_path.c"), "-L" + os.path.dirname(abi.LIB_PATH), "-larrow_cuda", "-larrow_cuda_testgen",
            "-Wl,-rpath," + os.path.dirname(abi.LIB_PATH), "-o", exe]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
