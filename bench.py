@@ -56,10 +56,20 @@ SELECTIVITY, NULL_DENSITY = 0.10, 0.05
 
 
 def so_sha16():
+    """Identity of the kernel build: sha256 over the kernel SOURCES (csrc/*.cu, *.cuh, Makefile, the C header), in name order.
+    (nvcc's output is not bit-reproducible from one build to the next, so the binary's own hash would call a clean rebuild of
+    the same sources a different build.) tools/gpu_profiles.sh records the same value beside every ncu capture."""
+    import glob
     import hashlib
-    p = os.path.join(REPO, "arrow-rs_b200", "libarrow_cuda.so")
+    h = hashlib.sha256()
+    src = os.path.join(REPO, "arrow-rs_b200", "csrc")
+    files = sorted(glob.glob(os.path.join(src, "*.cu")) + glob.glob(os.path.join(src, "*.cuh")) + [os.path.join(src, "Makefile"),
+                   os.path.join(REPO, "include", "arrow_cuda.h")])
     try:
-        return hashlib.sha256(open(p, "rb").read()).hexdigest()[:16]
+        for f in files:
+            h.update(os.path.basename(f).encode() + b"\0")
+            h.update(open(f, "rb").read())
+        return h.hexdigest()[:16]
     except Exception:
         return None
 
@@ -686,7 +696,8 @@ def run_gpu(args):
         "roofline": {"bound": "hbm", "kernel": "k_arith<double> (Float64 add, fused validity AND + popcount)",
                      "achieved": dom.get("achieved_gbs"), "peak": peak, "unit": "GB/s", "frac": dom.get("frac"),
                      "traffic": dom.get("traffic"), "traffic_source": f"profiles/{traffic_src} (ncu --set full, per launch)" if traffic_src else None,
-                     "traffic_so_sha16": traffic_sha, "so_sha16": sha, "traffic_same_build": (traffic_sha == sha) if traffic_sha else None,
+                     "traffic_so_sha16": traffic_sha, "so_sha16": sha, "sha_of": "kernel sources (csrc/*.cu, *.cuh, Makefile, include/arrow_cuda.h)",
+                     "traffic_same_build": (traffic_sha == sha) if traffic_sha else None,
                      "algorithmic_bytes": ab["add"], "peak_source": peak_src, "per_op": roof_ops},
         "roofline_filter": roof_ops.get("filter"), "roofline_take": roof_ops.get("take"),
         "kernels": kstats,

@@ -2,7 +2,7 @@
 # usage: tools/gpu_profiles.sh rNN   (one gpurun call, one GPU) — the captures profiles/rNN_* are derived from
 R=${1:-r02}
 mkdir -p gpurun_out
-sha256sum arrow-rs_b200/libarrow_cuda.so | cut -c1-16 > gpurun_out/so_sha16_$R.txt
+python -c "import bench; print(bench.so_sha16())" > gpurun_out/so_sha16_$R.txt   # hash of the kernel sources (see bench.so_sha16)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_$R.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-configs > gpurun_out/launches_$R.log 2>&1
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"k_arith|k_take|k_filter_fused|k_reduce|k_plan_mask" -s 20 -c 8 -f -o gpurun_out/prof_$R python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-configs > gpurun_out/prof_$R.log 2>&1
 ncu -i gpurun_out/prof_$R.ncu-rep --page details > gpurun_out/prof_${R}_details.txt 2>&1

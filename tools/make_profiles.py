@@ -30,7 +30,7 @@ for r in raw[2:]:
     traffic[name] = float(r[rd].replace(",", "")) * scale[units[rd]] + float(r[wr].replace(",", "")) * scale[units[wr]]
 sha = open(f"gpurun_out/so_sha16_{rnd}.txt").read().strip() if os.path.exists(f"gpurun_out/so_sha16_{rnd}.txt") else None
 # bench.py reads this file: per-launch DRAM bytes (read + write) of the step kernels at 1e9 rows, with the hash of the
-# libarrow_cuda.so the capture was taken on (roofline.traffic_same_build)
+# kernel sources the capture was taken on (bench.so_sha16(): sha256 over csrc/ + the header; roofline.traffic_same_build)
 json.dump({"so_sha16": sha, "rows": 1000000000, "source": f"ncu --set full (gpurun_out/prof_{rnd}.ncu-rep), dram__bytes_read.sum + dram__bytes_write.sum per launch",
            "kernels": traffic}, open(f"profiles/{rnd}_traffic.json", "w"), indent=1)
 # the ncu details page of the same capture (speed-of-light, occupancy, stall sections per kernel), as text
@@ -49,7 +49,7 @@ for line in sass.splitlines():
             if op in line:
                 counts[fn][op] = counts[fn].get(op, 0) + 1
 with open(f"profiles/{rnd}_sass_excerpts.txt", "w") as f:
-    f.write(f"# cuobjdump -sass arrow-rs_b200/libarrow_cuda.so (sha256[:16] = {sha}): memory-path instruction counts per hot kernel\n")
+    f.write(f"# cuobjdump -sass arrow-rs_b200/libarrow_cuda.so (kernel-source hash bench.so_sha16() = {sha}): memory-path instruction counts per hot kernel\n")
     f.write("# UBLKCP = cp.async.bulk (TMA engine), LDGSTS = cp.async (global -> shared), REDG = fire-and-forget global atomics,\n")
     f.write("# REDUX = redux.sync, no HMMA / UTC*MMA: no tensor-core instruction anywhere (HBM-bound integer / byte work)\n")
     import subprocess as sp
