@@ -184,7 +184,7 @@ def main():
         total = C.c_int64(0)
         b.timed("cast dict<i32,utf8>->utf8", [abi.K_TAKE, abi.K_BYTES], 4 * ns + ns / 8 + 4 * (ns + 1) + 0.95 * ns * 8 + ns / 8, ns,
                 lambda: ctx.check(lib.acu_take_bytes(h, 4, d_off, d_data, C.byref(dict_nulls), C.byref(keys), abi.I32, 0, d_out_off, d_out_data, ns * 13, C.byref(total), C.byref(on))),
-                note="kernel_ms counts the take(nulls) + byte-copy kernels; lengths/scan kernels are in call_ms")
+                note="kernel_ms = validity + table + lengths + copy kernels (the three tiny scan kernels only show in call_ms)")
     print("\n| op | rows | kernel ms | GB/s (algorithmic) | % of measured HBM peak | Mrows/s |")
     print("|---|---|---|---|---|---|")
     for r in b.rows:
