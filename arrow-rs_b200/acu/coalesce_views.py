@@ -84,6 +84,48 @@ class DeviceViewBackend:
     def rebase(self, src, offset, n, delta, out_views, out_at):
         self.ctx.check(self.ctx.lib.acu_view_rebase(self.ctx.h, src["views"] + 16 * offset, n, delta, out_views + 16 * out_at))
 
+    def filter_views(self, col, predicate):
+        """filter_byte_view (arrow-select/src/filter.rs:931-944): filter_native over the 16-byte views + filter_nulls; the data
+        buffers are shared. col: ViewColumn, predicate: HostArray(BOOL) -> ViewColumn (host)."""
+        from . import _abi as abi
+        ctx = self.ctx
+        n = col.length
+        views = np.ascontiguousarray(col.views).reshape(-1)
+        d_views = ctx.malloc(max(views.nbytes, 16) + 16)
+        if views.nbytes:
+            ctx.h2d(d_views, views)
+        d_valid = None
+        if col.nulls.validity is not None:
+            d_valid = ctx.malloc(col.nulls.validity.nbytes + 8)
+            ctx.h2d(d_valid, col.nulls.validity)
+        vd = abi.Array()
+        vd.values, vd.values_offset, vd.validity, vd.validity_offset = d_views, 0, d_valid, col.nulls.validity_offset
+        vd.len, vd.null_count, vd.is_scalar = n, (col.nulls.null_count if d_valid else 0), 0
+        dp = ctx.upload(predicate)
+        plan = C.c_void_p()
+        out = None
+        try:
+            pd = dp.descriptor()
+            ctx.check(ctx.lib.acu_filter_plan_create(ctx.h, C.byref(pd), C.byref(plan)))
+            count = ctx.lib.acu_filter_plan_count(plan)
+            out = ctx.alloc_out(count * 16, count)
+            ctx.check(ctx.lib.acu_filter_primitive(ctx.h, plan, 16, C.byref(vd), C.byref(out)))
+            fv = ctx.d2h(out.values, count * 16).reshape(count, 16) if count else np.zeros((0, 16), np.uint8)
+            validity = ctx.d2h(out.validity, bitmap_bytes(count)) if out.has_validity else None
+            nulls = HostArray(U8, np.zeros(0, np.uint8), count, validity, 0, 0, out.null_count if out.has_validity else 0)
+        finally:
+            if out is not None:
+                ctx._free_out(out)
+            if plan:
+                ctx.lib.acu_filter_plan_destroy(ctx.h, plan)
+            dp.free()
+            ctx.free(d_views)
+            if d_valid:
+                ctx.free(d_valid)
+        res = ViewColumn(fv, col.buffers, nulls)
+        res.buffer_capacities = getattr(col, "buffer_capacities", None)
+        return res
+
     # -- storage ----------------------------------------------------------------------------------------
     def alloc(self, nbytes):
         return self.ctx.malloc(max(nbytes, 16) + 16)
@@ -151,6 +193,26 @@ class InProgressByteViewArray:
             self._append_views_and_copy_strings(dev, offset, n, s["ideal"])
         else:
             self._append_views_and_update_buffer_index(dev, offset, n, s)
+        self.n_views += n
+
+    def copy_rows_by_filter_from(self, source_col, filtered_col):
+        """byte_view.rs:464-488: the sparse-filter path. All-inline sources: the filtered views / nulls are appended as they
+        are; sources with data buffers: the filtered views keep pointing into the SOURCE's buffers, which are adopted
+        (append_views_and_update_buffer_index(.., is_reused = false)) — no string is copied, no gc decision is taken."""
+        if self.views is None:
+            self.views = self.be.alloc(self.batch_size * 16)
+        n = filtered_col.length
+        if filtered_col.nulls.validity is not None:
+            self.valid.append(filtered_col.nulls.valid_mask()[:n].copy())
+        else:
+            self.valid.append(np.ones(n, dtype=bool))
+        dev = self.be.upload(filtered_col)
+        dev["refs"] = 1
+        if not source_col.buffers:
+            self.be.rebase(dev, 0, n, 0, self.views, self.n_views)
+        else:
+            self._append_views_and_update_buffer_index(dev, 0, n, None)
+        self._unref(dev)  # (an adopting batch holds its own reference)
         self.n_views += n
 
     def _finish_current(self):
@@ -254,6 +316,35 @@ class ViewBatchCoalescer:
             self.finish_buffered_batch()
         # the reference drops the source here (set_source(None), coalesce.rs:524-527); adopted buffers live on by refcount,
         # here they stay with the in-progress array until the next batch arrives
+
+    def push_batch_with_filter(self, view_column, predicate):
+        """push_batch_with_filtered_columns (coalesce.rs:620-681). predicate: HostArray(BOOL), no longer than the column."""
+        from . import ArrowError
+        from . import _abi as abi
+        n = view_column.length
+        if predicate.length > n:
+            raise ArrowError(abi.ERR_INVALID_ARGUMENT,
+                             f"Invalid argument error: Filter predicate of length {predicate.length} is larger than target array of length {n}")
+        sel = predicate.to_numpy_bool() if hasattr(predicate, "to_numpy_bool") else None
+        if sel is None:
+            bits = np.unpackbits(np.asarray(predicate.values, dtype=np.uint8), bitorder="little")[predicate.values_offset:predicate.values_offset + predicate.length].astype(bool)
+            if predicate.validity is not None:
+                bits &= np.unpackbits(predicate.validity, bitorder="little")[predicate.validity_offset:predicate.validity_offset + predicate.length].astype(bool)
+            sel = bits
+        selected = int(sel.sum())
+        if selected == 0:
+            return
+        if selected == n and predicate.length == n:
+            return self.push_batch(view_column)
+        does_not_fit = selected > self.target - self.buffered
+        sparse_ok = selected <= predicate.length // 16  # should_use_sparse_filter_copy (coalesce.rs:49-54)
+        filtered = self.col.be.filter_views(view_column, predicate)
+        if does_not_fit or not sparse_ok:
+            return self.push_batch(filtered)  # materialised filter, then the normal path (gc decision on the filtered array)
+        self.col.copy_rows_by_filter_from(view_column, filtered)
+        self.buffered += selected
+        if self.buffered >= self.target:
+            self.finish_buffered_batch()
 
     def finish_buffered_batch(self):
         if self.buffered == 0:

@@ -398,6 +398,7 @@ class OracleViewBackend:
 
     def __init__(self, oracle):
         self.lib = oracle.lib
+        self._oracle = oracle
         self.lib.orc_view_bytes_used.restype = i64
         self.lib.orc_view_bytes_used.argtypes = [vp, i64]
         self.lib.orc_view_copy_strings.restype = i64
@@ -429,6 +430,28 @@ class OracleViewBackend:
 
     def rebase(self, src, offset, n, delta, out_views, out_at):
         self.lib.orc_view_rebase(src["views"].ctypes.data + 16 * offset, n, delta, out_views.ctypes.data + 16 * out_at)
+
+    def filter_views(self, col, predicate):
+        """filter_byte_view = filter_native(views) + filter_nulls, buffers shared (filter.rs:931-944), through the oracle's
+        16-byte-wide filter."""
+        o = self._oracle
+        n = col.length
+        views = np.ascontiguousarray(col.views).reshape(-1).copy()
+        vd = abi.Array()
+        vd.values, vd.values_offset = views.ctypes.data, 0
+        vd.validity = col.nulls.validity.ctypes.data if col.nulls.validity is not None else None
+        vd.validity_offset, vd.len, vd.is_scalar = col.nulls.validity_offset, n, 0
+        vd.null_count = col.nulls.null_count if col.nulls.validity is not None else 0
+        out, vals, valid = o._out(max(n, predicate.length) * 16, max(n, predicate.length))
+        pd = acu.host_descriptor(predicate)
+        cnt, strat = i64(0), i32(0)
+        o.check(o.lib.orc_filter_primitive(C.byref(pd), 16, C.byref(vd), C.byref(out), C.byref(cnt), C.byref(strat)))
+        m = out.len
+        validity = valid[: bitmap_bytes(m)].copy() if out.has_validity else None
+        res = acu.ViewColumn(vals[: m * 16].copy().reshape(m, 16), col.buffers,
+                             HostArray(acu.U8, np.zeros(0, np.uint8), m, validity, 0, 0, out.null_count if out.has_validity else 0))
+        res.buffer_capacities = getattr(col, "buffer_capacities", None)
+        return res
 
     def alloc(self, nbytes):
         return np.zeros(max(nbytes, 16) + 16, dtype=np.uint8)

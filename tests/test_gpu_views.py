@@ -97,3 +97,51 @@ def test_primitives_edges(gpu, oracle):
     for p in (out_views, dst, big):
         gpu.free(p)
     be_g.release_source(dg)
+
+
+def both_filtered(gpu, oracle, steps, batch_size):
+    from acu import HostArray
+    outs = []
+    for be in (DeviceViewBackend(gpu), OracleViewBackend(oracle)):
+        co = ViewBatchCoalescer(be, batch_size)
+        for b, mask in steps:
+            if mask is None:
+                co.push_batch(b)
+            else:
+                co.push_batch_with_filter(b, HostArray.bool_from_numpy(np.asarray(mask, dtype=bool)))
+        co.finish_buffered_batch()
+        outs.append(co.completed)
+        co.close()
+    g, e = outs
+    assert len(g) == len(e)
+    for (gc, gl), (ec, el) in zip(g, e):
+        assert gl == el and np.array_equal(gc.views, ec.views)
+        assert len(gc.buffers) == len(ec.buffers) and all(np.array_equal(x, y) for x, y in zip(gc.buffers, ec.buffers))
+        assert (gc.nulls.validity is None) == (ec.nulls.validity is None) and gc.nulls.null_count == ec.nulls.null_count
+        assert view_values(gc) == view_values(ec)
+    return g
+
+
+def test_push_batch_with_filter(gpu, oracle):
+    """push_batch_with_filtered_columns (coalesce.rs:620-681) for view columns: the sparse per-column copy (views filtered on the
+    device by the 16-byte filter kernel, source buffers adopted) and the materialised path (filter, then push_batch with its gc
+    decision) — identical layouts on the device and on the oracle; reference cases coalesce.rs:1424-1441,1503-1520,
+    byte_view.rs:619-650."""
+    inline = view_batch(1000, ["foo", None, "barbaz"])
+    out = both_filtered(gpu, oracle, [(inline, [i % 8 == 0 for i in range(1000)])] * 2, 300)
+    assert [c.length for c, _ in out] == [250]
+    out = both_filtered(gpu, oracle, [(inline, [i % 20 == 0 for i in range(1000)])] * 2, 1024)
+    assert [c.length for c, _ in out] == [100]
+    vals = [f"This value is longer than 12 bytes: {i}" for i in range(32)]
+    b = view_batch(32, vals)
+    out = both_filtered(gpu, oracle, [(b, [i == 3 or i == 29 for i in range(32)])], 32)
+    assert out[0][1] == [(int(b.buffers[0].nbytes), 8192)]
+    large = view_batch(1000, [LONG])
+    out = both_filtered(gpu, oracle, [(large, [i % 8 == 0 for i in range(1000)])], 1000)
+    assert out[0][1] == [(125 * 35, 8192)]
+    # mixed sequence with nulls, slices, dense and sparse filters across batch boundaries
+    rng = np.random.default_rng(5)
+    mixed = view_batch(3000, [LONG, "Small", None, "another rather long string value", "x"])
+    steps = [(mixed, None), (view_slice(mixed, 100, 2000), rng.random(2000) < 0.03), (mixed, rng.random(3000) < 0.5),
+             (view_slice(mixed, 7, 900), rng.random(900) < 0.05), (large, rng.random(1000) < 0.04)]
+    both_filtered(gpu, oracle, steps, 700)

@@ -107,3 +107,63 @@ def test_fuzz_content_and_nulls(oracle):
         batches.append(b)
     out = run(oracle, batches, 257)
     assert all(c.length == 257 for c, _ in out[:-1])
+
+
+def bool_array(mask):
+    from acu import HostArray
+    return HostArray.bool_from_numpy(np.asarray(mask, dtype=bool))
+
+
+def run_filtered(oracle, steps, batch_size):
+    """steps: [(ViewColumn, predicate mask or None)] -> completed [(ViewColumn, layout)], checking the logical content."""
+    co = ViewBatchCoalescer(OracleViewBackend(oracle), batch_size)
+    expect = []
+    for b, mask in steps:
+        vals = view_values(b)
+        if mask is None:
+            expect += vals
+            co.push_batch(b)
+        else:
+            expect += [v for v, m in zip(vals, mask) if m]
+            co.push_batch_with_filter(b, bool_array(mask))
+    co.finish_buffered_batch()
+    got = []
+    for col, _ in co.completed:
+        got += view_values(col)
+    assert got == expect
+    return co.completed
+
+
+def test_string_view_filtered_inline(oracle):  # coalesce.rs:1424-1441 (+ :1404-1421 BinaryView): idx % 8 == 0 of 1000 rows, twice
+    b = view_batch(1000, ["foo", None, "barbaz"])
+    mask = [i % 8 == 0 for i in range(1000)]
+    out = run_filtered(oracle, [(b, mask), (b, mask)], 300)
+    assert [c.length for c, _ in out] == [250] and out[0][1] == []
+
+
+def test_inline_view_very_sparse(oracle):  # coalesce.rs:1503-1520: idx % 20 == 0 (the sparse per-column copy path)
+    b = view_batch(1000, ["foo", None, "barbaz"])
+    mask = [i % 20 == 0 for i in range(1000)]
+    out = run_filtered(oracle, [(b, mask), (b, mask)], 1024)
+    assert [c.length for c, _ in out] == [100] and out[0][1] == []
+
+
+def test_copy_rows_by_filter_from_reuses_non_inline_buffers(oracle):  # byte_view.rs:619-650
+    vals = [f"This value is longer than 12 bytes: {i}" for i in range(32)]
+    b = view_batch(32, vals)
+    assert len(b.buffers) == 1
+    mask = [i == 3 or i == 29 for i in range(32)]  # 2 of 32 rows: sparse path (2 <= 32 / 16)
+    out = run_filtered(oracle, [(b, mask)], 32)
+    col, layout = out[0]
+    assert view_values(col) == as_bytes([vals[3], vals[29]])
+    assert layout == [(int(b.buffers[0].nbytes), 8192)]  # the source's buffer, adopted as it is (no copy, no compaction)
+    assert np.array_equal(col.buffers[0], b.buffers[0])
+
+
+def test_filtered_dense_goes_through_push_batch(oracle):
+    """Not sparse enough (selected > len / 16): filter_record_batch, then push_batch — the gc decision is taken on the filtered
+    array (coalesce.rs:652-666): 125 of 1000 long strings use 4375 of 40960 buffer bytes => compacted into one 8 KiB buffer."""
+    b = view_batch(1000, [LONG])
+    mask = [i % 8 == 0 for i in range(1000)]
+    out = run_filtered(oracle, [(b, mask)], 1000)
+    assert [c.length for c, _ in out] == [125] and out[0][1] == [(125 * 35, 8192)]
