@@ -407,6 +407,29 @@ class Context:
                 self.lib.acu_filter_plan_destroy(self.h, plan)
             dp.free()
 
+    def filter_slices(self, predicate):
+        """SlicesIterator::new(&prep_null_mask_filter(predicate)).collect() -> [(start, end)] (filter.rs:44-77)."""
+        dp = self.upload(predicate)
+        plan = C.c_void_p()
+        out = None
+        try:
+            pd = dp.descriptor()
+            self.check(self.lib.acu_filter_plan_create(self.h, C.byref(pd), C.byref(plan)))
+            n = C.c_int64(0)
+            self.check(self.lib.acu_filter_plan_slices(self.h, plan, None, 0, C.byref(n)))
+            if n.value == 0:
+                return []
+            out = self.malloc(n.value * 16 + 16)
+            self.check(self.lib.acu_filter_plan_slices(self.h, plan, out, n.value, C.byref(n)))
+            pairs = self.d2h(out, n.value * 16, np.uint64).reshape(-1, 2)
+            return [(int(a), int(b)) for a, b in pairs]
+        finally:
+            if out:
+                self.free(out)
+            if plan:
+                self.lib.acu_filter_plan_destroy(self.h, plan)
+            dp.free()
+
     def chain(self, col, pred, idx, a, b, arith_op=ADD, agg_op=SUM, cmp_with=None):
         """filter(col, pred) -> take(col, idx) -> arith(a, b) -> aggregate(taken) queued in ONE stream-ordered section
         (acu_async_begin ... acu_results_fetch): one synchronisation for the five calls. With cmp_with = (op, x, y) the

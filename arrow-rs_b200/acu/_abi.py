@@ -227,6 +227,7 @@ PROTOTYPES = {
     "acu_view_fit": (i32, [vp, vp, i64, i64, P(i64), P(i64)]),
     "acu_view_copy_strings": (i32, [vp, vp, i64, P(vp), i32, C.c_uint32, vp, i64, i64, vp, P(i64)]),
     "acu_view_rebase": (i32, [vp, vp, i64, C.c_uint32, vp]),
+    "acu_filter_plan_slices": (i32, [vp, vp, vp, i64, P(i64)]),
     "acu_async_begin": (i32, [vp]),
     "acu_results_fetch": (i32, [vp]),
     "acu_async_active": (i32, [vp]),

@@ -1180,6 +1180,66 @@ extern "C" acu_status acu_filter_plan_indices(acu_ctx *ctx, const acu_filter_pla
   return ACU_OK;
 }
 
+// ---- IterationStrategy::Slices (FilterBuilder::optimize, filter.rs:285-298) = SlicesIterator (filter.rs:44-77) --------------
+// Runs of selected rows as [start, end) pairs in ascending order. A run starts at a set bit whose predecessor is clear and
+// ends after a set bit whose successor is clear; both are word-local tests once the neighbouring word's edge bit is known
+// (the plan's mask is normalised to bit offset 0 and zero padded). The k-th start and the k-th end belong to the same run,
+// so two independent scans of the per-word counts place them.
+__global__ void __launch_bounds__(256) k_plan_slice_counts(const uint64_t *__restrict__ mask, int64_t n_words, int64_t *__restrict__ n_starts,
+                                                           int64_t *__restrict__ n_ends) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) {
+    const uint64_t m = __ldg(mask + i);
+    const uint64_t prev = i ? (__ldg(mask + i - 1) >> 63) : 0ull, next = i + 1 < n_words ? (__ldg(mask + i + 1) & 1ull) : 0ull;
+    n_starts[i] = __popcll(m & ~((m << 1) | prev));
+    n_ends[i] = __popcll(m & ~((m >> 1) | (next << 63)));
+  }
+}
+
+__global__ void __launch_bounds__(256) k_plan_slices_emit(const uint64_t *__restrict__ mask, int64_t n_words, const int64_t *__restrict__ incl_starts,
+                                                          const int64_t *__restrict__ incl_ends, int64_t capacity, uint64_t *__restrict__ out_pairs) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) {
+    const uint64_t m = __ldg(mask + i);
+    if (!m) continue;
+    const uint64_t prev = i ? (__ldg(mask + i - 1) >> 63) : 0ull, next = i + 1 < n_words ? (__ldg(mask + i + 1) & 1ull) : 0ull;
+    uint64_t st = m & ~((m << 1) | prev), en = m & ~((m >> 1) | (next << 63));
+    int64_t ks = incl_starts[i] - __popcll(st), ke = incl_ends[i] - __popcll(en);
+    for (; st; st &= st - 1, ++ks)
+      if (ks < capacity) out_pairs[2 * ks] = (uint64_t)(i << 6) + (uint64_t)(__ffsll((long long)st) - 1);
+    for (; en; en &= en - 1, ++ke)
+      if (ke < capacity) out_pairs[2 * ke + 1] = (uint64_t)(i << 6) + (uint64_t)__ffsll((long long)en);
+  }
+}
+
+extern "C" acu_status acu_filter_plan_slices(acu_ctx *ctx, const acu_filter_plan *plan, uint64_t *out_pairs, int64_t capacity,
+                                             int64_t *out_slices) {
+  ACU_ENTER(ctx);
+  *out_slices = 0;
+  if (acu_filter_plan_len(plan) == 0 || acu_filter_plan_count(plan) == 0) return ACU_OK;
+  const int64_t n_words = acu_plan_n_words_padded(plan);
+  void *scratch;
+  const size_t one = ((size_t)n_words + (size_t)n_words / 4096 + 64) * 8;
+  ACU_TRY(acu_scratch(ctx, 3 * one, &scratch));
+  int64_t *ns = static_cast<int64_t *>(scratch), *ne = ns + one / 8, *tmp = ne + one / 8;
+  const int grid = acu_grid(ctx, (n_words + 255) / 256, 8);
+  ACU_LAUNCH(ctx, k_plan_slice_counts, grid, 256, 0, acu_plan_mask(plan), n_words, ns, ne);
+  ACU_TRY(scan_inclusive(ctx, ns, n_words, tmp));
+  ACU_TRY(scan_inclusive(ctx, ne, n_words, tmp));
+  int64_t total = 0;
+  ACU_CUDA(ctx, cudaMemcpyAsync(&total, ns + (n_words - 1), 8, cudaMemcpyDeviceToHost, ctx->stream));
+  ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *out_slices = total;
+  if (out_pairs == nullptr || total == 0) return ACU_OK;  // sizing call
+  if (capacity < total)
+    return acu_fail(ctx, ACU_ERR_INVALID_ARGUMENT, -1, 0, 0, (uint64_t)total, "filter_plan_slices: capacity %lld < %lld slices", (long long)capacity,
+                    (long long)total);
+  ACU_LAUNCH_TIMED(ctx, ACU_K_FILTER_PLAN, k_plan_slices_emit, grid, 256, 0, acu_plan_mask(plan), n_words, ns, ne, capacity, out_pairs);
+  ACU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  acu_kstats_drain(ctx);
+  return ACU_OK;
+}
+
 // The selected row ids of a plan (the reference's IterationStrategy::Indices, filter.rs:285-298), materialised once per
 // plan and shared by every variable-width column filtered with it: UInt32 when the predicate is short enough, else UInt64.
 acu_status acu_plan_cached_indices(acu_ctx *ctx, const acu_filter_plan *plan, const void **out_idx, int *out_kind) {

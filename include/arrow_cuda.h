@@ -238,6 +238,12 @@ void acu_filter_plan_destroy(acu_ctx *ctx, acu_filter_plan *plan);
  * selected row ids in ascending order, as index_dtype ACU_U32 or ACU_U64 (count entries). */
 acu_status acu_filter_plan_indices(acu_ctx *ctx, const acu_filter_plan *plan, acu_dtype index_dtype,
                                    void *out_indices);
+/* FilterBuilder::optimize for dense predicates: IterationStrategy::Slices(Vec<(usize, usize)>) = SlicesIterator
+ * (filter.rs:44-77, :285-298): the runs of selected rows as [start, end) pairs in ascending order, out_pairs[2k] = start,
+ * out_pairs[2k + 1] = end of run k. *out_slices = number of runs; out_pairs == NULL sizes only. Null predicate slots select
+ * nothing (the plan's mask is prep_null_mask_filter'ed). */
+acu_status acu_filter_plan_slices(acu_ctx *ctx, const acu_filter_plan *plan, uint64_t *out_pairs, int64_t capacity,
+                                  int64_t *out_slices);
 int64_t acu_filter_plan_count(const acu_filter_plan *plan);      /* FilterPredicate::count */
 int64_t acu_filter_plan_len(const acu_filter_plan *plan);        /* predicate length       */
 int32_t acu_filter_plan_strategy(const acu_filter_plan *plan);   /* acu_filter_strategy    */
@@ -320,7 +326,11 @@ acu_status acu_take_bytes(acu_ctx *ctx, int32_t offset_bytes, const void *offset
  * Floats: every op is the IEEE single operation (no FMA contraction), never errors.
  * Integers: wrapping ops via `binary` (op evaluated at every slot), checked ops via
  * `try_binary` (zero under nulls, first failing valid index reported)
- * (arity.rs:104-135, :254-299). Length mismatch => ACU_ERR_COMPUTE. */
+ * (arity.rs:104-135, :254-299). Length mismatch => ACU_ERR_COMPUTE.
+ * In place (binary_mut / try_binary_mut / unary_mut / try_unary_mut, arity.rs:137-252,301-363): out->values may BE a->values
+ * (or b->values), and out->validity an input validity buffer whose bit offset is 0 — every element / bitmap word is read
+ * before the same element / word is written. A failed checked op leaves the buffer partially overwritten (the reference's
+ * try_binary_mut consumes its input as well). */
 acu_status acu_arith(acu_ctx *ctx, acu_dtype dtype, acu_arith_op op, const acu_array *a,
                      const acu_array *b, acu_array_out *out);
 /* neg (checked != 0) / neg_wrapping (numeric.rs:103-186). */

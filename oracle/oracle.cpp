@@ -1702,4 +1702,28 @@ void orc_view_rebase(const uint8_t *views, int64_t n, uint32_t delta, uint8_t *o
   }
 }
 
+
+// SlicesIterator over prep_null_mask_filter(predicate) (arrow-select/src/filter.rs:44-77,167-171; BitSliceIterator,
+// arrow-buffer/src/util/bit_iterator.rs): [start, end) of every maximal run of rows with value && valid. Returns the run count;
+// pairs beyond `capacity` are not written.
+int64_t orc_filter_slices(const acu_array *pred, uint64_t *out_pairs, int64_t capacity) {
+  const uint8_t *vals = static_cast<const uint8_t *>(pred->values);
+  int64_t n_slices = 0, start = -1;
+  for (int64_t i = 0; i < pred->len; ++i) {
+    bool set = get_bit(vals, pred->values_offset + i);
+    if (set && pred->validity) set = get_bit(pred->validity, pred->validity_offset + i);
+    if (set && start < 0) start = i;
+    if (!set && start >= 0) {
+      if (n_slices < capacity) { out_pairs[2 * n_slices] = (uint64_t)start; out_pairs[2 * n_slices + 1] = (uint64_t)i; }
+      ++n_slices;
+      start = -1;
+    }
+  }
+  if (start >= 0) {
+    if (n_slices < capacity) { out_pairs[2 * n_slices] = (uint64_t)start; out_pairs[2 * n_slices + 1] = (uint64_t)pred->len; }
+    ++n_slices;
+  }
+  return n_slices;
+}
+
 }  // extern "C"

@@ -208,6 +208,7 @@ extern "C" {
     pub fn acu_ipc_stream_next(ctx: *mut acu_ctx, s: *mut acu_ipc_stream, out_columns: *mut acu_column, out_rows: *mut i64) -> acu_status;
     pub fn acu_ipc_stream_close(ctx: *mut acu_ctx, s: *mut acu_ipc_stream);
     pub fn acu_aggregate_allreduce(ctx: *mut acu_ctx, dtype: i32, op: i32, a: *const acu_array, out_bits: *mut u64, out_valid: *mut i64) -> acu_status;
+    pub fn acu_filter_plan_slices(ctx: *mut acu_ctx, plan: *const acu_filter_plan, out_pairs: *mut u64, capacity: i64, out_slices: *mut i64) -> acu_status;
     // stream-ordered sections (include/arrow_cuda.h): the entry points listed there only enqueue between the two calls
     pub fn acu_async_begin(ctx: *mut acu_ctx) -> acu_status;
     pub fn acu_results_fetch(ctx: *mut acu_ctx) -> acu_status;

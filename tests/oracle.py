@@ -107,6 +107,16 @@ class Oracle:
             self.check(self.lib.orc_filter_primitive(C.byref(pd), values.width(), C.byref(vd), C.byref(out), C.byref(cnt), C.byref(strat)))
         return self._result(out, vals, valid, values.dtype)
 
+    def filter_slices(self, predicate):
+        """SlicesIterator::new(&prep_null_mask_filter(predicate)).collect() -> [(start, end)]."""
+        self.lib.orc_filter_slices.restype = i64
+        self.lib.orc_filter_slices.argtypes = [P(abi.Array), vp, i64]
+        pd = acu.host_descriptor(predicate)
+        cap = predicate.length // 2 + 2
+        out = np.zeros(2 * cap, dtype=np.uint64)
+        n = self.lib.orc_filter_slices(C.byref(pd), out.ctypes.data, cap)
+        return [(int(out[2 * k]), int(out[2 * k + 1])) for k in range(n)]
+
     def filter_plan(self, predicate):
         out, vals, valid = self._out(predicate.length, predicate.length)
         dummy = HostArray(acu.U8, np.zeros(predicate.length + 1, np.uint8), predicate.length)

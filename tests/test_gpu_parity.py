@@ -8,6 +8,8 @@ compared bit-for-bit except that any NaN matches any NaN (tolerance stated by no
 1 ulp; we hold 0 ulp on non-NaN results). Float `sum` is tolerance-based (order-dependent in
 the reference itself, arrow-arith/src/aggregate.rs:303-313).
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -449,6 +451,30 @@ def test_byte_view_filter_take(gpu, oracle):
     dp.free()
     for p in owned:
         gpu.free(p)
+
+
+def test_arith_in_place(gpu, oracle):
+    """binary_mut / unary_mut (arrow-arith/src/arity.rs:137-252,301-363): the output aliases the first operand's buffers."""
+    rng = np.random.default_rng(99)
+    for dtype in (abi.I64, abi.F64, abi.I32):
+        for n in (1, 64, 4097, 70001):
+            a, b = rand_array(rng, dtype, n, 0.1, 0), rand_array(rng, dtype, n, 0.05, 0)
+            exp = oracle.arith(acu.MUL_WRAPPING, a, b)
+            da, db = gpu.upload(a), gpu.upload(b)
+            ad, bd = da.descriptor(), db.descriptor()
+            out = abi.ArrayOut()
+            out.values = ad.values
+            aliased_validity = ad.validity_offset == 0
+            out.validity = ad.validity if aliased_validity else gpu.malloc(acu.bitmap_bytes(n) + 8)
+            gpu.check(gpu.lib.acu_arith(gpu.h, dtype, acu.MUL_WRAPPING, C.byref(ad), C.byref(bd), C.byref(out)))
+            vals = gpu.d2h(out.values, n * abi.DTYPE_SIZE[dtype], acu.NP_DTYPES[dtype])
+            validity = gpu.d2h(out.validity, acu.bitmap_bytes(n)) if out.has_validity else None
+            got = HostArray(dtype, vals, n, validity, 0, 0, out.null_count if out.has_validity else 0)
+            assert_same(got, exp, f"in-place mul dtype={dtype} n={n}", float_nan_ok=True)
+            if not aliased_validity:
+                gpu.free(out.validity)
+            da.free()
+            db.free()
 
 
 # ---- numeric -------------------------------------------------------------------------------
