@@ -523,6 +523,22 @@ class FilterPredicate {
   FilterPredicate() = default;
   explicit FilterPredicate(acu_filter_plan *p) : plan_(p, [](acu_filter_plan *q) { acu_filter_plan_destroy(Context::get().raw(), q); }) {}
   int64_t count() const { return acu_filter_plan_count(plan_.get()); }
+  // IterationStrategy::Slices of FilterBuilder::optimize = SlicesIterator::new(&filter).collect() (filter.rs:44-77,285-298):
+  // the runs of selected rows as [start, end), computed on the device
+  Result<std::vector<std::pair<size_t, size_t>>> slices() const {
+    Context &c = Context::get();
+    int64_t n = 0;
+    acu_status st = acu_filter_plan_slices(c.raw(), plan_.get(), nullptr, 0, &n);
+    if (st != ACU_OK) return c.last_error(st);
+    std::vector<std::pair<size_t, size_t>> out((size_t)n);
+    if (n == 0) return out;
+    Buffer pairs = Buffer::allocate((size_t)n * 16);
+    if ((st = acu_filter_plan_slices(c.raw(), plan_.get(), static_cast<uint64_t *>(pairs.data()), n, &n)) != ACU_OK) return c.last_error(st);
+    std::vector<uint64_t> host((size_t)n * 2);
+    pairs.to_host(host.data(), host.size() * 8);
+    for (int64_t k = 0; k < n; ++k) out[(size_t)k] = {(size_t)host[2 * k], (size_t)host[2 * k + 1]};
+    return out;
+  }
   Result<ArrayRef> filter(const Array &values) const {
     Context &c = Context::get();
     const int64_t n = count();

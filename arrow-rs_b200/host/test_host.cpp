@@ -656,6 +656,21 @@ static void test_string_view_coalesce() {
   }
 }
 
+// arrow-select/src/filter.rs:1640-1678 test_slice_iterator_bits / _bits1 / _chunk_and_bits
+static void test_slice_iterator() {
+  using P = std::vector<std::pair<size_t, size_t>>;
+  auto bools = [](size_t n, std::function<bool(size_t)> f) {
+    std::vector<O<bool>> v;
+    for (size_t i = 0; i < n; ++i) v.push_back(f(i));
+    return BooleanArray::from(v);
+  };
+  CHECK((FilterBuilder(bools(64, [](size_t i) { return i == 1; })).build().slices().unwrap() == P{{1, 2}}));
+  CHECK((FilterBuilder(bools(64, [](size_t i) { return i != 1; })).build().slices().unwrap() == P{{0, 1}, {2, 64}}));
+  auto pred = FilterBuilder(bools(130, [](size_t i) { return i % 62 != 0; })).build();
+  CHECK((pred.slices().unwrap() == P{{1, 62}, {63, 124}, {125, 130}}));
+  CHECK_EQ(61 + 61 + 5, pred.count());
+}
+
 int main() {
   try {
     Context::get(0);
@@ -695,6 +710,7 @@ int main() {
       {"row_filter", test_row_filter},
       {"ipc_stream_reader", test_ipc_stream_reader},
       {"string_view_coalesce", test_string_view_coalesce},
+      {"slice_iterator", test_slice_iterator},
   };
   for (auto &t : tests) {
     int before = g_failed;
