@@ -905,13 +905,54 @@ def pyarrow_secondary(orc, n):
         return {"impl": "pyarrow", "skipped": repr(e)[:120]}
 
 
+def cpu_pin_order():
+    """Allowed CPUs ordered for pinning: one hyperthread of every physical core first, alternating between the NUMA nodes /
+    packages, then the sibling hyperthreads in the same order — so that ANY thread count spreads over all memory controllers."""
+    allowed = sorted(os.sched_getaffinity(0))
+    try:
+        info = {}
+        for c in allowed:
+            base = f"/sys/devices/system/cpu/cpu{c}/topology/"
+            pkg = int(open(base + "physical_package_id").read())
+            sib = open(base + "thread_siblings_list").read().strip().replace("-", ",").split(",")
+            info[c] = (pkg, min(int(x) for x in sib))
+        primaries = [c for c in allowed if info[c][1] == c or info[c][1] not in allowed]
+        seconds = [c for c in allowed if c not in primaries]
+
+        def interleave(cs):
+            by_pkg = {}
+            for c in cs:
+                by_pkg.setdefault(info[c][0], []).append(c)
+            out, lists = [], [by_pkg[k] for k in sorted(by_pkg)]
+            for i in range(max((len(x) for x in lists), default=0)):
+                out += [x[i] for x in lists if i < len(x)]
+            return out
+        return interleave(primaries) + interleave(seconds)
+    except Exception:
+        return allowed
+
+
 def cpu_reference(args, steps, warmup, secondary=True, one_thread=True):
     """Run the native reference harness: `warmup` untimed + `steps` timed passes of the hot-path step over
     reference_rows(args) rows. Returns (cpu_baseline dict, per-step seconds, checksums of the outputs)."""
     from oracle import Oracle, RefBench
     orc = Oracle()
     n, why = reference_rows(args)
-    with RefBench(n, SEEDS7, SELECTIVITY, NULL_DENSITY, threads=args.cpu_threads or 0, oracle=orc) as rb:
+    os.environ.setdefault("ORC_BENCH_CPU_ORDER", ",".join(str(c) for c in cpu_pin_order()))
+    calib = None
+    threads_req = args.cpu_threads or 0
+    if not threads_req and n >= 200_000_000:
+        # "all the host threads it can use" is not always the fastest way to run a memory-bound step: on the round-2 GPU box a
+        # plain Float64 add reaches 132 GB/s on 16 threads, 118 on 64 and 64 on all 128 hyperthreads (tools/experiments/membw.c).
+        # The arm therefore measures a 1e8-row sample at a few thread counts and runs the full table with the best one.
+        ncpu = len(os.sched_getaffinity(0))
+        calib = {}
+        for t in sorted({ncpu, max(ncpu // 2, 1), max(ncpu // 4, 1), max(ncpu // 8, 1)}):
+            with RefBench(100_000_000, SEEDS7, SELECTIVITY, NULL_DENSITY, threads=t, oracle=orc) as rbc:
+                rbc.step()
+                calib[t] = 100_000_000 / min(rbc.step()[0] for _ in range(2)) / 1e6
+        threads_req = max(calib, key=calib.get)
+    with RefBench(n, SEEDS7, SELECTIVITY, NULL_DENSITY, threads=threads_req, oracle=orc) as rb:
         for _ in range(max(warmup, 1)):
             rb.step()
         runs = [rb.step() for _ in range(max(steps, 1))]
@@ -925,7 +966,9 @@ def cpu_reference(args, steps, warmup, secondary=True, one_thread=True):
                        f"; same step (filter+take+add+sum) row-partitioned over {threads} pinned native threads (oracle/refbench.cpp: each thread first-touches "
                        "its own range, outputs pre-allocated, timer inside C); oracle/ C++ restatement of arrow-rs (no Rust toolchain here)"),
             "rows": n, "same_config": n == args.rows, "host_cores": os.cpu_count() or 1, "seconds_median": med, "seconds_min": best,
-            "value_best": n / best / 1e6, "spread": (max(secs) - best) / med if med else None, "timed_steps": len(secs), "generate_seconds": gen_s}
+            "value_best": n / best / 1e6, "spread": (max(secs) - best) / med if med else None, "timed_steps": len(secs), "generate_seconds": gen_s,
+            "thread_calibration_mrows_s": {str(k): round(v, 1) for k, v in calib.items()} if calib else None,
+            "pinning": "physical cores first, alternating NUMA nodes (ORC_BENCH_CPU_ORDER)"}
     if one_thread and threads > 1:  # arrow-rs kernels themselves are single-threaded: ONE call per op over a 1e8-row sample
         n1 = min(n, 100_000_000)
         with RefBench(n1, SEEDS7, SELECTIVITY, NULL_DENSITY, threads=1, oracle=orc) as rb1:

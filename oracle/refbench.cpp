@@ -255,7 +255,23 @@ acu_status orc_bench_create(int64_t rows, int64_t first_row, int32_t threads, co
   if ((int64_t)threads > (rows + 63) / 64) threads = (int)((rows + 63) / 64);
   if (threads < 1) threads = 1;
   rb->threads = threads;
-  if (pin) rb->cpus = allowed;
+  if (pin) {
+    rb->cpus = allowed;
+    // ORC_BENCH_CPU_ORDER="0,32,1,33,...": the order in which threads are pinned (bench.py passes physical cores first,
+    // alternating between the NUMA nodes, so that any thread count spreads over both sockets' memory controllers)
+    if (const char *order = getenv("ORC_BENCH_CPU_ORDER")) {
+      std::vector<int> ordered;
+      for (const char *q = order; *q;) {
+        char *end = nullptr;
+        const long c = strtol(q, &end, 10);
+        if (end == q) break;
+        for (int a : allowed)
+          if (a == (int)c) { ordered.push_back((int)c); break; }
+        q = *end == ',' ? end + 1 : end;
+      }
+      if (!ordered.empty()) rb->cpus = ordered;
+    }
+  }
   // contiguous ranges aligned to 64 rows (bitmaps split on u64 words)
   const int64_t per = (((rows + threads - 1) / threads) + 63) / 64 * 64;
   rb->parts.resize(threads);
